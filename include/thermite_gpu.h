@@ -1,0 +1,209 @@
+/* thermite_gpu.h -- C ABI of libthermite_gpu.so: the B200 (sm_100a) replacement for the read-alignment hot
+ * path of 10XGenomics/thermite.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference):
+ *   tg_index_host_create_*   Index::create_from_files              src/index.rs:52-223
+ *   tg_index_host_save/load  bincode .tai (de)serialisation        src/main.rs:37-43, 63-67; src/wrapper.rs:31-37
+ *   tg_index_host_* getters  Index::refs() / Index::txome()        src/index.rs:293-300 (used by src/aln_writer.rs:179-213,257)
+ *   tg_index_create*         (new) upload / adopt the flat index in HBM; one replica per GPU
+ *   tg_ctx_create            AlignOpts + per-read SwgExtend scratch  src/aligner.rs:452-464, :140-141
+ *   tg_align_batch           align_read, batched                   src/aligner.rs:123-190 (+ :198-449, src/swg.rs, src/txome.rs:82-160,
+ *                                                                   Index::all_smems src/index.rs:228-255)
+ *   tg_seed_batch            Index::all_smems, batched             src/index.rs:228-255
+ *   tg_swg_extend_batch      SwgExtend::extend, batched            src/swg.rs:31-207
+ *   tg_format_paf / _sam     PafEntry / aln_to_sam_record          src/aln_writer.rs:47-116, 118-253 ; src/aligner.rs:54-115
+ *
+ * Every function returns tg_status (0 = ok, < 0 = error); tg_last_error() gives the thread-local message.
+ * Nothing throws or aborts across the ABI.  There is no CPU fallback: without a CUDA device every device
+ * entry point fails with TG_ERR_CUDA.
+ *
+ * Threading: a tg_index is immutable and may be shared by any number of contexts/threads.  A tg_ctx owns a
+ * CUDA stream plus scratch and is NOT thread-safe: use one per host thread / per GPU (the reference's
+ * ThermiteAligner is Clone + Send with an Arc<Index>, src/wrapper.rs:20-27).
+ */
+#ifndef THERMITE_GPU_H
+#define THERMITE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t tg_status;
+enum {
+  TG_OK = 0,
+  TG_ERR_INVALID = -1,   /* bad argument (null pointer, read too long, x_drop < band width, ...) */
+  TG_ERR_IO = -2,        /* file could not be read / parsed */
+  TG_ERR_CUDA = -3,      /* CUDA runtime error or no device */
+  TG_ERR_CAPACITY = -4,  /* a documented fixed limit was exceeded (see TG_MAX_*) */
+  TG_ERR_INTERNAL = -5
+};
+
+#define TG_MAX_READ_LEN 512u        /* longest read accepted by tg_align_batch / tg_seed_batch */
+#define TG_MAX_SEED_LEN 32u         /* largest min_seed_len (k-mer table key is k 4-bit symbols) */
+#define TG_MAX_ALNS_PER_READ 256u   /* accepted alignments kept per read before the final filters */
+
+const char* tg_last_error(void);
+/* Library / build identification: "thermite_gpu <ver> sm_100a". */
+const char* tg_version(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Alignment operations: one u32 word = kind | (run << 3).
+ *   kind 0 Match, 1 Subst, 2 Del, 3 Ins : run = number of consecutive unit operations of that kind
+ *   kind 4 Xclip (soft clip), 5 Yclip (intron): run = clip length; every clip is its own word
+ * Expanding the words in order gives bio::alignment::Alignment::operations one for one.
+ * ------------------------------------------------------------------------------------------------- */
+enum { TG_OP_MATCH = 0, TG_OP_SUBST = 1, TG_OP_DEL = 2, TG_OP_INS = 3, TG_OP_XCLIP = 4, TG_OP_YCLIP = 5 };
+enum { TG_ALN_EXONIC = 0, TG_ALN_INTRONIC = 1, TG_ALN_INTERGENIC = 2 };
+
+/* GenomeAlignment (src/txome.rs:55-69) as a flat record. */
+typedef struct tg_aln {
+  uint64_t ystart, yend, ylen;            /* gx_aln: chromosome coordinates, forward-strand orientation; ylen = chromosome length */
+  uint64_t tx_ystart, tx_yend, tx_ylen;   /* Exonic only: tx_aln in transcript coordinates; tx_ylen = transcript length */
+  int32_t score;                          /* gx_aln.score */
+  uint32_t ref_id;                        /* index into refs() of the hit's Ref => ref_name and strand */
+  uint32_t xstart, xend, xlen;            /* read coordinates; xlen = read length */
+  uint32_t tx_or_gene_idx;                /* Exonic: tx_idx; Intronic: gene_idx; Intergenic: 0xFFFFFFFF */
+  int32_t tx_score;                       /* Exonic only */
+  uint32_t tx_xstart, tx_xend;            /* Exonic only */
+  uint32_t ops_off, ops_len;              /* gx_aln.operations: words [ops_off, ops_off+ops_len) of tg_result.ops */
+  uint32_t tx_ops_off, tx_ops_len;        /* Exonic only: tx_aln.operations */
+  uint8_t aln_type;                       /* TG_ALN_* */
+  uint8_t primary;
+  uint8_t strand;                         /* 1 = forward */
+  uint8_t pad;
+} tg_aln;
+
+/* AlignOpts (src/aligner.rs:452-464); tg_opts_default() gives src/main.rs:115-132 / src/wrapper.rs:40-46. */
+typedef struct tg_opts {
+  uint32_t min_seed_len;          /* -k, default 20 */
+  float min_aln_score_percent;    /* -s, default 0.66 */
+  int32_t min_aln_score;          /* --min-aln-score, default 30 */
+  uint32_t multimap_score_range;  /* --multimap-score-range, default 1 */
+  uint32_t intron_mode;           /* --intron-mode, default 0 */
+} tg_opts;
+void tg_opts_default(tg_opts* out);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Host-side flat index
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tg_index_host tg_index_host;
+
+/* FASTA (+ GTF) -> concatenated both-strand text, suffix array, flattened transcriptome.  The .fai the
+ * reference needs next to the FASTA is not required. */
+tg_status tg_index_host_create_from_files(const char* fasta_path, const char* gtf_path, tg_index_host** out);
+tg_status tg_index_host_create_from_memory(const char* fasta_text, size_t fasta_len, const char* gtf_text,
+                                           size_t gtf_len, tg_index_host** out);
+/* One contiguous, position-independent blob (what is saved to disk, uploaded, or broadcast over NCCL). */
+tg_status tg_index_host_blob(const tg_index_host* ix, const void** data, size_t* nbytes);
+tg_status tg_index_host_from_blob(const void* data, size_t nbytes, tg_index_host** out);
+tg_status tg_index_host_save(const tg_index_host* ix, const char* path);
+tg_status tg_index_host_load(const char* path, tg_index_host** out);
+void tg_index_host_destroy(tg_index_host* ix);
+
+/* refs() / txome() accessors for the writers.  Returned strings live as long as the index. */
+uint64_t tg_index_host_text_len(const tg_index_host* ix);
+uint32_t tg_index_host_n_refs(const tg_index_host* ix);
+uint32_t tg_index_host_n_txs(const tg_index_host* ix);
+uint32_t tg_index_host_n_genes(const tg_index_host* ix);
+/* out4 = { start_idx, end_idx, len, strand } */
+const char* tg_index_host_ref(const tg_index_host* ix, uint32_t i, uint64_t* out4);
+/* out4 = { gene_idx, strand, n_exons, seq_len } ; returns transcript id */
+const char* tg_index_host_tx(const tg_index_host* ix, uint32_t i, uint64_t* out4);
+const char* tg_index_host_gene_id(const tg_index_host* ix, uint32_t i);
+const char* tg_index_host_gene_name(const tg_index_host* ix, uint32_t i);
+/* Suffix array (text_len u32 entries) -- exposed so callers can expand tg_seed records into Mems. */
+const uint32_t* tg_index_host_sa(const tg_index_host* ix);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Device index (HBM-resident replica)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tg_index tg_index;
+tg_status tg_index_create(const tg_index_host* ix, int device, tg_index** out);
+/* Adopt a blob that already sits in device memory (e.g. after an NCCL broadcast).  The memory stays owned
+ * by the caller and must outlive the index. */
+tg_status tg_index_create_from_device_blob(const void* device_blob, size_t nbytes, int device, tg_index** out);
+void tg_index_destroy(tg_index* ix);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Alignment context: options, stream, k-mer table for opts.min_seed_len, scratch.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tg_ctx tg_ctx;
+tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out);
+void tg_ctx_destroy(tg_ctx* ctx);
+/* The CUDA stream (cudaStream_t) all of the context's work is enqueued on. */
+void* tg_ctx_stream(tg_ctx* ctx);
+/* Device time (CUDA events on the context's stream) of the seeding and extension kernels of the last
+ * tg_align_batch* / tg_seed_batch call, in milliseconds. */
+void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms);
+/* Size of the context's k-mer table in bytes. */
+uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx);
+
+typedef struct tg_result {
+  uint32_t n_reads;
+  uint64_t n_alns, n_ops;
+  const uint64_t* read_aln_first; /* [n_reads] index of the read's first record in alns */
+  const uint32_t* read_aln_count; /* [n_reads] number of records (0 = unmapped); records are in output order */
+  const tg_aln* alns;             /* [n_alns] */
+  const uint32_t* ops;            /* [n_ops] */
+  /* work counters of this batch */
+  uint64_t swg_cells;             /* DP cells as the reference's loops visit them (src/swg.rs:80,119) */
+  uint64_t swg_extensions;        /* non-trivial SwgExtend::extend calls */
+  uint64_t seed_hits;             /* Mems handed to align_seed_hit */
+  uint64_t n_smems;
+} tg_result;
+
+/* align_read for n_reads reads.  `bases` = concatenated ASCII reads (any case), read r = bases[offs[r], offs[r+1]).
+ * HOST buffers in, HOST result out (owned by ctx, valid until the next call on ctx or tg_ctx_destroy).
+ * The call does H2D, all kernels, D2H, and synchronises the context's stream. */
+tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_result* out);
+/* Same, but inputs are DEVICE pointers and the result pointers are DEVICE pointers (counters and n_* are
+ * still filled on the host after a stream sync). */
+tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n_reads,
+                                uint64_t total_bases, uint32_t max_read_len, tg_result* out);
+
+/* Seeding only: the SMEMs of every read in the order Index::all_smems returns them, one record per SMEM:
+ * occurrences are suffix-array rows [sa_lo, sa_lo+count) visited from the LAST row to the first; when
+ * `direct` is set the single occurrence position is sa_lo itself. */
+typedef struct tg_seed {
+  uint32_t query_idx, len, sa_lo, count;
+  uint32_t direct, pad;
+} tg_seed;
+typedef struct tg_seed_result {
+  uint32_t n_reads;
+  uint64_t n_seeds;
+  const uint64_t* read_seed_first; /* [n_reads] */
+  const uint32_t* read_seed_count; /* [n_reads] */
+  const tg_seed* seeds;
+} tg_seed_result;
+tg_status tg_seed_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_seed_result* out);
+
+/* SwgExtend::extend for n independent (x, y) pairs with unit scoring (gap_open -1, gap_extend -1, match +1,
+ * mismatch -1; src/aligner.rs:140).  Bytes are compared as given.  Requires x_drop[t] >= band_width[t] (with a
+ * smaller x_drop the reference reads stale columns or panics; see DESIGN.md "Q4").  HOST buffers in/out.
+ * ops_off has n+1 entries; task t's words are ops[ops_off[t], ops_off[t+1]).  *cells = DP cells visited. */
+tg_status tg_swg_extend_batch(tg_ctx* ctx, const uint8_t* xs, const uint64_t* xoff, const uint8_t* ys,
+                              const uint64_t* yoff, uint32_t n, const uint32_t* band_width, const int32_t* x_drop,
+                              int32_t* score, uint32_t* xend, uint32_t* yend, uint64_t* ops_off, uint32_t* ops,
+                              uint64_t ops_cap, uint64_t* cells, float* kernel_ms);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Writers: text identical to the reference's PAF / SAM output for the records of one batch.
+ * names/quals: concatenated with n+1 offsets (like bases).  The returned buffer is malloc'ed; free with tg_free.
+ * ------------------------------------------------------------------------------------------------- */
+tg_status tg_format_sam_header(const tg_index_host* ix, char** out, size_t* out_len);
+tg_status tg_format_batch(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
+                          const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals,
+                          const uint64_t* qual_offs, int sam, char** out, size_t* out_len);
+/* FASTQ text -> concatenated bases / names / quals with offsets (needletail::parse_fastx_file, src/aligner.rs:51-55).
+ * All six outputs are malloc'ed; free each with tg_free. */
+tg_status tg_parse_fastq(const char* text, size_t len, uint32_t* n_reads, uint8_t** bases, uint64_t** offs,
+                         uint8_t** names, uint64_t** name_offs, uint8_t** quals, uint64_t** qual_offs);
+void tg_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THERMITE_GPU_H */

@@ -727,7 +727,10 @@ Index Index::create(const std::vector<FastaRecord>& fasta, const std::string& gt
     size_t gene_idx = gene_by_id.at(tx.gene_id);
     const Ref& fwd = ix.refs[chrom_fwd.at(tx.chrom)];
     std::vector<uint8_t> tx_seq;  // tx.get_sequence: exon slices, reverse-complemented for '-'
-    for (auto& e : tx.exons) tx_seq.insert(tx_seq.end(), fwd.seq.begin() + e.first, fwd.seq.begin() + e.second);
+    for (auto& e : tx.exons) {
+      if (e.second > fwd.seq.size() || e.first >= e.second) throw std::runtime_error("exon outside its sequence: " + tx.id);
+      tx_seq.insert(tx_seq.end(), fwd.seq.begin() + e.first, fwd.seq.begin() + e.second);
+    }
     if (!tx.forward) tx_seq = revcomp(tx_seq.data(), tx_seq.size());
     for (auto& c : tx_seq) c = upper(c);
     bool strand = tx.forward;

@@ -1,0 +1,157 @@
+"""Parity of the CUDA path (through the C ABI of libthermite_gpu.so) against the CPU oracle.
+Everything here needs a B200: run with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import ht
+from common import golden, reads_to_batch, small_world, swg_pairs
+from oracle import orc
+from thermite_b200 import AlignOpts, Aligner, Index, parse_fastq, sam_header, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(gpu_res, orc_res, n):
+    d = ht.compare_alignments(dict(first=gpu_res.first, count=gpu_res.count, alns=gpu_res.alns, ops=gpu_res.ops),
+                              orc_res, n)
+    assert not d, d[:5]
+
+
+def test_test_dataset_paf_sam_text():
+    """config 1: data/test_query.fastq vs data/test_ref.fasta + .gtf, flags -k3 --min-aln-score=0 (data/Makefile:21)."""
+    fa, gtf, fq = golden("test_ref.fasta"), golden("test_ref.gtf"), golden("test_query.fastq")
+    oix = orc.Index.create(fa, gtf)
+    ix = Index.create_from_memory(fa, gtf)
+    al = Aligner(ix, AlignOpts(min_seed_len=3, min_aln_score=0))
+    bases, offs, names, name_offs, quals, qual_offs = parse_fastq(fq)
+    res = al.align_reads_raw(bases.ctypes.data, offs.ctypes.data, len(offs) - 1)
+    paf = al.format_result_raw(res, bases, offs, names, name_offs, quals, qual_offs, sam=False)
+    assert paf == oix.align_fastq_text(fq, k=3, min_score=0, sam=False)
+    assert paf == golden("test_query.paf")
+    sam = sam_header(ix) + al.format_result_raw(res, bases, offs, names, name_offs, quals, qual_offs, sam=True)
+    assert sam == oix.align_fastq_text(fq, k=3, min_score=0, sam=True)
+    assert sam == golden("test_query.sam")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_worlds_records_and_seeds(seed):
+    contigs, gtf, txs, fa = small_world(seed)
+    rng = np.random.default_rng(seed + 100)
+    L = int(rng.choice([40, 60, 91, 91, 120]))
+    k = int(rng.choice([12, 16, 20, 20, 25]))
+    pct = float(rng.choice([0.0, 0.5, 0.66]))
+    mins = int(rng.choice([0, 20, 30]))
+    intron = bool(rng.integers(0, 2))
+    srange = int(rng.choice([0, 1, 1, 3]))
+    n = 600
+    bases, offs = synth.make_reads(seed + 5, contigs, txs, n, L=L, sub=0.02, ins=0.003, dele=0.003, polya_frac=0.15,
+                                   polya_len=(10, 35))
+    oix = orc.Index.create(fa, gtf)
+    ix = Index.create_from_memory(fa, gtf)
+    assert (oix.sa() == ix.suffix_array()).all()
+    al = Aligner(ix, AlignOpts(k, pct, mins, srange, intron))
+    # seeds == Index::all_smems
+    seeds, first, count = al.seed_reads(bases, offs)
+    sa = ix.suffix_array()
+    for r in range(0, n, 7):
+        rd = bases[int(offs[r]): int(offs[r + 1])].tobytes()
+        assert ht.expand_seeds(seeds, first, count, sa, r) == oix.all_smems(rd, k), (seed, r)
+    # records == align_read
+    res = al.align_reads(bases, offs)
+    oix.counters_reset()
+    ores = oix.align_batch(bases, offs, k=k, pct=pct, min_score=mins, score_range=srange, intron_mode=intron)
+    _cmp(res, ores, n)
+    assert res.counters["swg_cells"] == oix.counters()["swg_cells"]
+    assert res.counters["seed_hits"] == oix.counters()["hits"]
+
+
+def test_chrM_synthM_records():
+    """config 2 stand-in at test size: reads simulated from the bundled chrM, flags -k20 -s0 --intron-mode."""
+    fa, gtf = golden("GRCh38-2020-A-chrM.fasta"), golden("GRCh38-2020-A-chrM.gtf")
+    oix = orc.Index.create(fa, gtf)
+    ix = Index.create_from_memory(fa, gtf)
+    g = np.frombuffer(b"".join(fa.split(b"\n")[1:]), np.uint8)
+    txs = []
+    for t in oix.txs():
+        pass
+    # transcripts for read simulation straight from the GTF (single-exon genes on chrM)
+    for ln in gtf.decode().splitlines():
+        f = ln.split("\t")
+        if len(f) > 8 and f[2] == "exon":
+            txs.append(dict(id="x", strand=f[6], exons=[(int(f[3]) - 1, int(f[4]))], chrom="chrM", gene="g"))
+    n = 4000
+    bases, offs = synth.make_reads(20211, [("chrM", g)], txs, n, L=91)
+    al = Aligner(ix, AlignOpts(20, 0.0, 30, 1, True))
+    res = al.align_reads(bases, offs)
+    ores = oix.align_batch(bases, offs, k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True)
+    _cmp(res, ores, n)
+    assert res.count.sum() > 0.9 * n
+
+
+def test_edge_reads():
+    contigs, gtf, txs, fa = small_world(11)
+    oix = orc.Index.create(fa, gtf)
+    ix = Index.create_from_memory(fa, gtf)
+    g = contigs[0][1]
+    reads = [b"", b"A", b"ACGT", g[100:191].tobytes().lower(), b"N" * 91, g[200:260].tobytes() + b"N" * 31,
+             b"ACGTRYKM" * 11, g[300:391].tobytes()[::-1], bytes(g[400:450]) + b"A" * 41, b"T" * 200,
+             g[500:1000].tobytes()]
+    bases, offs = reads_to_batch(reads)
+    for opts in (AlignOpts(20, 0.66, 30, 1, False), AlignOpts(10, 0.0, 0, 2, True), AlignOpts(5, 0.5, 0, 0, True)):
+        al = Aligner(ix, opts)
+        res = al.align_reads(bases, offs)
+        ores = oix.align_batch(bases, offs, k=opts.min_seed_len, pct=opts.min_aln_score_percent,
+                               min_score=opts.min_aln_score, score_range=opts.multimap_score_range,
+                               intron_mode=opts.intron_mode)
+        _cmp(res, ores, len(reads))
+    # empty batch
+    e = al.align_reads(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(e) == 0
+
+
+def test_swg_batch_matches_oracle():
+    """config 5 at test size: (score, xend, yend, ops) byte-identical to SwgExtend::extend, cells counted alike."""
+    ix = Index.create_from_memory(golden("test_ref.fasta"), golden("test_ref.gtf"))
+    al = Aligner(ix, AlignOpts(min_seed_len=3))
+    for seed, kw in ((1, {}), (2, dict(alphabet=b"AC")), (3, dict(max_x=200, bw_choices=(3, 30, 100)))):
+        xs, xo, ys, yo, bw, xd = swg_pairs(seed, 6000, **kw)
+        a = al.swg_extend_batch(xs, xo, ys, yo, bw, xd)
+        b = orc.swg_extend_batch(xs, xo, ys, yo, bw, xd)
+        for key in ("score", "xend", "yend", "ops_off", "ops"):
+            assert np.array_equal(a[key], b[key]), (seed, key)
+        assert a["cells"] == b["cells"]
+    # reference KATs (src/swg.rs:249-317)
+    kats = [(b"AAAAAAAA", b"AAAAAAAA", 1, 1), (b"AAAAATTT", b"AAAAAAAA", 1, 1), (b"AAATAAAA", b"AAAAAAAA", 1, 1),
+            (b"AAATTTT", b"AAACCTTTT", 2, 3)]
+    xs, xo = reads_to_batch([k[0] for k in kats])
+    ys, yo = reads_to_batch([k[1] for k in kats])
+    a = al.swg_extend_batch(xs, xo, ys, yo, [k[2] for k in kats], [k[3] for k in kats])
+    assert a["score"].tolist() == [8, 5, 6, 4]
+    assert a["xend"].tolist() == [8, 5, 8, 7] and a["yend"].tolist() == [8, 5, 8, 9]
+    # x_drop < band width is refused (the reference panics / reads stale state there)
+    from thermite_b200 import ThermiteError
+    with pytest.raises(ThermiteError):
+        al.swg_extend_batch(xs, xo, ys, yo, [4] * 4, [1] * 4)
+
+
+def test_roundtrip_properties_full_size():
+    """Size-independent properties on a larger batch: every perfect read maps back to where it came from with
+    score L and an all-match CIGAR; alignment spans are consistent with their operations."""
+    contigs, gtf, txs = synth.synth21(scale=0.02)
+    fa = synth.fasta_bytes(contigs)
+    ix = Index.create_from_memory(fa, gtf)
+    al = Aligner(ix, AlignOpts(20, 0.0, 30, 1, True))
+    n, L = 50_000, 91
+    bases, offs = synth.make_reads(7, contigs, txs, n, L=L, sub=0.0, ins=0.0, dele=0.0, polya_frac=0.0, tso_frac=0.0)
+    res = al.align_reads(bases, offs)
+    assert (res.count >= 1).all()
+    prim = res.alns[res.first.astype(np.int64)]
+    assert (prim["score"] == L).all() and (prim["primary"] == 1).all()
+    assert (prim["xstart"] == 0).all() and (prim["xend"] == L).all()
+    # ops consistency for all records
+    for a in res.alns[:: max(1, len(res.alns) // 2000)]:
+        w = res.ops[int(a["ops_off"]): int(a["ops_off"]) + int(a["ops_len"])]
+        kind, run = w & 7, w >> 3
+        yspan = int(run[(kind <= 2) | (kind == 5)].sum())
+        xspan = int(run[(kind <= 1) | (kind == 3)].sum())
+        assert yspan == int(a["yend"] - a["ystart"]) and xspan == int(a["xend"] - a["xstart"])

@@ -1,0 +1,522 @@
+"""Host-side mirror of thermite's aligner API over the C ABI of libthermite_gpu.so (include/thermite_gpu.h).
+
+Names follow the reference crate (paths under /root/reference):
+  Index.create_from_files / refs / txome      src/index.rs:52-57, 293-300
+  AlignOpts                                   src/aligner.rs:452-464 (defaults src/main.rs:115-132)
+  Aligner.align_reads (batched align_read)    src/aligner.rs:123-190
+  GenomeAlignment / AlnType                   src/txome.rs:55-69
+  align_reads_from_file                       src/aligner.rs:22-120
+  OutputFormat                                src/aln_writer.rs:16-21
+
+The CUDA library is the only compute path: importing works without a GPU (so the host-side logic and the
+symbol table can be tested), but every device call raises ThermiteError when the library or a device is
+missing.  Nothing here falls back to a CPU implementation.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(_CSRC, "libthermite_gpu.so")
+_LIB = None
+
+TG_MAX_READ_LEN = 512
+
+ALN_DTYPE = np.dtype([
+    ("ystart", "<u8"), ("yend", "<u8"), ("ylen", "<u8"),
+    ("tx_ystart", "<u8"), ("tx_yend", "<u8"), ("tx_ylen", "<u8"),
+    ("score", "<i4"), ("ref_id", "<u4"),
+    ("xstart", "<u4"), ("xend", "<u4"), ("xlen", "<u4"),
+    ("tx_or_gene_idx", "<u4"), ("tx_score", "<i4"),
+    ("tx_xstart", "<u4"), ("tx_xend", "<u4"),
+    ("ops_off", "<u4"), ("ops_len", "<u4"), ("tx_ops_off", "<u4"), ("tx_ops_len", "<u4"),
+    ("aln_type", "u1"), ("primary", "u1"), ("strand", "u1"), ("pad", "u1"),
+])
+SEED_DTYPE = np.dtype([("query_idx", "<u4"), ("len", "<u4"), ("sa_lo", "<u4"), ("count", "<u4"),
+                       ("direct", "<u4"), ("pad", "<u4")])
+OP_NAMES = ["Match", "Subst", "Del", "Ins", "Xclip", "Yclip"]
+ALN_TYPES = ["Exonic", "Intronic", "Intergenic"]
+
+
+class ThermiteError(RuntimeError):
+    pass
+
+
+class _Opts(C.Structure):
+    _fields_ = [("min_seed_len", C.c_uint32), ("min_aln_score_percent", C.c_float), ("min_aln_score", C.c_int32),
+                ("multimap_score_range", C.c_uint32), ("intron_mode", C.c_uint32)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_alns", C.c_uint64), ("n_ops", C.c_uint64),
+                ("read_aln_first", C.c_void_p), ("read_aln_count", C.c_void_p), ("alns", C.c_void_p),
+                ("ops", C.c_void_p), ("swg_cells", C.c_uint64), ("swg_extensions", C.c_uint64),
+                ("seed_hits", C.c_uint64), ("n_smems", C.c_uint64)]
+
+
+class _SeedResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_seeds", C.c_uint64), ("read_seed_first", C.c_void_p),
+                ("read_seed_count", C.c_void_p), ("seeds", C.c_void_p)]
+
+
+# every symbol include/thermite_gpu.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "tg_last_error", "tg_version", "tg_opts_default",
+    "tg_index_host_create_from_files", "tg_index_host_create_from_memory", "tg_index_host_blob",
+    "tg_index_host_from_blob", "tg_index_host_save", "tg_index_host_load", "tg_index_host_destroy",
+    "tg_index_host_text_len", "tg_index_host_n_refs", "tg_index_host_n_txs", "tg_index_host_n_genes",
+    "tg_index_host_ref", "tg_index_host_tx", "tg_index_host_gene_id", "tg_index_host_gene_name", "tg_index_host_sa",
+    "tg_index_create", "tg_index_create_from_device_blob", "tg_index_destroy",
+    "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_kmer_table_bytes",
+    "tg_align_batch", "tg_align_batch_device", "tg_seed_batch", "tg_swg_extend_batch",
+    "tg_format_sam_header", "tg_format_batch", "tg_parse_fastq", "tg_free",
+]
+
+
+def lib():
+    """Load libthermite_gpu.so (built by __graft_entry__.build() / `make -C thermite_b200/csrc`)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ThermiteError(f"{LIB_PATH} is missing: build it with `make -C thermite_b200/csrc` "
+                                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.tg_last_error.restype = C.c_char_p
+        L.tg_version.restype = C.c_char_p
+        L.tg_index_host_text_len.restype = C.c_uint64
+        for f in ("tg_index_host_ref", "tg_index_host_tx", "tg_index_host_gene_id", "tg_index_host_gene_name"):
+            getattr(L, f).restype = C.c_char_p
+        L.tg_index_host_sa.restype = C.c_void_p
+        L.tg_ctx_stream.restype = C.c_void_p
+        L.tg_ctx_kmer_table_bytes.restype = C.c_uint64
+        L.tg_ctx_last_kernel_ms.restype = None
+        L.tg_free.restype = None
+        _LIB = L
+    return _LIB
+
+
+def _check(st):
+    if st != 0:
+        raise ThermiteError(f"thermite_gpu error {st}: {lib().tg_last_error().decode()}")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def expand_ops(words):
+    """RLE words -> [(kind_name, n)], one entry per bio AlignmentOperation."""
+    out = []
+    for w in np.asarray(words, dtype=np.uint32).tolist():
+        k, n = w & 7, w >> 3
+        if k <= 3:
+            out.extend([(OP_NAMES[k], 1)] * n)
+        else:
+            out.append((OP_NAMES[k], n))
+    return out
+
+
+@dataclass
+class AlignOpts:
+    """src/aligner.rs:452-464; defaults = src/main.rs:115-132."""
+    min_seed_len: int = 20
+    min_aln_score_percent: float = 0.66
+    min_aln_score: int = 30
+    multimap_score_range: int = 1
+    intron_mode: bool = False
+
+    def _c(self):
+        return _Opts(self.min_seed_len, self.min_aln_score_percent, self.min_aln_score, self.multimap_score_range,
+                     int(self.intron_mode))
+
+
+@dataclass
+class Ref:
+    """src/index.rs:391-399 (the sequence itself stays in the packed index)."""
+    name: str
+    strand: bool
+    len: int
+    start_idx: int
+    end_idx: int
+
+
+@dataclass
+class Tx:
+    id: str
+    strand: bool
+    gene_idx: int
+    n_exons: int
+    seq_len: int
+
+
+@dataclass
+class Gene:
+    id: str
+    name: str
+
+
+class Txome:
+    def __init__(self, genes, txs):
+        self.genes, self.txs = genes, txs
+
+
+class Index:
+    """Flat host index + (lazily) its HBM replica.  src/index.rs:40-44."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self._dev = {}
+        self._blob_keepalive = None
+
+    # -- construction ---------------------------------------------------------------------------------------
+    @classmethod
+    def create_from_files(cls, ref_path: str, annot_path: str, sa_sampling_rate: int = 32,
+                          occ_sampling_rate: int = 128) -> "Index":
+        """src/index.rs:52-57.  The sampling rates are accepted for signature parity and ignored: the GPU
+        index keeps the full suffix array and has no Occ table."""
+        h = C.c_void_p()
+        _check(lib().tg_index_host_create_from_files(ref_path.encode(), annot_path.encode(), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def create_from_memory(cls, fasta_text: bytes, gtf_text: bytes) -> "Index":
+        h = C.c_void_p()
+        _check(lib().tg_index_host_create_from_memory(fasta_text, C.c_size_t(len(fasta_text)), gtf_text,
+                                                      C.c_size_t(len(gtf_text)), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_blob(cls, blob: np.ndarray) -> "Index":
+        blob = np.ascontiguousarray(blob, np.uint8)
+        h = C.c_void_p()
+        _check(lib().tg_index_host_from_blob(_p(blob), C.c_size_t(blob.nbytes), C.byref(h)))
+        return cls(h)
+
+    def save(self, path: str):
+        """The `.tai` of this implementation (src/main.rs:37-43)."""
+        _check(lib().tg_index_host_save(self._h, path.encode()))
+
+    @classmethod
+    def load(cls, path: str) -> "Index":
+        h = C.c_void_p()
+        _check(lib().tg_index_host_load(path.encode(), C.byref(h)))
+        return cls(h)
+
+    def blob(self) -> np.ndarray:
+        """Zero-copy view of the position-independent index blob."""
+        d, n = C.c_void_p(), C.c_size_t()
+        _check(lib().tg_index_host_blob(self._h, C.byref(d), C.byref(n)))
+        return np.ctypeslib.as_array(C.cast(d, C.POINTER(C.c_uint8)), shape=(n.value,))
+
+    def __del__(self):
+        try:
+            for d in self._dev.values():
+                lib().tg_index_destroy(d)
+            lib().tg_index_host_destroy(self._h)
+        except Exception:
+            pass
+
+    # -- accessors (src/index.rs:293-300) ---------------------------------------------------------------------
+    def text_len(self) -> int:
+        return lib().tg_index_host_text_len(self._h)
+
+    def refs(self) -> List[Ref]:
+        out = []
+        for i in range(lib().tg_index_host_n_refs(self._h)):
+            v = (C.c_uint64 * 4)()
+            name = lib().tg_index_host_ref(self._h, i, v).decode()
+            out.append(Ref(name, bool(v[3]), int(v[2]), int(v[0]), int(v[1])))
+        return out
+
+    def txome(self) -> Txome:
+        L = lib()
+        genes = [Gene(L.tg_index_host_gene_id(self._h, i).decode(), L.tg_index_host_gene_name(self._h, i).decode())
+                 for i in range(L.tg_index_host_n_genes(self._h))]
+        txs = []
+        for i in range(L.tg_index_host_n_txs(self._h)):
+            v = (C.c_uint64 * 4)()
+            tid = L.tg_index_host_tx(self._h, i, v).decode()
+            txs.append(Tx(tid, bool(v[1]), int(v[0]), int(v[2]), int(v[3])))
+        return Txome(genes, txs)
+
+    def suffix_array(self) -> np.ndarray:
+        n = self.text_len()
+        p = lib().tg_index_host_sa(self._h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,))
+
+    # -- device replica -----------------------------------------------------------------------------------------
+    def device_index(self, device: int = 0):
+        if device not in self._dev:
+            d = C.c_void_p()
+            _check(lib().tg_index_create(self._h, device, C.byref(d)))
+            self._dev[device] = d
+        return self._dev[device]
+
+    def adopt_device_blob(self, device_ptr: int, nbytes: int, device: int, keepalive=None):
+        """Use a blob that is already in HBM (e.g. received by an NCCL broadcast) as this index's replica."""
+        d = C.c_void_p()
+        _check(lib().tg_index_create_from_device_blob(C.c_void_p(device_ptr), C.c_size_t(nbytes), device, C.byref(d)))
+        self._dev[device] = d
+        self._blob_keepalive = keepalive
+        return d
+
+
+@dataclass
+class Alignment:
+    """bio::alignment::Alignment fields used on this path."""
+    score: int
+    ystart: int
+    xstart: int
+    yend: int
+    xend: int
+    ylen: int
+    xlen: int
+    operations: list
+
+
+@dataclass
+class GenomeAlignment:
+    """src/txome.rs:55-69"""
+    gx_aln: Alignment
+    aln_type: str
+    ref_name: str
+    strand: bool
+    primary: bool
+    tx_aln: Optional[Alignment] = None
+    tx_idx: Optional[int] = None
+    gene_idx: Optional[int] = None
+
+
+class AlignResult:
+    """Flat records of one batch (host copies).  read r owns alns[first[r] : first[r] + count[r]]."""
+
+    def __init__(self, first, count, alns, ops, counters, ref_names=None):
+        self.first, self.count, self.alns, self.ops = first, count, alns, ops
+        self.counters = counters
+        self._ref_names = ref_names
+
+    def __len__(self):
+        return len(self.first)
+
+    def read_alignments(self, r: int) -> List[GenomeAlignment]:
+        out = []
+        for a in self.alns[int(self.first[r]): int(self.first[r]) + int(self.count[r])]:
+            ops = expand_ops(self.ops[int(a["ops_off"]): int(a["ops_off"]) + int(a["ops_len"])])
+            gx = Alignment(int(a["score"]), int(a["ystart"]), int(a["xstart"]), int(a["yend"]), int(a["xend"]),
+                           int(a["ylen"]), int(a["xlen"]), ops)
+            g = GenomeAlignment(gx, ALN_TYPES[int(a["aln_type"])],
+                                self._ref_names[int(a["ref_id"])] if self._ref_names else str(int(a["ref_id"])),
+                                bool(a["strand"]), bool(a["primary"]))
+            if a["aln_type"] == 0:
+                tops = expand_ops(self.ops[int(a["tx_ops_off"]): int(a["tx_ops_off"]) + int(a["tx_ops_len"])])
+                g.tx_aln = Alignment(int(a["tx_score"]), int(a["tx_ystart"]), int(a["tx_xstart"]), int(a["tx_yend"]),
+                                     int(a["tx_xend"]), int(a["tx_ylen"]), int(a["xlen"]), tops)
+                g.tx_idx = int(a["tx_or_gene_idx"])
+            elif a["aln_type"] == 1:
+                g.gene_idx = int(a["tx_or_gene_idx"])
+            out.append(g)
+        return out
+
+
+class Aligner:
+    """One alignment context (CUDA stream + k-mer table + scratch) on one GPU.  Not thread-safe; create one per
+    host thread / per GPU (the reference's ThermiteAligner is Clone + Send, src/wrapper.rs:20-27)."""
+
+    def __init__(self, index: Index, opts: AlignOpts = None, device: int = 0):
+        self.index = index
+        self.opts = opts or AlignOpts()
+        self.device = device
+        dix = index.device_index(device)
+        h = C.c_void_p()
+        o = self.opts._c()
+        _check(lib().tg_ctx_create(dix, C.byref(o), C.byref(h)))
+        self._h = h
+        self._ref_names = [r.name for r in index.refs()]
+
+    def __del__(self):
+        try:
+            lib().tg_ctx_destroy(self._h)
+        except Exception:
+            pass
+
+    def stream_ptr(self) -> int:
+        return lib().tg_ctx_stream(self._h)
+
+    def last_kernel_ms(self):
+        a, b = C.c_float(), C.c_float()
+        lib().tg_ctx_last_kernel_ms(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def kmer_table_bytes(self) -> int:
+        return lib().tg_ctx_kmer_table_bytes(self._h)
+
+    @staticmethod
+    def _counters(res):
+        return dict(swg_cells=res.swg_cells, swg_extensions=res.swg_extensions, seed_hits=res.seed_hits,
+                    n_smems=res.n_smems, n_alns=res.n_alns, n_ops=res.n_ops)
+
+    def align_reads_raw(self, bases_ptr: int, offs_ptr: int, n_reads: int) -> _Result:
+        """tg_align_batch on raw HOST pointers; returns the C struct (pointers owned by the context)."""
+        res = _Result()
+        _check(lib().tg_align_batch(self._h, C.c_void_p(bases_ptr), C.c_void_p(offs_ptr), n_reads, C.byref(res)))
+        return res
+
+    def align_reads_device_raw(self, d_bases_ptr: int, d_offs_ptr: int, n_reads: int, total_bases: int,
+                               max_read_len: int) -> _Result:
+        """tg_align_batch_device: inputs and results stay in HBM."""
+        res = _Result()
+        _check(lib().tg_align_batch_device(self._h, C.c_void_p(d_bases_ptr), C.c_void_p(d_offs_ptr), n_reads,
+                                           C.c_uint64(total_bases), max_read_len, C.byref(res)))
+        return res
+
+    def align_reads(self, bases, offs) -> AlignResult:
+        """Batched align_read (src/aligner.rs:123-190).  bases: concatenated ASCII reads; offs: uint64[n+1]."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offs = np.ascontiguousarray(offs, np.uint64)
+        n = len(offs) - 1
+        res = self.align_reads_raw(bases.ctypes.data, offs.ctypes.data, n)
+        first = np.ctypeslib.as_array(C.cast(res.read_aln_first, C.POINTER(C.c_uint64)), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        count = np.ctypeslib.as_array(C.cast(res.read_aln_count, C.POINTER(C.c_uint32)), shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        alns = np.zeros(res.n_alns, ALN_DTYPE)
+        if res.n_alns:
+            C.memmove(alns.ctypes.data, res.alns, res.n_alns * ALN_DTYPE.itemsize)
+        ops = np.zeros(res.n_ops, np.uint32)
+        if res.n_ops:
+            C.memmove(ops.ctypes.data, res.ops, res.n_ops * 4)
+        return AlignResult(first, count, alns, ops, self._counters(res), self._ref_names)
+
+    def align_read(self, read: bytes) -> List[GenomeAlignment]:
+        """align_read for one read (src/aligner.rs:123)."""
+        b = np.frombuffer(read, np.uint8)
+        r = self.align_reads(b, np.array([0, len(b)], np.uint64))
+        return r.read_alignments(0)
+
+    def seed_reads(self, bases, offs):
+        """Index::all_smems, batched (src/index.rs:228-255) -> (seeds, first, count)."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offs = np.ascontiguousarray(offs, np.uint64)
+        n = len(offs) - 1
+        res = _SeedResult()
+        _check(lib().tg_seed_batch(self._h, _p(bases), _p(offs), n, C.byref(res)))
+        first = np.ctypeslib.as_array(C.cast(res.read_seed_first, C.POINTER(C.c_uint64)), shape=(n,)).copy()
+        count = np.ctypeslib.as_array(C.cast(res.read_seed_count, C.POINTER(C.c_uint32)), shape=(n,)).copy()
+        seeds = np.zeros(res.n_seeds, SEED_DTYPE)
+        if res.n_seeds:
+            C.memmove(seeds.ctypes.data, res.seeds, res.n_seeds * SEED_DTYPE.itemsize)
+        return seeds, first, count
+
+    def all_smems(self, read: bytes):
+        """Index::all_smems for one read -> [(ref_idx, query_idx, len)] in the reference's order."""
+        b = np.frombuffer(read, np.uint8)
+        seeds, first, count = self.seed_reads(b, np.array([0, len(b)], np.uint64))
+        sa = self.index.suffix_array()
+        out = []
+        for s in seeds[int(first[0]): int(first[0]) + int(count[0])]:
+            if s["direct"]:
+                out.append((int(s["sa_lo"]), int(s["query_idx"]), int(s["len"])))
+            else:
+                for rk in range(int(s["count"]) - 1, -1, -1):
+                    out.append((int(sa[int(s["sa_lo"]) + rk]), int(s["query_idx"]), int(s["len"])))
+        return out
+
+    def swg_extend_batch(self, xs, xoff, ys, yoff, bw, x_drop):
+        """SwgExtend::extend for independent pairs (src/swg.rs:31-207)."""
+        n = len(bw)
+        xs = np.ascontiguousarray(xs, np.uint8); ys = np.ascontiguousarray(ys, np.uint8)
+        xoff = np.ascontiguousarray(xoff, np.uint64); yoff = np.ascontiguousarray(yoff, np.uint64)
+        bw = np.ascontiguousarray(bw, np.uint32); x_drop = np.ascontiguousarray(x_drop, np.int32)
+        score = np.zeros(n, np.int32); xend = np.zeros(n, np.uint32); yend = np.zeros(n, np.uint32)
+        ops_off = np.zeros(n + 1, np.uint64)
+        cap = int(len(xs) + len(ys) + 4 * n + 16)
+        ops = np.zeros(cap, np.uint32)
+        cells, ms = C.c_uint64(), C.c_float()
+        _check(lib().tg_swg_extend_batch(self._h, _p(xs), _p(xoff), _p(ys), _p(yoff), n, _p(bw), _p(x_drop), _p(score),
+                                         _p(xend), _p(yend), _p(ops_off), _p(ops), C.c_uint64(cap), C.byref(cells),
+                                         C.byref(ms)))
+        return dict(score=score, xend=xend, yend=yend, ops_off=ops_off, ops=ops[: int(ops_off[n])].copy(),
+                    cells=cells.value, kernel_ms=ms.value)
+
+    def format_result_raw(self, res: _Result, bases, offs, names, name_offs, quals, qual_offs, sam: bool) -> bytes:
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(lib().tg_format_batch(self.index._h, C.byref(res), _p(bases), _p(offs), _p(names), _p(name_offs),
+                                     _p(quals) if quals is not None else None,
+                                     _p(qual_offs) if qual_offs is not None else None, int(sam), C.byref(out),
+                                     C.byref(n)))
+        s = C.string_at(out, n.value)
+        lib().tg_free(out)
+        return s
+
+
+class OutputFormat:
+    """src/aln_writer.rs:16-21"""
+    Bam = "bam"
+    Sam = "sam"
+    Paf = "paf"
+
+
+def parse_fastq(text: bytes):
+    """needletail::parse_fastx_file for FASTQ text -> (bases, offs, names, name_offs, quals, qual_offs)."""
+    L = lib()
+    n = C.c_uint32()
+    ptrs = [C.c_void_p() for _ in range(6)]
+    _check(L.tg_parse_fastq(text, C.c_size_t(len(text)), C.byref(n), *[C.byref(p) for p in ptrs]))
+    n = n.value
+
+    def take(ptr, ctype, count, dtype):
+        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(max(count, 1),))[:count].astype(dtype, copy=True)
+        return a
+    offs = take(ptrs[1], C.c_uint64, n + 1, np.uint64)
+    name_offs = take(ptrs[3], C.c_uint64, n + 1, np.uint64)
+    qual_offs = take(ptrs[5], C.c_uint64, n + 1, np.uint64)
+    bases = take(ptrs[0], C.c_uint8, int(offs[n]), np.uint8)
+    names = take(ptrs[2], C.c_uint8, int(name_offs[n]), np.uint8)
+    quals = take(ptrs[4], C.c_uint8, int(qual_offs[n]), np.uint8)
+    for p in ptrs:
+        L.tg_free(p)
+    return bases, offs, names, name_offs, quals, qual_offs
+
+
+def sam_header(index: Index) -> bytes:
+    out, n = C.c_void_p(), C.c_size_t()
+    _check(lib().tg_format_sam_header(index._h, C.byref(out), C.byref(n)))
+    s = C.string_at(out, n.value)
+    lib().tg_free(out)
+    return s
+
+
+def align_reads_from_file(index: Index, query_paths, output_path: str, output_fmt: str, align_opts: AlignOpts,
+                          device: int = 0, batch_reads: int = 1 << 20):
+    """src/aligner.rs:22-120: align FASTQ files and write PAF or SAM text.  BAM needs htslib/noodles, which this
+    image does not have: requesting it raises ThermiteError."""
+    if output_fmt == OutputFormat.Bam:
+        raise ThermiteError("BAM output is not available in this build (no htslib); use SAM or PAF")
+    aligner = Aligner(index, align_opts, device)
+    sam = output_fmt == OutputFormat.Sam
+    import sys
+    out = sys.stdout.buffer if output_path == "-" else open(output_path, "wb")
+    try:
+        if sam:
+            out.write(sam_header(index))
+        for qp in query_paths:
+            with open(qp, "rb") as f:
+                text = f.read()
+            bases, offs, names, name_offs, quals, qual_offs = parse_fastq(text)
+            n = len(offs) - 1
+            for lo in range(0, n, batch_reads):
+                hi = min(n, lo + batch_reads)
+                o = offs[lo: hi + 1] - offs[lo]
+                no = name_offs[lo: hi + 1] - name_offs[lo]
+                qo = qual_offs[lo: hi + 1] - qual_offs[lo]
+                b = bases[int(offs[lo]): int(offs[hi])]
+                nm = names[int(name_offs[lo]): int(name_offs[hi])]
+                ql = quals[int(qual_offs[lo]): int(qual_offs[hi])]
+                b = np.ascontiguousarray(b); o = np.ascontiguousarray(o)
+                res = aligner.align_reads_raw(b.ctypes.data, o.ctypes.data, hi - lo)
+                out.write(aligner.format_result_raw(res, b, o, np.ascontiguousarray(nm), np.ascontiguousarray(no),
+                                                    np.ascontiguousarray(ql), np.ascontiguousarray(qo), sam))
+    finally:
+        if out is not sys.stdout.buffer:
+            out.close()

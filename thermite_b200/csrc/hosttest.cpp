@@ -1,0 +1,318 @@
+// hosttest.cpp -- TEST-ONLY host build of tg_core.h (libtg_hosttest.so).
+//
+// There is no GPU in the development container, so the warp-cooperative code of tg_core.h is also compiled
+// by g++ and driven by an emulated warp: either 1 lane (plain serial) or 32 lanes on 32 threads that meet
+// at barriers for every shuffle / vote.  `tests/` uses this to check the kernel LOGIC against the oracle
+// on CPU.  The product (thermite_b200/, libthermite_gpu.so) never loads this library: there is no CPU
+// fallback in the product path.
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "tg_core.h"
+
+namespace {
+
+struct HostWarp1 {
+  static constexpr int LANES = 1;
+  int lane() const { return 0; }
+  int shfl_up(int v, int) { return v; }
+  int shfl(int v, int) { return v; }
+  unsigned long long shfl64(unsigned long long v, int) { return v; }
+  bool any(bool p) { return p; }
+  void sync() {}
+  void sync_global() {}
+  unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+  void atomic_or(int* p, int v) { *p |= v; }
+};
+
+struct Barrier {
+  std::atomic<int> count{0};
+  std::atomic<int> gen{0};
+  int n;
+  explicit Barrier(int n_) : n(n_) {}
+  void wait() {
+    int g = gen.load();
+    if (count.fetch_add(1) + 1 == n) {
+      count.store(0);
+      gen.fetch_add(1);
+    } else {
+      while (gen.load() == g) std::this_thread::yield();
+    }
+  }
+};
+struct Warp32Shared {
+  Barrier bar{32};
+  int xi[32];
+  unsigned long long xl[32];
+};
+struct HostWarp32 {
+  static constexpr int LANES = 32;
+  int l;
+  Warp32Shared* sh;
+  int lane() const { return l; }
+  int shfl_up(int v, int d) {
+    sh->xi[l] = v;
+    sh->bar.wait();
+    int r = l >= d ? sh->xi[l - d] : v;
+    sh->bar.wait();
+    return r;
+  }
+  int shfl(int v, int src) {
+    sh->xi[l] = v;
+    sh->bar.wait();
+    int r = sh->xi[src & 31];
+    sh->bar.wait();
+    return r;
+  }
+  unsigned long long shfl64(unsigned long long v, int src) {
+    sh->xl[l] = v;
+    sh->bar.wait();
+    unsigned long long r = sh->xl[src & 31];
+    sh->bar.wait();
+    return r;
+  }
+  bool any(bool p) {
+    sh->xi[l] = p;
+    sh->bar.wait();
+    bool r = false;
+    for (int i = 0; i < 32; i++) r |= sh->xi[i] != 0;
+    sh->bar.wait();
+    return r;
+  }
+  void sync() { sh->bar.wait(); }
+  void sync_global() { sh->bar.wait(); }
+  unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+  void atomic_or(int* p, int v) { *p |= v; }
+};
+
+TgIndexDev view_of(const tg_index_host* ix) {
+  const TgBlobHeader* h = ix->hdr();
+  const uint8_t* b = ix->blob.data();
+  TgIndexDev d;
+  d.text4 = (const uint64_t*)(b + h->off_text4);
+  d.sa = (const uint32_t*)(b + h->off_sa);
+  d.refs = (const TgRef*)(b + h->off_refs);
+  d.exon_nodes = (const TgTreeNode*)(b + h->off_exon_nodes);
+  d.gene_nodes = (const TgTreeNode*)(b + h->off_gene_nodes);
+  d.tx_seq_off = (const uint64_t*)(b + h->off_tx_seq_off);
+  d.tx_exon_off = (const uint32_t*)(b + h->off_tx_exon_off);
+  d.te_start = (const uint32_t*)(b + h->off_te_start);
+  d.te_end = (const uint32_t*)(b + h->off_te_end);
+  d.txseq4 = (const uint64_t*)(b + h->off_txseq4);
+  d.text_len = h->text_len;
+  d.n_refs = (uint32_t)h->n_refs;
+  d.n_txs = (uint32_t)h->n_txs;
+  d.exon_root = (int32_t)h->exon_root;
+  d.gene_root = (int32_t)h->gene_root;
+  return d;
+}
+
+struct HostCtx {
+  const tg_index_host* ix;
+  TgIndexDev dev;
+  tg_opts opts;
+  std::vector<TgSlot> slots;
+  uint64_t slot_mask;
+};
+
+struct WarpBuffers {
+  std::vector<uint8_t> rd, xs, ys, trace;
+  std::vector<uint32_t> a, b, c, t;
+  std::vector<int32_t> stack;
+  std::vector<uint64_t> rp;
+  std::vector<TgSeedHit> hits;
+  std::vector<tg_seed> sm;
+  std::vector<uint16_t> grp;
+  std::vector<TgCand> cands;
+  std::vector<uint32_t> arena;
+  TgWarpMem mem(uint32_t maxL, uint32_t max_bw, int lanes) {
+    uint32_t max_cols = maxL + max_bw + 2;
+    uint32_t cap = 2 * maxL + max_bw + 16;
+    rd.assign(maxL + 16, 0); xs.assign(maxL + 16, 0); ys.assign(max_cols + 16, 0);
+    size_t tb = (size_t)max_cols * tg_trace_bytes_per_col((int)maxL, lanes);
+    if (tb < 4 * TG_MAX_ALNS_PER_READ) tb = 4 * TG_MAX_ALNS_PER_READ;
+    trace.assign(tb + 64, 0);
+    a.assign(cap, 0); b.assign(cap, 0); c.assign(cap, 0); t.assign(cap, 0);
+    stack.assign(TG_TREE_STACK, 0);
+    return TgWarpMem{rd.data(), xs.data(), ys.data(), trace.data(), a.data(), b.data(), c.data(), t.data(), stack.data(), cap};
+  }
+  TgSeedMem seed_mem(uint32_t maxL) {
+    rp.assign(maxL / 16 + 4, 0); hits.assign(maxL + 1, TgSeedHit{0, 0, 0}); sm.assign(maxL + 1, tg_seed{}); grp.assign(maxL + 1, 0);
+    return TgSeedMem{rp.data(), hits.data(), sm.data(), grp.data()};
+  }
+};
+
+uint32_t max_bw_for(const tg_opts& o, uint32_t maxL) {
+  (void)o;
+  return maxL;  // bw = L - min_aln_score <= L
+}
+
+template <class F>
+void run_lanes(int lanes, F&& f) {
+  if (lanes == 1) {
+    HostWarp1 w;
+    f(w);
+    return;
+  }
+  Warp32Shared sh;
+  std::vector<std::thread> th;
+  for (int l = 0; l < 32; l++) th.emplace_back([&, l]() { HostWarp32 w{l, &sh}; f(w); });
+  for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+void* ht_ctx_create(const tg_index_host* ix, const tg_opts* opts) {
+  auto* c = new HostCtx();
+  c->ix = ix;
+  c->dev = view_of(ix);
+  c->opts = *opts;
+  // k-mer table, same per-row logic as the device build kernel
+  const uint32_t k = opts->min_seed_len;
+  const uint64_t T = c->dev.text_len;
+  uint64_t n_groups = 0;
+  for (uint64_t r = 0; r < T; r++) {
+    uint64_t w0, w1;
+    if (tg_kmer_group_start(c->dev.text4, T, c->dev.sa, r, k, w0, w1)) n_groups++;
+  }
+  uint64_t n_slots = 1024;
+  while (n_slots < 2 * n_groups + 2) n_slots <<= 1;
+  c->slots.assign(n_slots, TgSlot{0, 0, 0, 0});
+  c->slot_mask = n_slots - 1;
+  for (uint64_t r = 0; r < T; r++) {
+    uint64_t w0, w1;
+    if (!tg_kmer_group_start(c->dev.text4, T, c->dev.sa, r, k, w0, w1)) continue;
+    uint32_t cnt = tg_kmer_group_count(c->dev.text4, T, c->dev.sa, r, k, w0, w1);
+    uint64_t h = tg_hash_kmer(w0, w1);
+    uint64_t idx = h & c->slot_mask;
+    while (c->slots[idx].tag != 0) idx = (idx + 1) & c->slot_mask;
+    c->slots[idx] = TgSlot{tg_tag_of(h), cnt == 1 ? c->dev.sa[r] : (uint32_t)r, cnt, 0};
+  }
+  return c;
+}
+void ht_ctx_destroy(void* c) { delete (HostCtx*)c; }
+
+// seeds out: caller-provided arrays sized generously; returns total seeds or -1
+long long ht_seed_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes, tg_seed* pool,
+                        uint64_t pool_cap, uint64_t* read_first, uint32_t* read_count) {
+  HostCtx* c = (HostCtx*)cp;
+  uint32_t maxL = 1;
+  for (uint32_t r = 0; r < n; r++) maxL = std::max<uint32_t>(maxL, (uint32_t)(offs[r + 1] - offs[r]));
+  if (maxL > TG_MAX_READ_LEN) return -1;
+  WarpBuffers wb;
+  TgSeedMem sm = wb.seed_mem(maxL);
+  unsigned long long used = 0, n_smems = 0;
+  int flags = 0;
+  TgSeedOut out{pool, &used, pool_cap, read_first, read_count, &flags, &n_smems};
+  for (uint32_t r = 0; r < n; r++) {
+    uint32_t L = (uint32_t)(offs[r + 1] - offs[r]);
+    run_lanes(lanes, [&](auto& w) {
+      tg_seed_read(w, sm, bases, offs[r], L, c->opts.min_seed_len, c->slots.data(), c->slot_mask, c->dev.text4,
+                   c->dev.sa, out, r);
+    });
+  }
+  return flags ? -1 : (long long)used;
+}
+
+struct HtResult {
+  std::vector<uint64_t> first;
+  std::vector<uint32_t> count;
+  std::vector<tg_aln> alns;
+  std::vector<uint32_t> ops;
+  unsigned long long n_alns = 0, n_ops = 0;
+  TgCounters ctr{0, 0, 0};
+  int flags = 0;
+};
+
+void* ht_align_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes) {
+  HostCtx* c = (HostCtx*)cp;
+  uint32_t maxL = 1;
+  for (uint32_t r = 0; r < n; r++) maxL = std::max<uint32_t>(maxL, (uint32_t)(offs[r + 1] - offs[r]));
+  if (maxL > TG_MAX_READ_LEN) return nullptr;
+  auto* res = new HtResult();
+  res->first.assign(n, 0);
+  res->count.assign(n, 0);
+  res->alns.resize((size_t)n * 8 + 1024);
+  res->ops.resize((size_t)n * 64 + 65536);
+  WarpBuffers wb;
+  TgSeedMem sm = wb.seed_mem(maxL);
+  TgWarpMem wm = wb.mem(maxL, max_bw_for(c->opts, maxL), lanes);
+  wb.cands.resize(TG_MAX_ALNS_PER_READ);
+  wb.arena.resize(1 << 16);
+  TgWarpScratch sc{wb.cands.data(), wb.arena.data(), (uint32_t)wb.arena.size()};
+  std::vector<tg_seed> pool(maxL + 8);
+  std::vector<uint64_t> sfirst(1);
+  std::vector<uint32_t> scount(1);
+  TgAlignParams P{c->dev, c->opts};
+  TgAlignOut out{res->first.data(), res->count.data(), res->alns.data(), res->ops.data(), &res->n_alns, &res->n_ops,
+                 res->alns.size(), res->ops.size(), &res->flags};
+  for (uint32_t r = 0; r < n; r++) {
+    uint32_t L = (uint32_t)(offs[r + 1] - offs[r]);
+    unsigned long long used = 0, n_smems = 0;
+    TgSeedOut sout{pool.data(), &used, pool.size(), sfirst.data(), scount.data(), &res->flags, &n_smems};
+    std::vector<TgCounters> lane_ctr(32, TgCounters{0, 0, 0});
+    run_lanes(lanes, [&](auto& w) {
+      tg_seed_read(w, sm, bases, offs[r], L, c->opts.min_seed_len, c->slots.data(), c->slot_mask, c->dev.text4,
+                   c->dev.sa, sout, 0);
+      tg_align_read(w, wm, P, bases, offs[r], L, pool.data() + sfirst[0], scount[0], sc, out, r, lane_ctr[w.lane()]);
+    });
+    for (auto& lc : lane_ctr) { res->ctr.cells += lc.cells; res->ctr.n_ext += lc.n_ext; res->ctr.hits += lc.hits; }
+  }
+  return res;
+}
+void ht_result_info(void* rp, uint64_t* out /*n_alns,n_ops,cells,n_ext,hits,flags*/) {
+  auto* r = (HtResult*)rp;
+  out[0] = r->n_alns; out[1] = r->n_ops; out[2] = r->ctr.cells; out[3] = r->ctr.n_ext; out[4] = r->ctr.hits; out[5] = (uint64_t)r->flags;
+}
+void ht_result_copy(void* rp, uint64_t* first, uint32_t* count, tg_aln* alns, uint32_t* ops) {
+  auto* r = (HtResult*)rp;
+  memcpy(first, r->first.data(), r->first.size() * 8);
+  memcpy(count, r->count.data(), r->count.size() * 4);
+  memcpy(alns, r->alns.data(), r->n_alns * sizeof(tg_aln));
+  memcpy(ops, r->ops.data(), r->n_ops * 4);
+}
+void ht_result_free(void* rp) { delete (HtResult*)rp; }
+
+// SwgExtend::extend batch with raw byte comparison (like tg_swg_extend_batch)
+long long ht_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uint8_t* ys, const uint64_t* yoff,
+                              uint32_t n, const uint32_t* bw, const int32_t* x_drop, int lanes, int32_t* score,
+                              uint32_t* xend, uint32_t* yend, uint64_t* ops_off, uint32_t* ops, uint64_t ops_cap,
+                              uint64_t* cells_out) {
+  unsigned long long total = 0, cells = 0;
+  for (uint32_t t = 0; t < n; t++) {
+    int xlen = (int)(xoff[t + 1] - xoff[t]), ylen = (int)(yoff[t + 1] - yoff[t]);
+    if (xlen > (int)TG_MAX_READ_LEN || x_drop[t] < (int32_t)bw[t]) return -1;
+    int ncols = ylen < xlen + (int)bw[t] ? ylen : xlen + (int)bw[t];
+    std::vector<uint8_t> trace((size_t)(ncols + 1) * tg_trace_bytes_per_col(xlen, lanes) + 64);
+    std::vector<uint32_t> buf((size_t)xlen + ncols + 8);
+    TgOps o{buf.data(), 0};
+    TgSwgResult res{0, 0, 0};
+    std::vector<unsigned long long> lc(32, 0), le(32, 0);
+    int ylen_c = ylen > xlen + (int)bw[t] ? xlen + (int)bw[t] + 1 : ylen;
+    run_lanes(lanes, [&](auto& w) {
+      TgSwgResult r{0, 0, 0};
+      TgOps lo{buf.data(), 0};
+      tg_swg_extend(w, xs + xoff[t], ys + yoff[t], xlen, ylen_c, (int)bw[t], x_drop[t], trace.data(), r, lo,
+                    lc[w.lane()], le[w.lane()]);
+      if (w.lane() == 0) { res = r; o.n = lo.n; }
+    });
+    for (auto v : lc) cells += v;
+    score[t] = res.score; xend[t] = (uint32_t)res.xend; yend[t] = (uint32_t)res.yend;
+    ops_off[t] = total;
+    // buffer holds rev(operations): emit forward
+    for (uint32_t i = o.n; i-- > 0;) {
+      if (total < ops_cap) ops[total] = o.w[i];
+      total++;
+    }
+  }
+  ops_off[n] = total;
+  if (cells_out) *cells_out = cells;
+  return (long long)total;
+}
+
+}  // extern "C"

@@ -1,0 +1,1068 @@
+// tg_core.h -- the alignment hot path as warp-cooperative code, written once and compiled twice:
+//   * by nvcc for sm_100a inside the kernels of thermite_gpu.cu (W = DevWarp: 32 lanes, shuffles, votes);
+//   * by g++ inside csrc/hosttest.cpp (W = HostWarp: 1 lane, or 32 emulated lanes on threads) so the
+//     logic can be unit-tested in a container without a GPU.  The host build is TEST-ONLY: the shipped
+//     library never executes it (no CPU fallback; see thermite_gpu.cu).
+//
+// Reference being replaced (paths under /root/reference): src/index.rs:228-255 (all_smems),
+// src/aligner.rs:123-449, src/swg.rs:31-240, src/txome.rs:77-160.
+#pragma once
+#include "tg_internal.h"
+
+#ifdef __CUDACC__
+#define TG_HD __host__ __device__ __forceinline__
+#define TG_HDN __host__ __device__
+#else
+#define TG_HD inline
+#define TG_HDN
+#endif
+
+#ifdef __CUDA_ARCH__
+#define TG_LDG(p) __ldg(p)
+#define TG_CLZ64(x) __clzll((long long)(x))
+#else
+#define TG_LDG(p) (*(p))
+#define TG_CLZ64(x) __builtin_clzll(x)
+#endif
+
+#define TG_MINV (-(1 << 29))
+#define TG_DIRECT 0x80000000u
+
+// ------------------------------------------------------------------------------------------------
+// packed 4-bit sequences: 16 symbols per u64, first symbol in the top nibble.  Every packed array has
+// at least 2 readable words past its last symbol.
+// ------------------------------------------------------------------------------------------------
+TG_HD uint64_t tg_ld16(const uint64_t* s, uint64_t pos) {
+  uint64_t w = pos >> 4;
+  uint32_t sh = (uint32_t)(pos & 15) * 4;
+  uint64_t a = TG_LDG(s + w);
+  if (sh == 0) return a;
+  uint64_t b = TG_LDG(s + w + 1);
+  return (a << sh) | (b >> (64 - sh));
+}
+TG_HD uint64_t tg_ld16_local(const uint64_t* s, uint32_t pos) {  // shared / host memory
+  uint32_t w = pos >> 4, sh = (pos & 15) * 4;
+  uint64_t a = s[w];
+  if (sh == 0) return a;
+  return (a << sh) | (s[w + 1] >> (64 - sh));
+}
+TG_HD uint32_t tg_code_at(const uint64_t* s, uint64_t pos) {
+  return (uint32_t)(TG_LDG(s + (pos >> 4)) >> ((15 - (uint32_t)(pos & 15)) * 4)) & 15u;
+}
+
+// read byte -> symbol code after to_ascii_uppercase (src/aligner.rs:125)
+TG_HD uint32_t tg_ascii_code(uint8_t c) {
+  if (c >= 'a' && c <= 'z') c -= 32;
+  switch (c) {
+    case 'A': return TG_C_A;
+    case 'C': return TG_C_C;
+    case 'G': return TG_C_G;
+    case 'N': return TG_C_N;
+    case 'T': return TG_C_T;
+    default: return TG_C_OTHER;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-mer hashing (table build and probe must agree)
+// ------------------------------------------------------------------------------------------------
+TG_HD uint64_t tg_mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+TG_HD uint64_t tg_top_nibbles(uint32_t n) { return n >= 16 ? ~0ull : ~(~0ull >> (4 * n)); }
+TG_HD uint64_t tg_hash_kmer(uint64_t w0, uint64_t w1) { return tg_mix64(w0 ^ tg_mix64(w1 + 0x9e3779b97f4a7c15ULL)); }
+// true when some symbol of the top-n nibbles has its low three bits all set (codes 7 and 15)
+TG_HD bool tg_has_bad_symbol(uint64_t w) { return (w & (w >> 1) & (w >> 2) & 0x1111111111111111ULL) != 0; }
+// true when some nibble of w is zero (the '$' separator)
+TG_HD bool tg_has_zero_nibble(uint64_t w) {
+  uint64_t t = w | (w >> 1);
+  t |= t >> 2;
+  return (~t & 0x1111111111111111ULL) != 0;
+}
+TG_HD uint32_t tg_tag_of(uint64_t h) {
+  uint32_t t = (uint32_t)(h >> 32);
+  return t ? t : 1u;
+}
+
+// Longest common prefix of read[q..L) (packed, padded with 0xF) and seq[pos..).  *read_le is set when the
+// read suffix sorts before the text suffix or is a prefix of it.
+TG_HD uint32_t tg_lcp(const uint64_t* rp, uint32_t q, uint32_t L, const uint64_t* seq, uint64_t pos, bool* read_le) {
+  uint32_t maxl = L - q, off = 0;
+  while (off < maxl) {
+    uint64_t a = tg_ld16_local(rp, q + off), b = tg_ld16(seq, pos + off);
+    uint64_t x = a ^ b;
+    if (x) {
+      uint32_t nb = (uint32_t)TG_CLZ64(x) >> 2;
+      uint32_t l = off + nb;
+      if (l >= maxl) { *read_le = true; return maxl; }
+      uint32_t sh = (15 - nb) * 4;
+      *read_le = ((a >> sh) & 15) < ((b >> sh) & 15);
+      return l;
+    }
+    off += 16;
+  }
+  *read_le = true;
+  return maxl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Seeding (replaces Index::all_smems, src/index.rs:228-255).
+//
+// E(q) = q + (longest prefix of read[q..] that occurs in the text).  The SMEMs with length >= k are the
+// intervals [q, E(q)) with E(q)-q >= k and (q == 0 or E(q-1) < E(q)); the occurrences of an SMEM are a
+// contiguous range of suffix-array rows inside the range of its leading k-mer.
+// ------------------------------------------------------------------------------------------------
+struct TgSeedHit {
+  uint32_t e;    // E(q), 0 when read[q..q+k) does not occur
+  uint32_t lo;   // first SA row of the occurrences (or the text position when direct)
+  uint32_t cnt;  // number of occurrences | TG_DIRECT
+};
+
+TG_HD void tg_seed_offset(const uint64_t* rp, uint32_t L, uint32_t q, uint32_t k, const TgSlot* slots,
+                          uint64_t slot_mask, const uint64_t* text4, const uint32_t* sa, TgSeedHit& out) {
+  out.e = 0; out.lo = 0; out.cnt = 0;
+  uint64_t w0 = tg_ld16_local(rp, q) & tg_top_nibbles(k);
+  uint64_t w1 = k > 16 ? (tg_ld16_local(rp, q + 16) & tg_top_nibbles(k - 16)) : 0;
+  if (tg_has_bad_symbol(w0) || tg_has_bad_symbol(w1)) return;
+  uint64_t h = tg_hash_kmer(w0, w1);
+  uint32_t tag = tg_tag_of(h);
+  uint64_t idx = h & slot_mask;
+  for (;;) {
+#ifdef __CUDA_ARCH__
+    uint4 raw = __ldg((const uint4*)(slots + idx));
+    TgSlot s{raw.x, raw.y, raw.z, raw.w};
+#else
+    TgSlot s = slots[idx];
+#endif
+    if (s.tag == 0) return;
+    if (s.tag == tag) {
+      bool le;
+      if (s.count == 1) {
+        uint32_t l = tg_lcp(rp, q, L, text4, s.lo, &le);
+        if (l >= k) { out.e = q + l; out.lo = s.lo; out.cnt = 1u | TG_DIRECT; return; }
+      } else {
+        // first row whose suffix is >= the read suffix
+        uint32_t a = s.lo, b = s.lo + s.count;
+        bool ok = true;
+        while (a < b) {
+          uint32_t mid = a + ((b - a) >> 1);
+          uint32_t l = tg_lcp(rp, q, L, text4, TG_LDG(sa + mid), &le);
+          if (l < k) { ok = false; break; }  // tag collision: a different k-mer
+          if (le) b = mid; else a = mid + 1;
+        }
+        if (ok) {
+          uint32_t ins = a, hi = s.lo + s.count, best = 0;
+          uint32_t l_ins = 0, l_prev = 0;
+          if (ins < hi) l_ins = tg_lcp(rp, q, L, text4, TG_LDG(sa + ins), &le);
+          if (ins > s.lo) l_prev = tg_lcp(rp, q, L, text4, TG_LDG(sa + ins - 1), &le);
+          best = l_ins > l_prev ? l_ins : l_prev;
+          // rows with lcp >= best form one contiguous range around ins
+          uint32_t left = ins, right = ins;  // [left, right)
+          if (l_prev >= best) {              // lcp is non-decreasing on [s.lo, ins)
+            uint32_t x = s.lo, y = ins - 1;  // find the first row in [x, y] with lcp >= best
+            while (x < y) {
+              uint32_t mid = x + ((y - x) >> 1);
+              if (tg_lcp(rp, q, L, text4, TG_LDG(sa + mid), &le) >= best) y = mid; else x = mid + 1;
+            }
+            left = x;
+          }
+          if (l_ins >= best && ins < hi) {   // lcp is non-increasing on [ins, hi)
+            uint32_t x = ins, y = hi - 1;    // find the last row in [x, y] with lcp >= best
+            while (x < y) {
+              uint32_t mid = x + ((y - x + 1) >> 1);
+              if (tg_lcp(rp, q, L, text4, TG_LDG(sa + mid), &le) >= best) x = mid; else y = mid - 1;
+            }
+            right = x + 1;
+          }
+          out.e = q + best; out.lo = left; out.cnt = right - left;
+          return;
+        }
+      }
+    }
+    idx = (idx + 1) & slot_mask;
+  }
+}
+
+// Serial part of seeding: pick the SMEM starts from E[], order them as Index::all_smems does and write the
+// records.  hits[q] valid for q + k <= L.  Returns the number of SMEMs (<= L - k + 1).
+// Order: bio emits, for i0 = 0, max-end, ...: the SMEMs covering i0 by DESCENDING start; then
+// src/index.rs:251-253 stable-sorts by len ascending and reverses => len DESC, ties in REVERSE emission order.
+TG_HD uint32_t tg_smem_select(const TgSeedHit* hits, uint32_t L, uint32_t k, tg_seed* out, uint16_t* grp_scratch) {
+  if (L < k || k == 0) return 0;
+  uint32_t n = 0, prev_e = 0;
+  for (uint32_t q = 0; q + k <= L; q++) {
+    uint32_t e = hits[q].e;
+    if (e != 0 && (q == 0 || prev_e < e)) {
+      out[n].query_idx = q; out[n].len = e - q; out[n].sa_lo = hits[q].lo;
+      out[n].count = hits[q].cnt & ~TG_DIRECT; out[n].direct = (hits[q].cnt & TG_DIRECT) ? 1u : 0u; out[n].pad = 0;
+      n++;
+    }
+    prev_e = e;
+  }
+  // emission groups
+  uint32_t i0 = 0, idx = 0, g = 0;
+  while (idx < n) {
+    if (out[idx].query_idx > i0) i0 = out[idx].query_idx;
+    uint32_t maxend = i0 + 1;
+    while (idx < n && out[idx].query_idx <= i0) {
+      grp_scratch[idx] = (uint16_t)g;
+      uint32_t e = out[idx].query_idx + out[idx].len;
+      if (e > maxend) maxend = e;
+      idx++;
+    }
+    i0 = maxend;
+    g++;
+  }
+  // insertion sort by (len DESC, group DESC, start ASC)
+  for (uint32_t i = 1; i < n; i++) {
+    tg_seed cur = out[i];
+    uint16_t cg = grp_scratch[i];
+    uint32_t j = i;
+    while (j > 0) {
+      const tg_seed& p = out[j - 1];
+      uint16_t pg = grp_scratch[j - 1];
+      bool p_before = p.len > cur.len || (p.len == cur.len && (pg > cg || (pg == cg && p.query_idx < cur.query_idx)));
+      if (p_before) break;
+      out[j] = out[j - 1];
+      grp_scratch[j] = grp_scratch[j - 1];
+      j--;
+    }
+    out[j] = cur;
+    grp_scratch[j] = cg;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RLE op buffers
+// ------------------------------------------------------------------------------------------------
+struct TgOps {
+  uint32_t* w;
+  uint32_t n;
+};
+TG_HD void tg_ops_push(TgOps& o, uint32_t kind, uint32_t run) {
+  if (run == 0 && kind <= TG_OP_INS) return;
+  if (kind <= TG_OP_INS && o.n > 0 && (o.w[o.n - 1] & 7u) == kind) o.w[o.n - 1] += run << 3;
+  else o.w[o.n++] = kind | (run << 3);
+}
+TG_HD void tg_ops_append_reversed(TgOps& dst, const TgOps& src) {
+  for (uint32_t i = src.n; i-- > 0;) tg_ops_push(dst, src.w[i] & 7u, src.w[i] >> 3);
+}
+TG_HD void tg_ops_reverse(TgOps& o) {
+  for (uint32_t i = 0, j = o.n; i + 1 < j; i++) {
+    j--;
+    uint32_t t = o.w[i]; o.w[i] = o.w[j]; o.w[j] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Banded Smith-Waterman-Gotoh extension (replaces SwgExtend::extend / trace, src/swg.rs:31-207) as an
+// anti-diagonal wavefront: lane l owns rows [l*R, l*R+R) of the DP matrix and is one column behind lane l-1.
+//
+// Cell (i, j) (row i over x, column j over y) is in the reference's band iff
+//     lo(j) <= i <= hi(j),  lo(j) = max(0, j - bw),  hi(j) = min(xlen, max(2*bw, j + bw))
+// (rows 0..2bw for the first bw columns: quirk Q2), out-of-band neighbours count as MIN_SCORE, row-0 cells only
+// take the "deletion" branch whose column-0 seed is C[0] = 0 (quirk Q1).  Requires x_drop >= bw (then the
+// phase-1 x-drop break of src/swg.rs:110-112 is unreachable and no stale state exists: quirk Q4).
+// Scores are exact in 32-bit; MIN_SCORE is represented by TG_MINV and never wins a max against a real cell.
+// ------------------------------------------------------------------------------------------------
+template <int R>
+struct TgSwgLane {
+  int D[R], C[R];
+  uint8_t xc[R];
+  int diag_in;        // D(i0-1, j-1)
+  int sendD, sendR;   // D/R of this lane's last row for the column it just finished
+  int sendCM, sendCR; // running (column max, first row attaining it) for that column
+};
+
+TG_HD int tg_pack_dr(int d, int r) {
+  if (d < -32768) d = -32768;
+  if (r < -32768) r = -32768;
+  return (int)(((uint32_t)d << 16) | ((uint32_t)r & 0xffffu));
+}
+TG_HD void tg_unpack_dr(int p, int& d, int& r) {
+  d = p >> 16;
+  r = (int)(int16_t)(p & 0xffff);
+  if (d == -32768) d = TG_MINV;
+  if (r == -32768) r = TG_MINV;
+}
+
+template <int R>
+TG_HD void tg_swg_lane_init(TgSwgLane<R>& s, int lane, const uint8_t* xs, int xlen, int bw) {
+  const int i0 = lane * R;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    int i = i0 + r;
+    bool in0 = i <= 2 * bw;  // column 0 initialises rows 0..w-1 (src/swg.rs:62-71)
+    s.D[r] = in0 ? (i == 0 ? 0 : -(i + 1)) : TG_MINV;
+    s.C[r] = (in0 && i == 0) ? 0 : TG_MINV;
+    s.xc[r] = (i >= 1 && i <= xlen) ? xs[i - 1] : (uint8_t)0xFE;
+  }
+  int ip = i0 - 1;
+  s.diag_in = (ip < 0 || ip > 2 * bw) ? TG_MINV : (ip == 0 ? 0 : -(ip + 1));
+  s.sendD = TG_MINV; s.sendR = TG_MINV; s.sendCM = TG_MINV; s.sendCR = 0;
+}
+
+// One column for one lane.  recvD/recvR/recvCM/recvCR come from lane-1 (TG_MINV for lane 0).
+// bits[] receives the packed 2-bit directions of the lane's R cells (0 diag, 1 Del, 2 Ins), 16 cells per word.
+template <int R>
+TG_HD void tg_swg_lane_step(TgSwgLane<R>& s, int lane, int j, uint8_t y, int xlen, int bw, int recvD, int recvR,
+                            int recvCM, int recvCR, uint32_t (&bits)[(R + 15) / 16]) {
+  const int i0 = lane * R;
+  const int lo = j - bw > 0 ? j - bw : 0;
+  int hi = j + bw > 2 * bw ? j + bw : 2 * bw;
+  if (hi > xlen) hi = xlen;
+  int upD = recvD, upR = recvR, dg = s.diag_in, cm = recvCM, cr = recvCR;
+#pragma unroll
+  for (int b = 0; b < (R + 15) / 16; b++) bits[b] = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i = i0 + r;
+    int c = s.C[r] - 1 > s.D[r] - 2 ? s.C[r] - 1 : s.D[r] - 2;
+    int rr = upR - 1 > upD - 2 ? upR - 1 : upD - 2;
+    int d = dg + (s.xc[r] == y ? 1 : -1);
+    int nd = d > c ? d : c;
+    nd = nd > rr ? nd : rr;
+    uint32_t dir = (nd == d) ? 0u : ((nd == c) ? 1u : 2u);
+    dg = s.D[r];
+    if (i >= lo && i <= hi) {
+      s.D[r] = nd; s.C[r] = c; upD = nd; upR = rr;
+      bits[r >> 4] |= dir << (2 * (r & 15));
+      if (nd > cm) { cm = nd; cr = i; }
+    } else {
+      upD = TG_MINV; upR = TG_MINV;
+      if (i < lo) { s.D[r] = TG_MINV; s.C[r] = TG_MINV; }
+    }
+  }
+  s.diag_in = recvD;
+  s.sendD = upD; s.sendR = upR; s.sendCM = cm; s.sendCR = cr;
+}
+
+struct TgSwgResult {
+  int score, xend, yend;
+};
+
+// trace layout: bytes; row (j-1) holds LANES * TB bytes, lane l's TB = (2R+7)/8 bytes at offset l*TB.
+template <int R>
+struct TgTraceBytes { static constexpr int value = (2 * R + 7) / 8; };
+
+// W: warp policy (lane, LANES, shfl_up, shfl, any, sync).  xs: x symbols (xlen), ys: y symbols (ncols).
+// ncols = min(ylen, xlen + bw) (later columns are empty and only trigger the x-drop break).
+template <int R, class W>
+TG_HDN void tg_swg_fill(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, int ncols, int bw, int x_drop,
+                        uint8_t* trace, TgSwgResult& res, unsigned long long& cells) {
+  constexpr int TB = TgTraceBytes<R>::value;
+  const int lane = w.lane();
+  const int nl = (xlen + R) / R;  // lanes that own at least one existing row
+  TgSwgLane<R> s;
+  tg_swg_lane_init<R>(s, lane, xs, xlen, bw);
+  int max_score = 0, max_i = 0, max_j = 0;
+  bool stop = false;
+  const int nsteps = ncols + nl - 1;
+  for (int t = 0; t < nsteps; t++) {
+    int pdr = w.shfl_up(tg_pack_dr(s.sendD, s.sendR), 1);
+    int pcm = w.shfl_up(tg_pack_dr(s.sendCM, s.sendCR), 1);
+    int recvD, recvR, recvCM, recvCR;
+    tg_unpack_dr(pdr, recvD, recvR);
+    recvCM = pcm >> 16; recvCR = pcm & 0xffff;
+    if (recvCM == -32768) recvCM = TG_MINV;
+    if (lane == 0) { recvD = TG_MINV; recvR = TG_MINV; recvCM = TG_MINV; recvCR = 0; }
+    const int j = t - lane + 1;
+    if (lane < nl && j >= 1 && j <= ncols) {
+      uint32_t bits[(R + 15) / 16];
+      tg_swg_lane_step<R>(s, lane, j, ys[j - 1], xlen, bw, recvD, recvR, recvCM, recvCR, bits);
+      uint8_t* tp = trace + ((size_t)(j - 1) * W::LANES + lane) * TB;
+#pragma unroll
+      for (int b = 0; b < TB; b++) tp[b] = (uint8_t)(bits[b >> 2] >> (8 * (b & 3)));
+      if (lane == nl - 1) {  // this lane completes column j: src/swg.rs:101-112 / :142-153
+        int lo = j - bw > 0 ? j - bw : 0;
+        int hi = j + bw > 2 * bw ? j + bw : 2 * bw;
+        if (hi > xlen) hi = xlen;
+        if (hi >= lo) cells += (unsigned long long)(hi - lo + 1);
+        if (s.sendCM > max_score) { max_score = s.sendCM; max_i = s.sendCR; max_j = j; }
+        if (s.sendCM < max_score - x_drop) stop = true;
+      }
+    }
+    if (w.any(stop)) break;
+  }
+  res.score = w.shfl(max_score, nl - 1);
+  res.xend = w.shfl(max_i, nl - 1);
+  res.yend = w.shfl(max_j, nl - 1);
+  w.sync();
+}
+
+// Traceback (src/swg.rs:170-207) in generation order (end cell -> origin), i.e. rev(operations).
+// Uniform across lanes; only lane 0 of W writes.
+template <int R, class W>
+TG_HDN void tg_swg_traceback(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, const uint8_t* trace,
+                             const TgSwgResult& res, TgOps& out) {
+  constexpr int TB = TgTraceBytes<R>::value;
+  if (w.lane() == 0) {
+    int i = res.xend, j = res.yend;
+    if (i < xlen) tg_ops_push(out, TG_OP_XCLIP, (uint32_t)(xlen - i));
+    while (i > 0 || j > 0) {
+      uint32_t dir;
+      if (j == 0) dir = 2;  // column 0 is all Ins (src/swg.rs:65,70)
+      else {
+        const int rr = i % R;
+        const uint8_t* tp = trace + ((size_t)(j - 1) * W::LANES + (i / R)) * TB;
+        dir = ((uint32_t)tp[rr >> 2] >> (2 * (rr & 3))) & 3u;
+      }
+      if (dir == 0) {
+        tg_ops_push(out, xs[i - 1] == ys[j - 1] ? TG_OP_MATCH : TG_OP_SUBST, 1);
+        i--; j--;
+      } else if (dir == 1) {
+        tg_ops_push(out, TG_OP_DEL, 1);
+        j--;
+      } else {
+        tg_ops_push(out, TG_OP_INS, 1);
+        i--;
+      }
+    }
+  }
+  out.n = (uint32_t)w.shfl((int)out.n, 0);
+  w.sync();
+}
+
+// Full extension: early return for empty x or y (src/swg.rs:39-55), fill, traceback.
+// `out` receives rev(operations).  R is chosen by the caller so that 32*R > xlen (or R*LANES > xlen on host).
+template <int R, class W>
+TG_HDN void tg_swg_extend_r(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, int ylen, int bw, int x_drop,
+                            uint8_t* trace, TgSwgResult& res, TgOps& out, unsigned long long& cells,
+                            unsigned long long& n_ext) {
+  if (xlen == 0 || ylen == 0) {
+    res.score = 0; res.xend = 0; res.yend = 0;
+    if (xlen > 0 && w.lane() == 0) tg_ops_push(out, TG_OP_XCLIP, (uint32_t)xlen);
+    out.n = (uint32_t)w.shfl((int)out.n, 0);
+    w.sync();
+    return;
+  }
+  int ncols = ylen < xlen + bw ? ylen : xlen + bw;
+  tg_swg_fill<R, W>(w, xs, ys, xlen, ncols, bw, x_drop, trace, res, cells);
+  if (w.lane() == 0) n_ext++;
+  tg_swg_traceback<R, W>(w, xs, ys, xlen, trace, res, out);
+}
+
+// rows-per-lane classes compiled for the device
+TG_HD int tg_swg_rows_class(int xlen, int lanes) {
+  int need = (xlen + lanes) / lanes;  // ceil((xlen+1)/lanes)
+  if (need <= 1) return 1;
+  if (need <= 2) return 2;
+  if (need <= 3) return 3;
+  if (need <= 4) return 4;
+  if (need <= 6) return 6;
+  if (need <= 8) return 8;
+  if (need <= 12) return 12;
+  return 16;
+}
+
+// RMAX bounds the rows-per-lane classes that get instantiated (register pressure of the kernel is set by the
+// largest one); callers guarantee tg_swg_rows_class(xlen) <= RMAX.
+template <class W, int RMAX = 16>
+TG_HDN void tg_swg_extend(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, int ylen, int bw, int x_drop,
+                          uint8_t* trace, TgSwgResult& res, TgOps& out, unsigned long long& cells,
+                          unsigned long long& n_ext) {
+  if constexpr (W::LANES == 1) {
+    tg_swg_extend_r<TG_MAX_READ_LEN + 1, W>(w, xs, ys, xlen, ylen, bw, x_drop, trace, res, out, cells, n_ext);
+    return;
+  } else {
+    const int cls = tg_swg_rows_class(xlen, W::LANES);
+#define TG_SWG_CASE(RR)                                                                                   \
+  if constexpr (RMAX >= RR) {                                                                             \
+    if (cls == RR) { tg_swg_extend_r<RR, W>(w, xs, ys, xlen, ylen, bw, x_drop, trace, res, out, cells, n_ext); return; } \
+  }
+    TG_SWG_CASE(1) TG_SWG_CASE(2) TG_SWG_CASE(3) TG_SWG_CASE(4) TG_SWG_CASE(6) TG_SWG_CASE(8) TG_SWG_CASE(12) TG_SWG_CASE(16)
+#undef TG_SWG_CASE
+  }
+}
+// bytes of trace needed per column for a given longest x
+TG_HD int tg_trace_bytes_per_col(int max_xlen, int lanes) {
+  if (lanes == 1) return (2 * (TG_MAX_READ_LEN + 1) + 7) / 8;
+  int R = tg_swg_rows_class(max_xlen, lanes);
+  return lanes * ((2 * R + 7) / 8);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interval tree `find` (rust-bio IntervalTreeIterator): explicit stack, yields node, then right subtree,
+// then left subtree, pruned by query.start < node.max and query.end > node.start.
+// ------------------------------------------------------------------------------------------------
+#define TG_TREE_STACK 64
+struct TgTreeIter {
+  const TgTreeNode* nodes;
+  int32_t* stack;  // TG_TREE_STACK entries
+  int sp;
+  uint32_t qs, qe;
+};
+TG_HD void tg_tree_begin(TgTreeIter& it, const TgTreeNode* nodes, int32_t root, int32_t* stack, uint32_t qs, uint32_t qe) {
+  it.nodes = nodes; it.stack = stack; it.sp = 0; it.qs = qs; it.qe = qe;
+  if (root >= 0) it.stack[it.sp++] = root;
+}
+// returns false when exhausted
+TG_HD bool tg_tree_next(TgTreeIter& it, uint32_t& data) {
+  while (it.sp > 0) {
+    int32_t ci = it.stack[--it.sp];
+#ifdef __CUDA_ARCH__
+    const uint4 a = __ldg((const uint4*)(it.nodes + ci));
+    const int2 b = __ldg((const int2*)(it.nodes + ci) + 2);
+    TgTreeNode c{a.x, a.y, a.z, a.w, b.x, b.y};
+#else
+    TgTreeNode c = it.nodes[ci];
+#endif
+    if (it.qs < c.max) {
+      if (c.left >= 0 && it.sp < TG_TREE_STACK) it.stack[it.sp++] = c.left;
+      if (it.qe > c.start) {
+        if (c.right >= 0 && it.sp < TG_TREE_STACK) it.stack[it.sp++] = c.right;
+        if (c.start < it.qe && it.qs < c.end) { data = c.data; return true; }
+      }
+    }
+  }
+  return false;
+}
+
+// Index::idx_to_ref (src/index.rs:287-290): first ref whose end_idx > idx
+TG_HD uint32_t tg_idx_to_ref(const TgRef* refs, uint32_t n_refs, uint32_t idx) {
+  uint32_t lo = 0, hi = n_refs;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (TG_LDG(&refs[mid].end_idx) <= idx) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-read state shared by the lanes of one warp ("shared memory" on the device)
+// ------------------------------------------------------------------------------------------------
+struct TgWarpMem {
+  uint8_t* rd;       // read symbols [L]
+  uint8_t* xs;       // staged x (left extension: reversed read prefix)
+  uint8_t* ys;       // staged y [max_cols]
+  uint8_t* trace;    // [max_cols * bytes_per_col]; also scratch for the final filters
+  uint32_t* opsA;    // RLE buffers, ops_cap words each
+  uint32_t* opsB;
+  uint32_t* opsC;
+  uint32_t* opsT;
+  int32_t* stack;    // TG_TREE_STACK
+  uint32_t ops_cap;
+};
+
+struct TgAlignParams {
+  TgIndexDev ix;
+  tg_opts opts;
+};
+
+// One side-by-side extension result (bio Alignment without the ops)
+struct TgAln {
+  int32_t score;
+  uint32_t ystart, yend, xstart, xend;
+};
+
+struct TgCounters {
+  unsigned long long cells, n_ext, hits;
+};
+
+// extend_left_right (src/aligner.rs:352-407) on packed sequence `seq`: the reference sequence is
+// seq[lo_abs, hi_abs), the seed sits at absolute position r_abs.  Result coordinates are absolute in `seq`.
+// `out` receives the stitched operations: rev(left.ops) ++ Match*len ++ right.ops.
+template <class W, int RMAX = 16>
+TG_HDN void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64_t lo_abs, uint64_t hi_abs,
+                                 uint64_t r_abs, uint32_t q, uint32_t len, uint32_t L, uint32_t bw, int32_t x_drop,
+                                 TgAln& aln, TgOps& out, TgCounters& ctr) {
+  const int lane = w.lane();
+  TgSwgResult rr, rl;
+  // ---- right: x = read[q+len..], y = seq[r+len .. hi) (src/aligner.rs:360-362)
+  TgOps tmp{m.opsT, 0};
+  {
+    int xlen = (int)(L - (q + len));
+    uint64_t y0 = r_abs + len;
+    uint64_t ylen64 = hi_abs - y0;
+    int ylen = ylen64 > (uint64_t)(xlen + (int)bw) ? xlen + (int)bw + 1 : (int)ylen64;  // only the first xlen+bw columns matter
+    int ncols = ylen < xlen + (int)bw ? ylen : xlen + (int)bw;
+    if (xlen > 0)
+      for (int t = lane; t < ncols; t += W::LANES) m.ys[t] = (uint8_t)tg_code_at(seq, y0 + (uint64_t)t);
+    w.sync();
+    tg_swg_extend<W, RMAX>(w, m.rd + q + len, m.ys, xlen, ylen, (int)bw, x_drop, m.trace, rr, tmp, ctr.cells, ctr.n_ext);
+  }
+  // ---- left: x = rev(read[..q]), y = rev(seq[max(r-(L+bw), lo) .. r)) (src/aligner.rs:364-375)
+  out.n = 0;
+  {
+    int xlen = (int)q;
+    uint64_t span = (uint64_t)L + bw;
+    uint64_t ys0 = (r_abs - lo_abs > span) ? r_abs - span : lo_abs;
+    uint64_t ylen64 = r_abs - ys0;
+    int ylen = ylen64 > (uint64_t)(xlen + (int)bw) ? xlen + (int)bw + 1 : (int)ylen64;
+    int ncols = ylen < xlen + (int)bw ? ylen : xlen + (int)bw;
+    for (int t = lane; t < xlen; t += W::LANES) m.xs[t] = m.rd[q - 1 - t];
+    if (xlen > 0)
+      for (int t = lane; t < ncols; t += W::LANES) m.ys[t] = (uint8_t)tg_code_at(seq, r_abs - 1 - (uint64_t)t);
+    w.sync();
+    tg_swg_extend<W, RMAX>(w, m.xs, m.ys, xlen, ylen, (int)bw, x_drop, m.trace, rl, out, ctr.cells, ctr.n_ext);
+  }
+  // ---- stitch (src/aligner.rs:377-406)
+  if (lane == 0) {
+    tg_ops_push(out, TG_OP_MATCH, len);
+    tg_ops_append_reversed(out, tmp);
+  }
+  out.n = (uint32_t)w.shfl((int)out.n, 0);
+  w.sync();
+  aln.score = rl.score + (int32_t)len + rr.score;
+  aln.ystart = (uint32_t)(r_abs - (uint64_t)rl.yend);
+  aln.yend = (uint32_t)(r_abs + len + (uint64_t)rr.yend);
+  aln.xstart = q - (uint32_t)rl.xend;
+  aln.xend = q + len + (uint32_t)rr.xend;
+}
+
+// lift_mem_to_tx (src/txome.rs:82-103): first exon in tx order intersecting the seed
+TG_HD bool tg_lift_mem_to_tx(const uint32_t* te_start, const uint32_t* te_end, uint32_t e0, uint32_t e1,
+                             uint32_t ref_idx, uint32_t q, uint32_t len, uint32_t& t_ref, uint32_t& t_q, uint32_t& t_len) {
+  uint32_t exon_sum = 0;
+  for (uint32_t e = e0; e < e1; e++) {
+    uint32_t es = TG_LDG(te_start + e), ee = TG_LDG(te_end + e);
+    uint32_t a0 = ref_idx, a1 = ref_idx + len;
+    if ((a0 >= es && a0 < ee) || (es >= a0 && es < a1)) {
+      uint32_t start = (a0 > es ? a0 - es : 0) + exon_sum;
+      uint32_t start_off = es > a0 ? es - a0 : 0;
+      uint32_t end = (a1 < ee ? a1 : ee) - es + exon_sum;
+      t_ref = start; t_q = q + start_off; t_len = end - start;
+      return true;
+    }
+    exon_sum += ee - es;
+  }
+  return false;  // reference: unreachable!()
+}
+
+// lift_tx_to_gx (src/txome.rs:110-160) on RLE words.  Before EVERY unit op the reference advances at most
+// one exon when the running transcript coordinate sits on an exon end, pushing Yclip(intron length) -- also
+// in front of ops that consume no reference (the documented trailing-Ins quirk).
+TG_HD void tg_lift_tx_to_gx(const uint32_t* te_start, const uint32_t* te_end, uint32_t e0, uint32_t e1,
+                            const TgOps& tx_ops, uint32_t tx_ystart, uint32_t& g_ystart, uint32_t& g_yend, TgOps& out) {
+  out.n = 0;
+  uint32_t i = tx_ystart, exon_sum = 0, ex = e0;
+  while (exon_sum + (TG_LDG(te_end + ex) - TG_LDG(te_start + ex)) <= i) {
+    exon_sum += TG_LDG(te_end + ex) - TG_LDG(te_start + ex);
+    ex++;
+  }
+  g_ystart = TG_LDG(te_start + ex) + (i - exon_sum);
+  for (uint32_t k = 0; k < tx_ops.n; k++) {
+    uint32_t kind = tx_ops.w[k] & 7u, run = tx_ops.w[k] >> 3;
+    bool consumes = kind == TG_OP_MATCH || kind == TG_OP_SUBST || kind == TG_OP_DEL;
+    uint32_t units = (kind <= TG_OP_INS) ? run : 1u;  // a clip is one op
+    while (units > 0) {
+      uint32_t elen = TG_LDG(te_end + ex) - TG_LDG(te_start + ex);
+      if (ex + 1 < e1 && exon_sum + elen <= i) {
+        exon_sum += elen;
+        ex++;
+        tg_ops_push(out, TG_OP_YCLIP, TG_LDG(te_start + ex) - TG_LDG(te_end + ex - 1));
+        elen = TG_LDG(te_end + ex) - TG_LDG(te_start + ex);
+      }
+      if (kind > TG_OP_INS) {  // Xclip
+        tg_ops_push(out, kind, run);
+        units = 0;
+      } else if (!consumes) {
+        tg_ops_push(out, kind, units);
+        units = 0;
+      } else {
+        uint32_t room = (ex + 1 < e1) ? (exon_sum + elen - i) : units;  // units until the next boundary check fires
+        uint32_t take = units < room ? units : room;
+        if (take == 0) take = 1;  // zero-length exon guard (cannot happen for valid GTF)
+        tg_ops_push(out, kind, take);
+        i += take;
+        units -= take;
+      }
+    }
+  }
+  g_yend = TG_LDG(te_start + ex) + (i - exon_sum);
+}
+
+// Candidate record kept per accepted hit (before the end-of-read filters)
+struct TgCand {
+  tg_aln a;           // ops_off / tx_ops_off index the warp's ops arena
+  uint32_t name_rank; // sort key of filter_overlapping
+};
+
+// align_seed_hit (src/aligner.rs:198-314).  Fills `c` and leaves gx ops in gx_ops / tx ops in tx_ops
+// (views into the warp buffers).
+template <class W, int RMAX = 16>
+TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32_t L, uint32_t ref_idx, uint32_t q,
+                              uint32_t len, uint32_t bw, int32_t x_drop, TgCand& c, TgOps& gx_ops, TgOps& tx_ops,
+                              TgCounters& ctr) {
+  const TgIndexDev& ix = P.ix;
+  const int lane = w.lane();
+  uint32_t ref_id = tg_idx_to_ref(ix.refs, ix.n_refs, ref_idx);
+  TgRef aref = ix.refs[ref_id];
+  // genome window (src/aligner.rs:212-215)
+  uint64_t span = (uint64_t)L + bw;
+  uint64_t seq_start = ref_idx > span ? ref_idx - span : 0;
+  if (seq_start < aref.start_idx) seq_start = aref.start_idx;
+  uint64_t seq_end = (uint64_t)ref_idx + len + L + bw;
+  if (seq_end > (uint64_t)aref.end_idx - 1) seq_end = (uint64_t)aref.end_idx - 1;
+  TgAln gx;
+  TgOps A{m.opsA, 0};
+  tg_extend_left_right<W, RMAX>(w, m, ix.text4, seq_start, seq_end, ref_idx, q, len, L, bw, x_drop, gx, A, ctr);
+
+  // transcripts whose exon intersects the SEED (src/aligner.rs:231-258)
+  bool have_tx = false;
+  uint32_t best_tx = 0;
+  TgAln best{0, 0, 0, 0, 0};
+  uint32_t best_tlen = 0;
+  TgOps Bcur{m.opsB, 0}, Bbest{m.opsC, 0};
+  TgTreeIter it;
+  tg_tree_begin(it, ix.exon_nodes, ix.exon_root, m.stack, ref_idx, ref_idx + len);
+  for (;;) {
+    uint32_t tx_idx = 0;
+    int more = 0;
+    if (lane == 0) more = tg_tree_next(it, tx_idx) ? 1 : 0;
+    more = w.shfl(more, 0);
+    if (!more) break;
+    tx_idx = (uint32_t)w.shfl((int)tx_idx, 0);
+    uint32_t e0 = TG_LDG(ix.tx_exon_off + tx_idx), e1 = TG_LDG(ix.tx_exon_off + tx_idx + 1);
+    uint64_t t0 = TG_LDG(ix.tx_seq_off + tx_idx), t1 = TG_LDG(ix.tx_seq_off + tx_idx + 1);
+    uint32_t tlen = (uint32_t)(t1 - t0);
+    uint32_t tr = 0, tq = 0, tl = 0;
+    if (!tg_lift_mem_to_tx(ix.te_start, ix.te_end, e0, e1, ref_idx, q, len, tr, tq, tl)) continue;
+    // extend_seed_match (src/aligner.rs:410-426): right, then left
+    while (tr + tl < tlen && tq + tl < L && tg_code_at(ix.txseq4, t0 + tr + tl) == m.rd[tq + tl]) tl++;
+    while (tr > 0 && tq > 0 && tg_code_at(ix.txseq4, t0 + tr - 1) == m.rd[tq - 1]) { tr--; tq--; tl++; }
+    TgAln ta;
+    tg_extend_left_right<W, RMAX>(w, m, ix.txseq4, t0, t1, t0 + tr, tq, tl, L, bw, x_drop, ta, Bcur, ctr);
+    ta.ystart -= (uint32_t)t0;  // back to transcript coordinates (t0 < 2^32 is checked at index build)
+    ta.yend -= (uint32_t)t0;
+    if (!have_tx || ta.score > best.score) {  // strictly better only: first wins ties (:249)
+      have_tx = true; best = ta; best_tx = tx_idx; best_tlen = tlen;
+      uint32_t* t = Bcur.w; Bcur.w = Bbest.w; Bbest.w = t;
+      Bbest.n = Bcur.n;
+    }
+    if (ta.score >= (int32_t)L) break;  // :253-257
+  }
+
+  tg_aln& a = c.a;
+  a.ref_id = ref_id;
+  a.strand = (uint8_t)(aref.strand_rank & 1u);
+  a.primary = 0; a.pad = 0;
+  a.xlen = L;
+  c.name_rank = aref.strand_rank >> 1;
+  uint32_t ys, ye;
+  if (have_tx && best.score >= gx.score) {  // ties -> Exonic (:263)
+    uint32_t e0 = TG_LDG(ix.tx_exon_off + best_tx), e1 = TG_LDG(ix.tx_exon_off + best_tx + 1);
+    TgOps G{m.opsA, 0};
+    if (lane == 0) tg_lift_tx_to_gx(ix.te_start, ix.te_end, e0, e1, Bbest, best.ystart, ys, ye, G);
+    G.n = (uint32_t)w.shfl((int)G.n, 0);
+    ys = (uint32_t)w.shfl((int)ys, 0);
+    ye = (uint32_t)w.shfl((int)ye, 0);
+    w.sync();
+    a.aln_type = TG_ALN_EXONIC;
+    a.score = best.score; a.xstart = best.xstart; a.xend = best.xend;
+    a.tx_or_gene_idx = best_tx;
+    a.tx_score = best.score; a.tx_ystart = best.ystart; a.tx_yend = best.yend; a.tx_ylen = best_tlen;
+    a.tx_xstart = best.xstart; a.tx_xend = best.xend;
+    gx_ops = G;
+    tx_ops = Bbest;
+  } else {
+    // first gene (in find order) whose span intersects the ALIGNMENT (src/aligner.rs:283-306)
+    uint32_t gene = 0;
+    int found = 0;
+    if (lane == 0) {
+      TgTreeIter gi;
+      tg_tree_begin(gi, ix.gene_nodes, ix.gene_root, m.stack, gx.ystart, gx.yend);
+      found = tg_tree_next(gi, gene) ? 1 : 0;
+    }
+    found = w.shfl(found, 0);
+    gene = (uint32_t)w.shfl((int)gene, 0);
+    a.aln_type = found ? TG_ALN_INTRONIC : TG_ALN_INTERGENIC;
+    a.tx_or_gene_idx = found ? gene : 0xFFFFFFFFu;
+    a.score = gx.score; a.xstart = gx.xstart; a.xend = gx.xend;
+    a.tx_score = 0; a.tx_ystart = 0; a.tx_yend = 0; a.tx_ylen = 0; a.tx_xstart = 0; a.tx_xend = 0;
+    ys = gx.ystart; ye = gx.yend;
+    gx_ops = A;
+    tx_ops = TgOps{m.opsC, 0};
+  }
+  // concat_to_chr_aln (src/aligner.rs:429-449) -- keyed on the alignment's own ystart
+  uint32_t rid2 = tg_idx_to_ref(ix.refs, ix.n_refs, ys);
+  TgRef r2 = ix.refs[rid2];
+  if (r2.strand_rank & 1u) {
+    a.ystart = ys - r2.start_idx;
+    a.yend = ye - r2.start_idx;
+  } else {
+    a.ystart = (uint64_t)r2.len - (ye - r2.start_idx);
+    a.yend = (uint64_t)r2.len - (ys - r2.start_idx);
+    if (lane == 0) tg_ops_reverse(gx_ops);
+    w.sync();
+  }
+  a.ylen = r2.len;
+}
+
+// End-of-read filters on the accepted candidates (src/aligner.rs:177-187 and filter_overlapping :317-349).
+// Serial; `order`/`tmp` are scratch arrays of n entries.  Returns the number of output records; order[0..ret)
+// lists candidate indices in output order.
+TG_HD uint32_t tg_finalize_read(const TgCand* cands, uint32_t n, int32_t max_aln_score, int32_t range,
+                                uint16_t* order, uint16_t* tmp) {
+  // retain (:177-179)
+  uint32_t m = 0;
+  for (uint32_t i = 0; i < n; i++)
+    if (cands[i].a.score >= max_aln_score - range) order[m++] = (uint16_t)i;
+  if (m == 0) return 0;
+  // stable sort by (ref_name, strand false<true, ystart) (:322-327)
+  for (uint32_t i = 1; i < m; i++) {
+    uint16_t cur = order[i];
+    const TgCand& cc = cands[cur];
+    uint32_t j = i;
+    while (j > 0) {
+      const TgCand& p = cands[order[j - 1]];
+      bool greater = p.name_rank > cc.name_rank ||
+                     (p.name_rank == cc.name_rank &&
+                      (p.a.strand > cc.a.strand || (p.a.strand == cc.a.strand && p.a.ystart > cc.a.ystart)));
+      if (!greater) break;
+      order[j] = order[j - 1];
+      j--;
+    }
+    order[j] = cur;
+  }
+  // sweep (:329-346)
+  uint32_t k = 0;
+  uint64_t max_end = 0;
+  for (uint32_t i = 0; i < m; i++) {
+    const TgCand& cc = cands[order[i]];
+    bool fresh = k == 0 || cc.a.ystart >= max_end || cc.name_rank != cands[tmp[k - 1]].name_rank ||
+                 cc.a.strand != cands[tmp[k - 1]].a.strand;
+    if (fresh) {
+      max_end = cc.a.yend;
+      tmp[k++] = order[i];
+    } else {
+      if (cc.a.score > cands[tmp[k - 1]].a.score) tmp[k - 1] = order[i];
+      uint64_t ce = cands[tmp[k - 1]].a.yend;
+      if (ce > max_end) max_end = ce;
+    }
+  }
+  // stable sort by -score (:183)
+  for (uint32_t i = 0; i < k; i++) order[i] = tmp[i];
+  for (uint32_t i = 1; i < k; i++) {
+    uint16_t cur = order[i];
+    int32_t cs = cands[cur].a.score;
+    uint32_t j = i;
+    while (j > 0 && cands[order[j - 1]].a.score < cs) { order[j] = order[j - 1]; j--; }
+    order[j] = cur;
+  }
+  return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-mer table build over the suffix array (one thread per SA row on the device).
+// A row starts a k-mer group when its first k symbols contain no '$' and differ from the previous row's.
+// ------------------------------------------------------------------------------------------------
+TG_HD bool tg_kmer_valid(const uint64_t* text4, uint64_t text_len, uint32_t pos, uint32_t k, uint64_t& w0, uint64_t& w1) {
+  if ((uint64_t)pos + k > text_len) return false;
+  w0 = tg_ld16(text4, pos) & tg_top_nibbles(k);
+  w1 = k > 16 ? (tg_ld16(text4, (uint64_t)pos + 16) & tg_top_nibbles(k - 16)) : 0;
+  // a zero nibble inside the first k symbols is a '$'
+  uint64_t m0 = w0 | ~tg_top_nibbles(k);  // force the unused nibbles non-zero
+  if (tg_has_zero_nibble(m0)) return false;
+  if (k > 16) {
+    uint64_t m1 = w1 | ~tg_top_nibbles(k - 16);
+    if (tg_has_zero_nibble(m1)) return false;
+  }
+  return true;
+}
+// Is SA row r the first row of a valid k-mer group?  If so returns its key words.
+TG_HD bool tg_kmer_group_start(const uint64_t* text4, uint64_t text_len, const uint32_t* sa, uint64_t r, uint32_t k,
+                               uint64_t& w0, uint64_t& w1) {
+  if (!tg_kmer_valid(text4, text_len, TG_LDG(sa + r), k, w0, w1)) return false;
+  if (r == 0) return true;
+  uint64_t p0, p1;
+  if (!tg_kmer_valid(text4, text_len, TG_LDG(sa + r - 1), k, p0, p1)) return true;
+  return p0 != w0 || p1 != w1;
+}
+// number of consecutive rows from r that share the k-mer (galloping + binary search)
+TG_HD uint32_t tg_kmer_group_count(const uint64_t* text4, uint64_t text_len, const uint32_t* sa, uint64_t r, uint32_t k,
+                                   uint64_t w0, uint64_t w1) {
+  auto same = [&](uint64_t row) {
+    uint64_t a0, a1;
+    return tg_kmer_valid(text4, text_len, TG_LDG(sa + row), k, a0, a1) && a0 == w0 && a1 == w1;
+  };
+  uint64_t step = 1, lo = r;  // lo: last row known to match
+  while (r + step < text_len && same(r + step)) { lo = r + step; step <<= 1; }
+  uint64_t hi = r + step < text_len ? r + step : text_len;  // first row known NOT to match (or end)
+  while (lo + 1 < hi) {
+    uint64_t mid = lo + ((hi - lo) >> 1);
+    if (same(mid)) lo = mid; else hi = mid;
+  }
+  return (uint32_t)(lo - r + 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Read-level drivers.  W adds: atomic_add(unsigned long long*, v) and atomic_or(int*, v).
+// ------------------------------------------------------------------------------------------------
+enum { TG_FLAG_SEED_POOL = 1, TG_FLAG_ALN_POOL = 2, TG_FLAG_OPS_POOL = 4, TG_FLAG_READ_CAP = 8, TG_FLAG_ARENA = 16 };
+
+struct TgSeedMem {  // per-warp scratch of the seeding stage
+  uint64_t* rp;       // packed read, (maxL/16 + 3) words
+  TgSeedHit* hits;    // maxL
+  tg_seed* sm;        // maxL
+  uint16_t* grp;      // maxL
+};
+struct TgSeedOut {
+  tg_seed* pool;
+  unsigned long long* pool_used;
+  unsigned long long pool_cap;
+  uint64_t* read_first;
+  uint32_t* read_count;
+  int* flags;
+  unsigned long long* n_smems;
+};
+
+template <class W>
+TG_HDN void tg_seed_read(W& w, TgSeedMem& m, const uint8_t* bases, uint64_t off, uint32_t L, uint32_t k,
+                         const TgSlot* slots, uint64_t slot_mask, const uint64_t* text4, const uint32_t* sa,
+                         const TgSeedOut& out, uint32_t r) {
+  const int lane = w.lane();
+  const uint32_t nw = L / 16 + 3;
+  for (uint32_t wi = lane; wi < nw; wi += W::LANES) {
+    uint64_t word = 0;
+    for (uint32_t t = 0; t < 16; t++) {
+      uint32_t p = wi * 16 + t;
+      uint64_t c = p < L ? tg_ascii_code(TG_LDG(bases + off + p)) : (uint64_t)TG_C_PAD;
+      word |= c << ((15 - t) * 4);
+    }
+    m.rp[wi] = word;
+  }
+  w.sync();
+  for (uint32_t q = lane; q + k <= L; q += W::LANES) {
+    TgSeedHit h;
+    tg_seed_offset(m.rp, L, q, k, slots, slot_mask, text4, sa, h);
+    m.hits[q] = h;
+  }
+  w.sync();
+  int n = 0;
+  if (lane == 0) n = (int)tg_smem_select(m.hits, L, k, m.sm, m.grp);
+  n = w.shfl(n, 0);
+  unsigned long long base = 0;
+  if (lane == 0 && n > 0) base = w.atomic_add(out.pool_used, (unsigned long long)n);
+  base = w.shfl64(base, 0);
+  w.sync();
+  if (base + (unsigned long long)n > out.pool_cap) {
+    if (lane == 0) w.atomic_or(out.flags, TG_FLAG_SEED_POOL);
+    n = 0;
+  }
+  for (int i = lane; i < n; i += W::LANES) out.pool[base + i] = m.sm[i];
+  if (lane == 0) {
+    out.read_first[r] = base;
+    out.read_count[r] = (uint32_t)n;
+    if (n > 0) w.atomic_add(out.n_smems, (unsigned long long)n);
+  }
+  w.sync();
+}
+
+struct TgWarpScratch {  // per-warp global scratch of the extension stage
+  TgCand* cands;       // TG_MAX_ALNS_PER_READ
+  uint32_t* arena;     // ops of the accepted candidates
+  uint32_t arena_cap;
+};
+struct TgAlignOut {
+  uint64_t* read_aln_first;
+  uint32_t* read_aln_count;
+  tg_aln* alns;
+  uint32_t* ops;
+  unsigned long long* alns_used;
+  unsigned long long* ops_used;
+  unsigned long long alns_cap, ops_cap;
+  int* flags;
+};
+
+// align_read (src/aligner.rs:123-190) for one read, seeds already ordered as Index::all_smems orders them.
+template <class W, int RMAX = 16>
+TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint8_t* bases, uint64_t off, uint32_t L,
+                          const tg_seed* seeds, uint32_t n_seeds, const TgWarpScratch& sc, const TgAlignOut& out,
+                          uint32_t r, TgCounters& ctr) {
+  const int lane = w.lane();
+  for (uint32_t i = lane; i < L; i += W::LANES) m.rd[i] = (uint8_t)tg_ascii_code(TG_LDG(bases + off + i));
+  w.sync();
+  // :130-138
+  float prod = P.opts.min_aln_score_percent * (float)L;
+  int32_t pct_score = (int32_t)prod;
+  const int32_t min_aln_score = pct_score > P.opts.min_aln_score ? pct_score : P.opts.min_aln_score;
+  int32_t max_aln_score = min_aln_score;
+  uint32_t bw = (min_aln_score < 0) ? 0u : (L > (uint32_t)min_aln_score ? L - (uint32_t)min_aln_score : 0u);
+  uint32_t x_drop = bw;
+  const int32_t range = (int32_t)P.opts.multimap_score_range;
+  uint32_t n_acc = 0, arena_used = 0;
+  bool capped = false;
+
+  for (uint32_t si = 0; si < n_seeds && !capped; si++) {
+    tg_seed sd = seeds[si];
+    for (uint32_t rk = sd.count; rk-- > 0 && !capped;) {  // reversed SA-rank order (src/index.rs:251-253)
+      uint32_t ref_idx = sd.direct ? sd.sa_lo : TG_LDG(P.ix.sa + sd.sa_lo + rk);
+      if (lane == 0) ctr.hits++;
+      TgCand c;
+      TgOps gx_ops{nullptr, 0}, tx_ops{nullptr, 0};
+      tg_align_seed_hit<W, RMAX>(w, m, P, L, ref_idx, sd.query_idx, sd.len, bw, (int32_t)x_drop, c, gx_ops, tx_ops, ctr);
+      if (!P.opts.intron_mode && c.a.aln_type != TG_ALN_EXONIC) continue;  // :146-151
+      int32_t s = c.a.score;
+      if (s < P.opts.min_aln_score || s < min_aln_score || s < max_aln_score - range) continue;  // :154-159
+      // :162-171 (`score as usize` wraps for negative scores => saturating_sub gives 0)
+      uint32_t lim = (s < 0) ? 0u : ((L + P.opts.multimap_score_range > (uint32_t)s) ? L + P.opts.multimap_score_range - (uint32_t)s : 0u);
+      if (lim < bw) bw = lim;
+      if (lim < x_drop) x_drop = lim;
+      if (s > max_aln_score) max_aln_score = s;
+      // keep the candidate
+      uint32_t need = gx_ops.n + tx_ops.n;
+      if (n_acc >= TG_MAX_ALNS_PER_READ || arena_used + need > sc.arena_cap) {
+        if (lane == 0) w.atomic_or(out.flags, n_acc >= TG_MAX_ALNS_PER_READ ? TG_FLAG_READ_CAP : TG_FLAG_ARENA);
+        capped = true;
+        break;
+      }
+      c.a.ops_off = arena_used; c.a.ops_len = gx_ops.n;
+      c.a.tx_ops_off = arena_used + gx_ops.n; c.a.tx_ops_len = tx_ops.n;
+      for (uint32_t i = lane; i < gx_ops.n; i += W::LANES) sc.arena[arena_used + i] = gx_ops.w[i];
+      for (uint32_t i = lane; i < tx_ops.n; i += W::LANES) sc.arena[arena_used + gx_ops.n + i] = tx_ops.w[i];
+      if (lane == 0) sc.cands[n_acc] = c;
+      arena_used += need;
+      n_acc++;
+      w.sync();
+    }
+  }
+  w.sync_global();
+  // :177-187
+  uint16_t* order = (uint16_t*)m.trace;
+  uint16_t* tmp = order + TG_MAX_ALNS_PER_READ;
+  int k = 0;
+  unsigned long long words = 0;
+  if (lane == 0) {
+    k = (int)tg_finalize_read(sc.cands, n_acc, max_aln_score, range, order, tmp);
+    for (int i = 0; i < k; i++) words += sc.cands[order[i]].a.ops_len + sc.cands[order[i]].a.tx_ops_len;
+  }
+  k = w.shfl(k, 0);
+  words = w.shfl64(words, 0);
+  unsigned long long abase = 0, obase = 0;
+  if (lane == 0 && k > 0) {
+    abase = w.atomic_add(out.alns_used, (unsigned long long)k);
+    obase = w.atomic_add(out.ops_used, words);
+  }
+  abase = w.shfl64(abase, 0);
+  obase = w.shfl64(obase, 0);
+  w.sync();
+  if (abase + (unsigned long long)k > out.alns_cap || obase + words > out.ops_cap || obase + words > 0xFFFFFFFFull) {
+    if (lane == 0) w.atomic_or(out.flags, abase + (unsigned long long)k > out.alns_cap ? TG_FLAG_ALN_POOL : TG_FLAG_OPS_POOL);
+    k = 0;
+  }
+  unsigned long long o = obase;
+  for (int i = 0; i < k; i++) {
+    const TgCand& c = sc.cands[order[i]];
+    uint32_t n1 = c.a.ops_len, n2 = c.a.tx_ops_len, src = c.a.ops_off;
+    for (uint32_t t = lane; t < n1 + n2; t += W::LANES) out.ops[o + t] = sc.arena[src + t];
+    if (lane == 0) {
+      tg_aln a = c.a;
+      a.ops_off = (uint32_t)o;
+      a.tx_ops_off = (uint32_t)(o + n1);
+      if (a.aln_type != TG_ALN_EXONIC) { a.tx_ops_off = 0; a.tx_ops_len = 0; }
+      a.primary = i == 0 ? 1 : 0;
+      out.alns[abase + i] = a;
+    }
+    o += n1 + n2;
+  }
+  if (lane == 0) {
+    out.read_aln_first[r] = abase;
+    out.read_aln_count[r] = (uint32_t)k;
+  }
+  w.sync();
+}

@@ -1,0 +1,86 @@
+// tg_internal.h -- layouts shared by the host index builder, the C ABI glue and the CUDA kernels.
+// Product code: must never include anything from oracle/.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/thermite_gpu.h"
+
+// ------------------------------------------------------------------------------------------------
+// Symbol codes.  Text and transcripts use 0..5 in the byte order of the reference's FM alphabet
+// ("$ACGNT", src/index.rs:108 + the '$' separators of :76,91) so that packed words compare
+// lexicographically.  Reads additionally use 7 for any byte outside ACGNT (matches nothing; the
+// reference's FM index has no such symbol) and 15 as end-of-read padding.
+// ------------------------------------------------------------------------------------------------
+enum : uint8_t { TG_C_SENT = 0, TG_C_A = 1, TG_C_C = 2, TG_C_G = 3, TG_C_N = 4, TG_C_T = 5, TG_C_OTHER = 7, TG_C_PAD = 15 };
+
+// One interval-tree node of the flattened AVL tree (rust-bio IntervalTree shape; src/index.rs:135,182,208).
+// Arrays of these reproduce `find()` by running the same stack DFS on the device.
+struct TgTreeNode {
+  uint32_t start, end, max, data;
+  int32_t left, right;
+};
+
+struct TgRef {
+  uint32_t start_idx, end_idx, len;
+  uint32_t strand_rank;  // bit0 = strand (1 forward), bits 1.. = rank of the name in byte order (filter_overlapping key)
+};
+
+#define TG_BLOB_MAGIC 0x3130424947544854ull /* "THTGIB01" */
+
+// Position-independent header at offset 0 of the index blob.  All off_* are byte offsets from the blob
+// start, 256-byte aligned.
+struct TgBlobHeader {
+  uint64_t magic, nbytes;
+  uint64_t text_len;       // T = 2 * (sum chrom len + n_chrom)
+  uint64_t n_refs, n_txs, n_genes, n_exon_nodes, n_gene_nodes, n_tx_exons, txseq_len;
+  int64_t exon_root, gene_root;
+  uint64_t device_bytes;   // prefix of the blob the GPU needs (everything before the host-only metadata)
+  uint64_t off_text4, off_sa, off_refs, off_exon_nodes, off_gene_nodes, off_tx_seq_off, off_tx_exon_off,
+      off_te_start, off_te_end, off_txseq4;
+  // host-only metadata (string tables: u64 offsets[n+1] followed by bytes)
+  uint64_t off_ref_names, off_tx_ids, off_gene_ids, off_gene_names, off_tx_gene, off_tx_strand;
+  uint64_t reserved[8];
+};
+
+// Device-side view (plain pointers into the device copy of the blob).
+struct TgIndexDev {
+  const uint64_t* text4;
+  const uint32_t* sa;
+  const TgRef* refs;
+  const TgTreeNode* exon_nodes;
+  const TgTreeNode* gene_nodes;
+  const uint64_t* tx_seq_off;
+  const uint32_t* tx_exon_off;
+  const uint32_t* te_start;
+  const uint32_t* te_end;
+  const uint64_t* txseq4;
+  uint64_t text_len;
+  uint32_t n_refs, n_txs;
+  int32_t exon_root, gene_root;
+};
+
+// k-mer table slot (16 B, one 128-bit load).  tag == 0: empty.
+struct TgSlot {
+  uint32_t tag;
+  uint32_t lo;    // first suffix-array row of the k-mer, or the text position itself when count == 1
+  uint32_t count;
+  uint32_t pad;
+};
+
+struct tg_index_host {
+  std::vector<uint8_t> blob;
+  const TgBlobHeader* hdr() const { return (const TgBlobHeader*)blob.data(); }
+  // decoded metadata
+  std::vector<std::string> ref_names, tx_ids, gene_ids, gene_names;
+  std::vector<uint32_t> tx_gene, tx_strand;
+};
+
+void tg_set_error(const std::string& msg);
+tg_status tg_fail(tg_status code, const std::string& msg);
+
+// host_index.cpp
+void tg_sais(const uint8_t* text, size_t n, int32_t* sa);  // plain byte-lexicographic suffix order

@@ -1,0 +1,852 @@
+// thermite_gpu.cu -- CUDA kernels (sm_100a) and the device half of the C ABI of libthermite_gpu.so.
+//
+// Kernels (one warp owns one read / one task from start to finish; warps pull work from a global counter):
+//   k_kmer_count / k_kmer_insert  build the open-addressing k-mer table over the suffix array (ctx create)
+//   k_seed      Index::all_smems           (reference src/index.rs:228-255)      HBM random-access bound
+//   k_extend    align_read hit loop        (src/aligner.rs:123-449, src/swg.rs, src/txome.rs)   INT-pipe bound
+//   k_swg_batch SwgExtend::extend, batched (src/swg.rs:31-207)                   INT-pipe bound
+// The algorithmic code lives in tg_core.h.  No CPU fallback exists: every entry point below needs a device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tg_core.h"
+
+#define TG_FULL 0xffffffffu
+#define TG_WARPS_PER_CTA 4
+
+namespace {
+
+struct DevWarp {
+  static constexpr int LANES = 32;
+  TG_HD int lane() const {
+#ifdef __CUDA_ARCH__
+    return (int)(threadIdx.x & 31);
+#else
+    return 0;
+#endif
+  }
+  TG_HD int shfl_up(int v, int d) {
+#ifdef __CUDA_ARCH__
+    return __shfl_up_sync(TG_FULL, v, d);
+#else
+    return v;
+#endif
+  }
+  TG_HD int shfl(int v, int src) {
+#ifdef __CUDA_ARCH__
+    return __shfl_sync(TG_FULL, v, src);
+#else
+    return v;
+#endif
+  }
+  TG_HD unsigned long long shfl64(unsigned long long v, int src) {
+#ifdef __CUDA_ARCH__
+    return __shfl_sync(TG_FULL, v, src);
+#else
+    return v;
+#endif
+  }
+  TG_HD bool any(bool p) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(TG_FULL, p) != 0;
+#else
+    return p;
+#endif
+  }
+  TG_HD void sync() {
+#ifdef __CUDA_ARCH__
+    __syncwarp();
+#endif
+  }
+  TG_HD void sync_global() {
+#ifdef __CUDA_ARCH__
+    __threadfence_block();
+    __syncwarp();
+#endif
+  }
+  TG_HD unsigned long long atomic_add(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    unsigned long long o = *p; *p += v; return o;
+#endif
+  }
+  TG_HD void atomic_or(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+  }
+};
+
+struct DevCounters {
+  unsigned long long seed_used, n_smems, alns_used, ops_used, cells, n_ext, hits, work_seed, work_ext, swg_ops_used,
+      work_swg, kmer_groups;
+  int flags;
+  int pad;
+};
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(TG_FULL, v, d);
+  return v;
+}
+__device__ __forceinline__ uint32_t next_work(unsigned long long* ctr) {
+  unsigned long long r = 0;
+  if ((threadIdx.x & 31) == 0) r = atomicAdd(ctr, 1ull);
+  return (uint32_t)__shfl_sync(TG_FULL, r, 0);
+}
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// ---------------------------------------------------------------------------------------------------
+// k-mer table build
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_kmer_count(const uint64_t* __restrict__ text4, uint64_t T, const uint32_t* __restrict__ sa, uint32_t k,
+                             DevCounters* ctr) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long local = 0;
+  for (; r < T; r += stride) {
+    uint64_t w0, w1;
+    if (tg_kmer_group_start(text4, T, sa, r, k, w0, w1)) local++;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&ctr->kmer_groups, local);
+}
+
+__global__ void k_kmer_insert(const uint64_t* __restrict__ text4, uint64_t T, const uint32_t* __restrict__ sa, uint32_t k,
+                              TgSlot* slots, uint64_t slot_mask) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; r < T; r += stride) {
+    uint64_t w0, w1;
+    if (!tg_kmer_group_start(text4, T, sa, r, k, w0, w1)) continue;
+    uint32_t cnt = tg_kmer_group_count(text4, T, sa, r, k, w0, w1);
+    uint64_t h = tg_hash_kmer(w0, w1);
+    uint32_t tag = tg_tag_of(h);
+    uint64_t idx = h & slot_mask;
+    for (;;) {
+      uint32_t old = atomicCAS(&slots[idx].tag, 0u, tag);
+      if (old == 0u) {
+        slots[idx].lo = cnt == 1 ? sa[r] : (uint32_t)r;
+        slots[idx].count = cnt;
+        break;
+      }
+      idx = (idx + 1) & slot_mask;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// seeding
+// ---------------------------------------------------------------------------------------------------
+struct SeedParams {
+  const uint8_t* bases;
+  const uint64_t* offs;
+  uint32_t n_reads, k, max_len;
+  const TgSlot* slots;
+  uint64_t slot_mask;
+  const uint64_t* text4;
+  const uint32_t* sa;
+  TgSeedOut out;
+  DevCounters* ctr;
+};
+__host__ __device__ inline size_t seed_smem_per_warp(uint32_t maxL) {
+  return align16((maxL / 16 + 4) * 8) + align16((size_t)(maxL + 1) * sizeof(TgSeedHit)) +
+         align16((size_t)(maxL + 1) * sizeof(tg_seed)) + align16((size_t)(maxL + 1) * 2);
+}
+
+__global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_seed(SeedParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* base = smem + (threadIdx.x >> 5) * seed_smem_per_warp(p.max_len);
+  TgSeedMem m;
+  m.rp = (uint64_t*)base; base += align16((p.max_len / 16 + 4) * 8);
+  m.hits = (TgSeedHit*)base; base += align16((size_t)(p.max_len + 1) * sizeof(TgSeedHit));
+  m.sm = (tg_seed*)base; base += align16((size_t)(p.max_len + 1) * sizeof(tg_seed));
+  m.grp = (uint16_t*)base;
+  DevWarp w;
+  for (;;) {
+    uint32_t r = next_work(&p.ctr->work_seed);
+    if (r >= p.n_reads) break;
+    uint64_t off = p.offs[r];
+    uint32_t L = (uint32_t)(p.offs[r + 1] - off);
+    tg_seed_read<DevWarp>(w, m, p.bases, off, L, p.k, p.slots, p.slot_mask, p.text4, p.sa, p.out, r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// extension
+// ---------------------------------------------------------------------------------------------------
+struct ExtParams {
+  TgAlignParams P;
+  const uint8_t* bases;
+  const uint64_t* offs;
+  uint32_t n_reads, max_len, max_cols, trace_bytes, ops_cap;
+  const tg_seed* seeds;
+  const uint64_t* read_seed_first;
+  const uint32_t* read_seed_count;
+  TgCand* cands;      // [n_warps][TG_MAX_ALNS_PER_READ]
+  uint32_t* arena;    // [n_warps][arena_cap]
+  uint32_t arena_cap;
+  TgAlignOut out;
+  DevCounters* ctr;
+};
+struct ExtSmemLayout {
+  size_t rd, xs, ys, trace, ops, stack, total;
+};
+__host__ __device__ inline ExtSmemLayout ext_smem_layout(uint32_t maxL, uint32_t max_cols, uint32_t trace_bytes, uint32_t ops_cap) {
+  ExtSmemLayout l;
+  size_t o = 0;
+  l.rd = o; o += align16(maxL + 16);
+  l.xs = o; o += align16(maxL + 16);
+  l.ys = o; o += align16(max_cols + 16);
+  l.trace = o; o += align16(trace_bytes);
+  l.ops = o; o += align16((size_t)ops_cap * 4) * 4;
+  l.stack = o; o += align16(TG_TREE_STACK * 4);
+  l.total = o;
+  return l;
+}
+
+template <int RMAX>
+__global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const ExtSmemLayout lay = ext_smem_layout(p.max_len, p.max_cols, p.trace_bytes, p.ops_cap);
+  uint8_t* base = smem + (threadIdx.x >> 5) * lay.total;
+  TgWarpMem m;
+  m.rd = base + lay.rd; m.xs = base + lay.xs; m.ys = base + lay.ys; m.trace = base + lay.trace;
+  const size_t ob = align16((size_t)p.ops_cap * 4);
+  m.opsA = (uint32_t*)(base + lay.ops); m.opsB = (uint32_t*)(base + lay.ops + ob);
+  m.opsC = (uint32_t*)(base + lay.ops + 2 * ob); m.opsT = (uint32_t*)(base + lay.ops + 3 * ob);
+  m.stack = (int32_t*)(base + lay.stack);
+  m.ops_cap = p.ops_cap;
+  const uint32_t gw = blockIdx.x * TG_WARPS_PER_CTA + (threadIdx.x >> 5);
+  TgWarpScratch sc{p.cands + (size_t)gw * TG_MAX_ALNS_PER_READ, p.arena + (size_t)gw * p.arena_cap, p.arena_cap};
+  DevWarp w;
+  TgCounters ctr{0, 0, 0};
+  for (;;) {
+    uint32_t r = next_work(&p.ctr->work_ext);
+    if (r >= p.n_reads) break;
+    uint64_t off = p.offs[r];
+    uint32_t L = (uint32_t)(p.offs[r + 1] - off);
+    tg_align_read<DevWarp, RMAX>(w, m, p.P, p.bases, off, L, p.seeds + p.read_seed_first[r], p.read_seed_count[r], sc, p.out, r, ctr);
+  }
+  unsigned long long c = warp_sum(ctr.cells), e = warp_sum(ctr.n_ext), h = warp_sum(ctr.hits);
+  if ((threadIdx.x & 31) == 0) {
+    if (c) atomicAdd(&p.ctr->cells, c);
+    if (e) atomicAdd(&p.ctr->n_ext, e);
+    if (h) atomicAdd(&p.ctr->hits, h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SWG microbench / batched SwgExtend::extend
+// ---------------------------------------------------------------------------------------------------
+struct SwgParams {
+  const uint8_t* xs; const uint64_t* xoff; const uint8_t* ys; const uint64_t* yoff;
+  uint32_t n;
+  const uint32_t* bw; const int32_t* x_drop;
+  int32_t* score; uint32_t* xend; uint32_t* yend;
+  uint64_t* task_off; uint32_t* task_len;
+  uint32_t* ops; unsigned long long ops_cap;
+  uint32_t max_xlen, max_cols, trace_bytes, ops_words;
+  DevCounters* ctr;
+};
+__host__ __device__ inline size_t swg_smem_per_warp(uint32_t max_xlen, uint32_t max_cols, uint32_t trace_bytes, uint32_t ops_words) {
+  return align16(max_xlen + 16) + align16(max_cols + 16) + align16(trace_bytes) + align16((size_t)ops_words * 4);
+}
+template <int RMAX>
+__global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_swg_batch(SwgParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* base = smem + (threadIdx.x >> 5) * swg_smem_per_warp(p.max_xlen, p.max_cols, p.trace_bytes, p.ops_words);
+  uint8_t* sx = base; base += align16(p.max_xlen + 16);
+  uint8_t* sy = base; base += align16(p.max_cols + 16);
+  uint8_t* trace = base; base += align16(p.trace_bytes);
+  uint32_t* obuf = (uint32_t*)base;
+  DevWarp w;
+  const int lane = threadIdx.x & 31;
+  unsigned long long cells = 0, n_ext = 0;
+  for (;;) {
+    uint32_t t = next_work(&p.ctr->work_swg);
+    if (t >= p.n) break;
+    const uint64_t x0 = p.xoff[t], y0 = p.yoff[t];
+    const int xlen = (int)(p.xoff[t + 1] - x0);
+    const int ylen_full = (int)min((unsigned long long)(p.yoff[t + 1] - y0), 0x7fffffffull);
+    const int bw = (int)p.bw[t];
+    const int ylen = ylen_full > xlen + bw ? xlen + bw + 1 : ylen_full;
+    const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
+    for (int i = lane; i < xlen; i += 32) sx[i] = p.xs[x0 + i];
+    for (int i = lane; i < ncols; i += 32) sy[i] = p.ys[y0 + i];
+    __syncwarp();
+    TgSwgResult res{0, 0, 0};
+    TgOps o{obuf, 0};
+    tg_swg_extend<DevWarp, RMAX>(w, sx, sy, xlen, ylen, bw, p.x_drop[t], trace, res, o, cells, n_ext);
+    unsigned long long dst = 0;
+    if (lane == 0 && o.n) dst = atomicAdd(&p.ctr->swg_ops_used, (unsigned long long)o.n);
+    dst = __shfl_sync(TG_FULL, dst, 0);
+    if (dst + o.n > p.ops_cap) {
+      if (lane == 0) atomicOr(&p.ctr->flags, TG_FLAG_OPS_POOL);
+    } else {
+      for (uint32_t i = lane; i < o.n; i += 32) p.ops[dst + i] = obuf[o.n - 1 - i];  // buffer holds rev(operations)
+    }
+    if (lane == 0) {
+      p.score[t] = res.score; p.xend[t] = (uint32_t)res.xend; p.yend[t] = (uint32_t)res.yend;
+      p.task_off[t] = dst; p.task_len[t] = o.n;
+    }
+    __syncwarp();
+  }
+  cells = warp_sum(cells);
+  n_ext = warp_sum(n_ext);
+  if (lane == 0) {
+    if (cells) atomicAdd(&p.ctr->cells, cells);
+    if (n_ext) atomicAdd(&p.ctr->n_ext, n_ext);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------------------------------
+#define CU_CHECK(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return tg_fail(TG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  tg_status ensure(size_t n) {
+    if (n <= cap) return TG_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return tg_fail(TG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cap = want;
+    return TG_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  tg_status ensure(size_t n) {
+    if (n <= cap) return TG_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) return tg_fail(TG_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    cap = want;
+    return TG_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct tg_index {
+  int device = 0;
+  void* d_blob = nullptr;
+  bool owns = false;
+  TgBlobHeader hdr;
+  TgIndexDev dev;
+};
+
+struct tg_ctx {
+  const tg_index* ix = nullptr;
+  tg_opts opts;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  float last_seed_ms = 0.f, last_extend_ms = 0.f;
+  int n_sms = 0;
+  TgSlot* slots = nullptr;
+  uint64_t n_slots = 0;
+  DevCounters* d_ctr = nullptr;
+  DevCounters* h_ctr = nullptr;  // pinned
+  // inputs
+  DevBuf d_bases, d_offs;
+  // seeding
+  DevBuf d_seeds, d_seed_first, d_seed_count;
+  uint64_t seed_cap = 0;
+  // extension
+  DevBuf d_cands, d_arena, d_aln_first, d_aln_count, d_alns, d_ops;
+  uint64_t alns_cap = 0, ops_cap = 0;
+  uint32_t scratch_warps = 0;
+  // host results
+  PinBuf h_first, h_count, h_alns, h_ops, h_seeds, h_seed_first, h_seed_count;
+  // swg batch
+  DevBuf s_x, s_xo, s_y, s_yo, s_bw, s_xd, s_score, s_xe, s_ye, s_toff, s_tlen, s_ops;
+};
+
+namespace {
+
+tg_status adopt_blob(tg_index* ix, const void* d_blob, size_t nbytes) {
+  TgBlobHeader h;
+  if (nbytes < sizeof(h)) return tg_fail(TG_ERR_INVALID, "index blob too small");
+  CU_CHECK(cudaMemcpy(&h, d_blob, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h.magic != TG_BLOB_MAGIC || h.device_bytes > nbytes) return tg_fail(TG_ERR_INVALID, "not a thermite_gpu index blob");
+  ix->hdr = h;
+  const uint8_t* b = (const uint8_t*)d_blob;
+  TgIndexDev& d = ix->dev;
+  d.text4 = (const uint64_t*)(b + h.off_text4);
+  d.sa = (const uint32_t*)(b + h.off_sa);
+  d.refs = (const TgRef*)(b + h.off_refs);
+  d.exon_nodes = (const TgTreeNode*)(b + h.off_exon_nodes);
+  d.gene_nodes = (const TgTreeNode*)(b + h.off_gene_nodes);
+  d.tx_seq_off = (const uint64_t*)(b + h.off_tx_seq_off);
+  d.tx_exon_off = (const uint32_t*)(b + h.off_tx_exon_off);
+  d.te_start = (const uint32_t*)(b + h.off_te_start);
+  d.te_end = (const uint32_t*)(b + h.off_te_end);
+  d.txseq4 = (const uint64_t*)(b + h.off_txseq4);
+  d.text_len = h.text_len;
+  d.n_refs = (uint32_t)h.n_refs;
+  d.n_txs = (uint32_t)h.n_txs;
+  d.exon_root = (int32_t)h.exon_root;
+  d.gene_root = (int32_t)h.gene_root;
+  return TG_OK;
+}
+
+uint32_t band_for(const tg_opts& o, uint32_t L) {  // src/aligner.rs:130-138
+  float prod = o.min_aln_score_percent * (float)L;
+  int32_t s = (int32_t)prod;
+  if (o.min_aln_score > s) s = o.min_aln_score;
+  if (s < 0) return 0;
+  return L > (uint32_t)s ? L - (uint32_t)s : 0;
+}
+
+tg_status check_flags(int flags) {
+  if (flags & TG_FLAG_READ_CAP)
+    return tg_fail(TG_ERR_CAPACITY, "a read accepted more than TG_MAX_ALNS_PER_READ alignments");
+  if (flags & TG_FLAG_ARENA) return tg_fail(TG_ERR_CAPACITY, "per-read operation arena exhausted");
+  return TG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+tg_status tg_index_create(const tg_index_host* hix, int device, tg_index** out) {
+  if (!hix || !out) return tg_fail(TG_ERR_INVALID, "null argument");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return tg_fail(TG_ERR_CUDA, "no CUDA device: libthermite_gpu has no CPU fallback");
+  CU_CHECK(cudaSetDevice(device));
+  auto* ix = new tg_index();
+  ix->device = device;
+  size_t nb = hix->hdr()->device_bytes;
+  cudaError_t e = cudaMalloc(&ix->d_blob, nb);
+  if (e != cudaSuccess) { delete ix; return tg_fail(TG_ERR_CUDA, std::string("cudaMalloc(index): ") + cudaGetErrorString(e)); }
+  ix->owns = true;
+  e = cudaMemcpy(ix->d_blob, hix->blob.data(), nb, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(ix->d_blob); delete ix; return tg_fail(TG_ERR_CUDA, std::string("cudaMemcpy(index): ") + cudaGetErrorString(e)); }
+  tg_status st = adopt_blob(ix, ix->d_blob, nb);
+  if (st != TG_OK) { cudaFree(ix->d_blob); delete ix; return st; }
+  *out = ix;
+  return TG_OK;
+}
+
+tg_status tg_index_create_from_device_blob(const void* device_blob, size_t nbytes, int device, tg_index** out) {
+  if (!device_blob || !out) return tg_fail(TG_ERR_INVALID, "null argument");
+  CU_CHECK(cudaSetDevice(device));
+  auto* ix = new tg_index();
+  ix->device = device;
+  ix->d_blob = const_cast<void*>(device_blob);
+  ix->owns = false;
+  tg_status st = adopt_blob(ix, device_blob, nbytes);
+  if (st != TG_OK) { delete ix; return st; }
+  *out = ix;
+  return TG_OK;
+}
+
+void tg_index_destroy(tg_index* ix) {
+  if (!ix) return;
+  if (ix->owns && ix->d_blob) { cudaSetDevice(ix->device); cudaFree(ix->d_blob); }
+  delete ix;
+}
+
+void tg_ctx_destroy(tg_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->ix->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_cands, &c->d_arena,
+                    &c->d_aln_first, &c->d_aln_count, &c->d_alns, &c->d_ops, &c->s_x, &c->s_xo, &c->s_y, &c->s_yo, &c->s_bw,
+                    &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops})
+    b->release();
+  for (PinBuf* b : {&c->h_first, &c->h_count, &c->h_alns, &c->h_ops, &c->h_seeds, &c->h_seed_first, &c->h_seed_count}) b->release();
+  if (c->slots) cudaFree(c->slots);
+  if (c->d_ctr) cudaFree(c->d_ctr);
+  if (c->h_ctr) cudaFreeHost(c->h_ctr);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev2) cudaEventDestroy(c->ev2);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
+  if (!ix || !opts || !out) return tg_fail(TG_ERR_INVALID, "null argument");
+  if (opts->min_seed_len < 1 || opts->min_seed_len > TG_MAX_SEED_LEN)
+    return tg_fail(TG_ERR_INVALID, "min_seed_len must be in [1, TG_MAX_SEED_LEN]");
+  if (!(opts->min_aln_score_percent >= 0.0f && opts->min_aln_score_percent <= 1.0f))
+    return tg_fail(TG_ERR_INVALID, "Min alignment score percent must be between 0.0 and 1.0!");  // src/main.rs:46-49
+  CU_CHECK(cudaSetDevice(ix->device));
+  auto* c = new tg_ctx();
+  c->ix = ix;
+  c->opts = *opts;
+  auto fail = [&](tg_status s) { tg_ctx_destroy(c); return s; };
+#define CTX_CHECK(call)                                                                                        \
+  do {                                                                                                         \
+    cudaError_t e_ = (call);                                                                                   \
+    if (e_ != cudaSuccess) return fail(tg_fail(TG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
+  } while (0)
+  CTX_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CTX_CHECK(cudaEventCreate(&c->ev0));
+  CTX_CHECK(cudaEventCreate(&c->ev1));
+  CTX_CHECK(cudaEventCreate(&c->ev2));
+  CTX_CHECK(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, ix->device));
+  CTX_CHECK(cudaMalloc(&c->d_ctr, sizeof(DevCounters)));
+  CTX_CHECK(cudaMallocHost(&c->h_ctr, sizeof(DevCounters)));
+  CTX_CHECK(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+  // k-mer table for this min_seed_len, built on the device from the suffix array
+  const uint64_t T = ix->dev.text_len;
+  const int threads = 256;
+  const int blocks = (int)std::min<uint64_t>((T + threads - 1) / threads, (uint64_t)c->n_sms * 32);
+  k_kmer_count<<<blocks, threads, 0, c->stream>>>(ix->dev.text4, T, ix->dev.sa, opts->min_seed_len, c->d_ctr);
+  CTX_CHECK(cudaGetLastError());
+  CTX_CHECK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  CTX_CHECK(cudaStreamSynchronize(c->stream));
+  uint64_t groups = c->h_ctr->kmer_groups;
+  uint64_t n_slots = 1024;
+  while (n_slots < 2 * groups + 2) n_slots <<= 1;
+  c->n_slots = n_slots;
+  CTX_CHECK(cudaMalloc(&c->slots, n_slots * sizeof(TgSlot)));
+  CTX_CHECK(cudaMemsetAsync(c->slots, 0, n_slots * sizeof(TgSlot), c->stream));
+  k_kmer_insert<<<blocks, threads, 0, c->stream>>>(ix->dev.text4, T, ix->dev.sa, opts->min_seed_len, c->slots, n_slots - 1);
+  CTX_CHECK(cudaGetLastError());
+  CTX_CHECK(cudaStreamSynchronize(c->stream));
+#undef CTX_CHECK
+  *out = c;
+  return TG_OK;
+}
+
+void* tg_ctx_stream(tg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms) {
+  if (seed_ms) *seed_ms = ctx ? ctx->last_seed_ms : 0.f;
+  if (extend_ms) *extend_ms = ctx ? ctx->last_extend_ms : 0.f;
+}
+uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots * sizeof(TgSlot) : 0; }
+
+}  // extern "C"
+
+namespace {
+
+tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL) {
+  size_t per_warp = seed_smem_per_warp(maxL);
+  size_t smem = per_warp * TG_WARPS_PER_CTA;
+  CU_CHECK(cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_seed, TG_WARPS_PER_CTA * 32, smem));
+  if (occ < 1) return tg_fail(TG_ERR_CAPACITY, "seed kernel does not fit in shared memory");
+  int blocks = (int)std::min<uint64_t>((uint64_t)c->n_sms * occ, ((uint64_t)n + TG_WARPS_PER_CTA - 1) / TG_WARPS_PER_CTA);
+  if (blocks < 1) blocks = 1;
+  SeedParams p;
+  p.bases = d_bases; p.offs = d_offs; p.n_reads = n; p.k = c->opts.min_seed_len; p.max_len = maxL;
+  p.slots = c->slots; p.slot_mask = c->n_slots - 1; p.text4 = c->ix->dev.text4; p.sa = c->ix->dev.sa;
+  p.out.pool = (tg_seed*)c->d_seeds.p; p.out.pool_used = &c->d_ctr->seed_used; p.out.pool_cap = c->seed_cap;
+  p.out.read_first = (uint64_t*)c->d_seed_first.p; p.out.read_count = (uint32_t*)c->d_seed_count.p;
+  p.out.flags = &c->d_ctr->flags; p.out.n_smems = &c->d_ctr->n_smems;
+  p.ctr = c->d_ctr;
+  k_seed<<<blocks, TG_WARPS_PER_CTA * 32, smem, c->stream>>>(p);
+  CU_CHECK(cudaGetLastError());
+  return TG_OK;
+}
+
+tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL) {
+  uint32_t max_bw = band_for(c->opts, maxL);
+  uint32_t max_xlen = maxL > 0 ? maxL - 1 : 0;
+  uint32_t max_cols = max_xlen + max_bw + 1;
+  uint32_t trace_bytes = max_cols * (uint32_t)tg_trace_bytes_per_col((int)max_xlen, 32);
+  if (trace_bytes < 4 * TG_MAX_ALNS_PER_READ) trace_bytes = 4 * TG_MAX_ALNS_PER_READ;
+  uint32_t ops_cap = 2 * maxL + max_bw + 16;
+  ExtSmemLayout lay = ext_smem_layout(maxL, max_cols, trace_bytes, ops_cap);
+  size_t smem = lay.total * TG_WARPS_PER_CTA;
+  if (smem > 227 * 1024) return tg_fail(TG_ERR_CAPACITY, "reads too long for the extension kernel's shared memory");
+  const int rcls = tg_swg_rows_class((int)max_xlen, 32);
+  void (*kern)(ExtParams) = rcls <= 3 ? k_extend<3> : rcls <= 6 ? k_extend<6> : k_extend<16>;
+  CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TG_WARPS_PER_CTA * 32, smem));
+  if (occ < 1) return tg_fail(TG_ERR_CAPACITY, "extension kernel does not fit in shared memory");
+  int blocks = (int)std::min<uint64_t>((uint64_t)c->n_sms * occ, ((uint64_t)n + TG_WARPS_PER_CTA - 1) / TG_WARPS_PER_CTA);
+  if (blocks < 1) blocks = 1;
+  uint32_t warps = (uint32_t)blocks * TG_WARPS_PER_CTA;
+  const uint32_t arena_cap = 32768;
+  if (warps > c->scratch_warps) {
+    tg_status st = c->d_cands.ensure((size_t)warps * TG_MAX_ALNS_PER_READ * sizeof(TgCand));
+    if (st != TG_OK) return st;
+    st = c->d_arena.ensure((size_t)warps * arena_cap * 4);
+    if (st != TG_OK) return st;
+    c->scratch_warps = warps;
+  }
+  ExtParams p;
+  p.P.ix = c->ix->dev; p.P.opts = c->opts;
+  p.bases = d_bases; p.offs = d_offs; p.n_reads = n; p.max_len = maxL; p.max_cols = max_cols; p.trace_bytes = trace_bytes;
+  p.ops_cap = ops_cap;
+  p.seeds = (const tg_seed*)c->d_seeds.p; p.read_seed_first = (const uint64_t*)c->d_seed_first.p;
+  p.read_seed_count = (const uint32_t*)c->d_seed_count.p;
+  p.cands = (TgCand*)c->d_cands.p; p.arena = (uint32_t*)c->d_arena.p; p.arena_cap = arena_cap;
+  p.out.read_aln_first = (uint64_t*)c->d_aln_first.p; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p;
+  p.out.alns = (tg_aln*)c->d_alns.p; p.out.ops = (uint32_t*)c->d_ops.p;
+  p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;
+  p.out.alns_cap = c->alns_cap; p.out.ops_cap = c->ops_cap; p.out.flags = &c->d_ctr->flags;
+  p.ctr = c->d_ctr;
+  kern<<<blocks, TG_WARPS_PER_CTA * 32, smem, c->stream>>>(p);
+  CU_CHECK(cudaGetLastError());
+  return TG_OK;
+}
+
+tg_status ensure_pools(tg_ctx* c, uint32_t n) {
+  if (c->seed_cap < (uint64_t)n * 4 + 4096) c->seed_cap = (uint64_t)n * 4 + 4096;
+  if (c->alns_cap < (uint64_t)n * 2 + 4096) c->alns_cap = (uint64_t)n * 2 + 4096;
+  if (c->ops_cap < (uint64_t)n * 24 + 65536) c->ops_cap = (uint64_t)n * 24 + 65536;
+  tg_status st;
+  if ((st = c->d_seeds.ensure(c->seed_cap * sizeof(tg_seed))) != TG_OK) return st;
+  if ((st = c->d_seed_first.ensure((size_t)n * 8 + 8)) != TG_OK) return st;
+  if ((st = c->d_seed_count.ensure((size_t)n * 4 + 4)) != TG_OK) return st;
+  if ((st = c->d_aln_first.ensure((size_t)n * 8 + 8)) != TG_OK) return st;
+  if ((st = c->d_aln_count.ensure((size_t)n * 4 + 4)) != TG_OK) return st;
+  if ((st = c->d_alns.ensure(c->alns_cap * sizeof(tg_aln))) != TG_OK) return st;
+  if ((st = c->d_ops.ensure(c->ops_cap * 4)) != TG_OK) return st;
+  return TG_OK;
+}
+
+// seeds (+ optionally extension) with pool-overflow retry; leaves the counters in c->h_ctr
+tg_status run_pipeline(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL, bool extend) {
+  for (int attempt = 0; attempt < 8; attempt++) {
+    tg_status st = ensure_pools(c, n);
+    if (st != TG_OK) return st;
+    CU_CHECK(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+    CU_CHECK(cudaEventRecord(c->ev0, c->stream));
+    if ((st = launch_seed(c, d_bases, d_offs, n, maxL)) != TG_OK) return st;
+    CU_CHECK(cudaEventRecord(c->ev1, c->stream));
+    if (extend && (st = launch_extend(c, d_bases, d_offs, n, maxL)) != TG_OK) return st;
+    CU_CHECK(cudaEventRecord(c->ev2, c->stream));
+    CU_CHECK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    CU_CHECK(cudaEventElapsedTime(&c->last_seed_ms, c->ev0, c->ev1));
+    CU_CHECK(cudaEventElapsedTime(&c->last_extend_ms, c->ev1, c->ev2));
+    int f = c->h_ctr->flags;
+    if (f & (TG_FLAG_SEED_POOL | TG_FLAG_ALN_POOL | TG_FLAG_OPS_POOL)) {  // grow the pool that overflowed and redo the batch
+      if (f & TG_FLAG_SEED_POOL) c->seed_cap = std::max<uint64_t>(c->seed_cap * 2, c->h_ctr->seed_used + 4096);
+      if (f & TG_FLAG_ALN_POOL) c->alns_cap = std::max<uint64_t>(c->alns_cap * 2, c->h_ctr->alns_used + 4096);
+      if (f & TG_FLAG_OPS_POOL) c->ops_cap = std::max<uint64_t>(c->ops_cap * 2, c->h_ctr->ops_used + 4096);
+      continue;
+    }
+    return check_flags(f);
+  }
+  return tg_fail(TG_ERR_CAPACITY, "result pools kept overflowing");
+}
+
+tg_status check_batch_args(tg_ctx* ctx, const void* a, const void* b, const void* out) {
+  if (!ctx || !out || !a || !b) return tg_fail(TG_ERR_INVALID, "null argument");
+  cudaError_t e = cudaSetDevice(ctx->ix->device);
+  if (e != cudaSuccess) return tg_fail(TG_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  return TG_OK;
+}
+
+tg_status upload_reads(tg_ctx* c, const uint8_t* bases, const uint64_t* offs, uint32_t n, uint32_t* maxL_out) {
+  uint32_t maxL = 0;
+  for (uint32_t r = 0; r < n; r++) {
+    if (offs[r + 1] < offs[r]) return tg_fail(TG_ERR_INVALID, "read offsets must be non-decreasing");
+    uint64_t L = offs[r + 1] - offs[r];
+    if (L > TG_MAX_READ_LEN) return tg_fail(TG_ERR_INVALID, "read longer than TG_MAX_READ_LEN");
+    if (L > maxL) maxL = (uint32_t)L;
+  }
+  uint64_t total = offs[n];
+  tg_status st;
+  if ((st = c->d_bases.ensure(total + 64)) != TG_OK) return st;
+  if ((st = c->d_offs.ensure((size_t)(n + 1) * 8)) != TG_OK) return st;
+  if (total) CU_CHECK(cudaMemcpyAsync(c->d_bases.p, bases, total, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaMemcpyAsync(c->d_offs.p, offs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  *maxL_out = maxL;
+  return TG_OK;
+}
+
+void fill_result(tg_ctx* c, uint32_t n, tg_result* out) {
+  out->n_reads = n;
+  out->n_alns = c->h_ctr->alns_used;
+  out->n_ops = c->h_ctr->ops_used;
+  out->swg_cells = c->h_ctr->cells;
+  out->swg_extensions = c->h_ctr->n_ext;
+  out->seed_hits = c->h_ctr->hits;
+  out->n_smems = c->h_ctr->n_smems;
+}
+
+}  // namespace
+
+extern "C" {
+
+tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n_reads,
+                                uint64_t total_bases, uint32_t max_read_len, tg_result* out) {
+  tg_status st = check_batch_args(ctx, d_bases, d_offs, out);
+  if (st != TG_OK) return st;
+  (void)total_bases;
+  if (max_read_len > TG_MAX_READ_LEN) return tg_fail(TG_ERR_INVALID, "read longer than TG_MAX_READ_LEN");
+  memset(out, 0, sizeof(*out));
+  if (n_reads == 0) return TG_OK;
+  if ((st = run_pipeline(ctx, d_bases, d_offs, n_reads, std::max(max_read_len, 1u), true)) != TG_OK) return st;
+  fill_result(ctx, n_reads, out);
+  out->read_aln_first = (const uint64_t*)ctx->d_aln_first.p;
+  out->read_aln_count = (const uint32_t*)ctx->d_aln_count.p;
+  out->alns = (const tg_aln*)ctx->d_alns.p;
+  out->ops = (const uint32_t*)ctx->d_ops.p;
+  return TG_OK;
+}
+
+tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_result* out) {
+  tg_status st = check_batch_args(ctx, offs, offs, out);
+  if (st != TG_OK) return st;
+  memset(out, 0, sizeof(*out));
+  if (n_reads == 0) return TG_OK;
+  if (!bases && offs[n_reads] > 0) return tg_fail(TG_ERR_INVALID, "null argument");
+  uint32_t maxL = 0;
+  if ((st = upload_reads(ctx, bases, offs, n_reads, &maxL)) != TG_OK) return st;
+  if ((st = run_pipeline(ctx, (const uint8_t*)ctx->d_bases.p, (const uint64_t*)ctx->d_offs.p, n_reads, std::max(maxL, 1u), true)) != TG_OK)
+    return st;
+  fill_result(ctx, n_reads, out);
+  if ((st = ctx->h_first.ensure((size_t)n_reads * 8)) != TG_OK) return st;
+  if ((st = ctx->h_count.ensure((size_t)n_reads * 4)) != TG_OK) return st;
+  if ((st = ctx->h_alns.ensure((size_t)out->n_alns * sizeof(tg_aln) + 16)) != TG_OK) return st;
+  if ((st = ctx->h_ops.ensure((size_t)out->n_ops * 4 + 16)) != TG_OK) return st;
+  CU_CHECK(cudaMemcpyAsync(ctx->h_first.p, ctx->d_aln_first.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(cudaMemcpyAsync(ctx->h_count.p, ctx->d_aln_count.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out->n_alns)
+    CU_CHECK(cudaMemcpyAsync(ctx->h_alns.p, ctx->d_alns.p, (size_t)out->n_alns * sizeof(tg_aln), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out->n_ops)
+    CU_CHECK(cudaMemcpyAsync(ctx->h_ops.p, ctx->d_ops.p, (size_t)out->n_ops * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(cudaStreamSynchronize(ctx->stream));
+  out->read_aln_first = (const uint64_t*)ctx->h_first.p;
+  out->read_aln_count = (const uint32_t*)ctx->h_count.p;
+  out->alns = (const tg_aln*)ctx->h_alns.p;
+  out->ops = (const uint32_t*)ctx->h_ops.p;
+  return TG_OK;
+}
+
+tg_status tg_seed_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_seed_result* out) {
+  tg_status st = check_batch_args(ctx, offs, offs, out);
+  if (st != TG_OK) return st;
+  memset(out, 0, sizeof(*out));
+  if (n_reads == 0) return TG_OK;
+  if (!bases && offs[n_reads] > 0) return tg_fail(TG_ERR_INVALID, "null argument");
+  uint32_t maxL = 0;
+  if ((st = upload_reads(ctx, bases, offs, n_reads, &maxL)) != TG_OK) return st;
+  if ((st = run_pipeline(ctx, (const uint8_t*)ctx->d_bases.p, (const uint64_t*)ctx->d_offs.p, n_reads, std::max(maxL, 1u), false)) != TG_OK)
+    return st;
+  uint64_t ns = ctx->h_ctr->seed_used;
+  if ((st = ctx->h_seed_first.ensure((size_t)n_reads * 8)) != TG_OK) return st;
+  if ((st = ctx->h_seed_count.ensure((size_t)n_reads * 4)) != TG_OK) return st;
+  if ((st = ctx->h_seeds.ensure((size_t)ns * sizeof(tg_seed) + 16)) != TG_OK) return st;
+  CU_CHECK(cudaMemcpyAsync(ctx->h_seed_first.p, ctx->d_seed_first.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(cudaMemcpyAsync(ctx->h_seed_count.p, ctx->d_seed_count.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ns) CU_CHECK(cudaMemcpyAsync(ctx->h_seeds.p, ctx->d_seeds.p, (size_t)ns * sizeof(tg_seed), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(cudaStreamSynchronize(ctx->stream));
+  out->n_reads = n_reads;
+  out->n_seeds = ns;
+  out->read_seed_first = (const uint64_t*)ctx->h_seed_first.p;
+  out->read_seed_count = (const uint32_t*)ctx->h_seed_count.p;
+  out->seeds = (const tg_seed*)ctx->h_seeds.p;
+  return TG_OK;
+}
+
+tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff, const uint8_t* ys, const uint64_t* yoff,
+                              uint32_t n, const uint32_t* band_width, const int32_t* x_drop, int32_t* score, uint32_t* xend,
+                              uint32_t* yend, uint64_t* ops_off, uint32_t* ops, uint64_t ops_cap, uint64_t* cells,
+                              float* kernel_ms) {
+  if (!c || !xoff || !yoff || !band_width || !x_drop || !score || !xend || !yend || !ops_off)
+    return tg_fail(TG_ERR_INVALID, "null argument");
+  CU_CHECK(cudaSetDevice(c->ix->device));
+  if (cells) *cells = 0;
+  if (kernel_ms) *kernel_ms = 0.f;
+  if (n == 0) { ops_off[0] = 0; return TG_OK; }
+  uint32_t max_xlen = 0, max_cols = 1;
+  uint64_t worst_ops = 0;
+  for (uint32_t t = 0; t < n; t++) {
+    uint64_t xl = xoff[t + 1] - xoff[t], yl = yoff[t + 1] - yoff[t];
+    if (xl > TG_MAX_READ_LEN) return tg_fail(TG_ERR_INVALID, "x longer than TG_MAX_READ_LEN");
+    if (band_width[t] > 2 * TG_MAX_READ_LEN) return tg_fail(TG_ERR_INVALID, "band width too large");
+    if (x_drop[t] < (int32_t)band_width[t])
+      return tg_fail(TG_ERR_INVALID, "x_drop < band_width: the reference reads stale columns or panics there (unsupported)");
+    uint64_t cols = std::min<uint64_t>(yl, xl + band_width[t]);
+    max_xlen = std::max<uint32_t>(max_xlen, (uint32_t)xl);
+    max_cols = std::max<uint32_t>(max_cols, (uint32_t)cols);
+    worst_ops += xl + cols + 2;
+  }
+  uint32_t trace_bytes = (max_cols + 1) * (uint32_t)tg_trace_bytes_per_col((int)max_xlen, 32);
+  uint32_t ops_words = max_xlen + max_cols + 8;
+  size_t smem = swg_smem_per_warp(max_xlen, max_cols, trace_bytes, ops_words) * TG_WARPS_PER_CTA;
+  if (smem > 227 * 1024) return tg_fail(TG_ERR_CAPACITY, "sequences too long for the SWG kernel's shared memory");
+  tg_status st;
+  uint64_t nx = xoff[n], ny = yoff[n];
+#define ENS(buf, bytes) if ((st = c->buf.ensure(bytes)) != TG_OK) return st
+  ENS(s_x, nx + 64); ENS(s_xo, (size_t)(n + 1) * 8); ENS(s_y, ny + 64); ENS(s_yo, (size_t)(n + 1) * 8);
+  ENS(s_bw, (size_t)n * 4); ENS(s_xd, (size_t)n * 4); ENS(s_score, (size_t)n * 4); ENS(s_xe, (size_t)n * 4);
+  ENS(s_ye, (size_t)n * 4); ENS(s_toff, (size_t)n * 8); ENS(s_tlen, (size_t)n * 4); ENS(s_ops, worst_ops * 4 + 64);
+#undef ENS
+  if (nx) CU_CHECK(cudaMemcpyAsync(c->s_x.p, xs, nx, cudaMemcpyHostToDevice, c->stream));
+  if (ny) CU_CHECK(cudaMemcpyAsync(c->s_y.p, ys, ny, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaMemcpyAsync(c->s_xo.p, xoff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaMemcpyAsync(c->s_yo.p, yoff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaMemcpyAsync(c->s_bw.p, band_width, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaMemcpyAsync(c->s_xd.p, x_drop, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+  const int rcls = tg_swg_rows_class((int)max_xlen, 32);
+  void (*kern)(SwgParams) = rcls <= 3 ? k_swg_batch<3> : rcls <= 6 ? k_swg_batch<6> : k_swg_batch<16>;
+  CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TG_WARPS_PER_CTA * 32, smem));
+  if (occ < 1) return tg_fail(TG_ERR_CAPACITY, "SWG kernel does not fit in shared memory");
+  int blocks = (int)std::min<uint64_t>((uint64_t)c->n_sms * occ, ((uint64_t)n + TG_WARPS_PER_CTA - 1) / TG_WARPS_PER_CTA);
+  SwgParams p;
+  p.xs = (const uint8_t*)c->s_x.p; p.xoff = (const uint64_t*)c->s_xo.p; p.ys = (const uint8_t*)c->s_y.p; p.yoff = (const uint64_t*)c->s_yo.p;
+  p.n = n; p.bw = (const uint32_t*)c->s_bw.p; p.x_drop = (const int32_t*)c->s_xd.p;
+  p.score = (int32_t*)c->s_score.p; p.xend = (uint32_t*)c->s_xe.p; p.yend = (uint32_t*)c->s_ye.p;
+  p.task_off = (uint64_t*)c->s_toff.p; p.task_len = (uint32_t*)c->s_tlen.p; p.ops = (uint32_t*)c->s_ops.p; p.ops_cap = worst_ops;
+  p.max_xlen = max_xlen; p.max_cols = max_cols; p.trace_bytes = trace_bytes; p.ops_words = ops_words; p.ctr = c->d_ctr;
+  CU_CHECK(cudaEventRecord(c->ev0, c->stream));
+  kern<<<blocks, TG_WARPS_PER_CTA * 32, smem, c->stream>>>(p);
+  CU_CHECK(cudaGetLastError());
+  CU_CHECK(cudaEventRecord(c->ev1, c->stream));
+  CU_CHECK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaMemcpyAsync(score, c->s_score.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaMemcpyAsync(xend, c->s_xe.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaMemcpyAsync(yend, c->s_ye.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  if (c->h_ctr->flags) return tg_fail(TG_ERR_INTERNAL, "SWG ops pool overflow");
+  if (kernel_ms) CU_CHECK(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+  if (cells) *cells = c->h_ctr->cells;
+  // reorder the ops pool into task order on the host
+  uint64_t used = c->h_ctr->swg_ops_used;
+  std::vector<uint64_t> toff(n);
+  std::vector<uint32_t> tlen(n), pool(used);
+  CU_CHECK(cudaMemcpy(toff.data(), c->s_toff.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  CU_CHECK(cudaMemcpy(tlen.data(), c->s_tlen.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (used) CU_CHECK(cudaMemcpy(pool.data(), c->s_ops.p, used * 4, cudaMemcpyDeviceToHost));
+  uint64_t o = 0;
+  for (uint32_t t = 0; t < n; t++) {
+    ops_off[t] = o;
+    if (ops && o + tlen[t] <= ops_cap) memcpy(ops + o, pool.data() + toff[t], (size_t)tlen[t] * 4);
+    o += tlen[t];
+  }
+  ops_off[n] = o;
+  if (ops && o > ops_cap) return tg_fail(TG_ERR_CAPACITY, "ops buffer too small");
+  return TG_OK;
+}
+
+}  // extern "C"
