@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s of the B200 alignment hot path on the chr21 stand-in workload (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path (seeding -> hit loop with banded SWG -> lifting -> filters) over one batch of
+synthetic 10x-R2-shaped reads per GPU.  Reads shard across ranks with no data-path collective (weak scaling);
+the only collective is the NCCL broadcast of the flat index at start-up.
+
+Rank 0 prints ONE JSON line.  `value` = reads/s with inputs resident in HBM; `e2e` = the same through
+tg_align_batch with pinned HOST buffers (H2D + kernels + D2H inside the timed region); `roofline` describes the
+dominant kernel; `cpu_baseline` is the CPU oracle (a C++ restatement of thermite's CPU path -- the Rust reference
+cannot be built in this image) timed on the box's host cores on a bounded sample of the same workload.
+`--impl reference` times that CPU restatement as its own arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLAGS = dict(k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True)  # data/Makefile:39  -k20 -s0 --intron-mode
+READ_LEN = 91
+SEEDS = dict(genome=20212, reads=20213)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="genome scale (1.0 = chr21-sized stand-in)")
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per step per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline work per step (all threads)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(scale):
+    base = "synth21-91bp: synthetic chr21 stand-in (46,709,983 bp, N blocks, repeat families, poly-A runs; GTF 800 genes) " \
+           "vs 10x-R2-shaped reads, flags -k20 -s0 --intron-mode"
+    return base if scale == 1.0 else base + f" [genome scale {scale}]"
+
+
+def make_world(scale):
+    from thermite_b200 import synth
+    contigs, gtf, txs = synth.synth21(scale, SEEDS["genome"])
+    return contigs, gtf, txs, synth.fasta_bytes(contigs)
+
+
+def make_reads(contigs, txs, n, seed):
+    from thermite_b200 import synth
+    return synth.make_reads(seed, contigs, txs, n, L=READ_LEN, frac_tx=0.8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            load = [v for v in sm if v >= 0.5 * max(sm)] or sm
+            out = dict(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, streaming copy)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def seed_algorithmic_bytes(n_reads, L, k, hits):
+    # sector-granular  32*(ceil(L/128) + (L-k+1) + 2H) + 8H  per read, H = Mems handed to align_seed_hit
+    return 32 * (n_reads * (-(-L // 128) + (L - k + 1)) + 2 * hits) + 8 * hits
+
+
+def cpu_baseline(fa, gtf, bases, offs, cpu_seconds, threads):
+    """Oracle (C++ port of thermite's CPU path) on a bounded sample of the same reads."""
+    from oracle import orc
+    t0 = time.time()
+    oix = orc.Index.create(fa, gtf)
+    build_s = time.time() - t0
+    probe = 2000
+    r = oix.align_batch(bases[: int(offs[probe])], offs[: probe + 1], n_threads=1, **_orc_flags())
+    rate1 = probe / max(r.seconds, 1e-9)
+    n = int(min(len(offs) - 1, max(probe, rate1 * cpu_seconds * max(1, threads) * 0.6)))
+    r = oix.align_batch(bases[: int(offs[n])], offs[: n + 1], n_threads=threads, **_orc_flags())
+    return dict(value=n / r.seconds, unit="reads/s", cores=threads, kind="port",
+                sample=f"first {n} reads of the step batch, {threads} host threads over contiguous shards "
+                       f"(single thread: {rate1:.0f} reads/s on {probe} reads); oracle index build {build_s:.0f}s not timed",
+                single_thread_reads_per_s=rate1), oix
+
+
+def _orc_flags():
+    return dict(k=FLAGS["k"], pct=FLAGS["pct"], min_score=FLAGS["min_score"], score_range=FLAGS["score_range"],
+                intron_mode=FLAGS["intron_mode"])
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores, same workload/metric."""
+    if rank != 0:
+        return
+    from oracle import orc
+    threads = os.cpu_count() or 1
+    contigs, gtf, txs, fa = make_world(args.scale)
+    bases, offs = make_reads(contigs, txs, min(args.reads, 400_000), SEEDS["reads"])
+    oix = orc.Index.create(fa, gtf)
+    probe = 2000
+    r = oix.align_batch(bases[: int(offs[probe])], offs[: probe + 1], n_threads=1, **_orc_flags())
+    rate1 = probe / max(r.seconds, 1e-9)
+    n = int(min(len(offs) - 1, max(probe, rate1 * args.cpu_seconds * threads * 0.6)))
+    times = []
+    for s in range(args.warmup + args.steps):
+        r = oix.align_batch(bases[: int(offs[n])], offs[: n + 1], n_threads=threads, **_orc_flags())
+        if s >= args.warmup:
+            times.append(r.seconds)
+    total = sum(times)
+    value = n * len(times) / total
+    line = dict(metric="reads/sec", value=value, unit="reads/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
+                data="synthetic", impl="reference",
+                config=dict(workload=workload_name(args.scale), reads_per_step=n, read_len=READ_LEN,
+                            note="CPU arm: C++ restatement of thermite's CPU algorithm (oracle), not the Rust binary "
+                                 "(no cargo/rustc in the image); bounded sample per step"),
+                cpu_baseline=dict(value=value, unit="reads/s", cores=threads, kind="port",
+                                  sample=f"{n} reads per step, {threads} host threads (single thread {rate1:.0f} reads/s)"),
+                e2e=dict(value=value, unit="reads/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from thermite_b200 import AlignOpts, Aligner, Index
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload + index: built on rank 0, replicated with ONE NCCL broadcast -----------------------------------
+    t_setup = time.time()
+    contigs, gtf, txs, fa = make_world(args.scale)
+    if rank == 0:
+        index = Index.create_from_memory(fa, gtf)
+        blob = torch.from_numpy(index.blob())
+        nbytes = torch.tensor([blob.numel()], dtype=torch.int64, device=dev)
+    else:
+        index, blob, nbytes = None, None, torch.zeros(1, dtype=torch.int64, device=dev)
+    bcast_ms = 0.0
+    if world > 1:
+        dist.broadcast(nbytes, 0)
+        d_blob = blob.to(dev) if rank == 0 else torch.empty(int(nbytes.item()), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(d_blob, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+        if rank != 0:
+            index = Index.from_blob(d_blob.cpu().numpy())
+        index.adopt_device_blob(d_blob.data_ptr(), d_blob.numel(), local_rank, keepalive=d_blob)
+    opts = AlignOpts(FLAGS["k"], FLAGS["pct"], FLAGS["min_score"], FLAGS["score_range"], FLAGS["intron_mode"])
+    aligner = Aligner(index, opts, device=local_rank)
+    bases, offs = make_reads(contigs, txs, args.reads, SEEDS["reads"] + 1000 * rank)
+    n = len(offs) - 1
+    setup_s = time.time() - t_setup
+
+    # HBM-resident inputs for `value`; pinned host inputs for `e2e`
+    d_bases = torch.from_numpy(bases).to(dev)
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    h_bases = torch.from_numpy(bases).pin_memory()
+    h_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(aligner.stream_ptr(), device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return aligner.align_reads_device_raw(d_bases.data_ptr(), d_offs.data_ptr(), n, int(offs[n]), READ_LEN)
+
+    def step_host():
+        return aligner.align_reads_raw(h_bases.data_ptr(), h_offs.data_ptr(), n)
+
+    # ---- value: device-resident ------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        res = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    seed_ms = ext_ms = 0.0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        res = step_device()
+        a, b = aligner.last_kernel_ms()
+        seed_ms += a
+        ext_ms += b
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    counters = dict(swg_cells=res.swg_cells, swg_extensions=res.swg_extensions, seed_hits=res.seed_hits, n_smems=res.n_smems,
+                    n_alns=res.n_alns, n_ops=res.n_ops)
+
+    # ---- e2e: host buffers through the C ABI --------------------------------------------------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        hres = step_host()
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev2.record(stream)
+    for _ in range(args.steps):
+        hres = step_host()
+    ev3.record(stream)
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(ev2.elapsed_time(ev3), e2e_wall_ms)  # the call is host-synchronous: wall clock bounds it from above
+    clocks = sampler.stop() if sampler else None
+    h2d = int(bases.nbytes + offs.nbytes)
+    d2h = int(n * 12 + hres.n_alns * 104 + hres.n_ops * 4)
+
+    t = torch.tensor([dev_ms, e2e_ms, seed_ms, ext_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([counters["swg_cells"], counters["seed_hits"], counters["n_alns"], counters["n_ops"], counters["n_smems"],
+                        counters["swg_extensions"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, seed_ms, ext_ms = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_reads = n * world * args.steps
+    value = total_reads / (dev_ms / 1e3)
+    e2e_value = total_reads / (e2e_ms / 1e3)
+    hbm_peak, peak_src, sm_max = peaks()
+    cells, hits, n_alns, n_ops, n_smems, n_ext = [float(x) / world for x in cnt.tolist()]  # per GPU, per step
+    seed_launch_ms = seed_ms / args.steps
+    ext_launch_ms = ext_ms / args.steps
+    seed_bytes = seed_algorithmic_bytes(n, READ_LEN, FLAGS["k"], hits)
+    ext_bytes = n * READ_LEN + n_smems * 24 + cells / 4 + n_alns * 104 + n_ops * 4
+    seed_gbs = seed_bytes / (seed_launch_ms / 1e3) / 1e9
+    ext_gbs = ext_bytes / (ext_launch_ms / 1e3) / 1e9
+    dominant = "k_extend" if ext_launch_ms >= seed_launch_ms else "k_seed"
+    ach = ext_gbs if dominant == "k_extend" else seed_gbs
+    gcups = cells / (ext_launch_ms / 1e3) / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+    # INT-pipe roofline: 148 SMs x 4 SMSP x 16 lanes/clk x f x P / I ; P = 1 cell per lane-op (32-bit), I = ALU
+    # instructions per cell-step of the shipped inner loop (DESIGN.md section "k_extend roofline")
+    INSTR_PER_CELL = 14.0
+    int_roof = 148 * 4 * 16 * (sm_mhz * 1e6) * 1.0 / INSTR_PER_CELL / 1e9
+    line = dict(
+        metric="reads/sec", value=value, unit="reads/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
+        data="synthetic",
+        config=dict(workload=workload_name(args.scale), reads_per_step_per_gpu=n, read_len=READ_LEN,
+                    flags="-k20 -s0 --intron-mode", parallelism=f"reads sharded over {world} GPU(s), index replicated",
+                    l2="inputs larger than L2: per step 91 MB of reads against a k-mer table + suffix array + text of several GB",
+                    index_bytes=int(index.blob().nbytes), kmer_table_bytes=int(aligner.kmer_table_bytes()),
+                    index_broadcast_ms=bcast_ms, setup_s=setup_s),
+        e2e=dict(value=e2e_value, unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),
+        gpu_launches=2 * args.steps,
+        roofline=dict(bound="hbm", kernel=dominant, achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None,
+                      peak_source=peak_src,
+                      note="algorithmic bytes per launch / CUDA-event duration of that kernel; k_extend is INT-pipe bound "
+                           "(see roofline_int), k_seed is HBM random-access bound (see roofline_seed)"),
+        roofline_seed=dict(bound="hbm", kernel="k_seed", achieved=seed_gbs, peak=hbm_peak, unit="GB/s", frac=seed_gbs / hbm_peak,
+                           ms_per_launch=seed_launch_ms, algorithmic_bytes_per_read=seed_bytes / n),
+        roofline_int=dict(bound="int-pipe", kernel="k_extend", achieved=gcups, peak=int_roof, unit="GCUPS", frac=gcups / int_roof,
+                          ms_per_launch=ext_launch_ms, cells_per_read=cells / n, sm_mhz=sm_mhz,
+                          instr_per_cell=INSTR_PER_CELL, cells_per_lane_op=1.0),
+        kernel_share=dict(k_seed=seed_ms / dev_ms, k_extend=ext_ms / dev_ms),
+        counters=dict(hits_per_read=hits / n, alns_per_read=n_alns / n, smems_per_read=n_smems / n, swg_ext_per_read=n_ext / n),
+        clocks=clocks,
+    )
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(fa, gtf, bases, offs, args.cpu_seconds, os.cpu_count() or 1)
+        line["cpu_baseline"] = cb
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

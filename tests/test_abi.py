@@ -1,0 +1,96 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/thermite_gpu.h declares, its host-side
+entry points work, and device entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import thermite_b200 as tb
+from common import golden
+from oracle import orc
+from thermite_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported():
+    hdr = open(os.path.join(ROOT, "include", "thermite_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)  # drop comments
+    declared = set(re.findall(r"\b(tg_[a-z0-9_]+)\s*\(", hdr))
+    L = tb.lib()
+    for sym in sorted(declared):
+        assert hasattr(L, sym), sym
+    assert declared == set(api.ABI_SYMBOLS), declared ^ set(api.ABI_SYMBOLS)
+
+
+def test_record_layouts_match_between_abi_and_oracle():
+    assert api.ALN_DTYPE == orc.ALN_DTYPE and api.ALN_DTYPE.itemsize == 104
+    assert api.SEED_DTYPE.itemsize == 24
+
+
+def test_host_index_metadata_and_blob_roundtrip(tmp_path):
+    fa, gtf = golden("test_ref.fasta"), golden("test_ref.gtf")
+    ix = tb.Index.create_from_memory(fa, gtf)
+    oix = orc.Index.create(fa, gtf)
+    assert [(r.name, r.strand, r.len, r.start_idx, r.end_idx) for r in ix.refs()] == \
+           [(r["name"], r["strand"], r["len"], r["start_idx"], r["end_idx"]) for r in oix.refs()]
+    assert [(t.id, t.strand, t.gene_idx, t.n_exons, t.seq_len) for t in ix.txome().txs] == \
+           [(t["id"], t["strand"], t["gene_idx"], len(t["exons"]), len(t["seq"])) for t in oix.txs()]
+    assert [(g.id, g.name) for g in ix.txome().genes] == [(g["id"], g["name"]) for g in oix.genes()]
+    assert (ix.suffix_array() == oix.sa()).all()
+    p = str(tmp_path / "t.tai")
+    ix.save(p)
+    ix2 = tb.Index.load(p)
+    assert (ix2.blob() == ix.blob()).all() and ix2.refs() == ix.refs()
+    ix3 = tb.Index.from_blob(ix.blob().copy())
+    assert ix3.txome().txs == ix.txome().txs
+    assert tb.sam_header(ix) == b"@SQ\tSN:some_ref\tLN:12\n@SQ\tSN:another_seq\tLN:12\n@SQ\tSN:introns_seq\tLN:26\n" \
+                                b"@SQ\tSN:introns_revcomp\tLN:26\n@PG\tID:thermite\n"
+
+
+def test_bad_inputs_are_errors_not_crashes():
+    with pytest.raises(tb.ThermiteError):
+        tb.Index.create_from_files("/nonexistent.fa", "/nonexistent.gtf")
+    with pytest.raises(tb.ThermiteError):
+        tb.Index.create_from_memory(b">a\nACGTRRRR\n", b"")
+    with pytest.raises(tb.ThermiteError):
+        tb.Index.from_blob(np.zeros(1000, np.uint8))
+    with pytest.raises(tb.ThermiteError):
+        tb.Index.create_from_memory(b">a\nACGTACGT\n", b'b\t.\texon\t1\t4\t.\t+\t.\tgene_id "g"; transcript_id "t";\n')
+
+
+def test_fastq_parser_and_writers_match_oracle_text():
+    """Host-side IO: records produced by the ORACLE, formatted by the PRODUCT writer, must equal the oracle's text."""
+    fa, gtf, fq = golden("test_ref.fasta"), golden("test_ref.gtf"), golden("test_query.fastq")
+    bases, offs, names, name_offs, quals, qual_offs = tb.parse_fastq(fq)
+    assert len(offs) == 11 and bytes(names[: int(name_offs[1])]) == b"all_match"
+    oix = orc.Index.create(fa, gtf)
+    ores = oix.align_batch(bases, offs, k=3, min_score=0)
+    ix = tb.Index.create_from_memory(fa, gtf)
+    n = len(offs) - 1
+    first = np.ascontiguousarray(ores.read_off[:-1])
+    count = np.ascontiguousarray((ores.read_off[1:] - ores.read_off[:-1]).astype(np.uint32))
+    res = api._Result(n, len(ores.alns), len(ores.ops), first.ctypes.data, count.ctypes.data, ores.alns.ctypes.data,
+                      ores.ops.ctypes.data, 0, 0, 0, 0)
+    for sam in (False, True):
+        out, ln = C.c_void_p(), C.c_size_t()
+        st = tb.lib().tg_format_batch(ix._h, C.byref(res), api._p(bases), api._p(offs), api._p(names), api._p(name_offs),
+                                      api._p(quals), api._p(qual_offs), int(sam), C.byref(out), C.byref(ln))
+        assert st == 0
+        text = C.string_at(out, ln.value)
+        tb.lib().tg_free(out)
+        want = oix.align_fastq_text(fq, k=3, min_score=0, sam=sam)
+        if sam:
+            text = tb.sam_header(ix) + text
+        assert text == want
+
+
+def test_device_entry_points_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ix = tb.Index.create_from_memory(golden("test_ref.fasta"), golden("test_ref.gtf"))
+    with pytest.raises(tb.ThermiteError, match="no CPU fallback|CUDA"):
+        tb.Aligner(ix)

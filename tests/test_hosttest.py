@@ -1,0 +1,96 @@
+"""The kernel LOGIC (thermite_b200/csrc/tg_core.h, the code the GPU runs) compiled for the host under an emulated
+warp (1 lane, and 32 lanes on threads with barrier-backed shuffles) against the CPU oracle.  The GPU itself is
+covered by tests/test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+import ht
+from common import golden, reads_to_batch, small_world, swg_pairs
+from oracle import orc
+from thermite_b200 import synth
+
+
+def test_product_suffix_array_matches_oracle_and_is_sorted():
+    for seed in (1, 2):
+        contigs, gtf, txs, fa = small_world(seed)
+        hix, oix = ht.HostIndex(fa, gtf), orc.Index.create(fa, gtf)
+        sa = hix.sa()
+        assert (sa == oix.sa()).all()
+        text = oix.text().tobytes()
+        assert sorted(sa.tolist()) == list(range(len(text)))
+        for i in range(0, len(sa) - 1, 37):
+            assert text[sa[i]:] < text[sa[i + 1]:]
+
+
+def test_seeds_equal_all_smems_test_dataset():
+    fa, gtf = golden("test_ref.fasta"), golden("test_ref.gtf")
+    hix, oix = ht.HostIndex(fa, gtf), orc.Index.create(fa, gtf)
+    reads = [b"ATT", b"CGAT", b"A" * 24, b"AATCGGCTTTT", b"AATTTTT", b"AATCGGCTCTT", b"AACTTTTT", b"AACCCCTT",
+             b"AAAGCCGATT", b"AATGCCGATT", b"", b"N", b"ccccc"]
+    bases, offs = reads_to_batch(reads)
+    for k in (1, 2, 3, 5):
+        ctx = ht.HostCtx(hix, k=k, min_score=0)
+        pool, first, count = ctx.seed_batch(bases, offs)
+        sa = hix.sa()
+        for r, rd in enumerate(reads):
+            assert ht.expand_seeds(pool, first, count, sa, r) == oix.all_smems(rd, k), (k, rd)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_align_records_equal_oracle_random_worlds(seed):
+    contigs, gtf, txs, fa = small_world(seed)
+    rng = np.random.default_rng(seed + 100)
+    L = int(rng.choice([40, 60, 91, 91, 120]))
+    k = int(rng.choice([12, 16, 20, 20, 25]))
+    pct = float(rng.choice([0.0, 0.5, 0.66]))
+    mins = int(rng.choice([0, 20, 30]))
+    intron = bool(rng.integers(0, 2))
+    srange = int(rng.choice([0, 1, 1, 3]))
+    n = 200
+    bases, offs = synth.make_reads(seed + 5, contigs, txs, n, L=L, sub=0.02, ins=0.003, dele=0.003, polya_frac=0.15,
+                                   polya_len=(10, 35))
+    hix, oix = ht.HostIndex(fa, gtf), orc.Index.create(fa, gtf)
+    ctx = ht.HostCtx(hix, k=k, pct=pct, min_score=mins, score_range=srange, intron_mode=intron)
+    pool, first, count = ctx.seed_batch(bases, offs)
+    sa = hix.sa()
+    for r in range(0, n, 5):
+        rd = bases[int(offs[r]): int(offs[r + 1])].tobytes()
+        assert ht.expand_seeds(pool, first, count, sa, r) == oix.all_smems(rd, k)
+    res = ctx.align_batch(bases, offs, lanes=1)
+    oix.counters_reset()
+    ores = oix.align_batch(bases, offs, k=k, pct=pct, min_score=mins, score_range=srange, intron_mode=intron)
+    d = ht.compare_alignments(res, ores, n)
+    assert not d, d[:3]
+    assert res["flags"] == 0 and res["cells"] == oix.counters()["swg_cells"] and res["hits"] == oix.counters()["hits"]
+    # the 32-lane wavefront (what the GPU executes) on a slice
+    m = 12
+    res32 = ctx.align_batch(bases[: int(offs[m])], offs[: m + 1], lanes=32)
+    d = ht.compare_alignments(res32, ores, m)
+    assert not d, d[:3]
+
+
+def test_swg_wavefront_equals_oracle():
+    for seed, lanes, n, kw in ((1, 1, 3000, {}), (2, 32, 150, {}), (3, 32, 60, dict(max_x=200, bw_choices=(3, 30, 100))),
+                               (4, 1, 1500, dict(alphabet=b"AC"))):
+        xs, xo, ys, yo, bw, xd = swg_pairs(seed, n, **kw)
+        a = ht.swg_extend_batch(xs, xo, ys, yo, bw, xd, lanes=lanes)
+        b = orc.swg_extend_batch(xs, xo, ys, yo, bw, xd)
+        for key in ("score", "xend", "yend", "ops_off", "ops"):
+            assert np.array_equal(a[key], b[key]), (seed, key)
+        assert a["cells"] == b["cells"]
+
+
+def test_chrM_reads_records():
+    fa, gtf = golden("GRCh38-2020-A-chrM.fasta"), golden("GRCh38-2020-A-chrM.gtf")
+    hix, oix = ht.HostIndex(fa, gtf), orc.Index.create(fa, gtf)
+    g = np.frombuffer(b"".join(fa.split(b"\n")[1:]), np.uint8)
+    txs = [dict(id="x", strand=f[6], exons=[(int(f[3]) - 1, int(f[4]))], chrom="chrM", gene="g")
+           for f in (ln.split("\t") for ln in gtf.decode().splitlines()) if len(f) > 8 and f[2] == "exon"]
+    n = 400
+    bases, offs = synth.make_reads(20211, [("chrM", g)], txs, n, L=91)
+    for flags in (dict(k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True),
+                  dict(k=20, pct=0.66, min_score=30, score_range=1, intron_mode=False)):
+        ctx = ht.HostCtx(hix, **flags)
+        res = ctx.align_batch(bases, offs)
+        ores = oix.align_batch(bases, offs, **flags)
+        assert not ht.compare_alignments(res, ores, n)

@@ -328,7 +328,7 @@ struct Avl {
     return rebalance(at);
   }
   void insert(uint32_t s, uint32_t e, uint32_t data) {
-    nodes.push_back(TgTreeNode{s, e, e, data, -1, -1});
+    nodes.push_back(TgTreeNode{s, e, e, data, -1, -1, 0u, 0u});
     height.push_back(1);
     root = ins(root, (int32_t)nodes.size() - 1);
   }

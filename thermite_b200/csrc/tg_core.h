@@ -506,8 +506,8 @@ TG_HD bool tg_tree_next(TgTreeIter& it, uint32_t& data) {
     int32_t ci = it.stack[--it.sp];
 #ifdef __CUDA_ARCH__
     const uint4 a = __ldg((const uint4*)(it.nodes + ci));
-    const int2 b = __ldg((const int2*)(it.nodes + ci) + 2);
-    TgTreeNode c{a.x, a.y, a.z, a.w, b.x, b.y};
+    const uint4 b = __ldg((const uint4*)(it.nodes + ci) + 1);
+    TgTreeNode c{a.x, a.y, a.z, a.w, (int32_t)b.x, (int32_t)b.y, 0u, 0u};
 #else
     TgTreeNode c = it.nodes[ci];
 #endif

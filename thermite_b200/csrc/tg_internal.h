@@ -19,9 +19,10 @@ enum : uint8_t { TG_C_SENT = 0, TG_C_A = 1, TG_C_C = 2, TG_C_G = 3, TG_C_N = 4, 
 
 // One interval-tree node of the flattened AVL tree (rust-bio IntervalTree shape; src/index.rs:135,182,208).
 // Arrays of these reproduce `find()` by running the same stack DFS on the device.
-struct TgTreeNode {
+struct alignas(16) TgTreeNode {  // 32 bytes: two 128-bit loads on the device
   uint32_t start, end, max, data;
   int32_t left, right;
+  uint32_t pad0, pad1;
 };
 
 struct TgRef {
@@ -29,7 +30,7 @@ struct TgRef {
   uint32_t strand_rank;  // bit0 = strand (1 forward), bits 1.. = rank of the name in byte order (filter_overlapping key)
 };
 
-#define TG_BLOB_MAGIC 0x3130424947544854ull /* "THTGIB01" */
+#define TG_BLOB_MAGIC 0x3230424947544854ull /* "THTGIB02" */
 
 // Position-independent header at offset 0 of the index blob.  All off_* are byte offsets from the blob
 // start, 256-byte aligned.

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
   m.opsC = (uint32_t*)(base + lay.ops + 2 * ob); m.opsT = (uint32_t*)(base + lay.ops + 3 * ob);
   m.stack = (int32_t*)(base + lay.stack);
   m.ops_cap = p.ops_cap;
-  const uint32_t gw = blockIdx.x * TG_WARPS_PER_CTA + (threadIdx.x >> 5);
+  const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   TgWarpScratch sc{p.cands + (size_t)gw * TG_MAX_ALNS_PER_READ, p.arena + (size_t)gw * p.arena_cap, p.arena_cap};
   DevWarp w;
   TgCounters ctr{0, 0, 0};
@@ -576,17 +576,19 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   if (trace_bytes < 4 * TG_MAX_ALNS_PER_READ) trace_bytes = 4 * TG_MAX_ALNS_PER_READ;
   uint32_t ops_cap = 2 * maxL + max_bw + 16;
   ExtSmemLayout lay = ext_smem_layout(maxL, max_cols, trace_bytes, ops_cap);
-  size_t smem = lay.total * TG_WARPS_PER_CTA;
+  int wpc = TG_WARPS_PER_CTA;
+  while (wpc > 1 && lay.total * wpc > 100 * 1024) wpc >>= 1;  // long reads: fewer warps per CTA
+  size_t smem = lay.total * wpc;
   if (smem > 227 * 1024) return tg_fail(TG_ERR_CAPACITY, "reads too long for the extension kernel's shared memory");
   const int rcls = tg_swg_rows_class((int)max_xlen, 32);
   void (*kern)(ExtParams) = rcls <= 3 ? k_extend<3> : rcls <= 6 ? k_extend<6> : k_extend<16>;
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TG_WARPS_PER_CTA * 32, smem));
+  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem));
   if (occ < 1) return tg_fail(TG_ERR_CAPACITY, "extension kernel does not fit in shared memory");
-  int blocks = (int)std::min<uint64_t>((uint64_t)c->n_sms * occ, ((uint64_t)n + TG_WARPS_PER_CTA - 1) / TG_WARPS_PER_CTA);
+  int blocks = (int)std::min<uint64_t>((uint64_t)c->n_sms * occ, ((uint64_t)n + wpc - 1) / wpc);
   if (blocks < 1) blocks = 1;
-  uint32_t warps = (uint32_t)blocks * TG_WARPS_PER_CTA;
+  uint32_t warps = (uint32_t)blocks * wpc;
   const uint32_t arena_cap = 32768;
   if (warps > c->scratch_warps) {
     tg_status st = c->d_cands.ensure((size_t)warps * TG_MAX_ALNS_PER_READ * sizeof(TgCand));
@@ -607,7 +609,7 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;
   p.out.alns_cap = c->alns_cap; p.out.ops_cap = c->ops_cap; p.out.flags = &c->d_ctr->flags;
   p.ctr = c->d_ctr;
-  kern<<<blocks, TG_WARPS_PER_CTA * 32, smem, c->stream>>>(p);
+  kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
   CU_CHECK(cudaGetLastError());
   return TG_OK;
 }
@@ -790,7 +792,9 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   }
   uint32_t trace_bytes = (max_cols + 1) * (uint32_t)tg_trace_bytes_per_col((int)max_xlen, 32);
   uint32_t ops_words = max_xlen + max_cols + 8;
-  size_t smem = swg_smem_per_warp(max_xlen, max_cols, trace_bytes, ops_words) * TG_WARPS_PER_CTA;
+  int wpc = TG_WARPS_PER_CTA;
+  while (wpc > 1 && swg_smem_per_warp(max_xlen, max_cols, trace_bytes, ops_words) * wpc > 100 * 1024) wpc >>= 1;
+  size_t smem = swg_smem_per_warp(max_xlen, max_cols, trace_bytes, ops_words) * wpc;
   if (smem > 227 * 1024) return tg_fail(TG_ERR_CAPACITY, "sequences too long for the SWG kernel's shared memory");
   tg_status st;
   uint64_t nx = xoff[n], ny = yoff[n];
@@ -810,9 +814,9 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   void (*kern)(SwgParams) = rcls <= 3 ? k_swg_batch<3> : rcls <= 6 ? k_swg_batch<6> : k_swg_batch<16>;
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TG_WARPS_PER_CTA * 32, smem));
+  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem));
   if (occ < 1) return tg_fail(TG_ERR_CAPACITY, "SWG kernel does not fit in shared memory");
-  int blocks = (int)std::min<uint64_t>((uint64_t)c->n_sms * occ, ((uint64_t)n + TG_WARPS_PER_CTA - 1) / TG_WARPS_PER_CTA);
+  int blocks = (int)std::min<uint64_t>((uint64_t)c->n_sms * occ, ((uint64_t)n + wpc - 1) / wpc);
   SwgParams p;
   p.xs = (const uint8_t*)c->s_x.p; p.xoff = (const uint64_t*)c->s_xo.p; p.ys = (const uint8_t*)c->s_y.p; p.yoff = (const uint64_t*)c->s_yo.p;
   p.n = n; p.bw = (const uint32_t*)c->s_bw.p; p.x_drop = (const int32_t*)c->s_xd.p;
@@ -820,7 +824,7 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   p.task_off = (uint64_t*)c->s_toff.p; p.task_len = (uint32_t*)c->s_tlen.p; p.ops = (uint32_t*)c->s_ops.p; p.ops_cap = worst_ops;
   p.max_xlen = max_xlen; p.max_cols = max_cols; p.trace_bytes = trace_bytes; p.ops_words = ops_words; p.ctr = c->d_ctr;
   CU_CHECK(cudaEventRecord(c->ev0, c->stream));
-  kern<<<blocks, TG_WARPS_PER_CTA * 32, smem, c->stream>>>(p);
+  kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
   CU_CHECK(cudaGetLastError());
   CU_CHECK(cudaEventRecord(c->ev1, c->stream));
   CU_CHECK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
