@@ -43,7 +43,7 @@ enum {
 
 #define TG_MAX_READ_LEN 512u        /* longest read accepted by tg_align_batch / tg_seed_batch */
 #define TG_MAX_SEED_LEN 32u         /* largest min_seed_len (k-mer table key is k 4-bit symbols) */
-#define TG_MAX_ALNS_PER_READ 256u   /* accepted alignments kept per read before the final filters */
+#define TG_MAX_ALNS_PER_READ 4096u  /* near-best alignments (score >= running max - range) kept per read before the final filters */
 
 const char* tg_last_error(void);
 /* Library / build identification: "thermite_gpu <ver> sm_100a". */

@@ -166,6 +166,7 @@ int64_t orc_all_smems(void* ix, const uint8_t* read, uint64_t len, uint32_t k, i
   std::vector<uint8_t> r(read, read + len);
   for (auto& c : r) if (c >= 'a' && c <= 'z') c -= 32;
   auto m = brute ? ((Index*)ix)->all_smems_brute(r.data(), len, k) : ((Index*)ix)->all_smems(r.data(), len, k);
+  ((Index*)ix)->fold_tl();
   for (size_t i = 0; i < m.size() && i < cap; i++) { out[3 * i] = m[i].ref_idx; out[3 * i + 1] = m[i].query_idx; out[3 * i + 2] = m[i].len; }
   return (int64_t)m.size();
   ORC_CATCH(-1)
@@ -299,10 +300,10 @@ void* orc_align_batch(void* ixp, const uint8_t* bases, const uint64_t* offs, uin
     uint64_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
     per[t].reserve(hi - lo);
     for (uint64_t r = lo; r < hi; r++) per[t].push_back(align_read(*ix, bases + offs[r], offs[r + 1] - offs[r], o));
+    ix->fold_tl();
   };
   if (n_threads == 1) work(0);
   else {
-    // counters are racy across threads (plain adds); they are only read in single-thread runs
     std::vector<std::thread> th;
     for (uint32_t t = 0; t < n_threads; t++) th.emplace_back(work, t);
     for (auto& t : th) t.join();
@@ -336,6 +337,7 @@ char* orc_align_fastq_text(void* ixp, const char* fastq, uint64_t len, uint32_t 
   ORC_TRY
   auto reads = parse_fastq(std::string(fastq, len));
   std::string s = align_fastq(*(Index*)ixp, reads, mk_opts(k, pct, min_score, range, intron), sam != 0);
+  ((Index*)ixp)->fold_tl();
   char* out = (char*)malloc(s.size() + 1);
   std::memcpy(out, s.data(), s.size());
   out[s.size()] = 0;

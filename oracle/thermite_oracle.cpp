@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <numeric>
 #include <sstream>
 #include <unordered_map>
@@ -395,8 +396,21 @@ static inline int sym_code(uint8_t a) {
 }
 
 // bio Occ::get: checkpoint every occ_rate rows plus a byte count over the remainder
+Counters& Index::tl() {
+  static thread_local Counters c;
+  return c;
+}
+void Index::fold_tl() const {
+  Counters& c = tl();
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  counters.swg_cells += c.swg_cells; counters.swg_calls += c.swg_calls; counters.occ_lookups += c.occ_lookups;
+  counters.fmd_ext += c.fmd_ext; counters.sa_locates += c.sa_locates; counters.hits += c.hits;
+  c = Counters();
+}
+
 size_t Index::occ(size_t r, uint8_t a) const {
-  counters.occ_lookups++;
+  tl().occ_lookups++;
   int c = sym_code(a);
   size_t i = r / occ_rate;
   size_t cnt = occ_samples[i * 6 + c];
@@ -407,7 +421,7 @@ size_t Index::occ(size_t r, uint8_t a) const {
 
 // bio SampledSuffixArray::get: LF-walk to a sampled row (or a sentinel row kept as "extra")
 size_t Index::sa_get(size_t r) const {
-  counters.sa_locates++;
+  tl().sa_locates++;
   size_t pos = r, offset = 0;
   for (;;) {
     if (pos % sa_rate == 0) return (size_t)sa_samples[pos / sa_rate] + offset;
@@ -430,7 +444,7 @@ struct Fmd {
     return BiInterval{less(a), less(complement(a)), ix.less[(size_t)a + 1] - ix.less[a]};
   }
   BiInterval backward_ext(const BiInterval& iv, uint8_t a) const {
-    ix.counters.fmd_ext++;
+    Index::tl().fmd_ext++;
     if (sym_code(a) < 0 || iv.size == 0) return BiInterval{0, 0, 0};
     size_t s = 0, o = 0, l = iv.lower_rev;
     static const uint8_t order[6] = {'$', 'T', 'G', 'C', 'N', 'A'};
@@ -513,7 +527,7 @@ std::vector<Mem> Index::all_smems(const uint8_t* query, size_t qlen, size_t min_
   }
   std::stable_sort(mems.begin(), mems.end(), [](const Mem& a, const Mem& b) { return a.len < b.len; });
   std::reverse(mems.begin(), mems.end());
-  counters.hits += mems.size();
+  tl().hits += mems.size();
   return mems;
 }
 
@@ -966,7 +980,7 @@ std::vector<GenomeAlignment> align_read(const Index& index, const uint8_t* read_
     max_aln_score = std::max(max_aln_score, s);
     gx_alns.push_back(std::move(g));
   }
-  index.counters.swg_cells += swg.cells - cells0;
+  Index::tl().swg_cells += swg.cells - cells0;
   {  // :177-179
     std::vector<GenomeAlignment> kept;
     for (auto& g : gx_alns) if (g.gx_aln.score >= max_aln_score - range) kept.push_back(std::move(g));

@@ -187,7 +187,9 @@ class Index {
   std::map<size_t, size_t> sa_extra;   // rows whose BWT byte is the sentinel
   std::vector<uint8_t> text;           // kept ONLY for all_smems_brute / tests (reference drops it)
   std::vector<uint32_t> full_sa;       // kept ONLY for tests (suffix-order checks)
-  mutable Counters counters;
+  mutable Counters counters;       // totals (single-thread runs update them directly)
+  static Counters& tl();           // per-thread counters used while aligning; folded into `counters` by fold_tl()
+  void fold_tl() const;
 
   size_t occ(size_t r, uint8_t a) const;
   size_t sa_get(size_t r) const;

@@ -133,7 +133,6 @@ struct WarpBuffers {
     uint32_t cap = 2 * maxL + max_bw + 16;
     rd.assign(maxL + 16, 0); xs.assign(maxL + 16, 0); ys.assign(max_cols + 16, 0);
     size_t tb = (size_t)max_cols * tg_trace_bytes_per_col((int)maxL, lanes);
-    if (tb < 4 * TG_MAX_ALNS_PER_READ) tb = 4 * TG_MAX_ALNS_PER_READ;
     trace.assign(tb + 64, 0);
     a.assign(cap, 0); b.assign(cap, 0); c.assign(cap, 0); t.assign(cap, 0);
     stack.assign(TG_TREE_STACK, 0);
@@ -244,7 +243,8 @@ void* ht_align_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint3
   TgWarpMem wm = wb.mem(maxL, max_bw_for(c->opts, maxL), lanes);
   wb.cands.resize(TG_MAX_ALNS_PER_READ);
   wb.arena.resize(1 << 16);
-  TgWarpScratch sc{wb.cands.data(), wb.arena.data(), (uint32_t)wb.arena.size()};
+  std::vector<uint16_t> order(2 * TG_MAX_ALNS_PER_READ);
+  TgWarpScratch sc{wb.cands.data(), wb.arena.data(), (uint32_t)wb.arena.size(), order.data()};
   std::vector<tg_seed> pool(maxL + 8);
   std::vector<uint64_t> sfirst(1);
   std::vector<uint32_t> scount(1);

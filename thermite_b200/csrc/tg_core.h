@@ -793,6 +793,25 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
   a.ylen = r2.len;
 }
 
+// stable bottom-up merge sort of an index array (a -> sorted in a; b is scratch of n entries)
+template <class Less>
+TG_HD void tg_merge_sort_idx(uint16_t* a, uint16_t* b, uint32_t n, Less less) {
+  uint16_t* src = a;
+  uint16_t* dst = b;
+  for (uint32_t width = 1; width < n; width <<= 1) {
+    for (uint32_t lo = 0; lo < n; lo += 2 * width) {
+      uint32_t mid = lo + width < n ? lo + width : n, hi = lo + 2 * width < n ? lo + 2 * width : n;
+      uint32_t i = lo, j = mid, k = lo;
+      while (i < mid && j < hi) dst[k++] = less(src[j], src[i]) ? src[j++] : src[i++];  // ties keep the left run first
+      while (i < mid) dst[k++] = src[i++];
+      while (j < hi) dst[k++] = src[j++];
+    }
+    uint16_t* t = src; src = dst; dst = t;
+  }
+  if (src != a)
+    for (uint32_t i = 0; i < n; i++) a[i] = src[i];
+}
+
 // End-of-read filters on the accepted candidates (src/aligner.rs:177-187 and filter_overlapping :317-349).
 // Serial; `order`/`tmp` are scratch arrays of n entries.  Returns the number of output records; order[0..ret)
 // lists candidate indices in output order.
@@ -804,21 +823,13 @@ TG_HD uint32_t tg_finalize_read(const TgCand* cands, uint32_t n, int32_t max_aln
     if (cands[i].a.score >= max_aln_score - range) order[m++] = (uint16_t)i;
   if (m == 0) return 0;
   // stable sort by (ref_name, strand false<true, ystart) (:322-327)
-  for (uint32_t i = 1; i < m; i++) {
-    uint16_t cur = order[i];
-    const TgCand& cc = cands[cur];
-    uint32_t j = i;
-    while (j > 0) {
-      const TgCand& p = cands[order[j - 1]];
-      bool greater = p.name_rank > cc.name_rank ||
-                     (p.name_rank == cc.name_rank &&
-                      (p.a.strand > cc.a.strand || (p.a.strand == cc.a.strand && p.a.ystart > cc.a.ystart)));
-      if (!greater) break;
-      order[j] = order[j - 1];
-      j--;
-    }
-    order[j] = cur;
-  }
+  tg_merge_sort_idx(order, tmp, m, [&](uint16_t x, uint16_t y) {
+    const TgCand& a = cands[x];
+    const TgCand& b = cands[y];
+    if (a.name_rank != b.name_rank) return a.name_rank < b.name_rank;
+    if (a.a.strand != b.a.strand) return a.a.strand < b.a.strand;
+    return a.a.ystart < b.a.ystart;
+  });
   // sweep (:329-346)
   uint32_t k = 0;
   uint64_t max_end = 0;
@@ -837,13 +848,7 @@ TG_HD uint32_t tg_finalize_read(const TgCand* cands, uint32_t n, int32_t max_aln
   }
   // stable sort by -score (:183)
   for (uint32_t i = 0; i < k; i++) order[i] = tmp[i];
-  for (uint32_t i = 1; i < k; i++) {
-    uint16_t cur = order[i];
-    int32_t cs = cands[cur].a.score;
-    uint32_t j = i;
-    while (j > 0 && cands[order[j - 1]].a.score < cs) { order[j] = order[j - 1]; j--; }
-    order[j] = cur;
-  }
+  tg_merge_sort_idx(order, tmp, k, [&](uint16_t x, uint16_t y) { return cands[x].a.score > cands[y].a.score; });
   return k;
 }
 
@@ -957,6 +962,7 @@ struct TgWarpScratch {  // per-warp global scratch of the extension stage
   TgCand* cands;       // TG_MAX_ALNS_PER_READ
   uint32_t* arena;     // ops of the accepted candidates
   uint32_t arena_cap;
+  uint16_t* order;     // 2 * TG_MAX_ALNS_PER_READ (order + tmp of tg_finalize_read)
 };
 struct TgAlignOut {
   uint64_t* read_aln_first;
@@ -1007,6 +1013,27 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
       // keep the candidate
       uint32_t need = gx_ops.n + tx_ops.n;
       if (n_acc >= TG_MAX_ALNS_PER_READ || arena_used + need > sc.arena_cap) {
+        // drop what the final `retain` (:177-179) would drop anyway, compacting records and their ops in place
+        w.sync_global();
+        int kept = 0, au = 0;
+        if (lane == 0) {
+          uint32_t o = 0, kk = 0;
+          for (uint32_t i = 0; i < n_acc; i++) {
+            TgCand ci = sc.cands[i];
+            if (ci.a.score < max_aln_score - range) continue;
+            uint32_t nn = ci.a.ops_len + ci.a.tx_ops_len, src = ci.a.ops_off;
+            for (uint32_t t = 0; t < nn; t++) sc.arena[o + t] = sc.arena[src + t];
+            ci.a.ops_off = o; ci.a.tx_ops_off = o + ci.a.ops_len;
+            sc.cands[kk++] = ci;
+            o += nn;
+          }
+          kept = (int)kk; au = (int)o;
+        }
+        n_acc = (uint32_t)w.shfl(kept, 0);
+        arena_used = (uint32_t)w.shfl(au, 0);
+        w.sync_global();
+      }
+      if (n_acc >= TG_MAX_ALNS_PER_READ || arena_used + need > sc.arena_cap) {
         if (lane == 0) w.atomic_or(out.flags, n_acc >= TG_MAX_ALNS_PER_READ ? TG_FLAG_READ_CAP : TG_FLAG_ARENA);
         capped = true;
         break;
@@ -1023,7 +1050,7 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
   }
   w.sync_global();
   // :177-187
-  uint16_t* order = (uint16_t*)m.trace;
+  uint16_t* order = sc.order;
   uint16_t* tmp = order + TG_MAX_ALNS_PER_READ;
   int k = 0;
   unsigned long long words = 0;

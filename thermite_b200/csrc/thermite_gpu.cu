@@ -193,6 +193,7 @@ struct ExtParams {
   TgCand* cands;      // [n_warps][TG_MAX_ALNS_PER_READ]
   uint32_t* arena;    // [n_warps][arena_cap]
   uint32_t arena_cap;
+  uint16_t* order;    // [n_warps][2 * TG_MAX_ALNS_PER_READ]
   TgAlignOut out;
   DevCounters* ctr;
 };
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
   m.stack = (int32_t*)(base + lay.stack);
   m.ops_cap = p.ops_cap;
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  TgWarpScratch sc{p.cands + (size_t)gw * TG_MAX_ALNS_PER_READ, p.arena + (size_t)gw * p.arena_cap, p.arena_cap};
+  TgWarpScratch sc{p.cands + (size_t)gw * TG_MAX_ALNS_PER_READ, p.arena + (size_t)gw * p.arena_cap, p.arena_cap,
+                   p.order + (size_t)gw * 2 * TG_MAX_ALNS_PER_READ};
   DevWarp w;
   TgCounters ctr{0, 0, 0};
   for (;;) {
@@ -375,7 +377,7 @@ struct tg_ctx {
   DevBuf d_seeds, d_seed_first, d_seed_count;
   uint64_t seed_cap = 0;
   // extension
-  DevBuf d_cands, d_arena, d_aln_first, d_aln_count, d_alns, d_ops;
+  DevBuf d_cands, d_arena, d_order, d_aln_first, d_aln_count, d_alns, d_ops;
   uint64_t alns_cap = 0, ops_cap = 0;
   uint32_t scratch_warps = 0;
   // host results
@@ -474,7 +476,7 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->ix->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_cands, &c->d_arena,
+  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_cands, &c->d_arena, &c->d_order,
                     &c->d_aln_first, &c->d_aln_count, &c->d_alns, &c->d_ops, &c->s_x, &c->s_xo, &c->s_y, &c->s_yo, &c->s_bw,
                     &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops})
     b->release();
@@ -573,7 +575,6 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   uint32_t max_xlen = maxL > 0 ? maxL - 1 : 0;
   uint32_t max_cols = max_xlen + max_bw + 1;
   uint32_t trace_bytes = max_cols * (uint32_t)tg_trace_bytes_per_col((int)max_xlen, 32);
-  if (trace_bytes < 4 * TG_MAX_ALNS_PER_READ) trace_bytes = 4 * TG_MAX_ALNS_PER_READ;
   uint32_t ops_cap = 2 * maxL + max_bw + 16;
   ExtSmemLayout lay = ext_smem_layout(maxL, max_cols, trace_bytes, ops_cap);
   int wpc = TG_WARPS_PER_CTA;
@@ -589,11 +590,13 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   int blocks = (int)std::min<uint64_t>((uint64_t)c->n_sms * occ, ((uint64_t)n + wpc - 1) / wpc);
   if (blocks < 1) blocks = 1;
   uint32_t warps = (uint32_t)blocks * wpc;
-  const uint32_t arena_cap = 32768;
+  const uint32_t arena_cap = 65536;
   if (warps > c->scratch_warps) {
     tg_status st = c->d_cands.ensure((size_t)warps * TG_MAX_ALNS_PER_READ * sizeof(TgCand));
     if (st != TG_OK) return st;
     st = c->d_arena.ensure((size_t)warps * arena_cap * 4);
+    if (st != TG_OK) return st;
+    st = c->d_order.ensure((size_t)warps * 2 * TG_MAX_ALNS_PER_READ * 2);
     if (st != TG_OK) return st;
     c->scratch_warps = warps;
   }
@@ -603,7 +606,7 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.ops_cap = ops_cap;
   p.seeds = (const tg_seed*)c->d_seeds.p; p.read_seed_first = (const uint64_t*)c->d_seed_first.p;
   p.read_seed_count = (const uint32_t*)c->d_seed_count.p;
-  p.cands = (TgCand*)c->d_cands.p; p.arena = (uint32_t*)c->d_arena.p; p.arena_cap = arena_cap;
+  p.cands = (TgCand*)c->d_cands.p; p.arena = (uint32_t*)c->d_arena.p; p.arena_cap = arena_cap; p.order = (uint16_t*)c->d_order.p;
   p.out.read_aln_first = (uint64_t*)c->d_aln_first.p; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p;
   p.out.alns = (tg_aln*)c->d_alns.p; p.out.ops = (uint32_t*)c->d_ops.p;
   p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;

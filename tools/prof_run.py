@@ -1,0 +1,19 @@
+"""Small fixed invocation of the hot path for ncu captures (see profiles/README.md).
+usage: python tools/prof_run.py <genome scale> <reads> [steps]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from thermite_b200 import AlignOpts, Aligner, Index  # noqa: E402
+
+scale, n = float(sys.argv[1]), int(sys.argv[2])
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+contigs, gtf, txs, fa = bench.make_world(scale)
+ix = Index.create_from_memory(fa, gtf)
+al = Aligner(ix, AlignOpts(bench.FLAGS["k"], bench.FLAGS["pct"], bench.FLAGS["min_score"], bench.FLAGS["score_range"],
+                           bench.FLAGS["intron_mode"]))
+bases, offs = bench.make_reads(contigs, txs, n, bench.SEEDS["reads"])
+for _ in range(steps):
+    r = al.align_reads(bases, offs)
+print("reads", n, "alns", len(r.alns), "kernel ms (seed, extend)", al.last_kernel_ms(), r.counters)
