@@ -520,3 +520,57 @@ def align_reads_from_file(index: Index, query_paths, output_path: str, output_fm
     finally:
         if out is not sys.stdout.buffer:
             out.close()
+
+
+# ---- multi-GPU plumbing (reads shard; index replicated; ordered merge on the host) ------------------------------
+def shard_range(n_reads: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of a batch owned by `rank` ([g*N/G, (g+1)*N/G))."""
+    return n_reads * rank // world, n_reads * (rank + 1) // world
+
+
+def merge_shards(shards):
+    """Concatenate per-rank results (each (first, count, alns, ops), given in rank order) into one result whose
+    reads are in the original order -- the reference's serial output order (src/aligner.rs:54-115)."""
+    firsts, counts, alns, ops = [], [], [], []
+    a_base = o_base = 0
+    for first, count, a, o in shards:
+        a = a.copy()
+        a["ops_off"] += np.uint32(o_base)
+        ex = a["aln_type"] == 0
+        a["tx_ops_off"][ex] += np.uint32(o_base)
+        firsts.append(first.astype(np.uint64) + np.uint64(a_base))
+        counts.append(count)
+        alns.append(a)
+        ops.append(o)
+        a_base += len(a)
+        o_base += len(o)
+    return (np.concatenate(firsts) if firsts else np.zeros(0, np.uint64),
+            np.concatenate(counts) if counts else np.zeros(0, np.uint32),
+            np.concatenate(alns) if alns else np.zeros(0, ALN_DTYPE),
+            np.concatenate(ops) if ops else np.zeros(0, np.uint32))
+
+
+def broadcast_index(index, rank: int, device=None):
+    """Replicate the flat index with ONE torch.distributed broadcast (NCCL over NVLink on GPUs, gloo on CPU).
+    Returns (Index, device blob tensor or None).  On GPU ranks the received blob is adopted in place as the HBM
+    replica; no other collective is ever issued on the data path."""
+    import torch
+    import torch.distributed as dist
+    on_gpu = device is not None and str(device).startswith("cuda")
+    dev = torch.device(device) if on_gpu else torch.device("cpu")
+    n = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == 0:
+        host = torch.from_numpy(index.blob())
+        n[0] = host.numel()
+    dist.broadcast(n, 0)
+    if rank == 0:
+        buf = host.to(dev) if on_gpu else host
+    else:
+        buf = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
+    dist.broadcast(buf, 0)
+    if rank != 0:
+        index = Index.from_blob(buf.cpu().numpy())
+    if on_gpu:
+        index.adopt_device_blob(buf.data_ptr(), buf.numel(), dev.index or 0, keepalive=buf)
+        return index, buf
+    return index, None
