@@ -22,6 +22,7 @@ struct HostWarp1 {
   int shfl(int v, int) { return v; }
   unsigned long long shfl64(unsigned long long v, int) { return v; }
   bool any(bool p) { return p; }
+  unsigned long long sum64(unsigned long long v) { return v; }
   void sync() {}
   void sync_global() {}
   unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
@@ -82,6 +83,14 @@ struct HostWarp32 {
     sh->bar.wait();
     return r;
   }
+  unsigned long long sum64(unsigned long long v) {
+    sh->xl[l] = v;
+    sh->bar.wait();
+    unsigned long long r = 0;
+    for (int i = 0; i < 32; i++) r += sh->xl[i];
+    sh->bar.wait();
+    return r;
+  }
   void sync() { sh->bar.wait(); }
   void sync_global() { sh->bar.wait(); }
   unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
@@ -122,7 +131,7 @@ struct WarpBuffers {
   std::vector<uint8_t> rd, xs, ys, trace;
   std::vector<uint32_t> a, b, c, t;
   std::vector<int32_t> stack;
-  std::vector<uint64_t> rp;
+  std::vector<uint64_t> rp, rp2;
   std::vector<TgSeedHit> hits;
   std::vector<tg_seed> sm;
   std::vector<uint16_t> grp;
@@ -136,7 +145,8 @@ struct WarpBuffers {
     trace.assign(tb + 64, 0);
     a.assign(cap, 0); b.assign(cap, 0); c.assign(cap, 0); t.assign(cap, 0);
     stack.assign(TG_TREE_STACK, 0);
-    return TgWarpMem{rd.data(), xs.data(), ys.data(), trace.data(), a.data(), b.data(), c.data(), t.data(), stack.data(), cap};
+    rp2.assign(maxL / 16 + 4, 0);
+    return TgWarpMem{rd.data(), xs.data(), ys.data(), trace.data(), a.data(), b.data(), c.data(), t.data(), stack.data(), cap, rp2.data()};
   }
   TgSeedMem seed_mem(uint32_t maxL) {
     rp.assign(maxL / 16 + 4, 0); hits.assign(maxL + 1, TgSeedHit{0, 0, 0}); sm.assign(maxL + 1, tg_seed{}); grp.assign(maxL + 1, 0);

@@ -20,9 +20,11 @@
 #ifdef __CUDA_ARCH__
 #define TG_LDG(p) __ldg(p)
 #define TG_CLZ64(x) __clzll((long long)(x))
+#define TG_CTZ64(x) (__ffsll((long long)(x)) - 1)
 #else
 #define TG_LDG(p) (*(p))
 #define TG_CLZ64(x) __builtin_clzll(x)
+#define TG_CTZ64(x) __builtin_ctzll(x)
 #endif
 
 #define TG_MINV (-(1 << 29))
@@ -269,77 +271,13 @@ TG_HD void tg_ops_reverse(TgOps& o) {
 // phase-1 x-drop break of src/swg.rs:110-112 is unreachable and no stale state exists: quirk Q4).
 // Scores are exact in 32-bit; MIN_SCORE is represented by TG_MINV and never wins a max against a real cell.
 // ------------------------------------------------------------------------------------------------
-template <int R>
-struct TgSwgLane {
-  int D[R], C[R];
-  uint8_t xc[R];
-  int diag_in;        // D(i0-1, j-1)
-  int sendD, sendR;   // D/R of this lane's last row for the column it just finished
-  int sendCM, sendCR; // running (column max, first row attaining it) for that column
-};
+#define TG_CM_MIN (-(1 << 20))  // "no in-band cell yet" for the per-column running maximum (fits the 22-bit packing)
 
-TG_HD int tg_pack_dr(int d, int r) {
-  if (d < -32768) d = -32768;
-  if (r < -32768) r = -32768;
-  return (int)(((uint32_t)d << 16) | ((uint32_t)r & 0xffffu));
-}
-TG_HD void tg_unpack_dr(int p, int& d, int& r) {
-  d = p >> 16;
-  r = (int)(int16_t)(p & 0xffff);
-  if (d == -32768) d = TG_MINV;
-  if (r == -32768) r = TG_MINV;
-}
-
-template <int R>
-TG_HD void tg_swg_lane_init(TgSwgLane<R>& s, int lane, const uint8_t* xs, int xlen, int bw) {
-  const int i0 = lane * R;
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    int i = i0 + r;
-    bool in0 = i <= 2 * bw;  // column 0 initialises rows 0..w-1 (src/swg.rs:62-71)
-    s.D[r] = in0 ? (i == 0 ? 0 : -(i + 1)) : TG_MINV;
-    s.C[r] = (in0 && i == 0) ? 0 : TG_MINV;
-    s.xc[r] = (i >= 1 && i <= xlen) ? xs[i - 1] : (uint8_t)0xFE;
-  }
-  int ip = i0 - 1;
-  s.diag_in = (ip < 0 || ip > 2 * bw) ? TG_MINV : (ip == 0 ? 0 : -(ip + 1));
-  s.sendD = TG_MINV; s.sendR = TG_MINV; s.sendCM = TG_MINV; s.sendCR = 0;
-}
-
-// One column for one lane.  recvD/recvR/recvCM/recvCR come from lane-1 (TG_MINV for lane 0).
-// bits[] receives the packed 2-bit directions of the lane's R cells (0 diag, 1 Del, 2 Ins), 16 cells per word.
-template <int R>
-TG_HD void tg_swg_lane_step(TgSwgLane<R>& s, int lane, int j, uint8_t y, int xlen, int bw, int recvD, int recvR,
-                            int recvCM, int recvCR, uint32_t (&bits)[(R + 15) / 16]) {
-  const int i0 = lane * R;
-  const int lo = j - bw > 0 ? j - bw : 0;
-  int hi = j + bw > 2 * bw ? j + bw : 2 * bw;
-  if (hi > xlen) hi = xlen;
-  int upD = recvD, upR = recvR, dg = s.diag_in, cm = recvCM, cr = recvCR;
-#pragma unroll
-  for (int b = 0; b < (R + 15) / 16; b++) bits[b] = 0;
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    const int i = i0 + r;
-    int c = s.C[r] - 1 > s.D[r] - 2 ? s.C[r] - 1 : s.D[r] - 2;
-    int rr = upR - 1 > upD - 2 ? upR - 1 : upD - 2;
-    int d = dg + (s.xc[r] == y ? 1 : -1);
-    int nd = d > c ? d : c;
-    nd = nd > rr ? nd : rr;
-    uint32_t dir = (nd == d) ? 0u : ((nd == c) ? 1u : 2u);
-    dg = s.D[r];
-    if (i >= lo && i <= hi) {
-      s.D[r] = nd; s.C[r] = c; upD = nd; upR = rr;
-      bits[r >> 4] |= dir << (2 * (r & 15));
-      if (nd > cm) { cm = nd; cr = i; }
-    } else {
-      upD = TG_MINV; upR = TG_MINV;
-      if (i < lo) { s.D[r] = TG_MINV; s.C[r] = TG_MINV; }
-    }
-  }
-  s.diag_in = recvD;
-  s.sendD = upD; s.sendR = upR; s.sendCM = cm; s.sendCR = cr;
-}
+#ifdef __CUDACC__
+#define TG_NOINLINE __noinline__
+#else
+#define TG_NOINLINE
+#endif
 
 struct TgSwgResult {
   int score, xend, yend;
@@ -349,55 +287,109 @@ struct TgSwgResult {
 template <int R>
 struct TgTraceBytes { static constexpr int value = (2 * R + 7) / 8; };
 
+TG_HD int tg_max(int a, int b) { return a > b ? a : b; }
+
 // W: warp policy (lane, LANES, shfl_up, shfl, any, sync).  xs: x symbols (xlen), ys: y symbols (ncols).
 // ncols = min(ylen, xlen + bw) (later columns are empty and only trigger the x-drop break).
+//
+// Lane state per owned row r (row i = lane*R + r), all for the previous column:
+//   Dm2[r] = D - 2 (what both the vertical-gap open of the row below and the horizontal-gap open of the next
+//   column consume), C[r].  Out-of-band cells hold TG_MINV-ish values: "below the band" rows are never written
+//   (they keep their MIN initialisation), "above the band" rows only need to hand MIN to the row below, so the
+//   per-cell band test feeds just two selects.  C of dead rows drifts by -1 per column, far from wrapping.
 template <int R, class W>
-TG_HDN void tg_swg_fill(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, int ncols, int bw, int x_drop,
-                        uint8_t* trace, TgSwgResult& res, unsigned long long& cells) {
+TG_HDN TG_NOINLINE void tg_swg_fill(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, int ncols, int bw, int x_drop,
+                                    uint8_t* trace, TgSwgResult& res, unsigned long long& cells) {
   constexpr int TB = TgTraceBytes<R>::value;
+  constexpr int NW = (R + 15) / 16;
   const int lane = w.lane();
   const int nl = (xlen + R) / R;  // lanes that own at least one existing row
-  TgSwgLane<R> s;
-  tg_swg_lane_init<R>(s, lane, xs, xlen, bw);
+  const int i0 = lane * R;
+  int Dm2[R], C[R];
+  uint8_t xc[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i = i0 + r;
+    const bool in0 = i <= 2 * bw;  // column 0 initialises rows 0..w-1 (src/swg.rs:62-71)
+    Dm2[r] = in0 ? (i == 0 ? -2 : -(i + 1) - 2) : TG_MINV;
+    C[r] = (in0 && i == 0) ? 0 : TG_MINV;
+    xc[r] = (i >= 1 && i <= xlen) ? xs[i - 1] : (uint8_t)0xFE;
+  }
+  // D(i0-1, 0): the diagonal input of this lane's first row at column 1
+  int diag_in;
+  {
+    const int ip = i0 - 1;
+    diag_in = (ip < 0 || ip > 2 * bw) ? TG_MINV : (ip == 0 ? 0 : -(ip + 1));
+  }
+  int sendDm2 = TG_MINV, sendR = TG_MINV, sendCM = TG_CM_MIN * 1024;
   int max_score = 0, max_i = 0, max_j = 0;
+  unsigned long long ccount = 0;
   bool stop = false;
+  const bool is_last = lane == nl - 1;
   const int nsteps = ncols + nl - 1;
+  const int two_bw = 2 * bw;
   for (int t = 0; t < nsteps; t++) {
-    int pdr = w.shfl_up(tg_pack_dr(s.sendD, s.sendR), 1);
-    int pcm = w.shfl_up(tg_pack_dr(s.sendCM, s.sendCR), 1);
-    int recvD, recvR, recvCM, recvCR;
-    tg_unpack_dr(pdr, recvD, recvR);
-    recvCM = pcm >> 16; recvCR = pcm & 0xffff;
-    if (recvCM == -32768) recvCM = TG_MINV;
-    if (lane == 0) { recvD = TG_MINV; recvR = TG_MINV; recvCM = TG_MINV; recvCR = 0; }
+    int upDm2 = w.shfl_up(sendDm2, 1);
+    int upR = w.shfl_up(sendR, 1);
+    int pcm = w.shfl_up(sendCM, 1);
+    if (lane == 0) { upDm2 = TG_MINV; upR = TG_MINV; pcm = TG_CM_MIN * 1024; }
     const int j = t - lane + 1;
     if (lane < nl && j >= 1 && j <= ncols) {
-      uint32_t bits[(R + 15) / 16];
-      tg_swg_lane_step<R>(s, lane, j, ys[j - 1], xlen, bw, recvD, recvR, recvCM, recvCR, bits);
+      const int next_diag = upDm2 + 2;  // D(i0-1, j) is the diagonal input of column j+1
+      const uint8_t y = ys[j - 1];
+      const int lo = tg_max(j - bw, 0);
+      int hi = tg_max(j + bw, two_bw);
+      hi = hi < xlen ? hi : xlen;
+      const unsigned span = (unsigned)(hi - lo);
+      const int rel0 = i0 - lo;
+      ccount += span + 1u;
+      int cm = pcm >> 10, cr = pcm & 1023;
+      int dg = diag_in;
+      uint32_t bits[NW];
+#pragma unroll
+      for (int b = 0; b < NW; b++) bits[b] = 0;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int c = tg_max(C[r] - 1, Dm2[r]);
+        const int rr = tg_max(upR - 1, upDm2);
+        const int d = dg + (xc[r] == y ? 1 : -1);
+        const int nd = tg_max(tg_max(d, c), rr);
+        const uint32_t gapdir = (nd != c) ? (2u << (2 * (r & 15))) : (1u << (2 * (r & 15)));
+        if (nd != d) bits[r >> 4] |= gapdir;
+        const bool inb = (unsigned)(rel0 + r) <= span;
+        const int dsel = inb ? nd : TG_MINV;
+        dg = Dm2[r] + 2;
+        Dm2[r] = dsel - 2;
+        C[r] = c;
+        upDm2 = dsel - 2;
+        upR = inb ? rr : TG_MINV;
+        if (dsel > cm) cr = i0 + r;
+        cm = tg_max(cm, dsel);
+      }
+      diag_in = next_diag;
+      sendDm2 = upDm2; sendR = upR; sendCM = cm * 1024 + cr;
       uint8_t* tp = trace + ((size_t)(j - 1) * W::LANES + lane) * TB;
 #pragma unroll
       for (int b = 0; b < TB; b++) tp[b] = (uint8_t)(bits[b >> 2] >> (8 * (b & 3)));
-      if (lane == nl - 1) {  // this lane completes column j: src/swg.rs:101-112 / :142-153
-        int lo = j - bw > 0 ? j - bw : 0;
-        int hi = j + bw > 2 * bw ? j + bw : 2 * bw;
-        if (hi > xlen) hi = xlen;
-        if (hi >= lo) cells += (unsigned long long)(hi - lo + 1);
-        if (s.sendCM > max_score) { max_score = s.sendCM; max_i = s.sendCR; max_j = j; }
-        if (s.sendCM < max_score - x_drop) stop = true;
-      }
+      // column bookkeeping (src/swg.rs:101-112 / :142-153): only the last lane sees the complete column, the other
+      // lanes run the same instructions on partial maxima and their result is ignored
+      if (cm > max_score) { max_i = cr; max_j = j; }
+      max_score = tg_max(max_score, cm);
+      stop = is_last && (cm < max_score - x_drop);
     }
     if (w.any(stop)) break;
   }
   res.score = w.shfl(max_score, nl - 1);
   res.xend = w.shfl(max_i, nl - 1);
   res.yend = w.shfl(max_j, nl - 1);
+  if (is_last) cells += ccount;  // cells the reference visits: rows lo(j)..hi(j) of every processed column
   w.sync();
 }
 
 // Traceback (src/swg.rs:170-207) in generation order (end cell -> origin), i.e. rev(operations).
 // Uniform across lanes; only lane 0 of W writes.
 template <int R, class W>
-TG_HDN void tg_swg_traceback(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, const uint8_t* trace,
+TG_HDN TG_NOINLINE void tg_swg_traceback(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, const uint8_t* trace,
                              const TgSwgResult& res, TgOps& out) {
   constexpr int TB = TgTraceBytes<R>::value;
   if (w.lane() == 0) {
@@ -546,6 +538,7 @@ struct TgWarpMem {
   uint32_t* opsT;
   int32_t* stack;    // TG_TREE_STACK
   uint32_t ops_cap;
+  uint64_t* rp;      // packed read (L/16 + 3 words, padded with 0xF)
 };
 
 struct TgAlignParams {
@@ -562,6 +555,76 @@ struct TgAln {
 struct TgCounters {
   unsigned long long cells, n_ext, hits;
 };
+
+// exact-match run lengths between the packed read and a packed sequence (extend_seed_match, src/aligner.rs:410-426)
+TG_HD uint32_t tg_match_fwd(const uint64_t* rp, uint32_t q, uint32_t L, const uint64_t* seq, uint64_t pos, uint64_t seq_end) {
+  uint64_t room = seq_end - pos;
+  uint32_t maxn = L - q;
+  if ((uint64_t)maxn > room) maxn = (uint32_t)room;
+  uint32_t n = 0;
+  while (n < maxn) {
+    uint64_t x = tg_ld16_local(rp, q + n) ^ tg_ld16(seq, pos + n);
+    if (x) { n += (uint32_t)TG_CLZ64(x) >> 2; break; }
+    n += 16;
+  }
+  return n < maxn ? n : maxn;
+}
+TG_HD uint32_t tg_match_bwd(const uint64_t* rp, uint32_t q, const uint64_t* seq, uint64_t pos, uint64_t seq_start) {
+  uint64_t room = pos - seq_start;
+  uint32_t maxn = q;
+  if ((uint64_t)maxn > room) maxn = (uint32_t)room;
+  uint32_t n = 0;
+  while (n < maxn) {
+    uint32_t m = maxn - n < 16 ? maxn - n : 16;
+    uint32_t sh = 4 * (16 - m);
+    uint64_t a = tg_ld16_local(rp, q - n - m) >> sh, b = tg_ld16(seq, pos - n - m) >> sh;
+    uint64_t x = a ^ b;
+    if (x) { n += (uint32_t)TG_CTZ64(x) >> 2; break; }
+    n += m;
+  }
+  return n < maxn ? n : maxn;
+}
+
+// An extend_left_right problem: reference sequence seq[lo_abs, hi_abs) with the seed at r_abs.
+struct TgProblem {
+  const uint64_t* seq;
+  uint64_t lo_abs, hi_abs, r_abs;
+  uint32_t q, len;
+};
+// The y windows extend_left_right hands to SwgExtend (only the first xlen+bw columns can be touched)
+TG_HD void tg_problem_windows(const TgProblem& p, uint32_t L, uint32_t bw, uint32_t& ncR, uint32_t& ncL) {
+  uint32_t xr = L - (p.q + p.len);
+  uint64_t yr = p.hi_abs - (p.r_abs + p.len);
+  ncR = xr == 0 ? 0u : (uint32_t)(yr < (uint64_t)xr + bw ? yr : (uint64_t)xr + bw);
+  uint64_t span = (uint64_t)L + bw;
+  uint64_t ys0 = (p.r_abs - p.lo_abs > span) ? p.r_abs - span : p.lo_abs;
+  uint64_t yl = p.r_abs - ys0;
+  ncL = p.q == 0 ? 0u : (uint32_t)(yl < (uint64_t)p.q + bw ? yl : (uint64_t)p.q + bw);
+}
+template <class W>
+TG_HDN bool tg_same_symbols(W& w, const uint64_t* sa, uint64_t pa, const uint64_t* sb, uint64_t pb, uint32_t n) {
+  bool diff = false;
+  for (uint32_t c = (uint32_t)w.lane() * 16; c < n; c += W::LANES * 16) {
+    uint64_t a = tg_ld16(sa, pa + c), b = tg_ld16(sb, pb + c);
+    uint32_t m = n - c;
+    if (m < 16) { uint64_t k = tg_top_nibbles(m); a &= k; b &= k; }
+    diff |= a != b;
+  }
+  return !w.any(diff);
+}
+// Two problems are the same DP (same x parts, same y symbols in every column that can be visited): then
+// extend_left_right returns the same score, read span, operations and the same offsets relative to the seed.
+template <class W>
+TG_HDN bool tg_same_problem(W& w, const TgProblem& a, const TgProblem& b, uint32_t L, uint32_t bw) {
+  if (a.q != b.q || a.len != b.len) return false;
+  uint32_t ar, al, br, bl;
+  tg_problem_windows(a, L, bw, ar, al);
+  tg_problem_windows(b, L, bw, br, bl);
+  if (ar != br || al != bl) return false;
+  if (ar && !tg_same_symbols(w, a.seq, a.r_abs + a.len, b.seq, b.r_abs + b.len, ar)) return false;
+  if (al && !tg_same_symbols(w, a.seq, a.r_abs - al, b.seq, b.r_abs - bl, al)) return false;
+  return true;
+}
 
 // extend_left_right (src/aligner.rs:352-407) on packed sequence `seq`: the reference sequence is
 // seq[lo_abs, hi_abs), the seed sits at absolute position r_abs.  Result coordinates are absolute in `seq`.
@@ -700,7 +763,15 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
   if (seq_end > (uint64_t)aref.end_idx - 1) seq_end = (uint64_t)aref.end_idx - 1;
   TgAln gx;
   TgOps A{m.opsA, 0};
-  tg_extend_left_right<W, RMAX>(w, m, ix.text4, seq_start, seq_end, ref_idx, q, len, L, bw, x_drop, gx, A, ctr);
+  TgProblem pg{ix.text4, seq_start, seq_end, ref_idx, q, len}, pb = pg;
+  unsigned long long g_cells, g_ext, b_cells = 0, b_ext = 0;
+  {
+    unsigned long long c0 = ctr.cells, e0n = ctr.n_ext;
+    tg_extend_left_right<W, RMAX>(w, m, ix.text4, seq_start, seq_end, ref_idx, q, len, L, bw, x_drop, gx, A, ctr);
+    // counters live on different lanes (cells: the DP's last lane, extensions: lane 0): take the warp total
+    g_cells = w.sum64(ctr.cells - c0);
+    g_ext = w.sum64(ctr.n_ext - e0n);
+  }
 
   // transcripts whose exon intersects the SEED (src/aligner.rs:231-258)
   bool have_tx = false;
@@ -723,16 +794,42 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
     uint32_t tr = 0, tq = 0, tl = 0;
     if (!tg_lift_mem_to_tx(ix.te_start, ix.te_end, e0, e1, ref_idx, q, len, tr, tq, tl)) continue;
     // extend_seed_match (src/aligner.rs:410-426): right, then left
-    while (tr + tl < tlen && tq + tl < L && tg_code_at(ix.txseq4, t0 + tr + tl) == m.rd[tq + tl]) tl++;
-    while (tr > 0 && tq > 0 && tg_code_at(ix.txseq4, t0 + tr - 1) == m.rd[tq - 1]) { tr--; tq--; tl++; }
+    tl += tg_match_fwd(m.rp, tq + tl, L, ix.txseq4, t0 + tr + tl, t1);
+    {
+      uint32_t back = tg_match_bwd(m.rp, tq, ix.txseq4, t0 + tr, t0);
+      tr -= back; tq -= back; tl += back;
+    }
     TgAln ta;
-    tg_extend_left_right<W, RMAX>(w, m, ix.txseq4, t0, t1, t0 + tr, tq, tl, L, bw, x_drop, ta, Bcur, ctr);
-    ta.ystart -= (uint32_t)t0;  // back to transcript coordinates (t0 < 2^32 is checked at index build)
-    ta.yend -= (uint32_t)t0;
-    if (!have_tx || ta.score > best.score) {  // strictly better only: first wins ties (:249)
-      have_tx = true; best = ta; best_tx = tx_idx; best_tlen = tlen;
-      uint32_t* t = Bcur.w; Bcur.w = Bbest.w; Bbest.w = t;
-      Bbest.n = Bcur.n;
+    TgProblem pt{ix.txseq4, t0, t1, t0 + tr, tq, tl};
+    unsigned long long c0 = ctr.cells, e0n = ctr.n_ext;
+    bool reuse_best = false;
+    if (tg_same_problem<W>(w, pt, pg, L, bw)) {
+      // same DP as the genome extension: reuse its result (the reference recomputes it; count its cells)
+      ta = gx;
+      ta.ystart = (uint32_t)(pt.r_abs - ((uint64_t)ref_idx - gx.ystart));
+      ta.yend = (uint32_t)(pt.r_abs + ((uint64_t)gx.yend - ref_idx));
+      for (uint32_t i = lane; i < A.n; i += W::LANES) Bcur.w[i] = A.w[i];
+      Bcur.n = A.n;
+      if (lane == 0) { ctr.cells += g_cells; ctr.n_ext += g_ext; }
+      w.sync();
+    } else if (have_tx && tg_same_problem<W>(w, pt, pb, L, bw)) {
+      // same DP as the best transcript so far: equal score, so it cannot replace it (:249)
+      ta = best;
+      reuse_best = true;
+      if (lane == 0) { ctr.cells += b_cells; ctr.n_ext += b_ext; }
+    } else {
+      tg_extend_left_right<W, RMAX>(w, m, ix.txseq4, t0, t1, t0 + tr, tq, tl, L, bw, x_drop, ta, Bcur, ctr);
+    }
+    unsigned long long t_cells = w.sum64(ctr.cells - c0), t_ext = w.sum64(ctr.n_ext - e0n);
+    if (!reuse_best) {
+      ta.ystart -= (uint32_t)t0;  // back to transcript coordinates (t0 < 2^32 is checked at index build)
+      ta.yend -= (uint32_t)t0;
+      if (!have_tx || ta.score > best.score) {  // strictly better only: first wins ties (:249)
+        have_tx = true; best = ta; best_tx = tx_idx; best_tlen = tlen;
+        pb = pt; b_cells = t_cells; b_ext = t_ext;
+        uint32_t* t = Bcur.w; Bcur.w = Bbest.w; Bbest.w = t;
+        Bbest.n = Bcur.n;
+      }
     }
     if (ta.score >= (int32_t)L) break;  // :253-257
   }
@@ -982,6 +1079,15 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
                           uint32_t r, TgCounters& ctr) {
   const int lane = w.lane();
   for (uint32_t i = lane; i < L; i += W::LANES) m.rd[i] = (uint8_t)tg_ascii_code(TG_LDG(bases + off + i));
+  w.sync();
+  for (uint32_t wi = lane; wi < L / 16 + 3; wi += W::LANES) {
+    uint64_t word = 0;
+    for (uint32_t t = 0; t < 16; t++) {
+      uint32_t p = wi * 16 + t;
+      word |= (uint64_t)(p < L ? m.rd[p] : (uint8_t)TG_C_PAD) << ((15 - t) * 4);
+    }
+    m.rp[wi] = word;
+  }
   w.sync();
   // :130-138
   float prod = P.opts.min_aln_score_percent * (float)L;

@@ -58,6 +58,12 @@ struct DevWarp {
     return p;
 #endif
   }
+  TG_HD unsigned long long sum64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(TG_FULL, v, d);
+#endif
+    return v;
+  }
   TG_HD void sync() {
 #ifdef __CUDA_ARCH__
     __syncwarp();
@@ -198,7 +204,7 @@ struct ExtParams {
   DevCounters* ctr;
 };
 struct ExtSmemLayout {
-  size_t rd, xs, ys, trace, ops, stack, total;
+  size_t rd, xs, ys, trace, ops, stack, rp, total;
 };
 __host__ __device__ inline ExtSmemLayout ext_smem_layout(uint32_t maxL, uint32_t max_cols, uint32_t trace_bytes, uint32_t ops_cap) {
   ExtSmemLayout l;
@@ -209,6 +215,7 @@ __host__ __device__ inline ExtSmemLayout ext_smem_layout(uint32_t maxL, uint32_t
   l.trace = o; o += align16(trace_bytes);
   l.ops = o; o += align16((size_t)ops_cap * 4) * 4;
   l.stack = o; o += align16(TG_TREE_STACK * 4);
+  l.rp = o; o += align16((maxL / 16 + 4) * 8);
   l.total = o;
   return l;
 }
@@ -224,6 +231,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
   m.opsA = (uint32_t*)(base + lay.ops); m.opsB = (uint32_t*)(base + lay.ops + ob);
   m.opsC = (uint32_t*)(base + lay.ops + 2 * ob); m.opsT = (uint32_t*)(base + lay.ops + 3 * ob);
   m.stack = (int32_t*)(base + lay.stack);
+  m.rp = (uint64_t*)(base + lay.rp);
   m.ops_cap = p.ops_cap;
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   TgWarpScratch sc{p.cands + (size_t)gw * TG_MAX_ALNS_PER_READ, p.arena + (size_t)gw * p.arena_cap, p.arena_cap,
