@@ -138,6 +138,11 @@ void* tg_ctx_stream(tg_ctx* ctx);
 /* Device time (CUDA events on the context's stream) of the seeding and extension kernels of the last
  * tg_align_batch* / tg_seed_batch call, in milliseconds. */
 void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms);
+/* Cell accounting.  By default an extension stops as soon as no later DP cell can STRICTLY exceed the running
+ * maximum (bound: best cell of the column + symbols of x still unread).  Score, end cell, traceback and therefore
+ * every output record are unchanged, but fewer cells are visited than the reference's loops visit.  With `on` = 1
+ * every column the reference runs is run, so tg_result.swg_cells / *cells equal the reference's cell count. */
+void tg_ctx_set_exact_cell_count(tg_ctx* ctx, int on);
 /* Size of the context's k-mer table in bytes. */
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx);
 

@@ -87,11 +87,11 @@ class HostCtx:
         assert tot >= 0
         return pool[:tot], first, count
 
-    def align_batch(self, bases, offs, lanes=1):
+    def align_batch(self, bases, offs, lanes=1, bound_stop=False):
         bases = np.ascontiguousarray(bases, np.uint8)
         offs = np.ascontiguousarray(offs, np.uint64)
         n = len(offs) - 1
-        r = lib().ht_align_batch(self.h, _p(bases), _p(offs), n, lanes)
+        r = lib().ht_align_batch(self.h, _p(bases), _p(offs), n, lanes, int(bound_stop))
         assert r
         r = C.c_void_p(r)
         info = (C.c_uint64 * 6)()
@@ -118,7 +118,7 @@ def expand_seeds(pool, first, count, sa, r):
     return out
 
 
-def swg_extend_batch(xs, xoff, ys, yoff, bw, x_drop, lanes=1):
+def swg_extend_batch(xs, xoff, ys, yoff, bw, x_drop, lanes=1, bound_stop=False):
     n = len(bw)
     xs = np.ascontiguousarray(xs, np.uint8); ys = np.ascontiguousarray(ys, np.uint8)
     xoff = np.ascontiguousarray(xoff, np.uint64); yoff = np.ascontiguousarray(yoff, np.uint64)
@@ -128,7 +128,7 @@ def swg_extend_batch(xs, xoff, ys, yoff, bw, x_drop, lanes=1):
     cap = int(len(xs) + len(ys) + 4 * n + 16)
     ops = np.zeros(cap, np.uint32)
     cells = C.c_uint64()
-    tot = lib().ht_swg_extend_batch(_p(xs), _p(xoff), _p(ys), _p(yoff), n, _p(bw), _p(x_drop), lanes, _p(score),
+    tot = lib().ht_swg_extend_batch(_p(xs), _p(xoff), _p(ys), _p(yoff), n, _p(bw), _p(x_drop), lanes, int(bound_stop), _p(score),
                                     _p(xend), _p(yend), _p(ops_off), _p(ops), C.c_uint64(cap), C.byref(cells))
     assert tot >= 0
     return dict(score=score, xend=xend, yend=yend, ops_off=ops_off, ops=ops[:tot].copy(), cells=cells.value)

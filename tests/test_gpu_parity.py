@@ -56,13 +56,18 @@ def test_random_worlds_records_and_seeds(seed):
     for r in range(0, n, 7):
         rd = bases[int(offs[r]): int(offs[r + 1])].tobytes()
         assert ht.expand_seeds(seeds, first, count, sa, r) == oix.all_smems(rd, k), (seed, r)
-    # records == align_read
+    # records == align_read (default mode: bound-stopped extensions)
     res = al.align_reads(bases, offs)
     oix.counters_reset()
     ores = oix.align_batch(bases, offs, k=k, pct=pct, min_score=mins, score_range=srange, intron_mode=intron)
     _cmp(res, ores, n)
-    assert res.counters["swg_cells"] == oix.counters()["swg_cells"]
+    assert res.counters["swg_cells"] <= oix.counters()["swg_cells"]
     assert res.counters["seed_hits"] == oix.counters()["hits"]
+    # exact-cell mode: same records, and the DP cell count equals the reference's
+    al.set_exact_cell_count(True)
+    res = al.align_reads(bases, offs)
+    _cmp(res, ores, n)
+    assert res.counters["swg_cells"] == oix.counters()["swg_cells"]
 
 
 def test_chrM_synthM_records():
@@ -115,11 +120,13 @@ def test_swg_batch_matches_oracle():
     al = Aligner(ix, AlignOpts(min_seed_len=3))
     for seed, kw in ((1, {}), (2, dict(alphabet=b"AC")), (3, dict(max_x=200, bw_choices=(3, 30, 100)))):
         xs, xo, ys, yo, bw, xd = swg_pairs(seed, 6000, **kw)
-        a = al.swg_extend_batch(xs, xo, ys, yo, bw, xd)
         b = orc.swg_extend_batch(xs, xo, ys, yo, bw, xd)
-        for key in ("score", "xend", "yend", "ops_off", "ops"):
-            assert np.array_equal(a[key], b[key]), (seed, key)
-        assert a["cells"] == b["cells"]
+        for exact in (False, True):
+            al.set_exact_cell_count(exact)
+            a = al.swg_extend_batch(xs, xo, ys, yo, bw, xd)
+            for key in ("score", "xend", "yend", "ops_off", "ops"):
+                assert np.array_equal(a[key], b[key]), (seed, key, exact)
+            assert a["cells"] == b["cells"] if exact else a["cells"] <= b["cells"]
     # reference KATs (src/swg.rs:249-317)
     kats = [(b"AAAAAAAA", b"AAAAAAAA", 1, 1), (b"AAAAATTT", b"AAAAAAAA", 1, 1), (b"AAATAAAA", b"AAAAAAAA", 1, 1),
             (b"AAATTTT", b"AAACCTTTT", 2, 3)]

@@ -62,22 +62,27 @@ def test_align_records_equal_oracle_random_worlds(seed):
     d = ht.compare_alignments(res, ores, n)
     assert not d, d[:3]
     assert res["flags"] == 0 and res["cells"] == oix.counters()["swg_cells"] and res["hits"] == oix.counters()["hits"]
+    # bound-stopped extensions (the product default): identical records, never more cells
+    resb = ctx.align_batch(bases, offs, lanes=1, bound_stop=True)
+    assert not ht.compare_alignments(resb, ores, n) and resb["cells"] <= res["cells"]
     # the 32-lane wavefront (what the GPU executes) on a slice
     m = 12
-    res32 = ctx.align_batch(bases[: int(offs[m])], offs[: m + 1], lanes=32)
-    d = ht.compare_alignments(res32, ores, m)
-    assert not d, d[:3]
+    for bs in (False, True):
+        res32 = ctx.align_batch(bases[: int(offs[m])], offs[: m + 1], lanes=32, bound_stop=bs)
+        d = ht.compare_alignments(res32, ores, m)
+        assert not d, d[:3]
 
 
 def test_swg_wavefront_equals_oracle():
     for seed, lanes, n, kw in ((1, 1, 3000, {}), (2, 32, 150, {}), (3, 32, 60, dict(max_x=200, bw_choices=(3, 30, 100))),
                                (4, 1, 1500, dict(alphabet=b"AC"))):
         xs, xo, ys, yo, bw, xd = swg_pairs(seed, n, **kw)
-        a = ht.swg_extend_batch(xs, xo, ys, yo, bw, xd, lanes=lanes)
         b = orc.swg_extend_batch(xs, xo, ys, yo, bw, xd)
-        for key in ("score", "xend", "yend", "ops_off", "ops"):
-            assert np.array_equal(a[key], b[key]), (seed, key)
-        assert a["cells"] == b["cells"]
+        for bs in (False, True):
+            a = ht.swg_extend_batch(xs, xo, ys, yo, bw, xd, lanes=lanes, bound_stop=bs)
+            for key in ("score", "xend", "yend", "ops_off", "ops"):
+                assert np.array_equal(a[key], b[key]), (seed, key, bs)
+            assert a["cells"] <= b["cells"] if bs else a["cells"] == b["cells"]
 
 
 def test_chrM_reads_records():

@@ -146,7 +146,7 @@ struct WarpBuffers {
     a.assign(cap, 0); b.assign(cap, 0); c.assign(cap, 0); t.assign(cap, 0);
     stack.assign(TG_TREE_STACK, 0);
     rp2.assign(maxL / 16 + 4, 0);
-    return TgWarpMem{rd.data(), xs.data(), ys.data(), trace.data(), a.data(), b.data(), c.data(), t.data(), stack.data(), cap, rp2.data()};
+    return TgWarpMem{rd.data(), xs.data(), ys.data(), trace.data(), a.data(), b.data(), c.data(), t.data(), stack.data(), cap, rp2.data(), false};
   }
   TgSeedMem seed_mem(uint32_t maxL) {
     rp.assign(maxL / 16 + 4, 0); hits.assign(maxL + 1, TgSeedHit{0, 0, 0}); sm.assign(maxL + 1, tg_seed{}); grp.assign(maxL + 1, 0);
@@ -238,7 +238,7 @@ struct HtResult {
   int flags = 0;
 };
 
-void* ht_align_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes) {
+void* ht_align_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes, int bound_stop) {
   HostCtx* c = (HostCtx*)cp;
   uint32_t maxL = 1;
   for (uint32_t r = 0; r < n; r++) maxL = std::max<uint32_t>(maxL, (uint32_t)(offs[r + 1] - offs[r]));
@@ -251,6 +251,7 @@ void* ht_align_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint3
   WarpBuffers wb;
   TgSeedMem sm = wb.seed_mem(maxL);
   TgWarpMem wm = wb.mem(maxL, max_bw_for(c->opts, maxL), lanes);
+  wm.bound_stop = bound_stop != 0;
   wb.cands.resize(TG_MAX_ALNS_PER_READ);
   wb.arena.resize(1 << 16);
   std::vector<uint16_t> order(2 * TG_MAX_ALNS_PER_READ);
@@ -290,7 +291,7 @@ void ht_result_free(void* rp) { delete (HtResult*)rp; }
 
 // SwgExtend::extend batch with raw byte comparison (like tg_swg_extend_batch)
 long long ht_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uint8_t* ys, const uint64_t* yoff,
-                              uint32_t n, const uint32_t* bw, const int32_t* x_drop, int lanes, int32_t* score,
+                              uint32_t n, const uint32_t* bw, const int32_t* x_drop, int lanes, int bound_stop, int32_t* score,
                               uint32_t* xend, uint32_t* yend, uint64_t* ops_off, uint32_t* ops, uint64_t ops_cap,
                               uint64_t* cells_out) {
   unsigned long long total = 0, cells = 0;
@@ -308,7 +309,7 @@ long long ht_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uin
       TgSwgResult r{0, 0, 0};
       TgOps lo{buf.data(), 0};
       tg_swg_extend(w, xs + xoff[t], ys + yoff[t], xlen, ylen_c, (int)bw[t], x_drop[t], trace.data(), r, lo,
-                    lc[w.lane()], le[w.lane()]);
+                    lc[w.lane()], le[w.lane()], bound_stop != 0);
       if (w.lane() == 0) { res = r; o.n = lo.n; }
     });
     for (auto v : lc) cells += v;

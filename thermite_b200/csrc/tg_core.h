@@ -299,7 +299,7 @@ TG_HD int tg_max(int a, int b) { return a > b ? a : b; }
 //   per-cell band test feeds just two selects.  C of dead rows drifts by -1 per column, far from wrapping.
 template <int R, class W>
 TG_HDN TG_NOINLINE void tg_swg_fill(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, int ncols, int bw, int x_drop,
-                                    uint8_t* trace, TgSwgResult& res, unsigned long long& cells) {
+                                    uint8_t* trace, TgSwgResult& res, unsigned long long& cells, bool bound_stop) {
   constexpr int TB = TgTraceBytes<R>::value;
   constexpr int NW = (R + 15) / 16;
   const int lane = w.lane();
@@ -321,7 +321,8 @@ TG_HDN TG_NOINLINE void tg_swg_fill(W& w, const uint8_t* xs, const uint8_t* ys, 
     const int ip = i0 - 1;
     diag_in = (ip < 0 || ip > 2 * bw) ? TG_MINV : (ip == 0 ? 0 : -(ip + 1));
   }
-  int sendDm2 = TG_MINV, sendR = TG_MINV, sendCM = TG_CM_MIN * 1024;
+  int sendDm2 = TG_MINV, sendR = TG_MINV, sendCM = TG_CM_MIN * 1024, sendUB = TG_CM_MIN;
+  const int rem0 = xlen - i0;  // x symbols left below row i0: a cell (i, j) can gain at most xlen - i more
   int max_score = 0, max_i = 0, max_j = 0;
   unsigned long long ccount = 0;
   bool stop = false;
@@ -332,7 +333,8 @@ TG_HDN TG_NOINLINE void tg_swg_fill(W& w, const uint8_t* xs, const uint8_t* ys, 
     int upDm2 = w.shfl_up(sendDm2, 1);
     int upR = w.shfl_up(sendR, 1);
     int pcm = w.shfl_up(sendCM, 1);
-    if (lane == 0) { upDm2 = TG_MINV; upR = TG_MINV; pcm = TG_CM_MIN * 1024; }
+    int ub = w.shfl_up(sendUB, 1);
+    if (lane == 0) { upDm2 = TG_MINV; upR = TG_MINV; pcm = TG_CM_MIN * 1024; ub = TG_CM_MIN; }
     const int j = t - lane + 1;
     if (lane < nl && j >= 1 && j <= ncols) {
       const int next_diag = upDm2 + 2;  // D(i0-1, j) is the diagonal input of column j+1
@@ -365,9 +367,10 @@ TG_HDN TG_NOINLINE void tg_swg_fill(W& w, const uint8_t* xs, const uint8_t* ys, 
         upR = inb ? rr : TG_MINV;
         if (dsel > cm) cr = i0 + r;
         cm = tg_max(cm, dsel);
+        ub = tg_max(ub, dsel + (rem0 - r));
       }
       diag_in = next_diag;
-      sendDm2 = upDm2; sendR = upR; sendCM = cm * 1024 + cr;
+      sendDm2 = upDm2; sendR = upR; sendCM = cm * 1024 + cr; sendUB = ub;
       uint8_t* tp = trace + ((size_t)(j - 1) * W::LANES + lane) * TB;
 #pragma unroll
       for (int b = 0; b < TB; b++) tp[b] = (uint8_t)(bits[b >> 2] >> (8 * (b & 3)));
@@ -375,7 +378,10 @@ TG_HDN TG_NOINLINE void tg_swg_fill(W& w, const uint8_t* xs, const uint8_t* ys, 
       // lanes run the same instructions on partial maxima and their result is ignored
       if (cm > max_score) { max_i = cr; max_j = j; }
       max_score = tg_max(max_score, cm);
-      stop = is_last && (cm < max_score - x_drop);
+      // x-drop of the reference, or (optionally) a proof that no later cell can STRICTLY exceed the running maximum:
+      // every path into a later column crosses this one at some (i, j) and gains at most +1 per remaining x symbol,
+      // so max_i(D(i,j) + xlen - i) <= max_score leaves score, end cell and traceback unchanged.
+      stop = is_last && ((cm < max_score - x_drop) || (bound_stop && ub <= max_score));
     }
     if (w.any(stop)) break;
   }
@@ -424,7 +430,7 @@ TG_HDN TG_NOINLINE void tg_swg_traceback(W& w, const uint8_t* xs, const uint8_t*
 template <int R, class W>
 TG_HDN void tg_swg_extend_r(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, int ylen, int bw, int x_drop,
                             uint8_t* trace, TgSwgResult& res, TgOps& out, unsigned long long& cells,
-                            unsigned long long& n_ext) {
+                            unsigned long long& n_ext, bool bound_stop) {
   if (xlen == 0 || ylen == 0) {
     res.score = 0; res.xend = 0; res.yend = 0;
     if (xlen > 0 && w.lane() == 0) tg_ops_push(out, TG_OP_XCLIP, (uint32_t)xlen);
@@ -433,7 +439,7 @@ TG_HDN void tg_swg_extend_r(W& w, const uint8_t* xs, const uint8_t* ys, int xlen
     return;
   }
   int ncols = ylen < xlen + bw ? ylen : xlen + bw;
-  tg_swg_fill<R, W>(w, xs, ys, xlen, ncols, bw, x_drop, trace, res, cells);
+  tg_swg_fill<R, W>(w, xs, ys, xlen, ncols, bw, x_drop, trace, res, cells, bound_stop);
   if (w.lane() == 0) n_ext++;
   tg_swg_traceback<R, W>(w, xs, ys, xlen, trace, res, out);
 }
@@ -456,15 +462,15 @@ TG_HD int tg_swg_rows_class(int xlen, int lanes) {
 template <class W, int RMAX = 16>
 TG_HDN void tg_swg_extend(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, int ylen, int bw, int x_drop,
                           uint8_t* trace, TgSwgResult& res, TgOps& out, unsigned long long& cells,
-                          unsigned long long& n_ext) {
+                          unsigned long long& n_ext, bool bound_stop = false) {
   if constexpr (W::LANES == 1) {
-    tg_swg_extend_r<TG_MAX_READ_LEN + 1, W>(w, xs, ys, xlen, ylen, bw, x_drop, trace, res, out, cells, n_ext);
+    tg_swg_extend_r<TG_MAX_READ_LEN + 1, W>(w, xs, ys, xlen, ylen, bw, x_drop, trace, res, out, cells, n_ext, bound_stop);
     return;
   } else {
     const int cls = tg_swg_rows_class(xlen, W::LANES);
 #define TG_SWG_CASE(RR)                                                                                   \
   if constexpr (RMAX >= RR) {                                                                             \
-    if (cls == RR) { tg_swg_extend_r<RR, W>(w, xs, ys, xlen, ylen, bw, x_drop, trace, res, out, cells, n_ext); return; } \
+    if (cls == RR) { tg_swg_extend_r<RR, W>(w, xs, ys, xlen, ylen, bw, x_drop, trace, res, out, cells, n_ext, bound_stop); return; } \
   }
     TG_SWG_CASE(1) TG_SWG_CASE(2) TG_SWG_CASE(3) TG_SWG_CASE(4) TG_SWG_CASE(6) TG_SWG_CASE(8) TG_SWG_CASE(12) TG_SWG_CASE(16)
 #undef TG_SWG_CASE
@@ -539,6 +545,7 @@ struct TgWarpMem {
   int32_t* stack;    // TG_TREE_STACK
   uint32_t ops_cap;
   uint64_t* rp;      // packed read (L/16 + 3 words, padded with 0xF)
+  bool bound_stop;   // stop an extension once no later cell can beat the running maximum (same records, fewer cells)
 };
 
 struct TgAlignParams {
@@ -646,7 +653,7 @@ TG_HDN void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64
     if (xlen > 0)
       for (int t = lane; t < ncols; t += W::LANES) m.ys[t] = (uint8_t)tg_code_at(seq, y0 + (uint64_t)t);
     w.sync();
-    tg_swg_extend<W, RMAX>(w, m.rd + q + len, m.ys, xlen, ylen, (int)bw, x_drop, m.trace, rr, tmp, ctr.cells, ctr.n_ext);
+    tg_swg_extend<W, RMAX>(w, m.rd + q + len, m.ys, xlen, ylen, (int)bw, x_drop, m.trace, rr, tmp, ctr.cells, ctr.n_ext, m.bound_stop);
   }
   // ---- left: x = rev(read[..q]), y = rev(seq[max(r-(L+bw), lo) .. r)) (src/aligner.rs:364-375)
   out.n = 0;
@@ -661,7 +668,7 @@ TG_HDN void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64
     if (xlen > 0)
       for (int t = lane; t < ncols; t += W::LANES) m.ys[t] = (uint8_t)tg_code_at(seq, r_abs - 1 - (uint64_t)t);
     w.sync();
-    tg_swg_extend<W, RMAX>(w, m.xs, m.ys, xlen, ylen, (int)bw, x_drop, m.trace, rl, out, ctr.cells, ctr.n_ext);
+    tg_swg_extend<W, RMAX>(w, m.xs, m.ys, xlen, ylen, (int)bw, x_drop, m.trace, rl, out, ctr.cells, ctr.n_ext, m.bound_stop);
   }
   // ---- stitch (src/aligner.rs:377-406)
   if (lane == 0) {

@@ -200,6 +200,7 @@ struct ExtParams {
   uint32_t* arena;    // [n_warps][arena_cap]
   uint32_t arena_cap;
   uint16_t* order;    // [n_warps][2 * TG_MAX_ALNS_PER_READ]
+  int bound_stop;
   TgAlignOut out;
   DevCounters* ctr;
 };
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
   m.stack = (int32_t*)(base + lay.stack);
   m.rp = (uint64_t*)(base + lay.rp);
   m.ops_cap = p.ops_cap;
+  m.bound_stop = p.bound_stop != 0;
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   TgWarpScratch sc{p.cands + (size_t)gw * TG_MAX_ALNS_PER_READ, p.arena + (size_t)gw * p.arena_cap, p.arena_cap,
                    p.order + (size_t)gw * 2 * TG_MAX_ALNS_PER_READ};
@@ -264,6 +266,7 @@ struct SwgParams {
   uint64_t* task_off; uint32_t* task_len;
   uint32_t* ops; unsigned long long ops_cap;
   uint32_t max_xlen, max_cols, trace_bytes, ops_words;
+  int bound_stop;
   DevCounters* ctr;
 };
 __host__ __device__ inline size_t swg_smem_per_warp(uint32_t max_xlen, uint32_t max_cols, uint32_t trace_bytes, uint32_t ops_words) {
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_swg_batch(SwgParams p
     __syncwarp();
     TgSwgResult res{0, 0, 0};
     TgOps o{obuf, 0};
-    tg_swg_extend<DevWarp, RMAX>(w, sx, sy, xlen, ylen, bw, p.x_drop[t], trace, res, o, cells, n_ext);
+    tg_swg_extend<DevWarp, RMAX>(w, sx, sy, xlen, ylen, bw, p.x_drop[t], trace, res, o, cells, n_ext, p.bound_stop != 0);
     unsigned long long dst = 0;
     if (lane == 0 && o.n) dst = atomicAdd(&p.ctr->swg_ops_used, (unsigned long long)o.n);
     dst = __shfl_sync(TG_FULL, dst, 0);
@@ -374,6 +377,7 @@ struct tg_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   float last_seed_ms = 0.f, last_extend_ms = 0.f;
+  int exact_cells = 0;  // 1: run every column the reference runs (swg_cells == reference count)
   int n_sms = 0;
   TgSlot* slots = nullptr;
   uint64_t n_slots = 0;
@@ -551,6 +555,9 @@ void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms) 
   if (seed_ms) *seed_ms = ctx ? ctx->last_seed_ms : 0.f;
   if (extend_ms) *extend_ms = ctx ? ctx->last_extend_ms : 0.f;
 }
+void tg_ctx_set_exact_cell_count(tg_ctx* ctx, int on) {
+  if (ctx) ctx->exact_cells = on ? 1 : 0;
+}
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots * sizeof(TgSlot) : 0; }
 
 }  // extern "C"
@@ -615,6 +622,7 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.seeds = (const tg_seed*)c->d_seeds.p; p.read_seed_first = (const uint64_t*)c->d_seed_first.p;
   p.read_seed_count = (const uint32_t*)c->d_seed_count.p;
   p.cands = (TgCand*)c->d_cands.p; p.arena = (uint32_t*)c->d_arena.p; p.arena_cap = arena_cap; p.order = (uint16_t*)c->d_order.p;
+  p.bound_stop = c->exact_cells ? 0 : 1;
   p.out.read_aln_first = (uint64_t*)c->d_aln_first.p; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p;
   p.out.alns = (tg_aln*)c->d_alns.p; p.out.ops = (uint32_t*)c->d_ops.p;
   p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;
@@ -834,6 +842,7 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   p.score = (int32_t*)c->s_score.p; p.xend = (uint32_t*)c->s_xe.p; p.yend = (uint32_t*)c->s_ye.p;
   p.task_off = (uint64_t*)c->s_toff.p; p.task_len = (uint32_t*)c->s_tlen.p; p.ops = (uint32_t*)c->s_ops.p; p.ops_cap = worst_ops;
   p.max_xlen = max_xlen; p.max_cols = max_cols; p.trace_bytes = trace_bytes; p.ops_words = ops_words; p.ctr = c->d_ctr;
+  p.bound_stop = c->exact_cells ? 0 : 1;
   CU_CHECK(cudaEventRecord(c->ev0, c->stream));
   kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
   CU_CHECK(cudaGetLastError());
