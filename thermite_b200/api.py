@@ -20,7 +20,7 @@ from typing import List, Optional
 import numpy as np
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(_CSRC, "libthermite_gpu.so")
+LIB_PATH = os.environ.get("THERMITE_GPU_LIB", os.path.join(_CSRC, "libthermite_gpu.so"))
 _LIB = None
 
 TG_MAX_READ_LEN = 512

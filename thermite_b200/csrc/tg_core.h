@@ -17,6 +17,12 @@
 #define TG_HDN
 #endif
 
+#ifdef __CUDACC__
+#define TG_NOINLINE __noinline__
+#else
+#define TG_NOINLINE
+#endif
+
 #ifdef __CUDA_ARCH__
 #define TG_LDG(p) __ldg(p)
 #define TG_CLZ64(x) __clzll((long long)(x))
@@ -273,12 +279,6 @@ TG_HD void tg_ops_reverse(TgOps& o) {
 // ------------------------------------------------------------------------------------------------
 #define TG_CM_MIN (-(1 << 20))  // "no in-band cell yet" for the per-column running maximum (fits the 22-bit packing)
 
-#ifdef __CUDACC__
-#define TG_NOINLINE __noinline__
-#else
-#define TG_NOINLINE
-#endif
-
 struct TgSwgResult {
   int score, xend, yend;
 };
@@ -499,7 +499,7 @@ TG_HD void tg_tree_begin(TgTreeIter& it, const TgTreeNode* nodes, int32_t root, 
   if (root >= 0) it.stack[it.sp++] = root;
 }
 // returns false when exhausted
-TG_HD bool tg_tree_next(TgTreeIter& it, uint32_t& data) {
+TG_HDN TG_NOINLINE bool tg_tree_next(TgTreeIter& it, uint32_t& data) {
   while (it.sp > 0) {
     int32_t ci = it.stack[--it.sp];
 #ifdef __CUDA_ARCH__
@@ -559,8 +559,28 @@ struct TgAln {
   uint32_t ystart, yend, xstart, xend;
 };
 
+#ifdef TG_PROFILE_PHASES
+#define TG_NPHASE 12
+TG_HD long long tg_clock() {
+#ifdef __CUDA_ARCH__
+  return clock64();
+#else
+  return 0;
+#endif
+}
+#define TG_TDECL() long long tg_t0_ = tg_clock()
+#define TG_T0() tg_t0_ = tg_clock()
+#define TG_T(ctr, k) do { long long tg_t1_ = tg_clock(); (ctr).ph[k] += (unsigned long long)(tg_t1_ - tg_t0_); tg_t0_ = tg_t1_; } while (0)
+#else
+#define TG_TDECL() do {} while (0)
+#define TG_T0() do {} while (0)
+#define TG_T(ctr, k) do {} while (0)
+#endif
 struct TgCounters {
   unsigned long long cells, n_ext, hits;
+#ifdef TG_PROFILE_PHASES
+  unsigned long long ph[TG_NPHASE];
+#endif
 };
 
 // exact-match run lengths between the packed read and a packed sequence (extend_seed_match, src/aligner.rs:410-426)
@@ -622,7 +642,7 @@ TG_HDN bool tg_same_symbols(W& w, const uint64_t* sa, uint64_t pa, const uint64_
 // Two problems are the same DP (same x parts, same y symbols in every column that can be visited): then
 // extend_left_right returns the same score, read span, operations and the same offsets relative to the seed.
 template <class W>
-TG_HDN bool tg_same_problem(W& w, const TgProblem& a, const TgProblem& b, uint32_t L, uint32_t bw) {
+TG_HDN TG_NOINLINE bool tg_same_problem(W& w, const TgProblem& a, const TgProblem& b, uint32_t L, uint32_t bw) {
   if (a.q != b.q || a.len != b.len) return false;
   uint32_t ar, al, br, bl;
   tg_problem_windows(a, L, bw, ar, al);
@@ -637,11 +657,12 @@ TG_HDN bool tg_same_problem(W& w, const TgProblem& a, const TgProblem& b, uint32
 // seq[lo_abs, hi_abs), the seed sits at absolute position r_abs.  Result coordinates are absolute in `seq`.
 // `out` receives the stitched operations: rev(left.ops) ++ Match*len ++ right.ops.
 template <class W, int RMAX = 16>
-TG_HDN void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64_t lo_abs, uint64_t hi_abs,
+TG_HDN TG_NOINLINE void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64_t lo_abs, uint64_t hi_abs,
                                  uint64_t r_abs, uint32_t q, uint32_t len, uint32_t L, uint32_t bw, int32_t x_drop,
                                  TgAln& aln, TgOps& out, TgCounters& ctr) {
   const int lane = w.lane();
   TgSwgResult rr, rl;
+  TG_TDECL();
   // ---- right: x = read[q+len..], y = seq[r+len .. hi) (src/aligner.rs:360-362)
   TgOps tmp{m.opsT, 0};
   {
@@ -653,7 +674,9 @@ TG_HDN void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64
     if (xlen > 0)
       for (int t = lane; t < ncols; t += W::LANES) m.ys[t] = (uint8_t)tg_code_at(seq, y0 + (uint64_t)t);
     w.sync();
+    TG_T(ctr, 0);
     tg_swg_extend<W, RMAX>(w, m.rd + q + len, m.ys, xlen, ylen, (int)bw, x_drop, m.trace, rr, tmp, ctr.cells, ctr.n_ext, m.bound_stop);
+    TG_T(ctr, 1);
   }
   // ---- left: x = rev(read[..q]), y = rev(seq[max(r-(L+bw), lo) .. r)) (src/aligner.rs:364-375)
   out.n = 0;
@@ -668,7 +691,9 @@ TG_HDN void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64
     if (xlen > 0)
       for (int t = lane; t < ncols; t += W::LANES) m.ys[t] = (uint8_t)tg_code_at(seq, r_abs - 1 - (uint64_t)t);
     w.sync();
+    TG_T(ctr, 0);
     tg_swg_extend<W, RMAX>(w, m.xs, m.ys, xlen, ylen, (int)bw, x_drop, m.trace, rl, out, ctr.cells, ctr.n_ext, m.bound_stop);
+    TG_T(ctr, 1);
   }
   // ---- stitch (src/aligner.rs:377-406)
   if (lane == 0) {
@@ -682,6 +707,7 @@ TG_HDN void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64
   aln.yend = (uint32_t)(r_abs + len + (uint64_t)rr.yend);
   aln.xstart = q - (uint32_t)rl.xend;
   aln.xend = q + len + (uint32_t)rr.xend;
+  TG_T(ctr, 2);
 }
 
 // lift_mem_to_tx (src/txome.rs:82-103): first exon in tx order intersecting the seed
@@ -706,7 +732,7 @@ TG_HD bool tg_lift_mem_to_tx(const uint32_t* te_start, const uint32_t* te_end, u
 // lift_tx_to_gx (src/txome.rs:110-160) on RLE words.  Before EVERY unit op the reference advances at most
 // one exon when the running transcript coordinate sits on an exon end, pushing Yclip(intron length) -- also
 // in front of ops that consume no reference (the documented trailing-Ins quirk).
-TG_HD void tg_lift_tx_to_gx(const uint32_t* te_start, const uint32_t* te_end, uint32_t e0, uint32_t e1,
+TG_HDN TG_NOINLINE void tg_lift_tx_to_gx(const uint32_t* te_start, const uint32_t* te_end, uint32_t e0, uint32_t e1,
                             const TgOps& tx_ops, uint32_t tx_ystart, uint32_t& g_ystart, uint32_t& g_yend, TgOps& out) {
   out.n = 0;
   uint32_t i = tx_ystart, exon_sum = 0, ex = e0;
@@ -760,6 +786,7 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
                               TgCounters& ctr) {
   const TgIndexDev& ix = P.ix;
   const int lane = w.lane();
+  TG_TDECL();
   uint32_t ref_id = tg_idx_to_ref(ix.refs, ix.n_refs, ref_idx);
   TgRef aref = ix.refs[ref_id];
   // genome window (src/aligner.rs:212-215)
@@ -772,6 +799,7 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
   TgOps A{m.opsA, 0};
   TgProblem pg{ix.text4, seq_start, seq_end, ref_idx, q, len}, pb = pg;
   unsigned long long g_cells, g_ext, b_cells = 0, b_ext = 0;
+  TG_T(ctr, 3);
   {
     unsigned long long c0 = ctr.cells, e0n = ctr.n_ext;
     tg_extend_left_right<W, RMAX>(w, m, ix.text4, seq_start, seq_end, ref_idx, q, len, L, bw, x_drop, gx, A, ctr);
@@ -788,11 +816,13 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
   TgOps Bcur{m.opsB, 0}, Bbest{m.opsC, 0};
   TgTreeIter it;
   tg_tree_begin(it, ix.exon_nodes, ix.exon_root, m.stack, ref_idx, ref_idx + len);
+  TG_T0();
   for (;;) {
     uint32_t tx_idx = 0;
     int more = 0;
     if (lane == 0) more = tg_tree_next(it, tx_idx) ? 1 : 0;
     more = w.shfl(more, 0);
+    TG_T(ctr, 4);
     if (!more) break;
     tx_idx = (uint32_t)w.shfl((int)tx_idx, 0);
     uint32_t e0 = TG_LDG(ix.tx_exon_off + tx_idx), e1 = TG_LDG(ix.tx_exon_off + tx_idx + 1);
@@ -810,6 +840,7 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
     TgProblem pt{ix.txseq4, t0, t1, t0 + tr, tq, tl};
     unsigned long long c0 = ctr.cells, e0n = ctr.n_ext;
     bool reuse_best = false;
+    TG_T(ctr, 5);
     if (tg_same_problem<W>(w, pt, pg, L, bw)) {
       // same DP as the genome extension: reuse its result (the reference recomputes it; count its cells)
       ta = gx;
@@ -827,6 +858,7 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
     } else {
       tg_extend_left_right<W, RMAX>(w, m, ix.txseq4, t0, t1, t0 + tr, tq, tl, L, bw, x_drop, ta, Bcur, ctr);
     }
+    TG_T0();
     unsigned long long t_cells = w.sum64(ctr.cells - c0), t_ext = w.sum64(ctr.n_ext - e0n);
     if (!reuse_best) {
       ta.ystart -= (uint32_t)t0;  // back to transcript coordinates (t0 < 2^32 is checked at index build)
@@ -838,8 +870,10 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
         Bbest.n = Bcur.n;
       }
     }
+    TG_T(ctr, 6);
     if (ta.score >= (int32_t)L) break;  // :253-257
   }
+  TG_T0();
 
   tg_aln& a = c.a;
   a.ref_id = ref_id;
@@ -895,6 +929,7 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
     w.sync();
   }
   a.ylen = r2.len;
+  TG_T(ctr, 7);
 }
 
 // stable bottom-up merge sort of an index array (a -> sorted in a; b is scratch of n entries)
@@ -919,7 +954,7 @@ TG_HD void tg_merge_sort_idx(uint16_t* a, uint16_t* b, uint32_t n, Less less) {
 // End-of-read filters on the accepted candidates (src/aligner.rs:177-187 and filter_overlapping :317-349).
 // Serial; `order`/`tmp` are scratch arrays of n entries.  Returns the number of output records; order[0..ret)
 // lists candidate indices in output order.
-TG_HD uint32_t tg_finalize_read(const TgCand* cands, uint32_t n, int32_t max_aln_score, int32_t range,
+TG_HDN TG_NOINLINE uint32_t tg_finalize_read(const TgCand* cands, uint32_t n, int32_t max_aln_score, int32_t range,
                                 uint16_t* order, uint16_t* tmp) {
   // retain (:177-179)
   uint32_t m = 0;
@@ -1085,6 +1120,7 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
                           const tg_seed* seeds, uint32_t n_seeds, const TgWarpScratch& sc, const TgAlignOut& out,
                           uint32_t r, TgCounters& ctr) {
   const int lane = w.lane();
+  TG_TDECL();
   for (uint32_t i = lane; i < L; i += W::LANES) m.rd[i] = (uint8_t)tg_ascii_code(TG_LDG(bases + off + i));
   w.sync();
   for (uint32_t wi = lane; wi < L / 16 + 3; wi += W::LANES) {
@@ -1106,6 +1142,7 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
   const int32_t range = (int32_t)P.opts.multimap_score_range;
   uint32_t n_acc = 0, arena_used = 0;
   bool capped = false;
+  TG_T(ctr, 8);
 
   for (uint32_t si = 0; si < n_seeds && !capped; si++) {
     tg_seed sd = seeds[si];
@@ -1115,6 +1152,7 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
       TgCand c;
       TgOps gx_ops{nullptr, 0}, tx_ops{nullptr, 0};
       tg_align_seed_hit<W, RMAX>(w, m, P, L, ref_idx, sd.query_idx, sd.len, bw, (int32_t)x_drop, c, gx_ops, tx_ops, ctr);
+      TG_T0();
       if (!P.opts.intron_mode && c.a.aln_type != TG_ALN_EXONIC) continue;  // :146-151
       int32_t s = c.a.score;
       if (s < P.opts.min_aln_score || s < min_aln_score || s < max_aln_score - range) continue;  // :154-159
@@ -1159,9 +1197,11 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
       arena_used += need;
       n_acc++;
       w.sync();
+      TG_T(ctr, 9);
     }
   }
   w.sync_global();
+  TG_T0();
   // :177-187
   uint16_t* order = sc.order;
   uint16_t* tmp = order + TG_MAX_ALNS_PER_READ;
@@ -1205,4 +1245,5 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
     out.read_aln_count[r] = (uint32_t)k;
   }
   w.sync();
+  TG_T(ctr, 10);
 }

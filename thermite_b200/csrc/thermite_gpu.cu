@@ -96,6 +96,7 @@ struct DevCounters {
       work_swg, kmer_groups;
   int flags;
   int pad;
+  unsigned long long phase[16];
 };
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
   TgWarpScratch sc{p.cands + (size_t)gw * TG_MAX_ALNS_PER_READ, p.arena + (size_t)gw * p.arena_cap, p.arena_cap,
                    p.order + (size_t)gw * 2 * TG_MAX_ALNS_PER_READ};
   DevWarp w;
-  TgCounters ctr{0, 0, 0};
+  TgCounters ctr{};
   for (;;) {
     uint32_t r = next_work(&p.ctr->work_ext);
     if (r >= p.n_reads) break;
@@ -252,6 +253,9 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
     if (c) atomicAdd(&p.ctr->cells, c);
     if (e) atomicAdd(&p.ctr->n_ext, e);
     if (h) atomicAdd(&p.ctr->hits, h);
+#ifdef TG_PROFILE_PHASES
+    for (int k = 0; k < TG_NPHASE; k++) atomicAdd(&p.ctr->phase[k], ctr.ph[k]);
+#endif
   }
 }
 
@@ -557,6 +561,9 @@ void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms) 
 }
 void tg_ctx_set_exact_cell_count(tg_ctx* ctx, int on) {
   if (ctx) ctx->exact_cells = on ? 1 : 0;
+}
+void tg_ctx_debug_phases(const tg_ctx* ctx, uint64_t* out16) {
+  for (int k = 0; k < 16; k++) out16[k] = ctx ? ctx->h_ctr->phase[k] : 0;
 }
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots * sizeof(TgSlot) : 0; }
 
