@@ -334,6 +334,27 @@ struct Avl {
   }
 };
 
+// sorted-by-start interval list with the tree's find() rank
+std::vector<TgStab> stab_list(const Avl& t, uint64_t& maxlen) {
+  std::vector<TgStab> out(t.nodes.size());
+  maxlen = 0;
+  std::vector<int32_t> stack;
+  if (t.root >= 0) stack.push_back(t.root);
+  uint32_t rank = 0;
+  while (!stack.empty()) {  // node, then right subtree, then left subtree
+    int32_t c = stack.back();
+    stack.pop_back();
+    const TgTreeNode& n = t.nodes[c];
+    if (n.left >= 0) stack.push_back(n.left);
+    if (n.right >= 0) stack.push_back(n.right);
+    out[rank] = TgStab{n.start, n.end, n.data, rank};
+    maxlen = std::max<uint64_t>(maxlen, (uint64_t)n.end - n.start);
+    rank++;
+  }
+  std::stable_sort(out.begin(), out.end(), [](const TgStab& a, const TgStab& b) { return a.start < b.start; });
+  return out;
+}
+
 struct BlobWriter {
   std::vector<uint8_t> buf;
   uint64_t reserve_section(size_t nbytes) {
@@ -517,6 +538,8 @@ tg_status build_index(const char* fasta, size_t fasta_len, const char* gtf, size
   h.off_te_start = w.put(te_start);
   h.off_te_end = w.put(te_end);
   h.off_txseq4 = w.put(txseq4);
+  h.off_exon_stab = w.put(stab_list(exon_tree, h.exon_maxlen));
+  h.off_gene_stab = w.put(stab_list(gene_tree, h.gene_maxlen));
   h.device_bytes = (w.buf.size() + 255) & ~(uint64_t)255;
   h.off_ref_names = w.put_strings(ref_names);
   h.off_tx_ids = w.put_strings(tx_ids);

@@ -5,6 +5,7 @@
 // at barriers for every shuffle / vote.  `tests/` uses this to check the kernel LOGIC against the oracle
 // on CPU.  The product (thermite_b200/, libthermite_gpu.so) never loads this library: there is no CPU
 // fallback in the product path.
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <memory>
@@ -23,6 +24,9 @@ struct HostWarp1 {
   unsigned long long shfl64(unsigned long long v, int) { return v; }
   bool any(bool p) { return p; }
   unsigned long long sum64(unsigned long long v) { return v; }
+  uint32_t ballot(bool p) { return p ? 1u : 0u; }
+  uint32_t reduce_min_u32(uint32_t v) { return v; }
+  int reduce_max_i32(int v) { return v; }
   void sync() {}
   void sync_global() {}
   unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
@@ -83,6 +87,30 @@ struct HostWarp32 {
     sh->bar.wait();
     return r;
   }
+  uint32_t ballot(bool p) {
+    sh->xi[l] = p;
+    sh->bar.wait();
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= (sh->xi[i] ? 1u : 0u) << i;
+    sh->bar.wait();
+    return r;
+  }
+  int reduce_max_i32(int v) {
+    sh->xi[l] = v;
+    sh->bar.wait();
+    int r = sh->xi[0];
+    for (int i = 1; i < 32; i++) r = std::max(r, sh->xi[i]);
+    sh->bar.wait();
+    return r;
+  }
+  uint32_t reduce_min_u32(uint32_t v) {
+    sh->xl[l] = v;
+    sh->bar.wait();
+    uint32_t r = 0xFFFFFFFFu;
+    for (int i = 0; i < 32; i++) r = std::min<uint32_t>(r, (uint32_t)sh->xl[i]);
+    sh->bar.wait();
+    return r;
+  }
   unsigned long long sum64(unsigned long long v) {
     sh->xl[l] = v;
     sh->bar.wait();
@@ -106,6 +134,10 @@ TgIndexDev view_of(const tg_index_host* ix) {
   d.refs = (const TgRef*)(b + h->off_refs);
   d.exon_nodes = (const TgTreeNode*)(b + h->off_exon_nodes);
   d.gene_nodes = (const TgTreeNode*)(b + h->off_gene_nodes);
+  d.exon_stab = (const TgStab*)(b + h->off_exon_stab);
+  d.gene_stab = (const TgStab*)(b + h->off_gene_stab);
+  d.n_exon_stab = (uint32_t)h->n_exon_nodes; d.n_gene_stab = (uint32_t)h->n_gene_nodes;
+  d.exon_maxlen = (uint32_t)h->exon_maxlen; d.gene_maxlen = (uint32_t)h->gene_maxlen;
   d.tx_seq_off = (const uint64_t*)(b + h->off_tx_seq_off);
   d.tx_exon_off = (const uint32_t*)(b + h->off_tx_exon_off);
   d.te_start = (const uint32_t*)(b + h->off_te_start);

@@ -392,21 +392,94 @@ TG_HDN TG_NOINLINE void tg_swg_fill(W& w, const uint8_t* xs, const uint8_t* ys, 
   w.sync();
 }
 
+// Narrow bands (2*bw + 1 <= 31 cells per column; every hit after a good first one): column-synchronous variant.
+// Lane l tracks the single in-band row i with i % 32 == l, all lanes work on the SAME column, and the vertical gap
+// state R(i) = max_{i' < i}(H(i') - 2 - (i - 1 - i')) with H = max(diag, horizontal) -- an exact rewrite of
+// R(i) = max(R(i-1) - 1, D(i-1) - 2) because D = max(H, R) and extending beats re-opening -- is an exclusive prefix
+// max over the band rows, done with log2(band) shuffles.  One column costs ~60 instructions instead of ~110 per
+// wavefront step and there is no pipeline fill/drain.  Trace: byte [(j-1)*32 + (i & 31)], 2 bits used.
+// W adds: reduce_max_i32(int), reduce_min_u32(u32).
+template <class W>
+TG_HDN TG_NOINLINE void tg_swg_fill_narrow(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, int ncols, int bw, int x_drop,
+                                           uint8_t* trace, TgSwgResult& res, unsigned long long& cells, bool bound_stop) {
+  const int lane = w.lane();
+  const int two_bw = 2 * bw;
+  int myrow = lane;  // column 0: rows 0..2bw live in lanes 0..2bw (src/swg.rs:62-71)
+  int Dp = lane <= two_bw ? (lane == 0 ? 0 : -(lane + 1)) : TG_MINV;
+  int Cp = lane == 0 ? 0 : TG_MINV;
+  uint8_t xc = (lane >= 1 && lane <= xlen) ? xs[lane - 1] : (uint8_t)0xFE;
+  int max_score = 0, max_i = 0, max_j = 0;
+  unsigned long long ccount = 0;
+  for (int j = 1; j <= ncols; j++) {
+    const int lo = tg_max(j - bw, 0);
+    int hi = tg_max(j + bw, two_bw);
+    hi = hi < xlen ? hi : xlen;
+    const int rl = (lane - lo) & 31;  // position of this lane's row inside the band
+    const int i = lo + rl;
+    // D(i-1, j-1) lives in the previous lane; read it BEFORE that lane may recycle itself for a new row (the row
+    // above the band's top row was in the band one column ago and is the top row's diagonal input)
+    const int diag = w.shfl(Dp, (lane + 31) & 31);
+    if (i != myrow) {  // the old row left the band at the top; the new one enters from below with MIN state
+      myrow = i;
+      Dp = TG_MINV; Cp = TG_MINV;
+      xc = (i >= 1 && i <= xlen) ? xs[i - 1] : (uint8_t)0xFE;
+    }
+    const bool inb = i <= hi;
+    const uint8_t y = ys[j - 1];
+    const int c = tg_max(Cp - 1, Dp - 2);
+    const int d = (i == 0 ? TG_MINV : diag) + (xc == y ? 1 : -1);
+    const int h = inb ? tg_max(d, c) : TG_MINV;
+    // exclusive prefix max of A(i') = H(i') + i' over the band rows above this one
+    int v = h + i;
+    const int span = hi - lo;
+    for (int dd = 1; dd <= span; dd <<= 1) {
+      const int t = w.shfl(v, (lane - dd) & 31);
+      if (rl >= dd) v = tg_max(v, t);
+    }
+    const int ex = w.shfl(v, (lane + 31) & 31);
+    const int rr = rl >= 1 ? ex - i - 1 : TG_MINV;
+    const int nd = inb ? tg_max(h, rr) : TG_MINV;
+    const uint32_t dir = (nd == d) ? 0u : ((nd == c) ? 1u : 2u);
+    Dp = nd; Cp = c;
+    trace[(size_t)(j - 1) * 32 + (i & 31)] = (uint8_t)dir;
+    // column bookkeeping (uniform): band max, first row attaining it, upper bound on anything later
+    const int cm = w.reduce_max_i32(nd);
+    ccount += (unsigned)(span + 1);
+    if (cm > max_score) {
+      max_i = (int)w.reduce_min_u32((inb && nd == cm) ? (uint32_t)i : 0x7fffffffu);
+      max_j = j;
+      max_score = cm;
+    }
+    bool stop = cm < max_score - x_drop;
+    if (bound_stop) {
+      const int ub = w.reduce_max_i32(inb ? nd + (xlen - i) : TG_MINV);
+      stop = stop || ub <= max_score;
+    }
+    if (stop) break;
+  }
+  res.score = max_score; res.xend = max_i; res.yend = max_j;
+  if (lane == 0) cells += ccount;
+  w.sync();
+}
+
 // Traceback (src/swg.rs:170-207) in generation order (end cell -> origin), i.e. rev(operations).
 // Uniform across lanes; only lane 0 of W writes.
 template <int R, class W>
 TG_HDN TG_NOINLINE void tg_swg_traceback(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, const uint8_t* trace,
                              const TgSwgResult& res, TgOps& out) {
-  constexpr int TB = TgTraceBytes<R>::value;
+  constexpr int TB = TgTraceBytes<R == 0 ? 1 : R>::value;
   if (w.lane() == 0) {
     int i = res.xend, j = res.yend;
     if (i < xlen) tg_ops_push(out, TG_OP_XCLIP, (uint32_t)(xlen - i));
     while (i > 0 || j > 0) {
       uint32_t dir;
       if (j == 0) dir = 2;  // column 0 is all Ins (src/swg.rs:65,70)
-      else {
-        const int rr = i % R;
-        const uint8_t* tp = trace + ((size_t)(j - 1) * W::LANES + (i / R)) * TB;
+      else if constexpr (R == 0) {
+        dir = trace[(size_t)(j - 1) * 32 + (i & 31)] & 3u;
+      } else {
+        constexpr int RR = R == 0 ? 1 : R;
+        const int rr = i % RR;
+        const uint8_t* tp = trace + ((size_t)(j - 1) * W::LANES + (i / RR)) * TB;
         dir = ((uint32_t)tp[rr >> 2] >> (2 * (rr & 3))) & 3u;
       }
       if (dir == 0) {
@@ -439,7 +512,8 @@ TG_HDN void tg_swg_extend_r(W& w, const uint8_t* xs, const uint8_t* ys, int xlen
     return;
   }
   int ncols = ylen < xlen + bw ? ylen : xlen + bw;
-  tg_swg_fill<R, W>(w, xs, ys, xlen, ncols, bw, x_drop, trace, res, cells, bound_stop);
+  if constexpr (R == 0) tg_swg_fill_narrow<W>(w, xs, ys, xlen, ncols, bw, x_drop, trace, res, cells, bound_stop);
+  else tg_swg_fill<R, W>(w, xs, ys, xlen, ncols, bw, x_drop, trace, res, cells, bound_stop);
   if (w.lane() == 0) n_ext++;
   tg_swg_traceback<R, W>(w, xs, ys, xlen, trace, res, out);
 }
@@ -467,6 +541,10 @@ TG_HDN void tg_swg_extend(W& w, const uint8_t* xs, const uint8_t* ys, int xlen, 
     tg_swg_extend_r<TG_MAX_READ_LEN + 1, W>(w, xs, ys, xlen, ylen, bw, x_drop, trace, res, out, cells, n_ext, bound_stop);
     return;
   } else {
+    if (W::LANES == 32 && 2 * bw + 1 <= 31) {
+      tg_swg_extend_r<0, W>(w, xs, ys, xlen, ylen, bw, x_drop, trace, res, out, cells, n_ext, bound_stop);
+      return;
+    }
     const int cls = tg_swg_rows_class(xlen, W::LANES);
 #define TG_SWG_CASE(RR)                                                                                   \
   if constexpr (RMAX >= RR) {                                                                             \
@@ -499,7 +577,7 @@ TG_HD void tg_tree_begin(TgTreeIter& it, const TgTreeNode* nodes, int32_t root, 
   if (root >= 0) it.stack[it.sp++] = root;
 }
 // returns false when exhausted
-TG_HDN TG_NOINLINE bool tg_tree_next(TgTreeIter& it, uint32_t& data) {
+TG_HD bool tg_tree_next(TgTreeIter& it, uint32_t& data) {
   while (it.sp > 0) {
     int32_t ci = it.stack[--it.sp];
 #ifdef __CUDA_ARCH__
@@ -518,6 +596,83 @@ TG_HDN TG_NOINLINE bool tg_tree_next(TgTreeIter& it, uint32_t& data) {
     }
   }
   return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative interval stabbing on the start-sorted lists (replaces the pointer-chasing tree walk on the
+// device): a 32-ary search bounds the candidates, the lanes test them in parallel, and results are handed out
+// in ascending find() rank, which is exactly the order rust-bio's IntervalTree::find yields them.
+// W adds: ballot(bool) -> u32 lane mask, reduce_min_u32(u32).
+// ------------------------------------------------------------------------------------------------
+TG_HD TgStab tg_stab_load(const TgStab* a, uint32_t i) {
+#ifdef __CUDA_ARCH__
+  const uint4 v = __ldg((const uint4*)(a + i));
+  return TgStab{v.x, v.y, v.z, v.w};
+#else
+  return a[i];
+#endif
+}
+TG_HD uint32_t tg_popc(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__popc(v);
+#else
+  return (uint32_t)__builtin_popcount(v);
+#endif
+}
+// first index whose start >= key
+template <class W>
+TG_HDN uint32_t tg_stab_lower_bound(W& w, const TgStab* a, uint32_t n, uint32_t key) {
+  uint32_t lo = 0, hi = n;
+  if constexpr (W::LANES == 1) {
+    while (lo < hi) {
+      uint32_t mid = lo + ((hi - lo) >> 1);
+      if (a[mid].start < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  } else {
+    const uint32_t lane = (uint32_t)w.lane();
+    while (hi - lo > (uint32_t)W::LANES) {
+      const uint32_t step = (hi - lo + W::LANES - 1) / W::LANES;
+      const uint32_t idx = lo + lane * step;
+      const bool less = idx < hi && tg_stab_load(a, idx).start < key;
+      const uint32_t c = tg_popc(w.ballot(less));  // starts are sorted: the probes that are < key form a prefix
+      const uint32_t nhi = lo + c * step;
+      if (c) lo = lo + (c - 1) * step + 1;
+      if (nhi < hi) hi = nhi;
+    }
+    const uint32_t idx = lo + lane;
+    const bool less = idx < hi && tg_stab_load(a, idx).start < key;
+    return lo + tg_popc(w.ballot(less));
+  }
+}
+struct TgStabRange {
+  uint32_t lo, hi, qs, qe;
+};
+template <class W>
+TG_HDN TgStabRange tg_stab_begin(W& w, const TgStab* a, uint32_t n, uint32_t maxlen, uint32_t qs, uint32_t qe) {
+  TgStabRange r;
+  r.qs = qs; r.qe = qe;
+  // an interval reaching past qs starts after qs - maxlen; one starting at or after qe cannot intersect
+  r.lo = tg_stab_lower_bound(w, a, n, qs >= maxlen ? qs - maxlen + 1 : 0u);
+  r.hi = tg_stab_lower_bound(w, a, n, qe);
+  return r;
+}
+// the intersecting interval with the smallest rank >= min_rank; false when there is none
+template <class W>
+TG_HDN bool tg_stab_next(W& w, const TgStab* a, const TgStabRange& r, uint32_t min_rank, uint32_t& rank, uint32_t& data) {
+  uint32_t best = 0xFFFFFFFFu, bdata = 0;
+  for (uint32_t i = r.lo + (uint32_t)w.lane(); i < r.hi; i += W::LANES) {
+    TgStab e = tg_stab_load(a, i);
+    if (e.start < r.qe && r.qs < e.end && e.rank >= min_rank && e.rank < best) { best = e.rank; bdata = e.data; }
+  }
+  const uint32_t m = w.reduce_min_u32(best);
+  if (m == 0xFFFFFFFFu) return false;
+  const uint32_t owners = w.ballot(best == m);
+  int src = 0;
+  while (!((owners >> src) & 1u)) src++;
+  data = (uint32_t)w.shfl((int)bdata, src);
+  rank = m;
+  return true;
 }
 
 // Index::idx_to_ref (src/index.rs:287-290): first ref whose end_idx > idx
@@ -642,7 +797,7 @@ TG_HDN bool tg_same_symbols(W& w, const uint64_t* sa, uint64_t pa, const uint64_
 // Two problems are the same DP (same x parts, same y symbols in every column that can be visited): then
 // extend_left_right returns the same score, read span, operations and the same offsets relative to the seed.
 template <class W>
-TG_HDN TG_NOINLINE bool tg_same_problem(W& w, const TgProblem& a, const TgProblem& b, uint32_t L, uint32_t bw) {
+TG_HDN bool tg_same_problem(W& w, const TgProblem& a, const TgProblem& b, uint32_t L, uint32_t bw) {
   if (a.q != b.q || a.len != b.len) return false;
   uint32_t ar, al, br, bl;
   tg_problem_windows(a, L, bw, ar, al);
@@ -657,7 +812,7 @@ TG_HDN TG_NOINLINE bool tg_same_problem(W& w, const TgProblem& a, const TgProble
 // seq[lo_abs, hi_abs), the seed sits at absolute position r_abs.  Result coordinates are absolute in `seq`.
 // `out` receives the stitched operations: rev(left.ops) ++ Match*len ++ right.ops.
 template <class W, int RMAX = 16>
-TG_HDN TG_NOINLINE void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64_t lo_abs, uint64_t hi_abs,
+TG_HDN void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64_t lo_abs, uint64_t hi_abs,
                                  uint64_t r_abs, uint32_t q, uint32_t len, uint32_t L, uint32_t bw, int32_t x_drop,
                                  TgAln& aln, TgOps& out, TgCounters& ctr) {
   const int lane = w.lane();
@@ -732,7 +887,7 @@ TG_HD bool tg_lift_mem_to_tx(const uint32_t* te_start, const uint32_t* te_end, u
 // lift_tx_to_gx (src/txome.rs:110-160) on RLE words.  Before EVERY unit op the reference advances at most
 // one exon when the running transcript coordinate sits on an exon end, pushing Yclip(intron length) -- also
 // in front of ops that consume no reference (the documented trailing-Ins quirk).
-TG_HDN TG_NOINLINE void tg_lift_tx_to_gx(const uint32_t* te_start, const uint32_t* te_end, uint32_t e0, uint32_t e1,
+TG_HD void tg_lift_tx_to_gx(const uint32_t* te_start, const uint32_t* te_end, uint32_t e0, uint32_t e1,
                             const TgOps& tx_ops, uint32_t tx_ystart, uint32_t& g_ystart, uint32_t& g_yend, TgOps& out) {
   out.n = 0;
   uint32_t i = tx_ystart, exon_sum = 0, ex = e0;
@@ -814,17 +969,15 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
   TgAln best{0, 0, 0, 0, 0};
   uint32_t best_tlen = 0;
   TgOps Bcur{m.opsB, 0}, Bbest{m.opsC, 0};
-  TgTreeIter it;
-  tg_tree_begin(it, ix.exon_nodes, ix.exon_root, m.stack, ref_idx, ref_idx + len);
+  const TgStabRange xr = tg_stab_begin<W>(w, ix.exon_stab, ix.n_exon_stab, ix.exon_maxlen, ref_idx, ref_idx + len);
+  uint32_t next_rank = 0;
   TG_T0();
   for (;;) {
-    uint32_t tx_idx = 0;
-    int more = 0;
-    if (lane == 0) more = tg_tree_next(it, tx_idx) ? 1 : 0;
-    more = w.shfl(more, 0);
+    uint32_t tx_idx = 0, xrank = 0;
+    const bool more = tg_stab_next<W>(w, ix.exon_stab, xr, next_rank, xrank, tx_idx);
     TG_T(ctr, 4);
     if (!more) break;
-    tx_idx = (uint32_t)w.shfl((int)tx_idx, 0);
+    next_rank = xrank + 1;
     uint32_t e0 = TG_LDG(ix.tx_exon_off + tx_idx), e1 = TG_LDG(ix.tx_exon_off + tx_idx + 1);
     uint64_t t0 = TG_LDG(ix.tx_seq_off + tx_idx), t1 = TG_LDG(ix.tx_seq_off + tx_idx + 1);
     uint32_t tlen = (uint32_t)(t1 - t0);
@@ -899,15 +1052,9 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
     tx_ops = Bbest;
   } else {
     // first gene (in find order) whose span intersects the ALIGNMENT (src/aligner.rs:283-306)
-    uint32_t gene = 0;
-    int found = 0;
-    if (lane == 0) {
-      TgTreeIter gi;
-      tg_tree_begin(gi, ix.gene_nodes, ix.gene_root, m.stack, gx.ystart, gx.yend);
-      found = tg_tree_next(gi, gene) ? 1 : 0;
-    }
-    found = w.shfl(found, 0);
-    gene = (uint32_t)w.shfl((int)gene, 0);
+    uint32_t gene = 0, grank = 0;
+    const TgStabRange gr = tg_stab_begin<W>(w, ix.gene_stab, ix.n_gene_stab, ix.gene_maxlen, gx.ystart, gx.yend);
+    const bool found = tg_stab_next<W>(w, ix.gene_stab, gr, 0u, grank, gene);
     a.aln_type = found ? TG_ALN_INTRONIC : TG_ALN_INTERGENIC;
     a.tx_or_gene_idx = found ? gene : 0xFFFFFFFFu;
     a.score = gx.score; a.xstart = gx.xstart; a.xend = gx.xend;
@@ -954,7 +1101,7 @@ TG_HD void tg_merge_sort_idx(uint16_t* a, uint16_t* b, uint32_t n, Less less) {
 // End-of-read filters on the accepted candidates (src/aligner.rs:177-187 and filter_overlapping :317-349).
 // Serial; `order`/`tmp` are scratch arrays of n entries.  Returns the number of output records; order[0..ret)
 // lists candidate indices in output order.
-TG_HDN TG_NOINLINE uint32_t tg_finalize_read(const TgCand* cands, uint32_t n, int32_t max_aln_score, int32_t range,
+TG_HD uint32_t tg_finalize_read(const TgCand* cands, uint32_t n, int32_t max_aln_score, int32_t range,
                                 uint16_t* order, uint16_t* tmp) {
   // retain (:177-179)
   uint32_t m = 0;

@@ -25,12 +25,18 @@ struct alignas(16) TgTreeNode {  // 32 bytes: two 128-bit loads on the device
   uint32_t pad0, pad1;
 };
 
+// One interval of a stab list: sorted by start; `rank` is the interval's position in the un-pruned traversal of the
+// rust-bio AVL tree (node, right subtree, left subtree), so results ordered by rank reproduce find()'s order.
+struct alignas(16) TgStab {
+  uint32_t start, end, data, rank;
+};
+
 struct TgRef {
   uint32_t start_idx, end_idx, len;
   uint32_t strand_rank;  // bit0 = strand (1 forward), bits 1.. = rank of the name in byte order (filter_overlapping key)
 };
 
-#define TG_BLOB_MAGIC 0x3230424947544854ull /* "THTGIB02" */
+#define TG_BLOB_MAGIC 0x3330424947544854ull /* "THTGIB03" */
 
 // Position-independent header at offset 0 of the index blob.  All off_* are byte offsets from the blob
 // start, 256-byte aligned.
@@ -44,7 +50,9 @@ struct TgBlobHeader {
       off_te_start, off_te_end, off_txseq4;
   // host-only metadata (string tables: u64 offsets[n+1] followed by bytes)
   uint64_t off_ref_names, off_tx_ids, off_gene_ids, off_gene_names, off_tx_gene, off_tx_strand;
-  uint64_t reserved[8];
+  // interval lists sorted by start for warp-cooperative stabbing (rank = position in the tree's find() order)
+  uint64_t off_exon_stab, off_gene_stab, exon_maxlen, gene_maxlen;
+  uint64_t reserved[4];
 };
 
 // Device-side view (plain pointers into the device copy of the blob).
@@ -54,6 +62,9 @@ struct TgIndexDev {
   const TgRef* refs;
   const TgTreeNode* exon_nodes;
   const TgTreeNode* gene_nodes;
+  const TgStab* exon_stab;
+  const TgStab* gene_stab;
+  uint32_t n_exon_stab, n_gene_stab, exon_maxlen, gene_maxlen;
   const uint64_t* tx_seq_off;
   const uint32_t* tx_exon_off;
   const uint32_t* te_start;

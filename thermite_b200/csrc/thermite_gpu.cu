@@ -58,6 +58,27 @@ struct DevWarp {
     return p;
 #endif
   }
+  TG_HD uint32_t ballot(bool p) {
+#ifdef __CUDA_ARCH__
+    return __ballot_sync(TG_FULL, p);
+#else
+    return p ? 1u : 0u;
+#endif
+  }
+  TG_HD int reduce_max_i32(int v) {
+#ifdef __CUDA_ARCH__
+    return __reduce_max_sync(TG_FULL, v);
+#else
+    return v;
+#endif
+  }
+  TG_HD uint32_t reduce_min_u32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __reduce_min_sync(TG_FULL, v);
+#else
+    return v;
+#endif
+  }
   TG_HD unsigned long long sum64(unsigned long long v) {
 #ifdef __CUDA_ARCH__
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(TG_FULL, v, d);
@@ -417,6 +438,10 @@ tg_status adopt_blob(tg_index* ix, const void* d_blob, size_t nbytes) {
   d.refs = (const TgRef*)(b + h.off_refs);
   d.exon_nodes = (const TgTreeNode*)(b + h.off_exon_nodes);
   d.gene_nodes = (const TgTreeNode*)(b + h.off_gene_nodes);
+  d.exon_stab = (const TgStab*)(b + h.off_exon_stab);
+  d.gene_stab = (const TgStab*)(b + h.off_gene_stab);
+  d.n_exon_stab = (uint32_t)h.n_exon_nodes; d.n_gene_stab = (uint32_t)h.n_gene_nodes;
+  d.exon_maxlen = (uint32_t)h.exon_maxlen; d.gene_maxlen = (uint32_t)h.gene_maxlen;
   d.tx_seq_off = (const uint64_t*)(b + h.off_tx_seq_off);
   d.tx_exon_off = (const uint32_t*)(b + h.off_tx_exon_off);
   d.te_start = (const uint32_t*)(b + h.off_te_start);
