@@ -143,6 +143,11 @@ void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms);
  * every output record are unchanged, but fewer cells are visited than the reference's loops visit.  With `on` = 1
  * every column the reference runs is run, so tg_result.swg_cells / *cells equal the reference's cell count. */
 void tg_ctx_set_exact_cell_count(tg_ctx* ctx, int on);
+/* Execution strategy of the hit loop.  on = 1 (default): round pipeline -- thread-per-read control kernels and a
+ * warp-per-task extension kernel, one hit per read per round; reads it cannot finish (many hits, many transcripts per
+ * seed, many accepted alignments) run on the single-warp kernel.  on = 0: every read on the single-warp kernel.
+ * Both produce identical records. */
+void tg_ctx_set_round_pipeline(tg_ctx* ctx, int on);
 /* Size of the context's k-mer table in bytes. */
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx);
 

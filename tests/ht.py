@@ -24,13 +24,14 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_CSRC, "libtg_hosttest.so")
-        srcs = [os.path.join(_CSRC, f) for f in ("hosttest.cpp", "host_index.cpp", "tg_core.h", "tg_internal.h")]
+        srcs = [os.path.join(_CSRC, f) for f in ("hosttest.cpp", "host_index.cpp", "tg_core.h", "tg_rounds.h", "tg_internal.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["make", "-C", _CSRC, "libtg_hosttest.so"], stdout=subprocess.DEVNULL)
         L = C.CDLL(so)
         L.tg_last_error.restype = C.c_char_p
         L.ht_ctx_create.restype = C.c_void_p
         L.ht_align_batch.restype = C.c_void_p
+        L.ht_align_batch_mode.restype = C.c_void_p
         L.ht_seed_batch.restype = C.c_longlong
         L.ht_swg_extend_batch.restype = C.c_longlong
         L.tg_index_host_sa.restype = C.c_void_p
@@ -87,11 +88,11 @@ class HostCtx:
         assert tot >= 0
         return pool[:tot], first, count
 
-    def align_batch(self, bases, offs, lanes=1, bound_stop=False):
+    def align_batch(self, bases, offs, lanes=1, bound_stop=False, rounds=False):
         bases = np.ascontiguousarray(bases, np.uint8)
         offs = np.ascontiguousarray(offs, np.uint64)
         n = len(offs) - 1
-        r = lib().ht_align_batch(self.h, _p(bases), _p(offs), n, lanes, int(bound_stop))
+        r = lib().ht_align_batch_mode(self.h, _p(bases), _p(offs), n, lanes, int(bound_stop), int(rounds))
         assert r
         r = C.c_void_p(r)
         info = (C.c_uint64 * 6)()

@@ -12,7 +12,7 @@
 #include <thread>
 #include <vector>
 
-#include "tg_core.h"
+#include "tg_rounds.h"
 
 namespace {
 
@@ -270,7 +270,14 @@ struct HtResult {
   int flags = 0;
 };
 
+void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes, int bound_stop, int rounds);
 void* ht_align_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes, int bound_stop) {
+  return ht_align_batch_mode(cp, bases, offs, n, lanes, bound_stop, 0);
+}
+
+// rounds = 1: reads go through tg_round_prep / tg_task_run / tg_round_post / tg_round_final (what the GPU's round
+// pipeline executes), falling back to the single-warp path exactly as the device does.
+void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes, int bound_stop, int rounds) {
   HostCtx* c = (HostCtx*)cp;
   uint32_t maxL = 1;
   for (uint32_t r = 0; r < n; r++) maxL = std::max<uint32_t>(maxL, (uint32_t)(offs[r + 1] - offs[r]));
@@ -299,11 +306,56 @@ void* ht_align_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint3
     unsigned long long used = 0, n_smems = 0;
     TgSeedOut sout{pool.data(), &used, pool.size(), sfirst.data(), scount.data(), &res->flags, &n_smems};
     std::vector<TgCounters> lane_ctr(32, TgCounters{0, 0, 0});
-    run_lanes(lanes, [&](auto& w) {
-      tg_seed_read(w, sm, bases, offs[r], L, c->opts.min_seed_len, c->slots.data(), c->slot_mask, c->dev.text4,
-                   c->dev.sa, sout, 0);
-      tg_align_read(w, wm, P, bases, offs[r], L, pool.data() + sfirst[0], scount[0], sc, out, r, lane_ctr[w.lane()]);
-    });
+    bool fast_done = false;
+    if (rounds) {
+      HostWarp1 w1;
+      tg_seed_read(w1, sm, bases, offs[r], L, c->opts.min_seed_len, c->slots.data(), c->slot_mask, c->dev.text4, c->dev.sa, sout, 0);
+      const tg_seed* sd = pool.data() + sfirst[0];
+      uint64_t hits = 0;
+      for (uint32_t i = 0; i < scount[0]; i++) hits += sd[i].count;
+      if (hits <= TG_FAST_MAX_HITS) {
+        TgReadState st;
+        tg_read_state_init(st, L, c->opts, scount[0], sd);
+        std::vector<uint64_t> rp(L / 16 + 4, 0);
+        for (uint32_t wi = 0; wi < L / 16 + 3; wi++) {
+          uint64_t word = 0;
+          for (uint32_t t = 0; t < 16; t++) {
+            uint32_t p = wi * 16 + t;
+            word |= (uint64_t)(p < L ? tg_ascii_code(bases[offs[r] + p]) : (uint32_t)TG_C_PAD) << ((15 - t) * 4);
+          }
+          rp[wi] = word;
+        }
+        TgHit hit;
+        std::vector<TgTask> tasks(4 * TG_PMAX);
+        std::vector<uint32_t> opool(1 << 16);
+        TgCand acc[TG_ACC_MAX];
+        uint32_t arena[TG_ARENA_WORDS];
+        bool ok = true;
+        while (ok && st.status == TG_RS_ACTIVE) {
+          unsigned long long tctr = 0, octr = 0;
+          ok = tg_round_prep(w1, P, rp.data(), st, sd, r, hit, tasks.data(), &tctr, tasks.size());
+          if (!ok) break;
+          for (unsigned long long t = 0; t < tctr; t++) {
+            run_lanes(lanes, [&](auto& w) {
+              tg_task_run(w, c->dev, bases, offs, tasks[t], wm.xs, wm.ys, wm.trace, wm.opsT, opool.data(), &octr, opool.size(),
+                          &res->flags, wm.bound_stop);
+            });
+          }
+          ok = tg_round_post(w1, P, st, sd, scount[0], hit, tasks.data(), opool.data(), acc, arena);
+        }
+        if (ok) {
+          tg_round_final(w1, P, st, acc, arena, out, r);
+          lane_ctr[0].cells += st.cells; lane_ctr[0].n_ext += st.n_ext; lane_ctr[0].hits += st.hits;
+          fast_done = true;
+        }
+      }
+    }
+    if (!fast_done)
+      run_lanes(lanes, [&](auto& w) {
+        tg_seed_read(w, sm, bases, offs[r], L, c->opts.min_seed_len, c->slots.data(), c->slot_mask, c->dev.text4,
+                     c->dev.sa, sout, 0);
+        tg_align_read(w, wm, P, bases, offs[r], L, pool.data() + sfirst[0], scount[0], sc, out, r, lane_ctr[w.lane()]);
+      });
     for (auto& lc : lane_ctr) { res->ctr.cells += lc.cells; res->ctr.n_ext += lc.n_ext; res->ctr.hits += lc.hits; }
   }
   return res;

@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "tg_core.h"
+#include "tg_rounds.h"
 
 #define TG_FULL 0xffffffffu
 #define TG_WARPS_PER_CTA 4
@@ -112,12 +112,46 @@ struct DevWarp {
   }
 };
 
+// One thread = one "warp" of a single lane: lets the thread-per-read round kernels reuse the templated code.
+struct DevThread {
+  static constexpr int LANES = 1;
+  TG_HD int lane() const { return 0; }
+  TG_HD int shfl_up(int v, int) { return v; }
+  TG_HD int shfl(int v, int) { return v; }
+  TG_HD unsigned long long shfl64(unsigned long long v, int) { return v; }
+  TG_HD bool any(bool p) { return p; }
+  TG_HD uint32_t ballot(bool p) { return p ? 1u : 0u; }
+  TG_HD int reduce_max_i32(int v) { return v; }
+  TG_HD uint32_t reduce_min_u32(uint32_t v) { return v; }
+  TG_HD unsigned long long sum64(unsigned long long v) { return v; }
+  TG_HD void sync() {}
+  TG_HD void sync_global() {}
+  TG_HD unsigned long long atomic_add(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    unsigned long long o = *p; *p += v; return o;
+#endif
+  }
+  TG_HD void atomic_or(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+  }
+};
+
+#define TG_MAX_ROUNDS 8
 struct DevCounters {
   unsigned long long seed_used, n_smems, alns_used, ops_used, cells, n_ext, hits, work_seed, work_ext, swg_ops_used,
       work_swg, kmer_groups;
   int flags;
   int pad;
   unsigned long long phase[16];
+  // round pipeline
+  unsigned long long n_complex, work_complex;
+  unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS];
 };
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -223,6 +257,7 @@ struct ExtParams {
   uint32_t arena_cap;
   uint16_t* order;    // [n_warps][2 * TG_MAX_ALNS_PER_READ]
   int bound_stop;
+  const uint32_t* read_list;  // when set: only these reads (the "complex" ones the round pipeline handed over)
   TgAlignOut out;
   DevCounters* ctr;
 };
@@ -263,8 +298,15 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
   DevWarp w;
   TgCounters ctr{};
   for (;;) {
-    uint32_t r = next_work(&p.ctr->work_ext);
-    if (r >= p.n_reads) break;
+    uint32_t r;
+    if (p.read_list) {
+      uint32_t wi = next_work(&p.ctr->work_complex);
+      if ((unsigned long long)wi >= p.ctr->n_complex) break;
+      r = p.read_list[wi];
+    } else {
+      r = next_work(&p.ctr->work_ext);
+      if (r >= p.n_reads) break;
+    }
     uint64_t off = p.offs[r];
     uint32_t L = (uint32_t)(p.offs[r + 1] - off);
     tg_align_read<DevWarp, RMAX>(w, m, p.P, p.bases, off, L, p.seeds + p.read_seed_first[r], p.read_seed_count[r], sc, p.out, r, ctr);
@@ -277,6 +319,126 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
 #ifdef TG_PROFILE_PHASES
     for (int k = 0; k < TG_NPHASE; k++) atomicAdd(&p.ctr->phase[k], ctr.ph[k]);
 #endif
+  }
+}
+
+__host__ __device__ inline size_t swg_smem_per_warp(uint32_t max_xlen, uint32_t max_cols, uint32_t trace_bytes, uint32_t ops_words);
+
+// ---------------------------------------------------------------------------------------------------
+// round pipeline (tg_rounds.h): thread-per-read control kernels + a warp-per-task extension kernel
+// ---------------------------------------------------------------------------------------------------
+struct RoundParams {
+  TgAlignParams P;
+  const uint8_t* bases;
+  const uint64_t* offs;
+  uint32_t n_reads, max_len, rp_words;
+  const tg_seed* seeds;
+  const uint64_t* read_seed_first;
+  const uint32_t* read_seed_count;
+  TgReadState* st;
+  TgHit* hits;
+  TgCand* acc;        // [n_reads][TG_ACC_MAX]
+  uint32_t* arena;    // [n_reads][TG_ARENA_WORDS]
+  uint64_t* rp;       // [n_reads][rp_words] packed reads
+  TgTask* tasks;
+  unsigned long long task_cap;
+  uint32_t* ops_pool;
+  unsigned long long ops_cap;
+  uint32_t* complex_list;
+  uint32_t round;
+  uint32_t max_xlen, max_cols, trace_bytes, ops_words;
+  int bound_stop;
+  TgAlignOut out;
+  DevCounters* ctr;
+};
+
+__device__ __forceinline__ void mark_complex(const RoundParams& p, uint32_t r) {
+  p.st[r].status = TG_RS_COMPLEX;
+  unsigned long long i = atomicAdd(&p.ctr->n_complex, 1ull);
+  p.complex_list[i] = r;
+}
+
+__global__ void __launch_bounds__(128) k_round_init(RoundParams p) {
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
+    const uint64_t off = p.offs[r];
+    const uint32_t L = (uint32_t)(p.offs[r + 1] - off);
+    const uint32_t ns = p.read_seed_count[r];
+    const tg_seed* sd = p.seeds + p.read_seed_first[r];
+    unsigned long long hits = 0;
+    for (uint32_t i = 0; i < ns; i++) hits += sd[i].count;
+    tg_read_state_init(p.st[r], L, p.P.opts, ns, sd);
+    if (hits > TG_FAST_MAX_HITS) { mark_complex(p, r); continue; }
+    if (ns == 0) continue;
+    uint64_t* rp = p.rp + (size_t)r * p.rp_words;
+    for (uint32_t wi = 0; wi < L / 16 + 3; wi++) {
+      uint64_t word = 0;
+      for (uint32_t t = 0; t < 16; t++) {
+        uint32_t q = wi * 16 + t;
+        word |= (uint64_t)(q < L ? tg_ascii_code(__ldg(p.bases + off + q)) : (uint32_t)TG_C_PAD) << ((15 - t) * 4);
+      }
+      rp[wi] = word;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_round_prep(RoundParams p) {
+  DevThread w;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
+    TgReadState st = p.st[r];
+    if (st.status != TG_RS_ACTIVE) continue;
+    const bool ok = tg_round_prep<DevThread>(w, p.P, p.rp + (size_t)r * p.rp_words, st, p.seeds + p.read_seed_first[r], r,
+                                             p.hits[r], p.tasks, &p.ctr->round_tasks[p.round], p.task_cap);
+    if (!ok) mark_complex(p, r);
+  }
+}
+
+template <int RMAX>
+__global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_round_dp(RoundParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* base = smem + (threadIdx.x >> 5) * swg_smem_per_warp(p.max_xlen, p.max_cols, p.trace_bytes, p.ops_words);
+  uint8_t* sx = base; base += align16(p.max_xlen + 16);
+  uint8_t* sy = base; base += align16(p.max_cols + 16);
+  uint8_t* trace = base; base += align16(p.trace_bytes);
+  uint32_t* obuf = (uint32_t*)base;
+  DevWarp w;
+  unsigned long long n_tasks = p.ctr->round_tasks[p.round];
+  if (n_tasks > p.task_cap) n_tasks = p.task_cap;
+  for (;;) {
+    uint32_t t = next_work(&p.ctr->round_work[p.round]);
+    if ((unsigned long long)t >= n_tasks) break;
+    tg_task_run<DevWarp, RMAX>(w, p.P.ix, p.bases, p.offs, p.tasks[t], sx, sy, trace, obuf, p.ops_pool, &p.ctr->round_ops[p.round],
+                               p.ops_cap, &p.ctr->flags, p.bound_stop != 0);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_round_post(RoundParams p) {
+  DevThread w;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
+    TgReadState st = p.st[r];
+    if (st.status != TG_RS_ACTIVE) continue;
+    const bool ok = tg_round_post<DevThread>(w, p.P, st, p.seeds + p.read_seed_first[r], p.read_seed_count[r], p.hits[r], p.tasks,
+                                             p.ops_pool, p.acc + (size_t)r * TG_ACC_MAX, p.arena + (size_t)r * TG_ARENA_WORDS);
+    if (!ok) { mark_complex(p, r); continue; }
+    p.st[r] = st;
+  }
+}
+
+// reads still active after the last round go to the single-warp path too
+__global__ void __launch_bounds__(128) k_round_final(RoundParams p) {
+  DevThread w;
+  unsigned long long cells = 0, n_ext = 0, hits = 0;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
+    const TgReadState st = p.st[r];
+    if (st.status == TG_RS_COMPLEX) continue;
+    if (st.status == TG_RS_ACTIVE) { mark_complex(p, r); continue; }
+    tg_round_final<DevThread>(w, p.P, st, p.acc + (size_t)r * TG_ACC_MAX, p.arena + (size_t)r * TG_ARENA_WORDS, p.out, r);
+    cells += st.cells; n_ext += st.n_ext; hits += st.hits;
+  }
+  cells = warp_sum(cells); n_ext = warp_sum(n_ext); hits = warp_sum(hits);
+  if ((threadIdx.x & 31) == 0) {
+    if (cells) atomicAdd(&p.ctr->cells, cells);
+    if (n_ext) atomicAdd(&p.ctr->n_ext, n_ext);
+    if (hits) atomicAdd(&p.ctr->hits, hits);
   }
 }
 
@@ -417,6 +579,10 @@ struct tg_ctx {
   DevBuf d_cands, d_arena, d_order, d_aln_first, d_aln_count, d_alns, d_ops;
   uint64_t alns_cap = 0, ops_cap = 0;
   uint32_t scratch_warps = 0;
+  // round pipeline scratch
+  DevBuf r_state, r_hits, r_acc, r_arena, r_rp, r_tasks, r_ops, r_complex;
+  uint64_t round_task_cap = 0, round_ops_cap = 0;
+  int use_rounds = 1;
   // host results
   PinBuf h_first, h_count, h_alns, h_ops, h_seeds, h_seed_first, h_seed_count;
   // swg batch
@@ -517,7 +683,7 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->ix->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_cands, &c->d_arena, &c->d_order,
+  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_acc, &c->r_arena, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex,
                     &c->d_aln_first, &c->d_aln_count, &c->d_alns, &c->d_ops, &c->s_x, &c->s_xo, &c->s_y, &c->s_yo, &c->s_bw,
                     &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops})
     b->release();
@@ -584,6 +750,9 @@ void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms) 
   if (seed_ms) *seed_ms = ctx ? ctx->last_seed_ms : 0.f;
   if (extend_ms) *extend_ms = ctx ? ctx->last_extend_ms : 0.f;
 }
+void tg_ctx_set_round_pipeline(tg_ctx* ctx, int on) {
+  if (ctx) ctx->use_rounds = on ? 1 : 0;
+}
 void tg_ctx_set_exact_cell_count(tg_ctx* ctx, int on) {
   if (ctx) ctx->exact_cells = on ? 1 : 0;
 }
@@ -617,7 +786,8 @@ tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs,
   return TG_OK;
 }
 
-tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL) {
+tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL,
+                        const uint32_t* read_list = nullptr) {
   uint32_t max_bw = band_for(c->opts, maxL);
   uint32_t max_xlen = maxL > 0 ? maxL - 1 : 0;
   uint32_t max_cols = max_xlen + max_bw + 1;
@@ -655,6 +825,7 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.read_seed_count = (const uint32_t*)c->d_seed_count.p;
   p.cands = (TgCand*)c->d_cands.p; p.arena = (uint32_t*)c->d_arena.p; p.arena_cap = arena_cap; p.order = (uint16_t*)c->d_order.p;
   p.bound_stop = c->exact_cells ? 0 : 1;
+  p.read_list = read_list;
   p.out.read_aln_first = (uint64_t*)c->d_aln_first.p; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p;
   p.out.alns = (tg_aln*)c->d_alns.p; p.out.ops = (uint32_t*)c->d_ops.p;
   p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;
@@ -663,6 +834,67 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
   CU_CHECK(cudaGetLastError());
   return TG_OK;
+}
+
+tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL) {
+  tg_status st;
+  const uint32_t rp_words = maxL / 16 + 4;
+  if (c->round_task_cap < (uint64_t)n * 3 + 4096) c->round_task_cap = (uint64_t)n * 3 + 4096;
+  if (c->round_ops_cap < (uint64_t)n * 12 + 65536) c->round_ops_cap = (uint64_t)n * 12 + 65536;
+  if ((st = c->r_state.ensure((size_t)n * sizeof(TgReadState))) != TG_OK) return st;
+  if ((st = c->r_hits.ensure((size_t)n * sizeof(TgHit))) != TG_OK) return st;
+  if ((st = c->r_acc.ensure((size_t)n * TG_ACC_MAX * sizeof(TgCand))) != TG_OK) return st;
+  if ((st = c->r_arena.ensure((size_t)n * TG_ARENA_WORDS * 4)) != TG_OK) return st;
+  if ((st = c->r_rp.ensure((size_t)n * rp_words * 8)) != TG_OK) return st;
+  if ((st = c->r_tasks.ensure(c->round_task_cap * sizeof(TgTask))) != TG_OK) return st;
+  if ((st = c->r_ops.ensure(c->round_ops_cap * 4)) != TG_OK) return st;
+  if ((st = c->r_complex.ensure((size_t)n * 4 + 16)) != TG_OK) return st;
+  const uint32_t max_bw = band_for(c->opts, maxL);
+  const uint32_t max_xlen = maxL > 0 ? maxL - 1 : 0;
+  const uint32_t max_cols = max_xlen + max_bw + 1;
+  const uint32_t trace_bytes = (max_cols + 1) * (uint32_t)tg_trace_bytes_per_col((int)max_xlen, 32);
+  const uint32_t ops_words = max_xlen + max_cols + 8;
+  RoundParams p;
+  p.P.ix = c->ix->dev; p.P.opts = c->opts;
+  p.bases = d_bases; p.offs = d_offs; p.n_reads = n; p.max_len = maxL; p.rp_words = rp_words;
+  p.seeds = (const tg_seed*)c->d_seeds.p; p.read_seed_first = (const uint64_t*)c->d_seed_first.p;
+  p.read_seed_count = (const uint32_t*)c->d_seed_count.p;
+  p.st = (TgReadState*)c->r_state.p; p.hits = (TgHit*)c->r_hits.p; p.acc = (TgCand*)c->r_acc.p;
+  p.arena = (uint32_t*)c->r_arena.p; p.rp = (uint64_t*)c->r_rp.p; p.tasks = (TgTask*)c->r_tasks.p;
+  p.task_cap = c->round_task_cap; p.ops_pool = (uint32_t*)c->r_ops.p; p.ops_cap = c->round_ops_cap;
+  p.complex_list = (uint32_t*)c->r_complex.p; p.round = 0;
+  p.max_xlen = max_xlen; p.max_cols = max_cols; p.trace_bytes = trace_bytes; p.ops_words = ops_words;
+  p.bound_stop = c->exact_cells ? 0 : 1;
+  p.out.read_aln_first = (uint64_t*)c->d_aln_first.p; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p;
+  p.out.alns = (tg_aln*)c->d_alns.p; p.out.ops = (uint32_t*)c->d_ops.p;
+  p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;
+  p.out.alns_cap = c->alns_cap; p.out.ops_cap = c->ops_cap; p.out.flags = &c->d_ctr->flags;
+  p.ctr = c->d_ctr;
+  // extension kernel geometry
+  int wpc = TG_WARPS_PER_CTA;
+  const size_t per_warp = swg_smem_per_warp(max_xlen, max_cols, trace_bytes, ops_words);
+  while (wpc > 1 && per_warp * wpc > 100 * 1024) wpc >>= 1;
+  const size_t smem = per_warp * wpc;
+  if (smem > 227 * 1024) return tg_fail(TG_ERR_CAPACITY, "reads too long for the extension kernel's shared memory");
+  const int rcls = tg_swg_rows_class((int)max_xlen, 32);
+  void (*kdp)(RoundParams) = rcls <= 3 ? k_round_dp<3> : rcls <= 6 ? k_round_dp<6> : k_round_dp<16>;
+  CU_CHECK(cudaFuncSetAttribute(kdp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kdp, wpc * 32, smem));
+  if (occ < 1) return tg_fail(TG_ERR_CAPACITY, "extension kernel does not fit in shared memory");
+  const int dp_blocks = c->n_sms * occ;
+  const int tblocks = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16);
+  k_round_init<<<tblocks, 128, 0, c->stream>>>(p);
+  for (uint32_t r = 0; r < TG_MAX_ROUNDS; r++) {
+    p.round = r;
+    k_round_prep<<<tblocks, 128, 0, c->stream>>>(p);
+    kdp<<<dp_blocks, wpc * 32, smem, c->stream>>>(p);
+    k_round_post<<<tblocks, 128, 0, c->stream>>>(p);
+  }
+  k_round_final<<<tblocks, 128, 0, c->stream>>>(p);
+  CU_CHECK(cudaGetLastError());
+  // whatever the rounds could not finish (many hits / candidates / accepted alignments) runs on the single-warp path
+  return launch_extend(c, d_bases, d_offs, n, maxL, (const uint32_t*)c->r_complex.p);
 }
 
 tg_status ensure_pools(tg_ctx* c, uint32_t n) {
@@ -689,7 +921,7 @@ tg_status run_pipeline(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs
     CU_CHECK(cudaEventRecord(c->ev0, c->stream));
     if ((st = launch_seed(c, d_bases, d_offs, n, maxL)) != TG_OK) return st;
     CU_CHECK(cudaEventRecord(c->ev1, c->stream));
-    if (extend && (st = launch_extend(c, d_bases, d_offs, n, maxL)) != TG_OK) return st;
+    if (extend && (st = (c->use_rounds ? launch_rounds(c, d_bases, d_offs, n, maxL) : launch_extend(c, d_bases, d_offs, n, maxL))) != TG_OK) return st;
     CU_CHECK(cudaEventRecord(c->ev2, c->stream));
     CU_CHECK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream));
@@ -699,7 +931,10 @@ tg_status run_pipeline(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs
     if (f & (TG_FLAG_SEED_POOL | TG_FLAG_ALN_POOL | TG_FLAG_OPS_POOL)) {  // grow the pool that overflowed and redo the batch
       if (f & TG_FLAG_SEED_POOL) c->seed_cap = std::max<uint64_t>(c->seed_cap * 2, c->h_ctr->seed_used + 4096);
       if (f & TG_FLAG_ALN_POOL) c->alns_cap = std::max<uint64_t>(c->alns_cap * 2, c->h_ctr->alns_used + 4096);
-      if (f & TG_FLAG_OPS_POOL) c->ops_cap = std::max<uint64_t>(c->ops_cap * 2, c->h_ctr->ops_used + 4096);
+      if (f & TG_FLAG_OPS_POOL) {
+        c->ops_cap = std::max<uint64_t>(c->ops_cap * 2, c->h_ctr->ops_used + 4096);
+        c->round_ops_cap *= 2;
+      }
       continue;
     }
     return check_flags(f);
