@@ -19,7 +19,7 @@
 #define TG_PMAX 6             // distinct extension problems per hit (problem 0 = genome)
 #define TG_ACC_MAX 4          // accepted alignments kept per read on the round path
 #define TG_ARENA_WORDS 320u   // RLE words of those alignments
-#define TG_FAST_MAX_HITS 8u   // reads with more hits take the single-warp path
+#define TG_FAST_MAX_HITS 48u  // reads with more hits take the single-warp path
 
 enum { TG_RS_DONE = 0, TG_RS_ACTIVE = 1, TG_RS_COMPLEX = 2 };
 

@@ -142,7 +142,7 @@ struct DevThread {
   }
 };
 
-#define TG_MAX_ROUNDS 8
+#define TG_MAX_ROUNDS 48
 struct DevCounters {
   unsigned long long seed_used, n_smems, alns_used, ops_used, cells, n_ext, hits, work_seed, work_ext, swg_ops_used,
       work_swg, kmer_groups;
@@ -352,8 +352,9 @@ struct RoundParams {
   DevCounters* ctr;
 };
 
-__device__ __forceinline__ void mark_complex(const RoundParams& p, uint32_t r) {
+__device__ __forceinline__ void mark_complex(const RoundParams& p, uint32_t r, int reason) {
   p.st[r].status = TG_RS_COMPLEX;
+  atomicAdd(&p.ctr->phase[12 + reason], 1ull);  // debug statistics: why reads leave the round path
   unsigned long long i = atomicAdd(&p.ctr->n_complex, 1ull);
   p.complex_list[i] = r;
 }
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(128) k_round_init(RoundParams p) {
     unsigned long long hits = 0;
     for (uint32_t i = 0; i < ns; i++) hits += sd[i].count;
     tg_read_state_init(p.st[r], L, p.P.opts, ns, sd);
-    if (hits > TG_FAST_MAX_HITS) { mark_complex(p, r); continue; }
+    if (hits > TG_FAST_MAX_HITS) { mark_complex(p, r, 0); continue; }
     if (ns == 0) continue;
     uint64_t* rp = p.rp + (size_t)r * p.rp_words;
     for (uint32_t wi = 0; wi < L / 16 + 3; wi++) {
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(128) k_round_prep(RoundParams p) {
     if (st.status != TG_RS_ACTIVE) continue;
     const bool ok = tg_round_prep<DevThread>(w, p.P, p.rp + (size_t)r * p.rp_words, st, p.seeds + p.read_seed_first[r], r,
                                              p.hits[r], p.tasks, &p.ctr->round_tasks[p.round], p.task_cap);
-    if (!ok) mark_complex(p, r);
+    if (!ok) mark_complex(p, r, 1);
   }
 }
 
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(128) k_round_post(RoundParams p) {
     if (st.status != TG_RS_ACTIVE) continue;
     const bool ok = tg_round_post<DevThread>(w, p.P, st, p.seeds + p.read_seed_first[r], p.read_seed_count[r], p.hits[r], p.tasks,
                                              p.ops_pool, p.acc + (size_t)r * TG_ACC_MAX, p.arena + (size_t)r * TG_ARENA_WORDS);
-    if (!ok) { mark_complex(p, r); continue; }
+    if (!ok) { mark_complex(p, r, 2); continue; }
     p.st[r] = st;
   }
 }
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(128) k_round_final(RoundParams p) {
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
     const TgReadState st = p.st[r];
     if (st.status == TG_RS_COMPLEX) continue;
-    if (st.status == TG_RS_ACTIVE) { mark_complex(p, r); continue; }
+    if (st.status == TG_RS_ACTIVE) { mark_complex(p, r, 3); continue; }
     tg_round_final<DevThread>(w, p.P, st, p.acc + (size_t)r * TG_ACC_MAX, p.arena + (size_t)r * TG_ARENA_WORDS, p.out, r);
     cells += st.cells; n_ext += st.n_ext; hits += st.hits;
   }

@@ -17,3 +17,8 @@ bases, offs = bench.make_reads(contigs, txs, n, bench.SEEDS["reads"])
 for _ in range(steps):
     r = al.align_reads(bases, offs)
 print("reads", n, "alns", len(r.alns), "kernel ms (seed, extend)", al.last_kernel_ms(), r.counters)
+import ctypes as C
+from thermite_b200 import lib
+out = (C.c_uint64 * 16)()
+lib().tg_ctx_debug_phases(al._h, out)
+print("reads leaving the round path: hits>max", out[12], "prep overflow", out[13], "post overflow", out[14], "still active", out[15])
