@@ -143,11 +143,15 @@ void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms);
  * every output record are unchanged, but fewer cells are visited than the reference's loops visit.  With `on` = 1
  * every column the reference runs is run, so tg_result.swg_cells / *cells equal the reference's cell count. */
 void tg_ctx_set_exact_cell_count(tg_ctx* ctx, int on);
-/* Execution strategy of the hit loop.  on = 1 (default): round pipeline -- thread-per-read control kernels and a
- * warp-per-task extension kernel, one hit per read per round; reads it cannot finish (many hits, many transcripts per
- * seed, many accepted alignments) run on the single-warp kernel.  on = 0: every read on the single-warp kernel.
- * Both produce identical records. */
+/* Execution strategy of the hit loop.  on = 1 (default): speculative round pipeline -- every round evaluates a batch of
+ * consecutive hits of each unfinished read under the read's current (band_width, x_drop) with thread-per-hit control
+ * kernels and a warp-per-task extension kernel, then replays the reference's serial accept / narrow logic over the
+ * batch and discards whatever was evaluated under a state that an accepted hit changed (csrc/tg_rounds.h).  Reads it
+ * cannot hold (more than 12 transcripts on one seed, ~100k hits) run on the single-warp kernel.  on = 0: every read on
+ * the single-warp kernel.  Both produce identical records. */
 void tg_ctx_set_round_pipeline(tg_ctx* ctx, int on);
+/* Number of kernels the last tg_align_batch* / tg_seed_batch call launched on the context's stream. */
+uint64_t tg_ctx_last_kernel_launches(const tg_ctx* ctx);
 /* Size of the context's k-mer table in bytes. */
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx);
 

@@ -95,7 +95,7 @@ class HostCtx:
         r = lib().ht_align_batch_mode(self.h, _p(bases), _p(offs), n, lanes, int(bound_stop), int(rounds))
         assert r
         r = C.c_void_p(r)
-        info = (C.c_uint64 * 6)()
+        info = (C.c_uint64 * 8)()
         lib().ht_result_info(r, info)
         first = np.zeros(n, np.uint64)
         count = np.zeros(n, np.uint32)
@@ -104,7 +104,7 @@ class HostCtx:
         lib().ht_result_copy(r, _p(first), _p(count), _p(alns), _p(ops))
         lib().ht_result_free(r)
         return dict(first=first, count=count, alns=alns, ops=ops, cells=info[2], n_ext=info[3], hits=info[4],
-                    flags=info[5])
+                    flags=info[5], items=info[6], rounds=info[7])
 
 
 def expand_seeds(pool, first, count, sa, r):

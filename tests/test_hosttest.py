@@ -65,6 +65,15 @@ def test_align_records_equal_oracle_random_worlds(seed):
     # bound-stopped extensions (the product default): identical records, never more cells
     resb = ctx.align_batch(bases, offs, lanes=1, bound_stop=True)
     assert not ht.compare_alignments(resb, ores, n) and resb["cells"] <= res["cells"]
+    # the speculative round pipeline (what the GPU runs by default): identical records AND identical work counters
+    # rounds=2 additionally runs every eligible extension through the thread-per-extension DP (tg_dpt.h)
+    for bs in (False, True):
+        for mode in (1, 2):
+            resr = ctx.align_batch(bases, offs, lanes=1, bound_stop=bs, rounds=mode)
+            d = ht.compare_alignments(resr, ores, n)
+            assert not d, (mode, d[:3])
+            assert resr["flags"] == 0 and resr["hits"] == res["hits"] and resr["n_ext"] == res["n_ext"]
+            assert resr["cells"] == (resb["cells"] if bs else res["cells"]), mode
     # the 32-lane wavefront (what the GPU executes) on a slice
     m = 12
     for bs in (False, True):
@@ -74,8 +83,11 @@ def test_align_records_equal_oracle_random_worlds(seed):
 
 
 def test_swg_wavefront_equals_oracle():
+    # lanes = 0: the thread-per-extension DP of tg_dpt.h (every band class) where eligible, else the 1-lane wavefront
     for seed, lanes, n, kw in ((1, 1, 3000, {}), (2, 32, 150, {}), (3, 32, 60, dict(max_x=200, bw_choices=(3, 30, 100))),
-                               (4, 1, 1500, dict(alphabet=b"AC"))):
+                               (4, 1, 1500, dict(alphabet=b"AC")), (5, 0, 6000, {}), (6, 0, 3000, dict(alphabet=b"AC")),
+                               (7, 0, 3000, dict(max_x=128, bw_choices=(0, 1, 3, 5, 11, 19, 27, 35, 39, 50, 64))),
+                               (8, 0, 2000, dict(alphabet=b"ACGTN", bw_choices=(2, 7, 15, 16, 23, 40)))):
         xs, xo, ys, yo, bw, xd = swg_pairs(seed, n, **kw)
         b = orc.swg_extend_batch(xs, xo, ys, yo, bw, xd)
         for bs in (False, True):
@@ -99,3 +111,35 @@ def test_chrM_reads_records():
         res = ctx.align_batch(bases, offs)
         ores = oix.align_batch(bases, offs, **flags)
         assert not ht.compare_alignments(res, ores, n)
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_round_pipeline_repeat_rich_reads(seed):
+    """Many hits per read (repeat families with near-identical copies, low k): batches of hits are evaluated
+    speculatively and re-planned when an accepted hit narrows the band; records and counters must not change."""
+    rng = np.random.default_rng(seed)
+    g = synth.make_genome(seed, 6000, families=((25, 150, 0.0, 0.06), (8, 300, 0.0, 0.03)), polya_runs=6, polya_len=(20, 40))
+    contigs = [("chrR", g)]
+    gtf, txs = synth.make_annotation(seed + 1, "chrR", g, n_genes=5, tx_per_gene=(1, 4), exons_per_tx=(1, 5),
+                                     exon_len=(20, 150), intron_len=(20, 300), lead=0, prefix="r")
+    fa = synth.fasta_bytes(contigs)
+    n = 150
+    bases, offs = synth.make_reads(seed + 2, contigs, txs, n, L=int(rng.choice([60, 91])), sub=0.03, ins=0.004, dele=0.004,
+                                   polya_frac=0.2, polya_len=(15, 35))
+    hix, oix = ht.HostIndex(fa, gtf), orc.Index.create(fa, gtf)
+    for flags in (dict(k=12, pct=0.0, min_score=20, score_range=1, intron_mode=True),
+                  dict(k=10, pct=0.5, min_score=0, score_range=3, intron_mode=True),
+                  dict(k=14, pct=0.66, min_score=30, score_range=0, intron_mode=False)):
+        ctx = ht.HostCtx(hix, **flags)
+        oix.counters_reset()
+        ores = oix.align_batch(bases, offs, **flags)
+        oc = oix.counters()
+        assert oc["hits"] > 3 * n  # the point of this world
+        res2 = ctx.align_batch(bases, offs, lanes=1, rounds=2)
+        assert not ht.compare_alignments(res2, ores, n) and res2["cells"] == oc["swg_cells"]
+        res = ctx.align_batch(bases, offs, lanes=1, rounds=True)
+        d = ht.compare_alignments(res, ores, n)
+        assert not d, d[:3]
+        assert res["flags"] == 0 and res["cells"] == oc["swg_cells"] and res["hits"] == oc["hits"]
+        # speculation really happened: several rounds, and some evaluated hits were discarded and redone
+        assert res["rounds"] >= 3 and res["items"] > res["hits"], (res["rounds"], res["items"], res["hits"])

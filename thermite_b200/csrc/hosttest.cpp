@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "tg_rounds.h"
+#include "tg_dpt.h"
 
 namespace {
 
@@ -204,6 +205,54 @@ void run_lanes(int lanes, F&& f) {
   for (auto& t : th) t.join();
 }
 
+// ---- tg_dpt.h on the host: one "thread", strides of 1 --------------------------------------------------------------
+struct DptScratch {
+  std::vector<uint32_t> msk, tr;
+  DptScratch() : msk(32, 0), tr((size_t)(TG_DPT_MAX_X + 2 * TG_MAX_READ_LEN + 2) * 5, 0) {}
+  TgDptMem mem() { return TgDptMem{msk.data(), 1, tr.data(), 1}; }
+};
+template <int WB>
+void dpt_one(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int bw, int x_drop, bool bound_stop, TgDptResult& res,
+             std::vector<uint32_t>& ops) {
+  tg_dpt_fill<WB>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res);
+  uint32_t n = tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [](uint32_t, uint32_t, uint32_t) {});
+  ops.assign(n, 0);
+  tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [&](uint32_t i, uint32_t kind, uint32_t run) { ops[i] = kind | (run << 3); });
+}
+void dpt_dispatch(int cls, const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int bw, int x_drop, bool bound_stop,
+                  TgDptResult& res, std::vector<uint32_t>& ops) {
+  switch (cls) {
+    case 1: dpt_one<8>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 2: dpt_one<16>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 3: dpt_one<24>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 4: dpt_one<32>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 5: dpt_one<40>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 6: dpt_one<48>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 7: dpt_one<56>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 8: dpt_one<64>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 9: dpt_one<72>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    default: dpt_one<80>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+  }
+}
+// one round task the way k_round_dpt runs it; false when the task is not eligible (class 0)
+bool dpt_task_host(const TgIndexDev& ix, const uint64_t* rp, TgTask& t, DptScratch& sc, bool bound_stop, uint32_t* ops_pool,
+                   unsigned long long* ops_ctr) {
+  const int xlen = (int)t.xlen, bw = (int)t.bw, ylen = (int)t.ylen;
+  const int cls = tg_dpt_class(xlen, bw, t.x_drop);
+  if (cls == 0) return false;
+  const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
+  TgDptMem m = sc.mem();
+  TgDptY ys{tg_seq_of(ix, t.seqsel), t.y0, ncols, (int)t.side, 0, 0};
+  tg_dpt_profile(m, rp, t.xoff, xlen, t.side);
+  TgDptResult res{0, 0, 0, 0};
+  std::vector<uint32_t> ops;
+  dpt_dispatch(cls, m, ys, xlen, ncols, bw, t.x_drop, bound_stop, res, ops);
+  t.score = res.score; t.xend = (uint32_t)res.xend; t.yend = (uint32_t)res.yend; t.cells = res.cells;
+  t.ops_off = (uint32_t)*ops_ctr; t.ops_n = (uint32_t)ops.size();
+  for (uint32_t w : ops) ops_pool[(*ops_ctr)++] = w;
+  return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -268,6 +317,7 @@ struct HtResult {
   unsigned long long n_alns = 0, n_ops = 0;
   TgCounters ctr{0, 0, 0};
   int flags = 0;
+  unsigned long long items = 0, rounds = 0;  // round pipeline: evaluated (read, hit) items incl. discarded ones
 };
 
 void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes, int bound_stop, int rounds);
@@ -275,8 +325,9 @@ void* ht_align_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint3
   return ht_align_batch_mode(cp, bases, offs, n, lanes, bound_stop, 0);
 }
 
-// rounds = 1: reads go through tg_round_prep / tg_task_run / tg_round_post / tg_round_final (what the GPU's round
-// pipeline executes), falling back to the single-warp path exactly as the device does.
+// rounds = 1: the batch goes through the speculative round pipeline exactly as the device drives it (tg_rounds.h:
+// plan / prep / task_run / post / scan per round over ALL reads, then final), and reads that leave it are redone on
+// the single-warp path.
 void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes, int bound_stop, int rounds) {
   HostCtx* c = (HostCtx*)cp;
   uint32_t maxL = 1;
@@ -295,74 +346,126 @@ void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, 
   wb.arena.resize(1 << 16);
   std::vector<uint16_t> order(2 * TG_MAX_ALNS_PER_READ);
   TgWarpScratch sc{wb.cands.data(), wb.arena.data(), (uint32_t)wb.arena.size(), order.data()};
-  std::vector<tg_seed> pool(maxL + 8);
-  std::vector<uint64_t> sfirst(1);
-  std::vector<uint32_t> scount(1);
   TgAlignParams P{c->dev, c->opts};
   TgAlignOut out{res->first.data(), res->count.data(), res->alns.data(), res->ops.data(), &res->n_alns, &res->n_ops,
                  res->alns.size(), res->ops.size(), &res->flags};
-  for (uint32_t r = 0; r < n; r++) {
-    uint32_t L = (uint32_t)(offs[r + 1] - offs[r]);
+  std::vector<uint8_t> done(n, 0);
+  HostWarp1 w1;
+  if (rounds) {
+    // seeds of every read
+    std::vector<tg_seed> pool((size_t)n * 8 + 1024);
+    std::vector<uint64_t> sfirst(n);
+    std::vector<uint32_t> scount(n);
     unsigned long long used = 0, n_smems = 0;
-    TgSeedOut sout{pool.data(), &used, pool.size(), sfirst.data(), scount.data(), &res->flags, &n_smems};
-    std::vector<TgCounters> lane_ctr(32, TgCounters{0, 0, 0});
-    bool fast_done = false;
-    if (rounds) {
-      HostWarp1 w1;
-      tg_seed_read(w1, sm, bases, offs[r], L, c->opts.min_seed_len, c->slots.data(), c->slot_mask, c->dev.text4, c->dev.sa, sout, 0);
-      const tg_seed* sd = pool.data() + sfirst[0];
-      uint64_t hits = 0;
-      for (uint32_t i = 0; i < scount[0]; i++) hits += sd[i].count;
-      if (hits <= TG_FAST_MAX_HITS) {
-        TgReadState st;
-        tg_read_state_init(st, L, c->opts, scount[0], sd);
-        std::vector<uint64_t> rp(L / 16 + 4, 0);
-        for (uint32_t wi = 0; wi < L / 16 + 3; wi++) {
-          uint64_t word = 0;
-          for (uint32_t t = 0; t < 16; t++) {
-            uint32_t p = wi * 16 + t;
-            word |= (uint64_t)(p < L ? tg_ascii_code(bases[offs[r] + p]) : (uint32_t)TG_C_PAD) << ((15 - t) * 4);
-          }
-          rp[wi] = word;
+    for (;;) {
+      used = 0; n_smems = 0; res->flags = 0;
+      TgSeedOut sout{pool.data(), &used, pool.size(), sfirst.data(), scount.data(), &res->flags, &n_smems};
+      for (uint32_t r = 0; r < n; r++)
+        tg_seed_read(w1, sm, bases, offs[r], (uint32_t)(offs[r + 1] - offs[r]), c->opts.min_seed_len, c->slots.data(), c->slot_mask,
+                     c->dev.text4, c->dev.sa, sout, r);
+      if (!(res->flags & TG_FLAG_SEED_POOL)) break;
+      pool.resize(pool.size() * 2);
+    }
+    const uint32_t rp_words = maxL / 16 + 4;
+    std::vector<uint64_t> rp((size_t)n * rp_words, 0);
+    std::vector<TgReadState> st(n);
+    uint64_t total_hits = 0;
+    for (uint32_t r = 0; r < n; r++) {
+      const uint32_t L = (uint32_t)(offs[r + 1] - offs[r]);
+      if (!tg_read_state_init(st[r], L, c->opts, scount[r], pool.data() + sfirst[r])) st[r].status = TG_RS_COMPLEX;
+      total_hits += st[r].n_hits;
+      for (uint32_t wi = 0; wi < L / 16 + 3; wi++) {
+        uint64_t word = 0;
+        for (uint32_t t = 0; t < 16; t++) {
+          uint32_t p = wi * 16 + t;
+          word |= (uint64_t)(p < L ? tg_ascii_code(bases[offs[r] + p]) : (uint32_t)TG_C_PAD) << ((15 - t) * 4);
         }
-        TgHit hit;
-        std::vector<TgTask> tasks(4 * TG_PMAX);
-        std::vector<uint32_t> opool(1 << 16);
-        TgCand acc[TG_ACC_MAX];
-        uint32_t arena[TG_ARENA_WORDS];
-        bool ok = true;
-        while (ok && st.status == TG_RS_ACTIVE) {
-          unsigned long long tctr = 0, octr = 0;
-          ok = tg_round_prep(w1, P, rp.data(), st, sd, r, hit, tasks.data(), &tctr, tasks.size());
-          if (!ok) break;
-          for (unsigned long long t = 0; t < tctr; t++) {
-            run_lanes(lanes, [&](auto& w) {
-              tg_task_run(w, c->dev, bases, offs, tasks[t], wm.xs, wm.ys, wm.trace, wm.opsT, opool.data(), &octr, opool.size(),
-                          &res->flags, wm.bound_stop);
-            });
-          }
-          ok = tg_round_post(w1, P, st, sd, scount[0], hit, tasks.data(), opool.data(), acc, arena);
-        }
-        if (ok) {
-          tg_round_final(w1, P, st, acc, arena, out, r);
-          lane_ctr[0].cells += st.cells; lane_ctr[0].n_ext += st.n_ext; lane_ctr[0].hits += st.hits;
-          fast_done = true;
-        }
+        rp[(size_t)r * rp_words + wi] = word;
       }
     }
-    if (!fast_done)
-      run_lanes(lanes, [&](auto& w) {
-        tg_seed_read(w, sm, bases, offs[r], L, c->opts.min_seed_len, c->slots.data(), c->slot_mask, c->dev.text4,
-                     c->dev.sa, sout, 0);
-        tg_align_read(w, wm, P, bases, offs[r], L, pool.data() + sfirst[0], scount[0], sc, out, r, lane_ctr[w.lane()]);
-      });
+    const size_t item_cap = (size_t)total_hits * 3 + 1024;
+    std::vector<TgHit> hits(item_cap);
+    std::vector<TgItemRes> ires(item_cap);
+    std::vector<TgCand> cands(item_cap);
+    std::vector<uint32_t> hops(item_cap * 64 + 65536);
+    unsigned long long hops_used = 0, items_used = 0;
+    TgHopsPool hp{hops.data(), &hops_used, hops.size()};
+    std::vector<TgTask> tasks;
+    std::vector<uint32_t> dp_ops;
+    for (uint32_t round = 0; round < TG_MAX_ROUNDS; round++) {
+      const unsigned long long lo = items_used;
+      for (uint32_t r = 0; r < n; r++) {  // plan
+        if (st[r].status != TG_RS_ACTIVE) continue;
+        uint32_t b = tg_plan_batch(st[r], round);
+        if (items_used + b > item_cap) b = 0;
+        st[r].batch_first = (uint32_t)items_used; st[r].batch_n = b;
+        for (uint32_t i = 0; i < b; i++) {
+          TgItemRes& ir = ires[items_used + i];
+          ir.read = r; ir.hit = st[r].next_hit + i; ir.flags = 0; ir.prev_acc = TG_NONE;
+        }
+        items_used += b;
+      }
+      const unsigned long long hi = items_used;
+      if (hi == lo) break;
+      res->rounds = round + 1;
+      tasks.assign((size_t)(hi - lo) * 2 * TG_PMAX + 16, TgTask{});
+      unsigned long long tctr = 0, octr = 0;
+      for (unsigned long long it = lo; it < hi; it++) {  // prep
+        const uint32_t r = ires[it].read;
+        if (!tg_item_prep(w1, P, rp.data() + (size_t)r * rp_words, st[r], pool.data() + sfirst[r], scount[r], r, ires[it].hit, hits[it],
+                          tasks.data(), &tctr, tasks.size(), &res->flags))
+          ires[it].flags = TG_IF_FAIL;
+      }
+      dp_ops.assign((size_t)tctr * (2 * maxL + 64) + 64, 0);
+      DptScratch dsc;
+      for (unsigned long long t = 0; t < tctr; t++) {  // extend
+        if (rounds == 2 && dpt_task_host(c->dev, rp.data() + (size_t)tasks[t].read * rp_words, tasks[t], dsc, wm.bound_stop, dp_ops.data(), &octr))
+          continue;
+        run_lanes(lanes, [&](auto& w) {
+          tg_task_run(w, c->dev, bases, offs, tasks[t], wm.xs, wm.ys, wm.trace, wm.opsT, dp_ops.data(), &octr, dp_ops.size(),
+                      &res->flags, wm.bound_stop);
+        });
+      }
+      for (unsigned long long it = lo; it < hi; it++) {  // post
+        if (ires[it].flags & TG_IF_FAIL) continue;
+        tg_item_post(w1, P, st[ires[it].read], hits[it], tasks.data(), dp_ops.data(), ires[it], cands[it], hp, &res->flags);
+      }
+      for (uint32_t r = 0; r < n; r++) {  // scan
+        if (st[r].status != TG_RS_ACTIVE || st[r].batch_n == 0) continue;
+        if (!tg_scan_read(c->opts, st[r], ires.data())) st[r].status = TG_RS_COMPLEX;
+      }
+    }
+    res->items = items_used;
+    for (uint32_t r = 0; r < n; r++) {  // final
+      if (st[r].status != TG_RS_DONE) continue;
+      std::vector<uint32_t> f(3 * (size_t)st[r].n_acc + 3);
+      tg_round_final<HostWarp1, uint32_t>(w1, P, st[r], cands.data(), ires.data(), hops.data(), f.data(), f.data() + st[r].n_acc,
+                                          f.data() + 2 * (size_t)st[r].n_acc, out, r);
+      res->ctr.cells += st[r].cells; res->ctr.n_ext += st[r].n_ext; res->ctr.hits += st[r].hits;
+      done[r] = 1;
+    }
+  }
+  std::vector<tg_seed> pool1(maxL + 8);
+  std::vector<uint64_t> sfirst1(1);
+  std::vector<uint32_t> scount1(1);
+  for (uint32_t r = 0; r < n; r++) {
+    if (done[r]) continue;
+    uint32_t L = (uint32_t)(offs[r + 1] - offs[r]);
+    unsigned long long used = 0, n_smems = 0;
+    TgSeedOut sout{pool1.data(), &used, pool1.size(), sfirst1.data(), scount1.data(), &res->flags, &n_smems};
+    std::vector<TgCounters> lane_ctr(32, TgCounters{0, 0, 0});
+    run_lanes(lanes, [&](auto& w) {
+      tg_seed_read(w, sm, bases, offs[r], L, c->opts.min_seed_len, c->slots.data(), c->slot_mask, c->dev.text4,
+                   c->dev.sa, sout, 0);
+      tg_align_read(w, wm, P, bases, offs[r], L, pool1.data() + sfirst1[0], scount1[0], sc, out, r, lane_ctr[w.lane()]);
+    });
     for (auto& lc : lane_ctr) { res->ctr.cells += lc.cells; res->ctr.n_ext += lc.n_ext; res->ctr.hits += lc.hits; }
   }
   return res;
 }
-void ht_result_info(void* rp, uint64_t* out /*n_alns,n_ops,cells,n_ext,hits,flags*/) {
+void ht_result_info(void* rp, uint64_t* out /*n_alns,n_ops,cells,n_ext,hits,flags,items,rounds*/) {
   auto* r = (HtResult*)rp;
-  out[0] = r->n_alns; out[1] = r->n_ops; out[2] = r->ctr.cells; out[3] = r->ctr.n_ext; out[4] = r->ctr.hits; out[5] = (uint64_t)r->flags;
+  out[0] = r->n_alns; out[1] = r->n_ops; out[2] = r->ctr.cells; out[3] = r->ctr.n_ext; out[4] = r->ctr.hits; out[5] = (uint64_t)r->flags; out[6] = r->items; out[7] = r->rounds;
 }
 void ht_result_copy(void* rp, uint64_t* first, uint32_t* count, tg_aln* alns, uint32_t* ops) {
   auto* r = (HtResult*)rp;
@@ -383,13 +486,36 @@ long long ht_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uin
     int xlen = (int)(xoff[t + 1] - xoff[t]), ylen = (int)(yoff[t + 1] - yoff[t]);
     if (xlen > (int)TG_MAX_READ_LEN || x_drop[t] < (int32_t)bw[t]) return -1;
     int ncols = ylen < xlen + (int)bw[t] ? ylen : xlen + (int)bw[t];
-    std::vector<uint8_t> trace((size_t)(ncols + 1) * tg_trace_bytes_per_col(xlen, lanes) + 64);
+    std::vector<uint8_t> trace((size_t)(ncols + 1) * tg_trace_bytes_per_col(xlen, lanes == 0 ? 1 : lanes) + 64);
     std::vector<uint32_t> buf((size_t)xlen + ncols + 8);
     TgOps o{buf.data(), 0};
     TgSwgResult res{0, 0, 0};
     std::vector<unsigned long long> lc(32, 0), le(32, 0);
     int ylen_c = ylen > xlen + (int)bw[t] ? xlen + (int)bw[t] + 1 : ylen;
-    run_lanes(lanes, [&](auto& w) {
+    const int dcls = tg_dpt_class(xlen, (int)bw[t], x_drop[t]);
+    if (lanes == 0 && dcls > 0 && xlen > 0 && ylen > 0) {
+      // pack y as 4-bit codes (ACGNT only), profile from x codes
+      std::vector<uint64_t> ypk((size_t)ylen / 16 + 4, 0);
+      for (int i = 0; i < ylen; i++) ypk[i >> 4] |= (uint64_t)tg_ascii_code(ys[yoff[t] + i]) << ((15 - (i & 15)) * 4);
+      std::vector<uint8_t> xc(xlen);
+      for (int i = 0; i < xlen; i++) xc[i] = (uint8_t)tg_ascii_code(xs[xoff[t] + i]);
+      DptScratch dsc;
+      TgDptMem m = dsc.mem();
+      tg_dpt_profile_codes(m, xc.data(), xlen);
+      TgDptY yy{ypk.data(), 0, ncols, 0, 0, 0};
+      TgDptResult dr{0, 0, 0, 0};
+      std::vector<uint32_t> dops;
+      dpt_dispatch(dcls, m, yy, xlen, ncols, (int)bw[t], x_drop[t], bound_stop != 0, dr, dops);
+      cells += dr.cells;
+      score[t] = dr.score; xend[t] = (uint32_t)dr.xend; yend[t] = (uint32_t)dr.yend;
+      ops_off[t] = total;
+      for (uint32_t i = (uint32_t)dops.size(); i-- > 0;) {
+        if (total < ops_cap) ops[total] = dops[i];
+        total++;
+      }
+      continue;
+    }
+    run_lanes(lanes == 0 ? 1 : lanes, [&](auto& w) {
       TgSwgResult r{0, 0, 0};
       TgOps lo{buf.data(), 0};
       tg_swg_extend(w, xs + xoff[t], ys + yoff[t], xlen, ylen_c, (int)bw[t], x_drop[t], trace.data(), r, lo,

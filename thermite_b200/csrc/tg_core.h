@@ -1080,10 +1080,10 @@ TG_HDN void tg_align_seed_hit(W& w, TgWarpMem& m, const TgAlignParams& P, uint32
 }
 
 // stable bottom-up merge sort of an index array (a -> sorted in a; b is scratch of n entries)
-template <class Less>
-TG_HD void tg_merge_sort_idx(uint16_t* a, uint16_t* b, uint32_t n, Less less) {
-  uint16_t* src = a;
-  uint16_t* dst = b;
+template <class T, class Less>
+TG_HD void tg_merge_sort_idx(T* a, T* b, uint32_t n, Less less) {
+  T* src = a;
+  T* dst = b;
   for (uint32_t width = 1; width < n; width <<= 1) {
     for (uint32_t lo = 0; lo < n; lo += 2 * width) {
       uint32_t mid = lo + width < n ? lo + width : n, hi = lo + 2 * width < n ? lo + 2 * width : n;
@@ -1092,7 +1092,7 @@ TG_HD void tg_merge_sort_idx(uint16_t* a, uint16_t* b, uint32_t n, Less less) {
       while (i < mid) dst[k++] = src[i++];
       while (j < hi) dst[k++] = src[j++];
     }
-    uint16_t* t = src; src = dst; dst = t;
+    T* t = src; src = dst; dst = t;
   }
   if (src != a)
     for (uint32_t i = 0; i < n; i++) a[i] = src[i];

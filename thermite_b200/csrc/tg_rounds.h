@@ -1,14 +1,24 @@
-// tg_rounds.h -- the hit loop of align_read (reference src/aligner.rs:143-175) as a ROUND pipeline:
+// tg_rounds.h -- the hit loop of align_read (reference src/aligner.rs:143-175) as a SPECULATIVE ROUND pipeline.
 //
-//   round r, for every read that still has hits:   prep (thread per read)  ->  extend (warp per task)  ->  post (thread per read)
+// The reference walks the hits of a read one after the other; every accepted hit may narrow (band_width, x_drop) for
+// the hits behind it (:162-171) and raises the running maximum that later hits are filtered against (:154-159).  The
+// DP result of a hit therefore depends on the hits before it only through (band_width, x_drop), and that pair changes
+// rarely: typically once, at the first accepted hit.  So a round evaluates a whole BATCH of consecutive hits of every
+// active read under the read's current (band_width, x_drop):
 //
-// instead of one warp walking a read from start to finish (tg_align_read in tg_core.h, still used for the few
-// "complex" reads: many hits, many transcripts per seed, many accepted alignments).  Why: the per-hit control
-// code (window, interval stab, lifting, seed matching, choosing tx vs genome, filters) is branchy and serial; run by
-// lane 0 of a warp it wastes 31/32 of every issue slot and thrashes the instruction cache, while the DP wants all
-// lanes.  Splitting puts the control code into small thread-per-read kernels (32 reads per warp) and leaves a DP
-// kernel whose warps all execute the same hot loop.  The serial dependency between hits of ONE read (band
-// narrowing, running maximum) is preserved: a read advances by exactly one hit per round.
+//   plan (thread/read)  ->  prep (thread/hit)  ->  extend (warp/task)  ->  post (thread/hit)  ->  scan (thread/read)
+//
+// and `scan` replays the reference's serial loop over the batch results: running maximum, accept / reject, narrowing.
+// When an accepted hit really narrows the band, the hits of the batch BEHIND it were evaluated under a stale state:
+// they are discarded and re-planned in the next round under the new state.  Every hit that is consumed was evaluated
+// with exactly the (band_width, x_drop) the serial loop would have used, so records are bit-identical; only wasted
+// (discarded) work differs.  Batch policy: 1 hit in round 0 (the first accept nearly always narrows the initial wide
+// band), then all remaining hits once something was accepted, else 4, 16, 64 ... (tg_plan_batch).
+//
+// Accepted alignments stay where `post` wrote them (item arrays are append-only within a batch of reads) and are
+// chained per read through TgItemRes::prev_acc; `final` applies src/aligner.rs:177-187.  Reads the tables cannot hold
+// (more than TG_CMAX transcripts on one seed, more hits than the rounds can consume) take the single-warp kernel
+// (tg_align_read in tg_core.h), which recomputes them from scratch.
 //
 // Everything here is expressed with the same building blocks as tg_core.h (and therefore under the same parity
 // tests): prep/post are tg_align_seed_hit cut at the SwgExtend calls.
@@ -17,11 +27,15 @@
 
 #define TG_CMAX 12            // transcript candidates tabulated per hit
 #define TG_PMAX 6             // distinct extension problems per hit (problem 0 = genome)
-#define TG_ACC_MAX 4          // accepted alignments kept per read on the round path
-#define TG_ARENA_WORDS 320u   // RLE words of those alignments
-#define TG_FAST_MAX_HITS 48u  // reads with more hits take the single-warp path
+#define TG_MAX_ROUNDS 16
+#define TG_BATCH_MAX 8192u    // hits of one read evaluated in one round
+#define TG_ROUND_MAX_HITS (TG_BATCH_MAX * (TG_MAX_ROUNDS - 4))  // reads with more hits go straight to the single-warp path
+#define TG_FINAL_SMALL 16u    // accepted alignments the thread-per-read finaliser sorts in local memory
+#define TG_NONE 0xFFFFFFFFu
 
 enum { TG_RS_DONE = 0, TG_RS_ACTIVE = 1, TG_RS_COMPLEX = 2 };
+enum { TG_IF_KEEP = 1, TG_IF_FAIL = 2 };
+enum { TG_FLAG_TASK_POOL = 32, TG_FLAG_ITEM_POOL = 64, TG_FLAG_HOPS_POOL = 128 };
 
 struct TgTask {  // one SwgExtend::extend call (src/swg.rs:31)
   uint32_t read;
@@ -53,21 +67,30 @@ struct TgHit {
   TgProbE prob[TG_PMAX];
   TgCandE cand[TG_CMAX];
 };
+struct TgItemRes {  // one (read, hit) evaluation
+  uint32_t read, hit;    // hit = flat index into the read's hit sequence (Index::all_smems order)
+  int32_t score;         // score of the GenomeAlignment align_seed_hit returns
+  uint32_t cells, n_ext; // work the reference does for this hit
+  uint32_t flags;        // TG_IF_*
+  uint32_t prev_acc;     // previous accepted item of the same read (TG_NONE: first)
+  uint32_t pad;
+};
 struct TgReadState {
   uint32_t L;
   int32_t min_aln, max_aln;
   uint32_t bw, x_drop;
-  uint32_t si, rk;       // cursor: seed index, occurrence (counts down)
-  uint32_t n_acc, arena_used;
+  uint32_t n_hits, next_hit;        // flat hit cursor
+  uint32_t batch_first, batch_n;    // items of the current round
+  uint32_t n_acc, acc_head;         // accepted alignments (chained through TgItemRes::prev_acc, newest first)
   uint32_t status;
-  uint32_t hits, n_ext;        // work counters of this read, added to the batch totals when it finishes on this path
+  uint32_t hits, n_ext;             // work counters of the consumed hits
   unsigned long long cells;
 };
 
 TG_HD const uint64_t* tg_seq_of(const TgIndexDev& ix, uint32_t seqsel) { return seqsel ? ix.txseq4 : ix.text4; }
 
-// src/aligner.rs:130-138
-TG_HD void tg_read_state_init(TgReadState& s, uint32_t L, const tg_opts& o, uint32_t n_seeds, const tg_seed* seeds) {
+// src/aligner.rs:130-138.  Returns false when the read has more hits than the round path handles.
+TG_HD bool tg_read_state_init(TgReadState& s, uint32_t L, const tg_opts& o, uint32_t n_seeds, const tg_seed* seeds) {
   float prod = o.min_aln_score_percent * (float)L;
   int32_t pct_score = (int32_t)prod;
   s.L = L;
@@ -75,11 +98,35 @@ TG_HD void tg_read_state_init(TgReadState& s, uint32_t L, const tg_opts& o, uint
   s.max_aln = s.min_aln;
   s.bw = (s.min_aln < 0) ? 0u : (L > (uint32_t)s.min_aln ? L - (uint32_t)s.min_aln : 0u);
   s.x_drop = s.bw;
-  s.si = 0;
-  s.rk = n_seeds ? seeds[0].count : 0;
-  s.n_acc = 0; s.arena_used = 0;
+  unsigned long long hits = 0;
+  for (uint32_t i = 0; i < n_seeds; i++) hits += seeds[i].count;
+  s.next_hit = 0;
+  s.batch_first = 0; s.batch_n = 0;
+  s.n_acc = 0; s.acc_head = TG_NONE;
   s.hits = 0; s.n_ext = 0; s.cells = 0;
-  s.status = n_seeds ? TG_RS_ACTIVE : TG_RS_DONE;
+  s.status = hits ? TG_RS_ACTIVE : TG_RS_DONE;
+  s.n_hits = hits > TG_ROUND_MAX_HITS ? 0u : (uint32_t)hits;
+  return hits <= TG_ROUND_MAX_HITS;
+}
+
+// hits of the batch a read submits in round `round`
+TG_HD uint32_t tg_plan_batch(const TgReadState& st, uint32_t round) {
+  const uint32_t rem = st.n_hits - st.next_hit;
+  uint32_t b = TG_BATCH_MAX;
+  if (st.n_acc == 0) {  // nothing accepted yet: the state is still the initial one and the next accept will narrow it
+    const uint32_t sh = 2 * round < 13 ? 2 * round : 13;
+    b = 1u << sh;
+  }
+  return rem < b ? rem : b;
+}
+
+// flat hit index -> (seed, occurrence): seeds in order, occurrences of a seed in DESCENDING suffix-array rank
+// (src/index.rs:236-253)
+TG_HD void tg_hit_locate(const tg_seed* seeds, uint32_t n_seeds, uint32_t h, uint32_t& si, uint32_t& rk) {
+  uint32_t s = 0;
+  while (s + 1 < n_seeds && h >= seeds[s].count) { h -= seeds[s].count; s++; }
+  si = s;
+  rk = seeds[s].count - 1 - h;
 }
 
 // ---- prep: everything of align_seed_hit (src/aligner.rs:198-258) that happens before a SwgExtend call ------------
@@ -87,12 +134,15 @@ TG_HD void tg_read_state_init(TgReadState& s, uint32_t L, const tg_opts& o, uint
 // reference's early `break` at a perfect transcript is applied in post), maps identical problems onto each other and
 // emits one task per non-trivial extension.  Returns false when a table overflows (the read becomes "complex").
 template <class W>
-TG_HDN bool tg_round_prep(W& w, const TgAlignParams& P, const uint64_t* rp, TgReadState& st, const tg_seed* seeds,
-                          uint32_t read, TgHit& hit, TgTask* tasks, unsigned long long* task_ctr, unsigned long long task_cap) {
+TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const TgReadState& st, const tg_seed* seeds,
+                         uint32_t n_seeds, uint32_t read, uint32_t flat_hit, TgHit& hit, TgTask* tasks,
+                         unsigned long long* task_ctr, unsigned long long task_cap, int* flags) {
   const TgIndexDev& ix = P.ix;
   const uint32_t L = st.L;
-  const tg_seed sd = seeds[st.si];
-  const uint32_t ref_idx = sd.direct ? sd.sa_lo : TG_LDG(ix.sa + sd.sa_lo + (st.rk - 1));
+  uint32_t si, rk;
+  tg_hit_locate(seeds, n_seeds, flat_hit, si, rk);
+  const tg_seed sd = seeds[si];
+  const uint32_t ref_idx = sd.direct ? sd.sa_lo : TG_LDG(ix.sa + sd.sa_lo + rk);
   const uint32_t q = sd.query_idx, len = sd.len, bw = st.bw;
   hit.ref_idx = ref_idx; hit.q = q; hit.len = len; hit.bw = bw; hit.x_drop = (int32_t)st.x_drop;
   hit.ref_id = tg_idx_to_ref(ix.refs, ix.n_refs, ref_idx);
@@ -148,7 +198,10 @@ TG_HDN bool tg_round_prep(W& w, const TgAlignParams& P, const uint64_t* rp, TgRe
     need += (ncR ? 1u : 0u) + (ncL ? 1u : 0u);
   }
   unsigned long long base = need ? w.atomic_add(task_ctr, (unsigned long long)need) : 0;
-  if (base + need > task_cap) return false;
+  if (base + need > task_cap) {
+    w.atomic_or(flags, TG_FLAG_TASK_POOL);
+    return false;
+  }
   for (uint32_t k = 0; k < hit.n_prob; k++) {
     TgProbE& e = hit.prob[k];
     const uint32_t xr_len = L - (e.q + e.len);
@@ -213,7 +266,7 @@ TG_HDN void tg_task_run(W& w, const TgIndexDev& ix, const uint8_t* bases, const 
   w.sync();
 }
 
-// ---- post: the rest of align_seed_hit (src/aligner.rs:240-314) + the filters of align_read (:146-174) ----------------
+// ---- post: the rest of align_seed_hit (src/aligner.rs:240-314) -------------------------------------------------------
 struct TgSideRes {
   int32_t score;
   uint32_t xend, yend, cells, n_ext, ops_off, ops_n, xclip;  // xclip: Xclip(xlen) of an empty-y extension
@@ -228,69 +281,31 @@ TG_HD TgSideRes tg_side_result(const TgTask* tasks, int32_t task, uint32_t xlen)
   }
   return r;
 }
-TG_HD bool tg_ops_push_cap(TgOps& o, uint32_t cap, uint32_t kind, uint32_t run) {
-  if (run == 0 && kind <= TG_OP_INS) return true;
-  if (kind <= TG_OP_INS && o.n > 0 && (o.w[o.n - 1] & 7u) == kind) { o.w[o.n - 1] += run << 3; return true; }
-  if (o.n >= cap) return false;
-  o.w[o.n++] = kind | (run << 3);
-  return true;
-}
-// rev(left.ops) ++ Match*len ++ right.ops (src/aligner.rs:388-394) from the stored (reversed) task operations
-TG_HD bool tg_stitch_ops(const uint32_t* pool, const TgSideRes& L_, const TgSideRes& R_, uint32_t len, TgOps& out, uint32_t cap) {
-  bool ok = true;
-  if (L_.xclip) ok = ok && tg_ops_push_cap(out, cap, TG_OP_XCLIP, L_.xclip);
-  for (uint32_t i = 0; i < L_.ops_n; i++) ok = ok && tg_ops_push_cap(out, cap, pool[L_.ops_off + i] & 7u, pool[L_.ops_off + i] >> 3);
-  ok = ok && tg_ops_push_cap(out, cap, TG_OP_MATCH, len);
-  for (uint32_t i = R_.ops_n; i-- > 0;) ok = ok && tg_ops_push_cap(out, cap, pool[R_.ops_off + i] & 7u, pool[R_.ops_off + i] >> 3);
-  if (R_.xclip) ok = ok && tg_ops_push_cap(out, cap, TG_OP_XCLIP, R_.xclip);
-  return ok;
-}
-// lift_tx_to_gx with a capacity check (same walk as tg_lift_tx_to_gx)
-TG_HD bool tg_lift_tx_to_gx_cap(const uint32_t* te_start, const uint32_t* te_end, uint32_t e0, uint32_t e1, const TgOps& tx_ops,
-                                uint32_t tx_ystart, uint32_t& g_ystart, uint32_t& g_yend, TgOps& out, uint32_t cap) {
-  out.n = 0;
-  uint32_t i = tx_ystart, exon_sum = 0, ex = e0;
-  while (exon_sum + (TG_LDG(te_end + ex) - TG_LDG(te_start + ex)) <= i) {
-    exon_sum += TG_LDG(te_end + ex) - TG_LDG(te_start + ex);
-    ex++;
-  }
-  g_ystart = TG_LDG(te_start + ex) + (i - exon_sum);
-  bool ok = true;
-  for (uint32_t k = 0; k < tx_ops.n && ok; k++) {
-    uint32_t kind = tx_ops.w[k] & 7u, run = tx_ops.w[k] >> 3;
-    bool consumes = kind == TG_OP_MATCH || kind == TG_OP_SUBST || kind == TG_OP_DEL;
-    uint32_t units = (kind <= TG_OP_INS) ? run : 1u;
-    while (units > 0 && ok) {
-      uint32_t elen = TG_LDG(te_end + ex) - TG_LDG(te_start + ex);
-      if (ex + 1 < e1 && exon_sum + elen <= i) {
-        exon_sum += elen;
-        ex++;
-        ok = ok && tg_ops_push_cap(out, cap, TG_OP_YCLIP, TG_LDG(te_start + ex) - TG_LDG(te_end + ex - 1));
-        elen = TG_LDG(te_end + ex) - TG_LDG(te_start + ex);
-      }
-      if (kind > TG_OP_INS) { ok = ok && tg_ops_push_cap(out, cap, kind, run); units = 0; }
-      else if (!consumes) { ok = ok && tg_ops_push_cap(out, cap, kind, units); units = 0; }
-      else {
-        uint32_t room = (ex + 1 < e1) ? (exon_sum + elen - i) : units;
-        uint32_t take = units < room ? units : room;
-        if (take == 0) take = 1;
-        ok = ok && tg_ops_push_cap(out, cap, kind, take);
-        i += take;
-        units -= take;
-      }
-    }
-  }
-  g_yend = TG_LDG(te_start + ex) + (i - exon_sum);
-  return ok;
+// rev(left.ops) ++ Match*len ++ right.ops (src/aligner.rs:388-394) from the stored (reversed) task operations.
+// `out` must have room for L.ops_n + R.ops_n + 3 words.
+TG_HD void tg_stitch_ops(const uint32_t* pool, const TgSideRes& L_, const TgSideRes& R_, uint32_t len, TgOps& out) {
+  if (L_.xclip) tg_ops_push(out, TG_OP_XCLIP, L_.xclip);
+  for (uint32_t i = 0; i < L_.ops_n; i++) tg_ops_push(out, pool[L_.ops_off + i] & 7u, pool[L_.ops_off + i] >> 3);
+  tg_ops_push(out, TG_OP_MATCH, len);
+  for (uint32_t i = R_.ops_n; i-- > 0;) tg_ops_push(out, pool[R_.ops_off + i] & 7u, pool[R_.ops_off + i] >> 3);
+  if (R_.xclip) tg_ops_push(out, TG_OP_XCLIP, R_.xclip);
 }
 
-// Returns false when the read has to leave the round path (accepted-list or arena overflow).
+struct TgHopsPool {  // operations of the evaluated hits (append-only within a batch of reads)
+  uint32_t* w;
+  unsigned long long* used;
+  unsigned long long cap;
+};
+
+// Evaluates one item: score / type of the GenomeAlignment align_seed_hit would return, and -- when the alignment
+// passes every filter that does not depend on hits in front of it -- the full candidate record with its operations.
 template <class W>
-TG_HDN bool tg_round_post(W& w, const TgAlignParams& P, TgReadState& st, const tg_seed* seeds, uint32_t n_seeds,
-                          const TgHit& hit, const TgTask* tasks, const uint32_t* ops_pool, TgCand* acc, uint32_t* arena) {
+TG_HDN void tg_item_post(W& w, const TgAlignParams& P, const TgReadState& st, const TgHit& hit, const TgTask* tasks,
+                         const uint32_t* dp_ops, TgItemRes& ir, TgCand& cand, const TgHopsPool& hp, int* flags) {
   const TgIndexDev& ix = P.ix;
   const uint32_t L = st.L;
-  struct { unsigned long long cells; uint32_t n_ext; } ctr{0, 0};
+  unsigned long long cells = 0;
+  uint32_t n_ext = 0;
   // extend_left_right results per distinct problem (src/aligner.rs:377-406)
   TgAln pa[TG_PMAX];
   uint32_t pcells[TG_PMAX], pext[TG_PMAX];
@@ -306,7 +321,7 @@ TG_HDN bool tg_round_post(W& w, const TgAlignParams& P, TgReadState& st, const t
     pext[k] = R_.n_ext + L_.n_ext;
   }
   const TgAln gx = pa[0];
-  ctr.cells += pcells[0]; ctr.n_ext += pext[0];
+  cells += pcells[0]; n_ext += pext[0];
   bool have_tx = false;
   uint32_t best_c = 0;
   TgAln best{0, 0, 0, 0, 0};
@@ -317,98 +332,165 @@ TG_HDN bool tg_round_post(W& w, const TgAlignParams& P, TgReadState& st, const t
     // same offsets relative to the seed, expressed in this transcript's coordinates
     ta.ystart = ce.tr - (uint32_t)(e.r_abs - pa[ce.prob].ystart);
     ta.yend = ce.tr + (uint32_t)(pa[ce.prob].yend - e.r_abs);
-    ctr.cells += pcells[ce.prob]; ctr.n_ext += pext[ce.prob];
+    cells += pcells[ce.prob]; n_ext += pext[ce.prob];
     if (!have_tx || ta.score > best.score) { have_tx = true; best = ta; best_c = c; }
     if (ta.score >= (int32_t)L) break;
   }
   const bool exonic = have_tx && best.score >= gx.score;  // ties -> Exonic (:263)
   const int32_t s = exonic ? best.score : gx.score;
   const int32_t range = (int32_t)P.opts.multimap_score_range;
+  ir.score = s;
+  ir.cells = (uint32_t)cells;
+  ir.n_ext = n_ext;
+  ir.prev_acc = TG_NONE;
   bool keep = true;
   if (!P.opts.intron_mode && !exonic) keep = false;                                              // :146-151
-  if (s < P.opts.min_aln_score || s < st.min_aln || s < st.max_aln - range) keep = false;         // :154-159
-  if (keep) {
-    if (st.n_acc >= TG_ACC_MAX) return false;
-    const TgRef aref = ix.refs[hit.ref_id];
-    TgCand c;
-    tg_aln& a = c.a;
-    a.ref_id = hit.ref_id; a.strand = (uint8_t)(aref.strand_rank & 1u); a.primary = 0; a.pad = 0; a.xlen = L;
-    c.name_rank = aref.strand_rank >> 1;
-    const uint32_t room = TG_ARENA_WORDS - st.arena_used;
-    uint32_t ys, ye;
-    TgOps gops{arena + st.arena_used, 0};
-    uint32_t tx_n = 0;
-    if (exonic) {
-      const TgCandE& ce = hit.cand[best_c];
-      const TgProbE& e = hit.prob[ce.prob];
-      // transcript ops go to the upper half of the free arena, the lifted ops in front, then the tx ops are moved up
-      const uint32_t half = room / 2;
-      TgOps tops{arena + st.arena_used + half, 0};
-      TgSideRes R_ = tg_side_result(tasks, e.task_r, L - (e.q + e.len)), L_ = tg_side_result(tasks, e.task_l, e.q);
-      if (!tg_stitch_ops(ops_pool, L_, R_, e.len, tops, room - half)) return false;
-      const uint32_t e0 = TG_LDG(ix.tx_exon_off + ce.tx_idx), e1 = TG_LDG(ix.tx_exon_off + ce.tx_idx + 1);
-      if (!tg_lift_tx_to_gx_cap(ix.te_start, ix.te_end, e0, e1, tops, best.ystart, ys, ye, gops, half)) return false;
-      for (uint32_t i = 0; i < tops.n; i++) arena[st.arena_used + gops.n + i] = tops.w[i];
-      tx_n = tops.n;
-      a.aln_type = TG_ALN_EXONIC;
-      a.score = best.score; a.xstart = best.xstart; a.xend = best.xend;
-      a.tx_or_gene_idx = ce.tx_idx;
-      a.tx_score = best.score; a.tx_ystart = best.ystart; a.tx_yend = best.yend; a.tx_ylen = ce.tlen;
-      a.tx_xstart = best.xstart; a.tx_xend = best.xend;
-    } else {
-      const TgProbE& e = hit.prob[0];
-      TgSideRes R_ = tg_side_result(tasks, e.task_r, L - (e.q + e.len)), L_ = tg_side_result(tasks, e.task_l, e.q);
-      if (!tg_stitch_ops(ops_pool, L_, R_, e.len, gops, room)) return false;
-      uint32_t gene = 0, grank = 0;
-      const TgStabRange gr = tg_stab_begin<W>(w, ix.gene_stab, ix.n_gene_stab, ix.gene_maxlen, gx.ystart, gx.yend);
-      const bool found = tg_stab_next<W>(w, ix.gene_stab, gr, 0u, grank, gene);
-      a.aln_type = found ? TG_ALN_INTRONIC : TG_ALN_INTERGENIC;
-      a.tx_or_gene_idx = found ? gene : 0xFFFFFFFFu;
-      a.score = gx.score; a.xstart = gx.xstart; a.xend = gx.xend;
-      a.tx_score = 0; a.tx_ystart = 0; a.tx_yend = 0; a.tx_ylen = 0; a.tx_xstart = 0; a.tx_xend = 0;
-      ys = gx.ystart; ye = gx.yend;
-    }
-    // concat_to_chr_aln (src/aligner.rs:429-449)
-    const uint32_t rid2 = tg_idx_to_ref(ix.refs, ix.n_refs, ys);
-    const TgRef r2 = ix.refs[rid2];
-    if (r2.strand_rank & 1u) {
-      a.ystart = ys - r2.start_idx;
-      a.yend = ye - r2.start_idx;
-    } else {
-      a.ystart = (uint64_t)r2.len - (ye - r2.start_idx);
-      a.yend = (uint64_t)r2.len - (ys - r2.start_idx);
-      tg_ops_reverse(gops);
-    }
-    a.ylen = r2.len;
-    a.ops_off = st.arena_used; a.ops_len = gops.n;
-    a.tx_ops_off = st.arena_used + gops.n; a.tx_ops_len = tx_n;
-    acc[st.n_acc++] = c;
-    st.arena_used += gops.n + tx_n;
-    // :162-172
-    uint32_t lim = (s < 0) ? 0u : ((L + P.opts.multimap_score_range > (uint32_t)s) ? L + P.opts.multimap_score_range - (uint32_t)s : 0u);
-    if (lim < st.bw) st.bw = lim;
-    if (lim < st.x_drop) st.x_drop = lim;
+  // :154-159 against the maximum at the START of the round (a lower bound of the running maximum `scan` applies)
+  if (s < P.opts.min_aln_score || s < st.min_aln || s < st.max_aln - range) keep = false;
+  ir.flags = 0;
+  if (!keep) return;
+  const TgRef aref = ix.refs[hit.ref_id];
+  tg_aln& a = cand.a;
+  a.ref_id = hit.ref_id; a.strand = (uint8_t)(aref.strand_rank & 1u); a.primary = 0; a.pad = 0; a.xlen = L;
+  cand.name_rank = aref.strand_rank >> 1;
+  const TgProbE& e = exonic ? hit.prob[hit.cand[best_c].prob] : hit.prob[0];
+  const TgSideRes R_ = tg_side_result(tasks, e.task_r, L - (e.q + e.len)), L_ = tg_side_result(tasks, e.task_l, e.q);
+  const uint32_t stitched_max = L_.ops_n + R_.ops_n + 3;
+  uint32_t e0 = 0, e1 = 0;
+  if (exonic) {
+    e0 = TG_LDG(ix.tx_exon_off + hit.cand[best_c].tx_idx);
+    e1 = TG_LDG(ix.tx_exon_off + hit.cand[best_c].tx_idx + 1);
+  }
+  // lifted ops: every exon boundary adds a Yclip and may split a run
+  const uint32_t lifted_max = exonic ? stitched_max + 2 * (e1 - e0) + 2 : 0;
+  const unsigned long long base = w.atomic_add(hp.used, (unsigned long long)(stitched_max + lifted_max));
+  if (base + stitched_max + lifted_max > hp.cap || base + stitched_max + lifted_max > 0xFFFFFFFFull) {
+    w.atomic_or(flags, TG_FLAG_HOPS_POOL);
+    return;
+  }
+  uint32_t ys, ye;
+  if (exonic) {
+    const TgCandE& ce = hit.cand[best_c];
+    TgOps gops{hp.w + base, 0}, tops{hp.w + base + lifted_max, 0};
+    tg_stitch_ops(dp_ops, L_, R_, e.len, tops);
+    tg_lift_tx_to_gx(ix.te_start, ix.te_end, e0, e1, tops, best.ystart, ys, ye, gops);
+    a.aln_type = TG_ALN_EXONIC;
+    a.score = best.score; a.xstart = best.xstart; a.xend = best.xend;
+    a.tx_or_gene_idx = ce.tx_idx;
+    a.tx_score = best.score; a.tx_ystart = best.ystart; a.tx_yend = best.yend; a.tx_ylen = ce.tlen;
+    a.tx_xstart = best.xstart; a.tx_xend = best.xend;
+    a.ops_off = (uint32_t)base; a.ops_len = gops.n;
+    a.tx_ops_off = (uint32_t)(base + lifted_max); a.tx_ops_len = tops.n;
+  } else {
+    TgOps gops{hp.w + base, 0};
+    tg_stitch_ops(dp_ops, L_, R_, e.len, gops);
+    uint32_t gene = 0, grank = 0;
+    const TgStabRange gr = tg_stab_begin<W>(w, ix.gene_stab, ix.n_gene_stab, ix.gene_maxlen, gx.ystart, gx.yend);
+    const bool found = tg_stab_next<W>(w, ix.gene_stab, gr, 0u, grank, gene);
+    a.aln_type = found ? TG_ALN_INTRONIC : TG_ALN_INTERGENIC;
+    a.tx_or_gene_idx = found ? gene : 0xFFFFFFFFu;
+    a.score = gx.score; a.xstart = gx.xstart; a.xend = gx.xend;
+    a.tx_score = 0; a.tx_ystart = 0; a.tx_yend = 0; a.tx_ylen = 0; a.tx_xstart = 0; a.tx_xend = 0;
+    ys = gx.ystart; ye = gx.yend;
+    a.ops_off = (uint32_t)base; a.ops_len = gops.n;
+    a.tx_ops_off = 0; a.tx_ops_len = 0;
+  }
+  // concat_to_chr_aln (src/aligner.rs:429-449)
+  const uint32_t rid2 = tg_idx_to_ref(ix.refs, ix.n_refs, ys);
+  const TgRef r2 = ix.refs[rid2];
+  if (r2.strand_rank & 1u) {
+    a.ystart = ys - r2.start_idx;
+    a.yend = ye - r2.start_idx;
+  } else {
+    a.ystart = (uint64_t)r2.len - (ye - r2.start_idx);
+    a.yend = (uint64_t)r2.len - (ys - r2.start_idx);
+    TgOps gops{hp.w + base, a.ops_len};
+    tg_ops_reverse(gops);
+  }
+  a.ylen = r2.len;
+  ir.flags = TG_IF_KEEP;
+}
+
+// ---- scan: the serial part of the reference's loop (src/aligner.rs:146-174) over the batch of one read -----------------
+// Returns false when the read has to leave the round path (an item of the batch overflowed a table).
+TG_HD bool tg_scan_read(const tg_opts& o, TgReadState& st, TgItemRes* ires) {
+  const int32_t range = (int32_t)o.multimap_score_range;
+  uint32_t consumed = 0;
+  for (uint32_t i = 0; i < st.batch_n; i++) {
+    const uint32_t item = st.batch_first + i;
+    TgItemRes& ir = ires[item];
+    if (ir.flags & TG_IF_FAIL) return false;
+    consumed = i + 1;
+    st.hits++; st.cells += ir.cells; st.n_ext += ir.n_ext;
+    if (!(ir.flags & TG_IF_KEEP)) continue;
+    const int32_t s = ir.score;
+    if (s < st.max_aln - range) continue;  // :154-159 against the running maximum
+    ir.prev_acc = st.acc_head;
+    st.acc_head = item;
+    st.n_acc++;
+    // :162-172 (`score as usize` wraps for negative scores => saturating_sub gives 0)
+    const uint32_t L = st.L;
+    const uint32_t lim = (s < 0) ? 0u : ((L + o.multimap_score_range > (uint32_t)s) ? L + o.multimap_score_range - (uint32_t)s : 0u);
+    bool narrowed = false;
+    if (lim < st.bw) { st.bw = lim; narrowed = true; }
+    if (lim < st.x_drop) { st.x_drop = lim; narrowed = true; }
     if (s > st.max_aln) st.max_aln = s;
+    if (narrowed) break;  // the rest of the batch was evaluated under the old (band_width, x_drop): redo it
   }
-  st.hits++; st.cells += ctr.cells; st.n_ext += ctr.n_ext;
-  // next hit: occurrences of a seed in descending SA rank, then the next seed (src/index.rs:236-253)
-  if (st.rk > 1) st.rk--;
-  else {
-    st.si++;
-    if (st.si >= n_seeds) st.status = TG_RS_DONE;
-    else st.rk = seeds[st.si].count;
-  }
+  st.next_hit += consumed;
+  st.batch_n = 0;
+  if (st.next_hit >= st.n_hits) st.status = TG_RS_DONE;
   return true;
 }
 
-// ---- end of read (src/aligner.rs:177-187) for reads that finished on the round path ---------------------------------------
-template <class W>
-TG_HDN void tg_round_final(W& w, const TgAlignParams& P, const TgReadState& st, const TgCand* acc, const uint32_t* arena,
-                           const TgAlignOut& out, uint32_t r) {
-  uint16_t order[TG_ACC_MAX], tmp[TG_ACC_MAX];
-  const uint32_t k = tg_finalize_read(acc, st.n_acc, st.max_aln, (int32_t)P.opts.multimap_score_range, order, tmp);
+// ---- end of read (src/aligner.rs:177-187) for reads that finished on the round path -----------------------------------
+// `idx` / `tmp` / `items`: scratch of n_acc entries each.  cands[] / ires[] are the item arrays.
+template <class T>
+TG_HD uint32_t tg_finalize_items(const TgCand* cands, const uint32_t* items, uint32_t n, int32_t max_aln_score, int32_t range,
+                                 T* order, T* tmp) {
+  // same algorithm as tg_finalize_read, candidates addressed through `items`
+  uint32_t m = 0;
+  for (uint32_t i = 0; i < n; i++)
+    if (cands[items[i]].a.score >= max_aln_score - range) order[m++] = (T)i;
+  if (m == 0) return 0;
+  tg_merge_sort_idx(order, tmp, m, [&](T x, T y) {
+    const TgCand& a = cands[items[x]];
+    const TgCand& b = cands[items[y]];
+    if (a.name_rank != b.name_rank) return a.name_rank < b.name_rank;
+    if (a.a.strand != b.a.strand) return a.a.strand < b.a.strand;
+    return a.a.ystart < b.a.ystart;
+  });
+  uint32_t k = 0;
+  uint64_t max_end = 0;
+  for (uint32_t i = 0; i < m; i++) {
+    const TgCand& cc = cands[items[order[i]]];
+    bool fresh = k == 0 || cc.a.ystart >= max_end || cc.name_rank != cands[items[tmp[k - 1]]].name_rank ||
+                 cc.a.strand != cands[items[tmp[k - 1]]].a.strand;
+    if (fresh) {
+      max_end = cc.a.yend;
+      tmp[k++] = order[i];
+    } else {
+      if (cc.a.score > cands[items[tmp[k - 1]]].a.score) tmp[k - 1] = order[i];
+      uint64_t ce = cands[items[tmp[k - 1]]].a.yend;
+      if (ce > max_end) max_end = ce;
+    }
+  }
+  for (uint32_t i = 0; i < k; i++) order[i] = tmp[i];
+  tg_merge_sort_idx(order, tmp, k, [&](T x, T y) { return cands[items[x]].a.score > cands[items[y]].a.score; });
+  return k;
+}
+
+// Writes the output records of one read.  Serial; `items`, `order`, `tmp` hold st.n_acc entries.
+template <class W, class T>
+TG_HDN void tg_round_final(W& w, const TgAlignParams& P, const TgReadState& st, const TgCand* cands, const TgItemRes* ires,
+                           const uint32_t* hops, uint32_t* items, T* order, T* tmp, const TgAlignOut& out,
+                           uint32_t r) {
+  // accepted items in acceptance order (the chain runs newest -> oldest)
+  uint32_t it = st.acc_head;
+  for (uint32_t i = st.n_acc; i-- > 0;) { items[i] = it; it = ires[it].prev_acc; }
+  const uint32_t k = tg_finalize_items(cands, items, st.n_acc, st.max_aln, (int32_t)P.opts.multimap_score_range, order, tmp);
   unsigned long long words = 0;
-  for (uint32_t i = 0; i < k; i++) words += acc[order[i]].a.ops_len + acc[order[i]].a.tx_ops_len;
+  for (uint32_t i = 0; i < k; i++) words += cands[items[order[i]]].a.ops_len + cands[items[order[i]]].a.tx_ops_len;
   unsigned long long abase = 0, obase = 0;
   uint32_t kk = k;
   if (k > 0) {
@@ -421,9 +503,10 @@ TG_HDN void tg_round_final(W& w, const TgAlignParams& P, const TgReadState& st, 
   }
   unsigned long long o = obase;
   for (uint32_t i = 0; i < kk; i++) {
-    const TgCand& c = acc[order[i]];
+    const TgCand& c = cands[items[order[i]]];
     const uint32_t n1 = c.a.ops_len, n2 = c.a.tx_ops_len;
-    for (uint32_t t = 0; t < n1 + n2; t++) out.ops[o + t] = arena[c.a.ops_off + t];
+    for (uint32_t t = 0; t < n1; t++) out.ops[o + t] = hops[c.a.ops_off + t];
+    for (uint32_t t = 0; t < n2; t++) out.ops[o + n1 + t] = hops[c.a.tx_ops_off + t];
     tg_aln a = c.a;
     a.ops_off = (uint32_t)o;
     a.tx_ops_off = (uint32_t)(o + n1);

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "tg_rounds.h"
+#include "tg_dpt.h"
 
 #define TG_FULL 0xffffffffu
 #define TG_WARPS_PER_CTA 4
@@ -142,7 +143,8 @@ struct DevThread {
   }
 };
 
-#define TG_MAX_ROUNDS 48
+#define TG_DPT_CBINS 64
+#define TG_DPT_NBINS (TG_DPT_NCLS * TG_DPT_CBINS)
 struct DevCounters {
   unsigned long long seed_used, n_smems, alns_used, ops_used, cells, n_ext, hits, work_seed, work_ext, swg_ops_used,
       work_swg, kmer_groups;
@@ -151,7 +153,12 @@ struct DevCounters {
   unsigned long long phase[16];
   // round pipeline
   unsigned long long n_complex, work_complex;
-  unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS];
+  unsigned long long items_used, hops_used, fin_used;
+  unsigned long long round_end[TG_MAX_ROUNDS];  // items_used after round r
+  unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS];
+  // task sorting for the thread-per-extension kernel: bins = class * TG_DPT_CBINS + column bucket
+  uint32_t bin_count[TG_DPT_NBINS], bin_cursor[TG_DPT_NBINS];
+  uint32_t cls_start[TG_DPT_NCLS + 1], cls_chunk0[TG_DPT_NCLS + 1];
 };
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -325,7 +332,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_extend(ExtParams p) {
 __host__ __device__ inline size_t swg_smem_per_warp(uint32_t max_xlen, uint32_t max_cols, uint32_t trace_bytes, uint32_t ops_words);
 
 // ---------------------------------------------------------------------------------------------------
-// round pipeline (tg_rounds.h): thread-per-read control kernels + a warp-per-task extension kernel
+// round pipeline (tg_rounds.h): thread-per-read / thread-per-hit control kernels + a warp-per-task extension kernel
 // ---------------------------------------------------------------------------------------------------
 struct RoundParams {
   TgAlignParams P;
@@ -336,16 +343,25 @@ struct RoundParams {
   const uint64_t* read_seed_first;
   const uint32_t* read_seed_count;
   TgReadState* st;
-  TgHit* hits;
-  TgCand* acc;        // [n_reads][TG_ACC_MAX]
-  uint32_t* arena;    // [n_reads][TG_ARENA_WORDS]
   uint64_t* rp;       // [n_reads][rp_words] packed reads
+  // items (append-only within the batch): one per evaluated (read, hit)
+  TgHit* hits;
+  TgItemRes* ires;
+  TgCand* cands;
+  unsigned long long item_cap;
+  TgHopsPool hp;      // operations of the kept items
+  uint32_t* fin;      // scratch of the finaliser for reads with many accepted alignments
+  unsigned long long fin_cap;
+  // per round
   TgTask* tasks;
   unsigned long long task_cap;
   uint32_t* ops_pool;
   unsigned long long ops_cap;
   uint32_t* complex_list;
   uint32_t round;
+  uint32_t* sorted;        // task indices of the round, grouped by class and (descending) column count
+  uint32_t* dpt_trace;     // thread kernel: [warp][col][word][lane]
+  size_t dpt_trace_words;  // per warp
   uint32_t max_xlen, max_cols, trace_bytes, ops_words;
   int bound_stop;
   TgAlignOut out;
@@ -358,6 +374,12 @@ __device__ __forceinline__ void mark_complex(const RoundParams& p, uint32_t r, i
   unsigned long long i = atomicAdd(&p.ctr->n_complex, 1ull);
   p.complex_list[i] = r;
 }
+__device__ __forceinline__ void round_item_range(const RoundParams& p, unsigned long long& lo, unsigned long long& hi) {
+  lo = p.round ? p.ctr->round_end[p.round - 1] : 0ull;
+  hi = p.ctr->items_used;
+  if (hi > p.item_cap) hi = p.item_cap;
+  if (lo > hi) lo = hi;
+}
 
 __global__ void __launch_bounds__(128) k_round_init(RoundParams p) {
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
@@ -365,10 +387,10 @@ __global__ void __launch_bounds__(128) k_round_init(RoundParams p) {
     const uint32_t L = (uint32_t)(p.offs[r + 1] - off);
     const uint32_t ns = p.read_seed_count[r];
     const tg_seed* sd = p.seeds + p.read_seed_first[r];
-    unsigned long long hits = 0;
-    for (uint32_t i = 0; i < ns; i++) hits += sd[i].count;
-    tg_read_state_init(p.st[r], L, p.P.opts, ns, sd);
-    if (hits > TG_FAST_MAX_HITS) { mark_complex(p, r, 0); continue; }
+    TgReadState st;
+    const bool ok = tg_read_state_init(st, L, p.P.opts, ns, sd);
+    p.st[r] = st;
+    if (!ok) { mark_complex(p, r, 0); continue; }
     if (ns == 0) continue;
     uint64_t* rp = p.rp + (size_t)r * p.rp_words;
     for (uint32_t wi = 0; wi < L / 16 + 3; wi++) {
@@ -382,14 +404,37 @@ __global__ void __launch_bounds__(128) k_round_init(RoundParams p) {
   }
 }
 
+// every active read submits its next batch of hits
+__global__ void __launch_bounds__(128) k_round_plan(RoundParams p) {
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
+    if (p.st[r].status != TG_RS_ACTIVE) continue;
+    TgReadState st = p.st[r];
+    uint32_t b = tg_plan_batch(st, p.round);
+    const unsigned long long base = atomicAdd(&p.ctr->items_used, (unsigned long long)b);
+    if (base + b > p.item_cap) {
+      atomicOr(&p.ctr->flags, TG_FLAG_ITEM_POOL);
+      b = 0;
+    }
+    st.batch_first = (uint32_t)base; st.batch_n = b;
+    for (uint32_t i = 0; i < b; i++) {
+      TgItemRes& ir = p.ires[base + i];
+      ir.read = r; ir.hit = st.next_hit + i; ir.flags = 0; ir.prev_acc = TG_NONE;
+    }
+    p.st[r] = st;
+  }
+}
+
 __global__ void __launch_bounds__(128) k_round_prep(RoundParams p) {
   DevThread w;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
-    TgReadState st = p.st[r];
-    if (st.status != TG_RS_ACTIVE) continue;
-    const bool ok = tg_round_prep<DevThread>(w, p.P, p.rp + (size_t)r * p.rp_words, st, p.seeds + p.read_seed_first[r], r,
-                                             p.hits[r], p.tasks, &p.ctr->round_tasks[p.round], p.task_cap);
-    if (!ok) mark_complex(p, r, 1);
+  unsigned long long lo, hi;
+  round_item_range(p, lo, hi);
+  for (unsigned long long it = lo + blockIdx.x * blockDim.x + threadIdx.x; it < hi; it += (unsigned long long)gridDim.x * blockDim.x) {
+    TgItemRes& ir = p.ires[it];
+    const uint32_t r = ir.read;
+    const bool ok = tg_item_prep<DevThread>(w, p.P, p.rp + (size_t)r * p.rp_words, p.st[r], p.seeds + p.read_seed_first[r],
+                                            p.read_seed_count[r], r, ir.hit, p.hits[it], p.tasks, &p.ctr->round_tasks[p.round],
+                                            p.task_cap, &p.ctr->flags);
+    if (!ok) ir.flags = TG_IF_FAIL;
   }
 }
 
@@ -402,29 +447,184 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_round_dp(RoundParams 
   uint8_t* trace = base; base += align16(p.trace_bytes);
   uint32_t* obuf = (uint32_t*)base;
   DevWarp w;
-  unsigned long long n_tasks = p.ctr->round_tasks[p.round];
-  if (n_tasks > p.task_cap) n_tasks = p.task_cap;
+  const uint32_t n_tasks = p.ctr->cls_start[1];  // class 0 = not eligible for the thread kernel
   for (;;) {
     uint32_t t = next_work(&p.ctr->round_work[p.round]);
-    if ((unsigned long long)t >= n_tasks) break;
-    tg_task_run<DevWarp, RMAX>(w, p.P.ix, p.bases, p.offs, p.tasks[t], sx, sy, trace, obuf, p.ops_pool, &p.ctr->round_ops[p.round],
+    if (t >= n_tasks) break;
+    tg_task_run<DevWarp, RMAX>(w, p.P.ix, p.bases, p.offs, p.tasks[p.sorted[t]], sx, sy, trace, obuf, p.ops_pool, &p.ctr->round_ops[p.round],
                                p.ops_cap, &p.ctr->flags, p.bound_stop != 0);
+  }
+}
+
+// ---- task sorting: histogram -> bin starts -> scatter ------------------------------------------------------------
+__device__ __forceinline__ uint32_t task_bin(const TgTask& t) {
+  const int xlen = (int)t.xlen, bw = (int)t.bw, ylen = (int)t.ylen;
+  const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
+  const int cls = tg_dpt_class(xlen, bw, t.x_drop);
+  const int cb = (ncols < 255 ? ncols : 255) >> 2;
+  return (uint32_t)(cls * TG_DPT_CBINS + (TG_DPT_CBINS - 1 - cb));
+}
+__global__ void __launch_bounds__(256) k_round_hist(RoundParams p) {
+  __shared__ uint32_t h[TG_DPT_NBINS];
+  for (int i = threadIdx.x; i < TG_DPT_NBINS; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  unsigned long long n_tasks = p.ctr->round_tasks[p.round];
+  if (n_tasks > p.task_cap) n_tasks = p.task_cap;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tasks; t += (unsigned long long)gridDim.x * blockDim.x)
+    atomicAdd(&h[task_bin(p.tasks[t])], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < TG_DPT_NBINS; i += blockDim.x)
+    if (h[i]) atomicAdd(&p.ctr->bin_count[i], h[i]);
+}
+// one block: exclusive scan of the bins; class ranges and warp-chunk table; clears the counts for the next round
+__global__ void __launch_bounds__(1024) k_round_binscan(RoundParams p) {
+  __shared__ uint32_t v[TG_DPT_NBINS + 1];
+  for (int i = threadIdx.x; i < TG_DPT_NBINS; i += blockDim.x) { v[i] = p.ctr->bin_count[i]; p.ctr->bin_count[i] = 0; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0, chunks = 0;
+    for (int c = 0; c < TG_DPT_NCLS; c++) {
+      p.ctr->cls_start[c] = acc;
+      p.ctr->cls_chunk0[c] = chunks;
+      const uint32_t a0 = acc;
+      for (int b = 0; b < TG_DPT_CBINS; b++) {
+        const uint32_t n = v[c * TG_DPT_CBINS + b];
+        v[c * TG_DPT_CBINS + b] = acc;
+        acc += n;
+      }
+      if (c > 0) chunks += (acc - a0 + 31) / 32;
+    }
+    p.ctr->cls_start[TG_DPT_NCLS] = acc;
+    p.ctr->cls_chunk0[TG_DPT_NCLS] = chunks;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TG_DPT_NBINS; i += blockDim.x) p.ctr->bin_cursor[i] = v[i];
+}
+__global__ void __launch_bounds__(256) k_round_scatter(RoundParams p) {
+  __shared__ uint32_t h[TG_DPT_NBINS];
+  unsigned long long n_tasks = p.ctr->round_tasks[p.round];
+  if (n_tasks > p.task_cap) n_tasks = p.task_cap;
+  const unsigned long long per_block = 256ull * 8;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * per_block; base < n_tasks; base += (unsigned long long)gridDim.x * per_block) {
+    for (int i = threadIdx.x; i < TG_DPT_NBINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    uint32_t bin[8], rank[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const unsigned long long t = base + (unsigned long long)k * 256 + threadIdx.x;
+      bin[k] = 0xFFFFFFFFu;
+      if (t < n_tasks) { bin[k] = task_bin(p.tasks[t]); rank[k] = atomicAdd(&h[bin[k]], 1u); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TG_DPT_NBINS; i += blockDim.x)
+      if (h[i]) h[i] = atomicAdd(&p.ctr->bin_cursor[i], h[i]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const unsigned long long t = base + (unsigned long long)k * 256 + threadIdx.x;
+      if (bin[k] != 0xFFFFFFFFu) p.sorted[h[bin[k]] + rank[k]] = (uint32_t)t;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- thread-per-extension kernel (tg_dpt.h) ----------------------------------------------------------------------------
+template <int WB>
+__device__ __noinline__ void dpt_task(const RoundParams& p, TgTask& t, bool active, const TgDptMem& m, int lane) {
+  TgDptResult res{0, 0, 0, 0};
+  TgDptY ys;
+  uint32_t n_ops = 0;
+  int xlen = 0, bw = 0;
+  if (active) {
+    xlen = (int)t.xlen; bw = (int)t.bw;
+    const int ylen = (int)t.ylen;
+    const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
+    ys.seq = tg_seq_of(p.P.ix, t.seqsel); ys.y0 = t.y0; ys.ncols = ncols; ys.side = t.side; ys.word = 0; ys.need = 0;
+    tg_dpt_profile(m, p.rp + (size_t)t.read * p.rp_words, t.xoff, xlen, t.side);
+    tg_dpt_fill<WB>(m, ys, xlen, ncols, bw, t.x_drop, p.bound_stop != 0, res);
+    n_ops = tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [](uint32_t, uint32_t, uint32_t) {});
+  }
+  __syncwarp();
+  // one pool allocation per warp
+  uint32_t incl = n_ops;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(TG_FULL, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const uint32_t total = __shfl_sync(TG_FULL, incl, 31);
+  unsigned long long base = 0;
+  if (lane == 0 && total) base = atomicAdd(&p.ctr->round_ops[p.round], (unsigned long long)total);
+  base = __shfl_sync(TG_FULL, base, 0);
+  if (base + total > p.ops_cap) {
+    if (lane == 0) atomicOr(&p.ctr->flags, TG_FLAG_OPS_POOL);
+    n_ops = 0;
+  }
+  if (active) {
+    const unsigned long long dst = base + incl - n_ops;
+    uint32_t* out = p.ops_pool + dst;
+    if (n_ops) tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [out](uint32_t i, uint32_t kind, uint32_t run) { out[i] = kind | (run << 3); });
+    t.score = res.score; t.xend = (uint32_t)res.xend; t.yend = (uint32_t)res.yend; t.cells = res.cells;
+    t.ops_off = (uint32_t)dst; t.ops_n = n_ops;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_round_dpt(RoundParams p) {
+  __shared__ uint32_t msk[32 * 128];
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  TgDptMem m;
+  m.msk = msk + threadIdx.x; m.mstride = 128;
+  m.tr = p.dpt_trace + (size_t)gw * p.dpt_trace_words + lane; m.tstride = 32;
+  const uint32_t n_chunks = p.ctr->cls_chunk0[TG_DPT_NCLS];
+  for (;;) {
+    const uint32_t g = next_work(&p.ctr->round_work2[p.round]);
+    if (g >= n_chunks) break;
+    int cls = 1;
+    while (cls + 1 < TG_DPT_NCLS && g >= p.ctr->cls_chunk0[cls + 1]) cls++;
+    const uint32_t first = p.ctr->cls_start[cls] + (g - p.ctr->cls_chunk0[cls]) * 32u;
+    const uint32_t end = p.ctr->cls_start[cls + 1];
+    const bool active = first + lane < end;
+    TgTask& t = p.tasks[active ? p.sorted[first + lane] : p.sorted[first]];
+    switch (cls) {
+      case 1: dpt_task<8>(p, t, active, m, lane); break;
+      case 2: dpt_task<16>(p, t, active, m, lane); break;
+      case 3: dpt_task<24>(p, t, active, m, lane); break;
+      case 4: dpt_task<32>(p, t, active, m, lane); break;
+      case 5: dpt_task<40>(p, t, active, m, lane); break;
+      case 6: dpt_task<48>(p, t, active, m, lane); break;
+      case 7: dpt_task<56>(p, t, active, m, lane); break;
+      case 8: dpt_task<64>(p, t, active, m, lane); break;
+      case 9: dpt_task<72>(p, t, active, m, lane); break;
+      default: dpt_task<80>(p, t, active, m, lane); break;
+    }
+    __syncwarp();
   }
 }
 
 __global__ void __launch_bounds__(128) k_round_post(RoundParams p) {
   DevThread w;
+  unsigned long long lo, hi;
+  round_item_range(p, lo, hi);
+  for (unsigned long long it = lo + blockIdx.x * blockDim.x + threadIdx.x; it < hi; it += (unsigned long long)gridDim.x * blockDim.x) {
+    TgItemRes& ir = p.ires[it];
+    if (ir.flags & TG_IF_FAIL) continue;
+    tg_item_post<DevThread>(w, p.P, p.st[ir.read], p.hits[it], p.tasks, p.ops_pool, ir, p.cands[it], p.hp, &p.ctr->flags);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_round_scan(RoundParams p) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.ctr->round_end[p.round] = p.ctr->items_used;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
+    if (p.st[r].status != TG_RS_ACTIVE) continue;
     TgReadState st = p.st[r];
-    if (st.status != TG_RS_ACTIVE) continue;
-    const bool ok = tg_round_post<DevThread>(w, p.P, st, p.seeds + p.read_seed_first[r], p.read_seed_count[r], p.hits[r], p.tasks,
-                                             p.ops_pool, p.acc + (size_t)r * TG_ACC_MAX, p.arena + (size_t)r * TG_ARENA_WORDS);
-    if (!ok) { mark_complex(p, r, 2); continue; }
+    if (st.batch_n == 0) continue;
+    if (!tg_scan_read(p.P.opts, st, p.ires)) { mark_complex(p, r, 1); continue; }
     p.st[r] = st;
   }
 }
 
-// reads still active after the last round go to the single-warp path too
+// src/aligner.rs:177-187 for the reads that finished on the round path; the others join the single-warp list
 __global__ void __launch_bounds__(128) k_round_final(RoundParams p) {
   DevThread w;
   unsigned long long cells = 0, n_ext = 0, hits = 0;
@@ -432,7 +632,16 @@ __global__ void __launch_bounds__(128) k_round_final(RoundParams p) {
     const TgReadState st = p.st[r];
     if (st.status == TG_RS_COMPLEX) continue;
     if (st.status == TG_RS_ACTIVE) { mark_complex(p, r, 3); continue; }
-    tg_round_final<DevThread>(w, p.P, st, p.acc + (size_t)r * TG_ACC_MAX, p.arena + (size_t)r * TG_ARENA_WORDS, p.out, r);
+    if (st.n_acc <= TG_FINAL_SMALL) {
+      uint32_t items[TG_FINAL_SMALL];
+      uint16_t order[TG_FINAL_SMALL], tmp[TG_FINAL_SMALL];
+      tg_round_final<DevThread, uint16_t>(w, p.P, st, p.cands, p.ires, p.hp.w, items, order, tmp, p.out, r);
+    } else {
+      const unsigned long long base = atomicAdd(&p.ctr->fin_used, 3ull * st.n_acc);
+      if (base + 3ull * st.n_acc > p.fin_cap) { mark_complex(p, r, 2); continue; }
+      uint32_t* f = p.fin + base;
+      tg_round_final<DevThread, uint32_t>(w, p.P, st, p.cands, p.ires, p.hp.w, f, f + st.n_acc, f + 2 * (size_t)st.n_acc, p.out, r);
+    }
     cells += st.cells; n_ext += st.n_ext; hits += st.hits;
   }
   cells = warp_sum(cells); n_ext = warp_sum(n_ext); hits = warp_sum(hits);
@@ -581,9 +790,10 @@ struct tg_ctx {
   uint64_t alns_cap = 0, ops_cap = 0;
   uint32_t scratch_warps = 0;
   // round pipeline scratch
-  DevBuf r_state, r_hits, r_acc, r_arena, r_rp, r_tasks, r_ops, r_complex;
-  uint64_t round_task_cap = 0, round_ops_cap = 0;
+  DevBuf r_state, r_hits, r_ires, r_cands, r_hops, r_fin, r_rp, r_tasks, r_ops, r_complex, r_sorted, r_dpt_trace;
+  uint64_t round_task_cap = 0, round_ops_cap = 0, item_cap = 0, hops_cap = 0;
   int use_rounds = 1;
+  uint64_t n_launches = 0;  // kernels launched by the last batch call
   // host results
   PinBuf h_first, h_count, h_alns, h_ops, h_seeds, h_seed_first, h_seed_count;
   // swg batch
@@ -684,7 +894,7 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->ix->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_acc, &c->r_arena, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex,
+  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_ires, &c->r_cands, &c->r_hops, &c->r_fin, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex, &c->r_sorted, &c->r_dpt_trace,
                     &c->d_aln_first, &c->d_aln_count, &c->d_alns, &c->d_ops, &c->s_x, &c->s_xo, &c->s_y, &c->s_yo, &c->s_bw,
                     &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops})
     b->release();
@@ -760,6 +970,15 @@ void tg_ctx_set_exact_cell_count(tg_ctx* ctx, int on) {
 void tg_ctx_debug_phases(const tg_ctx* ctx, uint64_t* out16) {
   for (int k = 0; k < 16; k++) out16[k] = ctx ? ctx->h_ctr->phase[k] : 0;
 }
+// debug: out[0..3] = items, hops words, complex reads, fin words; then round_end[16], round_tasks[16], round_ops[16]
+void tg_ctx_debug_rounds(const tg_ctx* ctx, uint64_t* out52) {
+  const DevCounters* h = ctx->h_ctr;
+  out52[0] = h->items_used; out52[1] = h->hops_used; out52[2] = h->n_complex; out52[3] = h->fin_used;
+  for (int r = 0; r < TG_MAX_ROUNDS; r++) {
+    out52[4 + r] = h->round_end[r]; out52[4 + TG_MAX_ROUNDS + r] = h->round_tasks[r]; out52[4 + 2 * TG_MAX_ROUNDS + r] = h->round_ops[r];
+  }
+}
+uint64_t tg_ctx_last_kernel_launches(const tg_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots * sizeof(TgSlot) : 0; }
 
 }  // extern "C"
@@ -783,6 +1002,7 @@ tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs,
   p.out.flags = &c->d_ctr->flags; p.out.n_smems = &c->d_ctr->n_smems;
   p.ctr = c->d_ctr;
   k_seed<<<blocks, TG_WARPS_PER_CTA * 32, smem, c->stream>>>(p);
+  c->n_launches++;
   CU_CHECK(cudaGetLastError());
   return TG_OK;
 }
@@ -833,6 +1053,7 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.out.alns_cap = c->alns_cap; p.out.ops_cap = c->ops_cap; p.out.flags = &c->d_ctr->flags;
   p.ctr = c->d_ctr;
   kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
+  c->n_launches++;
   CU_CHECK(cudaGetLastError());
   return TG_OK;
 }
@@ -840,12 +1061,17 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
 tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL) {
   tg_status st;
   const uint32_t rp_words = maxL / 16 + 4;
-  if (c->round_task_cap < (uint64_t)n * 3 + 4096) c->round_task_cap = (uint64_t)n * 3 + 4096;
-  if (c->round_ops_cap < (uint64_t)n * 12 + 65536) c->round_ops_cap = (uint64_t)n * 12 + 65536;
+  if (c->round_task_cap < (uint64_t)n * 4 + 65536) c->round_task_cap = (uint64_t)n * 4 + 65536;
+  if (c->round_ops_cap < (uint64_t)n * 16 + 65536) c->round_ops_cap = (uint64_t)n * 16 + 65536;
+  if (c->item_cap < (uint64_t)n * 3 + 65536) c->item_cap = (uint64_t)n * 3 + 65536;
+  if (c->hops_cap < (uint64_t)n * 64 + (1u << 20)) c->hops_cap = (uint64_t)n * 64 + (1u << 20);
+  if (c->item_cap > 0xFFFFFFF0ull) return tg_fail(TG_ERR_CAPACITY, "too many seed hits in one batch: split the batch");
   if ((st = c->r_state.ensure((size_t)n * sizeof(TgReadState))) != TG_OK) return st;
-  if ((st = c->r_hits.ensure((size_t)n * sizeof(TgHit))) != TG_OK) return st;
-  if ((st = c->r_acc.ensure((size_t)n * TG_ACC_MAX * sizeof(TgCand))) != TG_OK) return st;
-  if ((st = c->r_arena.ensure((size_t)n * TG_ARENA_WORDS * 4)) != TG_OK) return st;
+  if ((st = c->r_hits.ensure(c->item_cap * sizeof(TgHit))) != TG_OK) return st;
+  if ((st = c->r_ires.ensure(c->item_cap * sizeof(TgItemRes))) != TG_OK) return st;
+  if ((st = c->r_cands.ensure(c->item_cap * sizeof(TgCand))) != TG_OK) return st;
+  if ((st = c->r_hops.ensure(c->hops_cap * 4)) != TG_OK) return st;
+  if ((st = c->r_fin.ensure(c->item_cap * 12)) != TG_OK) return st;
   if ((st = c->r_rp.ensure((size_t)n * rp_words * 8)) != TG_OK) return st;
   if ((st = c->r_tasks.ensure(c->round_task_cap * sizeof(TgTask))) != TG_OK) return st;
   if ((st = c->r_ops.ensure(c->round_ops_cap * 4)) != TG_OK) return st;
@@ -860,9 +1086,12 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.bases = d_bases; p.offs = d_offs; p.n_reads = n; p.max_len = maxL; p.rp_words = rp_words;
   p.seeds = (const tg_seed*)c->d_seeds.p; p.read_seed_first = (const uint64_t*)c->d_seed_first.p;
   p.read_seed_count = (const uint32_t*)c->d_seed_count.p;
-  p.st = (TgReadState*)c->r_state.p; p.hits = (TgHit*)c->r_hits.p; p.acc = (TgCand*)c->r_acc.p;
-  p.arena = (uint32_t*)c->r_arena.p; p.rp = (uint64_t*)c->r_rp.p; p.tasks = (TgTask*)c->r_tasks.p;
-  p.task_cap = c->round_task_cap; p.ops_pool = (uint32_t*)c->r_ops.p; p.ops_cap = c->round_ops_cap;
+  p.st = (TgReadState*)c->r_state.p; p.rp = (uint64_t*)c->r_rp.p;
+  p.hits = (TgHit*)c->r_hits.p; p.ires = (TgItemRes*)c->r_ires.p; p.cands = (TgCand*)c->r_cands.p; p.item_cap = c->item_cap;
+  p.hp.w = (uint32_t*)c->r_hops.p; p.hp.used = &c->d_ctr->hops_used; p.hp.cap = c->hops_cap;
+  p.fin = (uint32_t*)c->r_fin.p; p.fin_cap = c->item_cap * 3;
+  p.tasks = (TgTask*)c->r_tasks.p; p.task_cap = c->round_task_cap;
+  p.ops_pool = (uint32_t*)c->r_ops.p; p.ops_cap = c->round_ops_cap;
   p.complex_list = (uint32_t*)c->r_complex.p; p.round = 0;
   p.max_xlen = max_xlen; p.max_cols = max_cols; p.trace_bytes = trace_bytes; p.ops_words = ops_words;
   p.bound_stop = c->exact_cells ? 0 : 1;
@@ -885,16 +1114,41 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   if (occ < 1) return tg_fail(TG_ERR_CAPACITY, "extension kernel does not fit in shared memory");
   const int dp_blocks = c->n_sms * occ;
   const int tblocks = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16);
+  const int iblocks = c->n_sms * 16;
+  // thread-per-extension kernel: geometry, trace scratch, sorted task list
+  int occ_t = 0;
+  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_round_dpt, 128, 0));
+  if (occ_t < 1) return tg_fail(TG_ERR_INTERNAL, "thread DP kernel does not fit");
+  const int dpt_blocks = c->n_sms * occ_t;
+  const uint32_t dpt_x = std::min<uint32_t>(max_xlen, TG_DPT_MAX_X);
+  const uint32_t dpt_rows = std::min<uint32_t>(std::min<uint32_t>(2 * max_bw, dpt_x) + 1, TG_DPT_MAX_WB);
+  const uint32_t dpt_wb = ((dpt_rows + 7) / 8) * 8;
+  p.dpt_trace_words = (size_t)(dpt_x + max_bw + 1) * ((2 * dpt_wb + 31) / 32) * 32;
+  if ((st = c->r_dpt_trace.ensure((size_t)dpt_blocks * 4 * p.dpt_trace_words * 4)) != TG_OK) return st;
+  if ((st = c->r_sorted.ensure(c->round_task_cap * 4)) != TG_OK) return st;
+  p.dpt_trace = (uint32_t*)c->r_dpt_trace.p;
+  p.sorted = (uint32_t*)c->r_sorted.p;
+  // tasks the thread kernel cannot take (long reads, very wide bands) exist only for such inputs
+  const bool need_warp_kernel = max_xlen > TG_DPT_MAX_X || std::min<uint32_t>(2 * max_bw, max_xlen) + 1 > TG_DPT_MAX_WB;
   k_round_init<<<tblocks, 128, 0, c->stream>>>(p);
+  c->n_launches++;
   for (uint32_t r = 0; r < TG_MAX_ROUNDS; r++) {
     p.round = r;
-    k_round_prep<<<tblocks, 128, 0, c->stream>>>(p);
-    kdp<<<dp_blocks, wpc * 32, smem, c->stream>>>(p);
-    k_round_post<<<tblocks, 128, 0, c->stream>>>(p);
+    k_round_plan<<<tblocks, 128, 0, c->stream>>>(p);
+    k_round_prep<<<iblocks, 128, 0, c->stream>>>(p);
+    k_round_hist<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
+    k_round_binscan<<<1, 1024, 0, c->stream>>>(p);
+    k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
+    k_round_dpt<<<dpt_blocks, 128, 0, c->stream>>>(p);
+    if (need_warp_kernel) { kdp<<<dp_blocks, wpc * 32, smem, c->stream>>>(p); c->n_launches++; }
+    k_round_post<<<iblocks, 128, 0, c->stream>>>(p);
+    k_round_scan<<<tblocks, 128, 0, c->stream>>>(p);
+    c->n_launches += 8;
   }
   k_round_final<<<tblocks, 128, 0, c->stream>>>(p);
+  c->n_launches++;
   CU_CHECK(cudaGetLastError());
-  // whatever the rounds could not finish (many hits / candidates / accepted alignments) runs on the single-warp path
+  // whatever the rounds could not finish (too many hits / transcripts per seed) runs on the single-warp path
   return launch_extend(c, d_bases, d_offs, n, maxL, (const uint32_t*)c->r_complex.p);
 }
 
@@ -915,6 +1169,7 @@ tg_status ensure_pools(tg_ctx* c, uint32_t n) {
 
 // seeds (+ optionally extension) with pool-overflow retry; leaves the counters in c->h_ctr
 tg_status run_pipeline(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL, bool extend) {
+  c->n_launches = 0;
   for (int attempt = 0; attempt < 8; attempt++) {
     tg_status st = ensure_pools(c, n);
     if (st != TG_OK) return st;
@@ -929,7 +1184,10 @@ tg_status run_pipeline(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs
     CU_CHECK(cudaEventElapsedTime(&c->last_seed_ms, c->ev0, c->ev1));
     CU_CHECK(cudaEventElapsedTime(&c->last_extend_ms, c->ev1, c->ev2));
     int f = c->h_ctr->flags;
-    if (f & (TG_FLAG_SEED_POOL | TG_FLAG_ALN_POOL | TG_FLAG_OPS_POOL)) {  // grow the pool that overflowed and redo the batch
+    if (f & (TG_FLAG_SEED_POOL | TG_FLAG_ALN_POOL | TG_FLAG_OPS_POOL | TG_FLAG_TASK_POOL | TG_FLAG_ITEM_POOL | TG_FLAG_HOPS_POOL)) {  // grow the pool that overflowed and redo the batch
+      if (f & TG_FLAG_TASK_POOL) c->round_task_cap *= 2;
+      if (f & TG_FLAG_ITEM_POOL) c->item_cap = std::max<uint64_t>(c->item_cap * 2, c->h_ctr->items_used + 65536);
+      if (f & TG_FLAG_HOPS_POOL) c->hops_cap = std::max<uint64_t>(c->hops_cap * 2, c->h_ctr->hops_used + 65536);
       if (f & TG_FLAG_SEED_POOL) c->seed_cap = std::max<uint64_t>(c->seed_cap * 2, c->h_ctr->seed_used + 4096);
       if (f & TG_FLAG_ALN_POOL) c->alns_cap = std::max<uint64_t>(c->alns_cap * 2, c->h_ctr->alns_used + 4096);
       if (f & TG_FLAG_OPS_POOL) {

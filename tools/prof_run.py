@@ -21,4 +21,10 @@ import ctypes as C
 from thermite_b200 import lib
 out = (C.c_uint64 * 16)()
 lib().tg_ctx_debug_phases(al._h, out)
-print("reads leaving the round path: hits>max", out[12], "prep overflow", out[13], "post overflow", out[14], "still active", out[15])
+print("reads leaving the round path: too many hits", out[12], "table overflow", out[13], "finaliser scratch", out[14], "still active", out[15])
+d = (C.c_uint64 * 52)()
+lib().tg_ctx_debug_rounds(al._h, d)
+print("items", d[0], "hops words", d[1], "complex reads", d[2], "fin words", d[3], "launches", al.last_kernel_launches())
+print("round_end  ", [int(d[4 + r]) for r in range(16)])
+print("round_tasks", [int(d[20 + r]) for r in range(16)])
+print("round_ops  ", [int(d[36 + r]) for r in range(16)])
