@@ -222,15 +222,16 @@ void dpt_one(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int bw, int x_d
 void dpt_dispatch(int cls, const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int bw, int x_drop, bool bound_stop,
                   TgDptResult& res, std::vector<uint32_t>& ops) {
   switch (cls) {
-    case 1: dpt_one<8>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
-    case 2: dpt_one<16>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
-    case 3: dpt_one<24>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
-    case 4: dpt_one<32>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
-    case 5: dpt_one<40>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
-    case 6: dpt_one<48>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
-    case 7: dpt_one<56>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
-    case 8: dpt_one<64>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
-    case 9: dpt_one<72>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 1: dpt_one<4>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 2: dpt_one<8>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 3: dpt_one<16>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 4: dpt_one<24>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 5: dpt_one<32>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 6: dpt_one<40>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 7: dpt_one<48>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 8: dpt_one<56>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 9: dpt_one<64>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 10: dpt_one<72>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
     default: dpt_one<80>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
   }
 }

@@ -26,9 +26,10 @@
 #define TG_DPT_MAX_X 128
 #define TG_DPT_MAX_WB 80
 #define TG_DPT_MIN (-(1 << 20))  // "minus infinity": far below any real score, far from overflowing the packed keys
-#define TG_DPT_NCLS 11           // class 0: not eligible; class c >= 1: WB = 8 * c
+#define TG_DPT_NCLS 12           // class 0: not eligible; class 1: WB = 4; class c >= 2: WB = 8 * (c - 1)
 
 TG_HD int tg_dpt_max(int a, int b) { return a > b ? a : b; }
+TG_HD int tg_dpt_min(int a, int b) { return a < b ? a : b; }
 TG_HD int tg_dpt_max3(int a, int b, int c) { return tg_dpt_max(tg_dpt_max(a, b), c); }
 
 // band-slot class of an extension (0 = not eligible for the thread kernel)
@@ -36,8 +37,11 @@ TG_HD int tg_dpt_class(int xlen, int bw, int x_drop) {
   if (xlen > TG_DPT_MAX_X || x_drop < bw) return 0;
   const int rows = (2 * bw < xlen ? 2 * bw : xlen) + 1;
   if (rows > TG_DPT_MAX_WB) return 0;
-  return (rows + 7) >> 3;
+  return rows <= 4 ? 1 : 1 + ((rows + 7) >> 3);
 }
+// slots of class `cls` and the smallest number of band rows an extension of that class has
+TG_HD constexpr int tg_dpt_wb(int cls) { return cls == 1 ? 4 : 8 * (cls - 1); }
+TG_HD constexpr int tg_dpt_min_rows(int wb) { return wb == 4 ? 1 : (wb == 8 ? 5 : wb - 7); }
 
 struct TgDptMem {
   uint32_t* msk;     // match profile: word (sym * 4 + k) at msk[(sym * 4 + k) * mstride], sym in 0..7
@@ -123,12 +127,34 @@ struct TgDptResult {
   uint32_t cells;
 };
 
+// One DP cell (src/swg.rs:82-99 / :121-140 + triple_max :226-240).  hC/hDm2: same row, previous column; diag: D - 2 of the
+// row above in the previous column; rr/dvm2: R and D - 2 of the row above in this column.  Updates the running column
+// state and returns the new D - 2.
+TG_HD int tg_dpt_cell(int hC, int hDm2, int diag, uint32_t match, int b, int& rr, int& dvm2, int& c_out, uint32_t& tbits,
+                      int& key, int& ubm) {
+  const int c = tg_dpt_max(hC - 1, hDm2);
+  const int r_ = tg_dpt_max(rr - 1, dvm2);
+  const int d = diag + (match ? 3 : 1);
+  const int nd = tg_dpt_max3(d, c, r_);
+  // direction: 0 when nd == d, else 1 when nd == c, else 2 (nd >= d and nd >= c, so the differences are >= 0)
+  const int f1 = tg_dpt_min(nd - d, 1), f2 = tg_dpt_min(nd - c, 1);
+  tbits += (uint32_t)(f1 + f1 * f2) << (2 * (b & 15));
+  c_out = c;
+  rr = r_;
+  dvm2 = nd - 2;
+  key = tg_dpt_max(key, nd * 128 + (127 - b));
+  ubm = tg_dpt_max(ubm, nd - b);
+  return nd - 2;
+}
+
 // Fill.  Returns through `res`; trace in m.tr.  ncols = min(ylen, xlen + bw) >= 1, xlen >= 1.
+// Band rows of the extension: min(2bw, xlen) + 1 in [tg_dpt_min_rows(WB), WB].
 template <int WB>
 TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int bw, int x_drop, bool bound_stop,
                         TgDptResult& res) {
   constexpr int TW = (2 * WB + 31) / 32;  // trace words per column
   constexpr int NW = (WB + 31) / 32;      // profile words per column
+  constexpr int LB = tg_dpt_min_rows(WB); // slots 0 .. LB-1 exist in every column whose band is not clipped by xlen
   int Dm2[WB + 1], C[WB + 1];             // previous column: D - 2 and C per slot (slot WB: permanent "out of band")
   const int two_bw = 2 * bw;
 #pragma unroll
@@ -140,10 +166,10 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
   int max_score = 0, max_i = 0, max_j = 0;
   uint32_t cells = 0;
   int j = 1;
+  bool stopped = false;
   // ---- phase 1: columns 1 .. min(bw, ncols), rows 0 .. min(2bw, xlen), slot = row ----------------------------------
   const int p1_cols = bw < ncols ? bw : ncols;
-  const int span1 = two_bw < xlen ? two_bw : xlen;
-  bool stopped = false;
+  const int span1 = two_bw < xlen ? two_bw : xlen;  // >= LB - 1
   for (; j <= p1_cols; j++) {
     if (((j - 1) & 15) == 0) ys.refill(j - 1);
     const uint32_t yc = ys.at(j - 1);
@@ -154,44 +180,32 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
     for (int k = 0; k < TW; k++) tb[k] = 0;
     // row 0: only the horizontal (deletion) branch exists (d = R = MIN), quirk Q1: C[0] starts at 0
     int diag = Dm2[0];
-    int c0 = tg_dpt_max(C[0] - 1, Dm2[0]);
+    const int c0 = tg_dpt_max(C[0] - 1, Dm2[0]);
     C[0] = c0; Dm2[0] = c0 - 2;
     tb[0] = 1u;
-    int key = c0 * 128 + 127;
-    int ubm = c0;
+    int key = c0 * 128 + 127, ubm = c0;
     int rr = TG_DPT_MIN, dvm2 = c0 - 2;
 #pragma unroll
     for (int b = 1; b < WB; b++) {
-      if (b <= span1) {
-        const int c = tg_dpt_max(C[b] - 1, Dm2[b]);
-        const int r_ = tg_dpt_max(rr - 1, dvm2);
-        const int d = diag + (((w[b >> 5] >> (b & 31)) & 1u) ? 3 : 1);
-        const int nd = tg_dpt_max3(d, c, r_);
-        const uint32_t dir = (nd != d) ? ((nd != c) ? 2u : 1u) : 0u;
-        tb[b >> 4] |= dir << (2 * (b & 15));
-        diag = Dm2[b];
-        C[b] = c; Dm2[b] = nd - 2;
-        rr = r_; dvm2 = nd - 2;
-        key = tg_dpt_max(key, nd * 128 + (127 - b));
-        ubm = tg_dpt_max(ubm, nd - b);
-      }
+      if (b >= LB && b > span1) break;
+      const int old = Dm2[b];
+      Dm2[b] = tg_dpt_cell(C[b], old, diag, (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
+      diag = old;
     }
 #pragma unroll
     for (int k = 0; k < TW; k++) m.tr[((size_t)(j - 1) * TW + k) * m.tstride] = tb[k];
     cells += (uint32_t)span1 + 1u;
     const int cm = key >> 7;
     if (cm > max_score) { max_score = cm; max_i = 127 - (key & 127); max_j = j; }
-    if (cm < max_score - x_drop || (bound_stop && ubm + xlen <= max_score)) { stopped = true; j++; break; }
+    if (cm < max_score - x_drop || (bound_stop && ubm + xlen <= max_score)) { stopped = true; break; }
   }
-  // ---- phase 2: columns bw+1 .. ncols, rows j-bw .. min(j+bw, xlen), slot = row - (j - bw) -------------------------
   if (!stopped) {
-    for (; j <= ncols; j++) {
+    // ---- phase 2, band not clipped: columns bw+1 .. min(ncols, xlen - bw), rows j-bw .. j+bw, slot = row - (j - bw)
+    const int full_cols = ncols < xlen - bw ? ncols : xlen - bw;
+    for (; j <= full_cols; j++) {
       if (((j - 1) & 15) == 0) ys.refill(j - 1);
       const uint32_t yc = ys.at(j - 1);
       const int lo = j - bw;
-      int hi = j + bw;
-      hi = hi < xlen ? hi : xlen;
-      const int span = hi - lo;  // >= 0 because j <= xlen + bw
       uint32_t w[NW];
       tg_dpt_window<NW>(m, yc, lo, w);
       uint32_t tb[TW];
@@ -201,18 +215,35 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
       int rr = TG_DPT_MIN, dvm2 = TG_DPT_MIN;
 #pragma unroll
       for (int b = 0; b < WB; b++) {
-        if (b <= span) {
-          const int c = tg_dpt_max(C[b + 1] - 1, Dm2[b + 1]);
-          const int r_ = tg_dpt_max(rr - 1, dvm2);
-          const int d = Dm2[b] + (((w[b >> 5] >> (b & 31)) & 1u) ? 3 : 1);
-          const int nd = tg_dpt_max3(d, c, r_);
-          const uint32_t dir = (nd != d) ? ((nd != c) ? 2u : 1u) : 0u;
-          tb[b >> 4] |= dir << (2 * (b & 15));
-          C[b] = c; Dm2[b] = nd - 2;
-          rr = r_; dvm2 = nd - 2;
-          key = tg_dpt_max(key, nd * 128 + (127 - b));
-          ubm = tg_dpt_max(ubm, nd - b);
-        }
+        if (b >= LB && b > two_bw) break;
+        Dm2[b] = tg_dpt_cell(C[b + 1], Dm2[b + 1], Dm2[b], (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
+      }
+#pragma unroll
+      for (int k = 0; k < TW; k++) m.tr[((size_t)(j - 1) * TW + k) * m.tstride] = tb[k];
+      cells += (uint32_t)two_bw + 1u;
+      const int cm = key >> 7;
+      if (cm > max_score) { max_score = cm; max_i = lo + 127 - (key & 127); max_j = j; }
+      if (cm < max_score - x_drop || (bound_stop && ubm - lo + xlen <= max_score)) { stopped = true; break; }
+    }
+  }
+  if (!stopped) {
+    // ---- phase 2, band clipped by the last row: rows j-bw .. xlen (fewer every column) ----------------------------------
+    for (; j <= ncols; j++) {
+      if (((j - 1) & 15) == 0) ys.refill(j - 1);
+      const uint32_t yc = ys.at(j - 1);
+      const int lo = j - bw;
+      const int span = xlen - lo;  // >= 0 because j <= xlen + bw
+      uint32_t w[NW];
+      tg_dpt_window<NW>(m, yc, lo, w);
+      uint32_t tb[TW];
+#pragma unroll
+      for (int k = 0; k < TW; k++) tb[k] = 0;
+      int key = TG_DPT_MIN * 128, ubm = TG_DPT_MIN;
+      int rr = TG_DPT_MIN, dvm2 = TG_DPT_MIN;
+#pragma unroll
+      for (int b = 0; b < WB; b++) {
+        if (b > span) break;
+        Dm2[b] = tg_dpt_cell(C[b + 1], Dm2[b + 1], Dm2[b], (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
       }
 #pragma unroll
       for (int k = 0; k < TW; k++) m.tr[((size_t)(j - 1) * TW + k) * m.tstride] = tb[k];

@@ -155,10 +155,11 @@ struct DevCounters {
   unsigned long long n_complex, work_complex;
   unsigned long long items_used, hops_used, fin_used;
   unsigned long long round_end[TG_MAX_ROUNDS];  // items_used after round r
-  unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS];
+  unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS][4];
   // task sorting for the thread-per-extension kernel: bins = class * TG_DPT_CBINS + column bucket
   uint32_t bin_count[TG_DPT_NBINS], bin_cursor[TG_DPT_NBINS];
   uint32_t cls_start[TG_DPT_NCLS + 1], cls_chunk0[TG_DPT_NCLS + 1];
+  uint32_t round_cls[TG_MAX_ROUNDS][TG_DPT_NCLS];  // debug: tasks per band class
 };
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -493,6 +494,7 @@ __global__ void __launch_bounds__(1024) k_round_binscan(RoundParams p) {
         acc += n;
       }
       if (c > 0) chunks += (acc - a0 + 31) / 32;
+      p.ctr->round_cls[p.round][c] = acc - a0;
     }
     p.ctr->cls_start[TG_DPT_NCLS] = acc;
     p.ctr->cls_chunk0[TG_DPT_NCLS] = chunks;
@@ -530,7 +532,7 @@ __global__ void __launch_bounds__(256) k_round_scatter(RoundParams p) {
 
 // ---- thread-per-extension kernel (tg_dpt.h) ----------------------------------------------------------------------------
 template <int WB>
-__device__ __noinline__ void dpt_task(const RoundParams& p, TgTask& t, bool active, const TgDptMem& m, int lane) {
+__device__ __forceinline__ void dpt_task(const RoundParams& p, TgTask& t, bool active, const TgDptMem& m, int lane) {
   TgDptResult res{0, 0, 0, 0};
   TgDptY ys;
   uint32_t n_ops = 0;
@@ -569,34 +571,47 @@ __device__ __noinline__ void dpt_task(const RoundParams& p, TgTask& t, bool acti
   }
 }
 
-__global__ void __launch_bounds__(128) k_round_dpt(RoundParams p) {
+// Four kernels, one per group of band classes, so that the narrow classes are not held to the register budget (and
+// occupancy) of the widest one.  Group g handles classes [GFIRST, GLAST].
+template <int G> struct DptGroup;
+template <> struct DptGroup<0> { static constexpr int first = 1, last = 3, min_blocks = 6; };    // WB 4, 8, 16
+template <> struct DptGroup<1> { static constexpr int first = 4, last = 5, min_blocks = 4; };    // WB 24, 32
+template <> struct DptGroup<2> { static constexpr int first = 6, last = 8, min_blocks = 3; };    // WB 40, 48, 56
+template <> struct DptGroup<3> { static constexpr int first = 9, last = 11, min_blocks = 2; };   // WB 64, 72, 80
+
+template <int G>
+__global__ void __launch_bounds__(128, DptGroup<G>::min_blocks) k_round_dpt(RoundParams p) {
   __shared__ uint32_t msk[32 * 128];
   const int lane = threadIdx.x & 31;
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   TgDptMem m;
   m.msk = msk + threadIdx.x; m.mstride = 128;
   m.tr = p.dpt_trace + (size_t)gw * p.dpt_trace_words + lane; m.tstride = 32;
-  const uint32_t n_chunks = p.ctr->cls_chunk0[TG_DPT_NCLS];
+  const uint32_t chunk0 = p.ctr->cls_chunk0[DptGroup<G>::first], chunk1 = p.ctr->cls_chunk0[DptGroup<G>::last + 1];
   for (;;) {
-    const uint32_t g = next_work(&p.ctr->round_work2[p.round]);
-    if (g >= n_chunks) break;
-    int cls = 1;
-    while (cls + 1 < TG_DPT_NCLS && g >= p.ctr->cls_chunk0[cls + 1]) cls++;
+    const uint32_t g = chunk0 + next_work(&p.ctr->round_work2[p.round][G]);
+    if (g >= chunk1) break;
+    int cls = DptGroup<G>::first;
+    while (cls < DptGroup<G>::last && g >= p.ctr->cls_chunk0[cls + 1]) cls++;
     const uint32_t first = p.ctr->cls_start[cls] + (g - p.ctr->cls_chunk0[cls]) * 32u;
     const uint32_t end = p.ctr->cls_start[cls + 1];
     const bool active = first + lane < end;
     TgTask& t = p.tasks[active ? p.sorted[first + lane] : p.sorted[first]];
-    switch (cls) {
-      case 1: dpt_task<8>(p, t, active, m, lane); break;
-      case 2: dpt_task<16>(p, t, active, m, lane); break;
-      case 3: dpt_task<24>(p, t, active, m, lane); break;
-      case 4: dpt_task<32>(p, t, active, m, lane); break;
-      case 5: dpt_task<40>(p, t, active, m, lane); break;
-      case 6: dpt_task<48>(p, t, active, m, lane); break;
-      case 7: dpt_task<56>(p, t, active, m, lane); break;
-      case 8: dpt_task<64>(p, t, active, m, lane); break;
-      case 9: dpt_task<72>(p, t, active, m, lane); break;
-      default: dpt_task<80>(p, t, active, m, lane); break;
+    if constexpr (G == 0) {
+      if (cls == 1) dpt_task<4>(p, t, active, m, lane);
+      else if (cls == 2) dpt_task<8>(p, t, active, m, lane);
+      else dpt_task<16>(p, t, active, m, lane);
+    } else if constexpr (G == 1) {
+      if (cls == 4) dpt_task<24>(p, t, active, m, lane);
+      else dpt_task<32>(p, t, active, m, lane);
+    } else if constexpr (G == 2) {
+      if (cls == 6) dpt_task<40>(p, t, active, m, lane);
+      else if (cls == 7) dpt_task<48>(p, t, active, m, lane);
+      else dpt_task<56>(p, t, active, m, lane);
+    } else {
+      if (cls == 9) dpt_task<64>(p, t, active, m, lane);
+      else if (cls == 10) dpt_task<72>(p, t, active, m, lane);
+      else dpt_task<80>(p, t, active, m, lane);
     }
     __syncwarp();
   }
@@ -978,6 +993,9 @@ void tg_ctx_debug_rounds(const tg_ctx* ctx, uint64_t* out52) {
     out52[4 + r] = h->round_end[r]; out52[4 + TG_MAX_ROUNDS + r] = h->round_tasks[r]; out52[4 + 2 * TG_MAX_ROUNDS + r] = h->round_ops[r];
   }
 }
+void tg_ctx_debug_classes(const tg_ctx* ctx, uint32_t* out) {  // [TG_MAX_ROUNDS][TG_DPT_NCLS]
+  memcpy(out, ctx->h_ctr->round_cls, sizeof(ctx->h_ctr->round_cls));
+}
 uint64_t tg_ctx_last_kernel_launches(const tg_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots * sizeof(TgSlot) : 0; }
 
@@ -1116,13 +1134,21 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   const int tblocks = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16);
   const int iblocks = c->n_sms * 16;
   // thread-per-extension kernel: geometry, trace scratch, sorted task list
-  int occ_t = 0;
-  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_round_dpt, 128, 0));
-  if (occ_t < 1) return tg_fail(TG_ERR_INTERNAL, "thread DP kernel does not fit");
-  const int dpt_blocks = c->n_sms * occ_t;
+  int dpt_grid[4];
+  int dpt_blocks = 0;
+  {
+    void (*ks[4])(RoundParams) = {k_round_dpt<0>, k_round_dpt<1>, k_round_dpt<2>, k_round_dpt<3>};
+    for (int g = 0; g < 4; g++) {
+      int o = 0;
+      CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ks[g], 128, 0));
+      if (o < 1) return tg_fail(TG_ERR_INTERNAL, "thread DP kernel does not fit");
+      dpt_grid[g] = c->n_sms * o;
+      dpt_blocks = std::max(dpt_blocks, dpt_grid[g]);
+    }
+  }
   const uint32_t dpt_x = std::min<uint32_t>(max_xlen, TG_DPT_MAX_X);
   const uint32_t dpt_rows = std::min<uint32_t>(std::min<uint32_t>(2 * max_bw, dpt_x) + 1, TG_DPT_MAX_WB);
-  const uint32_t dpt_wb = ((dpt_rows + 7) / 8) * 8;
+  const uint32_t dpt_wb = (uint32_t)tg_dpt_wb(dpt_rows <= 4 ? 1 : 1 + (int)((dpt_rows + 7) / 8));
   p.dpt_trace_words = (size_t)(dpt_x + max_bw + 1) * ((2 * dpt_wb + 31) / 32) * 32;
   if ((st = c->r_dpt_trace.ensure((size_t)dpt_blocks * 4 * p.dpt_trace_words * 4)) != TG_OK) return st;
   if ((st = c->r_sorted.ensure(c->round_task_cap * 4)) != TG_OK) return st;
@@ -1139,11 +1165,14 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
     k_round_hist<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
     k_round_binscan<<<1, 1024, 0, c->stream>>>(p);
     k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
-    k_round_dpt<<<dpt_blocks, 128, 0, c->stream>>>(p);
+    k_round_dpt<0><<<dpt_grid[0], 128, 0, c->stream>>>(p);
+    k_round_dpt<1><<<dpt_grid[1], 128, 0, c->stream>>>(p);
+    k_round_dpt<2><<<dpt_grid[2], 128, 0, c->stream>>>(p);
+    k_round_dpt<3><<<dpt_grid[3], 128, 0, c->stream>>>(p);
     if (need_warp_kernel) { kdp<<<dp_blocks, wpc * 32, smem, c->stream>>>(p); c->n_launches++; }
     k_round_post<<<iblocks, 128, 0, c->stream>>>(p);
     k_round_scan<<<tblocks, 128, 0, c->stream>>>(p);
-    c->n_launches += 8;
+    c->n_launches += 11;
   }
   k_round_final<<<tblocks, 128, 0, c->stream>>>(p);
   c->n_launches++;

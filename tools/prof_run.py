@@ -28,3 +28,7 @@ print("items", d[0], "hops words", d[1], "complex reads", d[2], "fin words", d[3
 print("round_end  ", [int(d[4 + r]) for r in range(16)])
 print("round_tasks", [int(d[20 + r]) for r in range(16)])
 print("round_ops  ", [int(d[36 + r]) for r in range(16)])
+cl = (C.c_uint32 * (16 * 12))()
+lib().tg_ctx_debug_classes(al._h, cl)
+for r in range(6):
+    print("round", r, "tasks per band class (0 = warp kernel, 1 -> WB 4, c -> WB 8(c-1)):", [int(cl[r * 12 + c]) for c in range(12)])
