@@ -209,7 +209,7 @@ void run_lanes(int lanes, F&& f) {
 struct DptScratch {
   std::vector<uint32_t> msk, tr;
   DptScratch() : msk(32, 0), tr((size_t)(TG_DPT_MAX_X + 2 * TG_MAX_READ_LEN + 2) * 5, 0) {}
-  TgDptMem mem() { return TgDptMem{msk.data(), 1, tr.data(), 1}; }
+  TgDptMem mem() { return TgDptMem{msk.data(), 1, tr.data(), 1, 1, 128}; }
 };
 template <int WB>
 void dpt_one(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int bw, int x_drop, bool bound_stop, TgDptResult& res,

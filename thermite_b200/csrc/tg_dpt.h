@@ -32,6 +32,17 @@ TG_HD int tg_dpt_max(int a, int b) { return a > b ? a : b; }
 TG_HD int tg_dpt_min(int a, int b) { return a < b ? a : b; }
 TG_HD int tg_dpt_max3(int a, int b, int c) { return tg_dpt_max(tg_dpt_max(a, b), c); }
 
+// a * b + c, forced onto the FMA pipe on the device (ptxas otherwise picks IADD3 / LEA on the busier ALU pipe)
+TG_HD int tg_dpt_mad(int a, int b, int c) {
+#ifdef __CUDA_ARCH__
+  int r;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+#else
+  return a * b + c;
+#endif
+}
+
 // band-slot class of an extension (0 = not eligible for the thread kernel)
 TG_HD int tg_dpt_class(int xlen, int bw, int x_drop) {
   if (xlen > TG_DPT_MAX_X || x_drop < bw) return 0;
@@ -48,6 +59,8 @@ struct TgDptMem {
   uint32_t mstride;
   uint32_t* tr;      // trace: word (col * TW + k) at tr[(col * TW + k) * tstride]
   uint32_t tstride;
+  int one, k128;     // the constants 1 and 128 as RUNTIME values (kernel parameters): multiply-adds by them cannot be
+                     // strength-reduced to IADD / LEA, so they issue on the FMA pipe instead of the saturated ALU pipe
 };
 
 // y symbols in extension order, 16 at a time (side 0: seq[y0 + t]; side 1: seq[y0 - 1 - t])
@@ -130,8 +143,8 @@ struct TgDptResult {
 // One DP cell (src/swg.rs:82-99 / :121-140 + triple_max :226-240).  hC/hDm2: same row, previous column; diag: D - 2 of the
 // row above in the previous column; rr/dvm2: R and D - 2 of the row above in this column.  Updates the running column
 // state and returns the new D - 2.
-TG_HD int tg_dpt_cell(int hC, int hDm2, int diag, uint32_t match, int b, int& rr, int& dvm2, int& c_out, uint32_t& tbits,
-                      int& key, int& ubm) {
+TG_HD int tg_dpt_cell(const TgDptMem& m, int hC, int hDm2, int diag, uint32_t match, int b, int& rr, int& dvm2, int& c_out,
+                      uint32_t& tbits, int& key, int& ubm) {
   const int c = tg_dpt_max(hC - 1, hDm2);
   const int r_ = tg_dpt_max(rr - 1, dvm2);
   const int d = diag + (match ? 3 : 1);
@@ -141,10 +154,12 @@ TG_HD int tg_dpt_cell(int hC, int hDm2, int diag, uint32_t match, int b, int& rr
   tbits += (uint32_t)(f1 + f1 * f2) << (2 * (b & 15));
   c_out = c;
   rr = r_;
-  dvm2 = nd - 2;
-  key = tg_dpt_max(key, nd * 128 + (127 - b));
+  // the integer ALU pipe is the bottleneck of this loop: plain additions go to the FMA pipe as multiply-adds
+  const int nm2 = tg_dpt_mad(nd, m.one, -2);
+  dvm2 = nm2;
+  key = tg_dpt_max(key, tg_dpt_mad(nd, m.k128, 127 - b));
   ubm = tg_dpt_max(ubm, nd - b);
-  return nd - 2;
+  return nm2;
 }
 
 // Fill.  Returns through `res`; trace in m.tr.  ncols = min(ylen, xlen + bw) >= 1, xlen >= 1.
@@ -189,7 +204,7 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
     for (int b = 1; b < WB; b++) {
       if (b >= LB && b > span1) break;
       const int old = Dm2[b];
-      Dm2[b] = tg_dpt_cell(C[b], old, diag, (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
+      Dm2[b] = tg_dpt_cell(m, C[b], old, diag, (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
       diag = old;
     }
 #pragma unroll
@@ -216,7 +231,7 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
 #pragma unroll
       for (int b = 0; b < WB; b++) {
         if (b >= LB && b > two_bw) break;
-        Dm2[b] = tg_dpt_cell(C[b + 1], Dm2[b + 1], Dm2[b], (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
+        Dm2[b] = tg_dpt_cell(m, C[b + 1], Dm2[b + 1], Dm2[b], (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
       }
 #pragma unroll
       for (int k = 0; k < TW; k++) m.tr[((size_t)(j - 1) * TW + k) * m.tstride] = tb[k];
@@ -243,7 +258,7 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
 #pragma unroll
       for (int b = 0; b < WB; b++) {
         if (b > span) break;
-        Dm2[b] = tg_dpt_cell(C[b + 1], Dm2[b + 1], Dm2[b], (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
+        Dm2[b] = tg_dpt_cell(m, C[b + 1], Dm2[b + 1], Dm2[b], (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
       }
 #pragma unroll
       for (int k = 0; k < TW; k++) m.tr[((size_t)(j - 1) * TW + k) * m.tstride] = tb[k];

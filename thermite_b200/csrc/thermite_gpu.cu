@@ -7,6 +7,8 @@
 //   k_swg_batch SwgExtend::extend, batched (src/swg.rs:31-207)                   INT-pipe bound
 // The algorithmic code lives in tg_core.h.  No CPU fallback exists: every entry point below needs a device.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -113,6 +115,18 @@ struct DevWarp {
   }
 };
 
+// Pool allocation from thread-per-item kernels: the threads of a warp that reach the call together combine their
+// requests into ONE atomicAdd (a million same-address atomics per kernel otherwise serialise in L2).
+__device__ __forceinline__ unsigned long long warp_agg_add(unsigned long long* ctr, unsigned long long n) {
+  namespace cg = cooperative_groups;
+  cg::coalesced_group g = cg::coalesced_threads();
+  const unsigned long long prefix = cg::exclusive_scan(g, n);
+  unsigned long long base = 0;
+  if (g.thread_rank() == g.size() - 1) base = atomicAdd(ctr, prefix + n);
+  base = g.shfl(base, g.size() - 1);
+  return base + prefix;
+}
+
 // One thread = one "warp" of a single lane: lets the thread-per-read round kernels reuse the templated code.
 struct DevThread {
   static constexpr int LANES = 1;
@@ -129,7 +143,7 @@ struct DevThread {
   TG_HD void sync_global() {}
   TG_HD unsigned long long atomic_add(unsigned long long* p, unsigned long long v) {
 #ifdef __CUDA_ARCH__
-    return atomicAdd(p, v);
+    return warp_agg_add(p, v);
 #else
     unsigned long long o = *p; *p += v; return o;
 #endif
@@ -143,7 +157,7 @@ struct DevThread {
   }
 };
 
-#define TG_DPT_CBINS 64
+#define TG_DPT_CBINS 512  // per class: 32 band-width bins x 16 column-count bins
 #define TG_DPT_NBINS (TG_DPT_NCLS * TG_DPT_CBINS)
 struct DevCounters {
   unsigned long long seed_used, n_smems, alns_used, ops_used, cells, n_ext, hits, work_seed, work_ext, swg_ops_used,
@@ -155,6 +169,7 @@ struct DevCounters {
   unsigned long long n_complex, work_complex;
   unsigned long long items_used, hops_used, fin_used;
   unsigned long long round_end[TG_MAX_ROUNDS];  // items_used after round r
+  unsigned long long round_active[TG_MAX_ROUNDS];  // reads still unfinished after round r
   unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS][4];
   // task sorting for the thread-per-extension kernel: bins = class * TG_DPT_CBINS + column bucket
   uint32_t bin_count[TG_DPT_NBINS], bin_cursor[TG_DPT_NBINS];
@@ -361,8 +376,9 @@ struct RoundParams {
   uint32_t* complex_list;
   uint32_t round;
   uint32_t* sorted;        // task indices of the round, grouped by class and (descending) column count
-  uint32_t* dpt_trace;     // thread kernel: [warp][col][word][lane]
-  size_t dpt_trace_words;  // per warp
+  uint32_t* dpt_trace;     // thread kernels: per class group, [warp][col][word][lane]
+  size_t dpt_trace_off[4], dpt_trace_words[4];  // region of each group, words per warp
+  int dpt_one, dpt_k128;   // 1 and 128 (see TgDptMem)
   uint32_t max_xlen, max_cols, trace_bytes, ops_words;
   int bound_stop;
   TgAlignOut out;
@@ -411,7 +427,7 @@ __global__ void __launch_bounds__(128) k_round_plan(RoundParams p) {
     if (p.st[r].status != TG_RS_ACTIVE) continue;
     TgReadState st = p.st[r];
     uint32_t b = tg_plan_batch(st, p.round);
-    const unsigned long long base = atomicAdd(&p.ctr->items_used, (unsigned long long)b);
+    const unsigned long long base = warp_agg_add(&p.ctr->items_used, (unsigned long long)b);
     if (base + b > p.item_cap) {
       atomicOr(&p.ctr->flags, TG_FLAG_ITEM_POOL);
       b = 0;
@@ -462,8 +478,10 @@ __device__ __forceinline__ uint32_t task_bin(const TgTask& t) {
   const int xlen = (int)t.xlen, bw = (int)t.bw, ylen = (int)t.ylen;
   const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
   const int cls = tg_dpt_class(xlen, bw, t.x_drop);
-  const int cb = (ncols < 255 ? ncols : 255) >> 2;
-  return (uint32_t)(cls * TG_DPT_CBINS + (TG_DPT_CBINS - 1 - cb));
+  // lanes of a warp should agree on the phase boundaries (bw) and on the number of columns: sort by both
+  const int bwb = bw < 16 ? bw : 16 + (bw - 16 < 60 ? (bw - 16) >> 2 : 15);
+  const int cb = (ncols < 255 ? ncols : 255) >> 4;
+  return (uint32_t)(cls * TG_DPT_CBINS + bwb * 16 + (15 - cb));
 }
 __global__ void __launch_bounds__(256) k_round_hist(RoundParams p) {
   __shared__ uint32_t h[TG_DPT_NBINS];
@@ -478,29 +496,48 @@ __global__ void __launch_bounds__(256) k_round_hist(RoundParams p) {
     if (h[i]) atomicAdd(&p.ctr->bin_count[i], h[i]);
 }
 // one block: exclusive scan of the bins; class ranges and warp-chunk table; clears the counts for the next round
-__global__ void __launch_bounds__(1024) k_round_binscan(RoundParams p) {
-  __shared__ uint32_t v[TG_DPT_NBINS + 1];
-  for (int i = threadIdx.x; i < TG_DPT_NBINS; i += blockDim.x) { v[i] = p.ctr->bin_count[i]; p.ctr->bin_count[i] = 0; }
+#define TG_BINSCAN_THREADS 768
+__global__ void __launch_bounds__(TG_BINSCAN_THREADS) k_round_binscan(RoundParams p) {
+  __shared__ uint32_t cls_n[TG_DPT_NCLS + 1];
+  __shared__ uint32_t cls_base[TG_DPT_NCLS + 1];
+  if (threadIdx.x <= TG_DPT_NCLS) cls_n[threadIdx.x] = 0;
+  __syncthreads();
+  // thread t owns the bins [t * PER, t * PER + PER) of one class (TG_DPT_CBINS is a multiple of PER)
+  constexpr int PER = TG_DPT_NBINS / TG_BINSCAN_THREADS;
+  static_assert(TG_DPT_NBINS % TG_BINSCAN_THREADS == 0 && TG_DPT_CBINS % PER == 0, "bin layout");
+  uint32_t v[PER], sum = 0;
+  const int b0 = threadIdx.x * PER, cls = b0 / TG_DPT_CBINS;
+#pragma unroll
+  for (int k = 0; k < PER; k++) { v[k] = p.ctr->bin_count[b0 + k]; p.ctr->bin_count[b0 + k] = 0; sum += v[k]; }
+  // exclusive scan of `sum` inside the class: warp scan + per-class atomics are overkill for <= 86 threads per class;
+  // a shared array and a serial pass over the threads of the class by its first thread is cheap enough
+  __shared__ uint32_t tsum[TG_BINSCAN_THREADS];
+  tsum[threadIdx.x] = sum;
+  __syncthreads();
+  constexpr int TPC = TG_DPT_CBINS / PER;  // threads per class
+  if (threadIdx.x % TPC == 0) {
+    uint32_t acc = 0;
+    for (int t = 0; t < TPC; t++) { const uint32_t x = tsum[threadIdx.x + t]; tsum[threadIdx.x + t] = acc; acc += x; }
+    cls_n[cls] = acc;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t acc = 0, chunks = 0;
     for (int c = 0; c < TG_DPT_NCLS; c++) {
+      cls_base[c] = acc;
       p.ctr->cls_start[c] = acc;
       p.ctr->cls_chunk0[c] = chunks;
-      const uint32_t a0 = acc;
-      for (int b = 0; b < TG_DPT_CBINS; b++) {
-        const uint32_t n = v[c * TG_DPT_CBINS + b];
-        v[c * TG_DPT_CBINS + b] = acc;
-        acc += n;
-      }
-      if (c > 0) chunks += (acc - a0 + 31) / 32;
-      p.ctr->round_cls[p.round][c] = acc - a0;
+      p.ctr->round_cls[p.round][c] = cls_n[c];
+      acc += cls_n[c];
+      if (c > 0) chunks += (cls_n[c] + 31) / 32;
     }
     p.ctr->cls_start[TG_DPT_NCLS] = acc;
     p.ctr->cls_chunk0[TG_DPT_NCLS] = chunks;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < TG_DPT_NBINS; i += blockDim.x) p.ctr->bin_cursor[i] = v[i];
+  uint32_t acc = cls_base[cls] + tsum[threadIdx.x];
+#pragma unroll
+  for (int k = 0; k < PER; k++) { p.ctr->bin_cursor[b0 + k] = acc; acc += v[k]; }
 }
 __global__ void __launch_bounds__(256) k_round_scatter(RoundParams p) {
   __shared__ uint32_t h[TG_DPT_NBINS];
@@ -586,7 +623,8 @@ __global__ void __launch_bounds__(128, DptGroup<G>::min_blocks) k_round_dpt(Roun
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   TgDptMem m;
   m.msk = msk + threadIdx.x; m.mstride = 128;
-  m.tr = p.dpt_trace + (size_t)gw * p.dpt_trace_words + lane; m.tstride = 32;
+  m.tr = p.dpt_trace + p.dpt_trace_off[G] + (size_t)gw * p.dpt_trace_words[G] + lane; m.tstride = 32;
+  m.one = p.dpt_one; m.k128 = p.dpt_k128;
   const uint32_t chunk0 = p.ctr->cls_chunk0[DptGroup<G>::first], chunk1 = p.ctr->cls_chunk0[DptGroup<G>::last + 1];
   for (;;) {
     const uint32_t g = chunk0 + next_work(&p.ctr->round_work2[p.round][G]);
@@ -636,6 +674,7 @@ __global__ void __launch_bounds__(128) k_round_scan(RoundParams p) {
     if (st.batch_n == 0) continue;
     if (!tg_scan_read(p.P.opts, st, p.ires)) { mark_complex(p, r, 1); continue; }
     p.st[r] = st;
+    if (st.status == TG_RS_ACTIVE) warp_agg_add(&p.ctr->round_active[p.round], 1ull);
   }
 }
 
@@ -652,7 +691,7 @@ __global__ void __launch_bounds__(128) k_round_final(RoundParams p) {
       uint16_t order[TG_FINAL_SMALL], tmp[TG_FINAL_SMALL];
       tg_round_final<DevThread, uint16_t>(w, p.P, st, p.cands, p.ires, p.hp.w, items, order, tmp, p.out, r);
     } else {
-      const unsigned long long base = atomicAdd(&p.ctr->fin_used, 3ull * st.n_acc);
+      const unsigned long long base = warp_agg_add(&p.ctr->fin_used, 3ull * st.n_acc);
       if (base + 3ull * st.n_acc > p.fin_cap) { mark_complex(p, r, 2); continue; }
       uint32_t* f = p.fin + base;
       tg_round_final<DevThread, uint32_t>(w, p.P, st, p.cands, p.ires, p.hp.w, f, f + st.n_acc, f + 2 * (size_t)st.n_acc, p.out, r);
@@ -788,6 +827,9 @@ struct tg_ctx {
   tg_opts opts;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the band-class groups of a round's DP run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  unsigned long long* h_active = nullptr;  // pinned
   float last_seed_ms = 0.f, last_extend_ms = 0.f;
   int exact_cells = 0;  // 1: run every column the reference runs (swg_cells == reference count)
   int n_sms = 0;
@@ -920,6 +962,9 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int i = 0; i < 3; i++) { if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); if (c->side[i]) cudaStreamDestroy(c->side[i]); }
+  if (c->h_active) cudaFreeHost(c->h_active);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -944,6 +989,12 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
   CTX_CHECK(cudaEventCreate(&c->ev0));
   CTX_CHECK(cudaEventCreate(&c->ev1));
   CTX_CHECK(cudaEventCreate(&c->ev2));
+  CTX_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 3; i++) {
+    CTX_CHECK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    CTX_CHECK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+  }
+  CTX_CHECK(cudaMallocHost(&c->h_active, sizeof(unsigned long long)));
   CTX_CHECK(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, ix->device));
   CTX_CHECK(cudaMalloc(&c->d_ctr, sizeof(DevCounters)));
   CTX_CHECK(cudaMallocHost(&c->h_ctr, sizeof(DevCounters)));
@@ -990,7 +1041,7 @@ void tg_ctx_debug_rounds(const tg_ctx* ctx, uint64_t* out52) {
   const DevCounters* h = ctx->h_ctr;
   out52[0] = h->items_used; out52[1] = h->hops_used; out52[2] = h->n_complex; out52[3] = h->fin_used;
   for (int r = 0; r < TG_MAX_ROUNDS; r++) {
-    out52[4 + r] = h->round_end[r]; out52[4 + TG_MAX_ROUNDS + r] = h->round_tasks[r]; out52[4 + 2 * TG_MAX_ROUNDS + r] = h->round_ops[r];
+    out52[4 + r] = h->round_active[r]; out52[4 + TG_MAX_ROUNDS + r] = h->round_tasks[r]; out52[4 + 2 * TG_MAX_ROUNDS + r] = h->round_ops[r];
   }
 }
 void tg_ctx_debug_classes(const tg_ctx* ctx, uint32_t* out) {  // [TG_MAX_ROUNDS][TG_DPT_NCLS]
@@ -1147,12 +1198,19 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
     }
   }
   const uint32_t dpt_x = std::min<uint32_t>(max_xlen, TG_DPT_MAX_X);
-  const uint32_t dpt_rows = std::min<uint32_t>(std::min<uint32_t>(2 * max_bw, dpt_x) + 1, TG_DPT_MAX_WB);
-  const uint32_t dpt_wb = (uint32_t)tg_dpt_wb(dpt_rows <= 4 ? 1 : 1 + (int)((dpt_rows + 7) / 8));
-  p.dpt_trace_words = (size_t)(dpt_x + max_bw + 1) * ((2 * dpt_wb + 31) / 32) * 32;
-  if ((st = c->r_dpt_trace.ensure((size_t)dpt_blocks * 4 * p.dpt_trace_words * 4)) != TG_OK) return st;
+  {
+    const int group_wb[4] = {16, 32, 56, 80};  // widest class of each group
+    size_t off = 0;
+    for (int g = 0; g < 4; g++) {
+      p.dpt_trace_off[g] = off;
+      p.dpt_trace_words[g] = (size_t)(dpt_x + max_bw + 1) * ((2 * group_wb[g] + 31) / 32) * 32;
+      off += (size_t)dpt_grid[g] * 4 * p.dpt_trace_words[g];
+    }
+    if ((st = c->r_dpt_trace.ensure(off * 4)) != TG_OK) return st;
+  }
   if ((st = c->r_sorted.ensure(c->round_task_cap * 4)) != TG_OK) return st;
   p.dpt_trace = (uint32_t*)c->r_dpt_trace.p;
+  p.dpt_one = 1; p.dpt_k128 = 128;
   p.sorted = (uint32_t*)c->r_sorted.p;
   // tasks the thread kernel cannot take (long reads, very wide bands) exist only for such inputs
   const bool need_warp_kernel = max_xlen > TG_DPT_MAX_X || std::min<uint32_t>(2 * max_bw, max_xlen) + 1 > TG_DPT_MAX_WB;
@@ -1163,16 +1221,29 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
     k_round_plan<<<tblocks, 128, 0, c->stream>>>(p);
     k_round_prep<<<iblocks, 128, 0, c->stream>>>(p);
     k_round_hist<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
-    k_round_binscan<<<1, 1024, 0, c->stream>>>(p);
+    k_round_binscan<<<1, TG_BINSCAN_THREADS, 0, c->stream>>>(p);
     k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
+    // the four class groups (widest first: longest tasks) on their own streams, joined before `post`
+    CU_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+    for (int i = 0; i < 3; i++) CU_CHECK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+    k_round_dpt<3><<<dpt_grid[3], 128, 0, c->side[0]>>>(p);
+    k_round_dpt<2><<<dpt_grid[2], 128, 0, c->side[1]>>>(p);
+    k_round_dpt<1><<<dpt_grid[1], 128, 0, c->side[2]>>>(p);
     k_round_dpt<0><<<dpt_grid[0], 128, 0, c->stream>>>(p);
-    k_round_dpt<1><<<dpt_grid[1], 128, 0, c->stream>>>(p);
-    k_round_dpt<2><<<dpt_grid[2], 128, 0, c->stream>>>(p);
-    k_round_dpt<3><<<dpt_grid[3], 128, 0, c->stream>>>(p);
     if (need_warp_kernel) { kdp<<<dp_blocks, wpc * 32, smem, c->stream>>>(p); c->n_launches++; }
+    for (int i = 0; i < 3; i++) {
+      CU_CHECK(cudaEventRecord(c->ev_join[i], c->side[i]));
+      CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+    }
     k_round_post<<<iblocks, 128, 0, c->stream>>>(p);
     k_round_scan<<<tblocks, 128, 0, c->stream>>>(p);
     c->n_launches += 11;
+    // late rounds are short: a host check for "nothing left" costs less than launching the remaining empty rounds
+    if (r >= 3 && r + 1 < TG_MAX_ROUNDS) {
+      CU_CHECK(cudaMemcpyAsync(c->h_active, &c->d_ctr->round_active[r], sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      CU_CHECK(cudaStreamSynchronize(c->stream));
+      if (*c->h_active == 0) break;
+    }
   }
   k_round_final<<<tblocks, 128, 0, c->stream>>>(p);
   c->n_launches++;

@@ -25,7 +25,7 @@ print("reads leaving the round path: too many hits", out[12], "table overflow", 
 d = (C.c_uint64 * 52)()
 lib().tg_ctx_debug_rounds(al._h, d)
 print("items", d[0], "hops words", d[1], "complex reads", d[2], "fin words", d[3], "launches", al.last_kernel_launches())
-print("round_end  ", [int(d[4 + r]) for r in range(16)])
+print("round_active", [int(d[4 + r]) for r in range(16)])
 print("round_tasks", [int(d[20 + r]) for r in range(16)])
 print("round_ops  ", [int(d[36 + r]) for r in range(16)])
 cl = (C.c_uint32 * (16 * 12))()
