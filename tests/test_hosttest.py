@@ -52,10 +52,13 @@ def test_align_records_equal_oracle_random_worlds(seed):
     hix, oix = ht.HostIndex(fa, gtf), orc.Index.create(fa, gtf)
     ctx = ht.HostCtx(hix, k=k, pct=pct, min_score=mins, score_range=srange, intron_mode=intron)
     pool, first, count = ctx.seed_batch(bases, offs)
+    pool0, first0, count0 = ctx.seed_batch(bases, offs, lanes=0)  # the device's pack / probe / select pipeline
     sa = hix.sa()
     for r in range(0, n, 5):
         rd = bases[int(offs[r]): int(offs[r + 1])].tobytes()
-        assert ht.expand_seeds(pool, first, count, sa, r) == oix.all_smems(rd, k)
+        want = oix.all_smems(rd, k)
+        assert ht.expand_seeds(pool, first, count, sa, r) == want
+        assert ht.expand_seeds(pool0, first0, count0, sa, r) == want
     res = ctx.align_batch(bases, offs, lanes=1)
     oix.counters_reset()
     ores = oix.align_batch(bases, offs, k=k, pct=pct, min_score=mins, score_range=srange, intron_mode=intron)

@@ -302,6 +302,30 @@ long long ht_seed_batch(void* cp, const uint8_t* bases, const uint64_t* offs, ui
   TgSeedOut out{pool, &used, pool_cap, read_first, read_count, &flags, &n_smems};
   for (uint32_t r = 0; r < n; r++) {
     uint32_t L = (uint32_t)(offs[r + 1] - offs[r]);
+    if (lanes == 0) {
+      // the device pipeline: k_pack_reads -> k_seed_probe (offset 0 first, the rest unless the whole read matched) -> k_seed_select
+      const uint32_t k = c->opts.min_seed_len, max_q = maxL >= k ? maxL - k + 1 : 1;
+      std::vector<uint64_t> rp(maxL / 16 + 4);
+      for (uint32_t wi = 0; wi < rp.size(); wi++) rp[wi] = wi < L / 16 + 3 ? tg_pack_word(bases, offs[r], L, wi) : ~0ull;
+      std::vector<TgSeedHit> hits(max_q, TgSeedHit{0xDEADu, 0xDEADu, 0xDEADu});  // poison: skipped offsets must never be read
+      if (L >= k) {
+        const uint32_t q_last = L - k;
+        tg_seed_offset(rp.data(), L, 0, k, c->slots.data(), c->slot_mask, c->dev.text4, c->dev.sa, hits[0]);  // wave 0
+        if (hits[0].e != L) {
+          for (uint32_t j = 0; j < (max_q + TG_PROBE_STRIDE - 1) / TG_PROBE_STRIDE; j++) {  // wave 1
+            const uint32_t q = tg_probe_sample(j, q_last);
+            if (q != 0xFFFFFFFFu) tg_seed_offset(rp.data(), L, q, k, c->slots.data(), c->slot_mask, c->dev.text4, c->dev.sa, hits[q]);
+          }
+          for (uint32_t q = 1; q <= q_last; q++) {  // wave 2
+            if (tg_probe_is_sample(q, q_last) || tg_probe_bracketed(hits.data(), q, q_last)) continue;
+            tg_seed_offset(rp.data(), L, q, k, c->slots.data(), c->slot_mask, c->dev.text4, c->dev.sa, hits[q]);
+          }
+        }
+      }
+      HostWarp1 w1;
+      tg_seed_select_read(w1, hits.data(), L, k, out, r);
+      continue;
+    }
     run_lanes(lanes, [&](auto& w) {
       tg_seed_read(w, sm, bases, offs[r], L, c->opts.min_seed_len, c->slots.data(), c->slot_mask, c->dev.text4,
                    c->dev.sa, out, r);

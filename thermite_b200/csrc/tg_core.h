@@ -129,6 +129,27 @@ struct TgSeedHit {
   uint32_t cnt;  // number of occurrences | TG_DIRECT
 };
 
+// lcp of read[q..L) and seq[pos..) given that the first `known` symbols are equal
+TG_HD uint32_t tg_lcp_from(const uint64_t* rp, uint32_t q, uint32_t L, const uint64_t* seq, uint64_t pos, uint32_t known,
+                           bool* read_le) {
+  uint32_t maxl = L - q, off = known & ~15u;  // restart at the packed word that holds symbol `known`
+  while (off < maxl) {
+    uint64_t a = tg_ld16_local(rp, q + off), b = tg_ld16(seq, pos + off);
+    uint64_t x = a ^ b;
+    if (x) {
+      uint32_t nb = (uint32_t)TG_CLZ64(x) >> 2;
+      uint32_t l = off + nb;
+      if (l >= maxl) { *read_le = true; return maxl; }
+      uint32_t sh = (15 - nb) * 4;
+      *read_le = ((a >> sh) & 15) < ((b >> sh) & 15);
+      return l;
+    }
+    off += 16;
+  }
+  *read_le = true;
+  return maxl;
+}
+
 TG_HD void tg_seed_offset(const uint64_t* rp, uint32_t L, uint32_t q, uint32_t k, const TgSlot* slots,
                           uint64_t slot_mask, const uint64_t* text4, const uint32_t* sa, TgSeedHit& out) {
   out.e = 0; out.lo = 0; out.cnt = 0;
@@ -152,38 +173,64 @@ TG_HD void tg_seed_offset(const uint64_t* rp, uint32_t L, uint32_t q, uint32_t k
         uint32_t l = tg_lcp(rp, q, L, text4, s.lo, &le);
         if (l >= k) { out.e = q + l; out.lo = s.lo; out.cnt = 1u | TG_DIRECT; return; }
       } else {
-        // first row whose suffix is >= the read suffix
-        uint32_t a = s.lo, b = s.lo + s.count;
-        bool ok = true;
-        while (a < b) {
-          uint32_t mid = a + ((b - a) >> 1);
-          uint32_t l = tg_lcp(rp, q, L, text4, TG_LDG(sa + mid), &le);
-          if (l < k) { ok = false; break; }  // tag collision: a different k-mer
-          if (le) b = mid; else a = mid + 1;
-        }
-        if (ok) {
-          uint32_t ins = a, hi = s.lo + s.count, best = 0;
-          uint32_t l_ins = 0, l_prev = 0;
-          if (ins < hi) l_ins = tg_lcp(rp, q, L, text4, TG_LDG(sa + ins), &le);
-          if (ins > s.lo) l_prev = tg_lcp(rp, q, L, text4, TG_LDG(sa + ins - 1), &le);
-          best = l_ins > l_prev ? l_ins : l_prev;
-          // rows with lcp >= best form one contiguous range around ins
-          uint32_t left = ins, right = ins;  // [left, right)
-          if (l_prev >= best) {              // lcp is non-decreasing on [s.lo, ins)
-            uint32_t x = s.lo, y = ins - 1;  // find the first row in [x, y] with lcp >= best
-            while (x < y) {
-              uint32_t mid = x + ((y - x) >> 1);
-              if (tg_lcp(rp, q, L, text4, TG_LDG(sa + mid), &le) >= best) y = mid; else x = mid + 1;
+        // All rows of the group share their first k symbols; one row tells whether they are the read's k-mer (a tag
+        // collision is a different k-mer).  Then: first row whose suffix is >= the read suffix, by binary search that
+        // only compares beyond the prefix both current bounds are known to share with the read.
+        const uint32_t lo = s.lo, hi = s.lo + s.count;
+        uint32_t a = lo, b = hi;
+        uint32_t la = tg_lcp(rp, q, L, text4, TG_LDG(sa + lo), &le);  // lcp with row lo
+        if (la >= k) {
+          uint32_t lb = k;  // lcp with the (virtual) bound b: at least the k-mer
+          uint32_t l_ins = 0, l_prev = 0;  // lcp of the row at / before the insertion point
+          if (le) { b = lo; l_ins = la; }  // the read sorts before (or equals a prefix of) the first row
+          else {
+            a = lo + 1; l_prev = la;
+            while (a < b) {
+              const uint32_t mid = a + ((b - a) >> 1);
+              const uint32_t known = la < lb ? la : lb;
+              const uint32_t l = tg_lcp_from(rp, q, L, text4, TG_LDG(sa + mid), known, &le);
+              if (le) { b = mid; lb = l; l_ins = l; } else { a = mid + 1; la = l; l_prev = l; }
             }
-            left = x;
+          }
+          const uint32_t ins = a;
+          if (ins >= hi) l_ins = 0;
+          const uint32_t best = l_ins > l_prev ? l_ins : l_prev;
+          // rows with lcp >= best form one contiguous range around ins; it is usually a single row, so gallop outwards
+          uint32_t left = ins, right = ins;  // [left, right)
+          if (l_prev >= best && ins > lo) {  // lcp is non-decreasing on [lo, ins)
+            left = ins - 1;
+            uint32_t step = 1;
+            uint32_t known_ok = left;  // row known to have lcp >= best
+            for (;;) {  // find a row with lcp < best (or run out), doubling the step
+              if (known_ok == lo) { left = lo; break; }
+              const uint32_t probe = known_ok - lo > step ? known_ok - step : lo;
+              if (tg_lcp_from(rp, q, L, text4, TG_LDG(sa + probe), k, &le) >= best) { known_ok = probe; step <<= 1; continue; }
+              // first row in (probe, known_ok] with lcp >= best
+              uint32_t x = probe + 1, y = known_ok;
+              while (x < y) {
+                const uint32_t mid = x + ((y - x) >> 1);
+                if (tg_lcp_from(rp, q, L, text4, TG_LDG(sa + mid), k, &le) >= best) y = mid; else x = mid + 1;
+              }
+              left = x;
+              break;
+            }
           }
           if (l_ins >= best && ins < hi) {   // lcp is non-increasing on [ins, hi)
-            uint32_t x = ins, y = hi - 1;    // find the last row in [x, y] with lcp >= best
-            while (x < y) {
-              uint32_t mid = x + ((y - x + 1) >> 1);
-              if (tg_lcp(rp, q, L, text4, TG_LDG(sa + mid), &le) >= best) x = mid; else y = mid - 1;
+            uint32_t step = 1;
+            uint32_t known_ok = ins;
+            for (;;) {
+              if (known_ok == hi - 1) { right = hi; break; }
+              const uint32_t probe = hi - 1 - known_ok > step ? known_ok + step : hi - 1;
+              if (tg_lcp_from(rp, q, L, text4, TG_LDG(sa + probe), k, &le) >= best) { known_ok = probe; step <<= 1; continue; }
+              // last row in [known_ok, probe) with lcp >= best
+              uint32_t x = known_ok, y = probe - 1;
+              while (x < y) {
+                const uint32_t mid = x + ((y - x + 1) >> 1);
+                if (tg_lcp_from(rp, q, L, text4, TG_LDG(sa + mid), k, &le) >= best) x = mid; else y = mid - 1;
+              }
+              right = x + 1;
+              break;
             }
-            right = x + 1;
           }
           out.e = q + best; out.lo = left; out.cnt = right - left;
           return;
@@ -195,20 +242,34 @@ TG_HD void tg_seed_offset(const uint64_t* rp, uint32_t L, uint32_t q, uint32_t k
 }
 
 // Serial part of seeding: pick the SMEM starts from E[], order them as Index::all_smems does and write the
-// records.  hits[q] valid for q + k <= L.  Returns the number of SMEMs (<= L - k + 1).
+// records.  hits[q] valid for q + k <= L.
 // Order: bio emits, for i0 = 0, max-end, ...: the SMEMs covering i0 by DESCENDING start; then
 // src/index.rs:251-253 stable-sorts by len ascending and reverses => len DESC, ties in REVERSE emission order.
-TG_HD uint32_t tg_smem_select(const TgSeedHit* hits, uint32_t L, uint32_t k, tg_seed* out, uint16_t* grp_scratch) {
+TG_HD uint32_t tg_smem_count(const TgSeedHit* hits, uint32_t L, uint32_t k) {  // number of SMEMs (<= L - k + 1)
   if (L < k || k == 0) return 0;
   uint32_t n = 0, prev_e = 0;
   for (uint32_t q = 0; q + k <= L; q++) {
-    uint32_t e = hits[q].e;
+    const uint32_t e = hits[q].e;
+    if (e != 0 && (q == 0 || prev_e < e)) n++;
+    prev_e = e;
+    if (e == L) break;  // E is non-decreasing: every later offset ends at L too and starts no SMEM
+  }
+  return n;
+}
+// out: room for tg_smem_count() records; the `pad` field is used as scratch (emission group) and left 0
+TG_HD uint32_t tg_smem_select(const TgSeedHit* hits, uint32_t L, uint32_t k, tg_seed* out) {
+  if (L < k || k == 0) return 0;
+  uint32_t n = 0, prev_e = 0;
+  for (uint32_t q = 0; q + k <= L; q++) {
+    const TgSeedHit h = hits[q];
+    const uint32_t e = h.e;
     if (e != 0 && (q == 0 || prev_e < e)) {
-      out[n].query_idx = q; out[n].len = e - q; out[n].sa_lo = hits[q].lo;
-      out[n].count = hits[q].cnt & ~TG_DIRECT; out[n].direct = (hits[q].cnt & TG_DIRECT) ? 1u : 0u; out[n].pad = 0;
+      out[n].query_idx = q; out[n].len = e - q; out[n].sa_lo = h.lo;
+      out[n].count = h.cnt & ~TG_DIRECT; out[n].direct = (h.cnt & TG_DIRECT) ? 1u : 0u; out[n].pad = 0;
       n++;
     }
     prev_e = e;
+    if (e == L) break;
   }
   // emission groups
   uint32_t i0 = 0, idx = 0, g = 0;
@@ -216,7 +277,7 @@ TG_HD uint32_t tg_smem_select(const TgSeedHit* hits, uint32_t L, uint32_t k, tg_
     if (out[idx].query_idx > i0) i0 = out[idx].query_idx;
     uint32_t maxend = i0 + 1;
     while (idx < n && out[idx].query_idx <= i0) {
-      grp_scratch[idx] = (uint16_t)g;
+      out[idx].pad = g;
       uint32_t e = out[idx].query_idx + out[idx].len;
       if (e > maxend) maxend = e;
       idx++;
@@ -226,21 +287,18 @@ TG_HD uint32_t tg_smem_select(const TgSeedHit* hits, uint32_t L, uint32_t k, tg_
   }
   // insertion sort by (len DESC, group DESC, start ASC)
   for (uint32_t i = 1; i < n; i++) {
-    tg_seed cur = out[i];
-    uint16_t cg = grp_scratch[i];
+    const tg_seed cur = out[i];
     uint32_t j = i;
     while (j > 0) {
-      const tg_seed& p = out[j - 1];
-      uint16_t pg = grp_scratch[j - 1];
-      bool p_before = p.len > cur.len || (p.len == cur.len && (pg > cg || (pg == cg && p.query_idx < cur.query_idx)));
+      const tg_seed p = out[j - 1];
+      bool p_before = p.len > cur.len || (p.len == cur.len && (p.pad > cur.pad || (p.pad == cur.pad && p.query_idx < cur.query_idx)));
       if (p_before) break;
-      out[j] = out[j - 1];
-      grp_scratch[j] = grp_scratch[j - 1];
+      out[j] = p;
       j--;
     }
     out[j] = cur;
-    grp_scratch[j] = cg;
   }
+  for (uint32_t i = 0; i < n; i++) out[i].pad = 0;
   return n;
 }
 
@@ -1225,7 +1283,7 @@ TG_HDN void tg_seed_read(W& w, TgSeedMem& m, const uint8_t* bases, uint64_t off,
   }
   w.sync();
   int n = 0;
-  if (lane == 0) n = (int)tg_smem_select(m.hits, L, k, m.sm, m.grp);
+  if (lane == 0) n = (int)tg_smem_select(m.hits, L, k, m.sm);
   n = w.shfl(n, 0);
   unsigned long long base = 0;
   if (lane == 0 && n > 0) base = w.atomic_add(out.pool_used, (unsigned long long)n);
@@ -1242,6 +1300,59 @@ TG_HDN void tg_seed_read(W& w, TgSeedMem& m, const uint8_t* bases, uint64_t off,
     if (n > 0) w.atomic_add(out.n_smems, (unsigned long long)n);
   }
   w.sync();
+}
+
+// ---- thread-per-offset seeding (the device pipeline): pack -> probe -> select --------------------------------------------
+// One packed word (16 symbols) of a read; positions >= L are padding.
+TG_HD uint64_t tg_pack_word(const uint8_t* bases, uint64_t off, uint32_t L, uint32_t wi) {
+  uint64_t word = 0;
+  for (uint32_t t = 0; t < 16; t++) {
+    const uint32_t p = wi * 16 + t;
+    const uint64_t c = p < L ? tg_ascii_code(TG_LDG(bases + off + p)) : (uint64_t)TG_C_PAD;
+    word |= c << ((15 - t) * 4);
+  }
+  return word;
+}
+// Probe schedule.  E(q) is non-decreasing in q, so two probed offsets qa < qb with the same end E(qa) == E(qb) != 0 pin
+// E(q) = E(qa) for every q between them, and none of those q starts an SMEM: they need no table probe at all.
+//   wave 0: q = 0.  If the whole read matches (E(0) == L) nothing else is probed.
+//   wave 1: the sample offsets S, 2S, ... and the last offset L - k.
+//   wave 2: every other offset, probed only when its two bracketing samples disagree (or found nothing).
+#define TG_PROBE_STRIDE 8u
+TG_HD bool tg_probe_is_sample(uint32_t q, uint32_t q_last) { return q % TG_PROBE_STRIDE == 0 || q == q_last; }
+// the j-th wave-1 offset of a read whose last offset is q_last (0xFFFFFFFF: none)
+TG_HD uint32_t tg_probe_sample(uint32_t j, uint32_t q_last) {
+  const uint32_t q = (j + 1) * TG_PROBE_STRIDE;
+  if (q < q_last) return q;
+  return q - TG_PROBE_STRIDE < q_last ? q_last : 0xFFFFFFFFu;
+}
+// wave 2: true (and the entry is filled in) when the bracketing samples make the probe unnecessary
+TG_HD bool tg_probe_bracketed(TgSeedHit* row, uint32_t q, uint32_t q_last) {
+  const uint32_t qa = q - q % TG_PROBE_STRIDE;
+  const uint32_t qb = qa + TG_PROBE_STRIDE < q_last ? qa + TG_PROBE_STRIDE : q_last;
+  const uint32_t ea = row[qa].e, eb = row[qb].e;
+  if (ea != eb || ea == 0) return false;
+  row[q].e = ea; row[q].lo = 0; row[q].cnt = 0;
+  return true;
+}
+
+// Index::all_smems for one read from its probe results: SMEM records into the seed pool.
+template <class W>
+TG_HDN void tg_seed_select_read(W& w, const TgSeedHit* hits, uint32_t L, uint32_t k, const TgSeedOut& out, uint32_t r) {
+  const uint32_t n = tg_smem_count(hits, L, k);
+  unsigned long long base = 0;
+  uint32_t nn = n;
+  if (n) {
+    base = w.atomic_add(out.pool_used, (unsigned long long)n);
+    if (base + n > out.pool_cap) {
+      w.atomic_or(out.flags, TG_FLAG_SEED_POOL);
+      nn = 0;
+    }
+  }
+  if (nn) tg_smem_select(hits, L, k, out.pool + base);
+  out.read_first[r] = base;
+  out.read_count[r] = nn;
+  if (nn) w.atomic_add(out.n_smems, (unsigned long long)nn);
 }
 
 struct TgWarpScratch {  // per-warp global scratch of the extension stage

@@ -233,34 +233,63 @@ __global__ void k_kmer_insert(const uint64_t* __restrict__ text4, uint64_t T, co
 struct SeedParams {
   const uint8_t* bases;
   const uint64_t* offs;
-  uint32_t n_reads, k, max_len;
+  uint32_t n_reads, k, max_len, max_q, rp_words;  // max_q = max_len - k + 1 probe offsets per read
   const TgSlot* slots;
   uint64_t slot_mask;
   const uint64_t* text4;
   const uint32_t* sa;
+  uint64_t* rp;        // [n_reads][rp_words] packed reads (also used by the extension stage)
+  TgSeedHit* hits;     // [n_reads][max_q]
+  int wave;            // 0: offset 0 of every read; 1: the other offsets, skipped when the whole read matched at 0
   TgSeedOut out;
   DevCounters* ctr;
 };
-__host__ __device__ inline size_t seed_smem_per_warp(uint32_t maxL) {
-  return align16((maxL / 16 + 4) * 8) + align16((size_t)(maxL + 1) * sizeof(TgSeedHit)) +
-         align16((size_t)(maxL + 1) * sizeof(tg_seed)) + align16((size_t)(maxL + 1) * 2);
+
+// ASCII -> 4-bit codes, one thread per packed word
+__global__ void __launch_bounds__(256) k_pack_reads(SeedParams p) {
+  const unsigned long long total = (unsigned long long)p.n_reads * p.rp_words;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(t / p.rp_words), wi = (uint32_t)(t % p.rp_words);
+    const uint64_t off = p.offs[r];
+    const uint32_t L = (uint32_t)(p.offs[r + 1] - off);
+    p.rp[t] = wi < L / 16 + 3 ? tg_pack_word(p.bases, off, L, wi) : 0xFFFFFFFFFFFFFFFFull;
+  }
 }
 
-__global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_seed(SeedParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* base = smem + (threadIdx.x >> 5) * seed_smem_per_warp(p.max_len);
-  TgSeedMem m;
-  m.rp = (uint64_t*)base; base += align16((p.max_len / 16 + 4) * 8);
-  m.hits = (TgSeedHit*)base; base += align16((size_t)(p.max_len + 1) * sizeof(TgSeedHit));
-  m.sm = (tg_seed*)base; base += align16((size_t)(p.max_len + 1) * sizeof(tg_seed));
-  m.grp = (uint16_t*)base;
-  DevWarp w;
-  for (;;) {
-    uint32_t r = next_work(&p.ctr->work_seed);
-    if (r >= p.n_reads) break;
-    uint64_t off = p.offs[r];
-    uint32_t L = (uint32_t)(p.offs[r + 1] - off);
-    tg_seed_read<DevWarp>(w, m, p.bases, off, L, p.k, p.slots, p.slot_mask, p.text4, p.sa, p.out, r);
+// E(q): one thread per (read, offset), in the three waves of tg_core.h (TG_PROBE_STRIDE).  Consecutive threads probe
+// consecutive offsets of a read: their k-mer slots are random HBM accesses, their text verifications share sectors.
+__global__ void __launch_bounds__(256) k_seed_probe(SeedParams p) {
+  const uint32_t qn = p.wave == 0 ? 1u : p.wave == 1 ? (p.max_q + TG_PROBE_STRIDE - 1) / TG_PROBE_STRIDE : p.max_q - 1;
+  const unsigned long long total = (unsigned long long)p.n_reads * qn;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(t / qn), j = (uint32_t)(t % qn);
+    const uint32_t L = (uint32_t)(p.offs[r + 1] - p.offs[r]);
+    if (L < p.k) continue;
+    const uint32_t q_last = L - p.k;
+    TgSeedHit* row = p.hits + (size_t)r * p.max_q;
+    uint32_t q = 0;
+    if (p.wave > 0) {
+      if (row[0].e == L) continue;  // read[0..L) occurs: E(q) = L for every q, no other SMEM
+      if (p.wave == 1) {
+        q = tg_probe_sample(j, q_last);
+        if (q == 0xFFFFFFFFu) continue;
+      } else {
+        q = j + 1;
+        if (q > q_last || tg_probe_is_sample(q, q_last) || tg_probe_bracketed(row, q, q_last)) continue;
+      }
+    }
+    TgSeedHit h;
+    tg_seed_offset(p.rp + (size_t)r * p.rp_words, L, q, p.k, p.slots, p.slot_mask, p.text4, p.sa, h);
+    row[q] = h;
+  }
+}
+
+// Index::all_smems per read from E[]: one thread per read
+__global__ void __launch_bounds__(128) k_seed_select(SeedParams p) {
+  DevThread w;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
+    const uint32_t L = (uint32_t)(p.offs[r + 1] - p.offs[r]);
+    tg_seed_select_read<DevThread>(w, p.hits + (size_t)r * p.max_q, L, p.k, p.out, r);
   }
 }
 
@@ -407,17 +436,7 @@ __global__ void __launch_bounds__(128) k_round_init(RoundParams p) {
     TgReadState st;
     const bool ok = tg_read_state_init(st, L, p.P.opts, ns, sd);
     p.st[r] = st;
-    if (!ok) { mark_complex(p, r, 0); continue; }
-    if (ns == 0) continue;
-    uint64_t* rp = p.rp + (size_t)r * p.rp_words;
-    for (uint32_t wi = 0; wi < L / 16 + 3; wi++) {
-      uint64_t word = 0;
-      for (uint32_t t = 0; t < 16; t++) {
-        uint32_t q = wi * 16 + t;
-        word |= (uint64_t)(q < L ? tg_ascii_code(__ldg(p.bases + off + q)) : (uint32_t)TG_C_PAD) << ((15 - t) * 4);
-      }
-      rp[wi] = word;
-    }
+    if (!ok) mark_complex(p, r, 0);
   }
 }
 
@@ -840,7 +859,7 @@ struct tg_ctx {
   // inputs
   DevBuf d_bases, d_offs;
   // seeding
-  DevBuf d_seeds, d_seed_first, d_seed_count;
+  DevBuf d_seeds, d_seed_first, d_seed_count, d_probe;
   uint64_t seed_cap = 0;
   // extension
   DevBuf d_cands, d_arena, d_order, d_aln_first, d_aln_count, d_alns, d_ops;
@@ -951,7 +970,7 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->ix->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_ires, &c->r_cands, &c->r_hops, &c->r_fin, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex, &c->r_sorted, &c->r_dpt_trace,
+  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_probe, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_ires, &c->r_cands, &c->r_hops, &c->r_fin, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex, &c->r_sorted, &c->r_dpt_trace,
                     &c->d_aln_first, &c->d_aln_count, &c->d_alns, &c->d_ops, &c->s_x, &c->s_xo, &c->s_y, &c->s_yo, &c->s_bw,
                     &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops})
     b->release();
@@ -1055,23 +1074,31 @@ uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots 
 namespace {
 
 tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL) {
-  size_t per_warp = seed_smem_per_warp(maxL);
-  size_t smem = per_warp * TG_WARPS_PER_CTA;
-  CU_CHECK(cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_seed, TG_WARPS_PER_CTA * 32, smem));
-  if (occ < 1) return tg_fail(TG_ERR_CAPACITY, "seed kernel does not fit in shared memory");
-  int blocks = (int)std::min<uint64_t>((uint64_t)c->n_sms * occ, ((uint64_t)n + TG_WARPS_PER_CTA - 1) / TG_WARPS_PER_CTA);
-  if (blocks < 1) blocks = 1;
   SeedParams p;
   p.bases = d_bases; p.offs = d_offs; p.n_reads = n; p.k = c->opts.min_seed_len; p.max_len = maxL;
+  p.max_q = maxL >= p.k ? maxL - p.k + 1 : 1;
+  p.rp_words = maxL / 16 + 4;
+  tg_status st;
+  if ((st = c->r_rp.ensure((size_t)n * p.rp_words * 8)) != TG_OK) return st;
+  if ((st = c->d_probe.ensure((size_t)n * p.max_q * sizeof(TgSeedHit))) != TG_OK) return st;
   p.slots = c->slots; p.slot_mask = c->n_slots - 1; p.text4 = c->ix->dev.text4; p.sa = c->ix->dev.sa;
+  p.rp = (uint64_t*)c->r_rp.p; p.hits = (TgSeedHit*)c->d_probe.p; p.wave = 0;
   p.out.pool = (tg_seed*)c->d_seeds.p; p.out.pool_used = &c->d_ctr->seed_used; p.out.pool_cap = c->seed_cap;
   p.out.read_first = (uint64_t*)c->d_seed_first.p; p.out.read_count = (uint32_t*)c->d_seed_count.p;
   p.out.flags = &c->d_ctr->flags; p.out.n_smems = &c->d_ctr->n_smems;
   p.ctr = c->d_ctr;
-  k_seed<<<blocks, TG_WARPS_PER_CTA * 32, smem, c->stream>>>(p);
-  c->n_launches++;
+  const int grid = c->n_sms * 8;
+  k_pack_reads<<<grid, 256, 0, c->stream>>>(p);
+  k_seed_probe<<<grid, 256, 0, c->stream>>>(p);
+  if (p.max_q > 1) {
+    p.wave = 1;
+    k_seed_probe<<<grid, 256, 0, c->stream>>>(p);
+    p.wave = 2;
+    k_seed_probe<<<grid, 256, 0, c->stream>>>(p);
+    c->n_launches += 2;
+  }
+  k_seed_select<<<(int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16), 128, 0, c->stream>>>(p);
+  c->n_launches += 3;
   CU_CHECK(cudaGetLastError());
   return TG_OK;
 }
@@ -1141,7 +1168,6 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   if ((st = c->r_cands.ensure(c->item_cap * sizeof(TgCand))) != TG_OK) return st;
   if ((st = c->r_hops.ensure(c->hops_cap * 4)) != TG_OK) return st;
   if ((st = c->r_fin.ensure(c->item_cap * 12)) != TG_OK) return st;
-  if ((st = c->r_rp.ensure((size_t)n * rp_words * 8)) != TG_OK) return st;
   if ((st = c->r_tasks.ensure(c->round_task_cap * sizeof(TgTask))) != TG_OK) return st;
   if ((st = c->r_ops.ensure(c->round_ops_cap * 4)) != TG_OK) return st;
   if ((st = c->r_complex.ensure((size_t)n * 4 + 16)) != TG_OK) return st;
