@@ -251,13 +251,23 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    seed_ms = ext_ms = 0.0
+    # the reference's DP cell count for this batch (what GCUPS is credited on): one untimed pass that runs every column
+    # the reference runs; the timed passes stop extensions early where that provably cannot change a record
+    aligner.set_exact_cell_count(True)
+    ref_cells = float(step_device().swg_cells)
+    aligner.set_exact_cell_count(False)
+    step_device()
+    barrier()
+    seed_ms = ext_ms = dp_ms = 0.0
+    launches = 0
     ev0.record(stream)
     for _ in range(args.steps):
         res = step_device()
         a, b = aligner.last_kernel_ms()
         seed_ms += a
         ext_ms += b
+        dp_ms += aligner.last_dp_ms()
+        launches += aligner.last_kernel_launches()
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
@@ -281,13 +291,13 @@ def main():
     h2d = int(bases.nbytes + offs.nbytes)
     d2h = int(n * 12 + hres.n_alns * 104 + hres.n_ops * 4)
 
-    t = torch.tensor([dev_ms, e2e_ms, seed_ms, ext_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, seed_ms, ext_ms, dp_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([counters["swg_cells"], counters["seed_hits"], counters["n_alns"], counters["n_ops"], counters["n_smems"],
-                        counters["swg_extensions"]], dtype=torch.float64, device=dev)
+                        counters["swg_extensions"], ref_cells, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, seed_ms, ext_ms = [float(x) for x in t.tolist()]
+    dev_ms, e2e_ms, seed_ms, ext_ms, dp_ms = [float(x) for x in t.tolist()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -297,21 +307,26 @@ def main():
     value = total_reads / (dev_ms / 1e3)
     e2e_value = total_reads / (e2e_ms / 1e3)
     hbm_peak, peak_src, sm_max = peaks()
-    cells, hits, n_alns, n_ops, n_smems, n_ext = [float(x) / world for x in cnt.tolist()]  # per GPU, per step
-    seed_launch_ms = seed_ms / args.steps
-    ext_launch_ms = ext_ms / args.steps
+    cells, hits, n_alns, n_ops, n_smems, n_ext, ref_cells, launches = [float(x) / world for x in cnt.tolist()]  # per GPU
+    seed_launch_ms = seed_ms / args.steps   # pack + probe waves + select
+    ext_launch_ms = ext_ms / args.steps     # all rounds: control kernels + DP
+    dp_launch_ms = dp_ms / args.steps       # the banded-SWG kernels of all rounds (class groups run concurrently)
     seed_bytes = seed_algorithmic_bytes(n, READ_LEN, FLAGS["k"], hits)
-    ext_bytes = n * READ_LEN + n_smems * 24 + cells / 4 + n_alns * 104 + n_ops * 4
     seed_gbs = seed_bytes / (seed_launch_ms / 1e3) / 1e9
-    ext_gbs = ext_bytes / (ext_launch_ms / 1e3) / 1e9
-    dominant = "k_extend" if ext_launch_ms >= seed_launch_ms else "k_seed"
-    ach = ext_gbs if dominant == "k_extend" else seed_gbs
-    gcups = cells / (ext_launch_ms / 1e3) / 1e9
+    gcups_ref = ref_cells / (dp_launch_ms / 1e3) / 1e9
+    gcups_computed = cells / (dp_launch_ms / 1e3) / 1e9
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
-    # INT-pipe roofline: 148 SMs x 4 SMSP x 16 lanes/clk x f x P / I ; P = 1 cell per lane-op (32-bit), I = ALU
-    # instructions per cell-step of the shipped inner loop (DESIGN.md section "k_extend roofline")
-    INSTR_PER_CELL = 14.0
+    # INT-pipe roofline: 148 SMs x 4 SMSP x 16 lanes/clk x f x P / I.  P = 1 cell per lane-op (32-bit scores),
+    # I = 9 ALU-pipe instructions per cell in the shipped inner loop of k_round_dpt (cuobjdump -sass: VIADD, @P VIADD,
+    # 5 x VIADDMNMX, VIMNMX3, VIMNMX; 4 more IMADs issue on the FMA pipe) -- see DESIGN.md section 4.
+    INSTR_PER_CELL = 9.0
     int_roof = 148 * 4 * 16 * (sm_mhz * 1e6) * 1.0 / INSTR_PER_CELL / 1e9
+    traffic = {}
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f)
+    except OSError:
+        pass
     line = dict(
         metric="reads/sec", value=value, unit="reads/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
@@ -322,17 +337,24 @@ def main():
                     index_bytes=int(index.blob().nbytes), kmer_table_bytes=int(aligner.kmer_table_bytes()),
                     index_broadcast_ms=bcast_ms, setup_s=setup_s),
         e2e=dict(value=e2e_value, unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),
-        gpu_launches=2 * args.steps,
-        roofline=dict(bound="hbm", kernel=dominant, achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None,
-                      peak_source=peak_src,
-                      note="algorithmic bytes per launch / CUDA-event duration of that kernel; k_extend is INT-pipe bound "
-                           "(see roofline_int), k_seed is HBM random-access bound (see roofline_seed)"),
-        roofline_seed=dict(bound="hbm", kernel="k_seed", achieved=seed_gbs, peak=hbm_peak, unit="GB/s", frac=seed_gbs / hbm_peak,
-                           ms_per_launch=seed_launch_ms, algorithmic_bytes_per_read=seed_bytes / n),
-        roofline_int=dict(bound="int-pipe", kernel="k_extend", achieved=gcups, peak=int_roof, unit="GCUPS", frac=gcups / int_roof,
-                          ms_per_launch=ext_launch_ms, cells_per_read=cells / n, sm_mhz=sm_mhz,
-                          instr_per_cell=INSTR_PER_CELL, cells_per_lane_op=1.0),
-        kernel_share=dict(k_seed=seed_ms / dev_ms, k_extend=ext_ms / dev_ms),
+        gpu_launches=int(launches),
+        roofline=dict(bound="int-pipe", kernel="k_round_dpt<0..3> (banded SWG, thread per extension)", achieved=gcups_ref,
+                      peak=int_roof, unit="GCUPS", frac=gcups_ref / int_roof, traffic=traffic.get("k_round_dpt"),
+                      achieved_computed_cells=gcups_computed, ms_per_step=dp_launch_ms,
+                      cells_per_read_reference=ref_cells / n, cells_per_read_computed=cells / n, sm_mhz=sm_mhz,
+                      alu_instr_per_cell=INSTR_PER_CELL, cells_per_lane_op=1.0,
+                      peak_source="148 SM x 4 SMSP x 16 lanes/clk x sm_mhz / 9 ALU-pipe instructions per cell (no tensor cores: "
+                                  "max-plus integer DP); MEASURED_PEAKS.json has no integer figure",
+                      note="achieved = DP cells as the reference's loops visit them (credited count, one exact-count pass) / "
+                           "summed CUDA-event time of the DP sections of all rounds; achieved_computed_cells counts only "
+                           "the cells the early-stopped extensions really visit"),
+        roofline_seed=dict(bound="hbm", kernel="k_seed_probe x3 + k_pack_reads + k_seed_select", achieved=seed_gbs, peak=hbm_peak,
+                           unit="GB/s", frac=seed_gbs / hbm_peak, traffic=traffic.get("k_seed_probe"), peak_source=peak_src,
+                           ms_per_step=seed_launch_ms, algorithmic_bytes_per_read=seed_bytes / n,
+                           note="algorithmic bytes (SURVEY 8d sector formula) / CUDA-event time of the seeding stage; the peak "
+                                "is the streaming-copy figure, a random 32-B-sector gather peaks far lower"),
+        kernel_share=dict(seeding=seed_ms / dev_ms, extension_total=ext_ms / dev_ms, swg_dp=dp_ms / dev_ms,
+                          extension_control=(ext_ms - dp_ms) / dev_ms),
         counters=dict(hits_per_read=hits / n, alns_per_read=n_alns / n, smems_per_read=n_smems / n, swg_ext_per_read=n_ext / n),
         clocks=clocks,
     )

@@ -150,6 +150,9 @@ void tg_ctx_set_exact_cell_count(tg_ctx* ctx, int on);
  * cannot hold (more than 12 transcripts on one seed, ~100k hits) run on the single-warp kernel.  on = 0: every read on
  * the single-warp kernel.  Both produce identical records. */
 void tg_ctx_set_round_pipeline(tg_ctx* ctx, int on);
+/* Device time of the banded-SWG kernels alone (the DP sections of all rounds, CUDA events) in the last tg_align_batch*
+ * call, in milliseconds.  Part of extend_ms above. */
+float tg_ctx_last_dp_ms(const tg_ctx* ctx);
 /* Number of kernels the last tg_align_batch* / tg_seed_batch call launched on the context's stream. */
 uint64_t tg_ctx_last_kernel_launches(const tg_ctx* ctx);
 /* Size of the context's k-mer table in bytes. */

@@ -70,7 +70,7 @@ ABI_SYMBOLS = [
     "tg_index_host_text_len", "tg_index_host_n_refs", "tg_index_host_n_txs", "tg_index_host_n_genes",
     "tg_index_host_ref", "tg_index_host_tx", "tg_index_host_gene_id", "tg_index_host_gene_name", "tg_index_host_sa",
     "tg_index_create", "tg_index_create_from_device_blob", "tg_index_destroy",
-    "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
+    "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
     "tg_align_batch", "tg_align_batch_device", "tg_seed_batch", "tg_swg_extend_batch",
     "tg_format_sam_header", "tg_format_batch", "tg_parse_fastq", "tg_free",
 ]
@@ -93,6 +93,7 @@ def lib():
         L.tg_ctx_stream.restype = C.c_void_p
         L.tg_ctx_kmer_table_bytes.restype = C.c_uint64
         L.tg_ctx_last_kernel_launches.restype = C.c_uint64
+        L.tg_ctx_last_dp_ms.restype = C.c_float
         L.tg_ctx_last_kernel_ms.restype = None
         L.tg_ctx_set_exact_cell_count.restype = None
         L.tg_ctx_set_round_pipeline.restype = None
@@ -361,6 +362,10 @@ class Aligner:
     def set_round_pipeline(self, on: bool):
         """True (default): round pipeline (thread-per-read control + warp-per-task extension); False: single-warp kernel."""
         lib().tg_ctx_set_round_pipeline(self._h, int(on))
+
+    def last_dp_ms(self) -> float:
+        """Device time of the banded-SWG kernels in the last align call (part of the extend time)."""
+        return float(lib().tg_ctx_last_dp_ms(self._h))
 
     def last_kernel_launches(self) -> int:
         return int(lib().tg_ctx_last_kernel_launches(self._h))

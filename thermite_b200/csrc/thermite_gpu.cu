@@ -848,6 +848,9 @@ struct tg_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the band-class groups of a round's DP run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_dp0[TG_MAX_ROUNDS] = {}, ev_dp1[TG_MAX_ROUNDS] = {};  // DP section of every round (timing)
+  int rounds_run = 0;
+  float last_dp_ms = 0.f;
   unsigned long long* h_active = nullptr;  // pinned
   float last_seed_ms = 0.f, last_extend_ms = 0.f;
   int exact_cells = 0;  // 1: run every column the reference runs (swg_cells == reference count)
@@ -982,6 +985,7 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int i = 0; i < TG_MAX_ROUNDS; i++) { if (c->ev_dp0[i]) cudaEventDestroy(c->ev_dp0[i]); if (c->ev_dp1[i]) cudaEventDestroy(c->ev_dp1[i]); }
   for (int i = 0; i < 3; i++) { if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); if (c->side[i]) cudaStreamDestroy(c->side[i]); }
   if (c->h_active) cudaFreeHost(c->h_active);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1014,6 +1018,7 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
     CTX_CHECK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
   }
   CTX_CHECK(cudaMallocHost(&c->h_active, sizeof(unsigned long long)));
+  for (int i = 0; i < TG_MAX_ROUNDS; i++) { CTX_CHECK(cudaEventCreate(&c->ev_dp0[i])); CTX_CHECK(cudaEventCreate(&c->ev_dp1[i])); }
   CTX_CHECK(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, ix->device));
   CTX_CHECK(cudaMalloc(&c->d_ctr, sizeof(DevCounters)));
   CTX_CHECK(cudaMallocHost(&c->h_ctr, sizeof(DevCounters)));
@@ -1066,6 +1071,7 @@ void tg_ctx_debug_rounds(const tg_ctx* ctx, uint64_t* out52) {
 void tg_ctx_debug_classes(const tg_ctx* ctx, uint32_t* out) {  // [TG_MAX_ROUNDS][TG_DPT_NCLS]
   memcpy(out, ctx->h_ctr->round_cls, sizeof(ctx->h_ctr->round_cls));
 }
+float tg_ctx_last_dp_ms(const tg_ctx* ctx) { return ctx ? ctx->last_dp_ms : 0.f; }
 uint64_t tg_ctx_last_kernel_launches(const tg_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots * sizeof(TgSlot) : 0; }
 
@@ -1250,6 +1256,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
     k_round_binscan<<<1, TG_BINSCAN_THREADS, 0, c->stream>>>(p);
     k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
     // the four class groups (widest first: longest tasks) on their own streams, joined before `post`
+    CU_CHECK(cudaEventRecord(c->ev_dp0[r], c->stream));
     CU_CHECK(cudaEventRecord(c->ev_fork, c->stream));
     for (int i = 0; i < 3; i++) CU_CHECK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
     k_round_dpt<3><<<dpt_grid[3], 128, 0, c->side[0]>>>(p);
@@ -1261,6 +1268,8 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
       CU_CHECK(cudaEventRecord(c->ev_join[i], c->side[i]));
       CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
     }
+    CU_CHECK(cudaEventRecord(c->ev_dp1[r], c->stream));
+    c->rounds_run = (int)r + 1;
     k_round_post<<<iblocks, 128, 0, c->stream>>>(p);
     k_round_scan<<<tblocks, 128, 0, c->stream>>>(p);
     c->n_launches += 11;
@@ -1309,6 +1318,13 @@ tg_status run_pipeline(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs
     CU_CHECK(cudaStreamSynchronize(c->stream));
     CU_CHECK(cudaEventElapsedTime(&c->last_seed_ms, c->ev0, c->ev1));
     CU_CHECK(cudaEventElapsedTime(&c->last_extend_ms, c->ev1, c->ev2));
+    c->last_dp_ms = 0.f;
+    if (extend && c->use_rounds)
+      for (int r = 0; r < c->rounds_run; r++) {
+        float ms = 0.f;
+        CU_CHECK(cudaEventElapsedTime(&ms, c->ev_dp0[r], c->ev_dp1[r]));
+        c->last_dp_ms += ms;
+      }
     int f = c->h_ctr->flags;
     if (f & (TG_FLAG_SEED_POOL | TG_FLAG_ALN_POOL | TG_FLAG_OPS_POOL | TG_FLAG_TASK_POOL | TG_FLAG_ITEM_POOL | TG_FLAG_HOPS_POOL)) {  // grow the pool that overflowed and redo the batch
       if (f & TG_FLAG_TASK_POOL) c->round_task_cap *= 2;
