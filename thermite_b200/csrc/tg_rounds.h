@@ -54,7 +54,9 @@ struct TgProbE {
   uint64_t lo_abs, hi_abs, r_abs;
   uint32_t q, len;
   int32_t task_r, task_l;  // -1: trivial (empty x or empty y)
-  uint8_t seqsel, pad[7];
+  uint8_t seqsel, pad[3];
+  uint32_t gkey;           // text position of the seed when both y windows are one contiguous piece of text (the genome
+                           // problem; a transcript problem whose windows stay inside one exon), else TG_NONE
 };
 struct TgCandE {
   uint64_t t0;
@@ -154,7 +156,12 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
   if (seq_end > (uint64_t)aref.end_idx - 1) seq_end = (uint64_t)aref.end_idx - 1;
   hit.n_prob = 1; hit.n_cand = 0;
   hit.prob[0].lo_abs = seq_start; hit.prob[0].hi_abs = seq_end; hit.prob[0].r_abs = ref_idx;
-  hit.prob[0].q = q; hit.prob[0].len = len; hit.prob[0].seqsel = 0;
+  hit.prob[0].q = q; hit.prob[0].len = len; hit.prob[0].seqsel = 0; hit.prob[0].gkey = ref_idx;
+  uint32_t ncR0, ncL0;
+  {
+    TgProblem pg{nullptr, seq_start, seq_end, ref_idx, q, len};
+    tg_problem_windows(pg, L, bw, ncR0, ncL0);
+  }
   const TgStabRange xr = tg_stab_begin<W>(w, ix.exon_stab, ix.n_exon_stab, ix.exon_maxlen, ref_idx, ref_idx + len);
   uint32_t next_rank = 0;
   for (;;) {
@@ -172,16 +179,45 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
     }
     if (hit.n_cand >= TG_CMAX) return false;
     TgProblem pt{ix.txseq4, t0, t1, t0 + tr, tq, tl};
+    // Identical DP problems are evaluated once.  Cheap exact test first: when the y windows of the transcript problem
+    // stay inside ONE exon they are a contiguous piece of text, so the problem equals any other contiguous problem with
+    // the same seed position, seed and window lengths (transcript sequences are spliced text).  Only problems whose
+    // windows cross a junction are compared symbol by symbol, and only with each other; a missed match merely costs a
+    // duplicate evaluation with the same result.
+    uint32_t ncRt, ncLt;
+    tg_problem_windows(pt, L, bw, ncRt, ncLt);
+    uint32_t gkey = TG_NONE;
+    {
+      uint32_t exon_sum = 0;
+      for (uint32_t e = e0; e < e1; e++) {
+        const uint32_t es = TG_LDG(ix.te_start + e), elen = TG_LDG(ix.te_end + e) - es;
+        if (tr < exon_sum + elen) {  // the exon holding the seed start
+          if (tr - exon_sum >= ncLt && (uint64_t)tr + tl + ncRt <= (uint64_t)exon_sum + elen) gkey = es + (tr - exon_sum);
+          break;
+        }
+        exon_sum += elen;
+      }
+    }
     uint32_t pi = hit.n_prob;
     for (uint32_t k = 0; k < hit.n_prob; k++) {
       const TgProbE& e = hit.prob[k];
-      TgProblem pk{tg_seq_of(ix, e.seqsel), e.lo_abs, e.hi_abs, e.r_abs, e.q, e.len};
-      if (tg_same_problem<W>(w, pt, pk, L, bw)) { pi = k; break; }
+      if (gkey != TG_NONE) {
+        if (e.gkey != gkey || e.q != tq || e.len != tl) continue;
+        uint32_t ncRk = ncR0, ncLk = ncL0;
+        if (k > 0) {
+          TgProblem pk{nullptr, e.lo_abs, e.hi_abs, e.r_abs, e.q, e.len};
+          tg_problem_windows(pk, L, bw, ncRk, ncLk);
+        }
+        if (ncRk == ncRt && ncLk == ncLt) { pi = k; break; }
+      } else if (e.gkey == TG_NONE) {
+        TgProblem pk{tg_seq_of(ix, e.seqsel), e.lo_abs, e.hi_abs, e.r_abs, e.q, e.len};
+        if (tg_same_problem<W>(w, pt, pk, L, bw)) { pi = k; break; }
+      }
     }
     if (pi == hit.n_prob) {
       if (hit.n_prob >= TG_PMAX) return false;
       TgProbE& e = hit.prob[hit.n_prob++];
-      e.lo_abs = t0; e.hi_abs = t1; e.r_abs = t0 + tr; e.q = tq; e.len = tl; e.seqsel = 1;
+      e.lo_abs = t0; e.hi_abs = t1; e.r_abs = t0 + tr; e.q = tq; e.len = tl; e.seqsel = 1; e.gkey = gkey;
     }
     TgCandE& c = hit.cand[hit.n_cand++];
     c.t0 = t0; c.tx_idx = tx_idx; c.prob = pi; c.tr = tr; c.tlen = (uint32_t)(t1 - t0);
