@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_round_dp(RoundParams 
 __device__ __forceinline__ uint32_t task_bin(const TgTask& t) {
   const int xlen = (int)t.xlen, bw = (int)t.bw, ylen = (int)t.ylen;
   const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
-  const int cls = tg_dpt_class(xlen, bw, t.x_drop);
+  const int cls = t.pad0 ? 0 : tg_dpt_class(xlen, bw, t.x_drop);  // pad0: not for the thread kernel (tg_swg_extend_batch)
   // lanes of a warp should agree on the phase boundaries (bw) and on the number of columns: sort by both
   const int bwb = bw < 16 ? bw : 16 + (bw - 16 < 60 ? (bw - 16) >> 2 : 15);
   const int cb = (ncols < 255 ? ncols : 255) >> 4;
@@ -738,6 +738,14 @@ struct SwgParams {
   uint32_t max_xlen, max_cols, trace_bytes, ops_words;
   int bound_stop;
   DevCounters* ctr;
+  const uint32_t* list;  // when set: only the tasks list[0 .. ctr->cls_start[1]) (those the thread kernel cannot take)
+  // thread-kernel path: tasks in round-pipeline form, x as packed "reads", y as one packed text
+  TgTask* tasks;
+  uint64_t* xpk;
+  uint64_t* ypk;
+  const uint64_t* ysym_off;  // [n] first symbol of task t in ypk (multiple of 16)
+  uint32_t rp_words;
+  const uint32_t* dp_ops;    // operations written by the thread kernels (generation order)
 };
 __host__ __device__ inline size_t swg_smem_per_warp(uint32_t max_xlen, uint32_t max_cols, uint32_t trace_bytes, uint32_t ops_words) {
   return align16(max_xlen + 16) + align16(max_cols + 16) + align16(trace_bytes) + align16((size_t)ops_words * 4);
@@ -755,7 +763,10 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_swg_batch(SwgParams p
   unsigned long long cells = 0, n_ext = 0;
   for (;;) {
     uint32_t t = next_work(&p.ctr->work_swg);
-    if (t >= p.n) break;
+    if (p.list) {
+      if (t >= p.ctr->cls_start[1]) break;
+      t = p.list[t];
+    } else if (t >= p.n) break;
     const uint64_t x0 = p.xoff[t], y0 = p.yoff[t];
     const int xlen = (int)(p.xoff[t + 1] - x0);
     const int ylen_full = (int)min((unsigned long long)(p.yoff[t + 1] - y0), 0x7fffffffull);
@@ -785,6 +796,81 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_swg_batch(SwgParams p
   cells = warp_sum(cells);
   n_ext = warp_sum(n_ext);
   if (lane == 0) {
+    if (cells) atomicAdd(&p.ctr->cells, cells);
+    if (n_ext) atomicAdd(&p.ctr->n_ext, n_ext);
+  }
+}
+
+// SwgExtend::extend batch on the thread-per-extension kernels: every (x, y) pair becomes a round-pipeline task whose
+// x is a packed "read" and whose y lives in one packed text.  Bytes are compared AS GIVEN by the reference, so only
+// pairs made of the symbols A C G N T (upper case) may use the 4-bit codes; the others keep pad0 = 1 and run on
+// k_swg_batch with raw bytes.
+__device__ __forceinline__ uint32_t exact_code(uint8_t c) {
+  switch (c) {
+    case 'A': return TG_C_A;
+    case 'C': return TG_C_C;
+    case 'G': return TG_C_G;
+    case 'N': return TG_C_N;
+    case 'T': return TG_C_T;
+    default: return 0xFFu;
+  }
+}
+__global__ void __launch_bounds__(128) k_swg_prepare(SwgParams p) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < p.n; t += gridDim.x * blockDim.x) {
+    const uint64_t x0 = p.xoff[t], y0 = p.yoff[t];
+    const uint32_t xlen = (uint32_t)(p.xoff[t + 1] - x0);
+    const uint64_t ylen_full = p.yoff[t + 1] - y0;
+    const uint32_t bw = p.bw[t];
+    const uint32_t ylen = ylen_full > (uint64_t)xlen + bw ? xlen + bw + 1 : (uint32_t)ylen_full;
+    const uint32_t ncols = ylen < xlen + bw ? ylen : xlen + bw;
+    TgTask& k = p.tasks[t];
+    k.read = t; k.xoff = 0; k.xlen = xlen; k.ylen = ylen; k.y0 = p.ysym_off[t]; k.bw = bw; k.x_drop = p.x_drop[t];
+    k.side = 0; k.seqsel = 0; k.pad1 = 0;
+    k.score = 0; k.xend = 0; k.yend = 0; k.cells = 0; k.ops_off = 0; k.ops_n = 0;
+    bool bad = xlen == 0 || ylen == 0 || tg_dpt_class((int)xlen, (int)bw, k.x_drop) == 0;
+    if (!bad) {
+      uint64_t* xw = p.xpk + (size_t)t * p.rp_words;
+      for (uint32_t wi = 0; wi * 16 < xlen; wi++) {
+        uint64_t word = 0;
+        for (uint32_t u = 0; u < 16; u++) {
+          const uint32_t i = wi * 16 + u;
+          uint32_t c = TG_C_PAD;
+          if (i < xlen) { c = exact_code(p.xs[x0 + i]); bad |= c == 0xFFu; }
+          word |= (uint64_t)(c & 15u) << ((15 - u) * 4);
+        }
+        xw[wi] = word;
+      }
+      uint64_t* yw = p.ypk + (k.y0 >> 4);
+      for (uint32_t wi = 0; wi * 16 < ncols; wi++) {
+        uint64_t word = 0;
+        for (uint32_t u = 0; u < 16; u++) {
+          const uint32_t i = wi * 16 + u;
+          uint32_t c = TG_C_PAD;
+          if (i < ncols) { c = exact_code(p.ys[y0 + i]); bad |= c == 0xFFu; }
+          word |= (uint64_t)(c & 15u) << ((15 - u) * 4);
+        }
+        yw[wi] = word;
+      }
+    }
+    k.pad0 = bad ? 1 : 0;
+  }
+}
+// results of the thread-kernel tasks -> the flat result arrays of tg_swg_extend_batch (operations in forward order)
+__global__ void __launch_bounds__(128) k_swg_collect(SwgParams p) {
+  unsigned long long cells = 0, n_ext = 0;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < p.n; t += gridDim.x * blockDim.x) {
+    const TgTask k = p.tasks[t];
+    if (k.pad0) continue;
+    const unsigned long long dst = warp_agg_add(&p.ctr->swg_ops_used, (unsigned long long)k.ops_n);
+    if (dst + k.ops_n > p.ops_cap) atomicOr(&p.ctr->flags, TG_FLAG_OPS_POOL);
+    else
+      for (uint32_t i = 0; i < k.ops_n; i++) p.ops[dst + i] = p.dp_ops[k.ops_off + k.ops_n - 1 - i];
+    p.score[t] = k.score; p.xend[t] = k.xend; p.yend[t] = k.yend;
+    p.task_off[t] = dst; p.task_len[t] = k.ops_n;
+    cells += k.cells; n_ext++;
+  }
+  cells = warp_sum(cells); n_ext = warp_sum(n_ext);
+  if ((threadIdx.x & 31) == 0) {
     if (cells) atomicAdd(&p.ctr->cells, cells);
     if (n_ext) atomicAdd(&p.ctr->n_ext, n_ext);
   }
@@ -876,7 +962,7 @@ struct tg_ctx {
   // host results
   PinBuf h_first, h_count, h_alns, h_ops, h_seeds, h_seed_first, h_seed_count;
   // swg batch
-  DevBuf s_x, s_xo, s_y, s_yo, s_bw, s_xd, s_score, s_xe, s_ye, s_toff, s_tlen, s_ops;
+  DevBuf s_x, s_xo, s_y, s_yo, s_bw, s_xd, s_score, s_xe, s_ye, s_toff, s_tlen, s_ops, s_ypk, s_ysym;
 };
 
 namespace {
@@ -975,7 +1061,7 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_probe, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_ires, &c->r_cands, &c->r_hops, &c->r_fin, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex, &c->r_sorted, &c->r_dpt_trace,
                     &c->d_aln_first, &c->d_aln_count, &c->d_alns, &c->d_ops, &c->s_x, &c->s_xo, &c->s_y, &c->s_yo, &c->s_bw,
-                    &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops})
+                    &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops, &c->s_ypk, &c->s_ysym})
     b->release();
   for (PinBuf* b : {&c->h_first, &c->h_count, &c->h_alns, &c->h_ops, &c->h_seeds, &c->h_seed_first, &c->h_seed_count}) b->release();
   if (c->slots) cudaFree(c->slots);
@@ -1160,6 +1246,49 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   return TG_OK;
 }
 
+// Geometry and scratch of the thread-per-extension kernels: one grid per class group, trace regions for `max_cols`
+// columns, the sorted task index.
+tg_status dpt_geometry(tg_ctx* c, RoundParams& p, uint32_t max_cols, uint64_t task_cap, int grid[4]) {
+  tg_status st;
+  void (*ks[4])(RoundParams) = {k_round_dpt<0>, k_round_dpt<1>, k_round_dpt<2>, k_round_dpt<3>};
+  const int group_wb[4] = {16, 32, 56, 80};  // widest class of each group
+  size_t off = 0;
+  for (int g = 0; g < 4; g++) {
+    int o = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ks[g], 128, 0));
+    if (o < 1) return tg_fail(TG_ERR_INTERNAL, "thread DP kernel does not fit");
+    grid[g] = c->n_sms * o;
+    p.dpt_trace_off[g] = off;
+    p.dpt_trace_words[g] = (size_t)max_cols * ((2 * group_wb[g] + 31) / 32) * 32;
+    off += (size_t)grid[g] * 4 * p.dpt_trace_words[g];
+  }
+  if ((st = c->r_dpt_trace.ensure(off * 4)) != TG_OK) return st;
+  if ((st = c->r_sorted.ensure(task_cap * 4)) != TG_OK) return st;
+  p.dpt_trace = (uint32_t*)c->r_dpt_trace.p;
+  p.dpt_one = 1; p.dpt_k128 = 128;
+  p.sorted = (uint32_t*)c->r_sorted.p;
+  return TG_OK;
+}
+
+// sort the tasks of round p.round by band class and run the thread-per-extension kernels (class groups concurrently)
+tg_status launch_dpt(tg_ctx* c, RoundParams& p, const int grid[4]) {
+  k_round_hist<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
+  k_round_binscan<<<1, TG_BINSCAN_THREADS, 0, c->stream>>>(p);
+  k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
+  CU_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+  for (int i = 0; i < 3; i++) CU_CHECK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+  k_round_dpt<3><<<grid[3], 128, 0, c->side[0]>>>(p);
+  k_round_dpt<2><<<grid[2], 128, 0, c->side[1]>>>(p);
+  k_round_dpt<1><<<grid[1], 128, 0, c->side[2]>>>(p);
+  k_round_dpt<0><<<grid[0], 128, 0, c->stream>>>(p);
+  for (int i = 0; i < 3; i++) {
+    CU_CHECK(cudaEventRecord(c->ev_join[i], c->side[i]));
+    CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+  }
+  c->n_launches += 7;
+  return TG_OK;
+}
+
 tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL) {
   tg_status st;
   const uint32_t rp_words = maxL / 16 + 4;
@@ -1218,32 +1347,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   const int iblocks = c->n_sms * 16;
   // thread-per-extension kernel: geometry, trace scratch, sorted task list
   int dpt_grid[4];
-  int dpt_blocks = 0;
-  {
-    void (*ks[4])(RoundParams) = {k_round_dpt<0>, k_round_dpt<1>, k_round_dpt<2>, k_round_dpt<3>};
-    for (int g = 0; g < 4; g++) {
-      int o = 0;
-      CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ks[g], 128, 0));
-      if (o < 1) return tg_fail(TG_ERR_INTERNAL, "thread DP kernel does not fit");
-      dpt_grid[g] = c->n_sms * o;
-      dpt_blocks = std::max(dpt_blocks, dpt_grid[g]);
-    }
-  }
-  const uint32_t dpt_x = std::min<uint32_t>(max_xlen, TG_DPT_MAX_X);
-  {
-    const int group_wb[4] = {16, 32, 56, 80};  // widest class of each group
-    size_t off = 0;
-    for (int g = 0; g < 4; g++) {
-      p.dpt_trace_off[g] = off;
-      p.dpt_trace_words[g] = (size_t)(dpt_x + max_bw + 1) * ((2 * group_wb[g] + 31) / 32) * 32;
-      off += (size_t)dpt_grid[g] * 4 * p.dpt_trace_words[g];
-    }
-    if ((st = c->r_dpt_trace.ensure(off * 4)) != TG_OK) return st;
-  }
-  if ((st = c->r_sorted.ensure(c->round_task_cap * 4)) != TG_OK) return st;
-  p.dpt_trace = (uint32_t*)c->r_dpt_trace.p;
-  p.dpt_one = 1; p.dpt_k128 = 128;
-  p.sorted = (uint32_t*)c->r_sorted.p;
+  if ((st = dpt_geometry(c, p, std::min<uint32_t>(max_xlen, TG_DPT_MAX_X) + max_bw + 1, c->round_task_cap, dpt_grid)) != TG_OK) return st;
   // tasks the thread kernel cannot take (long reads, very wide bands) exist only for such inputs
   const bool need_warp_kernel = max_xlen > TG_DPT_MAX_X || std::min<uint32_t>(2 * max_bw, max_xlen) + 1 > TG_DPT_MAX_WB;
   k_round_init<<<tblocks, 128, 0, c->stream>>>(p);
@@ -1252,27 +1356,14 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
     p.round = r;
     k_round_plan<<<tblocks, 128, 0, c->stream>>>(p);
     k_round_prep<<<iblocks, 128, 0, c->stream>>>(p);
-    k_round_hist<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
-    k_round_binscan<<<1, TG_BINSCAN_THREADS, 0, c->stream>>>(p);
-    k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
-    // the four class groups (widest first: longest tasks) on their own streams, joined before `post`
     CU_CHECK(cudaEventRecord(c->ev_dp0[r], c->stream));
-    CU_CHECK(cudaEventRecord(c->ev_fork, c->stream));
-    for (int i = 0; i < 3; i++) CU_CHECK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
-    k_round_dpt<3><<<dpt_grid[3], 128, 0, c->side[0]>>>(p);
-    k_round_dpt<2><<<dpt_grid[2], 128, 0, c->side[1]>>>(p);
-    k_round_dpt<1><<<dpt_grid[1], 128, 0, c->side[2]>>>(p);
-    k_round_dpt<0><<<dpt_grid[0], 128, 0, c->stream>>>(p);
+    if ((st = launch_dpt(c, p, dpt_grid)) != TG_OK) return st;
     if (need_warp_kernel) { kdp<<<dp_blocks, wpc * 32, smem, c->stream>>>(p); c->n_launches++; }
-    for (int i = 0; i < 3; i++) {
-      CU_CHECK(cudaEventRecord(c->ev_join[i], c->side[i]));
-      CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
-    }
     CU_CHECK(cudaEventRecord(c->ev_dp1[r], c->stream));
     c->rounds_run = (int)r + 1;
     k_round_post<<<iblocks, 128, 0, c->stream>>>(p);
     k_round_scan<<<tblocks, 128, 0, c->stream>>>(p);
-    c->n_launches += 11;
+    c->n_launches += 4;
     // late rounds are short: a host check for "nothing left" costs less than launching the remaining empty rounds
     if (r >= 3 && r + 1 < TG_MAX_ROUNDS) {
       CU_CHECK(cudaMemcpyAsync(c->h_active, &c->d_ctr->round_active[r], sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -1464,8 +1555,9 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   if (cells) *cells = 0;
   if (kernel_ms) *kernel_ms = 0.f;
   if (n == 0) { ops_off[0] = 0; return TG_OK; }
-  uint32_t max_xlen = 0, max_cols = 1;
-  uint64_t worst_ops = 0;
+  uint32_t max_xlen = 0, max_cols = 1, dpt_cols = 1, dpt_x = 1, n_dpt = 0;
+  uint64_t worst_ops = 0, ysym_total = 0;
+  std::vector<uint64_t> ysym(n);
   for (uint32_t t = 0; t < n; t++) {
     uint64_t xl = xoff[t + 1] - xoff[t], yl = yoff[t + 1] - yoff[t];
     if (xl > TG_MAX_READ_LEN) return tg_fail(TG_ERR_INVALID, "x longer than TG_MAX_READ_LEN");
@@ -1476,6 +1568,13 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
     max_xlen = std::max<uint32_t>(max_xlen, (uint32_t)xl);
     max_cols = std::max<uint32_t>(max_cols, (uint32_t)cols);
     worst_ops += xl + cols + 2;
+    ysym[t] = ysym_total;
+    if (xl && yl && tg_dpt_class((int)xl, (int)band_width[t], x_drop[t]) > 0) {  // may run on the thread kernels
+      dpt_cols = std::max<uint32_t>(dpt_cols, (uint32_t)cols);
+      dpt_x = std::max<uint32_t>(dpt_x, (uint32_t)xl);
+      ysym_total += ((cols + 15) / 16 + 2) * 16;
+      n_dpt++;
+    }
   }
   uint32_t trace_bytes = (max_cols + 1) * (uint32_t)tg_trace_bytes_per_col((int)max_xlen, 32);
   uint32_t ops_words = max_xlen + max_cols + 8;
@@ -1489,7 +1588,11 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   ENS(s_x, nx + 64); ENS(s_xo, (size_t)(n + 1) * 8); ENS(s_y, ny + 64); ENS(s_yo, (size_t)(n + 1) * 8);
   ENS(s_bw, (size_t)n * 4); ENS(s_xd, (size_t)n * 4); ENS(s_score, (size_t)n * 4); ENS(s_xe, (size_t)n * 4);
   ENS(s_ye, (size_t)n * 4); ENS(s_toff, (size_t)n * 8); ENS(s_tlen, (size_t)n * 4); ENS(s_ops, worst_ops * 4 + 64);
+  const uint32_t rp_words = dpt_x / 16 + 4;
+  ENS(r_tasks, (size_t)n * sizeof(TgTask)); ENS(r_rp, (size_t)n * rp_words * 8); ENS(s_ypk, (ysym_total / 16 + 4) * 8);
+  ENS(s_ysym, (size_t)n * 8); ENS(r_ops, worst_ops * 4 + 64);
 #undef ENS
+  CU_CHECK(cudaMemcpyAsync(c->s_ysym.p, ysym.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
   if (nx) CU_CHECK(cudaMemcpyAsync(c->s_x.p, xs, nx, cudaMemcpyHostToDevice, c->stream));
   if (ny) CU_CHECK(cudaMemcpyAsync(c->s_y.p, ys, ny, cudaMemcpyHostToDevice, c->stream));
   CU_CHECK(cudaMemcpyAsync(c->s_xo.p, xoff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1511,8 +1614,34 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   p.task_off = (uint64_t*)c->s_toff.p; p.task_len = (uint32_t*)c->s_tlen.p; p.ops = (uint32_t*)c->s_ops.p; p.ops_cap = worst_ops;
   p.max_xlen = max_xlen; p.max_cols = max_cols; p.trace_bytes = trace_bytes; p.ops_words = ops_words; p.ctr = c->d_ctr;
   p.bound_stop = c->exact_cells ? 0 : 1;
+  p.list = nullptr;
+  p.tasks = (TgTask*)c->r_tasks.p; p.xpk = (uint64_t*)c->r_rp.p; p.ypk = (uint64_t*)c->s_ypk.p;
+  p.ysym_off = (const uint64_t*)c->s_ysym.p; p.rp_words = rp_words; p.dp_ops = (const uint32_t*)c->r_ops.p;
+  c->n_launches = 0;
   CU_CHECK(cudaEventRecord(c->ev0, c->stream));
-  kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
+  if (n_dpt == 0 || !c->use_rounds) {
+    kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
+    c->n_launches++;
+  } else {
+    // pairs of A/C/G/N/T symbols that fit the register-band kernels: round-pipeline tasks on k_round_dpt<0..3>; the rest
+    // (other bytes, very long x, very wide bands, empty inputs) on the warp kernel with raw bytes
+    RoundParams rp{};
+    rp.P.ix = c->ix->dev; rp.P.ix.text4 = p.ypk; rp.P.opts = c->opts;
+    rp.n_reads = n; rp.rp_words = rp_words; rp.rp = p.xpk;
+    rp.tasks = p.tasks; rp.task_cap = n; rp.ops_pool = (uint32_t*)c->r_ops.p; rp.ops_cap = worst_ops; rp.round = 0;
+    rp.bound_stop = p.bound_stop; rp.ctr = c->d_ctr;
+    int grid[4];
+    if ((st = dpt_geometry(c, rp, dpt_cols + 1, n, grid)) != TG_OK) return st;
+    const unsigned long long n_tasks = n;
+    CU_CHECK(cudaMemcpyAsync(&c->d_ctr->round_tasks[0], &n_tasks, sizeof(n_tasks), cudaMemcpyHostToDevice, c->stream));
+    const int tb = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16);
+    k_swg_prepare<<<tb, 128, 0, c->stream>>>(p);
+    if ((st = launch_dpt(c, rp, grid)) != TG_OK) return st;
+    p.list = rp.sorted;
+    kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
+    k_swg_collect<<<tb, 128, 0, c->stream>>>(p);
+    c->n_launches += 3;
+  }
   CU_CHECK(cudaGetLastError());
   CU_CHECK(cudaEventRecord(c->ev1, c->stream));
   CU_CHECK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
