@@ -174,11 +174,29 @@ def run_reference(args, rank, world):
                 cpu_baseline=dict(value=value, unit="reads/s", cores=threads, kind="port",
                                   sample=f"{n} reads per step, {threads} host threads (single thread {rate1:.0f} reads/s)"),
                 e2e=dict(value=value, unit="reads/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    _RESULT_LINE.append(json.dumps(line))
 
 
 def main():
     args = parse_args()
+    # exactly ONE line on stdout (the JSON): libraries that print there (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _RESULT_LINE:
+        print(_RESULT_LINE[0], flush=True)
+
+
+_RESULT_LINE = []
+
+
+def _main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -225,6 +243,9 @@ def main():
     bases, offs = make_reads(contigs, txs, args.reads, SEEDS["reads"] + 1000 * rank)
     n = len(offs) - 1
     setup_s = time.time() - t_setup
+
+    # HBM random-access yardstick for the seeding roofline, measured live on this GPU over the k-mer table itself
+    gather_gbs = aligner.random_gather_gbs(1 << 26, 5) if rank == 0 else 0.0
 
     # HBM-resident inputs for `value`; pinned host inputs for `e2e`
     d_bases = torch.from_numpy(bases).to(dev)
@@ -348,11 +369,15 @@ def main():
                       note="achieved = DP cells as the reference's loops visit them (credited count, one exact-count pass) / "
                            "summed CUDA-event time of the DP sections of all rounds; achieved_computed_cells counts only "
                            "the cells the early-stopped extensions really visit"),
-        roofline_seed=dict(bound="hbm", kernel="k_seed_probe x3 + k_pack_reads + k_seed_select", achieved=seed_gbs, peak=hbm_peak,
-                           unit="GB/s", frac=seed_gbs / hbm_peak, traffic=traffic.get("k_seed_probe"), peak_source=peak_src,
+        roofline_seed=dict(bound="hbm", kernel="k_seed_probe x3 + k_pack_reads + k_seed_select", achieved=seed_gbs, peak=gather_gbs,
+                           unit="GB/s", frac=seed_gbs / gather_gbs if gather_gbs else None, traffic=traffic.get("k_seed_probe"),
+                           peak_source="random 16-B loads (32-B sectors) over the 4.3 GB k-mer table, measured live in this run "
+                                       "(tg_bench_random_gather, best of 5, CUDA events); streaming copy peak "
+                                       f"{hbm_peak:.0f} GB/s ({peak_src})",
+                           frac_of_streaming_peak=seed_gbs / hbm_peak,
                            ms_per_step=seed_launch_ms, algorithmic_bytes_per_read=seed_bytes / n,
-                           note="algorithmic bytes (SURVEY 8d sector formula) / CUDA-event time of the seeding stage; the peak "
-                                "is the streaming-copy figure, a random 32-B-sector gather peaks far lower"),
+                           note="algorithmic sector bytes (SURVEY 8d: one probe per read offset) / CUDA-event time of the "
+                                "seeding stage; the shipped kernels skip most probes (E(q) is monotone), so fewer bytes move"),
         kernel_share=dict(seeding=seed_ms / dev_ms, extension_total=ext_ms / dev_ms, swg_dp=dp_ms / dev_ms,
                           extension_control=(ext_ms - dp_ms) / dev_ms),
         counters=dict(hits_per_read=hits / n, alns_per_read=n_alns / n, smems_per_read=n_smems / n, swg_ext_per_read=n_ext / n),
@@ -363,7 +388,7 @@ def main():
         line["cpu_baseline"] = cb
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line))
+    _RESULT_LINE.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -155,6 +155,9 @@ void tg_ctx_set_round_pipeline(tg_ctx* ctx, int on);
 float tg_ctx_last_dp_ms(const tg_ctx* ctx);
 /* Number of kernels the last tg_align_batch* / tg_seed_batch call launched on the context's stream. */
 uint64_t tg_ctx_last_kernel_launches(const tg_ctx* ctx);
+/* Measurement aid for the seeding roofline: rate of independent random 16-B loads (one 32-B sector each) over the
+ * context's own k-mer table, in GB/s of sectors, best of `reps` launches (CUDA events). */
+tg_status tg_bench_random_gather(tg_ctx* ctx, uint64_t n_loads, int reps, double* sector_gbs, float* best_ms);
 /* Size of the context's k-mer table in bytes. */
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx);
 

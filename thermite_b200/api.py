@@ -70,7 +70,7 @@ ABI_SYMBOLS = [
     "tg_index_host_text_len", "tg_index_host_n_refs", "tg_index_host_n_txs", "tg_index_host_n_genes",
     "tg_index_host_ref", "tg_index_host_tx", "tg_index_host_gene_id", "tg_index_host_gene_name", "tg_index_host_sa",
     "tg_index_create", "tg_index_create_from_device_blob", "tg_index_destroy",
-    "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
+    "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_bench_random_gather", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
     "tg_align_batch", "tg_align_batch_device", "tg_seed_batch", "tg_swg_extend_batch",
     "tg_format_sam_header", "tg_format_batch", "tg_parse_fastq", "tg_free",
 ]
@@ -366,6 +366,12 @@ class Aligner:
     def last_dp_ms(self) -> float:
         """Device time of the banded-SWG kernels in the last align call (part of the extend time)."""
         return float(lib().tg_ctx_last_dp_ms(self._h))
+
+    def random_gather_gbs(self, n_loads: int = 1 << 26, reps: int = 5) -> float:
+        """HBM random-access yardstick: GB/s of 32-B sectors for independent random 16-B loads over the k-mer table."""
+        g, ms = C.c_double(), C.c_float()
+        _check(lib().tg_bench_random_gather(self._h, C.c_uint64(n_loads), reps, C.byref(g), C.byref(ms)))
+        return float(g.value)
 
     def last_kernel_launches(self) -> int:
         return int(lib().tg_ctx_last_kernel_launches(self._h))

@@ -876,6 +876,21 @@ __global__ void __launch_bounds__(128) k_swg_collect(SwgParams p) {
   }
 }
 
+// HBM random-access yardstick for the seeding roofline: every thread issues independent 16-B loads (one
+// 32-B sector each) at hashed positions of a table much larger than L2.
+__global__ void __launch_bounds__(256) k_random_gather(const uint4* __restrict__ table, uint64_t mask, uint32_t per_thread, uint32_t* sink) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t acc = 0;
+  for (uint32_t i = 0; i < per_thread; i += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = __ldg(table + (tg_mix64(tid * per_thread + i + u + 0x9e3779b97f4a7c15ULL) & mask));
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc ^= v[u].x ^ v[u].w;
+  }
+  if (acc == 0x12345678u) sink[0] = acc;  // keeps the loads alive
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------------------------------
@@ -1158,6 +1173,30 @@ void tg_ctx_debug_classes(const tg_ctx* ctx, uint32_t* out) {  // [TG_MAX_ROUNDS
   memcpy(out, ctx->h_ctr->round_cls, sizeof(ctx->h_ctr->round_cls));
 }
 float tg_ctx_last_dp_ms(const tg_ctx* ctx) { return ctx ? ctx->last_dp_ms : 0.f; }
+// Random 16-B gather rate over the context's own k-mer table (GB/s of 32-B sectors), best of `reps`.
+tg_status tg_bench_random_gather(tg_ctx* c, uint64_t n_loads, int reps, double* sector_gbs, float* best_ms) {
+  if (!c || !sector_gbs) return tg_fail(TG_ERR_INVALID, "null argument");
+  CU_CHECK(cudaSetDevice(c->ix->device));
+  uint32_t* sink = nullptr;
+  CU_CHECK(cudaMalloc(&sink, 64));
+  const uint32_t per_thread = 16;
+  const uint64_t threads = (n_loads + per_thread - 1) / per_thread;
+  const int blocks = (int)((threads + 255) / 256);
+  float best = 1e30f;
+  for (int r = 0; r < reps + 1; r++) {
+    CU_CHECK(cudaEventRecord(c->ev0, c->stream));
+    k_random_gather<<<blocks, 256, 0, c->stream>>>((const uint4*)c->slots, c->n_slots - 1, per_thread, sink);
+    CU_CHECK(cudaEventRecord(c->ev1, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CU_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaFree(sink);
+  *sector_gbs = 32.0 * (double)(threads * per_thread) / (best / 1e3) / 1e9;
+  if (best_ms) *best_ms = best;
+  return TG_OK;
+}
 uint64_t tg_ctx_last_kernel_launches(const tg_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots * sizeof(TgSlot) : 0; }
 
