@@ -133,6 +133,10 @@ void tg_index_destroy(tg_index* ix);
 typedef struct tg_ctx tg_ctx;
 tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out);
 void tg_ctx_destroy(tg_ctx* ctx);
+/* tg_align_batch copies the bases of a large batch in chunks of this many reads (default 262144) and seeds every chunk
+ * as soon as it has landed; at the other end the records of the reads that are finished after the second round travel to
+ * the host while the late rounds run.  Results do not depend on the chunk size. */
+void tg_ctx_set_chunk_reads(tg_ctx* ctx, uint32_t reads);
 /* The CUDA stream (cudaStream_t) all of the context's work is enqueued on. */
 void* tg_ctx_stream(tg_ctx* ctx);
 /* Device time (CUDA events on the context's stream) of the seeding and extension kernels of the last

@@ -91,6 +91,13 @@ def test_chrM_synthM_records():
     ores = oix.align_batch(bases, offs, k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True)
     _cmp(res, ores, n)
     assert res.count.sum() > 0.9 * n
+    # the same batch in overlapped chunks (H2D / kernels / D2H pipelined inside tg_align_batch): one contiguous result,
+    # identical records and counters
+    al.set_chunk_reads(1024)
+    res_c = al.align_reads(bases, offs)
+    _cmp(res_c, ores, n)
+    assert res_c.counters == res.counters
+    assert np.array_equal(res_c.count, res.count) and len(res_c.alns) == len(res.alns) and len(res_c.ops) == len(res.ops)
 
 
 def test_edge_reads():

@@ -70,7 +70,7 @@ ABI_SYMBOLS = [
     "tg_index_host_text_len", "tg_index_host_n_refs", "tg_index_host_n_txs", "tg_index_host_n_genes",
     "tg_index_host_ref", "tg_index_host_tx", "tg_index_host_gene_id", "tg_index_host_gene_name", "tg_index_host_sa",
     "tg_index_create", "tg_index_create_from_device_blob", "tg_index_destroy",
-    "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_bench_random_gather", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
+    "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_set_chunk_reads", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_bench_random_gather", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
     "tg_align_batch", "tg_align_batch_device", "tg_seed_batch", "tg_swg_extend_batch",
     "tg_format_sam_header", "tg_format_batch", "tg_parse_fastq", "tg_free",
 ]
@@ -97,6 +97,7 @@ def lib():
         L.tg_ctx_last_kernel_ms.restype = None
         L.tg_ctx_set_exact_cell_count.restype = None
         L.tg_ctx_set_round_pipeline.restype = None
+        L.tg_ctx_set_chunk_reads.restype = None
         L.tg_free.restype = None
         _LIB = L
     return _LIB
@@ -362,6 +363,10 @@ class Aligner:
     def set_round_pipeline(self, on: bool):
         """True (default): round pipeline (thread-per-read control + warp-per-task extension); False: single-warp kernel."""
         lib().tg_ctx_set_round_pipeline(self._h, int(on))
+
+    def set_chunk_reads(self, reads: int):
+        """Chunk size of align_reads on host buffers (copies of one chunk overlap the kernels of the next)."""
+        lib().tg_ctx_set_chunk_reads(self._h, C.c_uint32(reads))
 
     def last_dp_ms(self) -> float:
         """Device time of the banded-SWG kernels in the last align call (part of the extend time)."""

@@ -33,7 +33,7 @@
 #define TG_FINAL_SMALL 16u    // accepted alignments the thread-per-read finaliser sorts in local memory
 #define TG_NONE 0xFFFFFFFFu
 
-enum { TG_RS_DONE = 0, TG_RS_ACTIVE = 1, TG_RS_COMPLEX = 2 };
+enum { TG_RS_DONE = 0, TG_RS_ACTIVE = 1, TG_RS_COMPLEX = 2, TG_RS_FINAL = 3 /* records already written */ };
 enum { TG_IF_KEEP = 1, TG_IF_FAIL = 2 };
 enum { TG_FLAG_TASK_POOL = 32, TG_FLAG_ITEM_POOL = 64, TG_FLAG_HOPS_POOL = 128 };
 

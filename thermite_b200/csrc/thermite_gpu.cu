@@ -173,7 +173,8 @@ struct DevCounters {
   unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS][4];
   // task sorting for the thread-per-extension kernel: bins = class * TG_DPT_CBINS + column bucket
   uint32_t bin_count[TG_DPT_NBINS], bin_cursor[TG_DPT_NBINS];
-  uint32_t cls_start[TG_DPT_NCLS + 1], cls_chunk0[TG_DPT_NCLS + 1];
+  uint32_t cls_start[TG_DPT_NCLS + 1], cls_end[TG_DPT_NCLS + 1], cls_chunk0[TG_DPT_NCLS + 1];
+  uint32_t warp_tasks;  // sorted[0 .. warp_tasks): tasks for the warp-cooperative kernel
   uint32_t round_cls[TG_MAX_ROUNDS][TG_DPT_NCLS];  // debug: tasks per band class
 };
 
@@ -404,6 +405,7 @@ struct RoundParams {
   unsigned long long ops_cap;
   uint32_t* complex_list;
   uint32_t round;
+  int early;               // k_round_final: first pass (finished reads only)
   uint32_t* sorted;        // task indices of the round, grouped by class and (descending) column count
   uint32_t* dpt_trace;     // thread kernels: per class group, [warp][col][word][lane]
   size_t dpt_trace_off[4], dpt_trace_words[4];  // region of each group, words per warp
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_round_dp(RoundParams 
   uint8_t* trace = base; base += align16(p.trace_bytes);
   uint32_t* obuf = (uint32_t*)base;
   DevWarp w;
-  const uint32_t n_tasks = p.ctr->cls_start[1];  // class 0 = not eligible for the thread kernel
+  const uint32_t n_tasks = p.ctr->warp_tasks;  // not eligible for the thread kernel, or too few of their class
   for (;;) {
     uint32_t t = next_work(&p.ctr->round_work[p.round]);
     if (t >= n_tasks) break;
@@ -541,16 +543,26 @@ __global__ void __launch_bounds__(TG_BINSCAN_THREADS) k_round_binscan(RoundParam
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    // A class with few tasks cannot fill the GPU with one thread per extension and would hold the round for the
+    // latency of a single long task (a wide band is ~100 us on one thread): such classes join class 0 on the
+    // warp-cooperative kernel, which spreads one extension over 32 lanes.  Layout: class 0, small classes, big classes.
     uint32_t acc = 0, chunks = 0;
+    bool small[TG_DPT_NCLS];
     for (int c = 0; c < TG_DPT_NCLS; c++) {
-      cls_base[c] = acc;
-      p.ctr->cls_start[c] = acc;
-      p.ctr->cls_chunk0[c] = chunks;
+      const uint32_t thr = tg_dpt_wb(c) <= 32 ? 4096u : 8192u;
+      small[c] = c == 0 || cls_n[c] < thr;
       p.ctr->round_cls[p.round][c] = cls_n[c];
-      acc += cls_n[c];
-      if (c > 0) chunks += (cls_n[c] + 31) / 32;
     }
-    p.ctr->cls_start[TG_DPT_NCLS] = acc;
+    for (int c = 0; c < TG_DPT_NCLS; c++)
+      if (small[c]) { cls_base[c] = acc; acc += cls_n[c]; }
+    p.ctr->warp_tasks = acc;
+    for (int c = 0; c < TG_DPT_NCLS; c++) {
+      if (!small[c]) { cls_base[c] = acc; acc += cls_n[c]; }
+      p.ctr->cls_start[c] = cls_base[c];
+      p.ctr->cls_end[c] = cls_base[c] + cls_n[c];
+      p.ctr->cls_chunk0[c] = chunks;
+      if (!small[c]) chunks += (cls_n[c] + 31) / 32;
+    }
     p.ctr->cls_chunk0[TG_DPT_NCLS] = chunks;
   }
   __syncthreads();
@@ -651,7 +663,7 @@ __global__ void __launch_bounds__(128, DptGroup<G>::min_blocks) k_round_dpt(Roun
     int cls = DptGroup<G>::first;
     while (cls < DptGroup<G>::last && g >= p.ctr->cls_chunk0[cls + 1]) cls++;
     const uint32_t first = p.ctr->cls_start[cls] + (g - p.ctr->cls_chunk0[cls]) * 32u;
-    const uint32_t end = p.ctr->cls_start[cls + 1];
+    const uint32_t end = p.ctr->cls_end[cls];
     const bool active = first + lane < end;
     TgTask& t = p.tasks[active ? p.sorted[first + lane] : p.sorted[first]];
     if constexpr (G == 0) {
@@ -703,15 +715,19 @@ __global__ void __launch_bounds__(128) k_round_final(RoundParams p) {
   unsigned long long cells = 0, n_ext = 0, hits = 0;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
     const TgReadState st = p.st[r];
-    if (st.status == TG_RS_COMPLEX) continue;
-    if (st.status == TG_RS_ACTIVE) { mark_complex(p, r, 3); continue; }
+    if (st.status == TG_RS_COMPLEX || st.status == TG_RS_FINAL) continue;
+    if (st.status == TG_RS_ACTIVE) {
+      if (!p.early) mark_complex(p, r, 3);  // early pass: unfinished reads simply wait for the last one
+      continue;
+    }
+    p.st[r].status = TG_RS_FINAL;
     if (st.n_acc <= TG_FINAL_SMALL) {
       uint32_t items[TG_FINAL_SMALL];
       uint16_t order[TG_FINAL_SMALL], tmp[TG_FINAL_SMALL];
       tg_round_final<DevThread, uint16_t>(w, p.P, st, p.cands, p.ires, p.hp.w, items, order, tmp, p.out, r);
     } else {
       const unsigned long long base = warp_agg_add(&p.ctr->fin_used, 3ull * st.n_acc);
-      if (base + 3ull * st.n_acc > p.fin_cap) { mark_complex(p, r, 2); continue; }
+      if (base + 3ull * st.n_acc > p.fin_cap) { mark_complex(p, r, 2); continue; }  // (status becomes COMPLEX again)
       uint32_t* f = p.fin + base;
       tg_round_final<DevThread, uint32_t>(w, p.P, st, p.cands, p.ires, p.hp.w, f, f + st.n_acc, f + 2 * (size_t)st.n_acc, p.out, r);
     }
@@ -738,7 +754,7 @@ struct SwgParams {
   uint32_t max_xlen, max_cols, trace_bytes, ops_words;
   int bound_stop;
   DevCounters* ctr;
-  const uint32_t* list;  // when set: only the tasks list[0 .. ctr->cls_start[1]) (those the thread kernel cannot take)
+  const uint32_t* list;  // when set: only the tasks list[0 .. ctr->warp_tasks) (those the thread kernels do not take)
   // thread-kernel path: tasks in round-pipeline form, x as packed "reads", y as one packed text
   TgTask* tasks;
   uint64_t* xpk;
@@ -764,7 +780,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_swg_batch(SwgParams p
   for (;;) {
     uint32_t t = next_work(&p.ctr->work_swg);
     if (p.list) {
-      if (t >= p.ctr->cls_start[1]) break;
+      if (t >= p.ctr->warp_tasks) break;
       t = p.list[t];
     } else if (t >= p.n) break;
     const uint64_t x0 = p.xoff[t], y0 = p.yoff[t];
@@ -790,6 +806,7 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_swg_batch(SwgParams p
     if (lane == 0) {
       p.score[t] = res.score; p.xend[t] = (uint32_t)res.xend; p.yend[t] = (uint32_t)res.yend;
       p.task_off[t] = dst; p.task_len[t] = o.n;
+      if (p.list) p.tasks[t].pad0 = 1;  // done here: k_swg_collect must not take it
     }
     __syncwarp();
   }
@@ -929,6 +946,19 @@ struct PinBuf {
     cap = want;
     return TG_OK;
   }
+  // grow while keeping the first `keep` bytes (results of earlier chunks)
+  tg_status ensure_keep(size_t n, size_t keep) {
+    if (n <= cap) return TG_OK;
+    void* old = p;
+    size_t want = n + n / 2 + 256;
+    void* q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, want);
+    if (e != cudaSuccess) return tg_fail(TG_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    if (old && keep) memcpy(q, old, keep);
+    if (old) cudaFreeHost(old);
+    p = q; cap = want;
+    return TG_OK;
+  }
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
@@ -947,8 +977,8 @@ struct tg_ctx {
   tg_opts opts;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-  cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the band-class groups of a round's DP run concurrently
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // the band-class groups of a round's DP run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_dp0[TG_MAX_ROUNDS] = {}, ev_dp1[TG_MAX_ROUNDS] = {};  // DP section of every round (timing)
   int rounds_run = 0;
   float last_dp_ms = 0.f;
@@ -973,6 +1003,17 @@ struct tg_ctx {
   DevBuf r_state, r_hits, r_ires, r_cands, r_hops, r_fin, r_rp, r_tasks, r_ops, r_complex, r_sorted, r_dpt_trace;
   uint64_t round_task_cap = 0, round_ops_cap = 0, item_cap = 0, hops_cap = 0;
   int use_rounds = 1;
+  // chunked host-buffer path: results of chunk k start at these pool positions / read row
+  unsigned long long base_alns = 0, base_ops = 0;
+  uint32_t out_row0 = 0;
+  uint32_t pool_reads = 0;  // reads the output pools are sized for (the whole batch when chunking)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  int early_out = 0;                 // host-buffer path: records of reads finished after round 1 go to the host early
+  unsigned long long* h_snap = nullptr;  // pinned {alns_used, ops_used} after the early final pass
+  unsigned long long early_alns = 0, early_ops = 0;  // what has been sent to the host already
+  uint32_t in_chunks = 0, in_chunk_reads = 0;        // host-buffer path: seeding follows the input copies chunk by chunk
+  std::vector<cudaEvent_t> ev_in;
+  uint32_t chunk_reads = 262144;
   uint64_t n_launches = 0;  // kernels launched by the last batch call
   // host results
   PinBuf h_first, h_count, h_alns, h_ops, h_seeds, h_seed_first, h_seed_count;
@@ -1087,8 +1128,12 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (c->ev2) cudaEventDestroy(c->ev2);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (int i = 0; i < TG_MAX_ROUNDS; i++) { if (c->ev_dp0[i]) cudaEventDestroy(c->ev_dp0[i]); if (c->ev_dp1[i]) cudaEventDestroy(c->ev_dp1[i]); }
-  for (int i = 0; i < 3; i++) { if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); if (c->side[i]) cudaStreamDestroy(c->side[i]); }
+  for (int i = 0; i < 4; i++) { if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); if (c->side[i]) cudaStreamDestroy(c->side[i]); }
   if (c->h_active) cudaFreeHost(c->h_active);
+  if (c->h_snap) cudaFreeHost(c->h_snap);
+  for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
+  if (c->copy_out) cudaStreamDestroy(c->copy_out);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1114,11 +1159,14 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
   CTX_CHECK(cudaEventCreate(&c->ev1));
   CTX_CHECK(cudaEventCreate(&c->ev2));
   CTX_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < 4; i++) {
     CTX_CHECK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
     CTX_CHECK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
   }
   CTX_CHECK(cudaMallocHost(&c->h_active, sizeof(unsigned long long)));
+  CTX_CHECK(cudaMallocHost(&c->h_snap, 2 * sizeof(unsigned long long)));
+  CTX_CHECK(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  CTX_CHECK(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
   for (int i = 0; i < TG_MAX_ROUNDS; i++) { CTX_CHECK(cudaEventCreate(&c->ev_dp0[i])); CTX_CHECK(cudaEventCreate(&c->ev_dp1[i])); }
   CTX_CHECK(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, ix->device));
   CTX_CHECK(cudaMalloc(&c->d_ctr, sizeof(DevCounters)));
@@ -1146,6 +1194,9 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
   return TG_OK;
 }
 
+void tg_ctx_set_chunk_reads(tg_ctx* ctx, uint32_t reads) {
+  if (ctx) ctx->chunk_reads = reads < 1024 ? 1024 : reads;
+}
 void* tg_ctx_stream(tg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms) {
@@ -1204,18 +1255,21 @@ uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots 
 
 namespace {
 
-tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL) {
+// seeding of the reads [r0, r0 + nk) of a batch of n reads (the whole batch when nk == n)
+tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL, uint32_t r0 = 0,
+                      uint32_t nk = 0xFFFFFFFFu) {
+  if (nk == 0xFFFFFFFFu) nk = n;
   SeedParams p;
-  p.bases = d_bases; p.offs = d_offs; p.n_reads = n; p.k = c->opts.min_seed_len; p.max_len = maxL;
+  p.bases = d_bases; p.offs = d_offs + r0; p.n_reads = nk; p.k = c->opts.min_seed_len; p.max_len = maxL;
   p.max_q = maxL >= p.k ? maxL - p.k + 1 : 1;
   p.rp_words = maxL / 16 + 4;
   tg_status st;
   if ((st = c->r_rp.ensure((size_t)n * p.rp_words * 8)) != TG_OK) return st;
   if ((st = c->d_probe.ensure((size_t)n * p.max_q * sizeof(TgSeedHit))) != TG_OK) return st;
   p.slots = c->slots; p.slot_mask = c->n_slots - 1; p.text4 = c->ix->dev.text4; p.sa = c->ix->dev.sa;
-  p.rp = (uint64_t*)c->r_rp.p; p.hits = (TgSeedHit*)c->d_probe.p; p.wave = 0;
+  p.rp = (uint64_t*)c->r_rp.p + (size_t)r0 * p.rp_words; p.hits = (TgSeedHit*)c->d_probe.p + (size_t)r0 * p.max_q; p.wave = 0;
   p.out.pool = (tg_seed*)c->d_seeds.p; p.out.pool_used = &c->d_ctr->seed_used; p.out.pool_cap = c->seed_cap;
-  p.out.read_first = (uint64_t*)c->d_seed_first.p; p.out.read_count = (uint32_t*)c->d_seed_count.p;
+  p.out.read_first = (uint64_t*)c->d_seed_first.p + r0; p.out.read_count = (uint32_t*)c->d_seed_count.p + r0;
   p.out.flags = &c->d_ctr->flags; p.out.n_smems = &c->d_ctr->n_smems;
   p.ctr = c->d_ctr;
   const int grid = c->n_sms * 8;
@@ -1228,7 +1282,7 @@ tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs,
     k_seed_probe<<<grid, 256, 0, c->stream>>>(p);
     c->n_launches += 2;
   }
-  k_seed_select<<<(int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16), 128, 0, c->stream>>>(p);
+  k_seed_select<<<(int)std::min<uint64_t>(((uint64_t)nk + 127) / 128, (uint64_t)c->n_sms * 16), 128, 0, c->stream>>>(p);
   c->n_launches += 3;
   CU_CHECK(cudaGetLastError());
   return TG_OK;
@@ -1274,7 +1328,7 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.cands = (TgCand*)c->d_cands.p; p.arena = (uint32_t*)c->d_arena.p; p.arena_cap = arena_cap; p.order = (uint16_t*)c->d_order.p;
   p.bound_stop = c->exact_cells ? 0 : 1;
   p.read_list = read_list;
-  p.out.read_aln_first = (uint64_t*)c->d_aln_first.p; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p;
+  p.out.read_aln_first = (uint64_t*)c->d_aln_first.p + c->out_row0; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p + c->out_row0;
   p.out.alns = (tg_aln*)c->d_alns.p; p.out.ops = (uint32_t*)c->d_ops.p;
   p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;
   p.out.alns_cap = c->alns_cap; p.out.ops_cap = c->ops_cap; p.out.flags = &c->d_ctr->flags;
@@ -1309,22 +1363,25 @@ tg_status dpt_geometry(tg_ctx* c, RoundParams& p, uint32_t max_cols, uint64_t ta
   return TG_OK;
 }
 
-// sort the tasks of round p.round by band class and run the thread-per-extension kernels (class groups concurrently)
-tg_status launch_dpt(tg_ctx* c, RoundParams& p, const int grid[4]) {
+// sort the tasks of round p.round by band class and run the thread-per-extension kernels and the warp-cooperative kernel
+// (`warp_launch`, for what the thread kernels do not take) concurrently on the context's side streams
+template <class WarpLaunch>
+tg_status launch_dpt(tg_ctx* c, RoundParams& p, const int grid[4], WarpLaunch&& warp_launch) {
   k_round_hist<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
   k_round_binscan<<<1, TG_BINSCAN_THREADS, 0, c->stream>>>(p);
   k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
   CU_CHECK(cudaEventRecord(c->ev_fork, c->stream));
-  for (int i = 0; i < 3; i++) CU_CHECK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+  for (int i = 0; i < 4; i++) CU_CHECK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
   k_round_dpt<3><<<grid[3], 128, 0, c->side[0]>>>(p);
   k_round_dpt<2><<<grid[2], 128, 0, c->side[1]>>>(p);
   k_round_dpt<1><<<grid[1], 128, 0, c->side[2]>>>(p);
+  warp_launch(c->side[3]);
   k_round_dpt<0><<<grid[0], 128, 0, c->stream>>>(p);
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < 4; i++) {
     CU_CHECK(cudaEventRecord(c->ev_join[i], c->side[i]));
     CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
   }
-  c->n_launches += 7;
+  c->n_launches += 8;
   return TG_OK;
 }
 
@@ -1361,10 +1418,10 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.fin = (uint32_t*)c->r_fin.p; p.fin_cap = c->item_cap * 3;
   p.tasks = (TgTask*)c->r_tasks.p; p.task_cap = c->round_task_cap;
   p.ops_pool = (uint32_t*)c->r_ops.p; p.ops_cap = c->round_ops_cap;
-  p.complex_list = (uint32_t*)c->r_complex.p; p.round = 0;
+  p.complex_list = (uint32_t*)c->r_complex.p; p.round = 0; p.early = 0;
   p.max_xlen = max_xlen; p.max_cols = max_cols; p.trace_bytes = trace_bytes; p.ops_words = ops_words;
   p.bound_stop = c->exact_cells ? 0 : 1;
-  p.out.read_aln_first = (uint64_t*)c->d_aln_first.p; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p;
+  p.out.read_aln_first = (uint64_t*)c->d_aln_first.p + c->out_row0; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p + c->out_row0;
   p.out.alns = (tg_aln*)c->d_alns.p; p.out.ops = (uint32_t*)c->d_ops.p;
   p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;
   p.out.alns_cap = c->alns_cap; p.out.ops_cap = c->ops_cap; p.out.flags = &c->d_ctr->flags;
@@ -1387,8 +1444,6 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   // thread-per-extension kernel: geometry, trace scratch, sorted task list
   int dpt_grid[4];
   if ((st = dpt_geometry(c, p, std::min<uint32_t>(max_xlen, TG_DPT_MAX_X) + max_bw + 1, c->round_task_cap, dpt_grid)) != TG_OK) return st;
-  // tasks the thread kernel cannot take (long reads, very wide bands) exist only for such inputs
-  const bool need_warp_kernel = max_xlen > TG_DPT_MAX_X || std::min<uint32_t>(2 * max_bw, max_xlen) + 1 > TG_DPT_MAX_WB;
   k_round_init<<<tblocks, 128, 0, c->stream>>>(p);
   c->n_launches++;
   for (uint32_t r = 0; r < TG_MAX_ROUNDS; r++) {
@@ -1396,13 +1451,29 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
     k_round_plan<<<tblocks, 128, 0, c->stream>>>(p);
     k_round_prep<<<iblocks, 128, 0, c->stream>>>(p);
     CU_CHECK(cudaEventRecord(c->ev_dp0[r], c->stream));
-    if ((st = launch_dpt(c, p, dpt_grid)) != TG_OK) return st;
-    if (need_warp_kernel) { kdp<<<dp_blocks, wpc * 32, smem, c->stream>>>(p); c->n_launches++; }
+    if ((st = launch_dpt(c, p, dpt_grid, [&](cudaStream_t s2) { kdp<<<dp_blocks, wpc * 32, smem, s2>>>(p); })) != TG_OK) return st;
     CU_CHECK(cudaEventRecord(c->ev_dp1[r], c->stream));
     c->rounds_run = (int)r + 1;
     k_round_post<<<iblocks, 128, 0, c->stream>>>(p);
     k_round_scan<<<tblocks, 128, 0, c->stream>>>(p);
     c->n_launches += 4;
+    if (r == 1 && c->early_out) {
+      // ~98 % of the reads are finished now: write their records and start moving them to the host while the late
+      // rounds (few reads, many hits each) run
+      p.early = 1;
+      k_round_final<<<tblocks, 128, 0, c->stream>>>(p);
+      p.early = 0;
+      c->n_launches++;
+      CU_CHECK(cudaMemcpyAsync(c->h_snap, &c->d_ctr->alns_used, 16, cudaMemcpyDeviceToHost, c->stream));
+      CU_CHECK(cudaStreamSynchronize(c->stream));
+      const unsigned long long a1 = std::min<unsigned long long>(c->h_snap[0], c->alns_cap), o1 = std::min<unsigned long long>(c->h_snap[1], c->ops_cap);
+      CU_CHECK(cudaStreamSynchronize(c->copy_out));  // (idle unless an earlier attempt of this batch was abandoned)
+      if ((st = c->h_alns.ensure((size_t)(a1 + a1 / 16 + 65536) * sizeof(tg_aln))) != TG_OK) return st;
+      if ((st = c->h_ops.ensure((size_t)(o1 + o1 / 16 + 262144) * 4)) != TG_OK) return st;
+      if (a1) CU_CHECK(cudaMemcpyAsync(c->h_alns.p, c->d_alns.p, (size_t)a1 * sizeof(tg_aln), cudaMemcpyDeviceToHost, c->copy_out));
+      if (o1) CU_CHECK(cudaMemcpyAsync(c->h_ops.p, c->d_ops.p, (size_t)o1 * 4, cudaMemcpyDeviceToHost, c->copy_out));
+      c->early_alns = a1; c->early_ops = o1;
+    }
     // late rounds are short: a host check for "nothing left" costs less than launching the remaining empty rounds
     if (r >= 3 && r + 1 < TG_MAX_ROUNDS) {
       CU_CHECK(cudaMemcpyAsync(c->h_active, &c->d_ctr->round_active[r], sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -1418,15 +1489,16 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
 }
 
 tg_status ensure_pools(tg_ctx* c, uint32_t n) {
+  const uint32_t np = std::max(n, c->pool_reads);  // output pools hold the whole batch when it is processed in chunks
   if (c->seed_cap < (uint64_t)n * 4 + 4096) c->seed_cap = (uint64_t)n * 4 + 4096;
-  if (c->alns_cap < (uint64_t)n * 2 + 4096) c->alns_cap = (uint64_t)n * 2 + 4096;
-  if (c->ops_cap < (uint64_t)n * 24 + 65536) c->ops_cap = (uint64_t)n * 24 + 65536;
+  if (c->alns_cap < (uint64_t)np * 2 + 4096) c->alns_cap = (uint64_t)np * 2 + 4096;
+  if (c->ops_cap < (uint64_t)np * 24 + 65536) c->ops_cap = (uint64_t)np * 24 + 65536;
   tg_status st;
   if ((st = c->d_seeds.ensure(c->seed_cap * sizeof(tg_seed))) != TG_OK) return st;
   if ((st = c->d_seed_first.ensure((size_t)n * 8 + 8)) != TG_OK) return st;
   if ((st = c->d_seed_count.ensure((size_t)n * 4 + 4)) != TG_OK) return st;
-  if ((st = c->d_aln_first.ensure((size_t)n * 8 + 8)) != TG_OK) return st;
-  if ((st = c->d_aln_count.ensure((size_t)n * 4 + 4)) != TG_OK) return st;
+  if ((st = c->d_aln_first.ensure((size_t)np * 8 + 8)) != TG_OK) return st;
+  if ((st = c->d_aln_count.ensure((size_t)np * 4 + 4)) != TG_OK) return st;
   if ((st = c->d_alns.ensure(c->alns_cap * sizeof(tg_aln))) != TG_OK) return st;
   if ((st = c->d_ops.ensure(c->ops_cap * 4)) != TG_OK) return st;
   return TG_OK;
@@ -1434,13 +1506,27 @@ tg_status ensure_pools(tg_ctx* c, uint32_t n) {
 
 // seeds (+ optionally extension) with pool-overflow retry; leaves the counters in c->h_ctr
 tg_status run_pipeline(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL, bool extend) {
-  c->n_launches = 0;
   for (int attempt = 0; attempt < 8; attempt++) {
     tg_status st = ensure_pools(c, n);
     if (st != TG_OK) return st;
     CU_CHECK(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+    if (c->base_alns || c->base_ops) {  // a later chunk of a batch: its records continue the pools (alns_used, ops_used adjacent)
+      static_assert(offsetof(DevCounters, ops_used) == offsetof(DevCounters, alns_used) + 8, "counter layout");
+      const unsigned long long bases2[2] = {c->base_alns, c->base_ops};
+      CU_CHECK(cudaMemcpyAsync(&c->d_ctr->alns_used, bases2, 16, cudaMemcpyHostToDevice, c->stream));
+    }
     CU_CHECK(cudaEventRecord(c->ev0, c->stream));
-    if ((st = launch_seed(c, d_bases, d_offs, n, maxL)) != TG_OK) return st;
+    c->early_alns = 0; c->early_ops = 0;
+    if (c->in_chunks > 1 && attempt == 0) {
+      for (uint32_t k = 0; k < c->in_chunks; k++) {  // seed chunk k as soon as its bases have arrived
+        const uint32_t r0 = k * c->in_chunk_reads, nk = std::min(n, r0 + c->in_chunk_reads) - r0;
+        CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        if ((st = launch_seed(c, d_bases, d_offs, n, maxL, r0, nk)) != TG_OK) return st;
+      }
+    } else {
+      if (c->in_chunks && attempt == 0) CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
+      if ((st = launch_seed(c, d_bases, d_offs, n, maxL)) != TG_OK) return st;
+    }
     CU_CHECK(cudaEventRecord(c->ev1, c->stream));
     if (extend && (st = (c->use_rounds ? launch_rounds(c, d_bases, d_offs, n, maxL) : launch_extend(c, d_bases, d_offs, n, maxL))) != TG_OK) return st;
     CU_CHECK(cudaEventRecord(c->ev2, c->stream));
@@ -1520,6 +1606,7 @@ tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint6
   if (max_read_len > TG_MAX_READ_LEN) return tg_fail(TG_ERR_INVALID, "read longer than TG_MAX_READ_LEN");
   memset(out, 0, sizeof(*out));
   if (n_reads == 0) return TG_OK;
+  ctx->n_launches = 0;
   if ((st = run_pipeline(ctx, d_bases, d_offs, n_reads, std::max(max_read_len, 1u), true)) != TG_OK) return st;
   fill_result(ctx, n_reads, out);
   out->read_aln_first = (const uint64_t*)ctx->d_aln_first.p;
@@ -1535,26 +1622,65 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
   memset(out, 0, sizeof(*out));
   if (n_reads == 0) return TG_OK;
   if (!bases && offs[n_reads] > 0) return tg_fail(TG_ERR_INVALID, "null argument");
-  uint32_t maxL = 0;
-  if ((st = upload_reads(ctx, bases, offs, n_reads, &maxL)) != TG_OK) return st;
-  if ((st = run_pipeline(ctx, (const uint8_t*)ctx->d_bases.p, (const uint64_t*)ctx->d_offs.p, n_reads, std::max(maxL, 1u), true)) != TG_OK)
-    return st;
-  fill_result(ctx, n_reads, out);
-  if ((st = ctx->h_first.ensure((size_t)n_reads * 8)) != TG_OK) return st;
-  if ((st = ctx->h_count.ensure((size_t)n_reads * 4)) != TG_OK) return st;
-  if ((st = ctx->h_alns.ensure((size_t)out->n_alns * sizeof(tg_aln) + 16)) != TG_OK) return st;
-  if ((st = ctx->h_ops.ensure((size_t)out->n_ops * 4 + 16)) != TG_OK) return st;
-  CU_CHECK(cudaMemcpyAsync(ctx->h_first.p, ctx->d_aln_first.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_CHECK(cudaMemcpyAsync(ctx->h_count.p, ctx->d_aln_count.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (out->n_alns)
-    CU_CHECK(cudaMemcpyAsync(ctx->h_alns.p, ctx->d_alns.p, (size_t)out->n_alns * sizeof(tg_aln), cudaMemcpyDeviceToHost, ctx->stream));
-  if (out->n_ops)
-    CU_CHECK(cudaMemcpyAsync(ctx->h_ops.p, ctx->d_ops.p, (size_t)out->n_ops * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_CHECK(cudaStreamSynchronize(ctx->stream));
-  out->read_aln_first = (const uint64_t*)ctx->h_first.p;
-  out->read_aln_count = (const uint32_t*)ctx->h_count.p;
-  out->alns = (const tg_aln*)ctx->h_alns.p;
-  out->ops = (const uint32_t*)ctx->h_ops.p;
+  tg_ctx* c = ctx;
+  // Copies overlap kernels at both ends of the call (three streams): the bases arrive in chunks and every chunk is
+  // seeded as soon as it has landed; the records of the reads that are finished after round 1 (~98 %) travel to the
+  // host while the late rounds run.  One pass over the whole batch, one contiguous result.
+  const uint32_t chunk = n_reads >= 2 * c->chunk_reads ? c->chunk_reads : n_reads;
+  const uint32_t n_chunks = (n_reads + chunk - 1) / chunk;
+  const uint64_t total = offs[n_reads];
+  if ((st = c->d_bases.ensure(total + 64)) != TG_OK) return st;
+  if ((st = c->d_offs.ensure((size_t)(n_reads + 1) * 8)) != TG_OK) return st;
+  while (c->ev_in.size() < n_chunks) {
+    cudaEvent_t e;
+    CU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_in.push_back(e);
+  }
+  CU_CHECK(cudaMemcpyAsync(c->d_offs.p, offs, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, c->copy_in));
+  uint32_t maxL = 1;
+  for (uint32_t k = 0; k < n_chunks; k++) {
+    const uint32_t r0 = k * chunk, r1 = std::min(n_reads, r0 + chunk);
+    for (uint32_t r = r0; r < r1; r++) {  // validate while earlier copies are in flight
+      if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > TG_MAX_READ_LEN) {
+        cudaStreamSynchronize(c->copy_in);
+        return tg_fail(TG_ERR_INVALID, offs[r + 1] < offs[r] ? "read offsets must be non-decreasing" : "read longer than TG_MAX_READ_LEN");
+      }
+      maxL = std::max<uint32_t>(maxL, (uint32_t)(offs[r + 1] - offs[r]));
+    }
+    const uint64_t b0 = offs[r0], b1 = offs[r1];
+    if (b1 > b0) CU_CHECK(cudaMemcpyAsync((uint8_t*)c->d_bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_in));
+    CU_CHECK(cudaEventRecord(c->ev_in[k], c->copy_in));
+  }
+  // maxL of the whole batch is needed before the first kernel: the loop above has run over every read by now
+  if ((st = c->h_first.ensure((size_t)n_reads * 8)) != TG_OK) return st;
+  if ((st = c->h_count.ensure((size_t)n_reads * 4)) != TG_OK) return st;
+  c->n_launches = 0;
+  c->in_chunks = n_chunks; c->in_chunk_reads = chunk;
+  c->early_out = c->use_rounds ? 1 : 0;
+  st = run_pipeline(c, (const uint8_t*)c->d_bases.p, (const uint64_t*)c->d_offs.p, n_reads, maxL, true);
+  c->in_chunks = 0; c->early_out = 0;
+  if (st != TG_OK) { cudaStreamSynchronize(c->copy_out); return st; }
+  fill_result(c, n_reads, out);
+  const uint64_t ea = std::min<uint64_t>(c->early_alns, out->n_alns), eo = std::min<uint64_t>(c->early_ops, out->n_ops);
+  if (out->n_alns * sizeof(tg_aln) + 16 > c->h_alns.cap || out->n_ops * 4 + 16 > c->h_ops.cap) {
+    CU_CHECK(cudaStreamSynchronize(c->copy_out));  // the early part has landed before the buffers move
+    if ((st = c->h_alns.ensure_keep((size_t)out->n_alns * sizeof(tg_aln) + 16, ea * sizeof(tg_aln))) != TG_OK) return st;
+    if ((st = c->h_ops.ensure_keep((size_t)out->n_ops * 4 + 16, eo * 4)) != TG_OK) return st;
+  }
+  CU_CHECK(cudaMemcpyAsync(c->h_first.p, c->d_aln_first.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaMemcpyAsync(c->h_count.p, c->d_aln_count.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (out->n_alns > ea)
+    CU_CHECK(cudaMemcpyAsync((tg_aln*)c->h_alns.p + ea, (tg_aln*)c->d_alns.p + ea, (size_t)(out->n_alns - ea) * sizeof(tg_aln),
+                             cudaMemcpyDeviceToHost, c->stream));
+  if (out->n_ops > eo)
+    CU_CHECK(cudaMemcpyAsync((uint32_t*)c->h_ops.p + eo, (uint32_t*)c->d_ops.p + eo, (size_t)(out->n_ops - eo) * 4,
+                             cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->copy_out));
+  out->read_aln_first = (const uint64_t*)c->h_first.p;
+  out->read_aln_count = (const uint32_t*)c->h_count.p;
+  out->alns = (const tg_aln*)c->h_alns.p;
+  out->ops = (const uint32_t*)c->h_ops.p;
   return TG_OK;
 }
 
@@ -1566,6 +1692,7 @@ tg_status tg_seed_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs,
   if (!bases && offs[n_reads] > 0) return tg_fail(TG_ERR_INVALID, "null argument");
   uint32_t maxL = 0;
   if ((st = upload_reads(ctx, bases, offs, n_reads, &maxL)) != TG_OK) return st;
+  ctx->n_launches = 0;
   if ((st = run_pipeline(ctx, (const uint8_t*)ctx->d_bases.p, (const uint64_t*)ctx->d_offs.p, n_reads, std::max(maxL, 1u), false)) != TG_OK)
     return st;
   uint64_t ns = ctx->h_ctr->seed_used;
@@ -1675,11 +1802,10 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
     CU_CHECK(cudaMemcpyAsync(&c->d_ctr->round_tasks[0], &n_tasks, sizeof(n_tasks), cudaMemcpyHostToDevice, c->stream));
     const int tb = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16);
     k_swg_prepare<<<tb, 128, 0, c->stream>>>(p);
-    if ((st = launch_dpt(c, rp, grid)) != TG_OK) return st;
     p.list = rp.sorted;
-    kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
+    if ((st = launch_dpt(c, rp, grid, [&](cudaStream_t s2) { kern<<<blocks, wpc * 32, smem, s2>>>(p); })) != TG_OK) return st;
     k_swg_collect<<<tb, 128, 0, c->stream>>>(p);
-    c->n_launches += 3;
+    c->n_launches += 2;
   }
   CU_CHECK(cudaGetLastError());
   CU_CHECK(cudaEventRecord(c->ev1, c->stream));
