@@ -150,12 +150,16 @@ TG_HD uint32_t tg_lcp_from(const uint64_t* rp, uint32_t q, uint32_t L, const uin
   return maxl;
 }
 
-TG_HD void tg_seed_offset(const uint64_t* rp, uint32_t L, uint32_t q, uint32_t k, const TgSlot* slots,
+// DEFER: return false (out untouched) instead of searching when the k-mer occurs more than once -- the device runs
+// those probes in a second kernel so that a warp holds either cheap single-occurrence probes or searches, not a mix.
+template <bool DEFER = false>
+TG_HD bool tg_seed_offset(const uint64_t* rp, uint32_t L, uint32_t q, uint32_t k, const TgSlot* slots,
                           uint64_t slot_mask, const uint64_t* text4, const uint32_t* sa, TgSeedHit& out) {
-  out.e = 0; out.lo = 0; out.cnt = 0;
+  if (!DEFER) { out.e = 0; out.lo = 0; out.cnt = 0; }
+  TgSeedHit none{0, 0, 0};
   uint64_t w0 = tg_ld16_local(rp, q) & tg_top_nibbles(k);
   uint64_t w1 = k > 16 ? (tg_ld16_local(rp, q + 16) & tg_top_nibbles(k - 16)) : 0;
-  if (tg_has_bad_symbol(w0) || tg_has_bad_symbol(w1)) return;
+  if (tg_has_bad_symbol(w0) || tg_has_bad_symbol(w1)) { out = none; return true; }
   uint64_t h = tg_hash_kmer(w0, w1);
   uint32_t tag = tg_tag_of(h);
   uint64_t idx = h & slot_mask;
@@ -166,13 +170,14 @@ TG_HD void tg_seed_offset(const uint64_t* rp, uint32_t L, uint32_t q, uint32_t k
 #else
     TgSlot s = slots[idx];
 #endif
-    if (s.tag == 0) return;
+    if (s.tag == 0) { out = none; return true; }
     if (s.tag == tag) {
       bool le;
       if (s.count == 1) {
         uint32_t l = tg_lcp(rp, q, L, text4, s.lo, &le);
-        if (l >= k) { out.e = q + l; out.lo = s.lo; out.cnt = 1u | TG_DIRECT; return; }
+        if (l >= k) { out.e = q + l; out.lo = s.lo; out.cnt = 1u | TG_DIRECT; return true; }
       } else {
+        if (DEFER) return false;
         // All rows of the group share their first k symbols; one row tells whether they are the read's k-mer (a tag
         // collision is a different k-mer).  Then: first row whose suffix is >= the read suffix, by binary search that
         // only compares beyond the prefix both current bounds are known to share with the read.
@@ -233,7 +238,7 @@ TG_HD void tg_seed_offset(const uint64_t* rp, uint32_t L, uint32_t q, uint32_t k
             }
           }
           out.e = q + best; out.lo = left; out.cnt = right - left;
-          return;
+          return true;
         }
       }
     }

@@ -167,6 +167,7 @@ struct DevCounters {
   unsigned long long phase[16];
   // round pipeline
   unsigned long long n_complex, work_complex;
+  unsigned long long probe_n[3][2];  // per probe wave: queued probes, deferred (multi-occurrence) probes
   unsigned long long items_used, hops_used, fin_used;
   unsigned long long round_end[TG_MAX_ROUNDS];  // items_used after round r
   unsigned long long round_active[TG_MAX_ROUNDS];  // reads still unfinished after round r
@@ -241,6 +242,8 @@ struct SeedParams {
   const uint32_t* sa;
   uint64_t* rp;        // [n_reads][rp_words] packed reads (also used by the extension stage)
   TgSeedHit* hits;     // [n_reads][max_q]
+  uint64_t* queue;     // probes of the current wave: read << 16 | offset
+  uint64_t* queue2;    // the ones whose k-mer occurs more than once
   int wave;            // 0: offset 0 of every read; 1: the other offsets, skipped when the whole read matched at 0
   TgSeedOut out;
   DevCounters* ctr;
@@ -257,9 +260,15 @@ __global__ void __launch_bounds__(256) k_pack_reads(SeedParams p) {
   }
 }
 
-// E(q): one thread per (read, offset), in the three waves of tg_core.h (TG_PROBE_STRIDE).  Consecutive threads probe
-// consecutive offsets of a read: their k-mer slots are random HBM accesses, their text verifications share sectors.
-__global__ void __launch_bounds__(256) k_seed_probe(SeedParams p) {
+// E(q) in the three waves of tg_core.h (TG_PROBE_STRIDE), two kernels per wave:
+//   light  one thread per candidate (read, offset): skip rules, hash, slot, verification of a single-occurrence k-mer;
+//          k-mers that occur more than once are queued
+//   heavy  one thread per queued probe: the suffix-array searches, 32 real searches per warp instead of a few live
+//          lanes holding a warp of finished ones
+__device__ __forceinline__ void probe_push(unsigned long long* ctr, uint64_t* queue, uint32_t r, uint32_t q) {
+  queue[warp_agg_add(ctr, 1ull)] = ((uint64_t)r << 16) | q;
+}
+__global__ void __launch_bounds__(256) k_probe_light(SeedParams p) {
   const uint32_t qn = p.wave == 0 ? 1u : p.wave == 1 ? (p.max_q + TG_PROBE_STRIDE - 1) / TG_PROBE_STRIDE : p.max_q - 1;
   const unsigned long long total = (unsigned long long)p.n_reads * qn;
   for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
@@ -280,8 +289,21 @@ __global__ void __launch_bounds__(256) k_seed_probe(SeedParams p) {
       }
     }
     TgSeedHit h;
-    tg_seed_offset(p.rp + (size_t)r * p.rp_words, L, q, p.k, p.slots, p.slot_mask, p.text4, p.sa, h);
-    row[q] = h;
+    if (tg_seed_offset<true>(p.rp + (size_t)r * p.rp_words, L, q, p.k, p.slots, p.slot_mask, p.text4, p.sa, h))
+      row[q] = h;
+    else
+      probe_push(&p.ctr->probe_n[p.wave][1], p.queue2, r, q);
+  }
+}
+__global__ void __launch_bounds__(256) k_probe_heavy(SeedParams p) {
+  const unsigned long long total = p.ctr->probe_n[p.wave][1];
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint64_t e = p.queue2[t];
+    const uint32_t r = (uint32_t)(e >> 16), q = (uint32_t)(e & 0xFFFFu);
+    const uint32_t L = (uint32_t)(p.offs[r + 1] - p.offs[r]);
+    TgSeedHit h;
+    tg_seed_offset<false>(p.rp + (size_t)r * p.rp_words, L, q, p.k, p.slots, p.slot_mask, p.text4, p.sa, h);
+    p.hits[(size_t)r * p.max_q + q] = h;
   }
 }
 
@@ -993,7 +1015,7 @@ struct tg_ctx {
   // inputs
   DevBuf d_bases, d_offs;
   // seeding
-  DevBuf d_seeds, d_seed_first, d_seed_count, d_probe;
+  DevBuf d_seeds, d_seed_first, d_seed_count, d_probe, d_queue, d_queue2;
   uint64_t seed_cap = 0;
   // extension
   DevBuf d_cands, d_arena, d_order, d_aln_first, d_aln_count, d_alns, d_ops;
@@ -1115,7 +1137,7 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->ix->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_probe, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_ires, &c->r_cands, &c->r_hops, &c->r_fin, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex, &c->r_sorted, &c->r_dpt_trace,
+  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_probe, &c->d_queue, &c->d_queue2, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_ires, &c->r_cands, &c->r_hops, &c->r_fin, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex, &c->r_sorted, &c->r_dpt_trace,
                     &c->d_aln_first, &c->d_aln_count, &c->d_alns, &c->d_ops, &c->s_x, &c->s_xo, &c->s_y, &c->s_yo, &c->s_bw,
                     &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops, &c->s_ypk, &c->s_ysym})
     b->release();
@@ -1272,16 +1294,18 @@ tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs,
   p.out.read_first = (uint64_t*)c->d_seed_first.p + r0; p.out.read_count = (uint32_t*)c->d_seed_count.p + r0;
   p.out.flags = &c->d_ctr->flags; p.out.n_smems = &c->d_ctr->n_smems;
   p.ctr = c->d_ctr;
+  if ((st = c->d_queue2.ensure((size_t)nk * p.max_q * 8 + 64)) != TG_OK) return st;
+  p.queue = nullptr; p.queue2 = (uint64_t*)c->d_queue2.p;
   const int grid = c->n_sms * 8;
   k_pack_reads<<<grid, 256, 0, c->stream>>>(p);
-  k_seed_probe<<<grid, 256, 0, c->stream>>>(p);
-  if (p.max_q > 1) {
-    p.wave = 1;
-    k_seed_probe<<<grid, 256, 0, c->stream>>>(p);
-    p.wave = 2;
-    k_seed_probe<<<grid, 256, 0, c->stream>>>(p);
+  for (int wave = 0; wave < (p.max_q > 1 ? 3 : 1); wave++) {
+    p.wave = wave;
+    if (r0 != 0) CU_CHECK(cudaMemsetAsync(&c->d_ctr->probe_n[wave][0], 0, 16, c->stream));  // a later chunk of the batch
+    k_probe_light<<<grid, 256, 0, c->stream>>>(p);
+    k_probe_heavy<<<grid, 256, 0, c->stream>>>(p);
     c->n_launches += 2;
   }
+  c->n_launches -= 1;
   k_seed_select<<<(int)std::min<uint64_t>(((uint64_t)nk + 127) / 128, (uint64_t)c->n_sms * 16), 128, 0, c->stream>>>(p);
   c->n_launches += 3;
   CU_CHECK(cudaGetLastError());
