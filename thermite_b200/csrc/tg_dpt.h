@@ -147,7 +147,7 @@ TG_HD int tg_dpt_cell(const TgDptMem& m, int hC, int hDm2, int diag, uint32_t ma
                       uint32_t& tbits, int& key, int& ubm) {
   const int c = tg_dpt_max(hC - 1, hDm2);
   const int r_ = tg_dpt_max(rr - 1, dvm2);
-  const int d = diag + (match ? 3 : 1);
+  const int d = diag + (match ? 3 : 1);  // (as multiply-adds on the FMA pipe: tried, same speed -- the loop is not ALU-pipe bound)
   const int nd = tg_dpt_max3(d, c, r_);
   // direction: 0 when nd == d, else 1 when nd == c, else 2 (nd >= d and nd >= c, so the differences are >= 0)
   const int f1 = tg_dpt_min(nd - d, 1), f2 = tg_dpt_min(nd - c, 1);

@@ -154,9 +154,13 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
   if (seq_start < aref.start_idx) seq_start = aref.start_idx;
   uint64_t seq_end = (uint64_t)ref_idx + len + L + bw;
   if (seq_end > (uint64_t)aref.end_idx - 1) seq_end = (uint64_t)aref.end_idx - 1;
-  hit.n_prob = 1; hit.n_cand = 0;
-  hit.prob[0].lo_abs = seq_start; hit.prob[0].hi_abs = seq_end; hit.prob[0].r_abs = ref_idx;
-  hit.prob[0].q = q; hit.prob[0].len = len; hit.prob[0].seqsel = 0; hit.prob[0].gkey = ref_idx;
+  // the problem table is read back many times while it is built: keep it in thread-local storage (L1) and store it to the
+  // item once at the end, instead of reloading global memory after every store
+  TgProbE prob[TG_PMAX];
+  uint32_t n_prob = 1, n_cand = 0;
+  prob[0].lo_abs = seq_start; prob[0].hi_abs = seq_end; prob[0].r_abs = ref_idx;
+  prob[0].q = q; prob[0].len = len; prob[0].seqsel = 0; prob[0].gkey = ref_idx;
+  prob[0].task_r = -1; prob[0].task_l = -1;
   uint32_t ncR0, ncL0;
   {
     TgProblem pg{nullptr, seq_start, seq_end, ref_idx, q, len};
@@ -177,7 +181,7 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
       uint32_t back = tg_match_bwd(rp, tq, ix.txseq4, t0 + tr, t0);
       tr -= back; tq -= back; tl += back;
     }
-    if (hit.n_cand >= TG_CMAX) return false;
+    if (n_cand >= TG_CMAX) return false;
     TgProblem pt{ix.txseq4, t0, t1, t0 + tr, tq, tl};
     // Identical DP problems are evaluated once.  Cheap exact test first: when the y windows of the transcript problem
     // stay inside ONE exon they are a contiguous piece of text, so the problem equals any other contiguous problem with
@@ -198,9 +202,9 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
         exon_sum += elen;
       }
     }
-    uint32_t pi = hit.n_prob;
-    for (uint32_t k = 0; k < hit.n_prob; k++) {
-      const TgProbE& e = hit.prob[k];
+    uint32_t pi = n_prob;
+    for (uint32_t k = 0; k < n_prob; k++) {
+      const TgProbE& e = prob[k];
       if (gkey != TG_NONE) {
         if (e.gkey != gkey || e.q != tq || e.len != tl) continue;
         uint32_t ncRk = ncR0, ncLk = ncL0;
@@ -214,18 +218,19 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
         if (tg_same_problem<W>(w, pt, pk, L, bw)) { pi = k; break; }
       }
     }
-    if (pi == hit.n_prob) {
-      if (hit.n_prob >= TG_PMAX) return false;
-      TgProbE& e = hit.prob[hit.n_prob++];
+    if (pi == n_prob) {
+      if (n_prob >= TG_PMAX) return false;
+      TgProbE& e = prob[n_prob++];
       e.lo_abs = t0; e.hi_abs = t1; e.r_abs = t0 + tr; e.q = tq; e.len = tl; e.seqsel = 1; e.gkey = gkey;
+      e.task_r = -1; e.task_l = -1;
     }
-    TgCandE& c = hit.cand[hit.n_cand++];
+    TgCandE& c = hit.cand[n_cand++];
     c.t0 = t0; c.tx_idx = tx_idx; c.prob = pi; c.tr = tr; c.tlen = (uint32_t)(t1 - t0);
   }
   // tasks (the windows are those of extend_left_right, src/aligner.rs:360-375)
   uint32_t need = 0;
-  for (uint32_t k = 0; k < hit.n_prob; k++) {
-    TgProbE& e = hit.prob[k];
+  for (uint32_t k = 0; k < n_prob; k++) {
+    TgProbE& e = prob[k];
     TgProblem pk{nullptr, e.lo_abs, e.hi_abs, e.r_abs, e.q, e.len};
     uint32_t ncR, ncL;
     tg_problem_windows(pk, L, bw, ncR, ncL);
@@ -238,8 +243,8 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
     w.atomic_or(flags, TG_FLAG_TASK_POOL);
     return false;
   }
-  for (uint32_t k = 0; k < hit.n_prob; k++) {
-    TgProbE& e = hit.prob[k];
+  for (uint32_t k = 0; k < n_prob; k++) {
+    TgProbE& e = prob[k];
     const uint32_t xr_len = L - (e.q + e.len);
     if (e.task_r == 0) {
       TgTask& t = tasks[base];
@@ -261,6 +266,8 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
       t.bw = bw; t.x_drop = (int32_t)st.x_drop;
     }
   }
+  hit.n_prob = n_prob; hit.n_cand = n_cand;
+  for (uint32_t k = 0; k < n_prob; k++) hit.prob[k] = prob[k];
   return true;
 }
 
