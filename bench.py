@@ -137,7 +137,44 @@ def cpu_baseline(fa, gtf, bases, offs, cpu_seconds, threads):
     return dict(value=n / r.seconds, unit="reads/s", cores=threads, kind="port",
                 sample=f"first {n} reads of the step batch, {threads} host threads over contiguous shards "
                        f"(single thread: {rate1:.0f} reads/s on {probe} reads); oracle index build {build_s:.0f}s not timed",
-                single_thread_reads_per_s=rate1), oix
+                single_thread_reads_per_s=rate1), (n, r)
+
+
+def _flat(first, count, alns, ops):
+    """Records and operations of a result in read order (vectorised)."""
+    count = count.astype(np.int64)
+    first = first.astype(np.int64)
+    rec = np.repeat(first - np.concatenate(([0], np.cumsum(count)[:-1])), count) + np.arange(int(count.sum()))
+    a = alns[rec]
+
+    def gather(off, ln):
+        ln = ln.astype(np.int64)
+        start = np.concatenate(([0], np.cumsum(ln)[:-1]))
+        idx = np.repeat(off.astype(np.int64) - start, ln) + np.arange(int(ln.sum()))
+        return ops[idx], ln
+
+    gx, gl = gather(a["ops_off"], a["ops_len"])
+    tx, tl = gather(a["tx_ops_off"], a["tx_ops_len"])
+    return a, gx, gl, tx, tl
+
+
+def parity_vs_oracle(gpu_res, orc_res, n):
+    """Bit-exact comparison of the GPU records of the first n reads with the oracle's (the checker, not the product)."""
+    from oracle.orc import ALN_DTYPE
+    ro = orc_res.read_off.astype(np.int64)
+    ocount = (ro[1:] - ro[:-1])[:n]
+    gcount = gpu_res.count[:n].astype(np.int64)
+    bad_reads = int((ocount != gcount).sum())
+    if bad_reads:
+        return dict(reads=n, reads_with_different_record_count=bad_reads, identical=False)
+    ga, ggx, ggl, gtx, gtl = _flat(gpu_res.first[:n], gpu_res.count[:n], gpu_res.alns, gpu_res.ops)
+    oa, ogx, ogl, otx, otl = _flat(ro[:n], ocount, orc_res.alns, orc_res.ops)
+    fields = [f for f in ALN_DTYPE.names if f not in ("ops_off", "tx_ops_off", "pad")]
+    diff_fields = [f for f in fields if not np.array_equal(ga[f], oa[f])]
+    ops_ok = np.array_equal(ggl, ogl) and np.array_equal(ggx, ogx) and np.array_equal(gtl, otl) and np.array_equal(gtx, otx)
+    return dict(reads=n, records=int(len(ga)), op_words=int(len(ggx) + len(gtx)), fields_compared=len(fields),
+                fields_with_differences=diff_fields, operations_identical=bool(ops_ok),
+                identical=bool(not diff_fields and ops_ok))
 
 
 def _orc_flags():
@@ -384,8 +421,11 @@ def _main(args):
         clocks=clocks,
     )
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_baseline(fa, gtf, bases, offs, args.cpu_seconds, os.cpu_count() or 1)
+        cb, (n_cpu, orc_res) = cpu_baseline(fa, gtf, bases, offs, args.cpu_seconds, os.cpu_count() or 1)
         line["cpu_baseline"] = cb
+        # the oracle output of that sample doubles as a full-scale parity check of the records the GPU produced
+        gres = aligner.align_reads(bases[: int(offs[n_cpu])], offs[: n_cpu + 1])
+        line["parity_vs_oracle"] = parity_vs_oracle(gres, orc_res, n_cpu)
     else:
         line["cpu_baseline"] = None
     _RESULT_LINE.append(json.dumps(line))

@@ -64,4 +64,10 @@ extern "C" {
     pub fn tg_ctx_create(ix: *const tg_index, opts: *const tg_opts, out: *mut *mut tg_ctx) -> tg_status;
     pub fn tg_ctx_destroy(ctx: *mut tg_ctx);
     pub fn tg_align_batch(ctx: *mut tg_ctx, bases: *const u8, offs: *const u64, n_reads: u32, out: *mut tg_result) -> tg_status;
+    /// chunk size of the input copies inside tg_align_batch (copies overlap the seeding kernels)
+    pub fn tg_ctx_set_chunk_reads(ctx: *mut tg_ctx, reads: u32);
+    /// 1 = tg_result.swg_cells equals the reference's DP cell count (no early stop of extensions)
+    pub fn tg_ctx_set_exact_cell_count(ctx: *mut tg_ctx, on: c_int);
+    pub fn tg_ctx_last_kernel_ms(ctx: *const tg_ctx, seed_ms: *mut f32, extend_ms: *mut f32);
+    pub fn tg_ctx_last_dp_ms(ctx: *const tg_ctx) -> f32;
 }
