@@ -397,7 +397,8 @@ def _main(args):
         e2e=dict(value=e2e_value, unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),
         gpu_launches=int(launches),
         roofline=dict(bound="int-pipe", kernel="k_round_dpt<0..3> (banded SWG, thread per extension)", achieved=gcups_ref,
-                      peak=int_roof, unit="GCUPS", frac=gcups_ref / int_roof, traffic=traffic.get("k_round_dpt"),
+                      peak=int_roof, unit="GCUPS", frac=gcups_ref / int_roof, traffic=(traffic.get("k_round_dpt") or {}).get("bytes"),
+                      traffic_note=(traffic.get("k_round_dpt") or {}).get("what"),
                       achieved_computed_cells=gcups_computed, ms_per_step=dp_launch_ms,
                       cells_per_read_reference=ref_cells / n, cells_per_read_computed=cells / n, sm_mhz=sm_mhz,
                       alu_instr_per_cell=INSTR_PER_CELL, cells_per_lane_op=1.0,
@@ -407,7 +408,8 @@ def _main(args):
                            "summed CUDA-event time of the DP sections of all rounds; achieved_computed_cells counts only "
                            "the cells the early-stopped extensions really visit"),
         roofline_seed=dict(bound="hbm", kernel="k_seed_probe x3 + k_pack_reads + k_seed_select", achieved=seed_gbs, peak=gather_gbs,
-                           unit="GB/s", frac=seed_gbs / gather_gbs if gather_gbs else None, traffic=traffic.get("k_seed_probe"),
+                           unit="GB/s", frac=seed_gbs / gather_gbs if gather_gbs else None, traffic=(traffic.get("k_seed_probe") or {}).get("bytes"),
+                           traffic_note=(traffic.get("k_seed_probe") or {}).get("what"),
                            peak_source="random 16-B loads (32-B sectors) over the 4.3 GB k-mer table, measured live in this run "
                                        "(tg_bench_random_gather, best of 5, CUDA events); streaming copy peak "
                                        f"{hbm_peak:.0f} GB/s ({peak_src})",
