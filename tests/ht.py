@@ -24,7 +24,7 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_CSRC, "libtg_hosttest.so")
-        srcs = [os.path.join(_CSRC, f) for f in ("hosttest.cpp", "host_index.cpp", "tg_core.h", "tg_rounds.h", "tg_internal.h")]
+        srcs = [os.path.join(_CSRC, f) for f in ("hosttest.cpp", "host_index.cpp", "tg_core.h", "tg_rounds.h", "tg_dpt.h", "tg_internal.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["make", "-C", _CSRC, "libtg_hosttest.so"], stdout=subprocess.DEVNULL)
         L = C.CDLL(so)
