@@ -243,7 +243,7 @@ bool dpt_task_host(const TgIndexDev& ix, const uint64_t* rp, TgTask& t, DptScrat
   if (cls == 0) return false;
   const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
   TgDptMem m = sc.mem();
-  TgDptY ys{tg_seq_of(ix, t.seqsel), t.y0, ncols, (int)t.side, 0, 0};
+  TgDptY ys{tg_seq_of(ix, t.seqsel), t.y0, ncols, (int)t.side, 0, 0, 0, 0, -1};
   tg_dpt_profile(m, rp, t.xoff, xlen, t.side);
   TgDptResult res{0, 0, 0, 0};
   std::vector<uint32_t> ops;
@@ -527,7 +527,7 @@ long long ht_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uin
       DptScratch dsc;
       TgDptMem m = dsc.mem();
       tg_dpt_profile_codes(m, xc.data(), xlen);
-      TgDptY yy{ypk.data(), 0, ncols, 0, 0, 0};
+      TgDptY yy{ypk.data(), 0, ncols, 0, 0, 0, 0, 0, -1};
       TgDptResult dr{0, 0, 0, 0};
       std::vector<uint32_t> dops;
       dpt_dispatch(dcls, m, yy, xlen, ncols, (int)bw[t], x_drop[t], bound_stop != 0, dr, dops);

@@ -63,20 +63,32 @@ struct TgDptMem {
                      // strength-reduced to IADD / LEA, so they issue on the FMA pipe instead of the saturated ALU pipe
 };
 
-// y symbols in extension order, 16 at a time (side 0: seq[y0 + t]; side 1: seq[y0 - 1 - t])
+// y symbols in extension order, 16 at a time (side 0: seq[y0 + t]; side 1: seq[y0 - 1 - t]).  The word after the one
+// in use is fetched ahead (the fill walks forward): a refill is a random HBM access the thread would otherwise wait for.
 struct TgDptY {
   const uint64_t* seq;
   uint64_t y0;
   int ncols, side;
   uint64_t word;
   int need;
-  TG_HD void refill(int t) {  // t % 16 == 0
+  uint64_t word_next;
+  int need_next, t_next;  // t_next < 0: nothing fetched ahead
+  TG_HD void load(int t, uint64_t& w, int& nd) const {
     if (side == 0) {
-      word = tg_ld16(seq, y0 + (uint64_t)t);
+      w = tg_ld16(seq, y0 + (uint64_t)t);
+      nd = 16;
     } else {
-      need = ncols - t < 16 ? ncols - t : 16;
-      word = tg_ld16(seq, y0 - (uint64_t)t - (uint64_t)need);
+      nd = ncols - t < 16 ? ncols - t : 16;
+      w = tg_ld16(seq, y0 - (uint64_t)t - (uint64_t)nd);
     }
+  }
+  TG_HD void refill(int t) {  // t % 16 == 0
+    if (t == t_next) { word = word_next; need = need_next; }
+    else load(t, word, need);
+    t_next = -1;
+  }
+  TG_HD void prefetch(int t) {  // t % 16 == 0; only columns below ncols are ever fetched
+    if (t < ncols) { load(t, word_next, need_next); t_next = t; }
   }
   TG_HD uint32_t at(int t) const {  // after refill(t & ~15)
     const int u = t & 15;
@@ -281,12 +293,31 @@ TG_HDN uint32_t tg_dpt_traceback(const TgDptMem& m, TgDptY& ys, int xlen, int bw
   if (i < xlen) { emit(n, (uint32_t)TG_OP_XCLIP, (uint32_t)(xlen - i)); n++; }
   uint32_t cur_kind = 0xFFu, cur_run = 0;
   int ybase = -1;
+  // one-word-per-column classes: the walk moves at most one column per step, so four columns are fetched at once
+  // (independent loads) instead of one dependent L2 round trip per step
+  uint32_t tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0;
+  int tw_base = 0x7fffffff;
   while (i > 0 || j > 0) {
     uint32_t dir;
     if (j == 0) dir = 2;  // column 0 is all Ins (src/swg.rs:65,70)
     else {
       const int slot = j <= bw ? i : i - (j - bw);
-      dir = (m.tr[((size_t)(j - 1) * TW + (slot >> 4)) * m.tstride] >> (2 * (slot & 15))) & 3u;
+      uint32_t word;
+      if (TW == 1) {
+        const int cj = j - 1;
+        if (cj < tw_base) {
+          tw_base = cj >= 3 ? cj - 3 : 0;
+          tw0 = m.tr[(size_t)tw_base * m.tstride];
+          tw1 = tw_base + 1 <= cj ? m.tr[(size_t)(tw_base + 1) * m.tstride] : 0u;
+          tw2 = tw_base + 2 <= cj ? m.tr[(size_t)(tw_base + 2) * m.tstride] : 0u;
+          tw3 = tw_base + 3 <= cj ? m.tr[(size_t)(tw_base + 3) * m.tstride] : 0u;
+        }
+        const int k = cj - tw_base;
+        word = k == 0 ? tw0 : k == 1 ? tw1 : k == 2 ? tw2 : tw3;
+      } else {
+        word = m.tr[((size_t)(j - 1) * TW + (slot >> 4)) * m.tstride];
+      }
+      dir = (word >> (2 * (slot & 15))) & 3u;
     }
     uint32_t kind;
     if (dir == 0) {

@@ -621,8 +621,9 @@ __global__ void __launch_bounds__(256) k_round_scatter(RoundParams p) {
 }
 
 // ---- thread-per-extension kernel (tg_dpt.h) ----------------------------------------------------------------------------
+#define DPT_OBUF 12u
 template <int WB>
-__device__ __forceinline__ void dpt_task(const RoundParams& p, TgTask& t, bool active, const TgDptMem& m, int lane) {
+__device__ __forceinline__ void dpt_task(const RoundParams& p, TgTask& t, bool active, const TgDptMem& m, uint32_t* obuf, int lane) {
   TgDptResult res{0, 0, 0, 0};
   TgDptY ys;
   uint32_t n_ops = 0;
@@ -632,9 +633,15 @@ __device__ __forceinline__ void dpt_task(const RoundParams& p, TgTask& t, bool a
     const int ylen = (int)t.ylen;
     const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
     ys.seq = tg_seq_of(p.P.ix, t.seqsel); ys.y0 = t.y0; ys.ncols = ncols; ys.side = t.side; ys.word = 0; ys.need = 0;
+    ys.word_next = 0; ys.need_next = 0; ys.t_next = -1;
     tg_dpt_profile(m, p.rp + (size_t)t.read * p.rp_words, t.xoff, xlen, t.side);
     tg_dpt_fill<WB>(m, ys, xlen, ncols, bw, t.x_drop, p.bound_stop != 0, res);
-    n_ops = tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [](uint32_t, uint32_t, uint32_t) {});
+    // one traceback pass: the RLE words go to a small shared-memory buffer (alignments have few runs); only an
+    // alignment with more than DPT_OBUF runs is walked a second time after the pool allocation
+    uint32_t* ob = obuf;
+    n_ops = tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [ob](uint32_t i, uint32_t kind, uint32_t run) {
+      if (i < DPT_OBUF) ob[i * 128] = kind | (run << 3);
+    });
   }
   __syncwarp();
   // one pool allocation per warp
@@ -655,7 +662,9 @@ __device__ __forceinline__ void dpt_task(const RoundParams& p, TgTask& t, bool a
   if (active) {
     const unsigned long long dst = base + incl - n_ops;
     uint32_t* out = p.ops_pool + dst;
-    if (n_ops) tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [out](uint32_t i, uint32_t kind, uint32_t run) { out[i] = kind | (run << 3); });
+    if (n_ops > DPT_OBUF) tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [out](uint32_t i, uint32_t kind, uint32_t run) { out[i] = kind | (run << 3); });
+    else
+      for (uint32_t i = 0; i < n_ops; i++) out[i] = obuf[i * 128];
     t.score = res.score; t.xend = (uint32_t)res.xend; t.yend = (uint32_t)res.yend; t.cells = res.cells;
     t.ops_off = (uint32_t)dst; t.ops_n = n_ops;
   }
@@ -672,6 +681,8 @@ template <> struct DptGroup<3> { static constexpr int first = 9, last = 11, min_
 template <int G>
 __global__ void __launch_bounds__(128, DptGroup<G>::min_blocks) k_round_dpt(RoundParams p) {
   __shared__ uint32_t msk[32 * 128];
+  __shared__ uint32_t obuf_s[DPT_OBUF * 128];
+  uint32_t* obuf = obuf_s + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   TgDptMem m;
@@ -689,20 +700,20 @@ __global__ void __launch_bounds__(128, DptGroup<G>::min_blocks) k_round_dpt(Roun
     const bool active = first + lane < end;
     TgTask& t = p.tasks[active ? p.sorted[first + lane] : p.sorted[first]];
     if constexpr (G == 0) {
-      if (cls == 1) dpt_task<4>(p, t, active, m, lane);
-      else if (cls == 2) dpt_task<8>(p, t, active, m, lane);
-      else dpt_task<16>(p, t, active, m, lane);
+      if (cls == 1) dpt_task<4>(p, t, active, m, obuf, lane);
+      else if (cls == 2) dpt_task<8>(p, t, active, m, obuf, lane);
+      else dpt_task<16>(p, t, active, m, obuf, lane);
     } else if constexpr (G == 1) {
-      if (cls == 4) dpt_task<24>(p, t, active, m, lane);
-      else dpt_task<32>(p, t, active, m, lane);
+      if (cls == 4) dpt_task<24>(p, t, active, m, obuf, lane);
+      else dpt_task<32>(p, t, active, m, obuf, lane);
     } else if constexpr (G == 2) {
-      if (cls == 6) dpt_task<40>(p, t, active, m, lane);
-      else if (cls == 7) dpt_task<48>(p, t, active, m, lane);
-      else dpt_task<56>(p, t, active, m, lane);
+      if (cls == 6) dpt_task<40>(p, t, active, m, obuf, lane);
+      else if (cls == 7) dpt_task<48>(p, t, active, m, obuf, lane);
+      else dpt_task<56>(p, t, active, m, obuf, lane);
     } else {
-      if (cls == 9) dpt_task<64>(p, t, active, m, lane);
-      else if (cls == 10) dpt_task<72>(p, t, active, m, lane);
-      else dpt_task<80>(p, t, active, m, lane);
+      if (cls == 9) dpt_task<64>(p, t, active, m, obuf, lane);
+      else if (cls == 10) dpt_task<72>(p, t, active, m, obuf, lane);
+      else dpt_task<80>(p, t, active, m, obuf, lane);
     }
     __syncwarp();
   }
