@@ -150,7 +150,8 @@ void tg_ctx_set_exact_cell_count(tg_ctx* ctx, int on);
 /* Execution strategy of the hit loop.  on = 1 (default): speculative round pipeline -- every round evaluates a batch of
  * consecutive hits of each unfinished read under the read's current (band_width, x_drop) with thread-per-hit control
  * kernels and a warp-per-task extension kernel, then replays the reference's serial accept / narrow logic over the
- * batch and discards whatever was evaluated under a state that an accepted hit changed (csrc/tg_rounds.h).  Reads it
+ * batch; hits evaluated under a state that an accepted hit changed are re-submitted under predicted states
+ * (csrc/tg_rounds.h).  Reads it
  * cannot hold (more than 12 transcripts on one seed, ~100k hits) run on the single-warp kernel.  on = 0: every read on
  * the single-warp kernel.  Both produce identical records. */
 void tg_ctx_set_round_pipeline(tg_ctx* ctx, int on);

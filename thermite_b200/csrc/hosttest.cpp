@@ -417,16 +417,17 @@ void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, 
     TgHopsPool hp{hops.data(), &hops_used, hops.size()};
     std::vector<TgTask> tasks;
     std::vector<uint32_t> dp_ops;
+    unsigned long long next_lo = 0;  // items appended by scan belong to the next round
     for (uint32_t round = 0; round < TG_MAX_ROUNDS; round++) {
-      const unsigned long long lo = items_used;
+      const unsigned long long lo = next_lo;
       for (uint32_t r = 0; r < n; r++) {  // plan
-        if (st[r].status != TG_RS_ACTIVE) continue;
+        if (st[r].status != TG_RS_ACTIVE || st[r].planned) continue;
         uint32_t b = tg_plan_batch(st[r], round);
         if (items_used + b > item_cap) b = 0;
         st[r].batch_first = (uint32_t)items_used; st[r].batch_n = b;
         for (uint32_t i = 0; i < b; i++) {
           TgItemRes& ir = ires[items_used + i];
-          ir.read = r; ir.hit = st[r].next_hit + i; ir.flags = 0; ir.prev_acc = TG_NONE;
+          ir.read = r; ir.hit = st[r].next_hit + i; ir.flags = 0; ir.prev_acc = TG_NONE; ir.state = tg_pack_state(st[r].bw, st[r].x_drop);
         }
         items_used += b;
       }
@@ -437,7 +438,7 @@ void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, 
       unsigned long long tctr = 0, octr = 0;
       for (unsigned long long it = lo; it < hi; it++) {  // prep
         const uint32_t r = ires[it].read;
-        if (!tg_item_prep(w1, P, rp.data() + (size_t)r * rp_words, st[r], pool.data() + sfirst[r], scount[r], r, ires[it].hit, hits[it],
+        if (!tg_item_prep(w1, P, rp.data() + (size_t)r * rp_words, st[r], ires[it].state, pool.data() + sfirst[r], scount[r], r, ires[it].hit, hits[it],
                           tasks.data(), &tctr, tasks.size(), &res->flags))
           ires[it].flags = TG_IF_FAIL;
       }
@@ -455,9 +456,10 @@ void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, 
         if (ires[it].flags & TG_IF_FAIL) continue;
         tg_item_post(w1, P, st[ires[it].read], hits[it], tasks.data(), dp_ops.data(), ires[it], cands[it], hp, &res->flags);
       }
+      next_lo = items_used;
       for (uint32_t r = 0; r < n; r++) {  // scan
         if (st[r].status != TG_RS_ACTIVE || st[r].batch_n == 0) continue;
-        if (!tg_scan_read(c->opts, st[r], ires.data())) st[r].status = TG_RS_COMPLEX;
+        if (!tg_scan_read(w1, c->opts, st[r], ires.data(), r, &items_used, item_cap, &res->flags)) st[r].status = TG_RS_COMPLEX;
       }
     }
     res->items = items_used;

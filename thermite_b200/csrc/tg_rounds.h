@@ -9,11 +9,15 @@
 //   plan (thread/read)  ->  prep (thread/hit)  ->  extend (warp/task)  ->  post (thread/hit)  ->  scan (thread/read)
 //
 // and `scan` replays the reference's serial loop over the batch results: running maximum, accept / reject, narrowing.
-// When an accepted hit really narrows the band, the hits of the batch BEHIND it were evaluated under a stale state:
-// they are discarded and re-planned in the next round under the new state.  Every hit that is consumed was evaluated
-// with exactly the (band_width, x_drop) the serial loop would have used, so records are bit-identical; only wasted
-// (discarded) work differs.  Batch policy: 1 hit in round 0 (the first accept nearly always narrows the initial wide
-// band), then all remaining hits once something was accepted, else 4, 16, 64 ... (tg_plan_batch).
+// Every item carries the (band_width, x_drop) it was evaluated under and is consumed only if that is the state the
+// read is really in when the scan reaches it.  When an accepted hit narrows the band, the hits of the batch BEHIND it
+// are stale; scan submits them again at once, each under a PREDICTED state: the stale evaluations almost always have
+// the scores the correct ones will have, so replaying accept / narrow over them tells which state every later hit will
+// see.  A wrong prediction only costs another round.  Every consumed hit was evaluated with exactly the
+// (band_width, x_drop) the serial loop would have used, so records and work counters are bit-identical; only wasted
+// (discarded) work differs (bench: 2.80 M evaluations for 2.56 M hits, 5 rounds, 26 of 1 M reads left after round 2).
+// Batch policy: 1 hit in round 0 (the first accept nearly always narrows the initial wide band), then all remaining
+// hits once something was accepted, else 4, 16, 64 ... (tg_plan_batch).
 //
 // Accepted alignments stay where `post` wrote them (item arrays are append-only within a batch of reads) and are
 // chained per read through TgItemRes::prev_acc; `final` applies src/aligner.rs:177-187.  Reads the tables cannot hold
@@ -75,7 +79,7 @@ struct TgItemRes {  // one (read, hit) evaluation
   uint32_t cells, n_ext; // work the reference does for this hit
   uint32_t flags;        // TG_IF_*
   uint32_t prev_acc;     // previous accepted item of the same read (TG_NONE: first)
-  uint32_t pad;
+  uint32_t state;        // (band_width | x_drop << 16) the item is evaluated under (tg_pack_state)
 };
 struct TgReadState {
   uint32_t L;
@@ -84,11 +88,13 @@ struct TgReadState {
   uint32_t n_hits, next_hit;        // flat hit cursor
   uint32_t batch_first, batch_n;    // items of the current round
   uint32_t n_acc, acc_head;         // accepted alignments (chained through TgItemRes::prev_acc, newest first)
+  uint32_t planned;                 // the next batch was already submitted by scan (predicted states)
   uint32_t status;
   uint32_t hits, n_ext;             // work counters of the consumed hits
   unsigned long long cells;
 };
 
+TG_HD uint32_t tg_pack_state(uint32_t bw, uint32_t x_drop) { return (bw & 0xFFFFu) | (x_drop << 16); }
 TG_HD const uint64_t* tg_seq_of(const TgIndexDev& ix, uint32_t seqsel) { return seqsel ? ix.txseq4 : ix.text4; }
 
 // src/aligner.rs:130-138.  Returns false when the read has more hits than the round path handles.
@@ -104,7 +110,7 @@ TG_HD bool tg_read_state_init(TgReadState& s, uint32_t L, const tg_opts& o, uint
   for (uint32_t i = 0; i < n_seeds; i++) hits += seeds[i].count;
   s.next_hit = 0;
   s.batch_first = 0; s.batch_n = 0;
-  s.n_acc = 0; s.acc_head = TG_NONE;
+  s.n_acc = 0; s.acc_head = TG_NONE; s.planned = 0;
   s.hits = 0; s.n_ext = 0; s.cells = 0;
   s.status = hits ? TG_RS_ACTIVE : TG_RS_DONE;
   s.n_hits = hits > TG_ROUND_MAX_HITS ? 0u : (uint32_t)hits;
@@ -136,17 +142,18 @@ TG_HD void tg_hit_locate(const tg_seed* seeds, uint32_t n_seeds, uint32_t h, uin
 // reference's early `break` at a perfect transcript is applied in post), maps identical problems onto each other and
 // emits one task per non-trivial extension.  Returns false when a table overflows (the read becomes "complex").
 template <class W>
-TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const TgReadState& st, const tg_seed* seeds,
-                         uint32_t n_seeds, uint32_t read, uint32_t flat_hit, TgHit& hit, TgTask* tasks,
+TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const TgReadState& st, uint32_t state,
+                         const tg_seed* seeds, uint32_t n_seeds, uint32_t read, uint32_t flat_hit, TgHit& hit, TgTask* tasks,
                          unsigned long long* task_ctr, unsigned long long task_cap, int* flags) {
   const TgIndexDev& ix = P.ix;
   const uint32_t L = st.L;
+  const uint32_t s_bw = state & 0xFFFFu, s_xd = state >> 16;  // the state this item is evaluated under
   uint32_t si, rk;
   tg_hit_locate(seeds, n_seeds, flat_hit, si, rk);
   const tg_seed sd = seeds[si];
   const uint32_t ref_idx = sd.direct ? sd.sa_lo : TG_LDG(ix.sa + sd.sa_lo + rk);
-  const uint32_t q = sd.query_idx, len = sd.len, bw = st.bw;
-  hit.ref_idx = ref_idx; hit.q = q; hit.len = len; hit.bw = bw; hit.x_drop = (int32_t)st.x_drop;
+  const uint32_t q = sd.query_idx, len = sd.len, bw = s_bw;
+  hit.ref_idx = ref_idx; hit.q = q; hit.len = len; hit.bw = bw; hit.x_drop = (int32_t)s_xd;
   hit.ref_id = tg_idx_to_ref(ix.refs, ix.n_refs, ref_idx);
   const TgRef aref = ix.refs[hit.ref_id];
   const uint64_t span = (uint64_t)L + bw;
@@ -253,7 +260,7 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
       t.y0 = e.r_abs + e.len;
       uint64_t yl = e.hi_abs - t.y0;
       t.ylen = (uint32_t)(yl > (uint64_t)xr_len + bw ? (uint64_t)xr_len + bw + 1 : yl);
-      t.bw = bw; t.x_drop = (int32_t)st.x_drop;
+      t.bw = bw; t.x_drop = (int32_t)s_xd;
     }
     if (e.task_l == 0) {
       TgTask& t = tasks[base];
@@ -263,7 +270,7 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
       uint64_t ys0 = (e.r_abs - e.lo_abs > span) ? e.r_abs - span : e.lo_abs;
       uint64_t yl = e.r_abs - ys0;
       t.ylen = (uint32_t)(yl > (uint64_t)e.q + bw ? (uint64_t)e.q + bw + 1 : yl);
-      t.bw = bw; t.x_drop = (int32_t)st.x_drop;
+      t.bw = bw; t.x_drop = (int32_t)s_xd;
     }
   }
   hit.n_prob = n_prob; hit.n_cand = n_cand;
@@ -455,14 +462,27 @@ TG_HDN void tg_item_post(W& w, const TgAlignParams& P, const TgReadState& st, co
 }
 
 // ---- scan: the serial part of the reference's loop (src/aligner.rs:146-174) over the batch of one read -----------------
+// Items are consumed while they were evaluated under the state the read is really in.  At the first item that was not
+// (an accepted hit in front of it narrowed the band), the rest of the batch -- and whatever hits lie behind it -- is
+// submitted again right here, each item under a PREDICTED state: the stale evaluations almost always have the scores the
+// correct ones will have, so replaying accept / narrow over them predicts the state every later hit will see.  The next
+// scan validates every item against the true state again, so a wrong prediction only costs another round.
 // Returns false when the read has to leave the round path (an item of the batch overflowed a table).
-TG_HD bool tg_scan_read(const tg_opts& o, TgReadState& st, TgItemRes* ires) {
+TG_HD uint32_t tg_narrow_limit(const tg_opts& o, uint32_t L, int32_t s) {
+  // :162-171 (`score as usize` wraps for negative scores => saturating_sub gives 0)
+  return (s < 0) ? 0u : ((L + o.multimap_score_range > (uint32_t)s) ? L + o.multimap_score_range - (uint32_t)s : 0u);
+}
+template <class W>
+TG_HDN bool tg_scan_read(W& w, const tg_opts& o, TgReadState& st, TgItemRes* ires, uint32_t read,
+                         unsigned long long* items_used, unsigned long long item_cap, int* flags) {
   const int32_t range = (int32_t)o.multimap_score_range;
   uint32_t consumed = 0;
+  bool cut = false;
   for (uint32_t i = 0; i < st.batch_n; i++) {
     const uint32_t item = st.batch_first + i;
     TgItemRes& ir = ires[item];
     if (ir.flags & TG_IF_FAIL) return false;
+    if (ir.state != tg_pack_state(st.bw, st.x_drop)) { cut = true; break; }  // evaluated under a state the read is not in
     consumed = i + 1;
     st.hits++; st.cells += ir.cells; st.n_ext += ir.n_ext;
     if (!(ir.flags & TG_IF_KEEP)) continue;
@@ -471,18 +491,42 @@ TG_HD bool tg_scan_read(const tg_opts& o, TgReadState& st, TgItemRes* ires) {
     ir.prev_acc = st.acc_head;
     st.acc_head = item;
     st.n_acc++;
-    // :162-172 (`score as usize` wraps for negative scores => saturating_sub gives 0)
-    const uint32_t L = st.L;
-    const uint32_t lim = (s < 0) ? 0u : ((L + o.multimap_score_range > (uint32_t)s) ? L + o.multimap_score_range - (uint32_t)s : 0u);
-    bool narrowed = false;
-    if (lim < st.bw) { st.bw = lim; narrowed = true; }
-    if (lim < st.x_drop) { st.x_drop = lim; narrowed = true; }
+    const uint32_t lim = tg_narrow_limit(o, st.L, s);
+    if (lim < st.bw) st.bw = lim;
+    if (lim < st.x_drop) st.x_drop = lim;
     if (s > st.max_aln) st.max_aln = s;
-    if (narrowed) break;  // the rest of the batch was evaluated under the old (band_width, x_drop): redo it
   }
+  const uint32_t rest = st.batch_n - consumed;  // stale items of this batch
+  const uint32_t old_first = st.batch_first + consumed;
   st.next_hit += consumed;
-  st.batch_n = 0;
-  if (st.next_hit >= st.n_hits) st.status = TG_RS_DONE;
+  st.batch_n = 0; st.planned = 0;
+  if (st.next_hit >= st.n_hits) { st.status = TG_RS_DONE; return true; }
+  if (!cut) return true;
+  // re-submit: the stale items under predicted states, then the hits behind the batch under the last prediction
+  const uint32_t remaining = st.n_hits - st.next_hit;
+  const uint32_t n_new = remaining < TG_BATCH_MAX ? remaining : TG_BATCH_MAX;
+  const unsigned long long base = w.atomic_add(items_used, (unsigned long long)n_new);
+  if (base + n_new > item_cap) {
+    w.atomic_or(flags, TG_FLAG_ITEM_POOL);
+    return true;
+  }
+  uint32_t pbw = st.bw, pxd = st.x_drop;
+  int32_t pmax = st.max_aln;
+  for (uint32_t t = 0; t < n_new; t++) {
+    TgItemRes& nw = ires[base + t];
+    nw.read = read; nw.hit = st.next_hit + t; nw.flags = 0; nw.prev_acc = TG_NONE;
+    nw.state = tg_pack_state(pbw, pxd);
+    if (t < rest) {
+      const TgItemRes old = ires[old_first + t];
+      if ((old.flags & TG_IF_KEEP) && old.score >= pmax - range) {
+        const uint32_t lim = tg_narrow_limit(o, st.L, old.score);
+        if (lim < pbw) pbw = lim;
+        if (lim < pxd) pxd = lim;
+        if (old.score > pmax) pmax = old.score;
+      }
+    }
+  }
+  st.batch_first = (uint32_t)base; st.batch_n = n_new; st.planned = 1;
   return true;
 }
 

@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(128) k_round_init(RoundParams p) {
 // every active read submits its next batch of hits
 __global__ void __launch_bounds__(128) k_round_plan(RoundParams p) {
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
-    if (p.st[r].status != TG_RS_ACTIVE) continue;
+    if (p.st[r].status != TG_RS_ACTIVE || p.st[r].planned) continue;  // (scan already submitted the batch)
     TgReadState st = p.st[r];
     uint32_t b = tg_plan_batch(st, p.round);
     const unsigned long long base = warp_agg_add(&p.ctr->items_used, (unsigned long long)b);
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(128) k_round_plan(RoundParams p) {
     st.batch_first = (uint32_t)base; st.batch_n = b;
     for (uint32_t i = 0; i < b; i++) {
       TgItemRes& ir = p.ires[base + i];
-      ir.read = r; ir.hit = st.next_hit + i; ir.flags = 0; ir.prev_acc = TG_NONE;
+      ir.read = r; ir.hit = st.next_hit + i; ir.flags = 0; ir.prev_acc = TG_NONE; ir.state = tg_pack_state(st.bw, st.x_drop);
     }
     p.st[r] = st;
   }
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(128) k_round_prep(RoundParams p) {
   for (unsigned long long it = lo + blockIdx.x * blockDim.x + threadIdx.x; it < hi; it += (unsigned long long)gridDim.x * blockDim.x) {
     TgItemRes& ir = p.ires[it];
     const uint32_t r = ir.read;
-    const bool ok = tg_item_prep<DevThread>(w, p.P, p.rp + (size_t)r * p.rp_words, p.st[r], p.seeds + p.read_seed_first[r],
+    const bool ok = tg_item_prep<DevThread>(w, p.P, p.rp + (size_t)r * p.rp_words, p.st[r], ir.state, p.seeds + p.read_seed_first[r],
                                             p.read_seed_count[r], r, ir.hit, p.hits[it], p.tasks, &p.ctr->round_tasks[p.round],
                                             p.task_cap, &p.ctr->flags);
     if (!ok) ir.flags = TG_IF_FAIL;
@@ -723,6 +723,8 @@ __global__ void __launch_bounds__(128) k_round_post(RoundParams p) {
   DevThread w;
   unsigned long long lo, hi;
   round_item_range(p, lo, hi);
+  // items appended from here on (by scan) belong to the next round
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.ctr->round_end[p.round] = p.ctr->items_used;
   for (unsigned long long it = lo + blockIdx.x * blockDim.x + threadIdx.x; it < hi; it += (unsigned long long)gridDim.x * blockDim.x) {
     TgItemRes& ir = p.ires[it];
     if (ir.flags & TG_IF_FAIL) continue;
@@ -731,12 +733,12 @@ __global__ void __launch_bounds__(128) k_round_post(RoundParams p) {
 }
 
 __global__ void __launch_bounds__(128) k_round_scan(RoundParams p) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.ctr->round_end[p.round] = p.ctr->items_used;
+  DevThread w;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += gridDim.x * blockDim.x) {
     if (p.st[r].status != TG_RS_ACTIVE) continue;
     TgReadState st = p.st[r];
     if (st.batch_n == 0) continue;
-    if (!tg_scan_read(p.P.opts, st, p.ires)) { mark_complex(p, r, 1); continue; }
+    if (!tg_scan_read<DevThread>(w, p.P.opts, st, p.ires, r, &p.ctr->items_used, p.item_cap, &p.ctr->flags)) { mark_complex(p, r, 1); continue; }
     p.st[r] = st;
     if (st.status == TG_RS_ACTIVE) warp_agg_add(&p.ctr->round_active[p.round], 1ull);
   }
