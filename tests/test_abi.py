@@ -87,6 +87,56 @@ def test_fastq_parser_and_writers_match_oracle_text():
         assert text == want
 
 
+def test_parallel_fastq_parser_and_writers_large_input():
+    """The multi-threaded ingest / writers: a FASTQ text large enough to be cut into per-thread
+    segments, with quality lines that start with '@' or '+', blank lines between records and CRLF line ends, must
+    parse like a plain sequential parser; oracle records formatted by the (threaded) product writer must equal the
+    oracle's own PAF / SAM text."""
+    from common import small_world
+    from thermite_b200 import synth
+    contigs, gtf, txs, fa = small_world(5)
+    n = 60_000
+    rbases, roffs = synth.make_reads(3, contigs, txs, n, L=91, sub=0.01, ins=0.001, dele=0.001)
+    rng = np.random.default_rng(9)
+    qual_first = rng.choice(np.frombuffer(b"@+FI#", np.uint8), n)
+    recs, want_names, want_quals = [], [], []
+    for r in range(n):
+        name = b"read%d extra field" % r
+        seq = rbases[int(roffs[r]): int(roffs[r + 1])].tobytes()
+        q = bytes([qual_first[r]]) + b"F" * 90
+        eol = b"\r\n" if r % 1000 == 7 else b"\n"
+        recs.append(b"@" + name + eol + seq + eol + b"+" + eol + q + eol + (b"\n" if r % 5000 == 11 else b""))
+        want_names.append(name); want_quals.append(q)
+    fq = b"".join(recs) + b"@truncated\nACGT\n"  # incomplete last record: dropped
+    assert len(fq) > (8 << 20)
+    bases, offs, names, name_offs, quals, qual_offs = tb.parse_fastq(fq)
+    assert len(offs) - 1 == n and np.array_equal(bases, rbases) and np.array_equal(offs, roffs)
+    assert names.tobytes() == b"".join(want_names) and quals.tobytes() == b"".join(want_quals)
+    assert np.array_equal(name_offs, np.cumsum([0] + [len(x) for x in want_names]).astype(np.uint64))
+    assert np.array_equal(qual_offs, (np.arange(n + 1) * 91).astype(np.uint64))
+    # writers: oracle records -> product text (threaded: n >= 32768) == oracle text
+    oix = orc.Index.create(fa, gtf)
+    flags = dict(k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True)
+    ores = oix.align_batch(bases, offs, n_threads=8, **flags)
+    ix = tb.Index.create_from_memory(fa, gtf)
+    first = np.ascontiguousarray(ores.read_off[:-1])
+    count = np.ascontiguousarray((ores.read_off[1:] - ores.read_off[:-1]).astype(np.uint32))
+    res = api._Result(n, len(ores.alns), len(ores.ops), first.ctypes.data, count.ctypes.data, ores.alns.ctypes.data,
+                      ores.ops.ctypes.data, 0, 0, 0, 0)
+    plain = b"".join(b"@" + want_names[r] + b"\n" + rbases[int(roffs[r]): int(roffs[r + 1])].tobytes() + b"\n+\n" + want_quals[r] + b"\n"
+                     for r in range(n))
+    for sam in (False, True):
+        out, ln = C.c_void_p(), C.c_size_t()
+        assert tb.lib().tg_format_batch(ix._h, C.byref(res), api._p(bases), api._p(offs), api._p(names), api._p(name_offs),
+                                        api._p(quals), api._p(qual_offs), int(sam), C.byref(out), C.byref(ln)) == 0
+        text = C.string_at(out, ln.value)
+        tb.lib().tg_free(out)
+        want = oix.align_fastq_text(plain, sam=sam, **flags)
+        if sam:
+            text = tb.sam_header(ix) + text
+        assert text == want
+
+
 def test_device_entry_points_fail_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():

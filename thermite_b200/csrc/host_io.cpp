@@ -5,7 +5,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "tg_internal.h"
@@ -91,14 +93,11 @@ tg_status tg_format_sam_header(const tg_index_host* ix, char** out, size_t* out_
   return TG_OK;
 }
 
-tg_status tg_format_batch(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
-                          const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
-                          int sam, char** out, size_t* out_len) {
-  if (!ix || !res || !offs || !names || !name_offs || !out || !out_len) return tg_fail(TG_ERR_INVALID, "null argument");
-  if (sam && (!quals || !qual_offs || !bases)) return tg_fail(TG_ERR_INVALID, "SAM output needs bases and qualities");
-  Out o;
-  o.s.reserve((size_t)res->n_reads * (sam ? 400 : 90));
-  for (uint32_t r = 0; r < res->n_reads; r++) {
+// records of the reads [r0, r1) as PAF / SAM text (appended to o)
+void format_range(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
+                         const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
+                         int sam, uint32_t r0, uint32_t r1, Out& o) {
+  for (uint32_t r = r0; r < r1; r++) {
     const char* nm = (const char*)names + name_offs[r];
     size_t nm_len = name_offs[r + 1] - name_offs[r];
     size_t qn_len = nm_len;  // format_read_name: cut at the first space (src/aln_writer.rs:344-349)
@@ -186,53 +185,156 @@ tg_status tg_format_batch(const tg_index_host* ix, const tg_result* res, const u
       }
     }
   }
-  *out = (char*)malloc(o.s.size() + 1);
+}
+
+tg_status tg_format_batch(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
+                          const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
+                          int sam, char** out, size_t* out_len) {
+  if (!ix || !res || !offs || !names || !name_offs || !out || !out_len) return tg_fail(TG_ERR_INVALID, "null argument");
+  if (sam && (!quals || !qual_offs || !bases)) return tg_fail(TG_ERR_INVALID, "SAM output needs bases and qualities");
+  // Reads are formatted independently: contiguous ranges on the host's cores, pieces concatenated in read order
+  // (byte-identical to the single-threaded text).
+  const uint32_t n = res->n_reads;
+  uint32_t T = (uint32_t)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64);
+  if (n < 32768) T = 1;
+  std::vector<Out> parts(T);
+  auto work = [&](uint32_t t) {
+    const uint32_t r0 = (uint32_t)((uint64_t)n * t / T), r1 = (uint32_t)((uint64_t)n * (t + 1) / T);
+    parts[t].s.reserve((size_t)(r1 - r0) * (sam ? 400 : 90));
+    format_range(ix, res, bases, offs, names, name_offs, quals, qual_offs, sam, r0, r1, parts[t]);
+  };
+  if (T == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  size_t total = 0;
+  std::vector<size_t> at(T);
+  for (uint32_t t = 0; t < T; t++) { at[t] = total; total += parts[t].s.size(); }
+  *out = (char*)malloc(total + 1);
   if (!*out) return tg_fail(TG_ERR_INTERNAL, "out of memory");
-  memcpy(*out, o.s.data(), o.s.size());
-  (*out)[o.s.size()] = 0;
-  *out_len = o.s.size();
+  auto copy = [&](uint32_t t) { memcpy(*out + at[t], parts[t].s.data(), parts[t].s.size()); };
+  if (T == 1) copy(0);
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; t++) th.emplace_back(copy, t);
+    for (auto& x : th) x.join();
+  }
+  (*out)[total] = 0;
+  *out_len = total;
   return TG_OK;
+}
+
+// One segment of FASTQ text (starts at a record start): 4-line records, blank lines between records skipped, a
+// truncated last record dropped (needletail::parse_fastx_file as src/aligner.rs:51-55 uses it).
+struct FastqSeg {
+  std::string b, nm, q;
+  std::vector<uint64_t> bo, no, qo;  // end offsets of every record inside b / nm / q
+  bool bad = false;
+};
+static void parse_fastq_segment(const char* text, size_t begin, size_t end, FastqSeg& o) {
+  size_t p = begin;
+  auto next_line = [&](size_t& lb, size_t& le) {  // false at the end of the segment
+    if (p >= end) return false;
+    const void* nl = memchr(text + p, '\n', end - p);
+    const size_t e = nl ? (size_t)((const char*)nl - text) : end;
+    lb = p; le = e;
+    if (le > lb && text[le - 1] == '\r') le--;
+    p = e + 1;
+    return true;
+  };
+  size_t lb[4], le[4];
+  for (;;) {
+    if (!next_line(lb[0], le[0])) return;
+    if (lb[0] == le[0]) continue;  // blank line between records
+    bool full = true;
+    for (int k = 1; k < 4; k++) full = full && next_line(lb[k], le[k]);
+    if (!full) return;             // truncated last record
+    if (text[lb[0]] != '@') { o.bad = true; return; }
+    o.nm.append(text + lb[0] + 1, le[0] - lb[0] - 1);
+    o.b.append(text + lb[1], le[1] - lb[1]);
+    o.q.append(text + lb[3], le[3] - lb[3]);
+    o.no.push_back(o.nm.size()); o.bo.push_back(o.b.size()); o.qo.push_back(o.q.size());
+  }
+}
+// first record start at or after p: a line that starts with '@' whose second next line starts with '+' (a quality line may
+// start with '@', but then the second next line is a sequence line, which never starts with '+')
+static size_t fastq_record_start(const char* text, size_t len, size_t p) {
+  if (p == 0) return 0;
+  const void* nl = memchr(text + p - 1, '\n', len - (p - 1));
+  if (!nl) return len;
+  size_t c = (size_t)((const char*)nl - text) + 1;
+  while (c < len) {
+    const void* n1 = memchr(text + c, '\n', len - c);
+    if (!n1) return len;
+    const size_t l1 = (size_t)((const char*)n1 - text) + 1;
+    if (text[c] == '@' && l1 < len) {
+      const void* n2 = memchr(text + l1, '\n', len - l1);
+      if (!n2) return len;
+      const size_t l2 = (size_t)((const char*)n2 - text) + 1;
+      if (l2 < len && text[l2] == '+') return c;
+    }
+    c = l1;
+  }
+  return len;
 }
 
 tg_status tg_parse_fastq(const char* text, size_t len, uint32_t* n_reads, uint8_t** bases, uint64_t** offs, uint8_t** names,
                          uint64_t** name_offs, uint8_t** quals, uint64_t** qual_offs) {
   if (!text || !n_reads || !bases || !offs || !names || !name_offs || !quals || !qual_offs)
     return tg_fail(TG_ERR_INVALID, "null argument");
-  std::vector<std::pair<size_t, size_t>> lines;  // [begin, end) without the line terminator
-  size_t p = 0;
-  while (p < len) {
-    size_t e = p;
-    while (e < len && text[e] != '\n') e++;
-    size_t ee = e;
-    if (ee > p && text[ee - 1] == '\r') ee--;
-    lines.push_back({p, ee});
-    p = e + 1;
+  // segments of the text on the host's cores, cut at record starts; pieces concatenated in order
+  uint32_t T = (uint32_t)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64);
+  if (len < (8u << 20)) T = 1;
+  std::vector<size_t> cut(T + 1, len);
+  cut[0] = 0;
+  for (uint32_t t = 1; t < T; t++) cut[t] = std::max(cut[t - 1], fastq_record_start(text, len, (size_t)((double)len * t / T)));
+  std::vector<FastqSeg> seg(T);
+  if (T == 1) parse_fastq_segment(text, 0, len, seg[0]);
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; t++) th.emplace_back([&, t]() { parse_fastq_segment(text, cut[t], cut[t + 1], seg[t]); });
+    for (auto& x : th) x.join();
   }
-  std::string b, nm, q;
-  std::vector<uint64_t> bo(1, 0), no(1, 0), qo(1, 0);
-  size_t i = 0;
-  while (i < lines.size()) {
-    if (lines[i].first == lines[i].second) { i++; continue; }
-    if (i + 3 >= lines.size()) break;
-    if (text[lines[i].first] != '@') return tg_fail(TG_ERR_IO, "FASTQ record does not start with '@'");
-    nm.append(text + lines[i].first + 1, lines[i].second - lines[i].first - 1);
-    b.append(text + lines[i + 1].first, lines[i + 1].second - lines[i + 1].first);
-    q.append(text + lines[i + 3].first, lines[i + 3].second - lines[i + 3].first);
-    no.push_back(nm.size()); bo.push_back(b.size()); qo.push_back(q.size());
-    i += 4;
+  size_t nb = 0, nn = 0, nq = 0, nr = 0;
+  for (auto& g : seg) {
+    if (g.bad) return tg_fail(TG_ERR_IO, "FASTQ record does not start with '@'");
+    nb += g.b.size(); nn += g.nm.size(); nq += g.q.size(); nr += g.bo.size();
   }
-  auto dup = [](const void* src, size_t n) {
-    void* d = malloc(n ? n : 1);
-    if (n) memcpy(d, src, n);
-    return d;
+  if (nr > 0xFFFFFFFFull) return tg_fail(TG_ERR_CAPACITY, "more than 2^32 reads in one FASTQ text");
+  *n_reads = (uint32_t)nr;
+  *bases = (uint8_t*)malloc(nb ? nb : 1);
+  *names = (uint8_t*)malloc(nn ? nn : 1);
+  *quals = (uint8_t*)malloc(nq ? nq : 1);
+  *offs = (uint64_t*)malloc((nr + 1) * 8);
+  *name_offs = (uint64_t*)malloc((nr + 1) * 8);
+  *qual_offs = (uint64_t*)malloc((nr + 1) * 8);
+  if (!*bases || !*names || !*quals || !*offs || !*name_offs || !*qual_offs) return tg_fail(TG_ERR_INTERNAL, "out of memory");
+  (*offs)[0] = 0; (*name_offs)[0] = 0; (*qual_offs)[0] = 0;
+  std::vector<size_t> ab(T), an(T), aq(T), ar(T);
+  size_t cb = 0, cn = 0, cq = 0, cr = 0;
+  for (uint32_t t = 0; t < T; t++) {
+    ab[t] = cb; an[t] = cn; aq[t] = cq; ar[t] = cr;
+    cb += seg[t].b.size(); cn += seg[t].nm.size(); cq += seg[t].q.size(); cr += seg[t].bo.size();
+  }
+  auto place = [&](uint32_t t) {
+    const FastqSeg& g = seg[t];
+    memcpy(*bases + ab[t], g.b.data(), g.b.size());
+    memcpy(*names + an[t], g.nm.data(), g.nm.size());
+    memcpy(*quals + aq[t], g.q.data(), g.q.size());
+    for (size_t i = 0; i < g.bo.size(); i++) {
+      (*offs)[ar[t] + i + 1] = ab[t] + g.bo[i];
+      (*name_offs)[ar[t] + i + 1] = an[t] + g.no[i];
+      (*qual_offs)[ar[t] + i + 1] = aq[t] + g.qo[i];
+    }
   };
-  *n_reads = (uint32_t)(bo.size() - 1);
-  *bases = (uint8_t*)dup(b.data(), b.size());
-  *names = (uint8_t*)dup(nm.data(), nm.size());
-  *quals = (uint8_t*)dup(q.data(), q.size());
-  *offs = (uint64_t*)dup(bo.data(), bo.size() * 8);
-  *name_offs = (uint64_t*)dup(no.data(), no.size() * 8);
-  *qual_offs = (uint64_t*)dup(qo.data(), qo.size() * 8);
+  if (T == 1) place(0);
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; t++) th.emplace_back(place, t);
+    for (auto& x : th) x.join();
+  }
   return TG_OK;
 }
 
