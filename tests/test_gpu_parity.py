@@ -100,6 +100,39 @@ def test_chrM_synthM_records():
     assert np.array_equal(res_c.count, res.count) and len(res_c.alns) == len(res.alns) and len(res_c.ops) == len(res.ops)
 
 
+@pytest.mark.parametrize("seed", [21, 22])
+def test_repeat_rich_reads_many_hits_many_accepted(seed):
+    """Repeat families with near-identical copies and a low k: hundreds of hits per read, batches that are cut and
+    re-submitted under predicted states, reads with more than 16 accepted alignments (global finaliser scratch)."""
+    g = synth.make_genome(seed, 20000, families=((60, 150, 0.0, 0.04), (20, 300, 0.0, 0.02)), polya_runs=10, polya_len=(20, 40))
+    contigs = [("chrR", g)]
+    gtf, txs = synth.make_annotation(seed + 1, "chrR", g, n_genes=8, tx_per_gene=(1, 4), exons_per_tx=(1, 5),
+                                     exon_len=(20, 150), intron_len=(20, 300), lead=0, prefix="r")
+    fa = synth.fasta_bytes(contigs)
+    n = 3000
+    bases, offs = synth.make_reads(seed + 2, contigs, txs, n, L=91, sub=0.03, ins=0.004, dele=0.004, polya_frac=0.2,
+                                   polya_len=(15, 35))
+    oix = orc.Index.create(fa, gtf)
+    ix = Index.create_from_memory(fa, gtf)
+    max_records = 0
+    for opts in (AlignOpts(12, 0.0, 20, 1, True), AlignOpts(10, 0.5, 0, 3, True), AlignOpts(14, 0.66, 30, 0, False)):
+        kw = dict(k=opts.min_seed_len, pct=opts.min_aln_score_percent, min_score=opts.min_aln_score,
+                  score_range=opts.multimap_score_range, intron_mode=opts.intron_mode)
+        oix.counters_reset()
+        ores = oix.align_batch(bases, offs, n_threads=8, **kw)
+        oc = oix.counters()
+        al = Aligner(ix, opts)
+        res = al.align_reads(bases, offs)
+        _cmp(res, ores, n)
+        assert res.counters["seed_hits"] == oc["hits"] and oc["hits"] > 5 * n
+        al.set_exact_cell_count(True)
+        res = al.align_reads(bases, offs)
+        _cmp(res, ores, n)
+        assert res.counters["swg_cells"] == oc["swg_cells"]
+        max_records = max(max_records, int(res.count.max()))
+    assert max_records > 16  # more records than the thread-local finaliser holds
+
+
 def test_edge_reads():
     contigs, gtf, txs, fa = small_world(11)
     oix = orc.Index.create(fa, gtf)

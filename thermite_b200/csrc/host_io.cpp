@@ -14,13 +14,39 @@
 
 namespace {
 
+// Append-only text buffer (std::string's per-character push_back dominated the writers' time).
+struct Text {
+  char* p = nullptr;
+  size_t n = 0, cap = 0;
+  Text() = default;
+  Text(const Text&) = delete;
+  Text& operator=(const Text&) = delete;
+  Text(Text&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+  ~Text() { free(p); }
+  void reserve(size_t c) {
+    if (c <= cap) return;
+    size_t want = cap ? cap : 4096;
+    while (want < c) want += want / 2 + 4096;
+    p = (char*)realloc(p, want);
+    cap = want;
+  }
+  char* room(size_t k) { if (n + k > cap) reserve(n + k); return p + n; }
+  void append(const char* src, size_t k) { memcpy(room(k), src, k); n += k; }
+  void push_back(char c) { *room(1) = c; n++; }
+  Text& operator+=(const char* lit) { append(lit, strlen(lit)); return *this; }
+  Text& operator+=(const std::string& str) { append(str.data(), str.size()); return *this; }
+  size_t size() const { return n; }
+  const char* data() const { return p; }
+};
 struct Out {
-  std::string s;
+  Text s;
   void num(uint64_t v) {
     char buf[24];
-    int n = 0;
-    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) s.push_back(buf[--n]);
+    int k = 0;
+    do { buf[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    char* d = s.room((size_t)k);
+    for (int i = 0; i < k; i++) d[i] = buf[k - 1 - i];
+    s.n += (size_t)k;
   }
   void snum(int64_t v) {
     if (v < 0) { s.push_back('-'); num((uint64_t)(-v)); } else num((uint64_t)v);
