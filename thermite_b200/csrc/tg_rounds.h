@@ -137,6 +137,41 @@ TG_HD void tg_hit_locate(const tg_seed* seeds, uint32_t n_seeds, uint32_t h, uin
   rk = seeds[s].count - 1 - h;
 }
 
+// Do two transcripts run through the same pieces of text for `n` symbols, starting at offset so_a of exon se_a (resp.
+// so_b of se_b) -- both the same text position -- and walking towards higher (dir = +1; e*_end = one past the last exon)
+// or lower (dir = -1; e*_end = the first exon; the walk starts just below the offsets) transcript coordinates?
+TG_HD bool tg_same_tx_pieces(const uint32_t* te_start, const uint32_t* te_end, uint32_t se_a, uint32_t so_a, uint32_t ea_end,
+                             uint32_t se_b, uint32_t so_b, uint32_t eb_end, uint32_t n, int dir) {
+  uint32_t ea = se_a, eb = se_b, oa = so_a, ob = so_b;
+  while (n > 0) {
+    const uint32_t sa_ = TG_LDG(te_start + ea), sb_ = TG_LDG(te_start + eb);
+    uint32_t roomA, roomB;
+    if (dir > 0) {
+      if (sa_ + oa != sb_ + ob) return false;           // different text position
+      roomA = TG_LDG(te_end + ea) - sa_ - oa;
+      roomB = TG_LDG(te_end + eb) - sb_ - ob;
+    } else {
+      if (sa_ + oa != sb_ + ob) return false;
+      roomA = oa; roomB = ob;                            // symbols below the offset inside the exon
+    }
+    const uint32_t takeA = roomA < n ? roomA : n, takeB = roomB < n ? roomB : n;
+    if (takeA != takeB) return false;                    // one transcript leaves its exon earlier
+    n -= takeA;
+    if (n == 0) return true;
+    if (dir > 0) {
+      ea++; eb++;
+      if (ea >= ea_end || eb >= eb_end) return false;    // (cannot happen: the windows lie inside the transcripts)
+      oa = 0; ob = 0;
+    } else {
+      if (ea == ea_end || eb == eb_end) return false;
+      ea--; eb--;
+      oa = TG_LDG(te_end + ea) - TG_LDG(te_start + ea);
+      ob = TG_LDG(te_end + eb) - TG_LDG(te_start + eb);
+    }
+  }
+  return true;
+}
+
 // ---- prep: everything of align_seed_hit (src/aligner.rs:198-258) that happens before a SwgExtend call ------------
 // Tabulates the genome problem and one candidate per transcript that the seed's exon stab yields (ALL of them: the
 // reference's early `break` at a perfect transcript is applied in post), maps identical problems onto each other and
@@ -168,10 +203,12 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
   prob[0].lo_abs = seq_start; prob[0].hi_abs = seq_end; prob[0].r_abs = ref_idx;
   prob[0].q = q; prob[0].len = len; prob[0].seqsel = 0; prob[0].gkey = ref_idx;
   prob[0].task_r = -1; prob[0].task_l = -1;
-  uint32_t ncR0, ncL0;
+  // per problem: window lengths; for transcript problems the seed's text position, its exon / offset and the exon range
+  uint32_t p_ncR[TG_PMAX], p_ncL[TG_PMAX], p_gpos[TG_PMAX], p_se[TG_PMAX], p_so[TG_PMAX], p_e0[TG_PMAX], p_e1[TG_PMAX];
   {
     TgProblem pg{nullptr, seq_start, seq_end, ref_idx, q, len};
-    tg_problem_windows(pg, L, bw, ncR0, ncL0);
+    tg_problem_windows(pg, L, bw, p_ncR[0], p_ncL[0]);
+    p_gpos[0] = ref_idx; p_se[0] = 0; p_so[0] = 0; p_e0[0] = 0; p_e1[0] = 0;
   }
   const TgStabRange xr = tg_stab_begin<W>(w, ix.exon_stab, ix.n_exon_stab, ix.exon_maxlen, ref_idx, ref_idx + len);
   uint32_t next_rank = 0;
@@ -190,20 +227,22 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
     }
     if (n_cand >= TG_CMAX) return false;
     TgProblem pt{ix.txseq4, t0, t1, t0 + tr, tq, tl};
-    // Identical DP problems are evaluated once.  Cheap exact test first: when the y windows of the transcript problem
-    // stay inside ONE exon they are a contiguous piece of text, so the problem equals any other contiguous problem with
-    // the same seed position, seed and window lengths (transcript sequences are spliced text).  Only problems whose
-    // windows cross a junction are compared symbol by symbol, and only with each other; a missed match merely costs a
+    // Identical DP problems are evaluated once, decided structurally (no symbol comparison): transcript sequences are
+    // spliced text, so two problems whose seed starts at the same text position, with the same seed and window
+    // lengths, and whose windows run through the SAME pieces of text are the same problem.  A transcript problem whose
+    // windows stay inside ONE exon is a contiguous piece of text like the genome problem (gkey); windows that cross
+    // junctions are compared exon by exon against the other junction-crossing problems.  A missed match merely costs a
     // duplicate evaluation with the same result.
     uint32_t ncRt, ncLt;
     tg_problem_windows(pt, L, bw, ncRt, ncLt);
-    uint32_t gkey = TG_NONE;
+    uint32_t gkey = TG_NONE, gpos = TG_NONE, se = e0, so = 0;
     {
       uint32_t exon_sum = 0;
       for (uint32_t e = e0; e < e1; e++) {
         const uint32_t es = TG_LDG(ix.te_start + e), elen = TG_LDG(ix.te_end + e) - es;
         if (tr < exon_sum + elen) {  // the exon holding the seed start
-          if (tr - exon_sum >= ncLt && (uint64_t)tr + tl + ncRt <= (uint64_t)exon_sum + elen) gkey = es + (tr - exon_sum);
+          se = e; so = tr - exon_sum; gpos = es + so;
+          if (so >= ncLt && (uint64_t)tr + tl + ncRt <= (uint64_t)exon_sum + elen) gkey = gpos;
           break;
         }
         exon_sum += elen;
@@ -212,17 +251,14 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
     uint32_t pi = n_prob;
     for (uint32_t k = 0; k < n_prob; k++) {
       const TgProbE& e = prob[k];
+      if (e.q != tq || e.len != tl || p_ncR[k] != ncRt || p_ncL[k] != ncLt) continue;
       if (gkey != TG_NONE) {
-        if (e.gkey != gkey || e.q != tq || e.len != tl) continue;
-        uint32_t ncRk = ncR0, ncLk = ncL0;
-        if (k > 0) {
-          TgProblem pk{nullptr, e.lo_abs, e.hi_abs, e.r_abs, e.q, e.len};
-          tg_problem_windows(pk, L, bw, ncRk, ncLk);
-        }
-        if (ncRk == ncRt && ncLk == ncLt) { pi = k; break; }
-      } else if (e.gkey == TG_NONE) {
-        TgProblem pk{tg_seq_of(ix, e.seqsel), e.lo_abs, e.hi_abs, e.r_abs, e.q, e.len};
-        if (tg_same_problem<W>(w, pt, pk, L, bw)) { pi = k; break; }
+        if (e.gkey == gkey) { pi = k; break; }
+      } else if (e.gkey == TG_NONE && p_gpos[k] == gpos &&
+                 tg_same_tx_pieces(ix.te_start, ix.te_end, se, so, e1, p_se[k], p_so[k], p_e1[k], tl + ncRt, +1) &&
+                 tg_same_tx_pieces(ix.te_start, ix.te_end, se, so, e0, p_se[k], p_so[k], p_e0[k], ncLt, -1)) {
+        pi = k;
+        break;
       }
     }
     if (pi == n_prob) {
@@ -230,6 +266,8 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
       TgProbE& e = prob[n_prob++];
       e.lo_abs = t0; e.hi_abs = t1; e.r_abs = t0 + tr; e.q = tq; e.len = tl; e.seqsel = 1; e.gkey = gkey;
       e.task_r = -1; e.task_l = -1;
+      const uint32_t k = n_prob - 1;
+      p_ncR[k] = ncRt; p_ncL[k] = ncLt; p_gpos[k] = gpos; p_se[k] = se; p_so[k] = so; p_e0[k] = e0; p_e1[k] = e1;
     }
     TgCandE& c = hit.cand[n_cand++];
     c.t0 = t0; c.tx_idx = tx_idx; c.prob = pi; c.tr = tr; c.tlen = (uint32_t)(t1 - t0);
@@ -238,9 +276,7 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
   uint32_t need = 0;
   for (uint32_t k = 0; k < n_prob; k++) {
     TgProbE& e = prob[k];
-    TgProblem pk{nullptr, e.lo_abs, e.hi_abs, e.r_abs, e.q, e.len};
-    uint32_t ncR, ncL;
-    tg_problem_windows(pk, L, bw, ncR, ncL);
+    const uint32_t ncR = p_ncR[k], ncL = p_ncL[k];
     e.task_r = ncR ? 0 : -1;
     e.task_l = ncL ? 0 : -1;
     need += (ncR ? 1u : 0u) + (ncL ? 1u : 0u);
