@@ -402,6 +402,10 @@ def _main(args):
                       achieved_computed_cells=gcups_computed, ms_per_step=dp_launch_ms,
                       cells_per_read_reference=ref_cells / n, cells_per_read_computed=cells / n, sm_mhz=sm_mhz,
                       alu_instr_per_cell=INSTR_PER_CELL, cells_per_lane_op=1.0,
+                      hbm_view=dict(peak=hbm_peak, unit="GB/s",
+                                    note="not HBM bound: the four DP launches of the heaviest round move 0.78 GB of DRAM traffic "
+                                         "in 3.2 ms (ncu, profiles/r1_ncu_dpt.csv) = 0.04 of the streaming peak; the contract's "
+                                         "bound enum (hbm | tensor) has no entry for an integer max-plus recurrence"),
                       peak_source="148 SM x 4 SMSP x 16 lanes/clk x sm_mhz / 9 ALU-pipe instructions per cell (no tensor cores: "
                                   "max-plus integer DP); MEASURED_PEAKS.json has no integer figure",
                       note="achieved = DP cells as the reference's loops visit them (credited count, one exact-count pass) / "

@@ -1,11 +1,21 @@
 // thermite_gpu.cu -- CUDA kernels (sm_100a) and the device half of the C ABI of libthermite_gpu.so.
 //
-// Kernels (one warp owns one read / one task from start to finish; warps pull work from a global counter):
-//   k_kmer_count / k_kmer_insert  build the open-addressing k-mer table over the suffix array (ctx create)
-//   k_seed      Index::all_smems           (reference src/index.rs:228-255)      HBM random-access bound
-//   k_extend    align_read hit loop        (src/aligner.rs:123-449, src/swg.rs, src/txome.rs)   INT-pipe bound
-//   k_swg_batch SwgExtend::extend, batched (src/swg.rs:31-207)                   INT-pipe bound
-// The algorithmic code lives in tg_core.h.  No CPU fallback exists: every entry point below needs a device.
+// Kernels (reference file:line of what each replaces; design in DESIGN.md section 4):
+//   k_kmer_count / k_kmer_insert      open-addressing k-mer table over the suffix array (ctx create)
+//   k_pack_reads, k_probe_light, k_probe_heavy, k_seed_select
+//                                     Index::all_smems (src/index.rs:228-255): thread per (read, offset) probes in
+//                                     three waves, thread per read SMEM selection.  HBM random-access bound
+//   k_round_{init,plan,prep,hist,binscan,scatter,post,scan,final}
+//                                     align_read / align_seed_hit (src/aligner.rs:123-449, src/txome.rs:82-160) as the
+//                                     speculative round pipeline of tg_rounds.h: thread per read / per hit
+//   k_round_dpt<0..3>                 SwgExtend::extend / trace (src/swg.rs:31-207): thread per extension, band in
+//                                     registers (tg_dpt.h), one kernel per group of band classes.  INT-pipe bound
+//   k_round_dp<R>, k_swg_batch<R>     the same on the warp-cooperative wavefront (tg_core.h): long reads, very wide
+//                                     bands, raw-byte pairs of tg_swg_extend_batch
+//   k_extend<R>                       one warp walks one read start to finish (tg_align_read): reads the round
+//                                     pipeline cannot hold, and tg_ctx_set_round_pipeline(ctx, 0)
+//   k_swg_prepare / k_swg_collect     tg_swg_extend_batch on the thread kernels;  k_random_gather: HBM yardstick
+// No CPU fallback exists: every entry point below needs a device.
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
