@@ -250,22 +250,27 @@ TG_HD bool tg_seed_offset(const uint64_t* rp, uint32_t L, uint32_t q, uint32_t k
 // records.  hits[q] valid for q + k <= L.
 // Order: bio emits, for i0 = 0, max-end, ...: the SMEMs covering i0 by DESCENDING start; then
 // src/index.rs:251-253 stable-sorts by len ascending and reverses => len DESC, ties in REVERSE emission order.
-TG_HD uint32_t tg_smem_count(const TgSeedHit* hits, uint32_t L, uint32_t k) {  // number of SMEMs (<= L - k + 1)
+// `sampled`: the table was filled by the probe waves (TG_PROBE_STRIDE): offsets inside a closed bracket hold nothing and
+// are stepped over -- their E equals the bracket's, so none of them starts an SMEM.
+#define TG_PROBE_STRIDE 8u
+TG_HD uint32_t tg_probe_step(const TgSeedHit* row, uint32_t q, uint32_t q_last);
+TG_HD uint32_t tg_smem_count(const TgSeedHit* hits, uint32_t L, uint32_t k, bool sampled = false) {  // number of SMEMs
   if (L < k || k == 0) return 0;
   uint32_t n = 0, prev_e = 0;
-  for (uint32_t q = 0; q + k <= L; q++) {
+  for (uint32_t q = 0; q + k <= L;) {
     const uint32_t e = hits[q].e;
     if (e != 0 && (q == 0 || prev_e < e)) n++;
     prev_e = e;
     if (e == L) break;  // E is non-decreasing: every later offset ends at L too and starts no SMEM
+    q = sampled ? tg_probe_step(hits, q, L - k) : q + 1;
   }
   return n;
 }
 // out: room for tg_smem_count() records; the `pad` field is used as scratch (emission group) and left 0
-TG_HD uint32_t tg_smem_select(const TgSeedHit* hits, uint32_t L, uint32_t k, tg_seed* out) {
+TG_HD uint32_t tg_smem_select(const TgSeedHit* hits, uint32_t L, uint32_t k, tg_seed* out, bool sampled = false) {
   if (L < k || k == 0) return 0;
   uint32_t n = 0, prev_e = 0;
-  for (uint32_t q = 0; q + k <= L; q++) {
+  for (uint32_t q = 0; q + k <= L;) {
     const TgSeedHit h = hits[q];
     const uint32_t e = h.e;
     if (e != 0 && (q == 0 || prev_e < e)) {
@@ -275,6 +280,7 @@ TG_HD uint32_t tg_smem_select(const TgSeedHit* hits, uint32_t L, uint32_t k, tg_
     }
     prev_e = e;
     if (e == L) break;
+    q = sampled ? tg_probe_step(hits, q, L - k) : q + 1;
   }
   // emission groups
   uint32_t i0 = 0, idx = 0, g = 0;
@@ -1287,7 +1293,6 @@ TG_HD uint64_t tg_pack_word(const uint8_t* bases, uint64_t off, uint32_t L, uint
 //   wave 0: q = 0.  If the whole read matches (E(0) == L) nothing else is probed.
 //   wave 1: the sample offsets S, 2S, ... and the last offset L - k.
 //   wave 2: every other offset, probed only when its two bracketing samples disagree (or found nothing).
-#define TG_PROBE_STRIDE 8u
 TG_HD bool tg_probe_is_sample(uint32_t q, uint32_t q_last) { return q % TG_PROBE_STRIDE == 0 || q == q_last; }
 // the j-th wave-1 offset of a read whose last offset is q_last (0xFFFFFFFF: none)
 TG_HD uint32_t tg_probe_sample(uint32_t j, uint32_t q_last) {
@@ -1295,20 +1300,26 @@ TG_HD uint32_t tg_probe_sample(uint32_t j, uint32_t q_last) {
   if (q < q_last) return q;
   return q - TG_PROBE_STRIDE < q_last ? q_last : 0xFFFFFFFFu;
 }
-// wave 2: true (and the entry is filled in) when the bracketing samples make the probe unnecessary
-TG_HD bool tg_probe_bracketed(TgSeedHit* row, uint32_t q, uint32_t q_last) {
+// wave 2: true when the bracketing samples make the probe unnecessary (the entry is then never written nor read:
+// tg_smem_count / tg_smem_select step over closed brackets)
+TG_HD bool tg_probe_bracketed(const TgSeedHit* row, uint32_t q, uint32_t q_last) {
   const uint32_t qa = q - q % TG_PROBE_STRIDE;
   const uint32_t qb = qa + TG_PROBE_STRIDE < q_last ? qa + TG_PROBE_STRIDE : q_last;
   const uint32_t ea = row[qa].e, eb = row[qb].e;
-  if (ea != eb || ea == 0) return false;
-  row[q].e = ea; row[q].lo = 0; row[q].cnt = 0;
-  return true;
+  return ea == eb && ea != 0;
+}
+// at sample offset q of a sampled probe table: the offset to continue with (the other end of a closed bracket, else q + 1)
+TG_HD uint32_t tg_probe_step(const TgSeedHit* row, uint32_t q, uint32_t q_last) {
+  if (q % TG_PROBE_STRIDE != 0 || q >= q_last) return q + 1;
+  const uint32_t qb = q + TG_PROBE_STRIDE < q_last ? q + TG_PROBE_STRIDE : q_last;
+  const uint32_t ea = row[q].e;
+  return (qb > q + 1 && ea != 0 && ea == row[qb].e) ? qb : q + 1;
 }
 
 // Index::all_smems for one read from its probe results: SMEM records into the seed pool.
 template <class W>
 TG_HDN void tg_seed_select_read(W& w, const TgSeedHit* hits, uint32_t L, uint32_t k, const TgSeedOut& out, uint32_t r) {
-  const uint32_t n = tg_smem_count(hits, L, k);
+  const uint32_t n = tg_smem_count(hits, L, k, true);
   unsigned long long base = 0;
   uint32_t nn = n;
   if (n) {
@@ -1318,7 +1329,7 @@ TG_HDN void tg_seed_select_read(W& w, const TgSeedHit* hits, uint32_t L, uint32_
       nn = 0;
     }
   }
-  if (nn) tg_smem_select(hits, L, k, out.pool + base);
+  if (nn) tg_smem_select(hits, L, k, out.pool + base, true);
   out.read_first[r] = base;
   out.read_count[r] = nn;
   if (nn) w.atomic_add(out.n_smems, (unsigned long long)nn);
