@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale (1.0 = chr21-sized stand-in)")
-    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per step per GPU")
+    ap.add_argument("--reads", type=int, default=4_000_000, help="reads per step per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline work per step (all threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -391,7 +391,7 @@ def _main(args):
         data="synthetic",
         config=dict(workload=workload_name(args.scale), reads_per_step_per_gpu=n, read_len=READ_LEN,
                     flags="-k20 -s0 --intron-mode", parallelism=f"reads sharded over {world} GPU(s), index replicated",
-                    l2="inputs larger than L2: per step 91 MB of reads against a k-mer table + suffix array + text of several GB",
+                    l2=f"inputs larger than L2: per step {n * READ_LEN / 1e6:.0f} MB of reads against a k-mer table + suffix array + text of several GB",
                     index_bytes=int(index.blob().nbytes), kmer_table_bytes=int(aligner.kmer_table_bytes()),
                     index_broadcast_ms=bcast_ms, setup_s=setup_s),
         e2e=dict(value=e2e_value, unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),

@@ -1504,9 +1504,9 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
     k_round_post<<<iblocks, 128, 0, c->stream>>>(p);
     k_round_scan<<<tblocks, 128, 0, c->stream>>>(p);
     c->n_launches += 4;
-    if (r == 1 && c->early_out) {
-      // ~98 % of the reads are finished now: write their records and start moving them to the host while the late
-      // rounds (few reads, many hits each) run
+    if (r <= 1 && c->early_out) {
+      // ~55 % of the reads are finished after round 0 and ~98 % after round 1: write their records now and move them to
+      // the host while the next rounds run (the records of round 0 travel under round 1, the heaviest one)
       p.early = 1;
       k_round_final<<<tblocks, 128, 0, c->stream>>>(p);
       p.early = 0;
@@ -1514,11 +1514,19 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
       CU_CHECK(cudaMemcpyAsync(c->h_snap, &c->d_ctr->alns_used, 16, cudaMemcpyDeviceToHost, c->stream));
       CU_CHECK(cudaStreamSynchronize(c->stream));
       const unsigned long long a1 = std::min<unsigned long long>(c->h_snap[0], c->alns_cap), o1 = std::min<unsigned long long>(c->h_snap[1], c->ops_cap);
-      CU_CHECK(cudaStreamSynchronize(c->copy_out));  // (idle unless an earlier attempt of this batch was abandoned)
-      if ((st = c->h_alns.ensure((size_t)(a1 + a1 / 16 + 65536) * sizeof(tg_aln))) != TG_OK) return st;
-      if ((st = c->h_ops.ensure((size_t)(o1 + o1 / 16 + 262144) * 4)) != TG_OK) return st;
-      if (a1) CU_CHECK(cudaMemcpyAsync(c->h_alns.p, c->d_alns.p, (size_t)a1 * sizeof(tg_aln), cudaMemcpyDeviceToHost, c->copy_out));
-      if (o1) CU_CHECK(cudaMemcpyAsync(c->h_ops.p, c->d_ops.p, (size_t)o1 * 4, cudaMemcpyDeviceToHost, c->copy_out));
+      const unsigned long long a0 = c->early_alns, o0 = c->early_ops;
+      // room for the whole batch, estimated from what is known (grown again at the end if a batch needs more)
+      const size_t want_a = (size_t)std::max<unsigned long long>(a1 + a1 / 16, (unsigned long long)n + n / 8) + 65536;
+      const size_t want_o = (size_t)std::max<unsigned long long>(o1 + o1 / 16, r == 0 ? 3 * o1 : 0ull) + 262144;
+      if (want_a * sizeof(tg_aln) > c->h_alns.cap || want_o * 4 > c->h_ops.cap) {
+        CU_CHECK(cudaStreamSynchronize(c->copy_out));  // what was sent so far has landed before the buffers move
+        if ((st = c->h_alns.ensure_keep(want_a * sizeof(tg_aln), (size_t)a0 * sizeof(tg_aln))) != TG_OK) return st;
+        if ((st = c->h_ops.ensure_keep(want_o * 4, (size_t)o0 * 4)) != TG_OK) return st;
+      }
+      if (a1 > a0)
+        CU_CHECK(cudaMemcpyAsync((tg_aln*)c->h_alns.p + a0, (tg_aln*)c->d_alns.p + a0, (size_t)(a1 - a0) * sizeof(tg_aln), cudaMemcpyDeviceToHost, c->copy_out));
+      if (o1 > o0)
+        CU_CHECK(cudaMemcpyAsync((uint32_t*)c->h_ops.p + o0, (uint32_t*)c->d_ops.p + o0, (size_t)(o1 - o0) * 4, cudaMemcpyDeviceToHost, c->copy_out));
       c->early_alns = a1; c->early_ops = o1;
     }
     // late rounds are short: a host check for "nothing left" costs less than launching the remaining empty rounds
