@@ -133,7 +133,8 @@ void tg_index_destroy(tg_index* ix);
 typedef struct tg_ctx tg_ctx;
 tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out);
 void tg_ctx_destroy(tg_ctx* ctx);
-/* tg_align_batch copies the bases of a large batch in chunks of this many reads (default 262144) and seeds every chunk
+/* tg_align_batch copies the bases of a large batch in chunks of this many reads (0 = default: an eighth of the batch, at
+ * least 262,144 reads) and seeds every chunk
  * as soon as it has landed; at the other end the records of the reads that are finished after the second round travel to
  * the host while the late rounds run.  Results do not depend on the chunk size. */
 void tg_ctx_set_chunk_reads(tg_ctx* ctx, uint32_t reads);

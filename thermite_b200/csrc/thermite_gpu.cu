@@ -1058,7 +1058,7 @@ struct tg_ctx {
   unsigned long long early_alns = 0, early_ops = 0;  // what has been sent to the host already
   uint32_t in_chunks = 0, in_chunk_reads = 0;        // host-buffer path: seeding follows the input copies chunk by chunk
   std::vector<cudaEvent_t> ev_in;
-  uint32_t chunk_reads = 262144;
+  uint32_t chunk_reads = 0;  // 0: automatic (an eighth of the batch, at least 262,144 reads)
   uint64_t n_launches = 0;  // kernels launched by the last batch call
   // host results
   PinBuf h_first, h_count, h_alns, h_ops, h_seeds, h_seed_first, h_seed_count;
@@ -1240,7 +1240,7 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
 }
 
 void tg_ctx_set_chunk_reads(tg_ctx* ctx, uint32_t reads) {
-  if (ctx) ctx->chunk_reads = reads < 1024 ? 1024 : reads;
+  if (ctx) ctx->chunk_reads = reads == 0 ? 0 : (reads < 1024 ? 1024 : reads);
 }
 void* tg_ctx_stream(tg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
@@ -1681,7 +1681,9 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
   // Copies overlap kernels at both ends of the call (three streams): the bases arrive in chunks and every chunk is
   // seeded as soon as it has landed; the records of the reads that are finished after round 1 (~98 %) travel to the
   // host while the late rounds run.  One pass over the whole batch, one contiguous result.
-  const uint32_t chunk = n_reads >= 2 * c->chunk_reads ? c->chunk_reads : n_reads;
+  // measured on B200: ~4-8 chunks hide the input copy best; smaller chunks lose more in the seeding kernels than they hide
+  const uint32_t want = c->chunk_reads ? c->chunk_reads : std::max<uint32_t>(262144u, (n_reads + 7) / 8);
+  const uint32_t chunk = n_reads >= 2 * (uint64_t)want ? want : n_reads;
   const uint32_t n_chunks = (n_reads + chunk - 1) / chunk;
   const uint64_t total = offs[n_reads];
   if ((st = c->d_bases.ensure(total + 64)) != TG_OK) return st;
