@@ -21,9 +21,11 @@
 #include <cooperative_groups/scan.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "tg_rounds.h"
@@ -179,6 +181,7 @@ struct DevCounters {
   unsigned long long n_complex, work_complex;
   unsigned long long probe_n[3][2];  // per probe wave: queued probes, deferred (multi-occurrence) probes
   unsigned long long items_used, hops_used, fin_used;
+  unsigned long long n_late;  // reads finalised by the LAST pass (their first/count reach the host as a fix-up list)
   unsigned long long round_end[TG_MAX_ROUNDS];  // items_used after round r
   unsigned long long round_active[TG_MAX_ROUNDS];  // reads still unfinished after round r
   unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS][4];
@@ -438,6 +441,7 @@ struct RoundParams {
   uint32_t* complex_list;
   uint32_t round;
   int early;               // k_round_final: first pass (finished reads only)
+  ulonglong2* late;        // last pass: {first, read | count << 32} of every read it finalises (null: not recorded)
   uint32_t* sorted;        // task indices of the round, grouped by class and (descending) column count
   uint32_t* dpt_trace;     // thread kernels: per class group, [warp][col][word][lane]
   size_t dpt_trace_off[4], dpt_trace_words[4];  // region of each group, words per warp
@@ -777,6 +781,8 @@ __global__ void __launch_bounds__(128) k_round_final(RoundParams p) {
       tg_round_final<DevThread, uint32_t>(w, p.P, st, p.cands, p.ires, p.hp.w, f, f + st.n_acc, f + 2 * (size_t)st.n_acc, p.out, r);
     }
     cells += st.cells; n_ext += st.n_ext; hits += st.hits;
+    if (!p.early && p.late && p.st[r].status == TG_RS_FINAL)
+      p.late[warp_agg_add(&p.ctr->n_late, 1ull)] = make_ulonglong2(p.out.read_aln_first[r], (unsigned long long)r | ((unsigned long long)p.out.read_aln_count[r] << 32));
   }
   cells = warp_sum(cells); n_ext = warp_sum(n_ext); hits = warp_sum(hits);
   if ((threadIdx.x & 31) == 0) {
@@ -1045,7 +1051,9 @@ struct tg_ctx {
   uint64_t alns_cap = 0, ops_cap = 0;
   uint32_t scratch_warps = 0;
   // round pipeline scratch
-  DevBuf r_state, r_hits, r_ires, r_cands, r_hops, r_fin, r_rp, r_tasks, r_ops, r_complex, r_sorted, r_dpt_trace;
+  DevBuf r_state, r_hits, r_ires, r_cands, r_hops, r_fin, r_rp, r_tasks, r_ops, r_complex, r_sorted, r_dpt_trace, r_late;
+  PinBuf h_late;
+  int early_rows = 0;  // host-buffer path: first/count went to the host after round 1; the last pass sends a fix-up list
   uint64_t round_task_cap = 0, round_ops_cap = 0, item_cap = 0, hops_cap = 0;
   int use_rounds = 1;
   // chunked host-buffer path: results of chunk k start at these pool positions / read row
@@ -1160,11 +1168,11 @@ void tg_ctx_destroy(tg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->ix->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_probe, &c->d_queue, &c->d_queue2, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_ires, &c->r_cands, &c->r_hops, &c->r_fin, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex, &c->r_sorted, &c->r_dpt_trace,
+  for (DevBuf* b : {&c->d_bases, &c->d_offs, &c->d_seeds, &c->d_seed_first, &c->d_seed_count, &c->d_probe, &c->d_queue, &c->d_queue2, &c->d_cands, &c->d_arena, &c->d_order, &c->r_state, &c->r_hits, &c->r_ires, &c->r_cands, &c->r_hops, &c->r_fin, &c->r_rp, &c->r_tasks, &c->r_ops, &c->r_complex, &c->r_sorted, &c->r_dpt_trace, &c->r_late,
                     &c->d_aln_first, &c->d_aln_count, &c->d_alns, &c->d_ops, &c->s_x, &c->s_xo, &c->s_y, &c->s_yo, &c->s_bw,
                     &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops, &c->s_ypk, &c->s_ysym})
     b->release();
-  for (PinBuf* b : {&c->h_first, &c->h_count, &c->h_alns, &c->h_ops, &c->h_seeds, &c->h_seed_first, &c->h_seed_count}) b->release();
+  for (PinBuf* b : {&c->h_first, &c->h_count, &c->h_alns, &c->h_ops, &c->h_seeds, &c->h_seed_first, &c->h_seed_count, &c->h_late}) b->release();
   if (c->slots) cudaFree(c->slots);
   if (c->d_ctr) cudaFree(c->d_ctr);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -1466,6 +1474,12 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.tasks = (TgTask*)c->r_tasks.p; p.task_cap = c->round_task_cap;
   p.ops_pool = (uint32_t*)c->r_ops.p; p.ops_cap = c->round_ops_cap;
   p.complex_list = (uint32_t*)c->r_complex.p; p.round = 0; p.early = 0;
+  p.late = nullptr;
+  c->early_rows = 0;
+  if (c->early_out) {
+    if ((st = c->r_late.ensure((size_t)n * 16 + 64)) != TG_OK) return st;
+    p.late = (ulonglong2*)c->r_late.p;
+  }
   p.max_xlen = max_xlen; p.max_cols = max_cols; p.trace_bytes = trace_bytes; p.ops_words = ops_words;
   p.bound_stop = c->exact_cells ? 0 : 1;
   p.out.read_aln_first = (uint64_t*)c->d_aln_first.p + c->out_row0; p.out.read_aln_count = (uint32_t*)c->d_aln_count.p + c->out_row0;
@@ -1528,6 +1542,11 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
       if (o1 > o0)
         CU_CHECK(cudaMemcpyAsync((uint32_t*)c->h_ops.p + o0, (uint32_t*)c->d_ops.p + o0, (size_t)(o1 - o0) * 4, cudaMemcpyDeviceToHost, c->copy_out));
       c->early_alns = a1; c->early_ops = o1;
+      if (r == 1) {  // first/count of every read that is finished by now; the others follow as a fix-up list
+        CU_CHECK(cudaMemcpyAsync(c->h_first.p, c->d_aln_first.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->copy_out));
+        CU_CHECK(cudaMemcpyAsync(c->h_count.p, c->d_aln_count.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->copy_out));
+        c->early_rows = 1;
+      }
     }
     // late rounds are short: a host check for "nothing left" costs less than launching the remaining empty rounds
     if (r >= 2 && r + 1 < TG_MAX_ROUNDS) {
@@ -1678,6 +1697,9 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
   if (n_reads == 0) return TG_OK;
   if (!bases && offs[n_reads] > 0) return tg_fail(TG_ERR_INVALID, "null argument");
   tg_ctx* c = ctx;
+  const bool dbg = getenv("TG_DEBUG_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_in = now();
   // Copies overlap kernels at both ends of the call (three streams): the bases arrive in chunks and every chunk is
   // seeded as soon as it has landed; the records of the reads that are finished after round 1 (~98 %) travel to the
   // host while the late rounds run.  One pass over the whole batch, one contiguous result.
@@ -1697,19 +1719,40 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
   uint32_t maxL = 1;
   for (uint32_t k = 0; k < n_chunks; k++) {
     const uint32_t r0 = k * chunk, r1 = std::min(n_reads, r0 + chunk);
-    {  // validate while earlier copies are in flight (branch-free so that the compiler vectorises it: ~0.3 ns per read)
-      uint64_t longest = 0, decreasing = 0;
-      for (uint32_t r = r0; r < r1; r++) {
-        const uint64_t a = offs[r], b = offs[r + 1];
-        decreasing |= (uint64_t)(b < a);
-        const uint64_t d = b - a;
-        longest = d > longest ? d : longest;
+    {  // validate while earlier copies are in flight.  The offsets are 8 B per read and stream from host DRAM: one
+       // fused pass, split over a few threads for large chunks (a single core reads ~10 GB/s)
+      const uint64_t* o = offs + r0;
+      const uint32_t m = r1 - r0;
+      const uint32_t T = m >= 131072 ? 4 : 1;
+      uint64_t wide_t[4] = {0, 0, 0, 0};    // non-zero when some length is >= 1024 or negative (offsets decreasing)
+      uint32_t longest_t[4] = {0, 0, 0, 0};
+      auto scan = [&](uint32_t t) {
+        const uint32_t i0 = (uint32_t)((uint64_t)m * t / T), i1 = (uint32_t)((uint64_t)m * (t + 1) / T);
+        uint64_t wide = 0;
+        uint32_t longest = 0;
+        for (uint32_t i = i0; i < i1; i++) {
+          const uint64_t d = o[i + 1] - o[i];
+          wide |= d >> 10;
+          longest = (uint32_t)d > longest ? (uint32_t)d : longest;
+        }
+        wide_t[t] = wide; longest_t[t] = longest;
+      };
+      if (T == 1) scan(0);
+      else {
+        std::thread th[3];
+        for (uint32_t t = 1; t < T; t++) th[t - 1] = std::thread(scan, t);
+        scan(0);
+        for (uint32_t t = 1; t < T; t++) th[t - 1].join();
       }
-      if (decreasing || longest > TG_MAX_READ_LEN) {
+      const uint64_t wide = wide_t[0] | wide_t[1] | wide_t[2] | wide_t[3];
+      const uint32_t longest = std::max(std::max(longest_t[0], longest_t[1]), std::max(longest_t[2], longest_t[3]));
+      if (wide || longest > TG_MAX_READ_LEN) {
+        bool decreasing = false;
+        for (uint32_t i = 0; i < m; i++) decreasing |= o[i + 1] < o[i];
         cudaStreamSynchronize(c->copy_in);
         return tg_fail(TG_ERR_INVALID, decreasing ? "read offsets must be non-decreasing" : "read longer than TG_MAX_READ_LEN");
       }
-      maxL = std::max<uint32_t>(maxL, (uint32_t)longest);
+      maxL = std::max<uint32_t>(maxL, longest);
     }
     const uint64_t b0 = offs[r0], b1 = offs[r1];
     if (b1 > b0) CU_CHECK(cudaMemcpyAsync((uint8_t*)c->d_bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_in));
@@ -1718,11 +1761,13 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
   // maxL of the whole batch is needed before the first kernel: the loop above has run over every read by now
   if ((st = c->h_first.ensure((size_t)n_reads * 8)) != TG_OK) return st;
   if ((st = c->h_count.ensure((size_t)n_reads * 4)) != TG_OK) return st;
+  const double t_issued = now();
   c->n_launches = 0;
   c->in_chunks = n_chunks; c->in_chunk_reads = chunk;
   c->early_out = c->use_rounds ? 1 : 0;
   st = run_pipeline(c, (const uint8_t*)c->d_bases.p, (const uint64_t*)c->d_offs.p, n_reads, maxL, true);
   c->in_chunks = 0; c->early_out = 0;
+  const double t_pipe = now();
   if (st != TG_OK) { cudaStreamSynchronize(c->copy_out); return st; }
   fill_result(c, n_reads, out);
   const uint64_t ea = std::min<uint64_t>(c->early_alns, out->n_alns), eo = std::min<uint64_t>(c->early_ops, out->n_ops);
@@ -1731,8 +1776,19 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
     if ((st = c->h_alns.ensure_keep((size_t)out->n_alns * sizeof(tg_aln) + 16, ea * sizeof(tg_aln))) != TG_OK) return st;
     if ((st = c->h_ops.ensure_keep((size_t)out->n_ops * 4 + 16, eo * 4)) != TG_OK) return st;
   }
-  CU_CHECK(cudaMemcpyAsync(c->h_first.p, c->d_aln_first.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU_CHECK(cudaMemcpyAsync(c->h_count.p, c->d_aln_count.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+  // first/count: already on their way for the reads finished after round 1; the last pass lists the rest (a few per cent).
+  // Reads redone by the single-warp kernel are not in that list: then everything is copied again.
+  const uint64_t n_late = c->h_ctr->n_late;
+  const bool fixup = c->early_rows && c->h_ctr->n_complex == 0;
+  c->early_rows = 0;
+  if (fixup) {
+    if ((st = c->h_late.ensure((size_t)n_late * 16 + 16)) != TG_OK) return st;
+    if (n_late) CU_CHECK(cudaMemcpyAsync(c->h_late.p, c->r_late.p, (size_t)n_late * 16, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    CU_CHECK(cudaStreamSynchronize(c->copy_out));  // (an early copy of the same arrays must not land after this one)
+    CU_CHECK(cudaMemcpyAsync(c->h_first.p, c->d_aln_first.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaMemcpyAsync(c->h_count.p, c->d_aln_count.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
   if (out->n_alns > ea)
     CU_CHECK(cudaMemcpyAsync((tg_aln*)c->h_alns.p + ea, (tg_aln*)c->d_alns.p + ea, (size_t)(out->n_alns - ea) * sizeof(tg_aln),
                              cudaMemcpyDeviceToHost, c->stream));
@@ -1741,6 +1797,19 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
                              cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(cudaStreamSynchronize(c->stream));
   CU_CHECK(cudaStreamSynchronize(c->copy_out));
+  if (fixup) {
+    const unsigned long long* l = (const unsigned long long*)c->h_late.p;
+    uint64_t* hf = (uint64_t*)c->h_first.p;
+    uint32_t* hc = (uint32_t*)c->h_count.p;
+    for (uint64_t i = 0; i < n_late; i++) {
+      const uint32_t r = (uint32_t)(l[2 * i + 1] & 0xFFFFFFFFull);
+      hf[r] = l[2 * i];
+      hc[r] = (uint32_t)(l[2 * i + 1] >> 32);
+    }
+  }
+  if (dbg)
+    fprintf(stderr, "tg_align_batch: issue inputs %.2f ms, pipeline %.2f ms (seed %.2f + extend %.2f on the device), tail %.2f ms\n",
+            t_issued - t_in, t_pipe - t_issued, c->last_seed_ms, c->last_extend_ms, now() - t_pipe);
   out->read_aln_first = (const uint64_t*)c->h_first.p;
   out->read_aln_count = (const uint32_t*)c->h_count.p;
   out->alns = (const tg_aln*)c->h_alns.p;
