@@ -1518,7 +1518,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
     k_round_post<<<iblocks, 128, 0, c->stream>>>(p);
     k_round_scan<<<tblocks, 128, 0, c->stream>>>(p);
     c->n_launches += 4;
-    if (r <= 1 && c->early_out) {
+    if (r <= 1 && c->early_out && (c->early_out > 1 || r == 1)) {
       // ~55 % of the reads are finished after round 0 and ~98 % after round 1: write their records now and move them to
       // the host while the next rounds run (the records of round 0 travel under round 1, the heaviest one)
       p.early = 1;
@@ -1764,7 +1764,10 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
   const double t_issued = now();
   c->n_launches = 0;
   c->in_chunks = n_chunks; c->in_chunk_reads = chunk;
-  c->early_out = c->use_rounds ? 1 : 0;
+  {
+    const char* em = getenv("TG_EARLY_MODE");  // experiments: 0 no early output, 1 after round 1 only, 2 (default) after rounds 0 and 1
+    c->early_out = c->use_rounds ? (em ? atoi(em) : 2) : 0;
+  }
   st = run_pipeline(c, (const uint8_t*)c->d_bases.p, (const uint64_t*)c->d_offs.p, n_reads, maxL, true);
   c->in_chunks = 0; c->early_out = 0;
   const double t_pipe = now();
