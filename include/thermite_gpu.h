@@ -3,6 +3,7 @@
  *
  * What each entry point replaces in the reference (paths under /root/reference):
  *   tg_index_host_create_*   Index::create_from_files              src/index.rs:52-223
+ *   tg_index_host_create_*_gpu, tg_suffix_array_gpu   the same with divsufsort64 (src/index.rs:103-105) on the GPU
  *   tg_index_host_save/load  bincode .tai (de)serialisation        src/main.rs:37-43, 63-67; src/wrapper.rs:31-37
  *   tg_index_host_* getters  Index::refs() / Index::txome()        src/index.rs:293-300 (used by src/aln_writer.rs:179-213,257)
  *   tg_index_create*         (new) upload / adopt the flat index in HBM; one replica per GPU
@@ -96,6 +97,20 @@ typedef struct tg_index_host tg_index_host;
 tg_status tg_index_host_create_from_files(const char* fasta_path, const char* gtf_path, tg_index_host** out);
 tg_status tg_index_host_create_from_memory(const char* fasta_text, size_t fasta_len, const char* gtf_text,
                                            size_t gtf_len, tg_index_host** out);
+/* Same index, but the suffix array -- divsufsort64 in the reference (src/index.rs:103-105), the dominant cost of index
+ * creation -- is built on GPU `device` by prefix doubling over the unresolved suffixes (csrc/tg_sa.cu).
+ * The blob is byte-identical to the one the host-only functions produce.  Needs ~46 B of HBM per text symbol. */
+tg_status tg_index_host_create_from_files_gpu(const char* fasta_path, const char* gtf_path, int device,
+                                              tg_index_host** out);
+tg_status tg_index_host_create_from_memory_gpu(const char* fasta_text, size_t fasta_len, const char* gtf_text,
+                                               size_t gtf_len, int device, tg_index_host** out);
+/* The suffix-array builder on its own.  text4 = HOST pointer to text_len symbols as 4-bit codes ($ACGNT = 0..5), 16 per
+ * u64 with the first symbol in the most significant nibble, followed by at least one zero word; sa_out = HOST buffer of
+ * text_len u32.  Order: plain lexicographic, a suffix that is a proper prefix of another one first (what divsufsort64
+ * returns for the reference's `$`-joined text).  device_ms / n_steps (optional): device time without the copies and
+ * the number of sort steps taken. */
+tg_status tg_suffix_array_gpu(const uint64_t* text4, uint64_t text_len, int device, uint32_t* sa_out, float* device_ms,
+                              uint32_t* n_steps);
 /* One contiguous, position-independent blob (what is saved to disk, uploaded, or broadcast over NCCL). */
 tg_status tg_index_host_blob(const tg_index_host* ix, const void** data, size_t* nbytes);
 tg_status tg_index_host_from_blob(const void* data, size_t nbytes, tg_index_host** out);
@@ -116,6 +131,8 @@ const char* tg_index_host_gene_id(const tg_index_host* ix, uint32_t i);
 const char* tg_index_host_gene_name(const tg_index_host* ix, uint32_t i);
 /* Suffix array (text_len u32 entries) -- exposed so callers can expand tg_seed records into Mems. */
 const uint32_t* tg_index_host_sa(const tg_index_host* ix);
+/* Packed both-strand text (text_len 4-bit codes, 16 per u64, text_len / 16 + 4 words): the input of tg_suffix_array_gpu. */
+const uint64_t* tg_index_host_text4(const tg_index_host* ix);
 
 /* ---------------------------------------------------------------------------------------------------
  * Device index (HBM-resident replica)

@@ -144,3 +144,20 @@ def test_device_entry_points_fail_loudly_without_gpu():
     ix = tb.Index.create_from_memory(golden("test_ref.fasta"), golden("test_ref.gtf"))
     with pytest.raises(tb.ThermiteError, match="no CPU fallback|CUDA"):
         tb.Aligner(ix)
+    # the GPU suffix-array builder has no host fallback either
+    with pytest.raises(tb.ThermiteError, match="no CPU fallback"):
+        tb.suffix_array_gpu(ix.text4(), ix.text_len(), 0)
+    with pytest.raises(tb.ThermiteError, match="no CPU fallback"):
+        tb.Index.create_from_memory(golden("test_ref.fasta"), golden("test_ref.gtf"), sa_device=0)
+
+
+def test_text4_is_the_packed_both_strand_text():
+    """tg_index_host_text4 (input of tg_suffix_array_gpu): 4-bit codes $ACGNT = 0..5, first symbol in the top nibble,
+    zero padded; the suffix array over it orders the suffixes byte-lexicographically, a proper prefix first."""
+    ix = tb.Index.create_from_memory(golden("test_ref.fasta"), golden("test_ref.gtf"))
+    n, t4 = ix.text_len(), ix.text4()
+    codes = np.array([(int(t4[i >> 4]) >> (4 * (15 - (i & 15)))) & 15 for i in range(n)], np.uint8)
+    assert codes.max() <= 5 and (codes == 0).sum() == len(ix.refs()) and codes[-1] == 0
+    assert all(int(w) == 0 for w in t4[(n + 15) // 16:]) and len(t4) == n // 16 + 4
+    b = bytes(codes + 1)
+    assert list(ix.suffix_array()) == sorted(range(n), key=lambda i: b[i:])

@@ -69,6 +69,7 @@ ABI_SYMBOLS = [
     "tg_index_host_from_blob", "tg_index_host_save", "tg_index_host_load", "tg_index_host_destroy",
     "tg_index_host_text_len", "tg_index_host_n_refs", "tg_index_host_n_txs", "tg_index_host_n_genes",
     "tg_index_host_ref", "tg_index_host_tx", "tg_index_host_gene_id", "tg_index_host_gene_name", "tg_index_host_sa",
+    "tg_index_host_text4", "tg_index_host_create_from_files_gpu", "tg_index_host_create_from_memory_gpu", "tg_suffix_array_gpu",
     "tg_index_create", "tg_index_create_from_device_blob", "tg_index_destroy",
     "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_set_chunk_reads", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_bench_random_gather", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
     "tg_align_batch", "tg_align_batch_device", "tg_seed_batch", "tg_swg_extend_batch",
@@ -90,6 +91,7 @@ def lib():
         for f in ("tg_index_host_ref", "tg_index_host_tx", "tg_index_host_gene_id", "tg_index_host_gene_name"):
             getattr(L, f).restype = C.c_char_p
         L.tg_index_host_sa.restype = C.c_void_p
+        L.tg_index_host_text4.restype = C.c_void_p
         L.tg_ctx_stream.restype = C.c_void_p
         L.tg_ctx_kmer_table_bytes.restype = C.c_uint64
         L.tg_ctx_last_kernel_launches.restype = C.c_uint64
@@ -168,6 +170,20 @@ class Txome:
         self.genes, self.txs = genes, txs
 
 
+def suffix_array_gpu(text4: np.ndarray, text_len: int, device: int = 0):
+    """Suffix array of a packed text on the GPU (csrc/tg_sa.cu; divsufsort64 at src/index.rs:103-105).
+    `text4` needs at least one zero word behind the text.  Returns (sa, device_ms, sort_steps)."""
+    text4 = np.ascontiguousarray(text4, np.uint64)
+    if len(text4) < text_len // 16 + 2:
+        raise ThermiteError("text4 needs a zero word behind the text")
+    if len(text4) < text_len // 16 + 4:
+        text4 = np.concatenate([text4, np.zeros(4, np.uint64)])
+    sa = np.empty(text_len, np.uint32)
+    ms, steps = C.c_float(0), C.c_uint32(0)
+    _check(lib().tg_suffix_array_gpu(_p(text4), C.c_uint64(text_len), C.c_int(device), _p(sa), C.byref(ms), C.byref(steps)))
+    return sa, ms.value, steps.value
+
+
 class Index:
     """Flat host index + (lazily) its HBM replica.  src/index.rs:40-44."""
 
@@ -179,18 +195,27 @@ class Index:
     # -- construction ---------------------------------------------------------------------------------------
     @classmethod
     def create_from_files(cls, ref_path: str, annot_path: str, sa_sampling_rate: int = 32,
-                          occ_sampling_rate: int = 128) -> "Index":
+                          occ_sampling_rate: int = 128, sa_device: Optional[int] = None) -> "Index":
         """src/index.rs:52-57.  The sampling rates are accepted for signature parity and ignored: the GPU
-        index keeps the full suffix array and has no Occ table."""
+        index keeps the full suffix array and has no Occ table.  `sa_device` = GPU that builds the suffix array
+        (divsufsort64 in the reference, src/index.rs:103-105); None = SA-IS on the host.  Same blob either way."""
         h = C.c_void_p()
-        _check(lib().tg_index_host_create_from_files(ref_path.encode(), annot_path.encode(), C.byref(h)))
+        if sa_device is None:
+            _check(lib().tg_index_host_create_from_files(ref_path.encode(), annot_path.encode(), C.byref(h)))
+        else:
+            _check(lib().tg_index_host_create_from_files_gpu(ref_path.encode(), annot_path.encode(),
+                                                             C.c_int(sa_device), C.byref(h)))
         return cls(h)
 
     @classmethod
-    def create_from_memory(cls, fasta_text: bytes, gtf_text: bytes) -> "Index":
+    def create_from_memory(cls, fasta_text: bytes, gtf_text: bytes, sa_device: Optional[int] = None) -> "Index":
         h = C.c_void_p()
-        _check(lib().tg_index_host_create_from_memory(fasta_text, C.c_size_t(len(fasta_text)), gtf_text,
-                                                      C.c_size_t(len(gtf_text)), C.byref(h)))
+        if sa_device is None:
+            _check(lib().tg_index_host_create_from_memory(fasta_text, C.c_size_t(len(fasta_text)), gtf_text,
+                                                          C.c_size_t(len(gtf_text)), C.byref(h)))
+        else:
+            _check(lib().tg_index_host_create_from_memory_gpu(fasta_text, C.c_size_t(len(fasta_text)), gtf_text,
+                                                              C.c_size_t(len(gtf_text)), C.c_int(sa_device), C.byref(h)))
         return cls(h)
 
     @classmethod
@@ -251,6 +276,12 @@ class Index:
         n = self.text_len()
         p = lib().tg_index_host_sa(self._h)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,))
+
+    def text4(self) -> np.ndarray:
+        """The packed both-strand text: 4-bit codes ($ACGNT = 0..5), 16 per u64, first symbol in the top nibble."""
+        n = self.text_len()
+        p = lib().tg_index_host_text4(self._h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n // 16 + 4,))
 
     # -- device replica -----------------------------------------------------------------------------------------
     def device_index(self, device: int = 0):

@@ -408,7 +408,11 @@ tg_status finish_host_index(tg_index_host* ix) {
   return TG_OK;
 }
 
-tg_status build_index(const char* fasta, size_t fasta_len, const char* gtf, size_t gtf_len, tg_index_host** out) {
+// sa_device < 0: suffix array by SA-IS on the host; >= 0: on that GPU (csrc/tg_sa.cu)
+tg_status build_index(const char* fasta, size_t fasta_len, const char* gtf, size_t gtf_len, int sa_device,
+                      tg_index_host** out) {
+  if (sa_device >= 0 && !g_tg_sa_device)
+    return tg_fail(TG_ERR_CUDA, "this build has no GPU suffix-array builder (host test library)");
   std::vector<Chrom> chroms = read_fasta(fasta, fasta_len);
   if (chroms.empty()) return tg_fail(TG_ERR_IO, "no sequences in FASTA");
   // concatenated text: fwd $ revcomp $ per chromosome (src/index.rs:66-101)
@@ -509,13 +513,18 @@ tg_status build_index(const char* fasta, size_t fasta_len, const char* gtf, size
   for (size_t g = 0; g < genes.size(); g++)  // :208-213
     gene_tree.insert((uint32_t)gene_span[g].first, (uint32_t)gene_span[g].second, (uint32_t)g);
 
-  // suffix array
-  std::vector<uint32_t> sa(T);
-  tg_sais((const uint8_t*)text.data(), T, (int32_t*)sa.data());
-
   // pack
   std::vector<uint64_t> text4(T / 16 + 4, 0), txseq4(tx_seq_off.back() / 16 + 4, 0);
   pack4(text, [](char c) { return base_code(c); }, text4, 0);
+
+  // suffix array (divsufsort64 in the reference, src/index.rs:103-105)
+  std::vector<uint32_t> sa(T);
+  if (sa_device >= 0) {
+    tg_status st = g_tg_sa_device(text4.data(), T, sa_device, sa.data(), nullptr, nullptr);
+    if (st != TG_OK) return st;
+  } else {
+    tg_sais((const uint8_t*)text.data(), T, (int32_t*)sa.data());
+  }
   for (size_t t = 0; t < tx_seqs.size(); t++) pack4(tx_seqs[t], [](char c) { return base_code(c); }, txseq4, tx_seq_off[t]);
 
   BlobWriter w;
@@ -570,6 +579,8 @@ bool slurp(const char* path, std::string& out) {
 
 }  // namespace
 
+tg_sa_device_fn g_tg_sa_device = nullptr;  // set by the static initialiser of tg_sa.cu in libthermite_gpu.so
+
 #define TG_GUARD_BEGIN try {
 #define TG_GUARD_END                                                      \
   }                                                                       \
@@ -582,7 +593,15 @@ tg_status tg_index_host_create_from_memory(const char* fasta_text, size_t fasta_
                                            size_t gtf_len, tg_index_host** out) {
   if (!fasta_text || !out || (!gtf_text && gtf_len)) return tg_fail(TG_ERR_INVALID, "null argument");
   TG_GUARD_BEGIN
-  return build_index(fasta_text, fasta_len, gtf_text ? gtf_text : "", gtf_len, out);
+  return build_index(fasta_text, fasta_len, gtf_text ? gtf_text : "", gtf_len, -1, out);
+  TG_GUARD_END
+}
+
+tg_status tg_index_host_create_from_memory_gpu(const char* fasta_text, size_t fasta_len, const char* gtf_text,
+                                               size_t gtf_len, int device, tg_index_host** out) {
+  if (!fasta_text || !out || device < 0) return tg_fail(TG_ERR_INVALID, "null argument or negative device");
+  TG_GUARD_BEGIN
+  return build_index(fasta_text, fasta_len, gtf_text ? gtf_text : "", gtf_len, device, out);
   TG_GUARD_END
 }
 
@@ -592,7 +611,18 @@ tg_status tg_index_host_create_from_files(const char* fasta_path, const char* gt
   std::string fa, gtf;
   if (!slurp(fasta_path, fa)) return tg_fail(TG_ERR_IO, std::string("cannot read ") + fasta_path);
   if (!slurp(gtf_path, gtf)) return tg_fail(TG_ERR_IO, std::string("cannot read ") + gtf_path);
-  return build_index(fa.data(), fa.size(), gtf.data(), gtf.size(), out);
+  return build_index(fa.data(), fa.size(), gtf.data(), gtf.size(), -1, out);
+  TG_GUARD_END
+}
+
+tg_status tg_index_host_create_from_files_gpu(const char* fasta_path, const char* gtf_path, int device,
+                                              tg_index_host** out) {
+  if (!fasta_path || !gtf_path || !out || device < 0) return tg_fail(TG_ERR_INVALID, "null argument or negative device");
+  TG_GUARD_BEGIN
+  std::string fa, gtf;
+  if (!slurp(fasta_path, fa)) return tg_fail(TG_ERR_IO, std::string("cannot read ") + fasta_path);
+  if (!slurp(gtf_path, gtf)) return tg_fail(TG_ERR_IO, std::string("cannot read ") + gtf_path);
+  return build_index(fa.data(), fa.size(), gtf.data(), gtf.size(), device, out);
   TG_GUARD_END
 }
 
@@ -654,5 +684,6 @@ const char* tg_index_host_tx(const tg_index_host* ix, uint32_t i, uint64_t* out4
 const char* tg_index_host_gene_id(const tg_index_host* ix, uint32_t i) { return ix->gene_ids[i].c_str(); }
 const char* tg_index_host_gene_name(const tg_index_host* ix, uint32_t i) { return ix->gene_names[i].c_str(); }
 const uint32_t* tg_index_host_sa(const tg_index_host* ix) { return (const uint32_t*)(ix->blob.data() + ix->hdr()->off_sa); }
+const uint64_t* tg_index_host_text4(const tg_index_host* ix) { return (const uint64_t*)(ix->blob.data() + ix->hdr()->off_text4); }
 
 }  // extern "C"

@@ -95,4 +95,8 @@ void tg_set_error(const std::string& msg);
 tg_status tg_fail(tg_status code, const std::string& msg);
 
 // host_index.cpp
+// GPU suffix-array builder (csrc/tg_sa.cu), registered when that file is linked in; nullptr in the host test library.
+typedef tg_status (*tg_sa_device_fn)(const uint64_t* text4, uint64_t text_len, int device, uint32_t* sa_out, float* ms,
+                                     uint32_t* steps);
+extern tg_sa_device_fn g_tg_sa_device;
 void tg_sais(const uint8_t* text, size_t n, int32_t* sa);  // plain byte-lexicographic suffix order
