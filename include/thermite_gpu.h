@@ -10,6 +10,7 @@
  *   tg_ctx_create            AlignOpts + per-read SwgExtend scratch  src/aligner.rs:452-464, :140-141
  *   tg_align_batch           align_read, batched                   src/aligner.rs:123-190 (+ :198-449, src/swg.rs, src/txome.rs:82-160,
  *                                                                   Index::all_smems src/index.rs:228-255)
+ *   tg_batcher_*             ThermiteAligner::align_read from many threads  src/wrapper.rs:20-27, :72
  *   tg_seed_batch            Index::all_smems, batched             src/index.rs:228-255
  *   tg_swg_extend_batch      SwgExtend::extend, batched            src/swg.rs:31-207
  *   tg_format_paf / _sam     PafEntry / aln_to_sam_record          src/aln_writer.rs:47-116, 118-253 ; src/aligner.rs:54-115
@@ -206,6 +207,34 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
  * still filled on the host after a stream sync). */
 tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n_reads,
                                 uint64_t total_bases, uint32_t max_read_len, tg_result* out);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Per-read calls from many host threads: ThermiteAligner::align_read (src/wrapper.rs:20-27, :72).
+ * The reference's embedding callers hold one clone per worker thread and align one read per call.  A tg_batcher lets
+ * any number of threads do that against ONE context: reads are queued and a dispatcher thread runs tg_align_batch as
+ * soon as max_batch_reads are waiting or the oldest queued read is max_wait_us old (what arrives while a batch is on
+ * the GPU leaves together afterwards).  All tg_batcher_* calls except create / destroy are thread-safe; while the
+ * batcher lives, `ctx` must not be used for anything else.  Records are identical to tg_align_batch's.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tg_batcher tg_batcher;
+typedef struct tg_read_alns {   /* the Vec<GenomeAlignment> of one align_read call (src/aligner.rs:123) */
+  uint32_t n_alns;              /* 0 = unmapped */
+  uint32_t n_ops;
+  tg_aln* alns;                 /* [n_alns] in output order; ops_off / tx_ops_off index `ops` below */
+  uint32_t* ops;                /* [n_ops] */
+} tg_read_alns;
+tg_status tg_batcher_create(tg_ctx* ctx, uint32_t max_batch_reads, uint32_t max_wait_us, tg_batcher** out);
+/* Queue one read (the bytes are copied) and get a ticket; tg_batcher_wait blocks until that read's batch is done and
+ * hands over its records (free with tg_read_alns_free).  A ticket is waited for exactly once. */
+tg_status tg_batcher_submit(tg_batcher* b, const uint8_t* read, uint32_t len, uint64_t* ticket);
+tg_status tg_batcher_wait(tg_batcher* b, uint64_t ticket, tg_read_alns* out);
+/* submit + wait: the drop-in for a blocking align_read. */
+tg_status tg_batcher_align_read(tg_batcher* b, const uint8_t* read, uint32_t len, tg_read_alns* out);
+void tg_read_alns_free(tg_read_alns* r);
+/* Reads served, batches run and the largest batch so far (any pointer may be NULL). */
+tg_status tg_batcher_stats(tg_batcher* b, uint64_t* n_reads, uint64_t* n_batches, uint32_t* largest_batch);
+/* Serves what is still queued, frees results nobody waited for.  No other call may be in flight on `b`. */
+void tg_batcher_destroy(tg_batcher* b);
 
 /* Seeding only: the SMEMs of every read in the order Index::all_smems returns them, one record per SMEM:
  * occurrences are suffix-array rows [sa_lo, sa_lo+count) visited from the LAST row to the first; when

@@ -24,7 +24,7 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_CSRC, "libtg_hosttest.so")
-        srcs = [os.path.join(_CSRC, f) for f in ("hosttest.cpp", "host_index.cpp", "tg_core.h", "tg_rounds.h", "tg_dpt.h", "tg_internal.h")]
+        srcs = [os.path.join(_CSRC, f) for f in ("hosttest.cpp", "host_index.cpp", "host_batcher.cpp", "tg_core.h", "tg_rounds.h", "tg_dpt.h", "tg_internal.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["make", "-C", _CSRC, "libtg_hosttest.so"], stdout=subprocess.DEVNULL)
         L = C.CDLL(so)
@@ -42,6 +42,14 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def batcher_selftest(n_threads, per_thread, max_batch, max_wait_us, fail_every=0):
+    """csrc/host_batcher.cpp over a stand-in batch aligner: (mismatches, batches, largest batch, reads of failed batches)."""
+    nb, lg, nf = C.c_uint64(), C.c_uint32(), C.c_uint64()
+    bad = lib().ht_batcher_selftest(C.c_int(n_threads), C.c_int(per_thread), C.c_uint32(max_batch), C.c_uint32(max_wait_us),
+                                    C.c_int(fail_every), C.byref(nb), C.byref(lg), C.byref(nf))
+    return bad, nb.value, lg.value, nf.value
 
 
 class HostIndex:

@@ -6,7 +6,7 @@ import pytest
 import ht
 from common import golden, reads_to_batch, small_world, swg_pairs
 from oracle import orc
-from thermite_b200 import AlignOpts, Aligner, Index, parse_fastq, sam_header, suffix_array_gpu, synth
+from thermite_b200 import AlignOpts, Aligner, Index, ThermiteAligner, parse_fastq, sam_header, suffix_array_gpu, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -269,3 +269,52 @@ def test_suffix_array_gpu_adversarial_texts(kind):
     if n <= 1000:
         t = bytes((codes + 1).astype(np.uint8))
         assert list(sa) == sorted(range(n), key=lambda i: t[i:])
+
+
+def test_thermite_aligner_per_read_calls_from_threads():
+    """SURVEY 8f N4: ThermiteAligner::align_read (src/wrapper.rs:72) -- one read per call, from several host threads, and
+    pipelined submit / wait -- returns for every read exactly the records the batch call gives (and the oracle)."""
+    import threading
+    contigs, gtf2, txs, fa2 = small_world(4)
+    n = 600
+    b2, o2 = synth.make_reads(11, contigs, txs, n, L=91, sub=0.02, ins=0.003, dele=0.003)
+    ix = Index.create_from_memory(fa2, gtf2)
+    opts = AlignOpts(20, 0.0, 30, 1, True)
+    ores = orc.Index.create(fa2, gtf2).align_batch(b2, o2, k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True)
+    reads = [bytes(b2[int(o2[r]):int(o2[r + 1])]) for r in range(n)]
+    ta = ThermiteAligner(ix, opts, max_batch_reads=128, max_wait_us=300)
+    got = [None] * n
+
+    def worker(t, nt):
+        if t % 2 == 0:
+            for r in range(t, n, nt):
+                got[r] = ta.align_read_raw(reads[r])
+        else:
+            mine = list(range(t, n, nt))
+            tickets = [ta.submit(reads[r]) for r in mine]
+            for r, tk in zip(mine, tickets):
+                got[r] = ta.wait_raw(tk)
+
+    th = [threading.Thread(target=worker, args=(t, 6)) for t in range(6)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    st = ta.stats()
+    assert st["reads"] == n and st["batches"] < n and 1 < st["largest_batch"] <= 128
+    # stitch the per-read blocks back into one flat result and compare with the oracle
+    first, count, alns, ops, na, no = [], [], [], [], 0, 0
+    for r in range(n):
+        g = got[r]
+        a = g.alns.copy()
+        a["ops_off"] += no
+        a["tx_ops_off"] += no
+        first.append(na); count.append(len(a)); alns.append(a); ops.append(g.ops)
+        na += len(a); no += len(g.ops)
+    flat = dict(first=np.array(first, np.uint64), count=np.array(count, np.uint32), alns=np.concatenate(alns),
+                ops=np.concatenate(ops))
+    d = ht.compare_alignments(flat, ores, n)
+    assert not d, d[:5]
+    assert ta.align_read(reads[0]) == Aligner(ix, opts).align_read(reads[0])
+    assert ta.align_read(b"") == [] and ta.align_read(b"ACGT") == []
+    with pytest.raises(Exception):
+        ta.wait(10 ** 9)
+    ta.close()

@@ -146,3 +146,18 @@ def test_round_pipeline_repeat_rich_reads(seed):
         assert res["flags"] == 0 and res["cells"] == oc["swg_cells"] and res["hits"] == oc["hits"]
         # speculation really happened: several rounds, and some evaluated hits were discarded and redone
         assert res["rounds"] >= 3 and res["items"] > res["hits"], (res["rounds"], res["items"], res["hits"])
+
+
+def test_micro_batcher_hands_every_caller_its_own_records():
+    """SURVEY 8f N4 (ThermiteAligner::align_read from many threads, src/wrapper.rs:20-27): tg_batcher's queueing,
+    batch cutting, per-read result blocks (operations rebased, transcript and genome words in either order), ticket
+    life cycle and error propagation, driven by 1-16 threads over a stand-in batch aligner whose records are a
+    function of the read bytes."""
+    bad, batches, largest, failed = ht.batcher_selftest(1, 200, 64, 0)
+    assert (bad, batches, largest, failed) == (0, 200, 1, 0)      # one blocking caller: every read is its own batch
+    bad, batches, largest, failed = ht.batcher_selftest(16, 1500, 256, 200)
+    assert bad == 0 and failed == 0 and 1 < largest <= 256 and batches < 16 * 1500
+    bad, batches, largest, failed = ht.batcher_selftest(8, 1000, 7, 50)
+    assert bad == 0 and failed == 0 and largest == 7              # the batch limit cuts the queue
+    bad, batches, largest, failed = ht.batcher_selftest(8, 600, 64, 100, fail_every=5)
+    assert bad == 0 and failed > 0                                # a failed batch fails exactly its reads, nothing leaks through

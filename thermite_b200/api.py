@@ -69,6 +69,8 @@ ABI_SYMBOLS = [
     "tg_index_host_from_blob", "tg_index_host_save", "tg_index_host_load", "tg_index_host_destroy",
     "tg_index_host_text_len", "tg_index_host_n_refs", "tg_index_host_n_txs", "tg_index_host_n_genes",
     "tg_index_host_ref", "tg_index_host_tx", "tg_index_host_gene_id", "tg_index_host_gene_name", "tg_index_host_sa",
+    "tg_batcher_create", "tg_batcher_submit", "tg_batcher_wait", "tg_batcher_align_read", "tg_read_alns_free",
+    "tg_batcher_stats", "tg_batcher_destroy",
     "tg_index_host_text4", "tg_index_host_create_from_files_gpu", "tg_index_host_create_from_memory_gpu", "tg_suffix_array_gpu",
     "tg_index_create", "tg_index_create_from_device_blob", "tg_index_destroy",
     "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_set_chunk_reads", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_bench_random_gather", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
@@ -92,6 +94,8 @@ def lib():
             getattr(L, f).restype = C.c_char_p
         L.tg_index_host_sa.restype = C.c_void_p
         L.tg_index_host_text4.restype = C.c_void_p
+        L.tg_batcher_destroy.restype = None
+        L.tg_read_alns_free.restype = None
         L.tg_ctx_stream.restype = C.c_void_p
         L.tg_ctx_kmer_table_bytes.restype = C.c_uint64
         L.tg_ctx_last_kernel_launches.restype = C.c_uint64
@@ -547,6 +551,75 @@ def sam_header(index: Index) -> bytes:
     s = C.string_at(out, n.value)
     lib().tg_free(out)
     return s
+
+
+class _ReadAlns(C.Structure):
+    _fields_ = [("n_alns", C.c_uint32), ("n_ops", C.c_uint32), ("alns", C.c_void_p), ("ops", C.c_void_p)]
+
+
+class ThermiteAligner:
+    """The reference's embedding wrapper (src/wrapper.rs:20-27): `align_read` for ONE read, callable from any number of
+    host threads at once (the reference hands each worker thread its own clone).  All callers share one GPU context:
+    reads are micro-batched by the library (`tg_batcher_*`, csrc/host_batcher.cpp).  `submit` / `wait` let one thread keep
+    many reads in flight.  Records are those of `Aligner.align_reads`.  Defaults are the wrapper's (src/wrapper.rs:40-46)."""
+
+    def __init__(self, index: Index, opts: "AlignOpts" = None, device: int = 0, max_batch_reads: int = 1 << 16,
+                 max_wait_us: int = 200):
+        self._aligner = Aligner(index, opts, device)
+        h = C.c_void_p()
+        _check(lib().tg_batcher_create(self._aligner._h, C.c_uint32(max_batch_reads), C.c_uint32(max_wait_us), C.byref(h)))
+        self._h = h
+
+    def opts(self) -> "AlignOpts":
+        return self._aligner.opts
+
+    def _take(self, ra: _ReadAlns) -> AlignResult:
+        alns = np.zeros(ra.n_alns, ALN_DTYPE)
+        ops = np.zeros(ra.n_ops, np.uint32)
+        if ra.n_alns:
+            C.memmove(alns.ctypes.data, ra.alns, ra.n_alns * ALN_DTYPE.itemsize)
+        if ra.n_ops:
+            C.memmove(ops.ctypes.data, ra.ops, ra.n_ops * 4)
+        lib().tg_read_alns_free(C.byref(ra))
+        return AlignResult(np.zeros(1, np.uint64), np.array([len(alns)], np.uint32), alns, ops, {}, self._aligner._ref_names)
+
+    def align_read_raw(self, read: bytes) -> AlignResult:
+        ra = _ReadAlns()
+        _check(lib().tg_batcher_align_read(self._h, read, C.c_uint32(len(read)), C.byref(ra)))
+        return self._take(ra)
+
+    def align_read(self, read: bytes) -> List[GenomeAlignment]:
+        """src/wrapper.rs:72 / src/aligner.rs:123 (blocking; thread-safe; ctypes releases the GIL while it waits)."""
+        return self.align_read_raw(read).read_alignments(0)
+
+    def submit(self, read: bytes) -> int:
+        t = C.c_uint64()
+        _check(lib().tg_batcher_submit(self._h, read, C.c_uint32(len(read)), C.byref(t)))
+        return t.value
+
+    def wait_raw(self, ticket: int) -> AlignResult:
+        ra = _ReadAlns()
+        _check(lib().tg_batcher_wait(self._h, C.c_uint64(ticket), C.byref(ra)))
+        return self._take(ra)
+
+    def wait(self, ticket: int) -> List[GenomeAlignment]:
+        return self.wait_raw(ticket).read_alignments(0)
+
+    def stats(self):
+        r, b, l = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        _check(lib().tg_batcher_stats(self._h, C.byref(r), C.byref(b), C.byref(l)))
+        return dict(reads=r.value, batches=b.value, largest_batch=l.value)
+
+    def close(self):
+        if self._h:
+            lib().tg_batcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def align_reads_from_file(index: Index, query_paths, output_path: str, output_fmt: str, align_opts: AlignOpts,

@@ -11,6 +11,7 @@
 #include <memory>
 #include <thread>
 #include <vector>
+#include <random>
 
 #include "tg_rounds.h"
 #include "tg_dpt.h"
@@ -564,3 +565,143 @@ long long ht_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uin
 }
 
 }  // extern "C"
+
+// ---- micro-batcher (host_batcher.cpp) over a stand-in batch aligner -----------------------------------------------------
+// The stand-in derives a read's records from its bytes alone (count = len % 4, scores / coordinates / operation words
+// from a hash), scatters them through the result pools in a scrambled order and serves `n_threads` callers that each
+// submit `per_thread` reads -- half of them blocking, half in windows of tickets -- and check what comes back.
+// Returns 0 when every read got exactly its own records; batches / largest batch are reported through the pointers.
+namespace {
+struct FakeBackend {
+  std::vector<uint64_t> first;
+  std::vector<uint32_t> count, ops;
+  std::vector<tg_aln> alns;
+  int fail_every = 0, calls = 0;
+};
+uint32_t fb_hash(const uint8_t* p, uint32_t n, uint32_t salt) {
+  uint32_t h = 2166136261u ^ salt;
+  for (uint32_t i = 0; i < n; i++) h = (h ^ p[i]) * 16777619u;
+  return h;
+}
+void fb_expect(const uint8_t* r, uint32_t len, uint32_t a, tg_aln& rec, std::vector<uint32_t>& gx, std::vector<uint32_t>& tx) {
+  memset(&rec, 0, sizeof(rec));
+  rec.score = (int32_t)(fb_hash(r, len, a) & 0xFFFF);
+  rec.ref_id = fb_hash(r, len, 100 + a) & 7;
+  rec.xlen = len;
+  rec.aln_type = (uint8_t)(fb_hash(r, len, 200 + a) % 3);
+  rec.primary = a == 0;
+  gx.resize(1 + fb_hash(r, len, 300 + a) % 5);
+  for (size_t i = 0; i < gx.size(); i++) gx[i] = fb_hash(r, len, 400 + 16 * a + (uint32_t)i);
+  tx.resize(rec.aln_type == 0 ? 1 + fb_hash(r, len, 500 + a) % 3 : 0);
+  for (size_t i = 0; i < tx.size(); i++) tx[i] = fb_hash(r, len, 600 + 16 * a + (uint32_t)i);
+  rec.ops_len = (uint32_t)gx.size();
+  rec.tx_ops_len = (uint32_t)tx.size();
+}
+tg_status fb_align(void* user, const uint8_t* bases, const uint64_t* offs, uint32_t n, tg_result* out) {
+  FakeBackend* fb = (FakeBackend*)user;
+  if (fb->fail_every && ++fb->calls % fb->fail_every == 0) return tg_fail(TG_ERR_CAPACITY, "stand-in backend failure");
+  fb->first.assign(n, 0); fb->count.assign(n, 0); fb->alns.clear(); fb->ops.assign(7, 0xDEADu);
+  std::vector<uint32_t> gx, tx;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint8_t* r = bases + offs[i];
+    const uint32_t len = (uint32_t)(offs[i + 1] - offs[i]);
+    fb->first[i] = fb->alns.size();
+    fb->count[i] = len % 4;
+    for (uint32_t a = 0; a < fb->count[i]; a++) {
+      tg_aln rec;
+      fb_expect(r, len, a, rec, gx, tx);
+      // transcript operations first, a gap, then the genome operations: offsets are not monotonic
+      rec.tx_ops_off = (uint32_t)fb->ops.size();
+      fb->ops.insert(fb->ops.end(), tx.begin(), tx.end());
+      fb->ops.push_back(0xBEEFu);
+      rec.ops_off = (uint32_t)fb->ops.size();
+      fb->ops.insert(fb->ops.end(), gx.begin(), gx.end());
+      fb->alns.push_back(rec);
+    }
+  }
+  memset(out, 0, sizeof(*out));
+  out->n_reads = n; out->n_alns = fb->alns.size(); out->n_ops = fb->ops.size();
+  out->read_aln_first = fb->first.data(); out->read_aln_count = fb->count.data();
+  out->alns = fb->alns.data(); out->ops = fb->ops.data();
+  return TG_OK;
+}
+bool fb_check(const std::vector<uint8_t>& read, const tg_read_alns& got) {
+  const uint32_t len = (uint32_t)read.size();
+  if (got.n_alns != len % 4) return false;
+  std::vector<uint32_t> gx, tx;
+  uint32_t total = 0;
+  for (uint32_t a = 0; a < got.n_alns; a++) {
+    tg_aln want;
+    fb_expect(read.data(), len, a, want, gx, tx);
+    const tg_aln& g = got.alns[a];
+    if (g.score != want.score || g.ref_id != want.ref_id || g.xlen != len || g.aln_type != want.aln_type ||
+        g.primary != want.primary || g.ops_len != gx.size() || g.tx_ops_len != tx.size())
+      return false;
+    if ((uint64_t)g.ops_off + g.ops_len > got.n_ops || (uint64_t)g.tx_ops_off + g.tx_ops_len > got.n_ops) return false;
+    if (memcmp(got.ops + g.ops_off, gx.data(), gx.size() * 4) != 0) return false;
+    if (!tx.empty() && memcmp(got.ops + g.tx_ops_off, tx.data(), tx.size() * 4) != 0) return false;
+    total += g.ops_len + g.tx_ops_len;
+  }
+  return total == got.n_ops;
+}
+}  // namespace
+
+extern "C" int ht_batcher_selftest(int n_threads, int per_thread, uint32_t max_batch, uint32_t max_wait_us, int fail_every,
+                                   uint64_t* n_batches, uint32_t* largest, uint64_t* n_failed_reads) {
+  FakeBackend fb;
+  fb.fail_every = fail_every;
+  tg_batcher* b = nullptr;
+  if (tg_batcher_create_backend(fb_align, &fb, max_batch, max_wait_us, &b) != TG_OK) return -1;
+  std::atomic<int> bad{0};
+  std::atomic<uint64_t> failed{0};
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; t++)
+    th.emplace_back([&, t] {
+      std::mt19937 rng(1234 + t);
+      auto make = [&] {
+        std::vector<uint8_t> r(rng() % 120);
+        for (auto& c : r) c = "ACGTN"[rng() % 5];
+        return r;
+      };
+      for (int i = 0; i < per_thread;) {
+        if (t % 2 == 0) {  // blocking calls
+          std::vector<uint8_t> r = make();
+          tg_read_alns got;
+          tg_status st = tg_batcher_align_read(b, r.data(), (uint32_t)r.size(), &got);
+          if (st != TG_OK) { failed++; if (!fail_every || got.alns) bad++; }
+          else { if (!fb_check(r, got)) bad++; tg_read_alns_free(&got); }
+          i++;
+        } else {  // a window of tickets, waited for in reverse order
+          const int win = std::min(per_thread - i, 1 + (int)(rng() % 40));
+          std::vector<std::vector<uint8_t>> rs(win);
+          std::vector<uint64_t> tk(win);
+          for (int k = 0; k < win; k++) {
+            rs[k] = make();
+            std::vector<uint8_t> copy = rs[k];
+            if (tg_batcher_submit(b, copy.data(), (uint32_t)copy.size(), &tk[k]) != TG_OK) bad++;
+            std::fill(copy.begin(), copy.end(), 0);  // the batcher must have taken its own copy
+          }
+          for (int k = win - 1; k >= 0; k--) {
+            tg_read_alns got;
+            tg_status st = tg_batcher_wait(b, tk[k], &got);
+            if (st != TG_OK) { failed++; if (!fail_every) bad++; }
+            else { if (!fb_check(rs[k], got)) bad++; tg_read_alns_free(&got); }
+          }
+          tg_read_alns dummy;
+          if (tg_batcher_wait(b, tk[0], &dummy) != TG_ERR_INVALID) bad++;  // a ticket is good for one wait
+          i += win;
+        }
+      }
+    });
+  for (auto& x : th) x.join();
+  uint64_t reads = 0;
+  tg_batcher_stats(b, &reads, n_batches, largest);
+  if (reads != (uint64_t)n_threads * per_thread) bad++;
+  // results nobody waits for are freed by destroy (checked under valgrind/ASan runs; here: must not crash)
+  uint64_t orphan = 0;
+  const uint8_t r3[3] = {'A', 'C', 'G'};
+  tg_batcher_submit(b, r3, 3, &orphan);
+  tg_batcher_destroy(b);
+  if (n_failed_reads) *n_failed_reads = failed.load();
+  return bad.load();
+}

@@ -94,6 +94,12 @@ struct tg_index_host {
 void tg_set_error(const std::string& msg);
 tg_status tg_fail(tg_status code, const std::string& msg);
 
+// host_batcher.cpp: the micro-batcher over any batch aligner (tg_align_batch in the product; a stand-in in the host test)
+typedef tg_status (*tg_batch_backend_fn)(void* user, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads,
+                                         tg_result* out);
+tg_status tg_batcher_create_backend(tg_batch_backend_fn fn, void* user, uint32_t max_batch_reads, uint32_t max_wait_us,
+                                    tg_batcher** out);
+
 // host_index.cpp
 // GPU suffix-array builder (csrc/tg_sa.cu), registered when that file is linked in; nullptr in the host test library.
 typedef tg_status (*tg_sa_device_fn)(const uint64_t* text4, uint64_t text_len, int device, uint32_t* sa_out, float* ms,

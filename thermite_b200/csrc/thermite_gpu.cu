@@ -1191,6 +1191,17 @@ void tg_ctx_destroy(tg_ctx* c) {
   delete c;
 }
 
+// ThermiteAligner::align_read from many threads (src/wrapper.rs:20-27, :72): the micro-batcher of host_batcher.cpp over
+// tg_align_batch of this context
+tg_status tg_batcher_create(tg_ctx* ctx, uint32_t max_batch_reads, uint32_t max_wait_us, tg_batcher** out) {
+  if (!ctx || !out) return tg_fail(TG_ERR_INVALID, "null argument");
+  return tg_batcher_create_backend(
+      [](void* user, const uint8_t* bases, const uint64_t* offs, uint32_t n, tg_result* res) {
+        return tg_align_batch((tg_ctx*)user, bases, offs, n, res);
+      },
+      ctx, max_batch_reads, max_wait_us, out);
+}
+
 tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
   if (!ix || !opts || !out) return tg_fail(TG_ERR_INVALID, "null argument");
   if (opts->min_seed_len < 1 || opts->min_seed_len > TG_MAX_SEED_LEN)
