@@ -70,4 +70,26 @@ extern "C" {
     pub fn tg_ctx_set_exact_cell_count(ctx: *mut tg_ctx, on: c_int);
     pub fn tg_ctx_last_kernel_ms(ctx: *const tg_ctx, seed_ms: *mut f32, extend_ms: *mut f32);
     pub fn tg_ctx_last_dp_ms(ctx: *const tg_ctx) -> f32;
+    /// Index::create_from_files with divsufsort64 (src/index.rs:103-105) replaced by the GPU suffix-array builder
+    pub fn tg_index_host_create_from_files_gpu(fasta: *const c_char, gtf: *const c_char, device: c_int, out: *mut *mut tg_index_host) -> tg_status;
+    /// ThermiteAligner::align_read from many threads (src/wrapper.rs:20-27, :72): micro-batcher over one context
+    pub fn tg_batcher_create(ctx: *mut tg_ctx, max_batch_reads: u32, max_wait_us: u32, out: *mut *mut tg_batcher) -> tg_status;
+    pub fn tg_batcher_submit(b: *mut tg_batcher, read: *const u8, len: u32, ticket: *mut u64) -> tg_status;
+    pub fn tg_batcher_wait(b: *mut tg_batcher, ticket: u64, out: *mut tg_read_alns) -> tg_status;
+    pub fn tg_batcher_align_read(b: *mut tg_batcher, read: *const u8, len: u32, out: *mut tg_read_alns) -> tg_status;
+    pub fn tg_read_alns_free(r: *mut tg_read_alns);
+    pub fn tg_batcher_stats(b: *mut tg_batcher, n_reads: *mut u64, n_batches: *mut u64, largest_batch: *mut u32) -> tg_status;
+    pub fn tg_batcher_destroy(b: *mut tg_batcher);
+}
+
+#[repr(C)]
+pub struct tg_batcher { _private: [u8; 0] }
+
+/// the Vec<GenomeAlignment> of one align_read call; `alns` and `ops` are one block owned by the caller until tg_read_alns_free
+#[repr(C)]
+pub struct tg_read_alns {
+    pub n_alns: u32,
+    pub n_ops: u32,
+    pub alns: *mut tg_aln,
+    pub ops: *mut u32,
 }

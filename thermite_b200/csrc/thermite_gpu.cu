@@ -505,10 +505,12 @@ __global__ void __launch_bounds__(128) k_round_plan(RoundParams p) {
 // ---- item order: the thread-per-hit kernels (prep, post) walk data-dependent loops over the transcripts and exons at the
 // hit's locus, so a warp whose 32 hits sit at 32 unrelated loci runs 32 different control flows (3.8 active lanes per
 // instruction, profiles/r1_ncu_prep.csv).  Hits are therefore handed to threads in the order of their text position
-// (buckets of 2^ib_shift symbols, counting sort: count -> scan -> scatter): neighbours in a warp then see the same gene,
+// (2^TG_IB_BITS buckets of 2^ib_shift symbols, counting sort: count -> scan -> scatter): neighbours in a warp then see the same gene,
 // the same transcripts and the same cache lines (prep, round 0, 1 M hits: 436 M -> 190 M warp instructions, 4.7 -> 10.7
 // active lanes, 1.05 -> 0.63 ms).  Only prep's thread -> item mapping changes; items stay where they are.
+#ifndef TG_IB_BITS
 #define TG_IB_BITS 14
+#endif
 #define TG_IB_N (1 << TG_IB_BITS)
 __global__ void __launch_bounds__(256) k_round_ikey(RoundParams p) {
   unsigned long long lo, hi;
@@ -530,10 +532,9 @@ __global__ void __launch_bounds__(256) k_round_ikey(RoundParams p) {
 __global__ void __launch_bounds__(1024) k_round_iscan(RoundParams p) {
   constexpr int PER = TG_IB_N / 1024;
   __shared__ uint32_t wsum[32];
-  uint32_t v[PER], sum = 0;
+  uint32_t sum = 0;
   const int b0 = threadIdx.x * PER;
-#pragma unroll
-  for (int k = 0; k < PER; k++) { v[k] = p.ibins[b0 + k]; p.ibins[b0 + k] = 0; sum += v[k]; }
+  for (int k = 0; k < PER; k++) sum += p.ibins[b0 + k];
   uint32_t inc = sum;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -554,8 +555,12 @@ __global__ void __launch_bounds__(1024) k_round_iscan(RoundParams p) {
   }
   __syncthreads();
   uint32_t acc = wsum[wid] + inc - sum;
-#pragma unroll
-  for (int k = 0; k < PER; k++) { p.ibins[TG_IB_N + b0 + k] = acc; acc += v[k]; }
+  for (int k = 0; k < PER; k++) {
+    const uint32_t v = p.ibins[b0 + k];
+    p.ibins[b0 + k] = 0;
+    p.ibins[TG_IB_N + b0 + k] = acc;
+    acc += v;
+  }
 }
 __global__ void __launch_bounds__(256) k_round_iscatter(RoundParams p) {
   unsigned long long lo, hi;
