@@ -318,3 +318,19 @@ def test_thermite_aligner_per_read_calls_from_threads():
     with pytest.raises(Exception):
         ta.wait(10 ** 9)
     ta.close()
+
+
+@pytest.mark.parametrize("small_batch", ["0", "1000000000"])
+def test_large_and_small_batch_paths_give_the_same_records(small_batch, monkeypatch):
+    """tg_align_batch treats batches below TG_SMALL_BATCH reads (default 32,768) as latency-bound: no early output of
+    finished reads, no locus-ordered prep, an earlier "nothing left" check.  Both paths against the oracle on the same
+    reads (the environment variable is read when the context is created)."""
+    monkeypatch.setenv("TG_SMALL_BATCH", small_batch)
+    contigs, gtf2, txs, fa2 = small_world(5)
+    n = 3000
+    b2, o2 = synth.make_reads(12, contigs, txs, n, L=91, sub=0.02, ins=0.003, dele=0.003)
+    al = Aligner(Index.create_from_memory(fa2, gtf2), AlignOpts(20, 0.0, 30, 1, True))
+    ores = orc.Index.create(fa2, gtf2).align_batch(b2, o2, k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True)
+    _cmp(al.align_reads(b2, o2), ores, n)
+    for m in (1, 2, 7):   # tiny batches: the host check after round 0 / 1
+        _cmp(al.align_reads(b2[: int(o2[m])], o2[: m + 1]), ores, m)

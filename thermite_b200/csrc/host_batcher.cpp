@@ -8,14 +8,18 @@
 // old (so everything that arrived while the previous batch was on the GPU leaves at once).  Every caller gets its own
 // records (the Vec<GenomeAlignment> of its read, operations rebased to a private block).  Results are those of
 // tg_align_batch, which does not depend on how reads are batched.
+//
+// Host cost per read is what limits this path, so: requests live in a slab of reusable slots (no allocation per submit,
+// ticket = slot | generation << 32), the dispatcher only snapshots a finished batch (four bulk copies) and marks its
+// slots done, and every waiter cuts its own records out of the snapshot on its own thread.
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 
 #include "tg_internal.h"
@@ -24,17 +28,50 @@ namespace {
 
 using Clock = std::chrono::steady_clock;
 
-struct Request {
-  std::vector<uint8_t> read;  // copied at submit: the caller's buffer is free again when submit returns
-  Clock::time_point arrival;
-  tg_read_alns res{0, 0, nullptr, nullptr};
-  tg_status status = TG_OK;
-  bool done = false;
+struct BatchSnapshot {  // host copy of one tg_result (the context's own buffers are reused by the next batch)
+  std::vector<uint64_t> first;
+  std::vector<uint32_t> count, ops;
+  std::vector<tg_aln> alns;
 };
 
-void free_alns(tg_read_alns* r) {
-  free(r->alns);  // records and operations are one block
-  memset(r, 0, sizeof(*r));
+struct Slot {
+  uint32_t gen = 1;  // bumped when the slot is freed: a stale ticket no longer matches
+  uint32_t len = 0;
+  bool in_use = false, waited = false, done = false;
+  tg_status status = TG_OK;
+  Clock::time_point arrival;
+  std::shared_ptr<BatchSnapshot> batch;
+  uint32_t index = 0;  // the read's row in `batch`
+  uint8_t read[TG_MAX_READ_LEN];  // copied at submit: the caller's buffer is free again when submit returns
+};
+
+// the records of row i of a snapshot as one malloc'ed block: records, then their operation words (rebased)
+tg_status cut_read(const BatchSnapshot& b, uint32_t i, tg_read_alns* o) {
+  const uint64_t first = b.first[i];
+  const uint32_t cnt = b.count[i];
+  uint64_t n_ops = 0;
+  for (uint32_t a = 0; a < cnt; a++) n_ops += (uint64_t)b.alns[first + a].ops_len + b.alns[first + a].tx_ops_len;
+  o->n_alns = cnt;
+  o->n_ops = (uint32_t)n_ops;
+  o->alns = nullptr;
+  o->ops = nullptr;
+  if (!cnt) return TG_OK;
+  char* blk = (char*)malloc(cnt * sizeof(tg_aln) + n_ops * sizeof(uint32_t));
+  if (!blk) return tg_fail(TG_ERR_INTERNAL, "out of memory");
+  o->alns = (tg_aln*)blk;
+  o->ops = (uint32_t*)(blk + cnt * sizeof(tg_aln));
+  uint32_t w = 0;
+  for (uint32_t a = 0; a < cnt; a++) {
+    tg_aln rec = b.alns[first + a];
+    if (rec.ops_len) memcpy(o->ops + w, b.ops.data() + rec.ops_off, (size_t)rec.ops_len * 4);
+    rec.ops_off = w;
+    w += rec.ops_len;
+    if (rec.tx_ops_len) memcpy(o->ops + w, b.ops.data() + rec.tx_ops_off, (size_t)rec.tx_ops_len * 4);
+    rec.tx_ops_off = rec.tx_ops_len ? w : 0;
+    w += rec.tx_ops_len;
+    o->alns[a] = rec;
+  }
+  return TG_OK;
 }
 
 }  // namespace
@@ -47,9 +84,9 @@ struct tg_batcher {
 
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
-  std::deque<Request*> queue;                        // submitted, not yet on the GPU
-  std::unordered_map<uint64_t, Request*> tickets;    // submitted, not yet waited for
-  uint64_t next_ticket = 1;
+  std::deque<Slot> slots;          // stable addresses; indexed only under `mu`
+  std::vector<uint32_t> free_slots;
+  std::deque<Slot*> queue;         // submitted, not yet on the GPU
   bool stop = false;
   std::string error;  // message of the last failed batch (copied into the waiters' thread-local error)
   uint64_t n_reads = 0, n_batches = 0;
@@ -57,11 +94,11 @@ struct tg_batcher {
   std::thread worker;
 
   void run();
-  void serve(std::vector<Request*>& batch, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs);
+  void serve(std::vector<Slot*>& batch, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs);
 };
 
 void tg_batcher::run() {
-  std::vector<Request*> batch;
+  std::vector<Slot*> batch;
   std::vector<uint8_t> bases;
   std::vector<uint64_t> offs;
   for (;;) {
@@ -80,12 +117,12 @@ void tg_batcher::run() {
   }
 }
 
-void tg_batcher::serve(std::vector<Request*>& batch, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs) {
+void tg_batcher::serve(std::vector<Slot*>& batch, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs) {
   const uint32_t n = (uint32_t)batch.size();
   offs.assign(1, 0);
   bases.clear();
-  for (Request* r : batch) {
-    bases.insert(bases.end(), r->read.begin(), r->read.end());
+  for (Slot* s : batch) {  // (a queued slot is not touched by anyone else until it is marked done)
+    bases.insert(bases.end(), s->read, s->read + s->len);
     offs.push_back(bases.size());
   }
   if (bases.empty()) bases.push_back('N');  // keep data() non-null for a batch of empty reads
@@ -93,41 +130,23 @@ void tg_batcher::serve(std::vector<Request*>& batch, std::vector<uint8_t>& bases
   memset(&res, 0, sizeof(res));
   tg_status st = TG_ERR_INTERNAL;
   std::string msg;
+  std::shared_ptr<BatchSnapshot> snap;
   try {
     st = fn(user, bases.data(), offs.data(), n, &res);
     if (st != TG_OK) msg = tg_last_error();
+    else {
+      snap = std::make_shared<BatchSnapshot>();
+      snap->first.assign(res.read_aln_first, res.read_aln_first + n);
+      snap->count.assign(res.read_aln_count, res.read_aln_count + n);
+      snap->alns.assign(res.alns, res.alns + res.n_alns);
+      snap->ops.assign(res.ops, res.ops + res.n_ops);
+    }
   } catch (const std::exception& e) {
+    st = TG_ERR_INTERNAL;
     msg = e.what();
   } catch (...) {
+    st = TG_ERR_INTERNAL;
     msg = "unknown exception in the batch backend";
-  }
-  if (st == TG_OK) {
-    for (uint32_t i = 0; i < n && st == TG_OK; i++) {
-      tg_read_alns* o = &batch[i]->res;
-      const uint64_t first = res.read_aln_first[i];
-      const uint32_t cnt = res.read_aln_count[i];
-      uint64_t n_ops = 0;
-      for (uint32_t a = 0; a < cnt; a++) n_ops += (uint64_t)res.alns[first + a].ops_len + res.alns[first + a].tx_ops_len;
-      o->n_alns = cnt;
-      o->n_ops = (uint32_t)n_ops;
-      if (!cnt) continue;
-      // one block: records, then their operation words
-      char* blk = (char*)malloc(cnt * sizeof(tg_aln) + n_ops * sizeof(uint32_t));
-      if (!blk) { st = TG_ERR_INTERNAL; msg = "out of memory"; break; }
-      o->alns = (tg_aln*)blk;
-      o->ops = (uint32_t*)(blk + cnt * sizeof(tg_aln));
-      uint32_t w = 0;
-      for (uint32_t a = 0; a < cnt; a++) {
-        tg_aln rec = res.alns[first + a];
-        if (rec.ops_len) memcpy(o->ops + w, res.ops + rec.ops_off, (size_t)rec.ops_len * 4);
-        rec.ops_off = w;
-        w += rec.ops_len;
-        if (rec.tx_ops_len) memcpy(o->ops + w, res.ops + rec.tx_ops_off, (size_t)rec.tx_ops_len * 4);
-        rec.tx_ops_off = rec.tx_ops_len ? w : 0;
-        w += rec.tx_ops_len;
-        o->alns[a] = rec;
-      }
-    }
   }
   {
     std::lock_guard<std::mutex> lk(mu);
@@ -135,9 +154,12 @@ void tg_batcher::serve(std::vector<Request*>& batch, std::vector<uint8_t>& bases
     n_reads += n;
     n_batches++;
     largest = std::max(largest, n);
-    for (Request* r : batch) {
-      r->status = st;
-      r->done = true;
+    for (uint32_t i = 0; i < n; i++) {
+      Slot* s = batch[i];
+      s->status = st;
+      s->batch = snap;
+      s->index = i;
+      s->done = true;
     }
   }
   cv_done.notify_all();
@@ -166,20 +188,26 @@ extern "C" {
 tg_status tg_batcher_submit(tg_batcher* b, const uint8_t* read, uint32_t len, uint64_t* ticket) {
   if (!b || !ticket || (!read && len)) return tg_fail(TG_ERR_INVALID, "null argument");
   if (len > TG_MAX_READ_LEN) return tg_fail(TG_ERR_CAPACITY, "read longer than TG_MAX_READ_LEN");
-  Request* rq = nullptr;
   try {
-    rq = new Request();
-    rq->read.assign(read, read + len);
     std::lock_guard<std::mutex> lk(b->mu);
-    if (b->stop) { delete rq; return tg_fail(TG_ERR_INVALID, "the batcher is being destroyed"); }
-    rq->arrival = Clock::now();
-    *ticket = b->next_ticket++;
-    b->tickets.emplace(*ticket, rq);
-    b->queue.push_back(rq);
-    if (b->queue.size() == 1 || b->queue.size() >= b->max_batch) b->cv_work.notify_one();
+    if (b->stop) return tg_fail(TG_ERR_INVALID, "the batcher is being destroyed");
+    uint32_t idx;
+    if (!b->free_slots.empty()) {
+      idx = b->free_slots.back();
+      b->free_slots.pop_back();
+    } else {
+      idx = (uint32_t)b->slots.size();
+      b->slots.emplace_back();
+    }
+    Slot& s = b->slots[idx];
+    s.in_use = true; s.waited = false; s.done = false; s.status = TG_OK; s.len = len;
+    if (len) memcpy(s.read, read, len);
+    s.arrival = Clock::now();
+    *ticket = (uint64_t)idx | ((uint64_t)s.gen << 32);
+    b->queue.push_back(&s);
+    if (b->queue.size() == 1 || b->queue.size() == b->max_batch) b->cv_work.notify_one();
     return TG_OK;
   } catch (const std::exception& e) {
-    delete rq;
     return tg_fail(TG_ERR_INTERNAL, e.what());
   }
 }
@@ -187,19 +215,30 @@ tg_status tg_batcher_submit(tg_batcher* b, const uint8_t* read, uint32_t len, ui
 tg_status tg_batcher_wait(tg_batcher* b, uint64_t ticket, tg_read_alns* out) {
   if (!b || !out) return tg_fail(TG_ERR_INVALID, "null argument");
   memset(out, 0, sizeof(*out));
-  std::unique_lock<std::mutex> lk(b->mu);
-  auto it = b->tickets.find(ticket);
-  if (it == b->tickets.end()) return tg_fail(TG_ERR_INVALID, "unknown ticket (never issued or already waited for)");
-  Request* rq = it->second;
-  b->tickets.erase(it);  // a ticket is waited for once
-  b->cv_done.wait(lk, [&] { return rq->done; });
-  const tg_status st = rq->status;
-  const std::string msg = st != TG_OK ? b->error : std::string();
-  lk.unlock();
-  if (st == TG_OK) *out = rq->res;
-  else free_alns(&rq->res);
-  delete rq;
-  return st == TG_OK ? TG_OK : tg_fail(st, "batched align_read failed: " + msg);
+  const uint32_t idx = (uint32_t)(ticket & 0xFFFFFFFFull), gen = (uint32_t)(ticket >> 32);
+  std::shared_ptr<BatchSnapshot> snap;
+  uint32_t row = 0;
+  tg_status st;
+  std::string msg;
+  {
+    std::unique_lock<std::mutex> lk(b->mu);
+    if (idx >= b->slots.size()) return tg_fail(TG_ERR_INVALID, "unknown ticket (never issued or already waited for)");
+    Slot* s = &b->slots[idx];
+    if (!s->in_use || s->gen != gen || s->waited) return tg_fail(TG_ERR_INVALID, "unknown ticket (never issued or already waited for)");
+    s->waited = true;  // a ticket is waited for once
+    b->cv_done.wait(lk, [&] { return s->done; });
+    st = s->status;
+    if (st != TG_OK) msg = b->error;
+    snap = std::move(s->batch);
+    row = s->index;
+    s->batch.reset();
+    s->in_use = false;
+    s->gen++;
+    if (s->gen == 0) s->gen = 1;
+    b->free_slots.push_back(idx);
+  }
+  if (st != TG_OK) return tg_fail(st, "batched align_read failed: " + msg);
+  return cut_read(*snap, row, out);  // on the caller's thread, outside the lock
 }
 
 tg_status tg_batcher_align_read(tg_batcher* b, const uint8_t* read, uint32_t len, tg_read_alns* out) {
@@ -209,7 +248,9 @@ tg_status tg_batcher_align_read(tg_batcher* b, const uint8_t* read, uint32_t len
 }
 
 void tg_read_alns_free(tg_read_alns* r) {
-  if (r) free_alns(r);
+  if (!r) return;
+  free(r->alns);  // records and operations are one block
+  memset(r, 0, sizeof(*r));
 }
 
 tg_status tg_batcher_stats(tg_batcher* b, uint64_t* n_reads, uint64_t* n_batches, uint32_t* largest_batch) {
@@ -229,11 +270,7 @@ void tg_batcher_destroy(tg_batcher* b) {
   }
   b->cv_work.notify_all();
   if (b->worker.joinable()) b->worker.join();
-  for (auto& kv : b->tickets) {  // results nobody waited for
-    free_alns(&kv.second->res);
-    delete kv.second;
-  }
-  delete b;
+  delete b;  // results nobody waited for go with their snapshots
 }
 
 }  // extern "C"

@@ -1133,6 +1133,7 @@ struct tg_ctx {
   uint64_t round_task_cap = 0, round_ops_cap = 0, item_cap = 0, hops_cap = 0;
   int use_rounds = 1;
   int item_sort = 2;  // rounds whose items are handed out in locus order (TG_ITEM_SORT; 0 = off)
+  uint32_t small_batch = 32768;  // below this many reads a batch is latency-bound: no early output, no item sort (TG_SMALL_BATCH)
   // chunked host-buffer path: results of chunk k start at these pool positions / read row
   unsigned long long base_alns = 0, base_ops = 0;
   uint32_t out_row0 = 0;
@@ -1287,6 +1288,7 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
     return tg_fail(TG_ERR_INVALID, "Min alignment score percent must be between 0.0 and 1.0!");  // src/main.rs:46-49
   CU_CHECK(cudaSetDevice(ix->device));
   auto* c = new tg_ctx();
+  if (const char* e = getenv("TG_SMALL_BATCH")) c->small_batch = (uint32_t)atol(e);  // tests: 0 = every batch takes the large-batch path
   if (const char* e = getenv("TG_ITEM_SORT")) c->item_sort = atoi(e);  // experiments: rounds with locus-ordered items (0 = off)
   c->ix = ix;
   c->opts = *opts;
@@ -1603,11 +1605,15 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   if ((st = dpt_geometry(c, p, std::min<uint32_t>(max_xlen, TG_DPT_MAX_X) + max_bw + 1, c->round_task_cap, dpt_grid)) != TG_OK) return st;
   k_round_init<<<tblocks, 128, 0, c->stream>>>(p);
   c->n_launches++;
+  // a small batch (per-read callers behind tg_batcher) is all launch latency: no item sort, and the host looks for "nothing
+  // left" one round earlier (98 % of the reads are finished after round 1; a round is 13 launches, a check one sync)
+  const bool small = n < c->small_batch;
+  const uint32_t check_from = n <= 2 ? 0u : small ? 1u : 2u;
   for (uint32_t r = 0; r < TG_MAX_ROUNDS; r++) {
     p.round = r;
     k_round_plan<<<tblocks, 128, 0, c->stream>>>(p);
     p.perm = nullptr;
-    if ((int)r < c->item_sort) {  // the big rounds: hand the items to prep / post in locus order
+    if ((int)r < c->item_sort && !small) {  // the big rounds: hand the items to prep / post in locus order
       p.perm = (uint32_t*)c->r_perm.p;
       k_round_ikey<<<c->n_sms * 8, 256, 0, c->stream>>>(p);
       k_round_iscan<<<1, 1024, 0, c->stream>>>(p);
@@ -1653,7 +1659,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
       }
     }
     // late rounds are short: a host check for "nothing left" costs less than launching the remaining empty rounds
-    if (r >= 2 && r + 1 < TG_MAX_ROUNDS) {
+    if (r >= check_from && r + 1 < TG_MAX_ROUNDS) {
       CU_CHECK(cudaMemcpyAsync(c->h_active, &c->d_ctr->round_active[r], sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
       CU_CHECK(cudaStreamSynchronize(c->stream));
       if (*c->h_active == 0) break;
@@ -1870,7 +1876,7 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
   c->in_chunks = n_chunks; c->in_chunk_reads = chunk;
   {
     const char* em = getenv("TG_EARLY_MODE");  // experiments: 0 no early output, 1 after round 1 only, 2 (default) after rounds 0 and 1
-    c->early_out = c->use_rounds ? (em ? atoi(em) : 2) : 0;
+    c->early_out = c->use_rounds && n_reads >= c->small_batch ? (em ? atoi(em) : 2) : 0;  // (small batch: nothing to hide)
   }
   st = run_pipeline(c, (const uint8_t*)c->d_bases.p, (const uint64_t*)c->d_offs.p, n_reads, maxL, true);
   c->in_chunks = 0; c->early_out = 0;
