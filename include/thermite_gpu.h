@@ -212,8 +212,9 @@ tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint6
  * Per-read calls from many host threads: ThermiteAligner::align_read (src/wrapper.rs:20-27, :72).
  * The reference's embedding callers hold one clone per worker thread and align one read per call.  A tg_batcher lets
  * any number of threads do that against ONE context: reads are queued and a dispatcher thread runs tg_align_batch as
- * soon as max_batch_reads are waiting or the oldest queued read is max_wait_us old (what arrives while a batch is on
- * the GPU leaves together afterwards).  All tg_batcher_* calls except create / destroy are thread-safe; while the
+ * soon as max_batch_reads are waiting, the oldest queued read is max_wait_us old, or no new read has arrived for
+ * max_wait_us / 16 (clamped to 10..100 us): blocking callers are served as soon as they have all resubmitted, callers
+ * that stream tickets build large batches.  All tg_batcher_* calls except create / destroy are thread-safe; while the
  * batcher lives, `ctx` must not be used for anything else.  Records are identical to tg_align_batch's.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct tg_batcher tg_batcher;

@@ -4,8 +4,8 @@
 // `Arc<Index>`, one clone per worker thread, `align_read(name, read, qual)` per read (:72) -> align_read
 // (src/aligner.rs:123).  A GPU context wants batches.  tg_batcher sits between the two: callers submit reads (ticket) and
 // wait for them -- or block in tg_batcher_align_read, which is submit + wait -- and a dispatcher thread runs one
-// tg_align_batch over what is queued as soon as `max_batch_reads` are waiting or the oldest request is `max_wait_us`
-// old (so everything that arrived while the previous batch was on the GPU leaves at once).  Every caller gets its own
+// tg_align_batch over what is queued as soon as `max_batch_reads` are waiting, the oldest request is `max_wait_us` old, or
+// no new request has arrived for max_wait_us / 16 (10..100 us).  Every caller gets its own
 // records (the Vec<GenomeAlignment> of its read, operations rebased to a private block).  Results are those of
 // tg_align_batch, which does not depend on how reads are batched.
 //
@@ -80,7 +80,8 @@ struct tg_batcher {
   tg_batch_backend_fn fn = nullptr;
   void* user = nullptr;
   uint32_t max_batch = 0;
-  std::chrono::microseconds max_wait{0};
+  std::chrono::microseconds max_wait{0}, quiet{0};
+  Clock::time_point last_arrival;
 
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
@@ -106,9 +107,14 @@ void tg_batcher::run() {
       std::unique_lock<std::mutex> lk(mu);
       cv_work.wait(lk, [&] { return stop || !queue.empty(); });
       if (queue.empty()) return;  // stop requested and nothing left to serve
-      // give concurrent callers until the oldest request is max_wait old to join; a full batch goes at once
-      const auto deadline = queue.front()->arrival + max_wait;
-      cv_work.wait_until(lk, deadline, [&] { return stop || queue.size() >= max_batch; });
+      // A batch leaves when it is full, when its oldest request is max_wait old, or when nothing new has arrived for
+      // `quiet` (blocking callers all resubmit within microseconds of the previous batch and then wait: no point in
+      // sitting out max_wait; callers streaming windows of tickets keep arriving, and the batch keeps growing).
+      while (!stop && queue.size() < max_batch) {
+        const auto deadline = std::min(queue.front()->arrival + max_wait, last_arrival + quiet);
+        if (Clock::now() >= deadline) break;
+        cv_work.wait_until(lk, deadline);
+      }
       const size_t take = std::min<size_t>(queue.size(), max_batch);
       batch.assign(queue.begin(), queue.begin() + take);
       queue.erase(queue.begin(), queue.begin() + take);
@@ -175,6 +181,8 @@ tg_status tg_batcher_create_backend(tg_batch_backend_fn fn, void* user, uint32_t
     b->user = user;
     b->max_batch = max_batch_reads;
     b->max_wait = std::chrono::microseconds(max_wait_us);
+    b->quiet = std::chrono::microseconds(std::min<uint32_t>(std::max<uint32_t>(max_wait_us / 16, 10u), 100u));
+    if (b->quiet > b->max_wait) b->quiet = b->max_wait;
     b->worker = std::thread([b] { b->run(); });
     *out = b;
     return TG_OK;
@@ -203,6 +211,7 @@ tg_status tg_batcher_submit(tg_batcher* b, const uint8_t* read, uint32_t len, ui
     s.in_use = true; s.waited = false; s.done = false; s.status = TG_OK; s.len = len;
     if (len) memcpy(s.read, read, len);
     s.arrival = Clock::now();
+    b->last_arrival = s.arrival;
     *ticket = (uint64_t)idx | ((uint64_t)s.gen << 32);
     b->queue.push_back(&s);
     if (b->queue.size() == 1 || b->queue.size() == b->max_batch) b->cv_work.notify_one();

@@ -26,7 +26,7 @@ with open("/tmp/bb_reads.bin", "wb") as f:
     f.write(np.ascontiguousarray(bases, np.uint8).tobytes())
 print(f"host threads available: {os.cpu_count()}", flush=True)
 # blocking calls keep only `threads` reads in flight (a batch per handful of reads): run them on a small sample
-for threads, window, max_batch, wait, use in ((16, 1, 65536, 200, 20_000), (16, 1024, 65536, 200, n), (16, 16384, 262144, 500, n),
-                                              (4, 65536, 262144, 500, n), (1, 262144, 262144, 500, n)):
+for threads, window, max_batch, wait, use in ((16, 1, 65536, 200, 20_000), (16, 1024, 65536, 2000, n), (16, 16384, 262144, 5000, n),
+                                              (4, 65536, 262144, 5000, n), (1, 262144, 262144, 5000, n)):
     subprocess.check_call([exe, "/tmp/bb_index.tai", "/tmp/bb_reads.bin", str(threads), str(window), str(max_batch), str(wait),
                            str(use)])
