@@ -213,7 +213,7 @@ tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint6
  * The reference's embedding callers hold one clone per worker thread and align one read per call.  A tg_batcher lets
  * any number of threads do that against ONE context: reads are queued and a dispatcher thread runs tg_align_batch as
  * soon as max_batch_reads are waiting, the oldest queued read is max_wait_us old, or no new read has arrived for
- * max_wait_us / 16 (clamped to 10..100 us): blocking callers are served as soon as they have all resubmitted, callers
+ * max_wait_us / 4 (clamped to 20..100 us): blocking callers are served as soon as they have all resubmitted, callers
  * that stream tickets build large batches.  All tg_batcher_* calls except create / destroy are thread-safe; while the
  * batcher lives, `ctx` must not be used for anything else.  Records are identical to tg_align_batch's.
  * ------------------------------------------------------------------------------------------------- */

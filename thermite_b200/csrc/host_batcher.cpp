@@ -5,13 +5,15 @@
 // (src/aligner.rs:123).  A GPU context wants batches.  tg_batcher sits between the two: callers submit reads (ticket) and
 // wait for them -- or block in tg_batcher_align_read, which is submit + wait -- and a dispatcher thread runs one
 // tg_align_batch over what is queued as soon as `max_batch_reads` are waiting, the oldest request is `max_wait_us` old, or
-// no new request has arrived for max_wait_us / 16 (10..100 us).  Every caller gets its own
+// no new request has arrived for max_wait_us / 4 (20..100 us).  Every caller gets its own
 // records (the Vec<GenomeAlignment> of its read, operations rebased to a private block).  Results are those of
 // tg_align_batch, which does not depend on how reads are batched.
 //
-// Host cost per read is what limits this path, so: requests live in a slab of reusable slots (no allocation per submit,
-// ticket = slot | generation << 32), the dispatcher only snapshots a finished batch (four bulk copies) and marks its
+// Host cost per read is what limits this path, so: requests live in slabs of reusable slots (no allocation per submit,
+// ticket = slot | shard << 24 | generation << 32), a caller thread only ever takes the lock of its own shard (32 shards,
+// assigned round-robin per thread), the dispatcher only snapshots a finished batch (four bulk copies) and marks its
 // slots done, and every waiter cuts its own records out of the snapshot on its own thread.
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
@@ -76,54 +78,82 @@ tg_status cut_read(const BatchSnapshot& b, uint32_t i, tg_read_alns* o) {
 
 }  // namespace
 
+struct Shard {
+  std::mutex mu;
+  std::condition_variable cv_done;
+  std::deque<Slot> slots;          // stable addresses; indexed only under `mu`
+  std::vector<uint32_t> free_slots;
+  std::vector<Slot*> queue;        // submitted, not yet on the GPU
+};
+
 struct tg_batcher {
+  static constexpr uint32_t NSHARD = 32, SLOT_BITS = 24;
   tg_batch_backend_fn fn = nullptr;
   void* user = nullptr;
   uint32_t max_batch = 0;
-  std::chrono::microseconds max_wait{0}, quiet{0};
-  Clock::time_point last_arrival;
+  int64_t max_wait_ns = 0, quiet_ns = 0;
 
-  std::mutex mu;
-  std::condition_variable cv_work, cv_done;
-  std::deque<Slot> slots;          // stable addresses; indexed only under `mu`
-  std::vector<uint32_t> free_slots;
-  std::deque<Slot*> queue;         // submitted, not yet on the GPU
-  bool stop = false;
+  Shard shards[NSHARD];
+  std::atomic<uint32_t> next_shard{0};
+  std::atomic<uint64_t> queued{0};                         // requests in the shard queues
+  std::atomic<int64_t> oldest_ns{0}, last_arrival_ns{0};   // arrival of the (approximately) oldest / the newest queued request
+  std::atomic<bool> stop{false};
+
+  std::mutex mu;  // dispatcher sleep / statistics / error text
+  std::condition_variable cv_work;
   std::string error;  // message of the last failed batch (copied into the waiters' thread-local error)
   uint64_t n_reads = 0, n_batches = 0;
   uint32_t largest = 0;
   std::thread worker;
 
+  static int64_t now_ns() { return std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now().time_since_epoch()).count(); }
+  Shard& my_shard(uint32_t& id) {
+    static thread_local uint32_t mine = 0xFFFFFFFFu;
+    if (mine == 0xFFFFFFFFu) mine = next_shard.fetch_add(1) % NSHARD;
+    id = mine;
+    return shards[mine];
+  }
   void run();
-  void serve(std::vector<Slot*>& batch, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs);
+  void serve(std::vector<Slot*>& batch, const std::vector<uint32_t>& shard_end, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs);
 };
 
 void tg_batcher::run() {
   std::vector<Slot*> batch;
+  std::vector<uint32_t> shard_end(NSHARD);
   std::vector<uint8_t> bases;
   std::vector<uint64_t> offs;
   for (;;) {
     {
       std::unique_lock<std::mutex> lk(mu);
-      cv_work.wait(lk, [&] { return stop || !queue.empty(); });
-      if (queue.empty()) return;  // stop requested and nothing left to serve
+      cv_work.wait(lk, [&] { return stop.load() || queued.load() > 0; });
+      if (queued.load() == 0) return;  // stop requested and nothing left to serve
       // A batch leaves when it is full, when its oldest request is max_wait old, or when nothing new has arrived for
       // `quiet` (blocking callers all resubmit within microseconds of the previous batch and then wait: no point in
       // sitting out max_wait; callers streaming windows of tickets keep arriving, and the batch keeps growing).
-      while (!stop && queue.size() < max_batch) {
-        const auto deadline = std::min(queue.front()->arrival + max_wait, last_arrival + quiet);
-        if (Clock::now() >= deadline) break;
-        cv_work.wait_until(lk, deadline);
+      while (!stop.load() && queued.load() < max_batch) {
+        const int64_t deadline = std::min(oldest_ns.load() + max_wait_ns, last_arrival_ns.load() + quiet_ns);
+        const int64_t now = now_ns();
+        if (now >= deadline) break;
+        cv_work.wait_for(lk, std::chrono::nanoseconds(deadline - now));
       }
-      const size_t take = std::min<size_t>(queue.size(), max_batch);
-      batch.assign(queue.begin(), queue.begin() + take);
-      queue.erase(queue.begin(), queue.begin() + take);
     }
-    serve(batch, bases, offs);
+    batch.clear();
+    for (uint32_t k = 0; k < NSHARD; k++) {
+      Shard& sh = shards[k];
+      std::lock_guard<std::mutex> lk(sh.mu);
+      const size_t room = max_batch - batch.size();
+      const size_t take = std::min(sh.queue.size(), room);
+      batch.insert(batch.end(), sh.queue.begin(), sh.queue.begin() + take);
+      sh.queue.erase(sh.queue.begin(), sh.queue.begin() + take);
+      shard_end[k] = (uint32_t)batch.size();
+    }
+    if (queued.fetch_sub(batch.size()) > batch.size()) oldest_ns.store(now_ns());  // what stays behind starts a new batch
+    if (!batch.empty()) serve(batch, shard_end, bases, offs);
   }
 }
 
-void tg_batcher::serve(std::vector<Slot*>& batch, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs) {
+void tg_batcher::serve(std::vector<Slot*>& batch, const std::vector<uint32_t>& shard_end, std::vector<uint8_t>& bases,
+                       std::vector<uint64_t>& offs) {
   const uint32_t n = (uint32_t)batch.size();
   offs.assign(1, 0);
   bases.clear();
@@ -160,15 +190,23 @@ void tg_batcher::serve(std::vector<Slot*>& batch, std::vector<uint8_t>& bases, s
     n_reads += n;
     n_batches++;
     largest = std::max(largest, n);
-    for (uint32_t i = 0; i < n; i++) {
-      Slot* s = batch[i];
-      s->status = st;
-      s->batch = snap;
-      s->index = i;
-      s->done = true;
-    }
   }
-  cv_done.notify_all();
+  uint32_t i = 0;
+  for (uint32_t k = 0; k < NSHARD; k++) {
+    if (shard_end[k] == i) continue;
+    Shard& sh = shards[k];
+    {
+      std::lock_guard<std::mutex> lk(sh.mu);
+      for (; i < shard_end[k]; i++) {
+        Slot* s = batch[i];
+        s->status = st;
+        s->batch = snap;
+        s->index = i;
+        s->done = true;
+      }
+    }
+    sh.cv_done.notify_all();
+  }
 }
 
 tg_status tg_batcher_create_backend(tg_batch_backend_fn fn, void* user, uint32_t max_batch_reads, uint32_t max_wait_us,
@@ -180,9 +218,8 @@ tg_status tg_batcher_create_backend(tg_batch_backend_fn fn, void* user, uint32_t
     b->fn = fn;
     b->user = user;
     b->max_batch = max_batch_reads;
-    b->max_wait = std::chrono::microseconds(max_wait_us);
-    b->quiet = std::chrono::microseconds(std::min<uint32_t>(std::max<uint32_t>(max_wait_us / 16, 10u), 100u));
-    if (b->quiet > b->max_wait) b->quiet = b->max_wait;
+    b->max_wait_ns = (int64_t)max_wait_us * 1000;
+    b->quiet_ns = std::min<int64_t>((int64_t)std::min<uint32_t>(std::max<uint32_t>(max_wait_us / 4, 20u), 100u) * 1000, b->max_wait_ns);
     b->worker = std::thread([b] { b->run(); });
     *out = b;
     return TG_OK;
@@ -196,25 +233,35 @@ extern "C" {
 tg_status tg_batcher_submit(tg_batcher* b, const uint8_t* read, uint32_t len, uint64_t* ticket) {
   if (!b || !ticket || (!read && len)) return tg_fail(TG_ERR_INVALID, "null argument");
   if (len > TG_MAX_READ_LEN) return tg_fail(TG_ERR_CAPACITY, "read longer than TG_MAX_READ_LEN");
+  if (b->stop.load()) return tg_fail(TG_ERR_INVALID, "the batcher is being destroyed");
   try {
-    std::lock_guard<std::mutex> lk(b->mu);
-    if (b->stop) return tg_fail(TG_ERR_INVALID, "the batcher is being destroyed");
-    uint32_t idx;
-    if (!b->free_slots.empty()) {
-      idx = b->free_slots.back();
-      b->free_slots.pop_back();
-    } else {
-      idx = (uint32_t)b->slots.size();
-      b->slots.emplace_back();
+    uint32_t sid;
+    Shard& sh = b->my_shard(sid);
+    const int64_t now = tg_batcher::now_ns();
+    {
+      std::lock_guard<std::mutex> lk(sh.mu);
+      uint32_t idx;
+      if (!sh.free_slots.empty()) {
+        idx = sh.free_slots.back();
+        sh.free_slots.pop_back();
+      } else {
+        idx = (uint32_t)sh.slots.size();
+        if (idx >= (1u << tg_batcher::SLOT_BITS)) return tg_fail(TG_ERR_CAPACITY, "too many reads in flight on one thread");
+        sh.slots.emplace_back();
+      }
+      Slot& s = sh.slots[idx];
+      s.in_use = true; s.waited = false; s.done = false; s.status = TG_OK; s.len = len;
+      if (len) memcpy(s.read, read, len);
+      *ticket = (uint64_t)idx | ((uint64_t)sid << tg_batcher::SLOT_BITS) | ((uint64_t)s.gen << 32);
+      sh.queue.push_back(&s);
     }
-    Slot& s = b->slots[idx];
-    s.in_use = true; s.waited = false; s.done = false; s.status = TG_OK; s.len = len;
-    if (len) memcpy(s.read, read, len);
-    s.arrival = Clock::now();
-    b->last_arrival = s.arrival;
-    *ticket = (uint64_t)idx | ((uint64_t)s.gen << 32);
-    b->queue.push_back(&s);
-    if (b->queue.size() == 1 || b->queue.size() == b->max_batch) b->cv_work.notify_one();
+    b->last_arrival_ns.store(now);
+    const uint64_t q = b->queued.fetch_add(1) + 1;
+    if (q == 1) b->oldest_ns.store(now);
+    if (q == 1 || q == b->max_batch) {
+      std::lock_guard<std::mutex> lk(b->mu);  // (the dispatcher checks `queued` under this lock before it sleeps)
+      b->cv_work.notify_one();
+    }
     return TG_OK;
   } catch (const std::exception& e) {
     return tg_fail(TG_ERR_INTERNAL, e.what());
@@ -224,29 +271,37 @@ tg_status tg_batcher_submit(tg_batcher* b, const uint8_t* read, uint32_t len, ui
 tg_status tg_batcher_wait(tg_batcher* b, uint64_t ticket, tg_read_alns* out) {
   if (!b || !out) return tg_fail(TG_ERR_INVALID, "null argument");
   memset(out, 0, sizeof(*out));
-  const uint32_t idx = (uint32_t)(ticket & 0xFFFFFFFFull), gen = (uint32_t)(ticket >> 32);
+  const uint32_t low = (uint32_t)(ticket & 0xFFFFFFFFull), gen = (uint32_t)(ticket >> 32);
+  const uint32_t idx = low & ((1u << tg_batcher::SLOT_BITS) - 1), sid = low >> tg_batcher::SLOT_BITS;
+  if (sid >= tg_batcher::NSHARD) return tg_fail(TG_ERR_INVALID, "unknown ticket (never issued or already waited for)");
+  Shard& sh = b->shards[sid];
   std::shared_ptr<BatchSnapshot> snap;
   uint32_t row = 0;
   tg_status st;
-  std::string msg;
   {
-    std::unique_lock<std::mutex> lk(b->mu);
-    if (idx >= b->slots.size()) return tg_fail(TG_ERR_INVALID, "unknown ticket (never issued or already waited for)");
-    Slot* s = &b->slots[idx];
+    std::unique_lock<std::mutex> lk(sh.mu);
+    if (idx >= sh.slots.size()) return tg_fail(TG_ERR_INVALID, "unknown ticket (never issued or already waited for)");
+    Slot* s = &sh.slots[idx];
     if (!s->in_use || s->gen != gen || s->waited) return tg_fail(TG_ERR_INVALID, "unknown ticket (never issued or already waited for)");
     s->waited = true;  // a ticket is waited for once
-    b->cv_done.wait(lk, [&] { return s->done; });
+    sh.cv_done.wait(lk, [&] { return s->done; });
     st = s->status;
-    if (st != TG_OK) msg = b->error;
     snap = std::move(s->batch);
     row = s->index;
     s->batch.reset();
     s->in_use = false;
     s->gen++;
     if (s->gen == 0) s->gen = 1;
-    b->free_slots.push_back(idx);
+    sh.free_slots.push_back(idx);
   }
-  if (st != TG_OK) return tg_fail(st, "batched align_read failed: " + msg);
+  if (st != TG_OK) {
+    std::string msg;
+    {
+      std::lock_guard<std::mutex> lk(b->mu);
+      msg = b->error;
+    }
+    return tg_fail(st, "batched align_read failed: " + msg);
+  }
   return cut_read(*snap, row, out);  // on the caller's thread, outside the lock
 }
 
@@ -275,7 +330,7 @@ void tg_batcher_destroy(tg_batcher* b) {
   if (!b) return;
   {
     std::lock_guard<std::mutex> lk(b->mu);
-    b->stop = true;  // queued requests are still served; new ones are refused
+    b->stop.store(true);  // queued requests are still served; new ones are refused
   }
   b->cv_work.notify_all();
   if (b->worker.joinable()) b->worker.join();
