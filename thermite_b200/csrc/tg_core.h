@@ -900,8 +900,10 @@ TG_HDN void tg_extend_left_right(W& w, TgWarpMem& m, const uint64_t* seq, uint64
 }
 
 // lift_mem_to_tx (src/txome.rs:82-103): first exon in tx order intersecting the seed
+// (exon_at / sum_at: the exon that was found and the transcript offset of its first symbol, for callers that go on walking)
 TG_HD bool tg_lift_mem_to_tx(const uint32_t* te_start, const uint32_t* te_end, uint32_t e0, uint32_t e1,
-                             uint32_t ref_idx, uint32_t q, uint32_t len, uint32_t& t_ref, uint32_t& t_q, uint32_t& t_len) {
+                             uint32_t ref_idx, uint32_t q, uint32_t len, uint32_t& t_ref, uint32_t& t_q, uint32_t& t_len,
+                             uint32_t* exon_at = nullptr, uint32_t* sum_at = nullptr) {
   uint32_t exon_sum = 0;
   for (uint32_t e = e0; e < e1; e++) {
     uint32_t es = TG_LDG(te_start + e), ee = TG_LDG(te_end + e);
@@ -911,6 +913,7 @@ TG_HD bool tg_lift_mem_to_tx(const uint32_t* te_start, const uint32_t* te_end, u
       uint32_t start_off = es > a0 ? es - a0 : 0;
       uint32_t end = (a1 < ee ? a1 : ee) - es + exon_sum;
       t_ref = start; t_q = q + start_off; t_len = end - start;
+      if (exon_at) { *exon_at = e; *sum_at = exon_sum; }
       return true;
     }
     exon_sum += ee - es;

@@ -219,7 +219,8 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
     const uint32_t e0 = TG_LDG(ix.tx_exon_off + tx_idx), e1 = TG_LDG(ix.tx_exon_off + tx_idx + 1);
     const uint64_t t0 = TG_LDG(ix.tx_seq_off + tx_idx), t1 = TG_LDG(ix.tx_seq_off + tx_idx + 1);
     uint32_t tr = 0, tq = 0, tl = 0;
-    if (!tg_lift_mem_to_tx(ix.te_start, ix.te_end, e0, e1, ref_idx, q, len, tr, tq, tl)) continue;
+    uint32_t lift_e = e0, lift_sum = 0;  // the exon holding the lifted seed start and its transcript offset
+    if (!tg_lift_mem_to_tx(ix.te_start, ix.te_end, e0, e1, ref_idx, q, len, tr, tq, tl, &lift_e, &lift_sum)) continue;
     tl += tg_match_fwd(rp, tq + tl, L, ix.txseq4, t0 + tr + tl, t1);
     {
       uint32_t back = tg_match_bwd(rp, tq, ix.txseq4, t0 + tr, t0);
@@ -237,16 +238,13 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
     tg_problem_windows(pt, L, bw, ncRt, ncLt);
     uint32_t gkey = TG_NONE, gpos = TG_NONE, se = e0, so = 0;
     {
-      uint32_t exon_sum = 0;
-      for (uint32_t e = e0; e < e1; e++) {
-        const uint32_t es = TG_LDG(ix.te_start + e), elen = TG_LDG(ix.te_end + e) - es;
-        if (tr < exon_sum + elen) {  // the exon holding the seed start
-          se = e; so = tr - exon_sum; gpos = es + so;
-          if (so >= ncLt && (uint64_t)tr + tl + ncRt <= (uint64_t)exon_sum + elen) gkey = gpos;
-          break;
-        }
-        exon_sum += elen;
-      }
+      // the exon holding the (extended) seed start: the backward match can only have moved it towards the transcript
+      // start, so walk back from the exon lift_mem_to_tx found instead of forward from the first one
+      uint32_t e = lift_e, exon_sum = lift_sum;
+      while (tr < exon_sum) { e--; exon_sum -= TG_LDG(ix.te_end + e) - TG_LDG(ix.te_start + e); }
+      const uint32_t es = TG_LDG(ix.te_start + e), elen = TG_LDG(ix.te_end + e) - es;
+      se = e; so = tr - exon_sum; gpos = es + so;
+      if (so >= ncLt && (uint64_t)tr + tl + ncRt <= (uint64_t)exon_sum + elen) gkey = gpos;
     }
     uint32_t pi = n_prob;
     for (uint32_t k = 0; k < n_prob; k++) {
