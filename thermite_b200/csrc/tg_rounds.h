@@ -211,11 +211,30 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
     p_gpos[0] = ref_idx; p_se[0] = 0; p_so[0] = 0; p_e0[0] = 0; p_e1[0] = 0;
   }
   const TgStabRange xr = tg_stab_begin<W>(w, ix.exon_stab, ix.n_exon_stab, ix.exon_maxlen, ref_idx, ref_idx + len);
+  // The intersecting exons in find() order.  One pass over the start-sorted range collects them, sorted by rank, into a
+  // short list (a range holds every exon that starts within exon_maxlen before the seed: hundreds on a dense annotation,
+  // and rescanning it for every next rank would cost range x candidates loads); only when more than TG_CMAX intersect
+  // does the walk fall back to one scan per rank (it then ends in "complex" at the TG_CMAX + 1st candidate as before).
+  uint32_t m_rank[TG_CMAX], m_tx[TG_CMAX], n_m = 0;
+  bool listed = true;
+  for (uint32_t i = xr.lo; i < xr.hi; i++) {
+    const TgStab e = tg_stab_load(ix.exon_stab, i);
+    if (!(e.start < xr.qe && xr.qs < e.end)) continue;
+    if (n_m == TG_CMAX) { listed = false; break; }
+    uint32_t k = n_m++;
+    for (; k > 0 && m_rank[k - 1] > e.rank; k--) { m_rank[k] = m_rank[k - 1]; m_tx[k] = m_tx[k - 1]; }
+    m_rank[k] = e.rank; m_tx[k] = e.data;
+  }
   uint32_t next_rank = 0;
-  for (;;) {
+  for (uint32_t ci = 0;; ci++) {
     uint32_t tx_idx = 0, xrank = 0;
-    if (!tg_stab_next<W>(w, ix.exon_stab, xr, next_rank, xrank, tx_idx)) break;
-    next_rank = xrank + 1;
+    if (listed) {
+      if (ci >= n_m) break;
+      tx_idx = m_tx[ci];
+    } else {
+      if (!tg_stab_next<W>(w, ix.exon_stab, xr, next_rank, xrank, tx_idx)) break;
+      next_rank = xrank + 1;
+    }
     const uint32_t e0 = TG_LDG(ix.tx_exon_off + tx_idx), e1 = TG_LDG(ix.tx_exon_off + tx_idx + 1);
     const uint64_t t0 = TG_LDG(ix.tx_seq_off + tx_idx), t1 = TG_LDG(ix.tx_seq_off + tx_idx + 1);
     uint32_t tr = 0, tq = 0, tl = 0;
