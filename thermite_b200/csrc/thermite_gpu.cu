@@ -813,8 +813,9 @@ __global__ void __launch_bounds__(128) k_round_post(RoundParams p) {
   round_item_range(p, lo, hi);
   // items appended from here on (by scan) belong to the next round
   if (blockIdx.x == 0 && threadIdx.x == 0) p.ctr->round_end[p.round] = p.ctr->items_used;
-  // (item order, not the locus order prep uses: post is bound by the latency of its loads of the item's tables, and
-  // neighbouring items keep those in neighbouring memory -- measured 0.53 ms against 0.63 ms per 1 M items)
+  // (item order, not the locus order prep uses: post is bound by the latency of its loads, and items are in read order,
+  // so neighbouring threads find their read states, packed reads and outputs in neighbouring memory -- 0.53 ms against
+  // 0.63 ms per 1 M items in locus order; storing the hit tables in prep's order as well did not help: 46.6 -> 47.1 ms per step)
   for (unsigned long long it = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < hi; it += (unsigned long long)gridDim.x * blockDim.x) {
     TgItemRes& ir = p.ires[it];
     if (ir.flags & TG_IF_FAIL) continue;
