@@ -10,6 +10,7 @@
  *   tg_ctx_create            AlignOpts + per-read SwgExtend scratch  src/aligner.rs:452-464, :140-141
  *   tg_align_batch           align_read, batched                   src/aligner.rs:123-190 (+ :198-449, src/swg.rs, src/txome.rs:82-160,
  *                                                                   Index::all_smems src/index.rs:228-255)
+ *   tg_format_bam_header / tg_format_batch_bam   bam::Writer path   src/aligner.rs:41-47, 69-72, 98-101
  *   tg_batcher_*             ThermiteAligner::align_read from many threads  src/wrapper.rs:20-27, :72
  *   tg_seed_batch            Index::all_smems, batched             src/index.rs:228-255
  *   tg_swg_extend_batch      SwgExtend::extend, batched            src/swg.rs:31-207
@@ -270,6 +271,15 @@ tg_status tg_format_sam_header(const tg_index_host* ix, char** out, size_t* out_
 tg_status tg_format_batch(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
                           const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals,
                           const uint64_t* qual_offs, int sam, char** out, size_t* out_len);
+/* BAM (OutputFormat::Bam, src/aligner.rs:41-47, 69-72, 98-101): the records of tg_format_sam_header / tg_format_batch's
+ * SAM text encoded as BAM and BGZF-compressed.  tg_format_bam_header = magic, header text and reference list
+ * (write_header + write_reference_sequences); tg_format_batch_bam = the alignment records of one batch, optionally
+ * followed by the BGZF end-of-file block.  header ++ batches (the last with append_eof = 1) is a complete BAM file.
+ * Compressed bytes and integer tag widths are encoder choices: parity is on the decoded records. */
+tg_status tg_format_bam_header(const tg_index_host* ix, void** out, size_t* out_len);
+tg_status tg_format_batch_bam(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
+                              const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
+                              int append_eof, void** out, size_t* out_len);
 /* FASTQ text -> concatenated bases / names / quals with offsets (needletail::parse_fastx_file, src/aligner.rs:51-55).
  * All six outputs are malloc'ed; free each with tg_free. */
 tg_status tg_parse_fastq(const char* text, size_t len, uint32_t* n_reads, uint8_t** bases, uint64_t** offs,

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import thermite_b200 as tb
-from common import golden
+from common import bam_to_sam, golden
 from oracle import orc
 from thermite_b200 import api
 
@@ -161,3 +161,45 @@ def test_text4_is_the_packed_both_strand_text():
     assert all(int(w) == 0 for w in t4[(n + 15) // 16:]) and len(t4) == n // 16 + 4
     b = bytes(codes + 1)
     assert list(ix.suffix_array()) == sorted(range(n), key=lambda i: b[i:])
+
+
+def test_bam_output_decodes_to_the_sam_text():
+    """SURVEY 8f N4 / OutputFormat::Bam (src/aligner.rs:41-47, 69-72, 98-101): header ++ records ++ EOF block is a valid
+    BGZF / BAM stream whose header, reference list and records decode to exactly the SAM text of the same records
+    (oracle records, product writer): mapped and unmapped reads, both strands, secondary records, every tag."""
+    from common import small_world
+    from thermite_b200 import synth
+    cases = []
+    fa, gtf, fq = golden("test_ref.fasta"), golden("test_ref.gtf"), golden("test_query.fastq")
+    cases.append((fa, gtf, tb.parse_fastq(fq), dict(k=3, min_score=0)))
+    contigs, gtf2, txs, fa2 = small_world(5)
+    n = 3000
+    rb, ro = synth.make_reads(3, contigs, txs, n, L=91, sub=0.01, ins=0.002, dele=0.002)
+    rng = np.random.default_rng(1)
+    fq2 = b"".join(b"@r%d some comment\n%s\n+\n%s\n" % (i, bytes(rb[int(ro[i]):int(ro[i + 1])]) if i % 50 else b"ACGTNNNNACGT" * 3,
+                                                   bytes(rng.integers(35, 74, 36 if i % 50 == 0 else int(ro[i + 1] - ro[i]), dtype=np.uint8)))
+                   for i in range(n))
+    cases.append((fa2, gtf2, tb.parse_fastq(fq2), dict(k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True)))
+    for fa, gtf, (bases, offs, names, name_offs, quals, qual_offs), kw in cases:
+        oix = orc.Index.create(fa, gtf)
+        ores = oix.align_batch(bases, offs, **kw)
+        ix = tb.Index.create_from_memory(fa, gtf)
+        n = len(offs) - 1
+        first = np.ascontiguousarray(ores.read_off[:-1])
+        count = np.ascontiguousarray((ores.read_off[1:] - ores.read_off[:-1]).astype(np.uint32))
+        res = api._Result(n, len(ores.alns), len(ores.ops), first.ctypes.data, count.ctypes.data, ores.alns.ctypes.data,
+                          ores.ops.ctypes.data, 0, 0, 0, 0)
+        out, ln = C.c_void_p(), C.c_size_t()
+        args = (ix._h, C.byref(res), api._p(bases), api._p(offs), api._p(names), api._p(name_offs), api._p(quals), api._p(qual_offs))
+        assert tb.lib().tg_format_batch(*args, 1, C.byref(out), C.byref(ln)) == 0
+        sam = C.string_at(out, ln.value)
+        tb.lib().tg_free(out)
+        assert tb.lib().tg_format_batch_bam(*args, 1, C.byref(out), C.byref(ln)) == 0
+        bam = tb.bam_header(ix) + C.string_at(out, ln.value)
+        tb.lib().tg_free(out)
+        assert bam.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+        text, refs, lines, n_blocks = bam_to_sam(bam)
+        assert text == tb.sam_header(ix)
+        assert [b"@SQ\tSN:%s\tLN:%d" % r for r in refs] == [l for l in text.split(b"\n") if l.startswith(b"@SQ")]
+        assert lines == sam and lines.count(b"\n") >= n
+        assert n_blocks >= 3

@@ -69,6 +69,7 @@ ABI_SYMBOLS = [
     "tg_index_host_from_blob", "tg_index_host_save", "tg_index_host_load", "tg_index_host_destroy",
     "tg_index_host_text_len", "tg_index_host_n_refs", "tg_index_host_n_txs", "tg_index_host_n_genes",
     "tg_index_host_ref", "tg_index_host_tx", "tg_index_host_gene_id", "tg_index_host_gene_name", "tg_index_host_sa",
+    "tg_format_bam_header", "tg_format_batch_bam",
     "tg_batcher_create", "tg_batcher_submit", "tg_batcher_wait", "tg_batcher_align_read", "tg_read_alns_free",
     "tg_batcher_stats", "tg_batcher_destroy",
     "tg_index_host_text4", "tg_index_host_create_from_files_gpu", "tg_index_host_create_from_memory_gpu", "tg_suffix_array_gpu",
@@ -516,6 +517,16 @@ class Aligner:
         return s
 
 
+    def format_result_bam_raw(self, res: _Result, bases, offs, names, name_offs, quals, qual_offs, eof: bool = False) -> bytes:
+        """BGZF-compressed BAM records of one batch (src/aligner.rs:69-72, 98-101)."""
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(lib().tg_format_batch_bam(self.index._h, C.byref(res), _p(bases), _p(offs), _p(names), _p(name_offs),
+                                         _p(quals), _p(qual_offs), int(eof), C.byref(out), C.byref(n)))
+        s = C.string_at(out, n.value)
+        lib().tg_free(out)
+        return s
+
+
 class OutputFormat:
     """src/aln_writer.rs:16-21"""
     Bam = "bam"
@@ -548,6 +559,15 @@ def parse_fastq(text: bytes):
 def sam_header(index: Index) -> bytes:
     out, n = C.c_void_p(), C.c_size_t()
     _check(lib().tg_format_sam_header(index._h, C.byref(out), C.byref(n)))
+    s = C.string_at(out, n.value)
+    lib().tg_free(out)
+    return s
+
+
+def bam_header(index: Index) -> bytes:
+    """BGZF block(s) with the BAM magic, header text and reference list (src/aligner.rs:41-47)."""
+    out, n = C.c_void_p(), C.c_size_t()
+    _check(lib().tg_format_bam_header(index._h, C.byref(out), C.byref(n)))
     s = C.string_at(out, n.value)
     lib().tg_free(out)
     return s
@@ -624,17 +644,18 @@ class ThermiteAligner:
 
 def align_reads_from_file(index: Index, query_paths, output_path: str, output_fmt: str, align_opts: AlignOpts,
                           device: int = 0, batch_reads: int = 1 << 20):
-    """src/aligner.rs:22-120: align FASTQ files and write PAF or SAM text.  BAM needs htslib/noodles, which this
-    image does not have: requesting it raises ThermiteError."""
-    if output_fmt == OutputFormat.Bam:
-        raise ThermiteError("BAM output is not available in this build (no htslib); use SAM or PAF")
+    """src/aligner.rs:22-120: align FASTQ files and write PAF, SAM or BAM (csrc/host_bam.cpp: the SAM records encoded
+    as BAM in BGZF blocks, end-of-file block last)."""
     aligner = Aligner(index, align_opts, device)
     sam = output_fmt == OutputFormat.Sam
+    bam = output_fmt == OutputFormat.Bam
     import sys
     out = sys.stdout.buffer if output_path == "-" else open(output_path, "wb")
     try:
         if sam:
             out.write(sam_header(index))
+        if bam:
+            out.write(bam_header(index))
         for qp in query_paths:
             with open(qp, "rb") as f:
                 text = f.read()
@@ -650,8 +671,14 @@ def align_reads_from_file(index: Index, query_paths, output_path: str, output_fm
                 ql = quals[int(qual_offs[lo]): int(qual_offs[hi])]
                 b = np.ascontiguousarray(b); o = np.ascontiguousarray(o)
                 res = aligner.align_reads_raw(b.ctypes.data, o.ctypes.data, hi - lo)
+                if bam:
+                    out.write(aligner.format_result_bam_raw(res, b, o, np.ascontiguousarray(nm), np.ascontiguousarray(no),
+                                                            np.ascontiguousarray(ql), np.ascontiguousarray(qo)))
+                    continue
                 out.write(aligner.format_result_raw(res, b, o, np.ascontiguousarray(nm), np.ascontiguousarray(no),
                                                     np.ascontiguousarray(ql), np.ascontiguousarray(qo), sam))
+        if bam:
+            out.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))  # BGZF end-of-file block
     finally:
         if out is not sys.stdout.buffer:
             out.close()

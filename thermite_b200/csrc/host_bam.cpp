@@ -1,0 +1,301 @@
+// host_bam.cpp -- BAM output: OutputFormat::Bam of align_reads_from_file
+// (/root/reference/src/aligner.rs:41-47, 69-72, 98-101: noodles `bam::Writer::write_header`, `write_reference_sequences`,
+// `write_sam_record`).  The reference builds a SAM record and lets the BAM writer encode it; this file does the same:
+// the SAM text of tg_format_batch / tg_format_sam_header is encoded line by line into BAM records (SAM spec v1 section
+// 4.2) and written as BGZF blocks (section 4.1; zlib raw deflate, 64 KB blocks, the 28-byte EOF marker on request).
+// Parity note: the compressed bytes depend on the deflate implementation and the integer tag width on the encoder
+// (the spec allows c/C/s/S/i/I for the same value; the smallest type that holds the value is used, as htslib does), so
+// BAM parity is defined on the decoded records: they must decode to exactly the SAM text (tests/test_abi.py).
+#include <zlib.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "tg_internal.h"
+
+namespace {
+
+void put16(std::string& s, uint32_t v) { char b[2] = {(char)(v & 255), (char)((v >> 8) & 255)}; s.append(b, 2); }
+void put32(std::string& s, uint32_t v) {
+  char b[4] = {(char)(v & 255), (char)((v >> 8) & 255), (char)((v >> 16) & 255), (char)((v >> 24) & 255)};
+  s.append(b, 4);
+}
+
+// one BGZF block for data[0, n), n <= 0xff00
+bool bgzf_block(const char* data, size_t n, std::string& out) {
+  z_stream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+  std::vector<unsigned char> buf(deflateBound(&zs, (uLong)n) + 64);
+  zs.next_in = (Bytef*)data;
+  zs.avail_in = (uInt)n;
+  zs.next_out = buf.data();
+  zs.avail_out = (uInt)buf.size();
+  const int rc = deflate(&zs, Z_FINISH);
+  const size_t clen = zs.total_out;
+  deflateEnd(&zs);
+  if (rc != Z_STREAM_END || clen + 26 > 65536) return false;
+  static const unsigned char hdr[12] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0};
+  out.append((const char*)hdr, 12);
+  out.push_back('B'); out.push_back('C');
+  put16(out, 2);
+  put16(out, (uint32_t)(clen + 25));  // BSIZE = total block size - 1
+  out.append((const char*)buf.data(), clen);
+  put32(out, (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)data, (uInt)n));
+  put32(out, (uint32_t)n);
+  return true;
+}
+
+// raw bytes -> BGZF blocks (independent blocks: compressed on the host's cores, concatenated in order)
+bool bgzf_compress(const std::string& raw, std::string& out) {
+  const size_t BLK = 0xff00;
+  const size_t nb = (raw.size() + BLK - 1) / BLK;
+  if (nb == 0) return true;
+  uint32_t T = (uint32_t)std::min<size_t>(std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64), nb);
+  if (nb < 16) T = 1;
+  std::vector<std::string> parts(T);
+  std::vector<char> ok(T, 1);
+  auto work = [&](uint32_t t) {
+    const size_t b0 = nb * t / T, b1 = nb * (t + 1) / T;
+    for (size_t b = b0; b < b1 && ok[t]; b++) {
+      const size_t at = b * BLK;
+      if (!bgzf_block(raw.data() + at, std::min(BLK, raw.size() - at), parts[t])) ok[t] = 0;
+    }
+  };
+  if (T == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  for (uint32_t t = 0; t < T; t++) {
+    if (!ok[t]) return false;
+    out += parts[t];
+  }
+  return true;
+}
+
+const unsigned char BGZF_EOF[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43,
+                                    0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+// SAM spec 5.3
+uint32_t reg2bin(int64_t beg, int64_t end) {
+  --end;
+  if (beg >> 14 == end >> 14) return (uint32_t)(((1 << 15) - 1) / 7 + (beg >> 14));
+  if (beg >> 17 == end >> 17) return (uint32_t)(((1 << 12) - 1) / 7 + (beg >> 17));
+  if (beg >> 20 == end >> 20) return (uint32_t)(((1 << 9) - 1) / 7 + (beg >> 20));
+  if (beg >> 23 == end >> 23) return (uint32_t)(((1 << 6) - 1) / 7 + (beg >> 23));
+  if (beg >> 26 == end >> 26) return (uint32_t)(((1 << 3) - 1) / 7 + (beg >> 26));
+  return 0;
+}
+
+struct Field { const char* p; size_t n; };
+
+// reference names of the header in @SQ order (build_sam_header collapses the two strands, src/aln_writer.rs:256-276)
+std::vector<std::string> header_refs(const tg_index_host* ix, std::vector<uint32_t>* lens) {
+  std::vector<std::string> seen;
+  for (uint32_t i = 0; i < ix->hdr()->n_refs; i++) {
+    const std::string& nm = ix->ref_names[i];
+    bool dup = false;
+    for (auto& s : seen) if (s == nm) { dup = true; break; }
+    if (dup) continue;
+    seen.push_back(nm);
+    if (lens) {
+      uint64_t v[4];
+      tg_index_host_ref(ix, i, v);
+      lens->push_back((uint32_t)v[2]);
+    }
+  }
+  return seen;
+}
+
+// one SAM line (without the newline) -> one BAM record appended to `out`
+bool sam_line_to_bam(const char* line, size_t len, const std::vector<std::string>& refs, std::string& out, std::string& err) {
+  std::vector<Field> f;
+  size_t b = 0;
+  for (size_t i = 0; i <= len; i++)
+    if (i == len || line[i] == '\t') { f.push_back(Field{line + b, i - b}); b = i + 1; }
+  if (f.size() < 11) { err = "SAM line with fewer than 11 fields"; return false; }
+  auto num = [](const Field& x) { long long v = 0; bool neg = false; size_t i = 0; if (x.n && x.p[0] == '-') { neg = true; i = 1; }
+                                  for (; i < x.n; i++) v = v * 10 + (x.p[i] - '0'); return neg ? -v : v; };
+  int32_t ref_id = -1;
+  if (!(f[2].n == 1 && f[2].p[0] == '*')) {
+    for (size_t i = 0; i < refs.size(); i++)
+      if (refs[i].size() == f[2].n && memcmp(refs[i].data(), f[2].p, f[2].n) == 0) { ref_id = (int32_t)i; break; }
+    if (ref_id < 0) { err = "reference name not in the header"; return false; }
+  }
+  const int64_t pos = num(f[3]) - 1;
+  // CIGAR
+  std::vector<uint32_t> cig;
+  int64_t ref_len = 0;
+  if (!(f[5].n == 1 && f[5].p[0] == '*')) {
+    uint64_t v = 0;
+    for (size_t i = 0; i < f[5].n; i++) {
+      const char c = f[5].p[i];
+      if (c >= '0' && c <= '9') { v = v * 10 + (uint64_t)(c - '0'); continue; }
+      const char* ops = "MIDNSHP=X";
+      const char* at = strchr(ops, c);
+      if (!at || v >= (1ull << 28)) { err = "bad CIGAR"; return false; }
+      const uint32_t op = (uint32_t)(at - ops);
+      cig.push_back((uint32_t)(v << 4) | op);
+      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += (int64_t)v;
+      v = 0;
+    }
+  }
+  const bool has_seq = !(f[9].n == 1 && f[9].p[0] == '*');
+  const uint32_t l_seq = has_seq ? (uint32_t)f[9].n : 0u;
+  const int64_t end = pos + (ref_len > 0 ? ref_len : 1);
+  const uint32_t bin = reg2bin(pos, end);  // unmapped (pos -1): reg2bin(-1, 0) = 4680, as the spec asks
+  std::string r;
+  put32(r, (uint32_t)ref_id);
+  put32(r, (uint32_t)(int32_t)pos);
+  r.push_back((char)(f[0].n + 1));
+  r.push_back((char)num(f[4]));
+  put16(r, bin);
+  put16(r, (uint32_t)cig.size());
+  put16(r, (uint32_t)num(f[1]));
+  put32(r, l_seq);
+  put32(r, 0xFFFFFFFFu);  // RNEXT '*'
+  put32(r, 0xFFFFFFFFu);  // PNEXT 0
+  put32(r, 0);            // TLEN
+  if (f[0].n > 254) { err = "read name longer than 254 bytes"; return false; }
+  r.append(f[0].p, f[0].n);
+  r.push_back('\0');
+  for (uint32_t c : cig) put32(r, c);
+  static const char* codes = "=ACMGRSVTWYHKDBN";
+  for (uint32_t i = 0; i < l_seq; i += 2) {
+    auto code = [&](char ch) { if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32); const char* at = strchr(codes, ch); return (unsigned)(at && ch ? at - codes : 15); };
+    const unsigned hi = code(f[9].p[i]), lo = i + 1 < l_seq ? code(f[9].p[i + 1]) : 0u;
+    r.push_back((char)(hi << 4 | lo));
+  }
+  if (f[10].n == 1 && f[10].p[0] == '*') r.append(l_seq, (char)0xFF);
+  else {
+    if (f[10].n != l_seq) { err = "SEQ and QUAL differ in length"; return false; }
+    for (uint32_t i = 0; i < l_seq; i++) r.push_back((char)(f[10].p[i] - 33));
+  }
+  for (size_t k = 11; k < f.size(); k++) {  // TAG:TYPE:VALUE
+    const Field& t = f[k];
+    if (t.n < 5 || t.p[2] != ':' || t.p[4] != ':') { err = "bad optional field"; return false; }
+    r.append(t.p, 2);
+    const Field val{t.p + 5, t.n - 5};
+    switch (t.p[3]) {
+      case 'A': r.push_back('A'); r.push_back(val.n ? val.p[0] : ' '); break;
+      case 'Z': r.push_back('Z'); r.append(val.p, val.n); r.push_back('\0'); break;
+      case 'i': {
+        const long long v = num(val);
+        if (v >= 0) {
+          if (v <= 255) { r.push_back('C'); r.push_back((char)v); }
+          else if (v <= 65535) { r.push_back('S'); put16(r, (uint32_t)v); }
+          else { r.push_back('I'); put32(r, (uint32_t)v); }
+        } else {
+          if (v >= -128) { r.push_back('c'); r.push_back((char)v); }
+          else if (v >= -32768) { r.push_back('s'); put16(r, (uint32_t)(int32_t)v); }
+          else { r.push_back('i'); put32(r, (uint32_t)(int32_t)v); }
+        }
+        break;
+      }
+      default: err = "optional field type not produced by thermite"; return false;
+    }
+  }
+  put32(out, (uint32_t)r.size());
+  out += r;
+  return true;
+}
+
+tg_status hand_over(const std::string& s, void** out, size_t* out_len) {
+  *out = malloc(s.size() + 1);
+  if (!*out) return tg_fail(TG_ERR_INTERNAL, "out of memory");
+  memcpy(*out, s.data(), s.size());
+  *out_len = s.size();
+  return TG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+tg_status tg_format_bam_header(const tg_index_host* ix, void** out, size_t* out_len) {
+  if (!ix || !out || !out_len) return tg_fail(TG_ERR_INVALID, "null argument");
+  try {
+    char* text = nullptr;
+    size_t tl = 0;
+    tg_status st = tg_format_sam_header(ix, &text, &tl);
+    if (st != TG_OK) return st;
+    std::string raw("BAM\1", 4);
+    put32(raw, (uint32_t)tl);
+    raw.append(text, tl);
+    free(text);
+    std::vector<uint32_t> lens;
+    const std::vector<std::string> refs = header_refs(ix, &lens);
+    put32(raw, (uint32_t)refs.size());
+    for (size_t i = 0; i < refs.size(); i++) {
+      put32(raw, (uint32_t)refs[i].size() + 1);
+      raw += refs[i];
+      raw.push_back('\0');
+      put32(raw, lens[i]);
+    }
+    std::string z;
+    if (!bgzf_compress(raw, z)) return tg_fail(TG_ERR_INTERNAL, "deflate failed");
+    return hand_over(z, out, out_len);
+  } catch (const std::exception& e) {
+    return tg_fail(TG_ERR_INTERNAL, e.what());
+  }
+}
+
+tg_status tg_format_batch_bam(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
+                              const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
+                              int append_eof, void** out, size_t* out_len) {
+  if (!out || !out_len) return tg_fail(TG_ERR_INVALID, "null argument");
+  try {
+    char* sam = nullptr;
+    size_t sl = 0;
+    tg_status st = tg_format_batch(ix, res, bases, offs, names, name_offs, quals, qual_offs, 1, &sam, &sl);
+    if (st != TG_OK) return st;
+    const std::vector<std::string> refs = header_refs(ix, nullptr);
+    // line ranges on the host's cores; pieces concatenated in order
+    uint32_t T = (uint32_t)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64);
+    if (sl < (1u << 22)) T = 1;
+    std::vector<size_t> cut(T + 1, sl);
+    cut[0] = 0;
+    for (uint32_t t = 1; t < T; t++) {
+      size_t p = sl * t / T;
+      while (p < sl && sam[p] != '\n') p++;
+      cut[t] = p < sl ? p + 1 : sl;
+    }
+    std::vector<std::string> parts(T), errs(T);
+    auto work = [&](uint32_t t) {
+      size_t p = cut[t];
+      const size_t e = cut[t + 1];
+      parts[t].reserve((e - p) * 3 / 4 + 64);
+      while (p < e) {
+        const char* nl = (const char*)memchr(sam + p, '\n', e - p);
+        const size_t n = nl ? (size_t)(nl - (sam + p)) : e - p;
+        if (n && !sam_line_to_bam(sam + p, n, refs, parts[t], errs[t])) return;
+        p += n + 1;
+      }
+    };
+    if (T == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (uint32_t t = 0; t < T; t++) th.emplace_back(work, t);
+      for (auto& x : th) x.join();
+    }
+    free(sam);
+    std::string raw;
+    for (uint32_t t = 0; t < T; t++) {
+      if (!errs[t].empty()) return tg_fail(TG_ERR_INTERNAL, "BAM encoding: " + errs[t]);
+      raw += parts[t];
+    }
+    std::string z;
+    if (!bgzf_compress(raw, z)) return tg_fail(TG_ERR_INTERNAL, "deflate failed");
+    if (append_eof) z.append((const char*)BGZF_EOF, 28);
+    return hand_over(z, out, out_len);
+  } catch (const std::exception& e) {
+    return tg_fail(TG_ERR_INTERNAL, e.what());
+  }
+}
+
+}  // extern "C"
