@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import ht
-from common import golden, reads_to_batch, small_world, swg_pairs
+from common import bam_to_sam, golden, reads_to_batch, small_world, swg_pairs
 from oracle import orc
 from thermite_b200 import AlignOpts, Aligner, Index, ThermiteAligner, parse_fastq, sam_header, suffix_array_gpu, synth
 
@@ -334,3 +334,24 @@ def test_large_and_small_batch_paths_give_the_same_records(small_batch, monkeypa
     _cmp(al.align_reads(b2, o2), ores, n)
     for m in (1, 2, 7):   # tiny batches: the host check after round 0 / 1
         _cmp(al.align_reads(b2[: int(o2[m])], o2[: m + 1]), ores, m)
+
+
+def test_align_reads_from_file_paf_sam_bam(tmp_path):
+    """align_reads_from_file (src/aligner.rs:22-120) end to end on the reference's own test files: PAF and SAM equal
+    the golden text, the BAM file decodes to the SAM file (header, reference list, records)."""
+    from thermite_b200 import OutputFormat, align_reads_from_file
+    fa, gtf, fq = golden("test_ref.fasta"), golden("test_ref.gtf"), golden("test_query.fastq")
+    qp = tmp_path / "q.fastq"
+    qp.write_bytes(fq)
+    ix = Index.create_from_memory(fa, gtf)
+    opts = AlignOpts(min_seed_len=3, min_aln_score=0)
+    outs = {}
+    for fmt in (OutputFormat.Paf, OutputFormat.Sam, OutputFormat.Bam):
+        op = tmp_path / ("out." + fmt)
+        align_reads_from_file(ix, [str(qp)], str(op), fmt, opts, batch_reads=4)   # several batches per file
+        outs[fmt] = op.read_bytes()
+    assert outs[OutputFormat.Paf] == golden("test_query.paf")
+    assert outs[OutputFormat.Sam] == golden("test_query.sam")
+    text, refs, lines, n_blocks = bam_to_sam(outs[OutputFormat.Bam])
+    assert text + lines == outs[OutputFormat.Sam]
+    assert [r[0] for r in refs] == [b"some_ref", b"another_seq", b"introns_seq", b"introns_revcomp"]
