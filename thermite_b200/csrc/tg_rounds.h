@@ -387,11 +387,27 @@ TG_HD TgSideRes tg_side_result(const TgTask* tasks, int32_t task, uint32_t xlen)
 // rev(left.ops) ++ Match*len ++ right.ops (src/aligner.rs:388-394) from the stored (reversed) task operations.
 // `out` must have room for L.ops_n + R.ops_n + 3 words.
 TG_HD void tg_stitch_ops(const uint32_t* pool, const TgSideRes& L_, const TgSideRes& R_, uint32_t len, TgOps& out) {
-  if (L_.xclip) tg_ops_push(out, TG_OP_XCLIP, L_.xclip);
-  for (uint32_t i = 0; i < L_.ops_n; i++) tg_ops_push(out, pool[L_.ops_off + i] & 7u, pool[L_.ops_off + i] >> 3);
-  tg_ops_push(out, TG_OP_MATCH, len);
-  for (uint32_t i = R_.ops_n; i-- > 0;) tg_ops_push(out, pool[R_.ops_off + i] & 7u, pool[R_.ops_off + i] >> 3);
-  if (R_.xclip) tg_ops_push(out, TG_OP_XCLIP, R_.xclip);
+  // tg_ops_push word by word, with the word under construction in a register: the stored task operations are already
+  // run-length encoded, so runs only merge at the two junctions, and re-reading the previous word from memory for every
+  // push made this the hottest spot of post (28 % of its instructions, profiles/r1_prep_post_hot_lines.txt)
+  uint32_t* w = out.w;
+  uint32_t n = out.n, cur = 0;
+  bool have = false;
+  if (n > 0) { cur = w[--n]; have = true; }
+  auto push = [&](uint32_t kind, uint32_t run) {
+    if (run == 0 && kind <= TG_OP_INS) return;
+    if (have && kind <= TG_OP_INS && (cur & 7u) == kind) { cur += run << 3; return; }
+    if (have) w[n++] = cur;
+    cur = kind | (run << 3);
+    have = true;
+  };
+  if (L_.xclip) push(TG_OP_XCLIP, L_.xclip);
+  for (uint32_t i = 0; i < L_.ops_n; i++) { const uint32_t v = pool[L_.ops_off + i]; push(v & 7u, v >> 3); }
+  push(TG_OP_MATCH, len);
+  for (uint32_t i = R_.ops_n; i-- > 0;) { const uint32_t v = pool[R_.ops_off + i]; push(v & 7u, v >> 3); }
+  if (R_.xclip) push(TG_OP_XCLIP, R_.xclip);
+  if (have) w[n++] = cur;
+  out.n = n;
 }
 
 struct TgHopsPool {  // operations of the evaluated hits (append-only within a batch of reads)

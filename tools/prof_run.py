@@ -10,7 +10,7 @@ from thermite_b200 import AlignOpts, Aligner, Index  # noqa: E402
 scale, n = float(sys.argv[1]), int(sys.argv[2])
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 contigs, gtf, txs, fa = bench.make_world(scale)
-ix = Index.create_from_memory(fa, gtf)
+ix = Index.create_from_memory(fa, gtf, sa_device=0)
 al = Aligner(ix, AlignOpts(bench.FLAGS["k"], bench.FLAGS["pct"], bench.FLAGS["min_score"], bench.FLAGS["score_range"],
                            bench.FLAGS["intron_mode"]))
 bases, offs = bench.make_reads(contigs, txs, n, bench.SEEDS["reads"])
