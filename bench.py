@@ -214,6 +214,139 @@ def run_reference(args, rank, world):
     _RESULT_LINE.append(json.dumps(line))
 
 
+def run_multi(args):
+    """`--gpus N` in ONE process (no torchrun): the product's multi-GPU entry point.  `value` = all N contexts running
+    device-resident shards concurrently; `e2e` = tg_multi_align_batch on one read-ordered batch of N x reads in pinned host
+    memory, result merged in read order (records land in one pinned result, nothing is copied afterwards)."""
+    import threading
+    import torch
+    from thermite_b200 import AlignOpts, Index, MultiAligner
+
+    G = args.gpus
+    if not torch.cuda.is_available() or torch.cuda.device_count() < G:
+        raise SystemExit(f"bench.py --gpus {G} needs {G} CUDA devices: the product path has no CPU fallback")
+    t_setup = time.time()
+    contigs, gtf, txs, fa = make_world(args.scale)
+    t_index = time.time()
+    index = Index.create_from_memory(fa, gtf, sa_device=0)
+    index_s = time.time() - t_index
+    opts = AlignOpts(FLAGS["k"], FLAGS["pct"], FLAGS["min_score"], FLAGS["score_range"], FLAGS["intron_mode"])
+    m = MultiAligner(index, opts, devices=list(range(G)))
+    how, bcast_ms = m.replication()
+    per = args.reads
+    shards = [make_reads(contigs, txs, per, SEEDS["reads"] + 1000 * g) for g in range(G)]
+    n = per * G
+    bases = np.concatenate([b for b, _ in shards])
+    offs = np.zeros(n + 1, np.uint64)
+    pos = 0
+    for g, (b, o) in enumerate(shards):
+        offs[g * per: (g + 1) * per + 1] = o + np.uint64(pos)
+        pos += len(b)
+    h_bases = torch.from_numpy(bases).pin_memory()
+    h_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    ctxs = [m.context(g) for g in range(G)]
+    d_in = []
+    for g, (b, o) in enumerate(shards):
+        dev = torch.device("cuda", g)
+        d_in.append((torch.from_numpy(b).to(dev), torch.from_numpy(o.view(np.int64)).to(dev), int(o[-1])))
+    setup_s = time.time() - t_setup
+
+    def sync_all():
+        for g in range(G):
+            torch.cuda.synchronize(g)
+
+    acc = [dict(seed=0.0, ext=0.0, dp=0.0, launches=0, ms=0.0, res=None) for _ in range(G)]
+
+    def dev_steps(g, k, timed):
+        torch.cuda.set_device(g)
+        st = torch.cuda.ExternalStream(ctxs[g].stream_ptr(), device=torch.device("cuda", g))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(k):
+            r = ctxs[g].align_reads_device_raw(d_in[g][0].data_ptr(), d_in[g][1].data_ptr(), per, d_in[g][2], READ_LEN)
+            if timed:
+                a, b = ctxs[g].last_kernel_ms()
+                acc[g]["seed"] += a; acc[g]["ext"] += b; acc[g]["dp"] += ctxs[g].last_dp_ms()
+                acc[g]["launches"] += ctxs[g].last_kernel_launches()
+        e1.record(st)
+        torch.cuda.synchronize(g)
+        acc[g]["ms"] = e0.elapsed_time(e1)
+        acc[g]["res"] = r
+
+    def all_devices(k, timed):
+        th = [threading.Thread(target=dev_steps, args=(g, k, timed)) for g in range(G)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    all_devices(args.warmup, False)
+    m.set_exact_cell_count(True)
+    all_devices(1, False)
+    ref_cells = float(sum(a["res"].swg_cells for a in acc))
+    m.set_exact_cell_count(False)
+    all_devices(1, False)
+    sync_all()
+    sampler = ClockSampler(0)
+    all_devices(args.steps, True)
+    sync_all()
+    dev_ms = max(a["ms"] for a in acc)
+    cells = float(sum(a["res"].swg_cells for a in acc))
+    launches = sum(a["launches"] for a in acc)
+
+    for _ in range(max(1, args.warmup // 2)):
+        hres = m.align_reads_raw(h_bases.data_ptr(), h_offs.data_ptr(), n)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hres = m.align_reads_raw(h_bases.data_ptr(), h_offs.data_ptr(), n)
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    timing = m.last_timing()
+    clocks = sampler.stop()
+    h2d = int(bases.nbytes + offs.nbytes)
+    d2h = int(n * 8 + hres.n_alns * 40 + hres.n_ops * 4)
+    hbm_peak, peak_src, sm_max = peaks()
+    sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+    dp_ms = max(a["dp"] for a in acc) / args.steps
+    int_roof = G * 148 * 4 * 16 * (sm_mhz * 1e6) / 9.0 / 1e9
+    line = dict(
+        metric="reads/sec", value=n * args.steps / (dev_ms / 1e3), unit="reads/s", n_gpus=G, steps=args.steps, warmup=args.warmup,
+        ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32", data="synthetic",
+        config=dict(workload=workload_name(args.scale), reads_per_step_per_gpu=per, read_len=READ_LEN, flags="-k20 -s0 --intron-mode",
+                    parallelism=f"ONE process, tg_multi_*: {G} GPUs, one host thread + context each, contiguous read shards, "
+                                f"index replicated by {how} in {bcast_ms:.2f} ms",
+                    l2=f"inputs larger than L2: per step per GPU {per * READ_LEN / 1e6:.0f} MB of reads against several GB of index",
+                    index_bytes=int(index.blob().nbytes), index_replication=how, index_broadcast_ms=bcast_ms, setup_s=setup_s,
+                    index_create_s=round(index_s, 2)),
+        e2e=dict(value=n * args.steps / (e2e_ms / 1e3), unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                 ms_per_step=e2e_ms / args.steps,
+                 call="tg_multi_align_batch: one read-ordered batch in pinned host memory -> one result in read order "
+                      "(40-byte records, segmented pools; every GPU's copies land at their final place)",
+                 per_device_last_call=timing, segments=int(hres.n_segments)),
+        gpu_launches=int(launches),
+        roofline=dict(bound="int-pipe", kernel="k_round_dpt<0..3> on every GPU", achieved=ref_cells / (dp_ms / 1e3) / 1e9, peak=int_roof,
+                      unit="GCUPS", frac=ref_cells / (dp_ms / 1e3) / 1e9 / int_roof, traffic=None,
+                      achieved_computed_cells=cells / (dp_ms / 1e3) / 1e9, ms_per_step=dp_ms, sm_mhz=sm_mhz,
+                      peak_source=f"{G} x 148 SM x 4 SMSP x 16 lanes/clk x sm_mhz / 9 ALU-pipe instructions per cell",
+                      note="aggregate over the GPUs; DP time = the slowest GPU's summed DP sections per step"),
+        kernel_share=dict(seeding=max(a["seed"] for a in acc) / dev_ms, extension_total=max(a["ext"] for a in acc) / dev_ms,
+                          swg_dp=max(a["dp"] for a in acc) / dev_ms),
+        clocks=clocks,
+    )
+    if not args.no_cpu_baseline:
+        cb, (n_cpu, orc_res) = cpu_baseline(fa, gtf, bases, offs, args.cpu_seconds, os.cpu_count() or 1)
+        line["cpu_baseline"] = cb
+        # parity of the MERGED multi-GPU result, in read order, on a batch that is itself cut into N shards
+        gres = m.align_reads(bases[: int(offs[n_cpu])], offs[: n_cpu + 1])
+        line["parity_vs_oracle"] = dict(parity_vs_oracle(gres, orc_res, n_cpu), shards=G,
+                                        what="tg_multi_align_batch over the first reads of the batch, cut into one shard per GPU")
+    else:
+        line["cpu_baseline"] = None
+    _RESULT_LINE.append(json.dumps(line))
+    m.close()
+
+
 def main():
     args = parse_args()
     # exactly ONE line on stdout (the JSON): libraries that print there (NCCL's version banner) go to stderr instead
@@ -239,6 +372,9 @@ def _main(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        run_multi(args)
         return
 
     import torch
@@ -303,7 +439,10 @@ def _main(args):
     def step_device():
         return aligner.align_reads_device_raw(d_bases.data_ptr(), d_offs.data_ptr(), n, int(offs[n]), READ_LEN)
 
-    def step_host():
+    def step_host():  # the call the Rust shim makes: compact records (tg_aln_c), host buffers in and out
+        return aligner.align_reads_compact_raw(h_bases.data_ptr(), h_offs.data_ptr(), n)
+
+    def step_host_wide():  # the same with 104-byte records (tg_align_batch)
         return aligner.align_reads_raw(h_bases.data_ptr(), h_offs.data_ptr(), n)
 
     # ---- value: device-resident ------------------------------------------------------------------------------------
@@ -350,15 +489,25 @@ def _main(args):
     e2e_ms = max(ev2.elapsed_time(ev3), e2e_wall_ms)  # the call is host-synchronous: wall clock bounds it from above
     clocks = sampler.stop() if sampler else None
     h2d = int(bases.nbytes + offs.nbytes)
-    d2h = int(n * 12 + hres.n_alns * 104 + hres.n_ops * 4)
+    d2h = int(n * 8 + hres.n_alns * 40 + hres.n_ops * 4)
+    # the wide-record call (104-byte tg_aln, u64 firsts) for comparison: a few steps, not the headline
+    wide_steps = max(2, args.steps // 4)
+    step_host_wide()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(wide_steps):
+        wres = step_host_wide()
+    barrier()
+    wide_ms = (time.perf_counter() - t0) * 1e3 / wide_steps
+    d2h_wide = int(n * 12 + wres.n_alns * 104 + wres.n_ops * 4)
 
-    t = torch.tensor([dev_ms, e2e_ms, seed_ms, ext_ms, dp_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, seed_ms, ext_ms, dp_ms, wide_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([counters["swg_cells"], counters["seed_hits"], counters["n_alns"], counters["n_ops"], counters["n_smems"],
                         counters["swg_extensions"], ref_cells, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, seed_ms, ext_ms, dp_ms = [float(x) for x in t.tolist()]
+    dev_ms, e2e_ms, seed_ms, ext_ms, dp_ms, wide_ms = [float(x) for x in t.tolist()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -398,7 +547,10 @@ def _main(args):
                     index_bytes=int(index.blob().nbytes), kmer_table_bytes=int(aligner.kmer_table_bytes()),
                     index_broadcast_ms=bcast_ms, setup_s=setup_s, index_create_s=round(index_s, 2),
                     index_suffix_array="gpu (tg_index_host_create_from_memory_gpu)"),
-        e2e=dict(value=e2e_value, unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),
+        e2e=dict(value=e2e_value, unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps,
+                 call="tg_align_batch_compact: pinned host buffers in, 40-byte records (tg_aln_c) + operations + per-read first/count out",
+                 wide_records=dict(value=n * world / (wide_ms / 1e3), ms_per_step=wide_ms, d2h_bytes_per_step=d2h_wide,
+                                   call="tg_align_batch: 104-byte records (tg_aln)")),
         gpu_launches=int(launches),
         roofline=dict(bound="int-pipe", kernel="k_round_dpt<0..3> (banded SWG, thread per extension)", achieved=gcups_ref,
                       peak=int_roof, unit="GCUPS", frac=gcups_ref / int_roof, traffic=(traffic.get("k_round_dpt") or {}).get("bytes"),

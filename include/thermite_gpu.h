@@ -210,6 +210,77 @@ tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint6
                                 uint64_t total_bases, uint32_t max_read_len, tg_result* out);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Compact results.  tg_aln spends 104 B on a record; 64 of them repeat what the caller already holds (ylen = length of
+ * refs()[ref_id], tx_ylen = length of txome().txs[tx_idx], xlen = the read's length, strand = refs()[ref_id].strand) or
+ * what the record says twice (tx_score / tx_xstart / tx_xend equal score / xstart / xend of an Exonic record, and the
+ * transcript operations follow the genome operations directly).  tg_aln_c is the same GenomeAlignment
+ * (src/txome.rs:55-69) in 40 B; tg_aln_expand gives back the wide form bit for bit.  The compact calls move 70 B per
+ * read to the host instead of 141 B, which is what bounds the end-to-end rate when 8 GPUs share one host.
+ * Limits: reads <= TG_MAX_READ_LEN (16-bit read coordinates and score), chromosomes < 2^32 bp.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tg_aln_c {
+  uint32_t ystart, yend;          /* gx_aln: chromosome coordinates, forward-strand orientation */
+  uint32_t tx_ystart, tx_yend;    /* Exonic only: tx_aln in transcript coordinates */
+  uint32_t ref_id;                /* index into refs() => ref_name, strand, ylen */
+  uint32_t tx_or_gene_idx;        /* Exonic: tx_idx; Intronic: gene_idx; Intergenic: 0xFFFFFFFF */
+  uint32_t ops_off;               /* gx_aln.operations = ops[ops_off, ops_off + ops_len); tx_aln.operations = the tx_ops_len words behind them */
+  int16_t score;
+  uint16_t xstart, xend;          /* read coordinates */
+  uint16_t ops_len, tx_ops_len;
+  uint8_t aln_type;               /* TG_ALN_* */
+  uint8_t primary;
+} tg_aln_c;
+
+/* Like tg_result with compact records.  The pools are SEGMENTED: tg_align_batch_compact fills one segment,
+ * tg_multi_align_batch one per GPU (every GPU's copies land at their final place, nothing is merged afterwards), so
+ * alns / ops may hold unused gaps between segments: n_alns / n_ops count what is in use, *_extent is one past the last
+ * used element.  Read r owns alns[read_aln_first[r] .. + read_aln_count[r]) in output order, r in the caller's order. */
+typedef struct tg_result_c {
+  uint32_t n_reads;
+  uint32_t n_segments;
+  uint64_t n_alns, n_ops;
+  uint64_t alns_extent, ops_extent;
+  const uint32_t* read_aln_first; /* [n_reads] */
+  const uint32_t* read_aln_count; /* [n_reads] */
+  const tg_aln_c* alns;           /* [alns_extent] */
+  const uint32_t* ops;            /* [ops_extent] */
+  uint64_t swg_cells, swg_extensions, seed_hits, n_smems;  /* as in tg_result */
+} tg_result_c;
+
+/* tg_align_batch with compact records (HOST buffers in, HOST result out, owned by ctx until the next call). */
+tg_status tg_align_batch_compact(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_result_c* out);
+/* One compact record -> the wide record.  read_len = length of the read the record belongs to.  The wide record's
+ * ops_off / tx_ops_off index the same `ops` array. */
+tg_status tg_aln_expand(const tg_index_host* ix, const tg_aln_c* c, uint32_t read_len, tg_aln* out);
+/* All records of a compact result -> wide records (alns_out[i] for i < alns_extent; gaps are zeroed) and u64 firsts
+ * (first_out[n_reads], may be NULL), on n_threads host threads (0 = all cores).  offs = the offsets given to the align call. */
+tg_status tg_result_expand(const tg_index_host* ix, const tg_result_c* res, const uint64_t* offs, tg_aln* alns_out,
+                           uint64_t* first_out, int n_threads);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Several GPUs of one host behind one call: the reference's driver is one process that writes its output in read order
+ * (src/main.rs:45-83 -> src/aligner.rs:22-120, serial loop :54-115).  A tg_multi holds one index replica, one context and
+ * one host thread per device.  tg_multi_create uploads the index to devices[0] and replicates it to the other GPUs with
+ * ONE NCCL broadcast over NVLink (libnccl.so.2 is loaded at run time; without it: peer-to-peer copies) -- the only
+ * collective on the path.  tg_multi_align_batch cuts the batch into contiguous shards [g*N/G, (g+1)*N/G),
+ * runs them concurrently and returns ONE result in the caller's read order.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tg_multi tg_multi;
+tg_status tg_multi_create(const tg_index_host* ix, const int* devices, int n_devices, const tg_opts* opts, tg_multi** out);
+void tg_multi_destroy(tg_multi* m);
+int tg_multi_n_devices(const tg_multi* m);
+/* "nccl" or "peer-copy": how the index replicas were made; *ms = device time of the broadcast (may be NULL). */
+const char* tg_multi_replication(const tg_multi* m, float* ms);
+/* Context of device slot g (e.g. for tg_ctx_set_exact_cell_count); NULL when g is out of range. */
+tg_ctx* tg_multi_ctx(tg_multi* m, int g);
+/* HOST buffers in, HOST result out (owned by m until the next call).  Records are identical to tg_align_batch_compact's
+ * over the whole batch on one GPU. */
+tg_status tg_multi_align_batch(tg_multi* m, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_result_c* out);
+/* Timing of the last tg_multi_align_batch for device slot g: host wall time of the shard's call and the device times
+ * tg_ctx_last_kernel_ms / tg_ctx_last_dp_ms report (any pointer may be NULL). */
+tg_status tg_multi_last_timing(const tg_multi* m, int g, double* wall_ms, float* seed_ms, float* extend_ms, float* dp_ms);
+
+/* ---------------------------------------------------------------------------------------------------
  * Per-read calls from many host threads: ThermiteAligner::align_read (src/wrapper.rs:20-27, :72).
  * The reference's embedding callers hold one clone per worker thread and align one read per call.  A tg_batcher lets
  * any number of threads do that against ONE context: reads are queued and a dispatcher thread runs tg_align_batch as

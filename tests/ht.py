@@ -96,10 +96,14 @@ class HostCtx:
         assert tot >= 0
         return pool[:tot], first, count
 
-    def align_batch(self, bases, offs, lanes=1, bound_stop=False, rounds=False):
+    def align_batch(self, bases, offs, lanes=1, bound_stop=False, rounds=False, compact=None):
+        """compact=(first_base, ops_base): write tg_aln_c records rebased like one shard of tg_multi_align_batch and expand
+        them back with tg_aln_expand."""
         bases = np.ascontiguousarray(bases, np.uint8)
         offs = np.ascontiguousarray(offs, np.uint64)
         n = len(offs) - 1
+        if compact is not None:
+            lib().ht_set_compact(1, C.c_uint64(compact[0]), C.c_uint64(compact[1]))
         r = lib().ht_align_batch_mode(self.h, _p(bases), _p(offs), n, lanes, int(bound_stop), int(rounds))
         assert r
         r = C.c_void_p(r)

@@ -149,6 +149,49 @@ def test_device_entry_points_fail_loudly_without_gpu():
         tb.suffix_array_gpu(ix.text4(), ix.text_len(), 0)
     with pytest.raises(tb.ThermiteError, match="no CPU fallback"):
         tb.Index.create_from_memory(golden("test_ref.fasta"), golden("test_ref.gtf"), sa_device=0)
+    with pytest.raises(tb.ThermiteError, match="no CPU fallback"):
+        tb.MultiAligner(ix, devices=[0, 1])
+
+
+def test_compact_record_layout_and_host_side_expansion():
+    """tg_aln_c is 40 bytes and tg_aln_expand / tg_result_expand (host functions) rebuild the wide record bit for bit:
+    oracle records -> compact (what the device writes) -> expanded == oracle records."""
+    assert api.ALN_C_DTYPE.itemsize == 40
+    fa, gtf, fq = golden("test_ref.fasta"), golden("test_ref.gtf"), golden("test_query.fastq")
+    bases, offs, *_ = tb.parse_fastq(fq)
+    ores = orc.Index.create(fa, gtf).align_batch(bases, offs, k=3, min_score=0, intron_mode=True)
+    ix = tb.Index.create_from_memory(fa, gtf)
+    n = len(offs) - 1
+    w = ores.alns
+    assert len(w) > 5 and (w["aln_type"] == 0).any() and (w["aln_type"] != 0).any()
+    # the oracle lays transcript operations right behind the genome operations, like the device's output pools
+    ex = w["aln_type"] == 0
+    assert (w["tx_ops_off"][ex] == w["ops_off"][ex] + w["ops_len"][ex]).all()
+    gap = 3  # a gap in front of the pool, as between two segments of a multi-GPU result
+    c = np.zeros(len(w) + gap, api.ALN_C_DTYPE)
+    for f in ("ystart", "yend", "tx_ystart", "tx_yend", "ref_id", "tx_or_gene_idx", "ops_off", "score", "xstart", "xend",
+              "ops_len", "tx_ops_len", "aln_type", "primary"):
+        c[f][gap:] = w[f]
+    first = (ores.read_off[:-1] + gap).astype(np.uint32)
+    count = (ores.read_off[1:] - ores.read_off[:-1]).astype(np.uint32)
+    ops = np.ascontiguousarray(ores.ops)
+    res = api._ResultC(n, 2, len(w), len(ops), len(c), len(ops), first.ctypes.data, count.ctypes.data, c.ctypes.data,
+                       ops.ctypes.data, 0, 0, 0, 0)
+    out = api.expand_result(ix, res, offs)
+    assert (out.first == first).all() and (out.alns[:gap].view(np.uint8) == 0).all()
+    got = out.alns[gap:]
+    for f in api.ALN_DTYPE.names:
+        if f == "tx_ops_off":
+            assert (got[f][ex] == w[f][ex]).all() and (got[f][~ex] == 0).all()
+        else:
+            assert (got[f] == w[f]).all(), f
+    one = np.zeros(1, api.ALN_DTYPE)
+    assert tb.lib().tg_aln_expand(ix._h, c[gap:].ctypes.data_as(C.c_void_p), C.c_uint32(int(offs[1] - offs[0])),
+                                  one.ctypes.data_as(C.c_void_p)) == 0
+    assert one[0]["ylen"] == w[0]["ylen"] and one[0]["strand"] == w[0]["strand"] and one[0]["xlen"] == offs[1] - offs[0]
+    c["ref_id"][gap] = 99  # a record of another index: refused, not read out of bounds
+    with pytest.raises(tb.ThermiteError):
+        api.expand_result(ix, res, offs)
 
 
 def test_text4_is_the_packed_both_strand_text():

@@ -77,6 +77,10 @@ def test_align_records_equal_oracle_random_worlds(seed):
             assert not d, (mode, d[:3])
             assert resr["flags"] == 0 and resr["hits"] == res["hits"] and resr["n_ext"] == res["n_ext"]
             assert resr["cells"] == (resb["cells"] if bs else res["cells"]), mode
+    # compact records (tg_aln_c) rebased like a shard of tg_multi_align_batch, expanded back by tg_aln_expand: both writers
+    for mode in (0, 1):
+        resc = ctx.align_batch(bases, offs, lanes=1, bound_stop=True, rounds=mode, compact=(1000 * seed + 7, 5000 * seed + 3))
+        assert resc["flags"] == 0 and not ht.compare_alignments(resc, ores, n), mode
     # the 32-lane wavefront (what the GPU executes) on a slice
     m = 12
     for bs in (False, True):

@@ -35,6 +35,13 @@ ALN_DTYPE = np.dtype([
     ("ops_off", "<u4"), ("ops_len", "<u4"), ("tx_ops_off", "<u4"), ("tx_ops_len", "<u4"),
     ("aln_type", "u1"), ("primary", "u1"), ("strand", "u1"), ("pad", "u1"),
 ])
+# tg_aln_c (40 B): the same record without what refs() / txome() / the read already say
+ALN_C_DTYPE = np.dtype([
+    ("ystart", "<u4"), ("yend", "<u4"), ("tx_ystart", "<u4"), ("tx_yend", "<u4"),
+    ("ref_id", "<u4"), ("tx_or_gene_idx", "<u4"), ("ops_off", "<u4"),
+    ("score", "<i2"), ("xstart", "<u2"), ("xend", "<u2"), ("ops_len", "<u2"), ("tx_ops_len", "<u2"),
+    ("aln_type", "u1"), ("primary", "u1"),
+])
 SEED_DTYPE = np.dtype([("query_idx", "<u4"), ("len", "<u4"), ("sa_lo", "<u4"), ("count", "<u4"),
                        ("direct", "<u4"), ("pad", "<u4")])
 OP_NAMES = ["Match", "Subst", "Del", "Ins", "Xclip", "Yclip"]
@@ -52,6 +59,14 @@ class _Opts(C.Structure):
 
 class _Result(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_alns", C.c_uint64), ("n_ops", C.c_uint64),
+                ("read_aln_first", C.c_void_p), ("read_aln_count", C.c_void_p), ("alns", C.c_void_p),
+                ("ops", C.c_void_p), ("swg_cells", C.c_uint64), ("swg_extensions", C.c_uint64),
+                ("seed_hits", C.c_uint64), ("n_smems", C.c_uint64)]
+
+
+class _ResultC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_segments", C.c_uint32), ("n_alns", C.c_uint64), ("n_ops", C.c_uint64),
+                ("alns_extent", C.c_uint64), ("ops_extent", C.c_uint64),
                 ("read_aln_first", C.c_void_p), ("read_aln_count", C.c_void_p), ("alns", C.c_void_p),
                 ("ops", C.c_void_p), ("swg_cells", C.c_uint64), ("swg_extensions", C.c_uint64),
                 ("seed_hits", C.c_uint64), ("n_smems", C.c_uint64)]
@@ -77,6 +92,9 @@ ABI_SYMBOLS = [
     "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_set_chunk_reads", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_bench_random_gather", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
     "tg_align_batch", "tg_align_batch_device", "tg_seed_batch", "tg_swg_extend_batch",
     "tg_format_sam_header", "tg_format_batch", "tg_parse_fastq", "tg_free",
+    "tg_align_batch_compact", "tg_aln_expand", "tg_result_expand",
+    "tg_multi_create", "tg_multi_destroy", "tg_multi_n_devices", "tg_multi_replication", "tg_multi_ctx",
+    "tg_multi_align_batch", "tg_multi_last_timing",
 ]
 
 
@@ -106,6 +124,9 @@ def lib():
         L.tg_ctx_set_round_pipeline.restype = None
         L.tg_ctx_set_chunk_reads.restype = None
         L.tg_free.restype = None
+        L.tg_multi_destroy.restype = None
+        L.tg_multi_replication.restype = C.c_char_p
+        L.tg_multi_ctx.restype = C.c_void_p
         _LIB = L
     return _LIB
 
@@ -379,9 +400,17 @@ class Aligner:
 
     def __del__(self):
         try:
-            lib().tg_ctx_destroy(self._h)
+            if getattr(self, "_owned", True):
+                lib().tg_ctx_destroy(self._h)
         except Exception:
             pass
+
+    @classmethod
+    def _view(cls, handle, index, opts, device, ref_names):
+        """An Aligner over a context somebody else owns (MultiAligner.context)."""
+        a = cls.__new__(cls)
+        a._h, a.index, a.opts, a.device, a._ref_names, a._owned = C.c_void_p(handle), index, opts, device, ref_names, False
+        return a
 
     def stream_ptr(self) -> int:
         return lib().tg_ctx_stream(self._h)
@@ -455,6 +484,20 @@ class Aligner:
             C.memmove(ops.ctypes.data, res.ops, res.n_ops * 4)
         return AlignResult(first, count, alns, ops, self._counters(res), self._ref_names)
 
+    def align_reads_compact_raw(self, bases_ptr: int, offs_ptr: int, n_reads: int) -> _ResultC:
+        """tg_align_batch_compact on raw HOST pointers: 40-byte records (tg_aln_c), u32 first indices."""
+        res = _ResultC()
+        _check(lib().tg_align_batch_compact(self._h, C.c_void_p(bases_ptr), C.c_void_p(offs_ptr), n_reads, C.byref(res)))
+        return res
+
+    def align_reads_compact(self, bases, offs) -> "AlignResult":
+        """align_reads through the compact call; the records are expanded back to the wide form (tg_result_expand)."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offs = np.ascontiguousarray(offs, np.uint64)
+        n = len(offs) - 1
+        res = self.align_reads_compact_raw(bases.ctypes.data, offs.ctypes.data, n)
+        return expand_result(self.index, res, offs, self._ref_names)
+
     def align_read(self, read: bytes) -> List[GenomeAlignment]:
         """align_read for one read (src/aligner.rs:123)."""
         b = np.frombuffer(read, np.uint8)
@@ -525,6 +568,94 @@ class Aligner:
         s = C.string_at(out, n.value)
         lib().tg_free(out)
         return s
+
+
+def compact_arrays(res: _ResultC):
+    """Zero-copy numpy views of a compact result (valid until the next call on its context / tg_multi)."""
+    n = res.n_reads
+    first = np.ctypeslib.as_array(C.cast(res.read_aln_first, C.POINTER(C.c_uint32)), shape=(n,)) if n else np.zeros(0, np.uint32)
+    count = np.ctypeslib.as_array(C.cast(res.read_aln_count, C.POINTER(C.c_uint32)), shape=(n,)) if n else np.zeros(0, np.uint32)
+    na, no = int(res.alns_extent), int(res.ops_extent)
+    alns = (np.ctypeslib.as_array(C.cast(res.alns, C.POINTER(C.c_uint8)), shape=(na * ALN_C_DTYPE.itemsize,)).view(ALN_C_DTYPE)
+            if na else np.zeros(0, ALN_C_DTYPE))
+    ops = np.ctypeslib.as_array(C.cast(res.ops, C.POINTER(C.c_uint32)), shape=(no,)) if no else np.zeros(0, np.uint32)
+    return first, count, alns, ops
+
+
+def expand_result(index: "Index", res: _ResultC, offs, ref_names=None, n_threads: int = 0) -> "AlignResult":
+    """tg_result_expand: compact records -> AlignResult with wide records (host copies)."""
+    offs = np.ascontiguousarray(offs, np.uint64)
+    n = res.n_reads
+    alns = np.zeros(int(res.alns_extent), ALN_DTYPE)
+    first = np.zeros(n, np.uint64)
+    if n:
+        _check(lib().tg_result_expand(index._h, C.byref(res), _p(offs), _p(alns), _p(first), n_threads))
+    _, count, _, ops = compact_arrays(res)
+    counters = dict(swg_cells=res.swg_cells, swg_extensions=res.swg_extensions, seed_hits=res.seed_hits,
+                    n_smems=res.n_smems, n_alns=res.n_alns, n_ops=res.n_ops, n_segments=res.n_segments)
+    return AlignResult(first, count.copy(), alns, ops.copy(), counters, ref_names)
+
+
+class MultiAligner:
+    """Several GPUs of one host behind one call (tg_multi_*): the index is replicated with one NCCL broadcast, a batch is
+    cut into contiguous shards, one per GPU, and comes back as ONE result in read order -- the reference's serial output
+    order (src/aligner.rs:54-115).  `devices` may list a GPU more than once (two contexts on one GPU)."""
+
+    def __init__(self, index: Index, opts: AlignOpts = None, devices=(0,)):
+        self.index = index
+        self.opts = opts or AlignOpts()
+        self.devices = list(devices)
+        h = C.c_void_p()
+        o = self.opts._c()
+        dv = (C.c_int * len(self.devices))(*self.devices)
+        _check(lib().tg_multi_create(index._h, dv, len(self.devices), C.byref(o), C.byref(h)))
+        self._h = h
+        self._ref_names = [r.name for r in index.refs()]
+
+    def close(self):
+        if self._h:
+            lib().tg_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def replication(self):
+        """("nccl" | "peer-copy" | "single", milliseconds)"""
+        ms = C.c_float()
+        how = lib().tg_multi_replication(self._h, C.byref(ms)).decode()
+        return how, ms.value
+
+    def context(self, g: int) -> "Aligner":
+        """The context of device slot g as an Aligner (owned by this object; not to be used while align_reads runs)."""
+        return Aligner._view(lib().tg_multi_ctx(self._h, g), self.index, self.opts, self.devices[g], self._ref_names)
+
+    def set_exact_cell_count(self, on: bool):
+        for g in range(len(self.devices)):
+            self.context(g).set_exact_cell_count(on)
+
+    def align_reads_raw(self, bases_ptr: int, offs_ptr: int, n_reads: int) -> _ResultC:
+        res = _ResultC()
+        _check(lib().tg_multi_align_batch(self._h, C.c_void_p(bases_ptr), C.c_void_p(offs_ptr), n_reads, C.byref(res)))
+        return res
+
+    def align_reads(self, bases, offs) -> "AlignResult":
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offs = np.ascontiguousarray(offs, np.uint64)
+        res = self.align_reads_raw(bases.ctypes.data, offs.ctypes.data, len(offs) - 1)
+        return expand_result(self.index, res, offs, self._ref_names)
+
+    def last_timing(self):
+        """Per device slot: dict(wall_ms, seed_ms, extend_ms, dp_ms) of the last call."""
+        out = []
+        for g in range(len(self.devices)):
+            w, a, b, d = C.c_double(), C.c_float(), C.c_float(), C.c_float()
+            _check(lib().tg_multi_last_timing(self._h, g, C.byref(w), C.byref(a), C.byref(b), C.byref(d)))
+            out.append(dict(wall_ms=w.value, seed_ms=a.value, extend_ms=b.value, dp_ms=d.value))
+        return out
 
 
 class OutputFormat:

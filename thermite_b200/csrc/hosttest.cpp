@@ -346,6 +346,14 @@ struct HtResult {
   unsigned long long items = 0, rounds = 0;  // round pipeline: evaluated (read, hit) items incl. discarded ones
 };
 
+// compact-record mode of the NEXT ht_align_batch_mode call: records are written as tg_aln_c with the first indices /
+// operation offsets rebased by (first_base, ops_base) -- what one shard of tg_multi_align_batch does on the device -- and
+// expanded back with tg_aln_expand before the result is handed out
+static bool g_ht_compact = false;
+static unsigned long long g_ht_first_base = 0, g_ht_ops_base = 0;
+void ht_set_compact(int on, unsigned long long first_base, unsigned long long ops_base) {
+  g_ht_compact = on != 0; g_ht_first_base = first_base; g_ht_ops_base = ops_base;
+}
 void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes, int bound_stop, int rounds);
 void* ht_align_batch(void* cp, const uint8_t* bases, const uint64_t* offs, uint32_t n, int lanes, int bound_stop) {
   return ht_align_batch_mode(cp, bases, offs, n, lanes, bound_stop, 0);
@@ -375,6 +383,11 @@ void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, 
   TgAlignParams P{c->dev, c->opts};
   TgAlignOut out{res->first.data(), res->count.data(), res->alns.data(), res->ops.data(), &res->n_alns, &res->n_ops,
                  res->alns.size(), res->ops.size(), &res->flags};
+  const bool compact = g_ht_compact;
+  std::vector<tg_aln_c> calns(compact ? res->alns.size() : 0);
+  std::vector<uint32_t> cfirst(compact ? n : 0);
+  if (compact) { out.alns_c = calns.data(); out.first32 = cfirst.data(); out.first_base = g_ht_first_base; out.ops_base = g_ht_ops_base; }
+  g_ht_compact = false;
   std::vector<uint8_t> done(n, 0);
   HostWarp1 w1;
   if (rounds) {
@@ -488,6 +501,16 @@ void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, 
       tg_align_read(w, wm, P, bases, offs[r], L, pool1.data() + sfirst1[0], scount1[0], sc, out, r, lane_ctr[w.lane()]);
     });
     for (auto& lc : lane_ctr) { res->ctr.cells += lc.cells; res->ctr.n_ext += lc.n_ext; res->ctr.hits += lc.hits; }
+  }
+  if (compact) {  // back to wide records, bases removed
+    for (uint32_t r = 0; r < n; r++) {
+      res->first[r] = cfirst[r] - out.first_base;
+      for (uint32_t i = 0; i < res->count[r]; i++) {
+        tg_aln_c cc = calns[res->first[r] + i];
+        cc.ops_off -= (uint32_t)out.ops_base;
+        if (tg_aln_expand(c->ix, &cc, (uint32_t)(offs[r + 1] - offs[r]), &res->alns[res->first[r] + i]) != TG_OK) res->flags |= 1 << 30;
+      }
+    }
   }
   return res;
 }

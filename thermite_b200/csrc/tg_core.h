@@ -1221,7 +1221,11 @@ TG_HD uint32_t tg_kmer_group_count(const uint64_t* text4, uint64_t text_len, con
 // ------------------------------------------------------------------------------------------------
 // Read-level drivers.  W adds: atomic_add(unsigned long long*, v) and atomic_or(int*, v).
 // ------------------------------------------------------------------------------------------------
-enum { TG_FLAG_SEED_POOL = 1, TG_FLAG_ALN_POOL = 2, TG_FLAG_OPS_POOL = 4, TG_FLAG_READ_CAP = 8, TG_FLAG_ARENA = 16 };
+enum { TG_FLAG_SEED_POOL = 1, TG_FLAG_ALN_POOL = 2, TG_FLAG_OPS_POOL = 4, TG_FLAG_READ_CAP = 8, TG_FLAG_ARENA = 16,
+       // an alignment whose own start lies on another Ref than its hit (concat_to_chr_aln keys ylen on the alignment,
+       // ref_name / strand on the hit): cannot happen -- windows are clamped to the hit's Ref and a transcript's exons lie on
+       // one Ref -- and the compact record (tg_aln_c) relies on it; checked so that it would fail loudly
+       TG_FLAG_YLEN = 256 };
 
 struct TgSeedMem {  // per-warp scratch of the seeding stage
   uint64_t* rp;       // packed read, (maxL/16 + 3) words
@@ -1353,7 +1357,35 @@ struct TgAlignOut {
   unsigned long long* ops_used;
   unsigned long long alns_cap, ops_cap;
   int* flags;
+  // compact output (tg_aln_c, include/thermite_gpu.h): when alns_c is set, records go there instead of `alns` and the
+  // per-read first index to first32; first_base / ops_base = where this pool segment starts in the caller's result
+  // (tg_multi_align_batch: one segment per GPU), added to every first index and operation offset written
+  tg_aln_c* alns_c = nullptr;
+  uint32_t* first32 = nullptr;
+  unsigned long long first_base = 0, ops_base = 0;
 };
+// the GenomeAlignment record `a` (ops_off = position in out.ops, transcript operations directly behind) as record
+// `idx` of the output pool
+TG_HD void tg_out_write_aln(const TgAlignOut& out, unsigned long long idx, const tg_aln& a) {
+  if (out.alns_c) {
+    tg_aln_c c;
+    c.ystart = (uint32_t)a.ystart; c.yend = (uint32_t)a.yend;
+    c.tx_ystart = (uint32_t)a.tx_ystart; c.tx_yend = (uint32_t)a.tx_yend;
+    c.ref_id = a.ref_id; c.tx_or_gene_idx = a.tx_or_gene_idx;
+    c.ops_off = a.ops_off + (uint32_t)out.ops_base;
+    c.score = (int16_t)a.score; c.xstart = (uint16_t)a.xstart; c.xend = (uint16_t)a.xend;
+    c.ops_len = (uint16_t)a.ops_len; c.tx_ops_len = (uint16_t)a.tx_ops_len;
+    c.aln_type = a.aln_type; c.primary = a.primary;
+    out.alns_c[idx] = c;
+  } else {
+    out.alns[idx] = a;
+  }
+}
+TG_HD void tg_out_write_read(const TgAlignOut& out, uint32_t r, unsigned long long first, uint32_t count) {
+  if (out.first32) out.first32[r] = (uint32_t)(first + out.first_base);
+  else out.read_aln_first[r] = first;
+  out.read_aln_count[r] = count;
+}
 
 // align_read (src/aligner.rs:123-190) for one read, seeds already ordered as Index::all_smems orders them.
 template <class W, int RMAX = 16>
@@ -1394,6 +1426,7 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
       TgOps gx_ops{nullptr, 0}, tx_ops{nullptr, 0};
       tg_align_seed_hit<W, RMAX>(w, m, P, L, ref_idx, sd.query_idx, sd.len, bw, (int32_t)x_drop, c, gx_ops, tx_ops, ctr);
       TG_T0();
+      if (lane == 0 && c.a.ylen != P.ix.refs[c.a.ref_id].len) w.atomic_or(out.flags, TG_FLAG_YLEN);
       if (!P.opts.intron_mode && c.a.aln_type != TG_ALN_EXONIC) continue;  // :146-151
       int32_t s = c.a.score;
       if (s < P.opts.min_aln_score || s < min_aln_score || s < max_aln_score - range) continue;  // :154-159
@@ -1462,7 +1495,7 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
   abase = w.shfl64(abase, 0);
   obase = w.shfl64(obase, 0);
   w.sync();
-  if (abase + (unsigned long long)k > out.alns_cap || obase + words > out.ops_cap || obase + words > 0xFFFFFFFFull) {
+  if (abase + (unsigned long long)k > out.alns_cap || obase + words > out.ops_cap || obase + words + out.ops_base > 0xFFFFFFFFull) {
     if (lane == 0) w.atomic_or(out.flags, abase + (unsigned long long)k > out.alns_cap ? TG_FLAG_ALN_POOL : TG_FLAG_OPS_POOL);
     k = 0;
   }
@@ -1477,14 +1510,11 @@ TG_HDN void tg_align_read(W& w, TgWarpMem& m, const TgAlignParams& P, const uint
       a.tx_ops_off = (uint32_t)(o + n1);
       if (a.aln_type != TG_ALN_EXONIC) { a.tx_ops_off = 0; a.tx_ops_len = 0; }
       a.primary = i == 0 ? 1 : 0;
-      out.alns[abase + i] = a;
+      tg_out_write_aln(out, abase + i, a);
     }
     o += n1 + n2;
   }
-  if (lane == 0) {
-    out.read_aln_first[r] = abase;
-    out.read_aln_count[r] = (uint32_t)k;
-  }
+  if (lane == 0) tg_out_write_read(out, r, abase, (uint32_t)k);
   w.sync();
   TG_T(ctr, 10);
 }

@@ -94,6 +94,34 @@ struct tg_index_host {
 void tg_set_error(const std::string& msg);
 tg_status tg_fail(tg_status code, const std::string& msg);
 
+// Nothing throws across the C ABI: every extern "C" entry point that can allocate or start threads runs inside these.
+#define TG_GUARD_BEGIN try {
+#define TG_GUARD_END                                                             \
+  }                                                                              \
+  catch (const std::exception& e) { return tg_fail(TG_ERR_INTERNAL, e.what()); } \
+  catch (...) { return tg_fail(TG_ERR_INTERNAL, "unknown exception"); }
+
+// thermite_gpu.cu, used by tg_multi.cpp: one shard of a multi-GPU batch on one context.  The records (compact) go straight
+// into the caller's pinned result segment; first indices / operation offsets are rebased on the device.
+struct TgHostSegment {
+  uint32_t* first;        // [n] of the shard
+  uint32_t* count;        // [n]
+  tg_aln_c* alns;         // segment start
+  uint32_t* ops;          // segment start
+  size_t alns_cap, ops_cap;                    // segment capacity in elements
+  unsigned long long first_base, ops_base;     // index of the segment start inside the whole result's pools
+};
+struct TgShardStat {
+  bool overflow;                     // the segment was too small: need_* hold what the shard needs, nothing else is valid
+  uint64_t n_alns, n_ops, need_alns, need_ops;
+  uint64_t swg_cells, swg_extensions, seed_hits, n_smems;
+  double wall_ms;
+  float seed_ms, extend_ms, dp_ms;
+};
+tg_status tg_ctx_align_segment(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads,
+                               const TgHostSegment& seg, TgShardStat* stat);
+int tg_ctx_device(const tg_ctx* ctx);
+
 // host_batcher.cpp: the micro-batcher over any batch aligner (tg_align_batch in the product; a stand-in in the host test)
 typedef tg_status (*tg_batch_backend_fn)(void* user, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads,
                                          tg_result* out);

@@ -39,7 +39,7 @@
 
 enum { TG_RS_DONE = 0, TG_RS_ACTIVE = 1, TG_RS_COMPLEX = 2, TG_RS_FINAL = 3 /* records already written */ };
 enum { TG_IF_KEEP = 1, TG_IF_FAIL = 2 };
-enum { TG_FLAG_TASK_POOL = 32, TG_FLAG_ITEM_POOL = 64, TG_FLAG_HOPS_POOL = 128 };
+enum { TG_FLAG_TASK_POOL = 32, TG_FLAG_ITEM_POOL = 64, TG_FLAG_HOPS_POOL = 128 };  // (256: TG_FLAG_YLEN, tg_core.h)
 
 struct TgTask {  // one SwgExtend::extend call (src/swg.rs:31)
   uint32_t read;
@@ -527,6 +527,7 @@ TG_HDN void tg_item_post(W& w, const TgAlignParams& P, const TgReadState& st, co
     tg_ops_reverse(gops);
   }
   a.ylen = r2.len;
+  if (r2.len != aref.len) w.atomic_or(flags, TG_FLAG_YLEN);  // never: compact records derive ylen from ref_id
   ir.flags = TG_IF_KEEP;
 }
 
@@ -652,7 +653,7 @@ TG_HDN void tg_round_final(W& w, const TgAlignParams& P, const TgReadState& st, 
   if (k > 0) {
     abase = w.atomic_add(out.alns_used, (unsigned long long)k);
     obase = w.atomic_add(out.ops_used, words);
-    if (abase + k > out.alns_cap || obase + words > out.ops_cap || obase + words > 0xFFFFFFFFull) {
+    if (abase + k > out.alns_cap || obase + words > out.ops_cap || obase + words + out.ops_base > 0xFFFFFFFFull) {
       w.atomic_or(out.flags, abase + k > out.alns_cap ? TG_FLAG_ALN_POOL : TG_FLAG_OPS_POOL);
       kk = 0;
     }
@@ -668,9 +669,8 @@ TG_HDN void tg_round_final(W& w, const TgAlignParams& P, const TgReadState& st, 
     a.tx_ops_off = (uint32_t)(o + n1);
     if (a.aln_type != TG_ALN_EXONIC) { a.tx_ops_off = 0; a.tx_ops_len = 0; }
     a.primary = i == 0 ? 1 : 0;
-    out.alns[abase + i] = a;
+    tg_out_write_aln(out, abase + i, a);
     o += n1 + n2;
   }
-  out.read_aln_first[r] = abase;
-  out.read_aln_count[r] = kk;
+  tg_out_write_read(out, r, abase, kk);
 }

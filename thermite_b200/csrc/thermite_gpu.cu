@@ -859,7 +859,8 @@ __global__ void __launch_bounds__(128) k_round_final(RoundParams p) {
     }
     cells += st.cells; n_ext += st.n_ext; hits += st.hits;
     if (!p.early && p.late && p.st[r].status == TG_RS_FINAL)
-      p.late[warp_agg_add(&p.ctr->n_late, 1ull)] = make_ulonglong2(p.out.read_aln_first[r], (unsigned long long)r | ((unsigned long long)p.out.read_aln_count[r] << 32));
+      p.late[warp_agg_add(&p.ctr->n_late, 1ull)] = make_ulonglong2(p.out.first32 ? (unsigned long long)p.out.first32[r] : p.out.read_aln_first[r],
+                                                                   (unsigned long long)r | ((unsigned long long)p.out.read_aln_count[r] << 32));
   }
   cells = warp_sum(cells); n_ext = warp_sum(n_ext); hits = warp_sum(hits);
   if ((threadIdx.x & 31) == 0) {
@@ -1149,6 +1150,21 @@ struct tg_ctx {
   uint64_t n_launches = 0;  // kernels launched by the last batch call
   // host results
   PinBuf h_first, h_count, h_alns, h_ops, h_seeds, h_seed_first, h_seed_count;
+  // where the records of the current host-buffer call go: the context's own pinned buffers (grown on demand) or a
+  // segment of a caller-owned result (tg_multi_align_batch: fixed capacity, the call reports what it needs instead)
+  struct HostOut {
+    uint8_t* first = nullptr;   // u64[n] (wide) or u32[n] (compact)
+    uint32_t* count = nullptr;
+    uint8_t* alns = nullptr;    // tg_aln[] or tg_aln_c[]
+    uint32_t* ops = nullptr;
+    size_t alns_cap = 0, ops_cap = 0;  // elements
+    bool external = false;
+  } ho;
+  int compact = 0;                                  // records leave as tg_aln_c, firsts as u32
+  unsigned long long first_base = 0, ops_base = 0;  // compact: added to every first index / operation offset on the device
+  bool ho_overflow = false;                         // external segment too small: need_alns / need_ops say how much the shard needs
+  uint64_t need_alns = 0, need_ops = 0;
+  double last_wall_ms = 0.0;
   // swg batch
   DevBuf s_x, s_xo, s_y, s_yo, s_bw, s_xd, s_score, s_xe, s_ye, s_toff, s_tlen, s_ops, s_ypk, s_ysym;
 };
@@ -1197,6 +1213,7 @@ tg_status check_flags(int flags) {
   if (flags & TG_FLAG_READ_CAP)
     return tg_fail(TG_ERR_CAPACITY, "a read accepted more than TG_MAX_ALNS_PER_READ alignments");
   if (flags & TG_FLAG_ARENA) return tg_fail(TG_ERR_CAPACITY, "per-read operation arena exhausted");
+  if (flags & TG_FLAG_YLEN) return tg_fail(TG_ERR_INTERNAL, "an alignment starts on another Ref than its seed hit");
   return TG_OK;
 }
 
@@ -1205,6 +1222,7 @@ tg_status check_flags(int flags) {
 extern "C" {
 
 tg_status tg_index_create(const tg_index_host* hix, int device, tg_index** out) {
+  TG_GUARD_BEGIN
   if (!hix || !out) return tg_fail(TG_ERR_INVALID, "null argument");
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
@@ -1222,9 +1240,11 @@ tg_status tg_index_create(const tg_index_host* hix, int device, tg_index** out) 
   if (st != TG_OK) { cudaFree(ix->d_blob); delete ix; return st; }
   *out = ix;
   return TG_OK;
+  TG_GUARD_END
 }
 
 tg_status tg_index_create_from_device_blob(const void* device_blob, size_t nbytes, int device, tg_index** out) {
+  TG_GUARD_BEGIN
   if (!device_blob || !out) return tg_fail(TG_ERR_INVALID, "null argument");
   CU_CHECK(cudaSetDevice(device));
   auto* ix = new tg_index();
@@ -1235,6 +1255,7 @@ tg_status tg_index_create_from_device_blob(const void* device_blob, size_t nbyte
   if (st != TG_OK) { delete ix; return st; }
   *out = ix;
   return TG_OK;
+  TG_GUARD_END
 }
 
 void tg_index_destroy(tg_index* ix) {
@@ -1273,15 +1294,18 @@ void tg_ctx_destroy(tg_ctx* c) {
 // ThermiteAligner::align_read from many threads (src/wrapper.rs:20-27, :72): the micro-batcher of host_batcher.cpp over
 // tg_align_batch of this context
 tg_status tg_batcher_create(tg_ctx* ctx, uint32_t max_batch_reads, uint32_t max_wait_us, tg_batcher** out) {
+  TG_GUARD_BEGIN
   if (!ctx || !out) return tg_fail(TG_ERR_INVALID, "null argument");
   return tg_batcher_create_backend(
       [](void* user, const uint8_t* bases, const uint64_t* offs, uint32_t n, tg_result* res) {
         return tg_align_batch((tg_ctx*)user, bases, offs, n, res);
       },
       ctx, max_batch_reads, max_wait_us, out);
+  TG_GUARD_END
 }
 
 tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
+  TG_GUARD_BEGIN
   if (!ix || !opts || !out) return tg_fail(TG_ERR_INVALID, "null argument");
   if (opts->min_seed_len < 1 || opts->min_seed_len > TG_MAX_SEED_LEN)
     return tg_fail(TG_ERR_INVALID, "min_seed_len must be in [1, TG_MAX_SEED_LEN]");
@@ -1337,6 +1361,7 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
 #undef CTX_CHECK
   *out = c;
   return TG_OK;
+  TG_GUARD_END
 }
 
 void tg_ctx_set_chunk_reads(tg_ctx* ctx, uint32_t reads) {
@@ -1371,6 +1396,7 @@ void tg_ctx_debug_classes(const tg_ctx* ctx, uint32_t* out) {  // [TG_MAX_ROUNDS
 float tg_ctx_last_dp_ms(const tg_ctx* ctx) { return ctx ? ctx->last_dp_ms : 0.f; }
 // Random 16-B gather rate over the context's own k-mer table (GB/s of 32-B sectors), best of `reps`.
 tg_status tg_bench_random_gather(tg_ctx* c, uint64_t n_loads, int reps, double* sector_gbs, float* best_ms) {
+  TG_GUARD_BEGIN
   if (!c || !sector_gbs) return tg_fail(TG_ERR_INVALID, "null argument");
   CU_CHECK(cudaSetDevice(c->ix->device));
   uint32_t* sink = nullptr;
@@ -1392,6 +1418,7 @@ tg_status tg_bench_random_gather(tg_ctx* c, uint64_t n_loads, int reps, double* 
   *sector_gbs = 32.0 * (double)(threads * per_thread) / (best / 1e3) / 1e9;
   if (best_ms) *best_ms = best;
   return TG_OK;
+  TG_GUARD_END
 }
 uint64_t tg_ctx_last_kernel_launches(const tg_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots * sizeof(TgSlot) : 0; }
@@ -1399,6 +1426,14 @@ uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx) { return ctx ? ctx->n_slots 
 }  // extern "C"
 
 namespace {
+
+// compact output: the device pools hold tg_aln_c records / u32 firsts (same buffers, smaller elements)
+void set_compact_out(tg_ctx* c, TgAlignOut& out) {
+  if (!c->compact) return;
+  out.alns_c = (tg_aln_c*)c->d_alns.p;
+  out.first32 = (uint32_t*)c->d_aln_first.p + c->out_row0;
+  out.first_base = c->first_base; out.ops_base = c->ops_base;
+}
 
 // seeding of the reads [r0, r0 + nk) of a batch of n reads (the whole batch when nk == n)
 tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n, uint32_t maxL, uint32_t r0 = 0,
@@ -1479,6 +1514,7 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.out.alns = (tg_aln*)c->d_alns.p; p.out.ops = (uint32_t*)c->d_ops.p;
   p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;
   p.out.alns_cap = c->alns_cap; p.out.ops_cap = c->ops_cap; p.out.flags = &c->d_ctr->flags;
+  set_compact_out(c, p.out);
   p.ctr = c->d_ctr;
   kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
   c->n_launches++;
@@ -1585,6 +1621,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   p.out.alns = (tg_aln*)c->d_alns.p; p.out.ops = (uint32_t*)c->d_ops.p;
   p.out.alns_used = &c->d_ctr->alns_used; p.out.ops_used = &c->d_ctr->ops_used;
   p.out.alns_cap = c->alns_cap; p.out.ops_cap = c->ops_cap; p.out.flags = &c->d_ctr->flags;
+  set_compact_out(c, p.out);
   p.ctr = c->d_ctr;
   // extension kernel geometry
   int wpc = TG_WARPS_PER_CTA;
@@ -1640,23 +1677,34 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
       CU_CHECK(cudaStreamSynchronize(c->stream));
       const unsigned long long a1 = std::min<unsigned long long>(c->h_snap[0], c->alns_cap), o1 = std::min<unsigned long long>(c->h_snap[1], c->ops_cap);
       const unsigned long long a0 = c->early_alns, o0 = c->early_ops;
-      // room for the whole batch, estimated from what is known (grown again at the end if a batch needs more)
-      const size_t want_a = (size_t)std::max<unsigned long long>(a1 + a1 / 16, (unsigned long long)n + n / 8) + 65536;
-      const size_t want_o = (size_t)std::max<unsigned long long>(o1 + o1 / 16, r == 0 ? 3 * o1 : 0ull) + 262144;
-      if (want_a * sizeof(tg_aln) > c->h_alns.cap || want_o * 4 > c->h_ops.cap) {
-        CU_CHECK(cudaStreamSynchronize(c->copy_out));  // what was sent so far has landed before the buffers move
-        if ((st = c->h_alns.ensure_keep(want_a * sizeof(tg_aln), (size_t)a0 * sizeof(tg_aln))) != TG_OK) return st;
-        if ((st = c->h_ops.ensure_keep(want_o * 4, (size_t)o0 * 4)) != TG_OK) return st;
+      const size_t rec = c->compact ? sizeof(tg_aln_c) : sizeof(tg_aln), fsz = c->compact ? 4 : 8;
+      bool room = true;
+      if (!c->ho.external) {
+        // room for the whole batch, estimated from what is known (grown again at the end if a batch needs more)
+        const size_t want_a = (size_t)std::max<unsigned long long>(a1 + a1 / 16, (unsigned long long)n + n / 8) + 65536;
+        const size_t want_o = (size_t)std::max<unsigned long long>(o1 + o1 / 16, r == 0 ? 3 * o1 : 0ull) + 262144;
+        if (want_a * rec > c->h_alns.cap || want_o * 4 > c->h_ops.cap) {
+          CU_CHECK(cudaStreamSynchronize(c->copy_out));  // what was sent so far has landed before the buffers move
+          if ((st = c->h_alns.ensure_keep(want_a * rec, (size_t)a0 * rec)) != TG_OK) return st;
+          if ((st = c->h_ops.ensure_keep(want_o * 4, (size_t)o0 * 4)) != TG_OK) return st;
+        }
+        c->ho.alns = (uint8_t*)c->h_alns.p; c->ho.ops = (uint32_t*)c->h_ops.p;
+        c->ho.alns_cap = c->h_alns.cap / rec; c->ho.ops_cap = c->h_ops.cap / 4;
+      } else if (a1 > c->ho.alns_cap || o1 > c->ho.ops_cap) {
+        room = false;  // the caller's segment is too small: the call will end with the sizes it needs
+        c->ho_overflow = true;
       }
-      if (a1 > a0)
-        CU_CHECK(cudaMemcpyAsync((tg_aln*)c->h_alns.p + a0, (tg_aln*)c->d_alns.p + a0, (size_t)(a1 - a0) * sizeof(tg_aln), cudaMemcpyDeviceToHost, c->copy_out));
-      if (o1 > o0)
-        CU_CHECK(cudaMemcpyAsync((uint32_t*)c->h_ops.p + o0, (uint32_t*)c->d_ops.p + o0, (size_t)(o1 - o0) * 4, cudaMemcpyDeviceToHost, c->copy_out));
-      c->early_alns = a1; c->early_ops = o1;
-      if (r == 1) {  // first/count of every read that is finished by now; the others follow as a fix-up list
-        CU_CHECK(cudaMemcpyAsync(c->h_first.p, c->d_aln_first.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->copy_out));
-        CU_CHECK(cudaMemcpyAsync(c->h_count.p, c->d_aln_count.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->copy_out));
-        c->early_rows = 1;
+      if (room && !c->ho_overflow) {
+        if (a1 > a0)
+          CU_CHECK(cudaMemcpyAsync(c->ho.alns + a0 * rec, (const uint8_t*)c->d_alns.p + a0 * rec, (size_t)(a1 - a0) * rec, cudaMemcpyDeviceToHost, c->copy_out));
+        if (o1 > o0)
+          CU_CHECK(cudaMemcpyAsync(c->ho.ops + o0, (uint32_t*)c->d_ops.p + o0, (size_t)(o1 - o0) * 4, cudaMemcpyDeviceToHost, c->copy_out));
+        c->early_alns = a1; c->early_ops = o1;
+        if (r == 1) {  // first/count of every read that is finished by now; the others follow as a fix-up list
+          CU_CHECK(cudaMemcpyAsync(c->ho.first, c->d_aln_first.p, (size_t)n * fsz, cudaMemcpyDeviceToHost, c->copy_out));
+          CU_CHECK(cudaMemcpyAsync(c->ho.count, c->d_aln_count.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->copy_out));
+          c->early_rows = 1;
+        }
       }
     }
     // late rounds are short: a host check for "nothing left" costs less than launching the remaining empty rounds
@@ -1785,6 +1833,7 @@ extern "C" {
 
 tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n_reads,
                                 uint64_t total_bases, uint32_t max_read_len, tg_result* out) {
+  TG_GUARD_BEGIN
   tg_status st = check_batch_args(ctx, d_bases, d_offs, out);
   if (st != TG_OK) return st;
   (void)total_bases;
@@ -1792,6 +1841,7 @@ tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint6
   memset(out, 0, sizeof(*out));
   if (n_reads == 0) return TG_OK;
   ctx->n_launches = 0;
+  ctx->compact = 0; ctx->first_base = 0; ctx->ops_base = 0;
   if ((st = run_pipeline(ctx, d_bases, d_offs, n_reads, std::max(max_read_len, 1u), true)) != TG_OK) return st;
   fill_result(ctx, n_reads, out);
   out->read_aln_first = (const uint64_t*)ctx->d_aln_first.p;
@@ -1799,18 +1849,21 @@ tg_status tg_align_batch_device(tg_ctx* ctx, const uint8_t* d_bases, const uint6
   out->alns = (const tg_aln*)ctx->d_alns.p;
   out->ops = (const uint32_t*)ctx->d_ops.p;
   return TG_OK;
+  TG_GUARD_END
 }
 
-tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_result* out) {
-  tg_status st = check_batch_args(ctx, offs, offs, out);
-  if (st != TG_OK) return st;
-  memset(out, 0, sizeof(*out));
-  if (n_reads == 0) return TG_OK;
-  if (!bases && offs[n_reads] > 0) return tg_fail(TG_ERR_INVALID, "null argument");
-  tg_ctx* c = ctx;
+// tg_align_batch / tg_align_batch_compact / one shard of tg_multi_align_batch.  offs[0] need not be 0 (a shard of a larger
+// batch): reads are bases[offs[r], offs[r+1]).  ext: caller-owned result segment (compact only), else the context's buffers.
+static tg_status align_host(tg_ctx* c, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, bool compact,
+                            const tg_ctx::HostOut* ext, unsigned long long first_base, unsigned long long ops_base) {
+  tg_status st;
   const bool dbg = getenv("TG_DEBUG_TIMING") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_in = now();
+  const size_t rec = compact ? sizeof(tg_aln_c) : sizeof(tg_aln), fsz = compact ? 4 : 8;
+  c->compact = compact ? 1 : 0;
+  c->first_base = first_base; c->ops_base = ops_base;
+  c->ho_overflow = false; c->need_alns = 0; c->need_ops = 0;
   // Copies overlap kernels at both ends of the call (three streams): the bases arrive in chunks and every chunk is
   // seeded as soon as it has landed; the records of the reads that are finished after round 1 (~98 %) travel to the
   // host while the late rounds run.  One pass over the whole batch, one contiguous result.
@@ -1818,7 +1871,9 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
   const uint32_t want = c->chunk_reads ? c->chunk_reads : std::max<uint32_t>(262144u, (n_reads + 7) / 8);
   const uint32_t chunk = n_reads >= 2 * (uint64_t)want ? want : n_reads;
   const uint32_t n_chunks = (n_reads + chunk - 1) / chunk;
-  const uint64_t total = offs[n_reads];
+  const uint64_t base0 = offs[0];
+  if (offs[n_reads] < base0) return tg_fail(TG_ERR_INVALID, "read offsets must be non-decreasing");
+  const uint64_t total = offs[n_reads] - base0;
   if ((st = c->d_bases.ensure(total + 64)) != TG_OK) return st;
   if ((st = c->d_offs.ensure((size_t)(n_reads + 1) * 8)) != TG_OK) return st;
   while (c->ev_in.size() < n_chunks) {
@@ -1866,12 +1921,19 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
       maxL = std::max<uint32_t>(maxL, longest);
     }
     const uint64_t b0 = offs[r0], b1 = offs[r1];
-    if (b1 > b0) CU_CHECK(cudaMemcpyAsync((uint8_t*)c->d_bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_in));
+    if (b1 > b0) CU_CHECK(cudaMemcpyAsync((uint8_t*)c->d_bases.p + (b0 - base0), bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_in));
     CU_CHECK(cudaEventRecord(c->ev_in[k], c->copy_in));
   }
   // maxL of the whole batch is needed before the first kernel: the loop above has run over every read by now
-  if ((st = c->h_first.ensure((size_t)n_reads * 8)) != TG_OK) return st;
-  if ((st = c->h_count.ensure((size_t)n_reads * 4)) != TG_OK) return st;
+  if (ext) c->ho = *ext;
+  else {
+    if ((st = c->h_first.ensure((size_t)n_reads * 8)) != TG_OK) return st;
+    if ((st = c->h_count.ensure((size_t)n_reads * 4)) != TG_OK) return st;
+    c->ho.first = (uint8_t*)c->h_first.p; c->ho.count = (uint32_t*)c->h_count.p;
+    c->ho.alns = (uint8_t*)c->h_alns.p; c->ho.ops = (uint32_t*)c->h_ops.p;
+    c->ho.alns_cap = c->h_alns.cap / rec; c->ho.ops_cap = c->h_ops.cap / 4;
+    c->ho.external = false;
+  }
   const double t_issued = now();
   c->n_launches = 0;
   c->in_chunks = n_chunks; c->in_chunk_reads = chunk;
@@ -1879,16 +1941,25 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
     const char* em = getenv("TG_EARLY_MODE");  // experiments: 0 no early output, 1 after round 1 only, 2 (default) after rounds 0 and 1
     c->early_out = c->use_rounds && n_reads >= c->small_batch ? (em ? atoi(em) : 2) : 0;  // (small batch: nothing to hide)
   }
-  st = run_pipeline(c, (const uint8_t*)c->d_bases.p, (const uint64_t*)c->d_offs.p, n_reads, maxL, true);
+  // the kernels address the reads through the caller's offsets: hand them the device buffer shifted by offs[0]
+  st = run_pipeline(c, (const uint8_t*)c->d_bases.p - base0, (const uint64_t*)c->d_offs.p, n_reads, maxL, true);
   c->in_chunks = 0; c->early_out = 0;
   const double t_pipe = now();
   if (st != TG_OK) { cudaStreamSynchronize(c->copy_out); return st; }
-  fill_result(c, n_reads, out);
-  const uint64_t ea = std::min<uint64_t>(c->early_alns, out->n_alns), eo = std::min<uint64_t>(c->early_ops, out->n_ops);
-  if (out->n_alns * sizeof(tg_aln) + 16 > c->h_alns.cap || out->n_ops * 4 + 16 > c->h_ops.cap) {
-    CU_CHECK(cudaStreamSynchronize(c->copy_out));  // the early part has landed before the buffers move
-    if ((st = c->h_alns.ensure_keep((size_t)out->n_alns * sizeof(tg_aln) + 16, ea * sizeof(tg_aln))) != TG_OK) return st;
-    if ((st = c->h_ops.ensure_keep((size_t)out->n_ops * 4 + 16, eo * 4)) != TG_OK) return st;
+  const uint64_t n_alns = c->h_ctr->alns_used, n_ops = c->h_ctr->ops_used;
+  const uint64_t ea = std::min<uint64_t>(c->early_alns, n_alns), eo = std::min<uint64_t>(c->early_ops, n_ops);
+  if (!c->ho.external) {
+    if (n_alns * rec + 16 > c->h_alns.cap || n_ops * 4 + 16 > c->h_ops.cap) {
+      CU_CHECK(cudaStreamSynchronize(c->copy_out));  // the early part has landed before the buffers move
+      if ((st = c->h_alns.ensure_keep((size_t)n_alns * rec + 16, ea * rec)) != TG_OK) return st;
+      if ((st = c->h_ops.ensure_keep((size_t)n_ops * 4 + 16, eo * 4)) != TG_OK) return st;
+    }
+    c->ho.alns = (uint8_t*)c->h_alns.p; c->ho.ops = (uint32_t*)c->h_ops.p;
+  } else if (c->ho_overflow || n_alns > c->ho.alns_cap || n_ops > c->ho.ops_cap) {
+    c->ho_overflow = true; c->need_alns = n_alns; c->need_ops = n_ops;
+    c->early_rows = 0;
+    CU_CHECK(cudaStreamSynchronize(c->copy_out));
+    return TG_OK;  // (the caller looks at ho_overflow)
   }
   // first/count: already on their way for the reads finished after round 1; the last pass lists the rest (a few per cent).
   // Reads redone by the single-warp kernel are not in that list: then everything is copied again.
@@ -1900,38 +1971,106 @@ tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs
     if (n_late) CU_CHECK(cudaMemcpyAsync(c->h_late.p, c->r_late.p, (size_t)n_late * 16, cudaMemcpyDeviceToHost, c->stream));
   } else {
     CU_CHECK(cudaStreamSynchronize(c->copy_out));  // (an early copy of the same arrays must not land after this one)
-    CU_CHECK(cudaMemcpyAsync(c->h_first.p, c->d_aln_first.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU_CHECK(cudaMemcpyAsync(c->h_count.p, c->d_aln_count.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaMemcpyAsync(c->ho.first, c->d_aln_first.p, (size_t)n_reads * fsz, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaMemcpyAsync(c->ho.count, c->d_aln_count.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
   }
-  if (out->n_alns > ea)
-    CU_CHECK(cudaMemcpyAsync((tg_aln*)c->h_alns.p + ea, (tg_aln*)c->d_alns.p + ea, (size_t)(out->n_alns - ea) * sizeof(tg_aln),
+  if (n_alns > ea)
+    CU_CHECK(cudaMemcpyAsync(c->ho.alns + ea * rec, (const uint8_t*)c->d_alns.p + ea * rec, (size_t)(n_alns - ea) * rec,
                              cudaMemcpyDeviceToHost, c->stream));
-  if (out->n_ops > eo)
-    CU_CHECK(cudaMemcpyAsync((uint32_t*)c->h_ops.p + eo, (uint32_t*)c->d_ops.p + eo, (size_t)(out->n_ops - eo) * 4,
-                             cudaMemcpyDeviceToHost, c->stream));
+  if (n_ops > eo)
+    CU_CHECK(cudaMemcpyAsync(c->ho.ops + eo, (uint32_t*)c->d_ops.p + eo, (size_t)(n_ops - eo) * 4, cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(cudaStreamSynchronize(c->stream));
   CU_CHECK(cudaStreamSynchronize(c->copy_out));
   if (fixup) {
     const unsigned long long* l = (const unsigned long long*)c->h_late.p;
-    uint64_t* hf = (uint64_t*)c->h_first.p;
-    uint32_t* hc = (uint32_t*)c->h_count.p;
+    uint32_t* hc = c->ho.count;
     for (uint64_t i = 0; i < n_late; i++) {
       const uint32_t r = (uint32_t)(l[2 * i + 1] & 0xFFFFFFFFull);
-      hf[r] = l[2 * i];
+      if (compact) ((uint32_t*)c->ho.first)[r] = (uint32_t)l[2 * i];
+      else ((uint64_t*)c->ho.first)[r] = l[2 * i];
       hc[r] = (uint32_t)(l[2 * i + 1] >> 32);
     }
   }
+  c->last_wall_ms = now() - t_in;
   if (dbg)
-    fprintf(stderr, "tg_align_batch: issue inputs %.2f ms, pipeline %.2f ms (seed %.2f + extend %.2f on the device), tail %.2f ms\n",
-            t_issued - t_in, t_pipe - t_issued, c->last_seed_ms, c->last_extend_ms, now() - t_pipe);
-  out->read_aln_first = (const uint64_t*)c->h_first.p;
-  out->read_aln_count = (const uint32_t*)c->h_count.p;
-  out->alns = (const tg_aln*)c->h_alns.p;
-  out->ops = (const uint32_t*)c->h_ops.p;
+    fprintf(stderr, "tg_align_batch[dev %d]: %u reads, issue inputs %.2f ms, pipeline %.2f ms (seed %.2f + extend %.2f on the device), tail %.2f ms; "
+            "H2D %.1f MB, D2H %.1f MB (%.1f MB early)\n", c->ix->device, n_reads,
+            t_issued - t_in, t_pipe - t_issued, c->last_seed_ms, c->last_extend_ms, now() - t_pipe,
+            (total + 8.0 * (n_reads + 1)) / 1e6, (n_alns * rec + n_ops * 4.0 + n_reads * (fsz + 4.0)) / 1e6, (ea * rec + eo * 4.0) / 1e6);
   return TG_OK;
 }
 
+tg_status tg_align_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_result* out) {
+  TG_GUARD_BEGIN
+  tg_status st = check_batch_args(ctx, offs, offs, out);
+  if (st != TG_OK) return st;
+  memset(out, 0, sizeof(*out));
+  if (n_reads == 0) return TG_OK;
+  if (!bases && offs[n_reads] > offs[0]) return tg_fail(TG_ERR_INVALID, "null argument");
+  if ((st = align_host(ctx, bases, offs, n_reads, false, nullptr, 0, 0)) != TG_OK) return st;
+  fill_result(ctx, n_reads, out);
+  out->read_aln_first = (const uint64_t*)ctx->ho.first;
+  out->read_aln_count = ctx->ho.count;
+  out->alns = (const tg_aln*)ctx->ho.alns;
+  out->ops = ctx->ho.ops;
+  return TG_OK;
+  TG_GUARD_END
+}
+
+static void fill_result_c(const tg_ctx* c, uint32_t n, tg_result_c* out) {
+  out->n_reads = n; out->n_segments = 1;
+  out->n_alns = c->h_ctr->alns_used; out->n_ops = c->h_ctr->ops_used;
+  out->alns_extent = out->n_alns; out->ops_extent = out->n_ops;
+  out->swg_cells = c->h_ctr->cells; out->swg_extensions = c->h_ctr->n_ext;
+  out->seed_hits = c->h_ctr->hits; out->n_smems = c->h_ctr->n_smems;
+}
+
+tg_status tg_align_batch_compact(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_result_c* out) {
+  TG_GUARD_BEGIN
+  tg_status st = check_batch_args(ctx, offs, offs, out);
+  if (st != TG_OK) return st;
+  memset(out, 0, sizeof(*out));
+  if (n_reads == 0) return TG_OK;
+  if (!bases && offs[n_reads] > offs[0]) return tg_fail(TG_ERR_INVALID, "null argument");
+  if ((st = align_host(ctx, bases, offs, n_reads, true, nullptr, 0, 0)) != TG_OK) return st;
+  fill_result_c(ctx, n_reads, out);
+  out->read_aln_first = (const uint32_t*)ctx->ho.first;
+  out->read_aln_count = ctx->ho.count;
+  out->alns = (const tg_aln_c*)ctx->ho.alns;
+  out->ops = ctx->ho.ops;
+  return TG_OK;
+  TG_GUARD_END
+}
+
+}  // extern "C"
+
+int tg_ctx_device(const tg_ctx* ctx) { return ctx->ix->device; }
+
+tg_status tg_ctx_align_segment(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, const TgHostSegment& seg,
+                               TgShardStat* stat) {
+  TG_GUARD_BEGIN
+  memset(stat, 0, sizeof(*stat));
+  if (n_reads == 0) return TG_OK;
+  tg_status st = check_batch_args(ctx, offs, offs, stat);
+  if (st != TG_OK) return st;
+  tg_ctx::HostOut ho;
+  ho.first = (uint8_t*)seg.first; ho.count = seg.count; ho.alns = (uint8_t*)seg.alns; ho.ops = seg.ops;
+  ho.alns_cap = seg.alns_cap; ho.ops_cap = seg.ops_cap; ho.external = true;
+  if ((st = align_host(ctx, bases, offs, n_reads, true, &ho, seg.first_base, seg.ops_base)) != TG_OK) return st;
+  stat->overflow = ctx->ho_overflow;
+  stat->need_alns = ctx->need_alns; stat->need_ops = ctx->need_ops;
+  stat->n_alns = ctx->h_ctr->alns_used; stat->n_ops = ctx->h_ctr->ops_used;
+  stat->swg_cells = ctx->h_ctr->cells; stat->swg_extensions = ctx->h_ctr->n_ext;
+  stat->seed_hits = ctx->h_ctr->hits; stat->n_smems = ctx->h_ctr->n_smems;
+  stat->wall_ms = ctx->last_wall_ms; stat->seed_ms = ctx->last_seed_ms; stat->extend_ms = ctx->last_extend_ms; stat->dp_ms = ctx->last_dp_ms;
+  return TG_OK;
+  TG_GUARD_END
+}
+
+extern "C" {
+
 tg_status tg_seed_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, tg_seed_result* out) {
+  TG_GUARD_BEGIN
   tg_status st = check_batch_args(ctx, offs, offs, out);
   if (st != TG_OK) return st;
   memset(out, 0, sizeof(*out));
@@ -1956,12 +2095,14 @@ tg_status tg_seed_batch(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs,
   out->read_seed_count = (const uint32_t*)ctx->h_seed_count.p;
   out->seeds = (const tg_seed*)ctx->h_seeds.p;
   return TG_OK;
+  TG_GUARD_END
 }
 
 tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff, const uint8_t* ys, const uint64_t* yoff,
                               uint32_t n, const uint32_t* band_width, const int32_t* x_drop, int32_t* score, uint32_t* xend,
                               uint32_t* yend, uint64_t* ops_off, uint32_t* ops, uint64_t ops_cap, uint64_t* cells,
                               float* kernel_ms) {
+  TG_GUARD_BEGIN
   if (!c || !xoff || !yoff || !band_width || !x_drop || !score || !xend || !yend || !ops_off)
     return tg_fail(TG_ERR_INVALID, "null argument");
   CU_CHECK(cudaSetDevice(c->ix->device));
@@ -2080,6 +2221,7 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   ops_off[n] = o;
   if (ops && o > ops_cap) return tg_fail(TG_ERR_CAPACITY, "ops buffer too small");
   return TG_OK;
+  TG_GUARD_END
 }
 
 }  // extern "C"
