@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=4_000_000, help="reads per step per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline work per step (all threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--swg-pairs", type=int, default=1 << 20, help="config 5 microbench: pairs per band width per GPU")
+    ap.add_argument("--no-swg-microbench", action="store_true")
     return ap.parse_args()
 
 
@@ -175,6 +177,56 @@ def parity_vs_oracle(gpu_res, orc_res, n):
     return dict(reads=n, records=int(len(ga)), op_words=int(len(ggx) + len(gtx)), fields_compared=len(fields),
                 fields_with_differences=diff_fields, operations_identical=bool(ops_ok),
                 identical=bool(not diff_fields and ops_ok))
+
+
+SWG_BWS = (8, 16, 24, 32, 48, 61, 64)
+
+
+def swg_microbench(aligner, n_pairs, int_roof, seed_shift=0, parity=True, threads=1):
+    """BASELINE.json config 5 / SURVEY 8d: SwgExtend::extend alone on synthetic read / ref-window pairs, band widths 8..64,
+    x_drop = bw, through tg_swg_extend_batch (the thread-per-extension DP kernels).  Per band width: GCUPS on the cells the
+    reference's loops visit (credited) and on the cells the bound-stopped kernels really visit (executed), both as a
+    fraction of the INT-pipe roofline, and -- parity -- score / xend / yend / operations of ALL pairs compared with the
+    oracle's (blake2b digest of the concatenated arrays on both sides)."""
+    import hashlib
+    from thermite_b200 import synth
+    out = []
+    for bw in SWG_BWS:
+        xs, xo, ys, yo, b, xd = synth.swg_pairs(20215 + bw + seed_shift, n_pairs, bw)
+        aligner.set_exact_cell_count(True)
+        aligner.swg_extend_batch(xs, xo, ys, yo, b, xd)
+        ex = aligner.swg_extend_batch(xs, xo, ys, yo, b, xd)
+        aligner.set_exact_cell_count(False)
+        aligner.swg_extend_batch(xs, xo, ys, yo, b, xd)
+        r = aligner.swg_extend_batch(xs, xo, ys, yo, b, xd)
+        row = dict(bw=bw, pairs=n_pairs, cells_reference=int(ex["cells"]), cells_executed=int(r["cells"]),
+                   kernel_ms=r["kernel_ms"], kernel_ms_exact_mode=ex["kernel_ms"],
+                   gcups_credited=ex["cells"] / r["kernel_ms"] / 1e6, gcups_executed=r["cells"] / r["kernel_ms"] / 1e6,
+                   gcups_exact_mode=ex["cells"] / ex["kernel_ms"] / 1e6)
+        row["frac_credited"] = row["gcups_credited"] / int_roof
+        row["frac_executed"] = row["gcups_executed"] / int_roof
+        row["frac_exact_mode"] = row["gcups_exact_mode"] / int_roof
+
+        def digest(d):
+            h = hashlib.blake2b(digest_size=16)
+            for k in ("score", "xend", "yend", "ops_off", "ops"):
+                h.update(np.ascontiguousarray(d[k]).tobytes())
+            return h.hexdigest()
+        row["digest"] = digest(r)
+        same_modes = digest(ex) == row["digest"]
+        if parity:
+            from oracle import orc
+            t0 = time.time()
+            o = orc.swg_extend_batch(xs, xo, ys, yo, b, xd, n_threads=threads)
+            row["oracle_digest"] = digest(o)
+            row["oracle_cells"] = int(o["cells"])
+            row["oracle_gcups"] = o["cells"] / (time.time() - t0) / 1e9
+            row["identical"] = bool(row["oracle_digest"] == row["digest"] and same_modes and o["cells"] == ex["cells"] and
+                                    all(np.array_equal(r[k], o[k]) for k in ("score", "xend", "yend", "ops_off", "ops")))
+        else:
+            row["identical"] = None if same_modes else False
+        out.append(row)
+    return out
 
 
 def _orc_flags():
@@ -422,6 +474,8 @@ def _main(args):
 
     # HBM random-access yardstick for the seeding roofline, measured live on this GPU over the k-mer table itself
     gather_gbs = aligner.random_gather_gbs(1 << 26, 5) if rank == 0 else 0.0
+    # ALU-pipe yardstick for the SWG roofline: dependency-free VIADDMNMX / VIMNMX3 streams, lane-operations per second
+    int_peak = aligner.int_peak_lane_ops(5)
 
     # HBM-resident inputs for `value`; pinned host inputs for `e2e`
     d_bases = torch.from_numpy(bases).to(dev)
@@ -501,6 +555,18 @@ def _main(args):
     wide_ms = (time.perf_counter() - t0) * 1e3 / wide_steps
     d2h_wide = int(n * 12 + wres.n_alns * 104 + wres.n_ops * 4)
 
+    # ---- config 5: SWG-only microbench on every rank (parity against the oracle on rank 0 of a single-GPU run) ----------
+    INSTR_PER_CELL = 9.0
+    int_roof_measured = min(int_peak) / INSTR_PER_CELL / 1e9
+    swg_rows = None
+    if not args.no_swg_microbench:
+        swg_rows = swg_microbench(aligner, args.swg_pairs, int_roof_measured, seed_shift=1000 * rank,
+                                  parity=(world == 1 and not args.no_cpu_baseline), threads=os.cpu_count() or 1)
+    swg_gcups = torch.tensor([[r["gcups_credited"], r["gcups_executed"], r["gcups_exact_mode"]] for r in swg_rows] if swg_rows
+                             else [[0.0, 0.0, 0.0]] * len(SWG_BWS), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(swg_gcups, op=dist.ReduceOp.SUM)
+
     t = torch.tensor([dev_ms, e2e_ms, seed_ms, ext_ms, dp_ms, wide_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([counters["swg_cells"], counters["seed_hits"], counters["n_alns"], counters["n_ops"], counters["n_smems"],
                         counters["swg_extensions"], ref_cells, float(launches)], dtype=torch.float64, device=dev)
@@ -529,8 +595,8 @@ def _main(args):
     # INT-pipe roofline: 148 SMs x 4 SMSP x 16 lanes/clk x f x P / I.  P = 1 cell per lane-op (32-bit scores),
     # I = 9 ALU-pipe instructions per cell in the shipped inner loop of k_round_dpt (cuobjdump -sass: VIADD, @P VIADD,
     # 5 x VIADDMNMX, VIMNMX3, VIMNMX; 4 more IMADs issue on the FMA pipe) -- see DESIGN.md section 4.
-    INSTR_PER_CELL = 9.0
-    int_roof = 148 * 4 * 16 * (sm_mhz * 1e6) * 1.0 / INSTR_PER_CELL / 1e9
+    int_roof_theory = 148 * 4 * 16 * (sm_mhz * 1e6) * 1.0 / INSTR_PER_CELL / 1e9
+    int_roof = int_roof_measured  # measured ALU-pipe rate / 9 instructions per cell (theory kept beside it)
     traffic = {}
     try:
         with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
@@ -557,13 +623,18 @@ def _main(args):
                       traffic_note=(traffic.get("k_round_dpt") or {}).get("what"),
                       achieved_computed_cells=gcups_computed, ms_per_step=dp_launch_ms,
                       cells_per_read_reference=ref_cells / n, cells_per_read_computed=cells / n, sm_mhz=sm_mhz,
-                      alu_instr_per_cell=INSTR_PER_CELL, cells_per_lane_op=1.0,
+                      alu_instr_per_cell=INSTR_PER_CELL, cells_per_lane_op=1.0, frac_computed_cells=gcups_computed / int_roof,
+                      int_peak_measured=dict(viaddmnmx_lane_ops_per_s=int_peak[0], vimnmx3_lane_ops_per_s=int_peak[1],
+                                             how="tg_bench_int_peak: 16 independent chains per thread, 8 CTAs of 256 threads per SM, "
+                                                 "best of 5, CUDA events, measured in this run"),
+                      peak_theory=int_roof_theory,
                       hbm_view=dict(peak=hbm_peak, unit="GB/s",
                                     note="not HBM bound: the four DP launches of the heaviest round move 0.78 GB of DRAM traffic "
                                          "in 3.2 ms (ncu, profiles/r1_ncu_dpt.csv) = 0.04 of the streaming peak; the contract's "
                                          "bound enum (hbm | tensor) has no entry for an integer max-plus recurrence"),
-                      peak_source="148 SM x 4 SMSP x 16 lanes/clk x sm_mhz / 9 ALU-pipe instructions per cell (no tensor cores: "
-                                  "max-plus integer DP); MEASURED_PEAKS.json has no integer figure",
+                      peak_source="measured ALU-pipe rate (min of the VIADDMNMX and VIMNMX3 streams, int_peak_measured) / 9 ALU-pipe "
+                                  "instructions per cell; peak_theory = 148 SM x 4 SMSP x 16 lanes/clk x sm_mhz / 9 (no tensor "
+                                  "cores: max-plus integer DP); MEASURED_PEAKS.json has no integer figure",
                       note="achieved = DP cells as the reference's loops visit them (credited count, one exact-count pass) / "
                            "summed CUDA-event time of the DP sections of all rounds; achieved_computed_cells counts only "
                            "the cells the early-stopped extensions really visit"),
@@ -582,6 +653,18 @@ def _main(args):
         counters=dict(hits_per_read=hits / n, alns_per_read=n_alns / n, smems_per_read=n_smems / n, swg_ext_per_read=n_ext / n),
         clocks=clocks,
     )
+    if swg_rows:
+        agg = swg_gcups.tolist()
+        line["swg_microbench"] = dict(
+            what="config 5: SwgExtend::extend alone (tg_swg_extend_batch -> k_round_dpt<0..3>), synthetic pairs, x_drop = bw; "
+                 "GCUPS = cells / CUDA-event time of the kernels; credited = cells the reference's loops visit, executed = cells "
+                 "the bound-stopped kernels visit; exact_mode = every reference column computed",
+            pairs_per_bw_per_gpu=args.swg_pairs, n_gpus=world, int_roofline_gcups_per_gpu=int_roof,
+            rows=swg_rows,
+            aggregate_gcups=[dict(bw=bw, credited=a[0], executed=a[1], exact_mode=a[2], frac_executed=a[1] / (int_roof * world))
+                             for bw, a in zip(SWG_BWS, agg)],
+            identical_to_oracle=(all(r["identical"] for r in swg_rows) if swg_rows[0].get("oracle_digest") else None),
+            min_frac_executed=min(r["frac_executed"] for r in swg_rows))
     if world == 1 and not args.no_cpu_baseline:
         cb, (n_cpu, orc_res) = cpu_baseline(fa, gtf, bases, offs, args.cpu_seconds, os.cpu_count() or 1)
         line["cpu_baseline"] = cb

@@ -183,6 +183,9 @@ uint64_t tg_ctx_last_kernel_launches(const tg_ctx* ctx);
 /* Measurement aid for the seeding roofline: rate of independent random 16-B loads (one 32-B sector each) over the
  * context's own k-mer table, in GB/s of sectors, best of `reps` launches (CUDA events). */
 tg_status tg_bench_random_gather(tg_ctx* ctx, uint64_t n_loads, int reps, double* sector_gbs, float* best_ms);
+/* Measurement aid for the SWG roofline: lane-operations per second of dependency-free streams of the two instructions
+ * the DP inner loop consists of, VIADDMNMX (max(a + b, c)) and VIMNMX3 (max(a, b, c)), best of `reps` launches. */
+tg_status tg_bench_int_peak(tg_ctx* ctx, int reps, double* viaddmnmx_lane_ops, double* vimnmx3_lane_ops);
 /* Size of the context's k-mer table in bytes. */
 uint64_t tg_ctx_kmer_table_bytes(const tg_ctx* ctx);
 

@@ -219,6 +219,51 @@ int64_t orc_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uint
   }
 }
 
+// The same on n_threads host threads (contiguous task ranges; results in task order).  Test / bench infrastructure for
+// the config-5 microbench: 2^20 pairs per band width are too many for one core.
+int64_t orc_swg_extend_batch_mt(const uint8_t* xs, const uint64_t* xoff, const uint8_t* ys, const uint64_t* yoff,
+                                uint64_t n, const uint32_t* bw, const int32_t* x_drop, int32_t* score,
+                                uint32_t* xend, uint32_t* yend, uint64_t* ops_off, uint32_t* ops, uint64_t ops_cap,
+                                uint64_t* cells_total, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  std::vector<std::vector<uint32_t>> words(n_threads);
+  std::vector<uint64_t> cells(n_threads, 0);
+  std::vector<std::string> errs(n_threads);
+  std::vector<uint32_t> lens(n);
+  auto work = [&](int t) {
+    const uint64_t t0 = n * t / n_threads, t1 = n * (t + 1) / n_threads;
+    try {
+      for (uint64_t k = t0; k < t1; k++) {
+        SwgExtend swg(bw[k], -1, -1, 1, -1);
+        Alignment a = swg.extend(xs + xoff[k], xoff[k + 1] - xoff[k], ys + yoff[k], yoff[k + 1] - yoff[k], bw[k], x_drop[k]);
+        cells[t] += swg.cells;
+        const size_t before = words[t].size();
+        rle_append(words[t], a.operations);
+        lens[k] = (uint32_t)(words[t].size() - before);
+        score[k] = a.score; xend[k] = (uint32_t)a.xend; yend[k] = (uint32_t)a.yend;
+      }
+    } catch (const ReferencePanic& e) {
+      errs[t] = e.what();
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  for (auto& e : errs)
+    if (!e.empty()) { g_err = e; return -1; }
+  uint64_t total = 0, c = 0;
+  for (uint64_t k = 0; k < n; k++) { ops_off[k] = total; total += lens[k]; }
+  ops_off[n] = total;
+  uint64_t pos = 0;
+  for (int t = 0; t < n_threads; t++) {
+    c += cells[t];
+    for (uint32_t w : words[t]) { if (pos < ops_cap) ops[pos] = w; pos++; }
+  }
+  if (cells_total) *cells_total = c;
+  return (int64_t)total;
+}
+
 // src/aligner.rs:352-407 test hook (max_bw = bw)
 int orc_extend_left_right(const uint8_t* ref_seq, uint64_t ref_len, uint64_t h_ref, uint64_t h_q, uint64_t h_len,
                           const uint8_t* read, uint64_t read_len, uint64_t max_bw, uint64_t bw, int32_t x_drop,

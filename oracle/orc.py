@@ -55,6 +55,7 @@ def lib():
         L.orc_interval_find.restype = C.c_uint64
         L.orc_all_smems.restype = C.c_int64
         L.orc_swg_extend_batch.restype = C.c_int64
+        L.orc_swg_extend_batch_mt.restype = C.c_int64
         L.orc_filter_overlapping.restype = C.c_int64
         L.orc_result_n_alns.restype = C.c_uint64
         L.orc_result_n_ops.restype = C.c_uint64
@@ -100,7 +101,7 @@ def swg_extend(x: bytes, y: bytes, bw: int, x_drop: int, max_bw=None):
     return score.value, xend.value, yend.value, ops[: n_ops.value].copy(), cells.value
 
 
-def swg_extend_batch(xs, xoff, ys, yoff, bw, x_drop):
+def swg_extend_batch(xs, xoff, ys, yoff, bw, x_drop, n_threads=1):
     """xs/ys: uint8 arrays of concatenated sequences; xoff/yoff: uint64[n+1]; bw uint32[n]; x_drop int32[n]."""
     L = lib()
     n = len(bw)
@@ -112,8 +113,12 @@ def swg_extend_batch(xs, xoff, ys, yoff, bw, x_drop):
     cap = int(len(xs) + len(ys) + 4 * n + 16)
     ops = np.zeros(cap, np.uint32)
     cells = C.c_uint64()
-    tot = L.orc_swg_extend_batch(_p(xs), _p(xoff), _p(ys), _p(yoff), C.c_uint64(n), _p(bw), _p(x_drop), _p(score),
-                                 _p(xend), _p(yend), _p(ops_off), _p(ops), C.c_uint64(cap), C.byref(cells))
+    if n_threads > 1:
+        tot = L.orc_swg_extend_batch_mt(_p(xs), _p(xoff), _p(ys), _p(yoff), C.c_uint64(n), _p(bw), _p(x_drop), _p(score),
+                                        _p(xend), _p(yend), _p(ops_off), _p(ops), C.c_uint64(cap), C.byref(cells), C.c_int(n_threads))
+    else:
+        tot = L.orc_swg_extend_batch(_p(xs), _p(xoff), _p(ys), _p(yoff), C.c_uint64(n), _p(bw), _p(x_drop), _p(score),
+                                     _p(xend), _p(yend), _p(ops_off), _p(ops), C.c_uint64(cap), C.byref(cells))
     if tot < 0:
         raise RuntimeError("reference panics: " + err())
     assert tot <= cap

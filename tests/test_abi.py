@@ -54,11 +54,60 @@ def test_bad_inputs_are_errors_not_crashes():
     with pytest.raises(tb.ThermiteError):
         tb.Index.create_from_files("/nonexistent.fa", "/nonexistent.gtf")
     with pytest.raises(tb.ThermiteError):
-        tb.Index.create_from_memory(b">a\nACGTRRRR\n", b"")
+        tb.Index.create_from_memory(b">a\nACGT1234\n", b"")
+    # IUPAC ambiguity codes are indexed as N (documented deviation: the reference's FM alphabet has no rank for them)
+    assert (tb.Index.create_from_memory(b">a\nACGTRYKMacgtn\n", b"").blob() ==
+            tb.Index.create_from_memory(b">a\nACGTNNNNACGTN\n", b"").blob()).all()
     with pytest.raises(tb.ThermiteError):
         tb.Index.from_blob(np.zeros(1000, np.uint8))
     with pytest.raises(tb.ThermiteError):
         tb.Index.create_from_memory(b">a\nACGTACGT\n", b'b\t.\texon\t1\t4\t.\t+\t.\tgene_id "g"; transcript_id "t";\n')
+
+
+def test_corrupt_index_blobs_are_refused(tmp_path):
+    """A truncated, stale or foreign .tai must fail cleanly in tg_index_host_load / from_blob (the reference's bincode load
+    does), never reach the string decoder or a kernel with out-of-range offsets."""
+    ix = tb.Index.create_from_memory(golden("test_ref.fasta"), golden("test_ref.gtf"))
+    good = ix.blob().copy()
+    hdr = good[:512].view(np.uint64)
+    assert tb.Index.from_blob(good).refs() == ix.refs()
+    # field offsets in TgBlobHeader (u64 words): 0 magic, 1 nbytes, 2 text_len, 3 n_refs, 4 n_txs, 5 n_genes, 6/7 tree nodes,
+    # 8 n_tx_exons, 9 txseq_len, 10/11 roots, 12 device_bytes, 13..30 section offsets, 33 format_version
+    assert hdr[1] == len(good) and hdr[33] >= 4
+    p = str(tmp_path / "t.tai")
+    for what, mutate in (
+            ("truncated", lambda b: b[: len(b) - 64]),
+            ("truncated to the header", lambda b: b[:400]),
+            ("other version", lambda b: _set(b, 33, 3)),
+            ("text_len beyond the suffix array", lambda b: _set(b, 2, int(b[:512].view(np.uint64)[2]) + 4096)),
+            ("more transcripts than there are", lambda b: _set(b, 4, 1 << 20)),
+            ("section offset outside the blob", lambda b: _set(b, 14, len(b) * 2)),
+            ("unaligned section offset", lambda b: _set(b, 15, int(b[:512].view(np.uint64)[15]) + 3)),
+            ("device prefix larger than the blob", lambda b: _set(b, 12, len(b) + 256)),
+            ("string table offsets decreasing", lambda b: _poke_u64(b, int(b[:512].view(np.uint64)[23]) + 8, 1 << 40)),
+            ("suffix array entry outside the text", lambda b: _poke_u32(b, int(b[:512].view(np.uint64)[14]), 0xFFFFFFF0)),
+            ("gene index out of range", lambda b: _poke_u32(b, int(b[:512].view(np.uint64)[27]), 9999))):
+        bad = mutate(good.copy())
+        with pytest.raises(tb.ThermiteError, match="index blob"):
+            tb.Index.from_blob(bad)
+        bad.tofile(p)
+        with pytest.raises(tb.ThermiteError, match="index blob"):
+            tb.Index.load(p)
+
+
+def _set(b, word, value):
+    b[:512].view(np.uint64)[word] = value
+    return b
+
+
+def _poke_u64(b, off, value):
+    b[off: off + 8].view(np.uint64)[0] = value
+    return b
+
+
+def _poke_u32(b, off, value):
+    b[off: off + 4].view(np.uint32)[0] = value
+    return b
 
 
 def test_fastq_parser_and_writers_match_oracle_text():

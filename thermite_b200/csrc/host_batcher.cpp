@@ -238,6 +238,7 @@ tg_status tg_batcher_submit(tg_batcher* b, const uint8_t* read, uint32_t len, ui
     uint32_t sid;
     Shard& sh = b->my_shard(sid);
     const int64_t now = tg_batcher::now_ns();
+    uint64_t q = 0;
     {
       std::lock_guard<std::mutex> lk(sh.mu);
       uint32_t idx;
@@ -253,11 +254,13 @@ tg_status tg_batcher_submit(tg_batcher* b, const uint8_t* read, uint32_t len, ui
       s.in_use = true; s.waited = false; s.done = false; s.status = TG_OK; s.len = len;
       if (len) memcpy(s.read, read, len);
       *ticket = (uint64_t)idx | ((uint64_t)sid << tg_batcher::SLOT_BITS) | ((uint64_t)s.gen << 32);
+      // counted BEFORE the slot becomes visible to the dispatcher (which drains under this lock and then subtracts what it
+      // took): `queued` is never smaller than what sits in the shard queues, so it cannot wrap and queued == 0 means empty
+      b->last_arrival_ns.store(now);
+      q = b->queued.fetch_add(1) + 1;
+      if (q == 1) b->oldest_ns.store(now);
       sh.queue.push_back(&s);
     }
-    b->last_arrival_ns.store(now);
-    const uint64_t q = b->queued.fetch_add(1) + 1;
-    if (q == 1) b->oldest_ns.store(now);
     if (q == 1 || q == b->max_batch) {
       std::lock_guard<std::mutex> lk(b->mu);  // (the dispatcher checks `queued` under this lock before it sleeps)
       b->cv_work.notify_one();

@@ -396,9 +396,9 @@ void decode_strings(const uint8_t* blob, uint64_t off, size_t n, std::vector<std
 }
 
 tg_status finish_host_index(tg_index_host* ix) {
+  if (const char* why = tg_blob_validate_host(ix->blob.data(), ix->blob.size()))
+    return tg_fail(TG_ERR_INVALID, std::string("not a usable thermite_gpu index blob: ") + why);
   const TgBlobHeader* h = ix->hdr();
-  if (ix->blob.size() < sizeof(TgBlobHeader) || h->magic != TG_BLOB_MAGIC || h->nbytes != ix->blob.size())
-    return tg_fail(TG_ERR_INVALID, "not a thermite_gpu index blob");
   const uint8_t* b = ix->blob.data();
   decode_strings(b, h->off_ref_names, h->n_refs, ix->ref_names);
   decode_strings(b, h->off_tx_ids, h->n_txs, ix->tx_ids);
@@ -428,8 +428,14 @@ tg_status build_index(const char* fasta, size_t fasta_len, const char* gtf, size
     text.reserve(total);
   }
   for (auto& c : chroms) {
-    for (char ch : c.seq)
-      if (base_code(ch) < 1) return tg_fail(TG_ERR_IO, "reference sequence contains a symbol outside ACGNT");
+    // IUPAC ambiguity codes (real assemblies hold a few) are indexed as N: the reference's FM alphabet is "ACGNT"
+    // (src/index.rs:108) and has no rank for them, so one such base would make the contig unusable there.  A documented
+    // deviation; anything that is not a nucleotide code at all is still refused.
+    for (char& ch : c.seq) {
+      if (base_code(ch) >= 1) continue;
+      if (strchr("RYSWKMBDHVU", ch)) ch = 'N';
+      else return tg_fail(TG_ERR_IO, "reference sequence contains a symbol that is not a nucleotide code");
+    }
     uint32_t s0 = (uint32_t)text.size();
     text += c.seq;
     text.push_back('$');
@@ -533,6 +539,7 @@ tg_status build_index(const char* fasta, size_t fasta_len, const char* gtf, size
   TgBlobHeader h;
   memset(&h, 0, sizeof(h));
   h.magic = TG_BLOB_MAGIC;
+  h.format_version = TG_BLOB_VERSION;
   h.text_len = T;
   h.n_refs = refs.size(); h.n_txs = gtxs.size(); h.n_genes = genes.size();
   h.n_exon_nodes = exon_tree.nodes.size(); h.n_gene_nodes = gene_tree.nodes.size();
@@ -581,6 +588,94 @@ bool slurp(const char* path, std::string& out) {
 }  // namespace
 
 tg_sa_device_fn g_tg_sa_device = nullptr;  // set by the static initialiser of tg_sa.cu in libthermite_gpu.so
+
+const char* tg_blob_check_header(const TgBlobHeader& h, uint64_t avail, bool device_prefix_only) {
+  if (avail < sizeof(TgBlobHeader)) return "shorter than its header";
+  if (h.magic != TG_BLOB_MAGIC) return "wrong magic";
+  if (h.format_version != TG_BLOB_VERSION) return "written by another format version (re-create the index)";
+  if (h.device_bytes > h.nbytes || h.device_bytes < sizeof(TgBlobHeader)) return "device prefix larger than the blob";
+  if (device_prefix_only ? h.device_bytes > avail : h.nbytes != avail) return "size does not match the header (truncated?)";
+  if (h.text_len == 0 || h.text_len >= (1ull << 31)) return "text length out of range";
+  if (h.n_refs == 0 || h.n_refs > (1ull << 28) || h.n_txs > (1ull << 28) || h.n_genes > (1ull << 28) ||
+      h.n_exon_nodes > (1ull << 30) || h.n_gene_nodes > (1ull << 30) || h.n_tx_exons > (1ull << 30) || h.txseq_len >= (1ull << 40))
+    return "counts out of range";
+  // section = offset + count * element size, inside [header, limit), 8-byte aligned
+  auto inside = [&](uint64_t off, uint64_t count, uint64_t elem, uint64_t limit) {
+    return off >= sizeof(TgBlobHeader) && (off & 7) == 0 && off <= limit && count <= (limit - off) / elem;
+  };
+  const uint64_t dl = h.device_bytes;
+  if (!inside(h.off_text4, h.text_len / 16 + 4, 8, dl)) return "text section out of bounds";
+  if (!inside(h.off_sa, h.text_len, 4, dl)) return "suffix array out of bounds";
+  if (!inside(h.off_refs, h.n_refs, sizeof(TgRef), dl)) return "refs out of bounds";
+  if (!inside(h.off_exon_nodes, h.n_exon_nodes, sizeof(TgTreeNode), dl) || !inside(h.off_gene_nodes, h.n_gene_nodes, sizeof(TgTreeNode), dl))
+    return "interval tree nodes out of bounds";
+  if (!inside(h.off_exon_stab, h.n_exon_nodes, sizeof(TgStab), dl) || !inside(h.off_gene_stab, h.n_gene_nodes, sizeof(TgStab), dl))
+    return "stab lists out of bounds";
+  if (!inside(h.off_tx_seq_off, h.n_txs + 1, 8, dl) || !inside(h.off_tx_exon_off, h.n_txs + 1, 4, dl)) return "transcript tables out of bounds";
+  if (!inside(h.off_te_start, h.n_tx_exons, 4, dl) || !inside(h.off_te_end, h.n_tx_exons, 4, dl)) return "exon tables out of bounds";
+  if (!inside(h.off_txseq4, h.txseq_len / 16 + 4, 8, dl)) return "transcript sequences out of bounds";
+  if (h.exon_root < -1 || h.exon_root >= (int64_t)h.n_exon_nodes || h.gene_root < -1 || h.gene_root >= (int64_t)h.n_gene_nodes)
+    return "tree root out of range";
+  if (!device_prefix_only) {
+    const uint64_t hl = h.nbytes;
+    if (!inside(h.off_ref_names, h.n_refs + 1, 8, hl) || !inside(h.off_tx_ids, h.n_txs + 1, 8, hl) ||
+        !inside(h.off_gene_ids, h.n_genes + 1, 8, hl) || !inside(h.off_gene_names, h.n_genes + 1, 8, hl))
+      return "string tables out of bounds";
+    if (!inside(h.off_tx_gene, h.n_txs, 4, hl) || !inside(h.off_tx_strand, h.n_txs, 4, hl)) return "transcript metadata out of bounds";
+  }
+  return nullptr;
+}
+
+const char* tg_blob_validate_host(const uint8_t* b, uint64_t nbytes) {
+  if (nbytes < sizeof(TgBlobHeader)) return "shorter than its header";
+  TgBlobHeader h;
+  memcpy(&h, b, sizeof(h));
+  if (const char* why = tg_blob_check_header(h, nbytes, false)) return why;
+  // string tables: offsets start at 0, never decrease, bytes inside the blob
+  auto strings_ok = [&](uint64_t off, uint64_t n) {
+    const uint64_t* o = (const uint64_t*)(b + off);
+    const uint64_t room = h.nbytes - (off + (n + 1) * 8);
+    if (o[0] != 0) return false;
+    for (uint64_t i = 0; i < n; i++)
+      if (o[i + 1] < o[i]) return false;
+    return o[n] <= room;
+  };
+  if (!strings_ok(h.off_ref_names, h.n_refs) || !strings_ok(h.off_tx_ids, h.n_txs) || !strings_ok(h.off_gene_ids, h.n_genes) ||
+      !strings_ok(h.off_gene_names, h.n_genes))
+    return "corrupt string table";
+  // refs: consecutive pieces of the text
+  const TgRef* refs = (const TgRef*)(b + h.off_refs);
+  uint64_t pos = 0;
+  for (uint64_t i = 0; i < h.n_refs; i++) {
+    if (refs[i].start_idx != pos || refs[i].end_idx != refs[i].start_idx + (uint64_t)refs[i].len + 1) return "corrupt refs table";
+    pos = refs[i].end_idx;
+  }
+  if (pos != h.text_len) return "refs do not cover the text";
+  // transcripts: offset tables monotone and ending at the section sizes; exons inside the text; gene indices in range
+  const uint64_t* tso = (const uint64_t*)(b + h.off_tx_seq_off);
+  const uint32_t* teo = (const uint32_t*)(b + h.off_tx_exon_off);
+  const uint32_t* tg = (const uint32_t*)(b + h.off_tx_gene);
+  if (tso[0] != 0 || teo[0] != 0 || tso[h.n_txs] != h.txseq_len || teo[h.n_txs] != h.n_tx_exons) return "corrupt transcript offsets";
+  for (uint64_t t = 0; t < h.n_txs; t++)
+    if (tso[t + 1] < tso[t] || teo[t + 1] < teo[t] || tg[t] >= h.n_genes) return "corrupt transcript table";
+  const uint32_t* es = (const uint32_t*)(b + h.off_te_start);
+  const uint32_t* ee = (const uint32_t*)(b + h.off_te_end);
+  for (uint64_t e = 0; e < h.n_tx_exons; e++)
+    if (es[e] > ee[e] || ee[e] > h.text_len) return "corrupt exon table";
+  // suffix array entries are text positions (a permutation is not re-checked: that would cost a pass per load)
+  const uint32_t* sa = (const uint32_t*)(b + h.off_sa);
+  uint32_t bad = 0;
+  for (uint64_t i = 0; i < h.text_len; i++) bad |= sa[i] >= h.text_len;
+  if (bad) return "suffix array entry outside the text";
+  // stab lists: data = transcript / gene index
+  const TgStab* xs = (const TgStab*)(b + h.off_exon_stab);
+  for (uint64_t i = 0; i < h.n_exon_nodes; i++)
+    if (xs[i].data >= h.n_txs || xs[i].start > xs[i].end) return "corrupt exon stab list";
+  const TgStab* gs = (const TgStab*)(b + h.off_gene_stab);
+  for (uint64_t i = 0; i < h.n_gene_nodes; i++)
+    if (gs[i].data >= h.n_genes || gs[i].start > gs[i].end) return "corrupt gene stab list";
+  return nullptr;
+}
 
 
 extern "C" {

@@ -52,8 +52,18 @@ struct TgBlobHeader {
   uint64_t off_ref_names, off_tx_ids, off_gene_ids, off_gene_names, off_tx_gene, off_tx_strand;
   // interval lists sorted by start for warp-cooperative stabbing (rank = position in the tree's find() order)
   uint64_t off_exon_stab, off_gene_stab, exon_maxlen, gene_maxlen;
-  uint64_t reserved[4];
+  uint64_t format_version;  // TG_BLOB_VERSION: bumped whenever a section layout or a device struct changes
+  uint64_t reserved[3];
 };
+#define TG_BLOB_VERSION 4ull
+
+// Checks a header against the number of bytes that are really there (`avail`; the whole blob on the host, the device
+// prefix on the GPU side): magic, version, every section inside the blob, counts consistent with each other.  A
+// truncated, stale or foreign file must fail here and never reach decode_strings or a kernel.  Returns an error text or
+// nullptr.  (Section contents -- string offsets, exon tables -- are checked by tg_blob_validate_host.)
+const char* tg_blob_check_header(const TgBlobHeader& h, uint64_t avail, bool device_prefix_only);
+// The host-side walk over the section contents (monotone string tables, exon / transcript offset tables, refs).
+const char* tg_blob_validate_host(const uint8_t* blob, uint64_t nbytes);
 
 // Device-side view (plain pointers into the device copy of the blob).
 struct TgIndexDev {

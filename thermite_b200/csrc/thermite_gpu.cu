@@ -1037,6 +1037,28 @@ __global__ void __launch_bounds__(256) k_random_gather(const uint4* __restrict__
   if (acc == 0x12345678u) sink[0] = acc;  // keeps the loads alive
 }
 
+// Integer-pipe yardstick for the SWG roofline: dependency-free streams of the two instructions the DP inner
+// loop is made of -- VIADDMNMX (max(a + b, c)) and VIMNMX3 (max(a, b, c)) -- 16 independent chains per thread, enough
+// warps per scheduler to cover the pipe latency.  The measured lane-operations per second replace the assumed
+// "16 lanes per clock per scheduler" in the roofline's numerator.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_int_peak(int iters, int k1, int k2, int* sink) {
+  int v[16], w[16];
+#pragma unroll
+  for (int u = 0; u < 16; u++) { v[u] = (int)threadIdx.x * (u + 1) - k2; w[u] = k2 - u * (int)blockIdx.x; }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      if (KIND == 0) v[u] = __viaddmax_s32(v[u], k1, w[u]);
+      else v[u] = __vimax3_s32(v[u], v[(u + 1) & 15], w[u]);  // (neighbour of the previous iteration: 16 independent ops per iteration)
+    }
+  }
+  int acc = 0;
+#pragma unroll
+  for (int u = 0; u < 16; u++) acc ^= v[u];
+  if (acc == 0x7fffffff) sink[0] = acc;  // keeps the chains alive
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------------------------------
@@ -1175,7 +1197,8 @@ tg_status adopt_blob(tg_index* ix, const void* d_blob, size_t nbytes) {
   TgBlobHeader h;
   if (nbytes < sizeof(h)) return tg_fail(TG_ERR_INVALID, "index blob too small");
   CU_CHECK(cudaMemcpy(&h, d_blob, sizeof(h), cudaMemcpyDeviceToHost));
-  if (h.magic != TG_BLOB_MAGIC || h.device_bytes > nbytes) return tg_fail(TG_ERR_INVALID, "not a thermite_gpu index blob");
+  if (const char* why = tg_blob_check_header(h, nbytes, true))
+    return tg_fail(TG_ERR_INVALID, std::string("not a usable thermite_gpu index blob: ") + why);
   ix->hdr = h;
   const uint8_t* b = (const uint8_t*)d_blob;
   TgIndexDev& d = ix->dev;
@@ -1230,7 +1253,7 @@ tg_status tg_index_create(const tg_index_host* hix, int device, tg_index** out) 
   CU_CHECK(cudaSetDevice(device));
   auto* ix = new tg_index();
   ix->device = device;
-  size_t nb = hix->hdr()->device_bytes;
+  size_t nb = hix->hdr()->device_bytes;  // (validated when the host index was created / loaded: <= blob size)
   cudaError_t e = cudaMalloc(&ix->d_blob, nb);
   if (e != cudaSuccess) { delete ix; return tg_fail(TG_ERR_CUDA, std::string("cudaMalloc(index): ") + cudaGetErrorString(e)); }
   ix->owns = true;
@@ -1417,6 +1440,33 @@ tg_status tg_bench_random_gather(tg_ctx* c, uint64_t n_loads, int reps, double* 
   cudaFree(sink);
   *sector_gbs = 32.0 * (double)(threads * per_thread) / (best / 1e3) / 1e9;
   if (best_ms) *best_ms = best;
+  return TG_OK;
+  TG_GUARD_END
+}
+// ALU-pipe yardstick: lane-operations per second of dependency-free VIADDMNMX and VIMNMX3 streams (best of `reps`).
+tg_status tg_bench_int_peak(tg_ctx* c, int reps, double* viaddmnmx_lane_ops, double* vimnmx3_lane_ops) {
+  TG_GUARD_BEGIN
+  if (!c || !viaddmnmx_lane_ops || !vimnmx3_lane_ops) return tg_fail(TG_ERR_INVALID, "null argument");
+  CU_CHECK(cudaSetDevice(c->ix->device));
+  int* sink = nullptr;
+  CU_CHECK(cudaMalloc(&sink, 64));
+  const int iters = 4096, blocks = c->n_sms * 8;
+  for (int kind = 0; kind < 2; kind++) {
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; r++) {
+      CU_CHECK(cudaEventRecord(c->ev0, c->stream));
+      if (kind == 0) k_int_peak<0><<<blocks, 256, 0, c->stream>>>(iters, -1, 12345, sink);
+      else k_int_peak<1><<<blocks, 256, 0, c->stream>>>(iters, -1, 12345, sink);
+      CU_CHECK(cudaEventRecord(c->ev1, c->stream));
+      CU_CHECK(cudaStreamSynchronize(c->stream));
+      float ms = 0.f;
+      CU_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+      if (r > 0 && ms < best) best = ms;
+    }
+    const double ops = (double)iters * 16.0 * 256.0 * blocks / (best / 1e3);
+    if (kind == 0) *viaddmnmx_lane_ops = ops; else *vimnmx3_lane_ops = ops;
+  }
+  cudaFree(sink);
   return TG_OK;
   TG_GUARD_END
 }

@@ -215,3 +215,31 @@ def synth21(scale=1.0, seed=20212):
                     polya_runs=max(1, int(300 * scale)))
     gtf, txs = make_annotation(seed + 1, "chr21", g, n_genes=max(2, int(800 * scale)), lead=lead)
     return [("chr21", g)], gtf, txs
+
+
+def swg_pairs(seed, n, bw, max_x=71):
+    """SURVEY 8d config 5 (SWG-only microbench): len(x) ~ U[1,71]; y = mutated copy of x (2 % subst, 0.5 % indel: a few
+    copies start one symbol late) padded with random bases to len(x)+bw+20; 5 % unrelated pairs; 0.5 % empty x, 0.5 % empty y.
+    Vectorised (2^20 pairs in about a second).  Returns xs, xoff, ys, yoff, band_width, x_drop (= band_width)."""
+    rng = np.random.default_rng(seed)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    xl = rng.integers(1, max_x + 1, n)
+    kind = rng.random(n)
+    xl[kind < 0.005] = 0
+    xo = np.concatenate(([0], np.cumsum(xl))).astype(np.uint64)
+    xs = al[rng.integers(0, 4, int(xo[-1]), dtype=np.uint8)]
+    yl = xl + bw + 20
+    yl[(kind >= 0.005) & (kind < 0.01)] = 0
+    yo = np.concatenate(([0], np.cumsum(yl))).astype(np.uint64)
+    ys = al[rng.integers(0, 4, int(yo[-1]), dtype=np.uint8)]
+    rel = (kind >= 0.06) & (xl > 0)
+    t_of = np.repeat(np.arange(n), xl)                      # task of every x symbol
+    keep = rel[t_of]
+    pos = np.arange(len(xs)) - xo[:-1].astype(np.int64)[t_of]  # position inside its x
+    xm = xs.copy()
+    sub = rng.random(len(xs), dtype=np.float32) < 0.02
+    xm[sub] = al[rng.integers(0, 4, int(sub.sum()))]
+    shift = (rng.random(n) < 0.005 * xl).astype(np.int64)
+    dst = yo[:-1].astype(np.int64)[t_of] + shift[t_of] + pos
+    ys[dst[keep]] = xm[keep]
+    return xs, xo, ys, yo, np.full(n, bw, np.uint32), np.full(n, bw, np.int32)

@@ -12,27 +12,7 @@ from common import golden  # noqa: E402
 from thermite_b200 import AlignOpts, Aligner, Index  # noqa: E402
 
 
-def pairs(seed, n, bw, max_x=71):
-    """len(x) ~ U[1,71]; y = mutated copy of x (2 % subst, 0.5 % indel) padded to len(x)+bw+20; 5 % unrelated; 1 % empty."""
-    rng = np.random.default_rng(seed)
-    al = np.frombuffer(b"ACGT", np.uint8)
-    xl = rng.integers(1, max_x + 1, n)
-    kind = rng.random(n)
-    xl[kind < 0.005] = 0
-    xo = np.concatenate(([0], np.cumsum(xl))).astype(np.uint64)
-    xs = al[rng.integers(0, 4, int(xo[-1]))]
-    yl = xl + bw + 20
-    yl[(kind >= 0.005) & (kind < 0.01)] = 0
-    yo = np.concatenate(([0], np.cumsum(yl))).astype(np.uint64)
-    ys = al[rng.integers(0, 4, int(yo[-1]))]
-    # copy x into the head of y with substitutions (indels are approximated by shifting a few copies by one)
-    for t in np.nonzero((kind >= 0.06) & (xl > 0))[0]:
-        x = xs[int(xo[t]): int(xo[t + 1])].copy()
-        m = rng.random(len(x)) < 0.02
-        x[m] = al[rng.integers(0, 4, int(m.sum()))]
-        sh = 1 if rng.random() < 0.005 * len(x) else 0
-        ys[int(yo[t]) + sh: int(yo[t]) + sh + len(x)] = x
-    return xs, xo, ys, yo, np.full(n, bw, np.uint32), np.full(n, bw, np.int32)
+from thermite_b200.synth import swg_pairs as pairs  # noqa: E402
 
 
 if __name__ == "__main__":
