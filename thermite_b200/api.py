@@ -553,7 +553,7 @@ class Aligner:
                                          _p(xend), _p(yend), _p(ops_off), _p(ops), C.c_uint64(cap), C.byref(cells),
                                          C.byref(ms)))
         return dict(score=score, xend=xend, yend=yend, ops_off=ops_off, ops=ops[: int(ops_off[n])].copy(),
-                    cells=cells.value, kernel_ms=ms.value)
+                    cells=cells.value, kernel_ms=ms.value, dp_ms=self.last_dp_ms())
 
     def format_result_raw(self, res: _Result, bases, offs, names, name_offs, quals, qual_offs, sam: bool) -> bytes:
         out, n = C.c_void_p(), C.c_size_t()

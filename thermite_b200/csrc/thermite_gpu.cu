@@ -1037,6 +1037,15 @@ __global__ void __launch_bounds__(256) k_random_gather(const uint4* __restrict__
   if (acc == 0x12345678u) sink[0] = acc;  // keeps the loads alive
 }
 
+// A few counters -> pinned host memory, written by the device itself.  The host decisions inside a batch (how much early
+// output there is, whether a read is still active) used to travel as 16-byte D2H copies on the main stream; those queue on
+// the copy engine BEHIND the early record copies of the same batch (hundreds of MB, slow when 8 GPUs share one host) and
+// stalled the kernels behind them for milliseconds.
+__global__ void k_host_snapshot(volatile unsigned long long* host_dst, const unsigned long long* src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) host_dst[i] = src[i];
+  __threadfence_system();
+}
+
 // Integer-pipe yardstick for the SWG roofline: dependency-free streams of the two instructions the DP inner
 // loop is made of -- VIADDMNMX (max(a + b, c)) and VIMNMX3 (max(a, b, c)) -- 16 independent chains per thread, enough
 // warps per scheduler to cover the pipe latency.  The measured lane-operations per second replace the assumed
@@ -1133,6 +1142,7 @@ struct tg_ctx {
   cudaEvent_t ev_dp0[TG_MAX_ROUNDS] = {}, ev_dp1[TG_MAX_ROUNDS] = {};  // DP section of every round (timing)
   int rounds_run = 0;
   float last_dp_ms = 0.f;
+  float round_dp_ms[TG_MAX_ROUNDS] = {};  // DP section of every round of the last batch (debug)
   unsigned long long* h_active = nullptr;  // pinned
   float last_seed_ms = 0.f, last_extend_ms = 0.f;
   int exact_cells = 0;  // 1: run every column the reference runs (swg_cells == reference count)
@@ -1417,6 +1427,11 @@ void tg_ctx_debug_classes(const tg_ctx* ctx, uint32_t* out) {  // [TG_MAX_ROUNDS
   memcpy(out, ctx->h_ctr->round_cls, sizeof(ctx->h_ctr->round_cls));
 }
 float tg_ctx_last_dp_ms(const tg_ctx* ctx) { return ctx ? ctx->last_dp_ms : 0.f; }
+// debug: rounds run by the last batch and the device time of each round's DP section
+int tg_ctx_debug_round_dp_ms(const tg_ctx* ctx, float* out16) {
+  for (int r = 0; r < TG_MAX_ROUNDS; r++) out16[r] = r < ctx->rounds_run ? ctx->round_dp_ms[r] : 0.f;
+  return ctx->rounds_run;
+}
 // Random 16-B gather rate over the context's own k-mer table (GB/s of 32-B sectors), best of `reps`.
 tg_status tg_bench_random_gather(tg_ctx* c, uint64_t n_loads, int reps, double* sector_gbs, float* best_ms) {
   TG_GUARD_BEGIN
@@ -1723,7 +1738,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
       k_round_final<<<tblocks, 128, 0, c->stream>>>(p);
       p.early = 0;
       c->n_launches++;
-      CU_CHECK(cudaMemcpyAsync(c->h_snap, &c->d_ctr->alns_used, 16, cudaMemcpyDeviceToHost, c->stream));
+      k_host_snapshot<<<1, 32, 0, c->stream>>>(c->h_snap, &c->d_ctr->alns_used, 2);
       CU_CHECK(cudaStreamSynchronize(c->stream));
       const unsigned long long a1 = std::min<unsigned long long>(c->h_snap[0], c->alns_cap), o1 = std::min<unsigned long long>(c->h_snap[1], c->ops_cap);
       const unsigned long long a0 = c->early_alns, o0 = c->early_ops;
@@ -1759,7 +1774,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
     }
     // late rounds are short: a host check for "nothing left" costs less than launching the remaining empty rounds
     if (r >= check_from && r + 1 < TG_MAX_ROUNDS) {
-      CU_CHECK(cudaMemcpyAsync(c->h_active, &c->d_ctr->round_active[r], sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      k_host_snapshot<<<1, 32, 0, c->stream>>>(c->h_active, &c->d_ctr->round_active[r], 1);
       CU_CHECK(cudaStreamSynchronize(c->stream));
       if (*c->h_active == 0) break;
     }
@@ -1823,6 +1838,7 @@ tg_status run_pipeline(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs
         float ms = 0.f;
         CU_CHECK(cudaEventElapsedTime(&ms, c->ev_dp0[r], c->ev_dp1[r]));
         c->last_dp_ms += ms;
+        c->round_dp_ms[r] = ms;
       }
     int f = c->h_ctr->flags;
     if (f & (TG_FLAG_SEED_POOL | TG_FLAG_ALN_POOL | TG_FLAG_OPS_POOL | TG_FLAG_TASK_POOL | TG_FLAG_ITEM_POOL | TG_FLAG_HOPS_POOL)) {  // grow the pool that overflowed and redo the batch
@@ -1935,33 +1951,18 @@ static tg_status align_host(tg_ctx* c, const uint8_t* bases, const uint64_t* off
   uint32_t maxL = 1;
   for (uint32_t k = 0; k < n_chunks; k++) {
     const uint32_t r0 = k * chunk, r1 = std::min(n_reads, r0 + chunk);
-    {  // validate while earlier copies are in flight.  The offsets are 8 B per read and stream from host DRAM: one
-       // fused pass, split over a few threads for large chunks (a single core reads ~10 GB/s)
+    {  // validate while earlier copies are in flight: one streaming pass over the chunk's offsets (8 B per read, ~0.3 ms per
+       // 500 k reads on one core -- faster than the copy of the chunk it precedes, and no helper threads to start: eight
+       // contexts in one process or eight ranks on one host would start dozens of them per batch)
       const uint64_t* o = offs + r0;
       const uint32_t m = r1 - r0;
-      const uint32_t T = m >= 131072 ? 4 : 1;
-      uint64_t wide_t[4] = {0, 0, 0, 0};    // non-zero when some length is >= 1024 or negative (offsets decreasing)
-      uint32_t longest_t[4] = {0, 0, 0, 0};
-      auto scan = [&](uint32_t t) {
-        const uint32_t i0 = (uint32_t)((uint64_t)m * t / T), i1 = (uint32_t)((uint64_t)m * (t + 1) / T);
-        uint64_t wide = 0;
-        uint32_t longest = 0;
-        for (uint32_t i = i0; i < i1; i++) {
-          const uint64_t d = o[i + 1] - o[i];
-          wide |= d >> 10;
-          longest = (uint32_t)d > longest ? (uint32_t)d : longest;
-        }
-        wide_t[t] = wide; longest_t[t] = longest;
-      };
-      if (T == 1) scan(0);
-      else {
-        std::thread th[3];
-        for (uint32_t t = 1; t < T; t++) th[t - 1] = std::thread(scan, t);
-        scan(0);
-        for (uint32_t t = 1; t < T; t++) th[t - 1].join();
+      uint64_t wide = 0;  // non-zero when some length is >= 1024 or negative (offsets decreasing)
+      uint32_t longest = 0;
+      for (uint32_t i = 0; i < m; i++) {
+        const uint64_t d = o[i + 1] - o[i];
+        wide |= d >> 10;
+        longest = (uint32_t)d > longest ? (uint32_t)d : longest;
       }
-      const uint64_t wide = wide_t[0] | wide_t[1] | wide_t[2] | wide_t[3];
-      const uint32_t longest = std::max(std::max(longest_t[0], longest_t[1]), std::max(longest_t[2], longest_t[3]));
       if (wide || longest > TG_MAX_READ_LEN) {
         bool decreasing = false;
         for (uint32_t i = 0; i < m; i++) decreasing |= o[i + 1] < o[i];
@@ -2222,6 +2223,7 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   p.tasks = (TgTask*)c->r_tasks.p; p.xpk = (uint64_t*)c->r_rp.p; p.ypk = (uint64_t*)c->s_ypk.p;
   p.ysym_off = (const uint64_t*)c->s_ysym.p; p.rp_words = rp_words; p.dp_ops = (const uint32_t*)c->r_ops.p;
   c->n_launches = 0;
+  bool dp_timed = false;
   CU_CHECK(cudaEventRecord(c->ev0, c->stream));
   if (n_dpt == 0 || !c->use_rounds) {
     kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
@@ -2241,7 +2243,10 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
     const int tb = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16);
     k_swg_prepare<<<tb, 128, 0, c->stream>>>(p);
     p.list = rp.sorted;
+    CU_CHECK(cudaEventRecord(c->ev_dp0[0], c->stream));  // the DP kernels alone (tg_ctx_last_dp_ms): without pack / sort / collect
     if ((st = launch_dpt(c, rp, grid, [&](cudaStream_t s2) { kern<<<blocks, wpc * 32, smem, s2>>>(p); })) != TG_OK) return st;
+    CU_CHECK(cudaEventRecord(c->ev_dp1[0], c->stream));
+    dp_timed = true;
     k_swg_collect<<<tb, 128, 0, c->stream>>>(p);
     c->n_launches += 2;
   }
@@ -2254,6 +2259,8 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
   CU_CHECK(cudaStreamSynchronize(c->stream));
   if (c->h_ctr->flags) return tg_fail(TG_ERR_INTERNAL, "SWG ops pool overflow");
   if (kernel_ms) CU_CHECK(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+  if (dp_timed) CU_CHECK(cudaEventElapsedTime(&c->last_dp_ms, c->ev_dp0[0], c->ev_dp1[0]));
+  else CU_CHECK(cudaEventElapsedTime(&c->last_dp_ms, c->ev0, c->ev1));
   if (cells) *cells = c->h_ctr->cells;
   // reorder the ops pool into task order on the host
   uint64_t used = c->h_ctr->swg_ops_used;

@@ -32,3 +32,6 @@ cl = (C.c_uint32 * (16 * 12))()
 lib().tg_ctx_debug_classes(al._h, cl)
 for r in range(6):
     print("round", r, "tasks per band class (0 = warp kernel, 1 -> WB 4, c -> WB 8(c-1)):", [int(cl[r * 12 + c]) for c in range(12)])
+dpms = (C.c_float * 16)()
+nr = lib().tg_ctx_debug_round_dp_ms(al._h, dpms)
+print("rounds", nr, "DP ms per round", [round(float(dpms[r]), 3) for r in range(nr)], "total", round(al.last_dp_ms(), 3))
