@@ -157,6 +157,10 @@ void tg_ctx_destroy(tg_ctx* ctx);
  * as soon as it has landed; at the other end the records of the reads that are finished after the second round travel to
  * the host while the late rounds run.  Results do not depend on the chunk size. */
 void tg_ctx_set_chunk_reads(tg_ctx* ctx, uint32_t reads);
+/* Host result buffers of tg_align_batch / tg_align_batch_compact.  n = 1 (default): a result is valid until the next call
+ * on the context.  n = 2: two buffer sets used alternately, so a result stays valid until the SECOND next call -- a
+ * consumer (writer thread) may still read batch k while batch k + 1 is being aligned. */
+tg_status tg_ctx_set_result_buffers(tg_ctx* ctx, int n);
 /* The CUDA stream (cudaStream_t) all of the context's work is enqueued on. */
 void* tg_ctx_stream(tg_ctx* ctx);
 /* Device time (CUDA events on the context's stream) of the seeding and extension kernels of the last
@@ -272,6 +276,8 @@ typedef struct tg_multi tg_multi;
 tg_status tg_multi_create(const tg_index_host* ix, const int* devices, int n_devices, const tg_opts* opts, tg_multi** out);
 void tg_multi_destroy(tg_multi* m);
 int tg_multi_n_devices(const tg_multi* m);
+/* Like tg_ctx_set_result_buffers: with n = 2 a result stays valid until the second next tg_multi_align_batch. */
+tg_status tg_multi_set_result_buffers(tg_multi* m, int n);
 /* "nccl" or "peer-copy": how the index replicas were made; *ms = device time of the broadcast (may be NULL). */
 const char* tg_multi_replication(const tg_multi* m, float* ms);
 /* Context of device slot g (e.g. for tg_ctx_set_exact_cell_count); NULL when g is out of range. */

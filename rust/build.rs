@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from(env::var("THERMITE_GPU_CSRC").unwrap_or_else(|_| "thermite_b200/csrc".into()));
     let lib = out.join("libthermite_gpu.a");
-    let objs = ["thermite_gpu.cu", "tg_sa.cu", "host_index.cpp", "host_io.cpp", "host_bam.cpp", "host_batcher.cpp"];
+    let objs = ["thermite_gpu.cu", "tg_sa.cu", "tg_multi.cpp", "host_index.cpp", "host_io.cpp", "host_bam.cpp", "host_batcher.cpp"];
     let mut obj_paths = Vec::new();
     for src in objs.iter() {
         let obj = out.join(format!("{}.o", src));
@@ -30,9 +30,14 @@ fn main() {
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=z");  // BGZF blocks of the BAM writer (host_bam.cpp)
+    println!("cargo:rustc-link-lib=dylib=dl");  // tg_multi.cpp loads libnccl.so.2 at run time (index broadcast)
     println!("cargo:rustc-link-lib=dylib=stdc++");
     for src in objs.iter() {
         println!("cargo:rerun-if-changed={}", csrc.join(src).display());
     }
-    println!("cargo:rerun-if-changed={}", csrc.join("tg_core.h").display());
+    // headers every object depends on (the C ABI header lives in include/)
+    for h in ["tg_core.h", "tg_rounds.h", "tg_dpt.h", "tg_internal.h", "host_text.h"].iter() {
+        println!("cargo:rerun-if-changed={}", csrc.join(h).display());
+    }
+    println!("cargo:rerun-if-changed={}", csrc.join("../../include").join("thermite_gpu.h").display());
 }

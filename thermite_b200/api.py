@@ -89,11 +89,11 @@ ABI_SYMBOLS = [
     "tg_batcher_stats", "tg_batcher_destroy",
     "tg_index_host_text4", "tg_index_host_create_from_files_gpu", "tg_index_host_create_from_memory_gpu", "tg_suffix_array_gpu",
     "tg_index_create", "tg_index_create_from_device_blob", "tg_index_destroy",
-    "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_set_chunk_reads", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_bench_random_gather", "tg_bench_int_peak", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
+    "tg_ctx_create", "tg_ctx_destroy", "tg_ctx_set_chunk_reads", "tg_ctx_set_result_buffers", "tg_ctx_stream", "tg_ctx_last_kernel_ms", "tg_ctx_last_kernel_launches", "tg_ctx_last_dp_ms", "tg_bench_random_gather", "tg_bench_int_peak", "tg_ctx_kmer_table_bytes", "tg_ctx_set_exact_cell_count", "tg_ctx_set_round_pipeline",
     "tg_align_batch", "tg_align_batch_device", "tg_seed_batch", "tg_swg_extend_batch",
     "tg_format_sam_header", "tg_format_batch", "tg_parse_fastq", "tg_free",
     "tg_align_batch_compact", "tg_aln_expand", "tg_result_expand",
-    "tg_multi_create", "tg_multi_destroy", "tg_multi_n_devices", "tg_multi_replication", "tg_multi_ctx",
+    "tg_multi_create", "tg_multi_destroy", "tg_multi_set_result_buffers", "tg_multi_n_devices", "tg_multi_replication", "tg_multi_ctx",
     "tg_multi_align_batch", "tg_multi_last_timing",
 ]
 

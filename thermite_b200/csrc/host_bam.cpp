@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "tg_internal.h"
+#include "host_text.h"
 
 namespace {
 
@@ -245,15 +246,10 @@ tg_status tg_format_bam_header(const tg_index_host* ix, void** out, size_t* out_
   }
 }
 
-tg_status tg_format_batch_bam(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
-                              const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
-                              int append_eof, void** out, size_t* out_len) {
-  if (!out || !out_len) return tg_fail(TG_ERR_INVALID, "null argument");
-  try {
-    char* sam = nullptr;
-    size_t sl = 0;
-    tg_status st = tg_format_batch(ix, res, bases, offs, names, name_offs, quals, qual_offs, 1, &sam, &sl);
-    if (st != TG_OK) return st;
+}  // extern "C" (closed for an internal C++ function)
+
+// SAM lines (without header) -> BAM records in BGZF blocks (optionally followed by the end-of-file block)
+tg_status tg_sam_text_to_bam(const tg_index_host* ix, const char* sam, size_t sl, bool append_eof, std::string& z) {
     const std::vector<std::string> refs = header_refs(ix, nullptr);
     // line ranges on the host's cores; pieces concatenated in order
     uint32_t T = (uint32_t)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64);
@@ -283,15 +279,31 @@ tg_status tg_format_batch_bam(const tg_index_host* ix, const tg_result* res, con
       for (uint32_t t = 0; t < T; t++) th.emplace_back(work, t);
       for (auto& x : th) x.join();
     }
-    free(sam);
     std::string raw;
     for (uint32_t t = 0; t < T; t++) {
       if (!errs[t].empty()) return tg_fail(TG_ERR_INTERNAL, "BAM encoding: " + errs[t]);
       raw += parts[t];
     }
-    std::string z;
     if (!bgzf_compress(raw, z)) return tg_fail(TG_ERR_INTERNAL, "deflate failed");
     if (append_eof) z.append((const char*)BGZF_EOF, 28);
+    return TG_OK;
+}
+
+extern "C" {
+
+tg_status tg_format_batch_bam(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
+                              const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
+                              int append_eof, void** out, size_t* out_len) {
+  if (!out || !out_len) return tg_fail(TG_ERR_INVALID, "null argument");
+  try {
+    char* sam = nullptr;
+    size_t sl = 0;
+    tg_status st = tg_format_batch(ix, res, bases, offs, names, name_offs, quals, qual_offs, 1, &sam, &sl);
+    if (st != TG_OK) return st;
+    std::string z;
+    st = tg_sam_text_to_bam(ix, sam, sl, append_eof != 0, z);
+    free(sam);
+    if (st != TG_OK) return st;
     return hand_over(z, out, out_len);
   } catch (const std::exception& e) {
     return tg_fail(TG_ERR_INTERNAL, e.what());

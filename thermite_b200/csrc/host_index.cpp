@@ -778,33 +778,10 @@ const uint32_t* tg_index_host_sa(const tg_index_host* ix) { return (const uint32
 const uint64_t* tg_index_host_text4(const tg_index_host* ix) { return (const uint64_t*)(ix->blob.data() + ix->hdr()->off_text4); }
 
 // ---- compact records -> wide records (include/thermite_gpu.h: tg_aln_c) ------------------------------------------------
-static inline bool expand_one(const TgRef* refs, uint32_t n_refs, const uint64_t* tx_seq_off, uint32_t n_txs, const tg_aln_c& c,
-                              uint32_t read_len, tg_aln& a) {
-  if (c.ref_id >= n_refs) return false;
-  const TgRef& r = refs[c.ref_id];
-  a.ystart = c.ystart; a.yend = c.yend; a.ylen = r.len;
-  a.score = c.score; a.ref_id = c.ref_id;
-  a.xstart = c.xstart; a.xend = c.xend; a.xlen = read_len;
-  a.tx_or_gene_idx = c.tx_or_gene_idx;
-  a.ops_off = c.ops_off; a.ops_len = c.ops_len;
-  a.aln_type = c.aln_type; a.primary = c.primary; a.strand = (uint8_t)(r.strand_rank & 1u); a.pad = 0;
-  if (c.aln_type == TG_ALN_EXONIC) {
-    if (c.tx_or_gene_idx >= n_txs) return false;
-    a.tx_ystart = c.tx_ystart; a.tx_yend = c.tx_yend;
-    a.tx_ylen = tx_seq_off[c.tx_or_gene_idx + 1] - tx_seq_off[c.tx_or_gene_idx];
-    a.tx_score = c.score; a.tx_xstart = c.xstart; a.tx_xend = c.xend;
-    a.tx_ops_off = c.ops_off + c.ops_len; a.tx_ops_len = c.tx_ops_len;
-  } else {
-    a.tx_ystart = 0; a.tx_yend = 0; a.tx_ylen = 0; a.tx_score = 0; a.tx_xstart = 0; a.tx_xend = 0;
-    a.tx_ops_off = 0; a.tx_ops_len = 0;
-  }
-  return true;
-}
-
 tg_status tg_aln_expand(const tg_index_host* ix, const tg_aln_c* c, uint32_t read_len, tg_aln* out) {
   if (!ix || !c || !out) return tg_fail(TG_ERR_INVALID, "null argument");
   const TgBlobHeader* h = ix->hdr();
-  if (!expand_one((const TgRef*)(ix->blob.data() + h->off_refs), (uint32_t)h->n_refs,
+  if (!tg_expand_one((const TgRef*)(ix->blob.data() + h->off_refs), (uint32_t)h->n_refs,
                   (const uint64_t*)(ix->blob.data() + h->off_tx_seq_off), (uint32_t)h->n_txs, *c, read_len, *out))
     return tg_fail(TG_ERR_INVALID, "record does not belong to this index");
   return TG_OK;
@@ -829,7 +806,7 @@ tg_status tg_result_expand(const tg_index_host* ix, const tg_result_c* res, cons
       if (first_out) first_out[r] = f;
       if ((uint64_t)f + k > res->alns_extent) { if (k) bad[t] = 1; continue; }
       for (uint32_t i = 0; i < k; i++)
-        if (!expand_one(refs, n_refs, tso, n_txs, res->alns[f + i], L, alns_out[f + i])) bad[t] = 1;
+        if (!tg_expand_one(refs, n_refs, tso, n_txs, res->alns[f + i], L, alns_out[f + i])) bad[t] = 1;
     }
   };
   if (n_threads == 1) work(0);

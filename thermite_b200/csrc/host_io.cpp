@@ -11,47 +11,9 @@
 #include <vector>
 
 #include "tg_internal.h"
+#include "host_text.h"
 
 namespace {
-
-// Append-only text buffer (std::string's per-character push_back dominated the writers' time).
-struct Text {
-  char* p = nullptr;
-  size_t n = 0, cap = 0;
-  Text() = default;
-  Text(const Text&) = delete;
-  Text& operator=(const Text&) = delete;
-  Text(Text&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
-  ~Text() { free(p); }
-  void reserve(size_t c) {
-    if (c <= cap) return;
-    size_t want = cap ? cap : 4096;
-    while (want < c) want += want / 2 + 4096;
-    p = (char*)realloc(p, want);
-    cap = want;
-  }
-  char* room(size_t k) { if (n + k > cap) reserve(n + k); return p + n; }
-  void append(const char* src, size_t k) { memcpy(room(k), src, k); n += k; }
-  void push_back(char c) { *room(1) = c; n++; }
-  Text& operator+=(const char* lit) { append(lit, strlen(lit)); return *this; }
-  Text& operator+=(const std::string& str) { append(str.data(), str.size()); return *this; }
-  size_t size() const { return n; }
-  const char* data() const { return p; }
-};
-struct Out {
-  Text s;
-  void num(uint64_t v) {
-    char buf[24];
-    int k = 0;
-    do { buf[k++] = (char)('0' + v % 10); v /= 10; } while (v);
-    char* d = s.room((size_t)k);
-    for (int i = 0; i < k; i++) d[i] = buf[k - 1 - i];
-    s.n += (size_t)k;
-  }
-  void snum(int64_t v) {
-    if (v < 0) { s.push_back('-'); num((uint64_t)(-v)); } else num((uint64_t)v);
-  }
-};
 
 // multimapq (src/aln_writer.rs:332-340)
 unsigned mapq_of(uint64_t n) {
@@ -61,7 +23,7 @@ unsigned mapq_of(uint64_t n) {
 }
 
 // to_noodles_cigar (src/aln_writer.rs:279-323): Match and Subst both print as M and merge
-void cigar(Out& o, const uint32_t* w, uint32_t n) {
+void cigar(TgOut& o, const uint32_t* w, uint32_t n) {
   static const char sym[6] = {'M', 'M', 'D', 'I', 'S', 'N'};
   uint32_t i = 0;
   while (i < n) {
@@ -99,7 +61,7 @@ extern "C" {
 tg_status tg_format_sam_header(const tg_index_host* ix, char** out, size_t* out_len) {
   if (!ix || !out || !out_len) return tg_fail(TG_ERR_INVALID, "null argument");
   // build_sam_header (src/aln_writer.rs:256-276): a map keyed by name, so the two strands collapse
-  Out o;
+  TgOut o;
   std::vector<std::string> seen;
   for (uint32_t i = 0; i < ix->hdr()->n_refs; i++) {
     const std::string& nm = ix->ref_names[i];
@@ -119,17 +81,23 @@ tg_status tg_format_sam_header(const tg_index_host* ix, char** out, size_t* out_
   return TG_OK;
 }
 
+}  // extern "C"
+
 // records of the reads [r0, r1) as PAF / SAM text (appended to o)
-void format_range(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
-                         const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
-                         int sam, uint32_t r0, uint32_t r1, Out& o) {
+void tg_format_reads(const tg_index_host* ix, const TgRecView& v, const uint8_t* bases, const uint64_t* offs,
+                     const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
+                     int sam, uint32_t r0, uint32_t r1, TgOut& o) {
+  const TgBlobHeader* bh = ix->hdr();
+  const TgRef* refs = (const TgRef*)(ix->blob.data() + bh->off_refs);
+  const uint64_t* tso = (const uint64_t*)(ix->blob.data() + bh->off_tx_seq_off);
   for (uint32_t r = r0; r < r1; r++) {
     const char* nm = (const char*)names + name_offs[r];
     size_t nm_len = name_offs[r + 1] - name_offs[r];
     size_t qn_len = nm_len;  // format_read_name: cut at the first space (src/aln_writer.rs:344-349)
     if (sam) for (size_t i = 0; i < nm_len; i++) if (nm[i] == ' ') { qn_len = i; break; }
     const uint64_t L = offs[r + 1] - offs[r];
-    const uint32_t cnt = res->read_aln_count[r];
+    const uint32_t cnt = v.count[r];
+    const uint64_t first = v.first64 ? v.first64[r] : (uint64_t)v.first32[r];
     if (cnt == 0) {
       if (sam) {  // unmapped_sam_record (src/aln_writer.rs:241-253)
         o.s.append(nm, qn_len);
@@ -143,8 +111,10 @@ void format_range(const tg_index_host* ix, const tg_result* res, const uint8_t* 
       continue;  // PAF prints nothing for unmapped reads (src/aligner.rs:77)
     }
     for (uint32_t i = 0; i < cnt; i++) {
-      const tg_aln& a = res->alns[res->read_aln_first[r] + i];
-      const uint32_t* w = res->ops + a.ops_off;
+      tg_aln a;
+      if (v.wide) a = v.wide[first + i];
+      else if (!tg_expand_one(refs, (uint32_t)bh->n_refs, tso, (uint32_t)bh->n_txs, v.comp[first + i], (uint32_t)L, a)) continue;
+      const uint32_t* w = v.ops + a.ops_off;
       const std::string& rname = ix->ref_names[a.ref_id];
       if (!sam) {  // PafEntry (src/aln_writer.rs:47-116)
         uint64_t n_match = 0, n_match_gap = 0;
@@ -196,7 +166,7 @@ void format_range(const tg_index_host* ix, const tg_result* res, const uint8_t* 
         if (a.aln_type == TG_ALN_EXONIC) {
           uint32_t g = ix->tx_gene[a.tx_or_gene_idx];
           o.s += "\tTX:Z:"; o.s += ix->tx_ids[a.tx_or_gene_idx]; o.s += ",+"; o.num(a.tx_ystart); o.s.push_back(',');
-          cigar(o, res->ops + a.tx_ops_off, a.tx_ops_len);
+          cigar(o, v.ops + a.tx_ops_off, a.tx_ops_len);
           o.s += "\tGX:Z:"; o.s += ix->gene_ids[g];
           o.s += "\tGN:Z:"; o.s += ix->gene_names[g];
           o.s += "\tRE:A:E";
@@ -213,6 +183,8 @@ void format_range(const tg_index_host* ix, const tg_result* res, const uint8_t* 
   }
 }
 
+extern "C" {
+
 tg_status tg_format_batch(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
                           const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
                           int sam, char** out, size_t* out_len) {
@@ -223,11 +195,13 @@ tg_status tg_format_batch(const tg_index_host* ix, const tg_result* res, const u
   const uint32_t n = res->n_reads;
   uint32_t T = (uint32_t)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64);
   if (n < 32768) T = 1;
-  std::vector<Out> parts(T);
+  std::vector<TgOut> parts(T);
   auto work = [&](uint32_t t) {
     const uint32_t r0 = (uint32_t)((uint64_t)n * t / T), r1 = (uint32_t)((uint64_t)n * (t + 1) / T);
     parts[t].s.reserve((size_t)(r1 - r0) * (sam ? 400 : 90));
-    format_range(ix, res, bases, offs, names, name_offs, quals, qual_offs, sam, r0, r1, parts[t]);
+    TgRecView v;
+    v.first64 = res->read_aln_first; v.count = res->read_aln_count; v.wide = res->alns; v.ops = res->ops;
+    tg_format_reads(ix, v, bases, offs, names, name_offs, quals, qual_offs, sam, r0, r1, parts[t]);
   };
   if (T == 1) work(0);
   else {
@@ -365,3 +339,63 @@ tg_status tg_parse_fastq(const char* text, size_t len, uint32_t* n_reads, uint8_
 }
 
 }  // extern "C"
+
+// ---- FASTQ text in two passes (host_stream.cpp): count, then fill one batch in place from many threads ------------------
+// Same record rules as parse_fastq_segment: 4-line records, blank lines between records skipped, '\r' dropped, a truncated
+// last record left unconsumed.
+namespace {
+struct LineWalker {
+  const char* text;
+  size_t p, end;
+  bool final;  // `end` is the end of the file: a last line without '\n' is a line; otherwise it is an incomplete one
+  bool next(size_t& lb, size_t& le) {
+    if (p >= end) return false;
+    const void* nl = memchr(text + p, '\n', end - p);
+    if (!nl && !final) return false;
+    const size_t e = nl ? (size_t)((const char*)nl - text) : end;
+    lb = p; le = e;
+    if (le > lb && text[le - 1] == '\r') le--;
+    p = e + 1;
+    return true;
+  }
+};
+}  // namespace
+
+void tg_fastq_count(const char* text, size_t begin, size_t end, bool final, TgFastqCount& c) {
+  LineWalker w{text, begin, end, final};
+  c = TgFastqCount();
+  c.consumed = begin;
+  size_t lb[4], le[4];
+  for (;;) {
+    const size_t rec_start = w.p;
+    if (!w.next(lb[0], le[0])) { c.consumed = rec_start; return; }
+    if (lb[0] == le[0]) { c.consumed = w.p < end ? w.p : end; continue; }  // blank line between records
+    bool full = true;
+    for (int k = 1; k < 4; k++) full = full && w.next(lb[k], le[k]);
+    // (a record is complete only when its quality line is terminated, or the text ends here for good)
+    if (!full) { c.consumed = rec_start; return; }
+    if (text[lb[0]] != '@') { c.bad = true; return; }
+    c.n++;
+    c.names += le[0] - lb[0] - 1; c.bases += le[1] - lb[1]; c.quals += le[3] - lb[3];
+    c.consumed = w.p < end ? w.p : end;
+  }
+}
+
+void tg_fastq_fill(const char* text, size_t begin, size_t end, uint64_t n, uint8_t* bases, uint64_t* offs, uint64_t base0,
+                   uint8_t* names, uint64_t* name_offs, uint64_t name0, uint8_t* quals, uint64_t* qual_offs, uint64_t qual0) {
+  LineWalker w{text, begin, end, true};
+  size_t lb[4], le[4];
+  uint64_t b = base0, nm = name0, q = qual0;
+  for (uint64_t i = 0; i < n;) {
+    if (!w.next(lb[0], le[0])) return;
+    if (lb[0] == le[0]) continue;
+    for (int k = 1; k < 4; k++) w.next(lb[k], le[k]);
+    memcpy(names + nm, text + lb[0] + 1, le[0] - lb[0] - 1); nm += le[0] - lb[0] - 1;
+    memcpy(bases + b, text + lb[1], le[1] - lb[1]); b += le[1] - lb[1];
+    memcpy(quals + q, text + lb[3], le[3] - lb[3]); q += le[3] - lb[3];
+    i++;
+    offs[i] = b; name_offs[i] = nm; qual_offs[i] = q;  // offs / name_offs / qual_offs point at the segment's first record
+  }
+}
+
+size_t tg_fastq_record_start(const char* text, size_t len, size_t p) { return fastq_record_start(text, len, p); }

@@ -13,7 +13,7 @@
 //     shift per column aligns the mask of y[j-1] with the slots, a cell tests one (static) bit.
 //   * column maximum and its FIRST row come from one max over keys  D * 128 + (127 - slot)  (src/swg.rs:101-104 strict
 //     '>' in row order); the x-drop test (:110-112) and the optional bound stop run once per column.
-//   * trace: 2 bits per slot {0 diag, 1 Del, 2 or 3 Ins} (tie priority diag > Del > Ins, src/swg.rs:226-240), TW words per
+//   * trace: 2 bits per slot {0 diag, 1 Del, 2 Ins} (tie priority diag > Del > Ins, src/swg.rs:226-240), TW words per
 //     column, written to a per-thread strided buffer; traceback re-derives Match/Subst from the profile.
 //
 // Limits (the caller routes everything else to the warp kernels): xlen <= TG_DPT_MAX_X, rows in band
@@ -152,46 +152,26 @@ struct TgDptResult {
   uint32_t cells;
 };
 
-// max(a + b, c) in one instruction (VIADDMNMX) on the device
-TG_HD int tg_dpt_addmax(int a, int b, int c) {
-#ifdef __CUDA_ARCH__
-  return __viaddmax_s32(a, b, c);
-#else
-  return a + b > c ? a + b : c;
-#endif
-}
-
-// One DP cell (src/swg.rs:82-99 / :121-140 + triple_max :226-240) on COLUMN-OFFSET scores: every state of column j is
-// stored as value + j (H = D + j, C' = C + j, R' = R + j).  With unit scoring (match +1, mismatch -1, gap open -1,
-// gap extend -1) the recurrences become
-//     C'(i,j) = max(C'(i,j-1), H(i,j-1) - 1)                 horizontal gap: the extension step costs nothing
-//     d(i,j)  = H(i-1,j-1) + (match ? 2 : 0)                 a mismatch on the diagonal costs no instruction
-//     P       = max(d, C')
-//     R'(i,j) = max(R'(i-1,j) - 1, P(i-1,j) - 2)             (P instead of H of the row above: H = max(P, R') and
-//                                                            R' - 2 never beats R' - 1)
-//     H(i,j)  = max(P, R')
-// so the only dependency that runs down a column is rk = R' + 2:  rk_i = max(rk_{i-1} - 1, P_{i-1}),
-// ONE instruction per cell (it was add-max -> max3 -> subtract), H = max(rk - 2, P) hangs off it, and the stored H / C'
-// feed the next column without a further subtraction.  All comparisons inside a column see the same offset, so maxima,
-// tie-breaking and directions are those of the reference; the true column maximum is (max H) - j.
-// Direction bits: bit 0 = C' beats the diagonal, bit 1 = R' beats both (priority diag > Del > Ins): 0 diag, 1 Del, 2 / 3 Ins.
-// hC/hH: same row, previous column; diag: H of the row above in the previous column; rk/Pprev: running state of this column.
-TG_HD void tg_dpt_cell(const TgDptMem& m, int hC, int hH, int diag, uint32_t wword, int b, int& rk, int& Pprev, int& c_out, int& h_out,
-                       uint32_t& tbits, int& key, int& ubm) {
-  const int c = tg_dpt_addmax(hH, -1, hC);
-  const int d = diag + (int)((wword >> (b & 31)) & 1u) * 2;  // (compiles to shift + mask + add: a predicated add is no cheaper)
-  const int P = tg_dpt_max(d, c);
-  rk = tg_dpt_addmax(rk, -1, Pprev);
-  const int H = tg_dpt_addmax(rk, -2, P);
-  const int f1 = tg_dpt_min(P - d, 1), f2 = tg_dpt_min(H - P, 1);
-  // the integer ALU pipe is the bottleneck of this loop: what can be a multiply-add goes to the FMA pipe (runtime
-  // constants m.one / m.k128 keep ptxas from turning them back into IADD3 / LEA)
-  tbits += (uint32_t)tg_dpt_mad(f2, 2 * m.one, f1) << (2 * (b & 15));
+// One DP cell (src/swg.rs:82-99 / :121-140 + triple_max :226-240).  hC/hDm2: same row, previous column; diag: D - 2 of the
+// row above in the previous column; rr/dvm2: R and D - 2 of the row above in this column.  Updates the running column
+// state and returns the new D - 2.
+TG_HD int tg_dpt_cell(const TgDptMem& m, int hC, int hDm2, int diag, uint32_t match, int b, int& rr, int& dvm2, int& c_out,
+                      uint32_t& tbits, int& key, int& ubm) {
+  const int c = tg_dpt_max(hC - 1, hDm2);
+  const int r_ = tg_dpt_max(rr - 1, dvm2);
+  const int d = diag + (match ? 3 : 1);  // (as multiply-adds on the FMA pipe: tried, same speed -- the loop is not ALU-pipe bound)
+  const int nd = tg_dpt_max3(d, c, r_);
+  // direction: 0 when nd == d, else 1 when nd == c, else 2 (nd >= d and nd >= c, so the differences are >= 0)
+  const int f1 = tg_dpt_min(nd - d, 1), f2 = tg_dpt_min(nd - c, 1);
+  tbits += (uint32_t)(f1 + f1 * f2) << (2 * (b & 15));
   c_out = c;
-  h_out = H;
-  Pprev = P;
-  key = tg_dpt_max(key, tg_dpt_mad(H, m.k128, 127 - b));
-  ubm = tg_dpt_max(ubm, tg_dpt_mad(H, m.one, -b));
+  rr = r_;
+  // the integer ALU pipe is the bottleneck of this loop: plain additions go to the FMA pipe as multiply-adds
+  const int nm2 = tg_dpt_mad(nd, m.one, -2);
+  dvm2 = nm2;
+  key = tg_dpt_max(key, tg_dpt_mad(nd, m.k128, 127 - b));
+  ubm = tg_dpt_max(ubm, nd - b);
+  return nm2;
 }
 
 // Fill.  Returns through `res`; trace in m.tr.  ncols = min(ylen, xlen + bw) >= 1, xlen >= 1.
@@ -202,12 +182,12 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
   constexpr int TW = (2 * WB + 31) / 32;  // trace words per column
   constexpr int NW = (WB + 31) / 32;      // profile words per column
   constexpr int LB = tg_dpt_min_rows(WB); // slots 0 .. LB-1 exist in every column whose band is not clipped by xlen
-  int H[WB + 1], C[WB + 1];               // previous column: D + j and C + j per slot (slot WB: permanent "out of band")
+  int Dm2[WB + 1], C[WB + 1];             // previous column: D - 2 and C per slot (slot WB: permanent "out of band")
   const int two_bw = 2 * bw;
 #pragma unroll
   for (int b = 0; b <= WB; b++) {         // column 0 (src/swg.rs:62-71)
     const bool in0 = b <= two_bw;
-    H[b] = in0 ? (b == 0 ? 0 : -(b + 1)) : TG_DPT_MIN;
+    Dm2[b] = in0 ? (b == 0 ? -2 : -(b + 1) - 2) : TG_DPT_MIN;
     C[b] = b == 0 ? 0 : TG_DPT_MIN;
   }
   int max_score = 0, max_i = 0, max_j = 0;
@@ -226,25 +206,25 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
 #pragma unroll
     for (int k = 0; k < TW; k++) tb[k] = 0;
     // row 0: only the horizontal (deletion) branch exists (d = R = MIN), quirk Q1: C[0] starts at 0
-    int diag = H[0];
-    const int c0 = tg_dpt_addmax(H[0], -1, C[0]);
-    C[0] = c0; H[0] = c0;
+    int diag = Dm2[0];
+    const int c0 = tg_dpt_max(C[0] - 1, Dm2[0]);
+    C[0] = c0; Dm2[0] = c0 - 2;
     tb[0] = 1u;
     int key = c0 * 128 + 127, ubm = c0;
-    int rk = TG_DPT_MIN, Pprev = c0;
+    int rr = TG_DPT_MIN, dvm2 = c0 - 2;
 #pragma unroll
     for (int b = 1; b < WB; b++) {
       if (b >= LB && b > span1) break;
-      const int old = H[b];
-      tg_dpt_cell(m, C[b], old, diag, w[b >> 5], b, rk, Pprev, C[b], H[b], tb[b >> 4], key, ubm);
+      const int old = Dm2[b];
+      Dm2[b] = tg_dpt_cell(m, C[b], old, diag, (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
       diag = old;
     }
 #pragma unroll
     for (int k = 0; k < TW; k++) m.tr[((size_t)(j - 1) * TW + k) * m.tstride] = tb[k];
     cells += (uint32_t)span1 + 1u;
-    const int cm = (key >> 7) - j;
+    const int cm = key >> 7;
     if (cm > max_score) { max_score = cm; max_i = 127 - (key & 127); max_j = j; }
-    if (cm < max_score - x_drop || (bound_stop && ubm - j + xlen <= max_score)) { stopped = true; break; }
+    if (cm < max_score - x_drop || (bound_stop && ubm + xlen <= max_score)) { stopped = true; break; }
   }
   if (!stopped) {
     // ---- phase 2, band not clipped: columns bw+1 .. min(ncols, xlen - bw), rows j-bw .. j+bw, slot = row - (j - bw)
@@ -259,18 +239,18 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
 #pragma unroll
       for (int k = 0; k < TW; k++) tb[k] = 0;
       int key = TG_DPT_MIN * 128, ubm = TG_DPT_MIN;
-      int rk = TG_DPT_MIN, Pprev = TG_DPT_MIN;
+      int rr = TG_DPT_MIN, dvm2 = TG_DPT_MIN;
 #pragma unroll
       for (int b = 0; b < WB; b++) {
         if (b >= LB && b > two_bw) break;
-        tg_dpt_cell(m, C[b + 1], H[b + 1], H[b], w[b >> 5], b, rk, Pprev, C[b], H[b], tb[b >> 4], key, ubm);
+        Dm2[b] = tg_dpt_cell(m, C[b + 1], Dm2[b + 1], Dm2[b], (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
       }
 #pragma unroll
       for (int k = 0; k < TW; k++) m.tr[((size_t)(j - 1) * TW + k) * m.tstride] = tb[k];
       cells += (uint32_t)two_bw + 1u;
-      const int cm = (key >> 7) - j;
+      const int cm = key >> 7;
       if (cm > max_score) { max_score = cm; max_i = lo + 127 - (key & 127); max_j = j; }
-      if (cm < max_score - x_drop || (bound_stop && ubm - j - lo + xlen <= max_score)) { stopped = true; break; }
+      if (cm < max_score - x_drop || (bound_stop && ubm - lo + xlen <= max_score)) { stopped = true; break; }
     }
   }
   if (!stopped) {
@@ -286,18 +266,18 @@ TG_HDN void tg_dpt_fill(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int 
 #pragma unroll
       for (int k = 0; k < TW; k++) tb[k] = 0;
       int key = TG_DPT_MIN * 128, ubm = TG_DPT_MIN;
-      int rk = TG_DPT_MIN, Pprev = TG_DPT_MIN;
+      int rr = TG_DPT_MIN, dvm2 = TG_DPT_MIN;
 #pragma unroll
       for (int b = 0; b < WB; b++) {
         if (b > span) break;
-        tg_dpt_cell(m, C[b + 1], H[b + 1], H[b], w[b >> 5], b, rk, Pprev, C[b], H[b], tb[b >> 4], key, ubm);
+        Dm2[b] = tg_dpt_cell(m, C[b + 1], Dm2[b + 1], Dm2[b], (w[b >> 5] >> (b & 31)) & 1u, b, rr, dvm2, C[b], tb[b >> 4], key, ubm);
       }
 #pragma unroll
       for (int k = 0; k < TW; k++) m.tr[((size_t)(j - 1) * TW + k) * m.tstride] = tb[k];
       cells += (uint32_t)span + 1u;
-      const int cm = (key >> 7) - j;
+      const int cm = key >> 7;
       if (cm > max_score) { max_score = cm; max_i = lo + 127 - (key & 127); max_j = j; }
-      if (cm < max_score - x_drop || (bound_stop && ubm - j - lo + xlen <= max_score)) break;
+      if (cm < max_score - x_drop || (bound_stop && ubm - lo + xlen <= max_score)) break;
     }
   }
   res.score = max_score; res.xend = max_i; res.yend = max_j; res.cells = cells;
@@ -350,7 +330,7 @@ TG_HDN uint32_t tg_dpt_traceback(const TgDptMem& m, TgDptY& ys, int xlen, int bw
     } else if (dir == 1) {
       kind = TG_OP_DEL;
       j--;
-    } else {  // 2 or 3
+    } else {
       kind = TG_OP_INS;
       i--;
     }

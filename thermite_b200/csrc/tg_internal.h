@@ -101,6 +101,30 @@ struct tg_index_host {
   std::vector<uint32_t> tx_gene, tx_strand;
 };
 
+// compact record -> wide record (include/thermite_gpu.h: tg_aln_c); false when an index is out of range
+inline bool tg_expand_one(const TgRef* refs, uint32_t n_refs, const uint64_t* tx_seq_off, uint32_t n_txs, const tg_aln_c& c,
+                              uint32_t read_len, tg_aln& a) {
+  if (c.ref_id >= n_refs) return false;
+  const TgRef& r = refs[c.ref_id];
+  a.ystart = c.ystart; a.yend = c.yend; a.ylen = r.len;
+  a.score = c.score; a.ref_id = c.ref_id;
+  a.xstart = c.xstart; a.xend = c.xend; a.xlen = read_len;
+  a.tx_or_gene_idx = c.tx_or_gene_idx;
+  a.ops_off = c.ops_off; a.ops_len = c.ops_len;
+  a.aln_type = c.aln_type; a.primary = c.primary; a.strand = (uint8_t)(r.strand_rank & 1u); a.pad = 0;
+  if (c.aln_type == TG_ALN_EXONIC) {
+    if (c.tx_or_gene_idx >= n_txs) return false;
+    a.tx_ystart = c.tx_ystart; a.tx_yend = c.tx_yend;
+    a.tx_ylen = tx_seq_off[c.tx_or_gene_idx + 1] - tx_seq_off[c.tx_or_gene_idx];
+    a.tx_score = c.score; a.tx_xstart = c.xstart; a.tx_xend = c.xend;
+    a.tx_ops_off = c.ops_off + c.ops_len; a.tx_ops_len = c.tx_ops_len;
+  } else {
+    a.tx_ystart = 0; a.tx_yend = 0; a.tx_ylen = 0; a.tx_score = 0; a.tx_xstart = 0; a.tx_xend = 0;
+    a.tx_ops_off = 0; a.tx_ops_len = 0;
+  }
+  return true;
+}
+
 void tg_set_error(const std::string& msg);
 tg_status tg_fail(tg_status code, const std::string& msg);
 

@@ -90,12 +90,15 @@ struct tg_multi {
   int job_kind = 0;                    // 0: align shard, 1: create context
   const uint8_t* bases = nullptr;
   const uint64_t* offs = nullptr;
-  // result buffers (pinned, portable: every device copies into them)
-  uint32_t* first = nullptr;
-  uint32_t* count = nullptr;
-  tg_aln_c* alns = nullptr;
-  uint32_t* ops = nullptr;
-  size_t cap_first = 0, cap_count = 0, cap_alns = 0, cap_ops = 0;
+  // result buffers (pinned, portable: every device copies into them); two sets when tg_multi_set_result_buffers(m, 2)
+  struct ResultSet {
+    uint32_t* first = nullptr;
+    uint32_t* count = nullptr;
+    tg_aln_c* alns = nullptr;
+    uint32_t* ops = nullptr;
+    size_t cap_first = 0, cap_count = 0, cap_alns = 0, cap_ops = 0;
+  } rs[2];
+  int result_sets = 1, cur = 0;
   double rate_alns = 1.25, rate_ops = 8.0;  // records / operation words per read expected in the next batch
 };
 
@@ -254,10 +257,12 @@ void tg_multi_destroy(tg_multi* m) {
     if (ix) tg_index_destroy(ix);
   for (size_t d = 0; d < m->owned_blob.size(); d++)
     if (m->owned_blob[d]) { cudaSetDevice(m->distinct[d]); cudaFree(m->owned_blob[d]); }
-  if (m->first) cudaFreeHost(m->first);
-  if (m->count) cudaFreeHost(m->count);
-  if (m->alns) cudaFreeHost(m->alns);
-  if (m->ops) cudaFreeHost(m->ops);
+  for (auto& r : m->rs) {
+    if (r.first) cudaFreeHost(r.first);
+    if (r.count) cudaFreeHost(r.count);
+    if (r.alns) cudaFreeHost(r.alns);
+    if (r.ops) cudaFreeHost(r.ops);
+  }
   delete m;
 }
 
@@ -289,6 +294,12 @@ tg_status tg_multi_create(const tg_index_host* ix, const int* devices, int n_dev
 
 int tg_multi_n_devices(const tg_multi* m) { return m ? (int)m->w.size() : 0; }
 
+tg_status tg_multi_set_result_buffers(tg_multi* m, int n) {
+  if (!m || (n != 1 && n != 2)) return tg_fail(TG_ERR_INVALID, "result buffers: 1 or 2");
+  m->result_sets = n;
+  return TG_OK;
+}
+
 const char* tg_multi_replication(const tg_multi* m, float* ms) {
   if (ms) *ms = m ? m->bcast_ms : 0.f;
   return m ? m->replication.c_str() : "";
@@ -314,8 +325,10 @@ tg_status tg_multi_align_batch(tg_multi* m, const uint8_t* bases, const uint64_t
   if (!bases && offs[n_reads] > offs[0]) return tg_fail(TG_ERR_INVALID, "null argument");
   const int G = (int)m->w.size();
   tg_status st;
-  if ((st = grow_pinned(m->first, m->cap_first, (size_t)n_reads)) != TG_OK) return st;
-  if ((st = grow_pinned(m->count, m->cap_count, (size_t)n_reads)) != TG_OK) return st;
+  if (m->result_sets == 2) m->cur ^= 1;  // the previous call's result stays valid during this one
+  tg_multi::ResultSet& R = m->rs[m->cur];
+  if ((st = grow_pinned(R.first, R.cap_first, (size_t)n_reads)) != TG_OK) return st;
+  if ((st = grow_pinned(R.count, R.cap_count, (size_t)n_reads)) != TG_OK) return st;
   m->bases = bases; m->offs = offs;
   std::vector<uint64_t> need_a(G, 0), need_o(G, 0);  // exact needs reported by a failed attempt
   for (int attempt = 0;; attempt++) {
@@ -333,12 +346,12 @@ tg_status tg_multi_align_batch(tg_multi* m, const uint8_t* bases, const uint64_t
     }
     if (a_base > 0xFFFFFFFFull || o_base > 0xFFFFFFFFull)
       return tg_fail(TG_ERR_CAPACITY, "batch too large for 32-bit record / operation offsets: split the batch");
-    if ((st = grow_pinned(m->alns, m->cap_alns, (size_t)a_base)) != TG_OK) return st;
-    if ((st = grow_pinned(m->ops, m->cap_ops, (size_t)o_base)) != TG_OK) return st;
+    if ((st = grow_pinned(R.alns, R.cap_alns, (size_t)a_base)) != TG_OK) return st;
+    if ((st = grow_pinned(R.ops, R.cap_ops, (size_t)o_base)) != TG_OK) return st;
     for (int g = 0; g < G; g++) {
       Worker& w = m->w[g];
-      w.seg.first = m->first + w.lo; w.seg.count = m->count + w.lo;
-      w.seg.alns = m->alns + ab[g]; w.seg.ops = m->ops + ob[g];
+      w.seg.first = R.first + w.lo; w.seg.count = R.count + w.lo;
+      w.seg.alns = R.alns + ab[g]; w.seg.ops = R.ops + ob[g];
       w.seg.alns_cap = ac[g]; w.seg.ops_cap = oc[g];
       w.seg.first_base = ab[g]; w.seg.ops_base = ob[g];
     }
@@ -371,8 +384,8 @@ tg_status tg_multi_align_batch(tg_multi* m, const uint8_t* bases, const uint64_t
     }
     if (attempt >= 3) return tg_fail(TG_ERR_CAPACITY, "result segments kept overflowing");
   }
-  out->read_aln_first = m->first; out->read_aln_count = m->count;
-  out->alns = m->alns; out->ops = m->ops;
+  out->read_aln_first = R.first; out->read_aln_count = R.count;
+  out->alns = R.alns; out->ops = R.ops;
   return TG_OK;
   TG_GUARD_END
 }

@@ -281,24 +281,51 @@ __global__ void __launch_bounds__(256) k_pack_reads(SeedParams p) {
 __device__ __forceinline__ void probe_push(unsigned long long* ctr, uint64_t* queue, uint32_t r, uint32_t q) {
   queue[warp_agg_add(ctr, 1ull)] = ((uint64_t)r << 16) | q;
 }
-__global__ void __launch_bounds__(256) k_probe_light(SeedParams p) {
-  const uint32_t qn = p.wave == 0 ? 1u : p.wave == 1 ? (p.max_q + TG_PROBE_STRIDE - 1) / TG_PROBE_STRIDE : p.max_q - 1;
-  const unsigned long long total = (unsigned long long)p.n_reads * qn;
+// wave 2, step 1: one thread per (read, bracket of TG_PROBE_STRIDE offsets).  A bracket whose two samples ended at the same
+// place pins every E in between (closed: nothing to do, the usual case); the interior offsets of an open bracket are queued.
+// (The first version gave every interior offset of every read its own thread, 7 of 8 of which only re-read the two samples
+// and left: 284 M threads and 2.1 kB of table traffic per read for a 4 M-read batch.)
+__global__ void __launch_bounds__(256) k_probe_brackets(SeedParams p) {
+  const uint32_t nb = (p.max_q + TG_PROBE_STRIDE - 1) / TG_PROBE_STRIDE;
+  const unsigned long long total = (unsigned long long)p.n_reads * nb;
   for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint32_t r = (uint32_t)(t / qn), j = (uint32_t)(t % qn);
+    const uint32_t r = (uint32_t)(t / nb), j = (uint32_t)(t % nb);
     const uint32_t L = (uint32_t)(p.offs[r + 1] - p.offs[r]);
     if (L < p.k) continue;
-    const uint32_t q_last = L - p.k;
-    TgSeedHit* row = p.hits + (size_t)r * p.max_q;
-    uint32_t q = 0;
-    if (p.wave > 0) {
-      if (row[0].e == L) continue;  // read[0..L) occurs: E(q) = L for every q, no other SMEM
+    const uint32_t q_last = L - p.k, qa = j * TG_PROBE_STRIDE;
+    if (qa >= q_last) continue;
+    const TgSeedHit* row = p.hits + (size_t)r * p.max_q;
+    if (row[0].e == L) continue;  // read[0..L) occurs: E(q) = L for every q, no other SMEM
+    const uint32_t qb = qa + TG_PROBE_STRIDE < q_last ? qa + TG_PROBE_STRIDE : q_last;
+    if (qb - qa < 2) continue;
+    const uint32_t ea = row[qa].e, eb = row[qb].e;
+    if (ea == eb && ea != 0) continue;  // tg_probe_bracketed
+    const unsigned long long base = warp_agg_add(&p.ctr->probe_n[2][0], (unsigned long long)(qb - qa - 1));
+    for (uint32_t q = qa + 1; q < qb; q++) p.queue[base + (q - qa - 1)] = ((uint64_t)r << 16) | q;
+  }
+}
+__global__ void __launch_bounds__(256) k_probe_light(SeedParams p) {
+  const uint32_t qn = p.wave == 0 ? 1u : (p.max_q + TG_PROBE_STRIDE - 1) / TG_PROBE_STRIDE;
+  const unsigned long long total = p.wave == 2 ? p.ctr->probe_n[2][0] : (unsigned long long)p.n_reads * qn;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+    uint32_t r, q = 0, L;
+    TgSeedHit* row;
+    if (p.wave == 2) {  // step 2: one thread per queued offset
+      const uint64_t e = p.queue[t];
+      r = (uint32_t)(e >> 16); q = (uint32_t)(e & 0xFFFFu);
+      L = (uint32_t)(p.offs[r + 1] - p.offs[r]);
+      row = p.hits + (size_t)r * p.max_q;
+    } else {
+      r = (uint32_t)(t / qn);
+      const uint32_t j = (uint32_t)(t % qn);
+      L = (uint32_t)(p.offs[r + 1] - p.offs[r]);
+      if (L < p.k) continue;
+      const uint32_t q_last = L - p.k;
+      row = p.hits + (size_t)r * p.max_q;
       if (p.wave == 1) {
+        if (row[0].e == L) continue;  // read[0..L) occurs: E(q) = L for every q, no other SMEM
         q = tg_probe_sample(j, q_last);
         if (q == 0xFFFFFFFFu) continue;
-      } else {
-        q = j + 1;
-        if (q > q_last || tg_probe_is_sample(q, q_last) || tg_probe_bracketed(row, q, q_last)) continue;
       }
     }
     TgSeedHit h;
@@ -1182,6 +1209,8 @@ struct tg_ctx {
   uint64_t n_launches = 0;  // kernels launched by the last batch call
   // host results
   PinBuf h_first, h_count, h_alns, h_ops, h_seeds, h_seed_first, h_seed_count;
+  PinBuf h2_first, h2_count, h2_alns, h2_ops;  // second result set (tg_ctx_set_result_buffers(ctx, 2)): swapped in before every call
+  int result_sets = 1;
   // where the records of the current host-buffer call go: the context's own pinned buffers (grown on demand) or a
   // segment of a caller-owned result (tg_multi_align_batch: fixed capacity, the call reports what it needs instead)
   struct HostOut {
@@ -1305,7 +1334,8 @@ void tg_ctx_destroy(tg_ctx* c) {
                     &c->d_aln_first, &c->d_aln_count, &c->d_alns, &c->d_ops, &c->s_x, &c->s_xo, &c->s_y, &c->s_yo, &c->s_bw,
                     &c->s_xd, &c->s_score, &c->s_xe, &c->s_ye, &c->s_toff, &c->s_tlen, &c->s_ops, &c->s_ypk, &c->s_ysym})
     b->release();
-  for (PinBuf* b : {&c->h_first, &c->h_count, &c->h_alns, &c->h_ops, &c->h_seeds, &c->h_seed_first, &c->h_seed_count, &c->h_late}) b->release();
+  for (PinBuf* b : {&c->h_first, &c->h_count, &c->h_alns, &c->h_ops, &c->h_seeds, &c->h_seed_first, &c->h_seed_count, &c->h_late,
+                    &c->h2_first, &c->h2_count, &c->h2_alns, &c->h2_ops}) b->release();
   if (c->slots) cudaFree(c->slots);
   if (c->d_ctr) cudaFree(c->d_ctr);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -1397,6 +1427,11 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
   TG_GUARD_END
 }
 
+tg_status tg_ctx_set_result_buffers(tg_ctx* ctx, int n) {
+  if (!ctx || (n != 1 && n != 2)) return tg_fail(TG_ERR_INVALID, "result buffers: 1 or 2");
+  ctx->result_sets = n;
+  return TG_OK;
+}
 void tg_ctx_set_chunk_reads(tg_ctx* ctx, uint32_t reads) {
   if (ctx) ctx->chunk_reads = reads == 0 ? 0 : (reads < 1024 ? 1024 : reads);
 }
@@ -1518,12 +1553,14 @@ tg_status launch_seed(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_offs,
   p.out.flags = &c->d_ctr->flags; p.out.n_smems = &c->d_ctr->n_smems;
   p.ctr = c->d_ctr;
   if ((st = c->d_queue2.ensure((size_t)nk * p.max_q * 8 + 64)) != TG_OK) return st;
-  p.queue = nullptr; p.queue2 = (uint64_t*)c->d_queue2.p;
+  if ((st = c->d_queue.ensure((size_t)nk * p.max_q * 8 + 64)) != TG_OK) return st;
+  p.queue = (uint64_t*)c->d_queue.p; p.queue2 = (uint64_t*)c->d_queue2.p;
   const int grid = c->n_sms * 8;
   k_pack_reads<<<grid, 256, 0, c->stream>>>(p);
   for (int wave = 0; wave < (p.max_q > 1 ? 3 : 1); wave++) {
     p.wave = wave;
     if (r0 != 0) CU_CHECK(cudaMemsetAsync(&c->d_ctr->probe_n[wave][0], 0, 16, c->stream));  // a later chunk of the batch
+    if (wave == 2) { k_probe_brackets<<<grid, 256, 0, c->stream>>>(p); c->n_launches++; }
     k_probe_light<<<grid, 256, 0, c->stream>>>(p);
     k_probe_heavy<<<grid, 256, 0, c->stream>>>(p);
     c->n_launches += 2;
@@ -1930,6 +1967,10 @@ static tg_status align_host(tg_ctx* c, const uint8_t* bases, const uint64_t* off
   c->compact = compact ? 1 : 0;
   c->first_base = first_base; c->ops_base = ops_base;
   c->ho_overflow = false; c->need_alns = 0; c->need_ops = 0;
+  if (c->result_sets == 2 && !ext) {  // the previous call's result stays where it is; this call fills the other set
+    std::swap(c->h_first, c->h2_first); std::swap(c->h_count, c->h2_count);
+    std::swap(c->h_alns, c->h2_alns); std::swap(c->h_ops, c->h2_ops);
+  }
   // Copies overlap kernels at both ends of the call (three streams): the bases arrive in chunks and every chunk is
   // seeded as soon as it has landed; the records of the reads that are finished after round 1 (~98 %) travel to the
   // host while the late rounds run.  One pass over the whole batch, one contiguous result.
