@@ -206,118 +206,53 @@ void run_lanes(int lanes, F&& f) {
   for (auto& t : th) t.join();
 }
 
-// ---- tg_dpt.h on the host: one "thread" (a pair of extensions), strides of 1 -----------------------------------------
+// ---- tg_dpt.h on the host: one "thread", strides of 1 --------------------------------------------------------------
 struct DptScratch {
   std::vector<uint32_t> msk, tr;
-  DptScratch() : msk(64, 0), tr((size_t)(TG_DPT_MAX_X + 2 * TG_MAX_READ_LEN + 2) * tg_dpt_twp(TG_DPT_MAX_WB), 0) {}
-  TgDptMem mem() { return TgDptMem{msk.data(), 1, tr.data(), 1}; }
-};
-struct DptHalf {  // one extension of a pair: y stream, columns, x-drop; results
-  TgDptY ys;
-  int ncols, x_drop;
-  std::vector<uint32_t> ops;
-};
-struct DptHalfX {  // where the shortcut finds x: packed sequence, offset, side
-  const uint64_t* xseq = nullptr;
-  uint32_t xoff = 0;
-  int side = 0;
-  uint64_t y0 = 0;
+  DptScratch() : msk(32, 0), tr((size_t)(TG_DPT_MAX_X + 2 * TG_MAX_READ_LEN + 2) * 5, 0) {}
+  TgDptMem mem() { return TgDptMem{msk.data(), 1, tr.data(), 1, 1, 128}; }
 };
 template <int WB>
-void dpt_two(const TgDptMem& m, DptHalf& A, DptHalf& B, const DptHalfX& XA, const DptHalfX& XB, int xlen, int bw, bool bound_stop,
-             TgDpt2Result& res) {
-  tg_dpt2_fill<WB>(m, A.ys, B.ys, xlen, bw, A.ncols, B.ncols, A.x_drop, B.x_drop, bound_stop, res);
-  // operations the way dpt_pair (thermite_gpu.cu) produces them: gapless shortcut where it applies, else traceback
-  bool diag[2];
-  uint64_t lo[2], hi[2];
-  for (int h = 0; h < 2; h++) {
-    const DptHalfX& X = h == 0 ? XA : XB;
-    DptHalf& H = h == 0 ? A : B;
-    diag[h] = tg_dpt_diag_mask(X.xseq, X.xoff, xlen, X.side, H.ys.seq, X.y0, res.xend[h], res.yend[h], res.score[h], lo[h], hi[h]);
-    if (diag[h]) {
-      const uint32_t n = tg_dpt_diag_emit(lo[h], hi[h], res.xend[h], xlen, h, [](int, uint32_t, uint32_t, uint32_t) {});
-      H.ops.assign(n, 0);
-      tg_dpt_diag_emit(lo[h], hi[h], res.xend[h], xlen, h, [&](int, uint32_t i, uint32_t kind, uint32_t run) { H.ops[i] = kind | (run << 3); });
-    }
-  }
-  if (!diag[0] || !diag[1]) {
-    uint32_t nA = 0, nB = 0;
-    tg_dpt2_traceback<WB>(m, A.ys, B.ys, xlen, bw, res, !diag[0], !diag[1], nA, nB, [](int, uint32_t, uint32_t, uint32_t) {});
-    if (!diag[0]) A.ops.assign(nA, 0);
-    if (!diag[1]) B.ops.assign(nB, 0);
-    tg_dpt2_traceback<WB>(m, A.ys, B.ys, xlen, bw, res, !diag[0], !diag[1], nA, nB,
-                          [&](int h, uint32_t i, uint32_t kind, uint32_t run) { (h == 0 ? A : B).ops[i] = kind | (run << 3); });
-  }
+void dpt_one(const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int bw, int x_drop, bool bound_stop, TgDptResult& res,
+             std::vector<uint32_t>& ops) {
+  tg_dpt_fill<WB>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res);
+  uint32_t n = tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [](uint32_t, uint32_t, uint32_t) {});
+  ops.assign(n, 0);
+  tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [&](uint32_t i, uint32_t kind, uint32_t run) { ops[i] = kind | (run << 3); });
 }
-void dpt_dispatch(int cls, const TgDptMem& m, DptHalf& A, DptHalf& B, const DptHalfX& XA, const DptHalfX& XB, int xlen, int bw,
-                  bool bound_stop, TgDpt2Result& res) {
+void dpt_dispatch(int cls, const TgDptMem& m, TgDptY& ys, int xlen, int ncols, int bw, int x_drop, bool bound_stop,
+                  TgDptResult& res, std::vector<uint32_t>& ops) {
   switch (cls) {
-    case 1: dpt_two<4>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    case 2: dpt_two<8>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    case 3: dpt_two<16>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    case 4: dpt_two<24>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    case 5: dpt_two<32>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    case 6: dpt_two<40>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    case 7: dpt_two<48>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    case 8: dpt_two<56>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    case 9: dpt_two<64>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    case 10: dpt_two<72>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
-    default: dpt_two<80>(m, A, B, XA, XB, xlen, bw, bound_stop, res); break;
+    case 1: dpt_one<4>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 2: dpt_one<8>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 3: dpt_one<16>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 4: dpt_one<24>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 5: dpt_one<32>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 6: dpt_one<40>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 7: dpt_one<48>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 8: dpt_one<56>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 9: dpt_one<64>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    case 10: dpt_one<72>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
+    default: dpt_one<80>(m, ys, xlen, ncols, bw, x_drop, bound_stop, res, ops); break;
   }
 }
-// Round tasks the way k_round_dpt runs them: sorted by (class, tg_dpt_subkey), neighbours with equal (xlen, band width)
-// share a "thread", the others run paired with themselves.  Tasks of class 0 are left alone (returned as not done).
-void dpt_tasks_host(const TgIndexDev& ix, const uint64_t* rp_base, uint32_t rp_words, TgTask* tasks, size_t n_tasks, bool bound_stop,
-                    uint32_t* ops_pool, unsigned long long* ops_ctr, std::vector<uint8_t>& done) {
-  done.assign(n_tasks, 0);
-  std::vector<std::pair<uint32_t, uint32_t>> order;  // (bin, task)
-  for (size_t t = 0; t < n_tasks; t++) {
-    const int cls = tg_dpt_class((int)tasks[t].xlen, (int)tasks[t].bw, tasks[t].x_drop);
-    if (cls == 0) continue;
-    order.emplace_back((uint32_t)cls * TG_DPT_CBINS + tg_dpt_subkey((int)tasks[t].xlen, (int)tasks[t].bw), (uint32_t)t);
-  }
-  std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-  DptScratch sc;
-  auto run = [&](uint32_t i0, uint32_t i1, bool commit1) {
-    TgTask& t0 = tasks[i0];
-    TgTask& t1 = tasks[i1];
-    const int xlen = (int)t0.xlen, bw = (int)t0.bw;
-    const int nc0 = (int)t0.ylen < xlen + bw ? (int)t0.ylen : xlen + bw, nc1 = (int)t1.ylen < xlen + bw ? (int)t1.ylen : xlen + bw;
-    TgDptMem m = sc.mem();
-    DptHalf A, B;
-    A.ys.init(tg_seq_of(ix, t0.seqsel), t0.y0, nc0, (int)t0.side); A.ncols = nc0; A.x_drop = t0.x_drop;
-    B.ys.init(tg_seq_of(ix, t1.seqsel), t1.y0, nc1, (int)t1.side); B.ncols = nc1; B.x_drop = t1.x_drop;
-    tg_dpt_profile(m, 0, rp_base + (size_t)t0.read * rp_words, t0.xoff, xlen, t0.side);
-    tg_dpt_profile(m, 1, rp_base + (size_t)t1.read * rp_words, t1.xoff, xlen, t1.side);
-    TgDpt2Result res;
-    DptHalfX XA, XB;
-    XA.xseq = rp_base + (size_t)t0.read * rp_words; XA.xoff = t0.xoff; XA.side = (int)t0.side; XA.y0 = t0.y0;
-    XB.xseq = rp_base + (size_t)t1.read * rp_words; XB.xoff = t1.xoff; XB.side = (int)t1.side; XB.y0 = t1.y0;
-    dpt_dispatch(tg_dpt_class(xlen, bw, t0.x_drop), m, A, B, XA, XB, xlen, bw, bound_stop, res);
-    for (int h = 0; h < (commit1 ? 2 : 1); h++) {
-      TgTask& t = h == 0 ? t0 : t1;
-      const std::vector<uint32_t>& ops = h == 0 ? A.ops : B.ops;
-      t.score = res.score[h]; t.xend = (uint32_t)res.xend[h]; t.yend = (uint32_t)res.yend[h]; t.cells = res.cells[h];
-      t.ops_off = (uint32_t)*ops_ctr; t.ops_n = (uint32_t)ops.size();
-      for (uint32_t w : ops) ops_pool[(*ops_ctr)++] = w;
-      done[&t - tasks] = 1;
-    }
-  };
-  for (size_t k = 0; k < order.size();) {
-    // entries of one bin in pairs, the odd one alone -- the padded layout k_round_binscan builds
-    size_t e = k;
-    while (e < order.size() && order[e].first == order[k].first) e++;
-    for (size_t u = k; u < e; u += 2) {
-      const uint32_t ia = order[u].second;
-      if (u + 1 < e) {
-        const uint32_t ib = order[u + 1].second;
-        const bool compat = tasks[ia].xlen == tasks[ib].xlen && tasks[ia].bw == tasks[ib].bw;
-        if (compat) run(ia, ib, true);
-        else { run(ia, ia, false); run(ib, ib, false); }
-      } else run(ia, ia, false);
-    }
-    k = e;
-  }
+// one round task the way k_round_dpt runs it; false when the task is not eligible (class 0)
+bool dpt_task_host(const TgIndexDev& ix, const uint64_t* rp, TgTask& t, DptScratch& sc, bool bound_stop, uint32_t* ops_pool,
+                   unsigned long long* ops_ctr) {
+  const int xlen = (int)t.xlen, bw = (int)t.bw, ylen = (int)t.ylen;
+  const int cls = tg_dpt_class(xlen, bw, t.x_drop);
+  if (cls == 0) return false;
+  const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
+  TgDptMem m = sc.mem();
+  TgDptY ys{tg_seq_of(ix, t.seqsel), t.y0, ncols, (int)t.side, 0, 0, 0, 0, -1};
+  tg_dpt_profile(m, rp, t.xoff, xlen, t.side);
+  TgDptResult res{0, 0, 0, 0};
+  std::vector<uint32_t> ops;
+  dpt_dispatch(cls, m, ys, xlen, ncols, bw, t.x_drop, bound_stop, res, ops);
+  t.score = res.score; t.xend = (uint32_t)res.xend; t.yend = (uint32_t)res.yend; t.cells = res.cells;
+  t.ops_off = (uint32_t)*ops_ctr; t.ops_n = (uint32_t)ops.size();
+  for (uint32_t w : ops) ops_pool[(*ops_ctr)++] = w;
+  return true;
 }
 
 }  // namespace
@@ -522,10 +457,10 @@ void* ht_align_batch_mode(void* cp, const uint8_t* bases, const uint64_t* offs, 
           ires[it].flags = TG_IF_FAIL;
       }
       dp_ops.assign((size_t)tctr * (2 * maxL + 64) + 64, 0);
-      std::vector<uint8_t> dpt_done(tctr, 0);
-      if (rounds == 2) dpt_tasks_host(c->dev, rp.data(), rp_words, tasks.data(), (size_t)tctr, wm.bound_stop, dp_ops.data(), &octr, dpt_done);
+      DptScratch dsc;
       for (unsigned long long t = 0; t < tctr; t++) {  // extend
-        if (dpt_done[t]) continue;
+        if (rounds == 2 && dpt_task_host(c->dev, rp.data() + (size_t)tasks[t].read * rp_words, tasks[t], dsc, wm.bound_stop, dp_ops.data(), &octr))
+          continue;
         run_lanes(lanes, [&](auto& w) {
           tg_task_run(w, c->dev, bases, offs, tasks[t], wm.xs, wm.ys, wm.trace, wm.opsT, dp_ops.data(), &octr, dp_ops.size(),
                       &res->flags, wm.bound_stop);
@@ -598,66 +533,6 @@ long long ht_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uin
                               uint32_t* xend, uint32_t* yend, uint64_t* ops_off, uint32_t* ops, uint64_t ops_cap,
                               uint64_t* cells_out) {
   unsigned long long total = 0, cells = 0;
-  // lanes == 0: the thread-per-pair code of tg_dpt.h.  Like the device, sort the eligible pairs by (class, sub-key) and
-  // let neighbours with the same (xlen, band width) share a "thread"; the rest runs paired with itself.
-  struct DptOut { bool done = false; int32_t score = 0; uint32_t xend = 0, yend = 0, cells = 0; std::vector<uint32_t> ops; };
-  std::vector<DptOut> dpt_res;
-  if (lanes == 0) {
-    dpt_res.resize(n);
-    std::vector<std::pair<uint32_t, uint32_t>> order;
-    for (uint32_t t = 0; t < n; t++) {
-      const int xlen = (int)(xoff[t + 1] - xoff[t]), ylen = (int)(yoff[t + 1] - yoff[t]);
-      if (xlen > (int)TG_MAX_READ_LEN || x_drop[t] < (int32_t)bw[t]) return -1;
-      const int dcls = tg_dpt_class(xlen, (int)bw[t], x_drop[t]);
-      if (dcls > 0 && xlen > 0 && ylen > 0) order.emplace_back((uint32_t)dcls * TG_DPT_CBINS + tg_dpt_subkey(xlen, (int)bw[t]), t);
-    }
-    std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-    DptScratch dsc;
-    auto run = [&](uint32_t t0, uint32_t t1, bool commit1) {
-      const uint32_t tt[2] = {t0, t1};
-      const int xlen = (int)(xoff[t0 + 1] - xoff[t0]), bwv = (int)bw[t0];
-      TgDptMem m = dsc.mem();
-      DptHalf H[2];
-      DptHalfX HX[2];
-      std::vector<uint64_t> ypk[2], xpk[2];
-      for (int h = 0; h < 2; h++) {
-        const uint32_t t = tt[h];
-        const int ylen = (int)(yoff[t + 1] - yoff[t]);
-        const int ncols = ylen < xlen + bwv ? ylen : xlen + bwv;
-        // pack y as 4-bit codes (ACGNT only), profile from x codes
-        ypk[h].assign((size_t)ylen / 16 + 4, 0);
-        for (int i = 0; i < ylen; i++) ypk[h][i >> 4] |= (uint64_t)tg_ascii_code(ys[yoff[t] + i]) << ((15 - (i & 15)) * 4);
-        std::vector<uint8_t> xc(xlen);
-        for (int i = 0; i < xlen; i++) xc[i] = (uint8_t)tg_ascii_code(xs[xoff[t] + i]);
-        tg_dpt_profile_codes(m, h, xc.data(), xlen);
-        xpk[h].assign((size_t)xlen / 16 + 4, 0);
-        for (int i = 0; i < 16 * ((xlen + 15) / 16); i++) xpk[h][i >> 4] |= (uint64_t)(i < xlen ? xc[i] : (uint8_t)TG_C_PAD) << ((15 - (i & 15)) * 4);
-        HX[h].xseq = xpk[h].data(); HX[h].xoff = 0; HX[h].side = 0; HX[h].y0 = 0;
-        H[h].ys.init(ypk[h].data(), 0, ncols, 0); H[h].ncols = ncols; H[h].x_drop = x_drop[t];
-      }
-      TgDpt2Result dr;
-      dpt_dispatch(tg_dpt_class(xlen, bwv, x_drop[t0]), m, H[0], H[1], HX[0], HX[1], xlen, bwv, bound_stop != 0, dr);
-      for (int h = 0; h < (commit1 ? 2 : 1); h++) {
-        DptOut& d = dpt_res[tt[h]];
-        d.done = true; d.score = dr.score[h]; d.xend = (uint32_t)dr.xend[h]; d.yend = (uint32_t)dr.yend[h]; d.cells = dr.cells[h];
-        d.ops = H[h].ops;
-      }
-    };
-    for (size_t k = 0; k < order.size();) {
-      size_t e = k;
-      while (e < order.size() && order[e].first == order[k].first) e++;
-      for (size_t u = k; u < e; u += 2) {
-        const uint32_t ia = order[u].second;
-        if (u + 1 < e) {
-          const uint32_t ib = order[u + 1].second;
-          const bool compat = xoff[ia + 1] - xoff[ia] == xoff[ib + 1] - xoff[ib] && bw[ia] == bw[ib];
-          if (compat) run(ia, ib, true);
-          else { run(ia, ia, false); run(ib, ib, false); }
-        } else run(ia, ia, false);
-      }
-      k = e;
-    }
-  }
   for (uint32_t t = 0; t < n; t++) {
     int xlen = (int)(xoff[t + 1] - xoff[t]), ylen = (int)(yoff[t + 1] - yoff[t]);
     if (xlen > (int)TG_MAX_READ_LEN || x_drop[t] < (int32_t)bw[t]) return -1;
@@ -668,13 +543,25 @@ long long ht_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uin
     TgSwgResult res{0, 0, 0};
     std::vector<unsigned long long> lc(32, 0), le(32, 0);
     int ylen_c = ylen > xlen + (int)bw[t] ? xlen + (int)bw[t] + 1 : ylen;
-    if (t < dpt_res.size() && dpt_res[t].done) {
-      const DptOut& d = dpt_res[t];
-      cells += d.cells;
-      score[t] = d.score; xend[t] = d.xend; yend[t] = d.yend;
+    const int dcls = tg_dpt_class(xlen, (int)bw[t], x_drop[t]);
+    if (lanes == 0 && dcls > 0 && xlen > 0 && ylen > 0) {
+      // pack y as 4-bit codes (ACGNT only), profile from x codes
+      std::vector<uint64_t> ypk((size_t)ylen / 16 + 4, 0);
+      for (int i = 0; i < ylen; i++) ypk[i >> 4] |= (uint64_t)tg_ascii_code(ys[yoff[t] + i]) << ((15 - (i & 15)) * 4);
+      std::vector<uint8_t> xc(xlen);
+      for (int i = 0; i < xlen; i++) xc[i] = (uint8_t)tg_ascii_code(xs[xoff[t] + i]);
+      DptScratch dsc;
+      TgDptMem m = dsc.mem();
+      tg_dpt_profile_codes(m, xc.data(), xlen);
+      TgDptY yy{ypk.data(), 0, ncols, 0, 0, 0, 0, 0, -1};
+      TgDptResult dr{0, 0, 0, 0};
+      std::vector<uint32_t> dops;
+      dpt_dispatch(dcls, m, yy, xlen, ncols, (int)bw[t], x_drop[t], bound_stop != 0, dr, dops);
+      cells += dr.cells;
+      score[t] = dr.score; xend[t] = (uint32_t)dr.xend; yend[t] = (uint32_t)dr.yend;
       ops_off[t] = total;
-      for (uint32_t i = (uint32_t)d.ops.size(); i-- > 0;) {
-        if (total < ops_cap) ops[total] = d.ops[i];
+      for (uint32_t i = (uint32_t)dops.size(); i-- > 0;) {
+        if (total < ops_cap) ops[total] = dops[i];
         total++;
       }
       continue;

@@ -8,7 +8,7 @@
 //   k_round_{init,plan,prep,hist,binscan,scatter,post,scan,final}
 //                                     align_read / align_seed_hit (src/aligner.rs:123-449, src/txome.rs:82-160) as the
 //                                     speculative round pipeline of tg_rounds.h: thread per read / per hit
-//   k_round_dpt<1..11>                SwgExtend::extend / trace (src/swg.rs:31-207): thread per PAIR of extensions, band in
+//   k_round_dpt<0..3>                 SwgExtend::extend / trace (src/swg.rs:31-207): thread per extension, band in
 //                                     registers (tg_dpt.h), one kernel per group of band classes.  INT-pipe bound
 //   k_round_dp<R>, k_swg_batch<R>     the same on the warp-cooperative wavefront (tg_core.h): long reads, very wide
 //                                     bands, raw-byte pairs of tg_swg_extend_batch
@@ -169,7 +169,8 @@ struct DevThread {
   }
 };
 
-#define TG_DPT_NBINS (TG_DPT_NCLS * TG_DPT_CBINS)  // per class: tg_dpt_subkey (tg_dpt.h)
+#define TG_DPT_CBINS 512  // per class: 32 band-width bins x 16 column-count bins
+#define TG_DPT_NBINS (TG_DPT_NCLS * TG_DPT_CBINS)
 struct DevCounters {
   unsigned long long seed_used, n_smems, alns_used, ops_used, cells, n_ext, hits, work_seed, work_ext, swg_ops_used,
       work_swg, kmer_groups;
@@ -183,12 +184,11 @@ struct DevCounters {
   unsigned long long n_late;  // reads finalised by the LAST pass (their first/count reach the host as a fix-up list)
   unsigned long long round_end[TG_MAX_ROUNDS];  // items_used after round r
   unsigned long long round_active[TG_MAX_ROUNDS];  // reads still unfinished after round r
-  unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS][TG_DPT_NCLS];
-  // task sorting for the thread-per-pair kernel: bins = class * TG_DPT_CBINS + tg_dpt_subkey
+  unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS][4];
+  // task sorting for the thread-per-extension kernel: bins = class * TG_DPT_CBINS + column bucket
   uint32_t bin_count[TG_DPT_NBINS], bin_cursor[TG_DPT_NBINS];
   uint32_t cls_start[TG_DPT_NCLS + 1], cls_end[TG_DPT_NCLS + 1], cls_chunk0[TG_DPT_NCLS + 1];
-  uint32_t warp_tasks;  // sorted[0 .. warp_tasks): tasks for the warp-cooperative kernel; the classes of the thread kernels
-                        // follow with every bin padded to an even number of entries (TG_NONE): entries 2u, 2u+1 = one thread
+  uint32_t warp_tasks;  // sorted[0 .. warp_tasks): tasks for the warp-cooperative kernel
   uint32_t round_cls[TG_MAX_ROUNDS][TG_DPT_NCLS];  // debug: tasks per band class
 };
 
@@ -474,8 +474,9 @@ struct RoundParams {
   uint32_t* ikey;          // [item] locus bucket
   uint32_t* ibins;         // [2][TG_IB_N] bucket counts, cursors
   uint32_t ib_shift;
-  uint32_t* dpt_trace;     // thread kernels: per band class, [warp][col][word][lane]
-  size_t dpt_trace_off[TG_DPT_NCLS], dpt_trace_words[TG_DPT_NCLS];  // region of each class, words per warp
+  uint32_t* dpt_trace;     // thread kernels: per class group, [warp][col][word][lane]
+  size_t dpt_trace_off[4], dpt_trace_words[4];  // region of each group, words per warp
+  int dpt_one, dpt_k128;   // 1 and 128 (see TgDptMem)
   uint32_t max_xlen, max_cols, trace_bytes, ops_words;
   int bound_stop;
   TgAlignOut out;
@@ -632,12 +633,13 @@ __global__ void __launch_bounds__(TG_WARPS_PER_CTA * 32) k_round_dp(RoundParams 
 
 // ---- task sorting: histogram -> bin starts -> scatter ------------------------------------------------------------
 __device__ __forceinline__ uint32_t task_bin(const TgTask& t) {
-  const int xlen = (int)t.xlen, bw = (int)t.bw;
+  const int xlen = (int)t.xlen, bw = (int)t.bw, ylen = (int)t.ylen;
+  const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
   const int cls = t.pad0 ? 0 : tg_dpt_class(xlen, bw, t.x_drop);  // pad0: not for the thread kernel (tg_swg_extend_batch)
-  // the two extensions of a thread must agree on xlen and band width (same phase boundaries, same slots): the key
-  // holds both, so equal neighbours in sorted order are the rule; the number of columns follows from them (except near
-  // the ends of a sequence), so the lanes of a warp finish together as well
-  return cls == 0 ? 0u : (uint32_t)cls * TG_DPT_CBINS + tg_dpt_subkey(xlen, bw);
+  // lanes of a warp should agree on the phase boundaries (bw) and on the number of columns: sort by both
+  const int bwb = bw < 16 ? bw : 16 + (bw - 16 < 60 ? (bw - 16) >> 2 : 15);
+  const int cb = (ncols < 255 ? ncols : 255) >> 4;
+  return (uint32_t)(cls * TG_DPT_CBINS + bwb * 16 + (15 - cb));
 }
 __global__ void __launch_bounds__(256) k_round_hist(RoundParams p) {
   __shared__ uint32_t h[TG_DPT_NBINS];
@@ -651,80 +653,59 @@ __global__ void __launch_bounds__(256) k_round_hist(RoundParams p) {
   for (int i = threadIdx.x; i < TG_DPT_NBINS; i += blockDim.x)
     if (h[i]) atomicAdd(&p.ctr->bin_count[i], h[i]);
 }
-// one block: exclusive scan of the bins; class ranges and warp-chunk table; clears the counts for the next round.
-// Thread t owns bin t of every class.
-#define TG_BINSCAN_THREADS TG_DPT_CBINS
+// one block: exclusive scan of the bins; class ranges and warp-chunk table; clears the counts for the next round
+#define TG_BINSCAN_THREADS 768
 __global__ void __launch_bounds__(TG_BINSCAN_THREADS) k_round_binscan(RoundParams p) {
-  __shared__ uint32_t cls_n[TG_DPT_NCLS], cls_np[TG_DPT_NCLS], cls_base[TG_DPT_NCLS];
-  __shared__ uint32_t small_s[TG_DPT_NCLS];
-  __shared__ uint32_t wsum[TG_DPT_NCLS][32], wsum_p[TG_DPT_NCLS][32];
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  uint32_t v[TG_DPT_NCLS];
+  __shared__ uint32_t cls_n[TG_DPT_NCLS + 1];
+  __shared__ uint32_t cls_base[TG_DPT_NCLS + 1];
+  if (threadIdx.x <= TG_DPT_NCLS) cls_n[threadIdx.x] = 0;
+  __syncthreads();
+  // thread t owns the bins [t * PER, t * PER + PER) of one class (TG_DPT_CBINS is a multiple of PER)
+  constexpr int PER = TG_DPT_NBINS / TG_BINSCAN_THREADS;
+  static_assert(TG_DPT_NBINS % TG_BINSCAN_THREADS == 0 && TG_DPT_CBINS % PER == 0, "bin layout");
+  uint32_t v[PER], sum = 0;
+  const int b0 = threadIdx.x * PER, cls = b0 / TG_DPT_CBINS;
 #pragma unroll
-  for (int c = 0; c < TG_DPT_NCLS; c++) {
-    v[c] = p.ctr->bin_count[c * TG_DPT_CBINS + t];
-    p.ctr->bin_count[c * TG_DPT_CBINS + t] = 0;
-    uint32_t a = v[c], b = (v[c] + 1u) & ~1u;
-    for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(TG_FULL, a, d); b += __shfl_xor_sync(TG_FULL, b, d); }
-    if (lane == 0) { wsum[c][wid] = a; wsum_p[c][wid] = b; }
+  for (int k = 0; k < PER; k++) { v[k] = p.ctr->bin_count[b0 + k]; p.ctr->bin_count[b0 + k] = 0; sum += v[k]; }
+  // exclusive scan of `sum` inside the class: warp scan + per-class atomics are overkill for <= 86 threads per class;
+  // a shared array and a serial pass over the threads of the class by its first thread is cheap enough
+  __shared__ uint32_t tsum[TG_BINSCAN_THREADS];
+  tsum[threadIdx.x] = sum;
+  __syncthreads();
+  constexpr int TPC = TG_DPT_CBINS / PER;  // threads per class
+  if (threadIdx.x % TPC == 0) {
+    uint32_t acc = 0;
+    for (int t = 0; t < TPC; t++) { const uint32_t x = tsum[threadIdx.x + t]; tsum[threadIdx.x + t] = acc; acc += x; }
+    cls_n[cls] = acc;
   }
   __syncthreads();
-  if (t < TG_DPT_NCLS) {
-    uint32_t a = 0, b = 0;
-    for (int w = 0; w < TG_BINSCAN_THREADS / 32; w++) { a += wsum[t][w]; b += wsum_p[t][w]; }
-    cls_n[t] = a; cls_np[t] = b;
-  }
-  __syncthreads();
-  if (t == 0) {
-    // A class with few tasks cannot fill the GPU with one thread per pair of extensions and would hold the round for the
+  if (threadIdx.x == 0) {
+    // A class with few tasks cannot fill the GPU with one thread per extension and would hold the round for the
     // latency of a single long task (a wide band is ~100 us on one thread): such classes join class 0 on the
-    // warp-cooperative kernel, which spreads one extension over 32 lanes.  Layout: class 0, small classes (plain lists),
-    // then the big classes with every bin padded to an even length.
+    // warp-cooperative kernel, which spreads one extension over 32 lanes.  Layout: class 0, small classes, big classes.
     uint32_t acc = 0, chunks = 0;
+    bool small[TG_DPT_NCLS];
     for (int c = 0; c < TG_DPT_NCLS; c++) {
       const uint32_t thr = tg_dpt_wb(c) <= 32 ? 4096u : 8192u;
-      small_s[c] = c == 0 || cls_n[c] < thr;
+      small[c] = c == 0 || cls_n[c] < thr;
       p.ctr->round_cls[p.round][c] = cls_n[c];
     }
     for (int c = 0; c < TG_DPT_NCLS; c++)
-      if (small_s[c]) { cls_base[c] = acc; acc += cls_n[c]; }
+      if (small[c]) { cls_base[c] = acc; acc += cls_n[c]; }
     p.ctr->warp_tasks = acc;
-    acc = (acc + 1u) & ~1u;
     for (int c = 0; c < TG_DPT_NCLS; c++) {
-      if (!small_s[c]) { cls_base[c] = acc; acc += cls_np[c]; }
+      if (!small[c]) { cls_base[c] = acc; acc += cls_n[c]; }
       p.ctr->cls_start[c] = cls_base[c];
-      p.ctr->cls_end[c] = cls_base[c] + (small_s[c] ? cls_n[c] : cls_np[c]);
+      p.ctr->cls_end[c] = cls_base[c] + cls_n[c];
       p.ctr->cls_chunk0[c] = chunks;
-      if (!small_s[c]) chunks += (cls_np[c] / 2 + 31) / 32;
+      if (!small[c]) chunks += (cls_n[c] + 31) / 32;
     }
     p.ctr->cls_chunk0[TG_DPT_NCLS] = chunks;
   }
   __syncthreads();
-  // exclusive scan inside every class (padded counts for the big classes)
-  uint32_t val[TG_DPT_NCLS], incl[TG_DPT_NCLS];
+  uint32_t acc = cls_base[cls] + tsum[threadIdx.x];
 #pragma unroll
-  for (int c = 0; c < TG_DPT_NCLS; c++) {
-    val[c] = small_s[c] ? v[c] : ((v[c] + 1u) & ~1u);
-    uint32_t x = val[c];
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(TG_FULL, x, d);
-      if (lane >= d) x += y;
-    }
-    incl[c] = x;
-    if (lane == 31) wsum[c][wid] = x;
-  }
-  __syncthreads();
-  if (t < TG_DPT_NCLS) {
-    uint32_t acc = 0;
-    for (int w = 0; w < TG_BINSCAN_THREADS / 32; w++) { const uint32_t x = wsum[t][w]; wsum[t][w] = acc; acc += x; }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int c = 0; c < TG_DPT_NCLS; c++) {
-    const uint32_t cursor = cls_base[c] + wsum[c][wid] + incl[c] - val[c];
-    p.ctr->bin_cursor[c * TG_DPT_CBINS + t] = cursor;
-    if (!small_s[c] && (v[c] & 1u)) p.sorted[cursor + v[c]] = TG_NONE;  // the odd task of a bin runs alone
-  }
+  for (int k = 0; k < PER; k++) { p.ctr->bin_cursor[b0 + k] = acc; acc += v[k]; }
 }
 __global__ void __launch_bounds__(256) k_round_scatter(RoundParams p) {
   __shared__ uint32_t h[TG_DPT_NBINS];
@@ -754,131 +735,101 @@ __global__ void __launch_bounds__(256) k_round_scatter(RoundParams p) {
   }
 }
 
-// ---- thread-per-pair kernel (tg_dpt.h) ----------------------------------------------------------------------------------
+// ---- thread-per-extension kernel (tg_dpt.h) ----------------------------------------------------------------------------
 #define DPT_OBUF 12u
-// One thread, two extensions (sorted neighbours ia, ib; ib may be TG_NONE).  Neighbours that do not agree on (xlen, band
-// width) -- possible only where a sort key was clamped -- run one after the other, each paired with itself.
 template <int WB>
-__device__ __forceinline__ void dpt_pair(const RoundParams& p, uint32_t ia, uint32_t ib, const TgDptMem& m, uint32_t* obuf, int lane) {
-  const bool has_a = ia != TG_NONE, has_b = ib != TG_NONE;
-  bool compat = false;
-  if (has_a && has_b) compat = p.tasks[ia].xlen == p.tasks[ib].xlen && p.tasks[ia].bw == p.tasks[ib].bw;
-  const int n_pass = __any_sync(TG_FULL, has_b && !compat) ? 2 : 1;
-  for (int pass = 0; pass < n_pass; pass++) {
-    // pass 0: (A, B) or (A, A); pass 1: (B, B) for the lanes whose neighbours did not fit together
-    const bool active = pass == 0 ? has_a : (has_b && !compat);
-    const uint32_t i0 = pass == 0 ? ia : ib, i1 = pass == 0 && compat ? ib : i0;
-    const bool commit1 = pass == 0 && compat;
-    TgDpt2Result res;
-    TgDptY ys0, ys1;
-    uint32_t n0 = 0, n1 = 0;
-    int xlen = 0, bw = 0;
-    bool diag0 = false, diag1 = false;
-    uint64_t e0lo = 0, e0hi = 0, e1lo = 0, e1hi = 0;
-    if (active) {
-      const TgTask& t0 = p.tasks[i0];
-      const TgTask& t1 = p.tasks[i1];
-      xlen = (int)t0.xlen; bw = (int)t0.bw;
-      const int yl0 = (int)t0.ylen, yl1 = (int)t1.ylen;
-      const int nc0 = yl0 < xlen + bw ? yl0 : xlen + bw, nc1 = yl1 < xlen + bw ? yl1 : xlen + bw;
-      ys0.init(tg_seq_of(p.P.ix, t0.seqsel), t0.y0, nc0, t0.side);
-      ys1.init(tg_seq_of(p.P.ix, t1.seqsel), t1.y0, nc1, t1.side);
-      tg_dpt_profile(m, 0, p.rp + (size_t)t0.read * p.rp_words, t0.xoff, xlen, t0.side);
-      tg_dpt_profile(m, 1, p.rp + (size_t)t1.read * p.rp_words, t1.xoff, xlen, t1.side);
-      tg_dpt2_fill<WB>(m, ys0, ys1, xlen, bw, nc0, nc1, t0.x_drop, t1.x_drop, p.bound_stop != 0, res);
-      // operations: the gapless shortcut where it applies (tg_dpt_diag_mask), else the traceback.  One pass: the RLE words
-      // go to a small shared-memory buffer (alignments have few runs); only an alignment with more than DPT_OBUF runs is
-      // produced a second time after the pool allocation
-      uint32_t* ob = obuf;
-      auto to_obuf = [ob](int h, uint32_t i, uint32_t kind, uint32_t run) {
-        if (i < DPT_OBUF) ob[(h * DPT_OBUF + i) * 128] = kind | (run << 3);
-      };
-      diag0 = tg_dpt_diag_mask(p.rp + (size_t)t0.read * p.rp_words, t0.xoff, xlen, t0.side, ys0.seq, t0.y0, res.xend[0], res.yend[0],
-                               res.score[0], e0lo, e0hi);
-      if (diag0) n0 = tg_dpt_diag_emit(e0lo, e0hi, res.xend[0], xlen, 0, to_obuf);
-      if (commit1) {
-        diag1 = tg_dpt_diag_mask(p.rp + (size_t)t1.read * p.rp_words, t1.xoff, xlen, t1.side, ys1.seq, t1.y0, res.xend[1], res.yend[1],
-                                 res.score[1], e1lo, e1hi);
-        if (diag1) n1 = tg_dpt_diag_emit(e1lo, e1hi, res.xend[1], xlen, 1, to_obuf);
-      }
-      if (!diag0 || (commit1 && !diag1)) {
-        uint32_t a0 = 0, a1 = 0;
-        tg_dpt2_traceback<WB>(m, ys0, ys1, xlen, bw, res, !diag0, commit1 && !diag1, a0, a1, to_obuf);
-        if (!diag0) n0 = a0;
-        if (commit1 && !diag1) n1 = a1;
-      }
-    }
-    __syncwarp();
-    // one pool allocation per warp
-    uint32_t n_ops = n0 + n1, incl = n_ops;
+__device__ __forceinline__ void dpt_task(const RoundParams& p, TgTask& t, bool active, const TgDptMem& m, uint32_t* obuf, int lane) {
+  TgDptResult res{0, 0, 0, 0};
+  TgDptY ys;
+  uint32_t n_ops = 0;
+  int xlen = 0, bw = 0;
+  if (active) {
+    xlen = (int)t.xlen; bw = (int)t.bw;
+    const int ylen = (int)t.ylen;
+    const int ncols = ylen < xlen + bw ? ylen : xlen + bw;
+    ys.seq = tg_seq_of(p.P.ix, t.seqsel); ys.y0 = t.y0; ys.ncols = ncols; ys.side = t.side; ys.word = 0; ys.need = 0;
+    ys.word_next = 0; ys.need_next = 0; ys.t_next = -1;
+    tg_dpt_profile(m, p.rp + (size_t)t.read * p.rp_words, t.xoff, xlen, t.side);
+    tg_dpt_fill<WB>(m, ys, xlen, ncols, bw, t.x_drop, p.bound_stop != 0, res);
+    // one traceback pass: the RLE words go to a small shared-memory buffer (alignments have few runs); only an
+    // alignment with more than DPT_OBUF runs is walked a second time after the pool allocation
+    uint32_t* ob = obuf;
+    n_ops = tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [ob](uint32_t i, uint32_t kind, uint32_t run) {
+      if (i < DPT_OBUF) ob[i * 128] = kind | (run << 3);
+    });
+  }
+  __syncwarp();
+  // one pool allocation per warp
+  uint32_t incl = n_ops;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t v = __shfl_up_sync(TG_FULL, incl, d);
-      if (lane >= d) incl += v;
-    }
-    const uint32_t total = __shfl_sync(TG_FULL, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 0 && total) base = atomicAdd(&p.ctr->round_ops[p.round], (unsigned long long)total);
-    base = __shfl_sync(TG_FULL, base, 0);
-    if (base + total > p.ops_cap) {
-      if (lane == 0) atomicOr(&p.ctr->flags, TG_FLAG_OPS_POOL);
-      n_ops = 0; n0 = 0; n1 = 0;
-    }
-    if (active) {
-      const unsigned long long dst0 = base + incl - n_ops, dst1 = dst0 + n0;
-      uint32_t* out0 = p.ops_pool + dst0;
-      uint32_t* out1 = p.ops_pool + dst1;
-      if (n0 > DPT_OBUF || n1 > DPT_OBUF) {
-        auto to_pool = [out0, out1](int h, uint32_t i, uint32_t kind, uint32_t run) { (h == 0 ? out0 : out1)[i] = kind | (run << 3); };
-        if (n0 > DPT_OBUF && diag0) tg_dpt_diag_emit(e0lo, e0hi, res.xend[0], xlen, 0, to_pool);
-        if (n1 > DPT_OBUF && diag1) tg_dpt_diag_emit(e1lo, e1hi, res.xend[1], xlen, 1, to_pool);
-        const bool g0 = n0 > DPT_OBUF && !diag0, g1 = n1 > DPT_OBUF && !diag1;
-        if (g0 || g1) {
-          uint32_t a0, a1;
-          tg_dpt2_traceback<WB>(m, ys0, ys1, xlen, bw, res, g0, g1, a0, a1, to_pool);
-        }
-      }
-      if (n0 <= DPT_OBUF)
-        for (uint32_t i = 0; i < n0; i++) out0[i] = obuf[i * 128];
-      if (n1 <= DPT_OBUF)
-        for (uint32_t i = 0; i < n1; i++) out1[i] = obuf[(DPT_OBUF + i) * 128];
-      TgTask& t0 = p.tasks[i0];
-      t0.score = res.score[0]; t0.xend = (uint32_t)res.xend[0]; t0.yend = (uint32_t)res.yend[0]; t0.cells = res.cells[0];
-      t0.ops_off = (uint32_t)dst0; t0.ops_n = n0;
-      if (commit1) {
-        TgTask& t1 = p.tasks[i1];
-        t1.score = res.score[1]; t1.xend = (uint32_t)res.xend[1]; t1.yend = (uint32_t)res.yend[1]; t1.cells = res.cells[1];
-        t1.ops_off = (uint32_t)dst1; t1.ops_n = n1;
-      }
-    }
-    __syncwarp();
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(TG_FULL, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const uint32_t total = __shfl_sync(TG_FULL, incl, 31);
+  unsigned long long base = 0;
+  if (lane == 0 && total) base = atomicAdd(&p.ctr->round_ops[p.round], (unsigned long long)total);
+  base = __shfl_sync(TG_FULL, base, 0);
+  if (base + total > p.ops_cap) {
+    if (lane == 0) atomicOr(&p.ctr->flags, TG_FLAG_OPS_POOL);
+    n_ops = 0;
+  }
+  if (active) {
+    const unsigned long long dst = base + incl - n_ops;
+    uint32_t* out = p.ops_pool + dst;
+    if (n_ops > DPT_OBUF) tg_dpt_traceback<WB>(m, ys, xlen, bw, res, [out](uint32_t i, uint32_t kind, uint32_t run) { out[i] = kind | (run << 3); });
+    else
+      for (uint32_t i = 0; i < n_ops; i++) out[i] = obuf[i * 128];
+    t.score = res.score; t.xend = (uint32_t)res.xend; t.yend = (uint32_t)res.yend; t.cells = res.cells;
+    t.ops_off = (uint32_t)dst; t.ops_n = n_ops;
   }
 }
 
-// One kernel per band class, so that a narrow class is not held to the register budget (and occupancy) of a wider one
-// and the instruction cache of an SM holds one unrolled band at a time.
-template <int CLS> struct DptCls { static constexpr int min_blocks = CLS <= 3 ? 4 : CLS <= 5 ? 3 : 2; };
+// Four kernels, one per group of band classes, so that the narrow classes are not held to the register budget (and
+// occupancy) of the widest one.  Group g handles classes [GFIRST, GLAST].
+template <int G> struct DptGroup;
+template <> struct DptGroup<0> { static constexpr int first = 1, last = 3, min_blocks = 6; };    // WB 4, 8, 16
+template <> struct DptGroup<1> { static constexpr int first = 4, last = 5, min_blocks = 4; };    // WB 24, 32
+template <> struct DptGroup<2> { static constexpr int first = 6, last = 8, min_blocks = 3; };    // WB 40, 48, 56
+template <> struct DptGroup<3> { static constexpr int first = 9, last = 11, min_blocks = 2; };   // WB 64, 72, 80
 
-template <int CLS>
-__global__ void __launch_bounds__(128, DptCls<CLS>::min_blocks) k_round_dpt(RoundParams p) {
-  __shared__ uint32_t msk[64 * 128];                 // match profiles of both extensions of every thread
-  __shared__ uint32_t obuf_s[2 * DPT_OBUF * 128];
+template <int G>
+__global__ void __launch_bounds__(128, DptGroup<G>::min_blocks) k_round_dpt(RoundParams p) {
+  __shared__ uint32_t msk[32 * 128];
+  __shared__ uint32_t obuf_s[DPT_OBUF * 128];
   uint32_t* obuf = obuf_s + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   TgDptMem m;
   m.msk = msk + threadIdx.x; m.mstride = 128;
-  m.tr = p.dpt_trace + p.dpt_trace_off[CLS] + (size_t)gw * p.dpt_trace_words[CLS] + lane; m.tstride = 32;
-  const uint32_t n_chunks = p.ctr->cls_chunk0[CLS + 1] - p.ctr->cls_chunk0[CLS];
-  const uint32_t start = p.ctr->cls_start[CLS], end = p.ctr->cls_end[CLS];
+  m.tr = p.dpt_trace + p.dpt_trace_off[G] + (size_t)gw * p.dpt_trace_words[G] + lane; m.tstride = 32;
+  m.one = p.dpt_one; m.k128 = p.dpt_k128;
+  const uint32_t chunk0 = p.ctr->cls_chunk0[DptGroup<G>::first], chunk1 = p.ctr->cls_chunk0[DptGroup<G>::last + 1];
   for (;;) {
-    const uint32_t g = next_work(&p.ctr->round_work2[p.round][CLS]);
-    if (g >= n_chunks) break;
-    // entries 2u, 2u + 1 of the class's padded range belong to one thread
-    const uint32_t pos = start + (g * 32u + (uint32_t)lane) * 2u;
-    uint32_t ia = TG_NONE, ib = TG_NONE;
-    if (pos < end) { ia = p.sorted[pos]; ib = p.sorted[pos + 1]; }
-    dpt_pair<tg_dpt_wb(CLS)>(p, ia, ib, m, obuf, lane);
+    const uint32_t g = chunk0 + next_work(&p.ctr->round_work2[p.round][G]);
+    if (g >= chunk1) break;
+    int cls = DptGroup<G>::first;
+    while (cls < DptGroup<G>::last && g >= p.ctr->cls_chunk0[cls + 1]) cls++;
+    const uint32_t first = p.ctr->cls_start[cls] + (g - p.ctr->cls_chunk0[cls]) * 32u;
+    const uint32_t end = p.ctr->cls_end[cls];
+    const bool active = first + lane < end;
+    TgTask& t = p.tasks[active ? p.sorted[first + lane] : p.sorted[first]];
+    if constexpr (G == 0) {
+      if (cls == 1) dpt_task<4>(p, t, active, m, obuf, lane);
+      else if (cls == 2) dpt_task<8>(p, t, active, m, obuf, lane);
+      else dpt_task<16>(p, t, active, m, obuf, lane);
+    } else if constexpr (G == 1) {
+      if (cls == 4) dpt_task<24>(p, t, active, m, obuf, lane);
+      else dpt_task<32>(p, t, active, m, obuf, lane);
+    } else if constexpr (G == 2) {
+      if (cls == 6) dpt_task<40>(p, t, active, m, obuf, lane);
+      else if (cls == 7) dpt_task<48>(p, t, active, m, obuf, lane);
+      else dpt_task<56>(p, t, active, m, obuf, lane);
+    } else {
+      if (cls == 9) dpt_task<64>(p, t, active, m, obuf, lane);
+      else if (cls == 10) dpt_task<72>(p, t, active, m, obuf, lane);
+      else dpt_task<80>(p, t, active, m, obuf, lane);
+    }
     __syncwarp();
   }
 }
@@ -1236,7 +1187,6 @@ struct tg_ctx {
   DevBuf d_cands, d_arena, d_order, d_aln_first, d_aln_count, d_alns, d_ops;
   uint64_t alns_cap = 0, ops_cap = 0;
   uint32_t scratch_warps = 0;
-  int dpt_occ[TG_DPT_NCLS] = {};  // resident CTAs per SM of k_round_dpt<cls> (queried once)
   // round pipeline scratch
   DevBuf r_state, r_hits, r_ires, r_cands, r_hops, r_fin, r_rp, r_tasks, r_ops, r_complex, r_sorted, r_dpt_trace, r_late, r_perm, r_ikey, r_ibins;
   PinBuf h_late;
@@ -1676,62 +1626,47 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
 
 // Geometry and scratch of the thread-per-extension kernels: one grid per class group, trace regions for `max_cols`
 // columns, the sorted task index.
-typedef void (*DptKernel)(RoundParams);
-static DptKernel dpt_kernel(int cls) {
-  switch (cls) {
-    case 1: return k_round_dpt<1>;
-    case 2: return k_round_dpt<2>;
-    case 3: return k_round_dpt<3>;
-    case 4: return k_round_dpt<4>;
-    case 5: return k_round_dpt<5>;
-    case 6: return k_round_dpt<6>;
-    case 7: return k_round_dpt<7>;
-    case 8: return k_round_dpt<8>;
-    case 9: return k_round_dpt<9>;
-    case 10: return k_round_dpt<10>;
-    default: return k_round_dpt<11>;
-  }
-}
-tg_status dpt_geometry(tg_ctx* c, RoundParams& p, uint32_t max_cols, uint64_t task_cap, int grid[TG_DPT_NCLS]) {
+tg_status dpt_geometry(tg_ctx* c, RoundParams& p, uint32_t max_cols, uint64_t task_cap, int grid[4]) {
   tg_status st;
+  void (*ks[4])(RoundParams) = {k_round_dpt<0>, k_round_dpt<1>, k_round_dpt<2>, k_round_dpt<3>};
+  const int group_wb[4] = {16, 32, 56, 80};  // widest class of each group
   size_t off = 0;
-  grid[0] = 0; p.dpt_trace_off[0] = 0; p.dpt_trace_words[0] = 0;
-  for (int g = 1; g < TG_DPT_NCLS; g++) {
-    if (c->dpt_occ[g] == 0) {
-      int o = 0;
-      CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dpt_kernel(g), 128, 0));
-      if (o < 1) return tg_fail(TG_ERR_INTERNAL, "thread DP kernel does not fit");
-      c->dpt_occ[g] = o;
-    }
-    grid[g] = c->n_sms * c->dpt_occ[g];
+  for (int g = 0; g < 4; g++) {
+    int o = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ks[g], 128, 0));
+    if (o < 1) return tg_fail(TG_ERR_INTERNAL, "thread DP kernel does not fit");
+    grid[g] = c->n_sms * o;
     p.dpt_trace_off[g] = off;
-    p.dpt_trace_words[g] = (size_t)max_cols * tg_dpt_twp(tg_dpt_wb(g)) * 32;  // per warp: [column][word][lane]
+    p.dpt_trace_words[g] = (size_t)max_cols * ((2 * group_wb[g] + 31) / 32) * 32;
     off += (size_t)grid[g] * 4 * p.dpt_trace_words[g];
   }
   if ((st = c->r_dpt_trace.ensure(off * 4)) != TG_OK) return st;
-  if ((st = c->r_sorted.ensure((task_cap + TG_DPT_NBINS + 2) * 4)) != TG_OK) return st;  // every bin may be padded by one entry
+  if ((st = c->r_sorted.ensure(task_cap * 4)) != TG_OK) return st;
   p.dpt_trace = (uint32_t*)c->r_dpt_trace.p;
+  p.dpt_one = 1; p.dpt_k128 = 128;
   p.sorted = (uint32_t*)c->r_sorted.p;
   return TG_OK;
 }
 
-// sort the tasks of round p.round by band class and run the thread-per-pair kernels (one per class, widest first) and the
-// warp-cooperative kernel (`warp_launch`, for what the thread kernels do not take) concurrently on the context's side streams
+// sort the tasks of round p.round by band class and run the thread-per-extension kernels and the warp-cooperative kernel
+// (`warp_launch`, for what the thread kernels do not take) concurrently on the context's side streams
 template <class WarpLaunch>
-tg_status launch_dpt(tg_ctx* c, RoundParams& p, const int grid[TG_DPT_NCLS], WarpLaunch&& warp_launch) {
+tg_status launch_dpt(tg_ctx* c, RoundParams& p, const int grid[4], WarpLaunch&& warp_launch) {
   k_round_hist<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
   k_round_binscan<<<1, TG_BINSCAN_THREADS, 0, c->stream>>>(p);
   k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
   CU_CHECK(cudaEventRecord(c->ev_fork, c->stream));
   for (int i = 0; i < 4; i++) CU_CHECK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+  k_round_dpt<3><<<grid[3], 128, 0, c->side[0]>>>(p);
+  k_round_dpt<2><<<grid[2], 128, 0, c->side[1]>>>(p);
+  k_round_dpt<1><<<grid[1], 128, 0, c->side[2]>>>(p);
   warp_launch(c->side[3]);
-  cudaStream_t lanes[4] = {c->side[0], c->side[1], c->side[2], c->stream};
-  for (int cls = TG_DPT_NCLS - 1, k = 0; cls >= 1; cls--, k++) dpt_kernel(cls)<<<grid[cls], 128, 0, lanes[k & 3]>>>(p);
+  k_round_dpt<0><<<grid[0], 128, 0, c->stream>>>(p);
   for (int i = 0; i < 4; i++) {
     CU_CHECK(cudaEventRecord(c->ev_join[i], c->side[i]));
     CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
   }
-  c->n_launches += 4 + (TG_DPT_NCLS - 1);
+  c->n_launches += 8;
   return TG_OK;
 }
 
@@ -1806,7 +1741,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   const int tblocks = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16);
   const int iblocks = c->n_sms * 16;
   // thread-per-extension kernel: geometry, trace scratch, sorted task list
-  int dpt_grid[TG_DPT_NCLS];
+  int dpt_grid[4];
   if ((st = dpt_geometry(c, p, std::min<uint32_t>(max_xlen, TG_DPT_MAX_X) + max_bw + 1, c->round_task_cap, dpt_grid)) != TG_OK) return st;
   k_round_init<<<tblocks, 128, 0, c->stream>>>(p);
   c->n_launches++;
@@ -2342,7 +2277,7 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
     rp.n_reads = n; rp.rp_words = rp_words; rp.rp = p.xpk;
     rp.tasks = p.tasks; rp.task_cap = n; rp.ops_pool = (uint32_t*)c->r_ops.p; rp.ops_cap = worst_ops; rp.round = 0;
     rp.bound_stop = p.bound_stop; rp.ctr = c->d_ctr;
-    int grid[TG_DPT_NCLS];
+    int grid[4];
     if ((st = dpt_geometry(c, rp, dpt_cols + 1, n, grid)) != TG_OK) return st;
     const unsigned long long n_tasks = n;
     CU_CHECK(cudaMemcpyAsync(&c->d_ctr->round_tasks[0], &n_tasks, sizeof(n_tasks), cudaMemcpyHostToDevice, c->stream));
