@@ -366,6 +366,44 @@ tg_status tg_parse_fastq(const char* text, size_t len, uint32_t* n_reads, uint8_
                          uint8_t** names, uint64_t** name_offs, uint8_t** quals, uint64_t** qual_offs);
 void tg_free(void* p);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Streaming ingest and the file-to-file driver (align_reads_from_file, src/aligner.rs:22-120).
+ *
+ * tg_fastq_reader = needletail::parse_fastx_file for FASTQ (src/aligner.rs:51-55): plain text, gzip (any number of
+ * members) or BGZF, told apart by the first bytes; "-" reads stdin.  Instead of one record at a time it hands out
+ * BATCHES: tg_fastq_next parses up to max_reads records on all host cores straight into buffers owned by the reader
+ * (bases and offsets page-locked when a CUDA device is present) and returns n_reads == 0 at the end of the input.  A
+ * batch stays valid until the THIRD next call (three buffer sets alternate: one being filled, one being aligned, one
+ * being written).  BGZF blocks are inflated in parallel, plain gzip members by one thread.  Record rules as
+ * tg_parse_fastq: four lines per record, blank lines between records skipped, '\r' dropped, a truncated last record
+ * dropped.  tg_fastq_format: 0 plain, 1 gzip, 2 BGZF.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tg_fastq_reader tg_fastq_reader;
+typedef struct tg_read_batch {
+  uint32_t n_reads;
+  uint32_t pad;
+  const uint8_t* bases;  const uint64_t* offs;       /* [n_reads + 1] */
+  const uint8_t* names;  const uint64_t* name_offs;  /* header line without '@' */
+  const uint8_t* quals;  const uint64_t* qual_offs;
+} tg_read_batch;
+tg_status tg_fastq_open(const char* path, tg_fastq_reader** out);
+tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* out);
+int tg_fastq_format(const tg_fastq_reader* r);
+void tg_fastq_close(tg_fastq_reader* r);
+
+/* align_reads_from_file (src/aligner.rs:22-120): query files -> PAF (output_fmt 0), SAM (1) or BAM (2) at out_path
+ * ("-" = stdout), records in input order.  Exactly one of ctx / multi is given (one GPU, or the reads of every batch
+ * sharded over the GPUs of a tg_multi).  Three overlapped stages: reader (inflate + parse batch k + 1), aligner (batch k
+ * on the GPU), writers (format batch k - 1 on all host cores and write it); no stage holds more than three batches of
+ * batch_reads reads (0 = 1 Mi).  The call switches ctx / multi to two alternating result sets. */
+typedef struct tg_file_stats {
+  uint64_t n_reads, n_alns, n_batches, bytes_out;
+  double read_ms, align_ms, write_ms;  /* busy time of each stage */
+  double wall_ms;
+} tg_file_stats;
+tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_multi* multi, const char* const* query_paths, int n_paths,
+                         const char* out_path, int output_fmt, uint32_t batch_reads, tg_file_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

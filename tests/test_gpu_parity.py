@@ -355,3 +355,31 @@ def test_align_reads_from_file_paf_sam_bam(tmp_path):
     text, refs, lines, n_blocks = bam_to_sam(outs[OutputFormat.Bam])
     assert text + lines == outs[OutputFormat.Sam]
     assert [r[0] for r in refs] == [b"some_ref", b"another_seq", b"introns_seq", b"introns_revcomp"]
+
+
+def test_align_files_gz_inputs_many_batches(tmp_path):
+    """The native file pipeline (tg_align_files: reader / aligner / writers overlapped) on a few thousand reads: gzip and
+    BGZF input (the reference's data sets are .fastq.gz, data/Makefile:26,35), two query files, batches far smaller than a
+    file so that every buffer set is reused many times; PAF and SAM text equal the oracle's text for the same reads."""
+    import gzip
+    from test_stream import bgzf
+    from thermite_b200 import OutputFormat, align_reads_from_file
+    contigs, gtf, txs, fa = small_world(11)
+    bases, offs = synth.make_reads(5, contigs, txs, 3000, L=91, sub=0.02, ins=0.003, dele=0.003)
+    lines = []
+    for i in range(len(offs) - 1):
+        seq = bases[int(offs[i]):int(offs[i + 1])].tobytes()
+        lines.append(b"@r%d extra words\n%s\n+\n%s\n" % (i, seq, b"F" * len(seq)))
+    half = len(lines) // 2
+    fq1, fq2 = b"".join(lines[:half]), b"".join(lines[half:])
+    (tmp_path / "a.fastq.gz").write_bytes(gzip.compress(fq1))
+    (tmp_path / "b.fastq.gz").write_bytes(bgzf(fq2, 20000))
+    ix = Index.create_from_memory(fa, gtf)
+    opts = AlignOpts(20, 0.0, 30, 1, True)
+    oix = orc.Index.create(fa, gtf)
+    for fmt, sam in ((OutputFormat.Paf, False), (OutputFormat.Sam, True)):
+        op = tmp_path / ("out." + fmt)
+        st = align_reads_from_file(ix, [str(tmp_path / "a.fastq.gz"), str(tmp_path / "b.fastq.gz")], str(op), fmt, opts, batch_reads=257)
+        assert st["n_reads"] == 3000 and st["n_batches"] >= 12
+        want = oix.align_fastq_text(fq1 + fq2, k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True, sam=sam)
+        assert op.read_bytes() == want, fmt   # (the oracle's SAM text starts with the header, like the file)

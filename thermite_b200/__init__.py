@@ -2,7 +2,7 @@
 reference's aligner API.  Compute lives in csrc/libthermite_gpu.so (hand-written CUDA); this package is
 the host-side mirror of the reference interface.  See DESIGN.md / INTEGRATION.md."""
 from .api import (ALN_C_DTYPE, ALN_DTYPE, SEED_DTYPE, MultiAligner, compact_arrays, expand_result, AlignOpts, Aligner, AlignResult, Alignment, GenomeAlignment, Index,
-                  OutputFormat, ThermiteAligner, ThermiteError, align_reads_from_file, bam_header, expand_ops, lib, parse_fastq, sam_header, suffix_array_gpu)
+                  OutputFormat, FastqReader, ThermiteAligner, ThermiteError, align_reads_from_file, bam_header, expand_ops, lib, parse_fastq, sam_header, suffix_array_gpu)
 
 __all__ = ["ALN_C_DTYPE", "MultiAligner", "compact_arrays", "expand_result", "ALN_DTYPE", "SEED_DTYPE", "AlignOpts", "Aligner", "AlignResult", "Alignment", "GenomeAlignment", "Index",
-           "OutputFormat", "ThermiteAligner", "ThermiteError", "align_reads_from_file", "bam_header", "expand_ops", "lib", "parse_fastq", "sam_header", "suffix_array_gpu"]
+           "OutputFormat", "FastqReader", "ThermiteAligner", "ThermiteError", "align_reads_from_file", "bam_header", "expand_ops", "lib", "parse_fastq", "sam_header", "suffix_array_gpu"]

@@ -95,6 +95,7 @@ ABI_SYMBOLS = [
     "tg_align_batch_compact", "tg_aln_expand", "tg_result_expand",
     "tg_multi_create", "tg_multi_destroy", "tg_multi_set_result_buffers", "tg_multi_n_devices", "tg_multi_replication", "tg_multi_ctx",
     "tg_multi_align_batch", "tg_multi_last_timing",
+    "tg_fastq_open", "tg_fastq_next", "tg_fastq_format", "tg_fastq_close", "tg_align_files",
 ]
 
 
@@ -125,6 +126,7 @@ def lib():
         L.tg_ctx_set_chunk_reads.restype = None
         L.tg_free.restype = None
         L.tg_multi_destroy.restype = None
+        L.tg_fastq_close.restype = None
         L.tg_multi_replication.restype = C.c_char_p
         L.tg_multi_ctx.restype = C.c_void_p
         _LIB = L
@@ -779,46 +781,89 @@ class ThermiteAligner:
             pass
 
 
+class _ReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("pad", C.c_uint32), ("bases", C.c_void_p), ("offs", C.c_void_p), ("names", C.c_void_p),
+                ("name_offs", C.c_void_p), ("quals", C.c_void_p), ("qual_offs", C.c_void_p)]
+
+
+class FileStats(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_alns", C.c_uint64), ("n_batches", C.c_uint64), ("bytes_out", C.c_uint64),
+                ("read_ms", C.c_double), ("align_ms", C.c_double), ("write_ms", C.c_double), ("wall_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class FastqReader:
+    """needletail::parse_fastx_file for FASTQ (src/aligner.rs:51-55) as a batch reader: plain, gzip or BGZF input, batches
+    of up to `max_reads` reads parsed on all host cores into buffers owned by the reader (`tg_fastq_*`, csrc/host_stream.cpp).
+    Iterating yields (bases, offs, names, name_offs, quals, qual_offs) as numpy COPIES."""
+    FORMATS = ("plain", "gzip", "bgzf")
+
+    def __init__(self, path: str, max_reads: int = 1 << 20):
+        h = C.c_void_p()
+        _check(lib().tg_fastq_open(path.encode(), C.byref(h)))
+        self._h = h
+        self.max_reads = max_reads
+
+    @property
+    def format(self) -> str:
+        return self.FORMATS[lib().tg_fastq_format(self._h)]
+
+    def next_raw(self) -> _ReadBatch:
+        b = _ReadBatch()
+        _check(lib().tg_fastq_next(self._h, C.c_uint32(self.max_reads), C.byref(b)))
+        return b
+
+    def __iter__(self):
+        while True:
+            b = self.next_raw()
+            n = b.n_reads
+            if n == 0:
+                return
+
+            def take(ptr, ctype, count, dtype):
+                if count == 0:
+                    return np.zeros(0, dtype)
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).astype(dtype, copy=True)
+            offs = take(b.offs, C.c_uint64, n + 1, np.uint64)
+            name_offs = take(b.name_offs, C.c_uint64, n + 1, np.uint64)
+            qual_offs = take(b.qual_offs, C.c_uint64, n + 1, np.uint64)
+            yield (take(b.bases, C.c_uint8, int(offs[n]), np.uint8), offs, take(b.names, C.c_uint8, int(name_offs[n]), np.uint8),
+                   name_offs, take(b.quals, C.c_uint8, int(qual_offs[n]), np.uint8), qual_offs)
+
+    def close(self):
+        if self._h:
+            lib().tg_fastq_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def align_reads_from_file(index: Index, query_paths, output_path: str, output_fmt: str, align_opts: AlignOpts,
-                          device: int = 0, batch_reads: int = 1 << 20):
-    """src/aligner.rs:22-120: align FASTQ files and write PAF, SAM or BAM (csrc/host_bam.cpp: the SAM records encoded
-    as BAM in BGZF blocks, end-of-file block last)."""
-    aligner = Aligner(index, align_opts, device)
-    sam = output_fmt == OutputFormat.Sam
-    bam = output_fmt == OutputFormat.Bam
-    import sys
-    out = sys.stdout.buffer if output_path == "-" else open(output_path, "wb")
-    try:
-        if sam:
-            out.write(sam_header(index))
-        if bam:
-            out.write(bam_header(index))
-        for qp in query_paths:
-            with open(qp, "rb") as f:
-                text = f.read()
-            bases, offs, names, name_offs, quals, qual_offs = parse_fastq(text)
-            n = len(offs) - 1
-            for lo in range(0, n, batch_reads):
-                hi = min(n, lo + batch_reads)
-                o = offs[lo: hi + 1] - offs[lo]
-                no = name_offs[lo: hi + 1] - name_offs[lo]
-                qo = qual_offs[lo: hi + 1] - qual_offs[lo]
-                b = bases[int(offs[lo]): int(offs[hi])]
-                nm = names[int(name_offs[lo]): int(name_offs[hi])]
-                ql = quals[int(qual_offs[lo]): int(qual_offs[hi])]
-                b = np.ascontiguousarray(b); o = np.ascontiguousarray(o)
-                res = aligner.align_reads_raw(b.ctypes.data, o.ctypes.data, hi - lo)
-                if bam:
-                    out.write(aligner.format_result_bam_raw(res, b, o, np.ascontiguousarray(nm), np.ascontiguousarray(no),
-                                                            np.ascontiguousarray(ql), np.ascontiguousarray(qo)))
-                    continue
-                out.write(aligner.format_result_raw(res, b, o, np.ascontiguousarray(nm), np.ascontiguousarray(no),
-                                                    np.ascontiguousarray(ql), np.ascontiguousarray(qo), sam))
-        if bam:
-            out.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))  # BGZF end-of-file block
-    finally:
-        if out is not sys.stdout.buffer:
-            out.close()
+                          device: int = 0, batch_reads: int = 1 << 20, devices=None) -> dict:
+    """src/aligner.rs:22-120: align FASTQ files (plain, .gz or BGZF) and write PAF, SAM or BAM, records in input order.
+    Runs natively (`tg_align_files`, csrc/host_stream.cpp): reader, aligner and writers are three overlapped stages and no
+    stage holds a whole file.  `devices` = several GPUs of this process (reads of every batch sharded, `MultiAligner`);
+    else one GPU (`device`).  Returns the pipeline's statistics (reads, records, bytes, busy time per stage, wall time)."""
+    fmt = {OutputFormat.Paf: 0, OutputFormat.Sam: 1, OutputFormat.Bam: 2}[output_fmt]
+    if isinstance(query_paths, (str, bytes)):
+        query_paths = [query_paths]
+    paths = (C.c_char_p * len(query_paths))(*[q.encode() if isinstance(q, str) else q for q in query_paths])
+    stats = FileStats()
+    if devices is not None and len(devices) > 1:
+        aligner = MultiAligner(index, align_opts, devices)
+        ctx, multi = None, aligner._h
+    else:
+        aligner = Aligner(index, align_opts, device if devices is None else devices[0])
+        ctx, multi = aligner._h, None
+    _check(lib().tg_align_files(index._h, ctx, multi, paths, len(query_paths), output_path.encode(), fmt, C.c_uint32(batch_reads),
+                                C.byref(stats)))
+    return stats.as_dict()
 
 
 # ---- multi-GPU plumbing (reads shard; index replicated; ordered merge on the host) ------------------------------

@@ -368,12 +368,12 @@ void tg_fastq_count(const char* text, size_t begin, size_t end, bool final, TgFa
   size_t lb[4], le[4];
   for (;;) {
     const size_t rec_start = w.p;
-    if (!w.next(lb[0], le[0])) { c.consumed = rec_start; return; }
+    if (!w.next(lb[0], le[0])) { c.consumed = rec_start < end ? rec_start : end; return; }  // (a last line without '\n' leaves p at end + 1)
     if (lb[0] == le[0]) { c.consumed = w.p < end ? w.p : end; continue; }  // blank line between records
     bool full = true;
     for (int k = 1; k < 4; k++) full = full && w.next(lb[k], le[k]);
     // (a record is complete only when its quality line is terminated, or the text ends here for good)
-    if (!full) { c.consumed = rec_start; return; }
+    if (!full) { c.consumed = rec_start < end ? rec_start : end; return; }
     if (text[lb[0]] != '@') { c.bad = true; return; }
     c.n++;
     c.names += le[0] - lb[0] - 1; c.bases += le[1] - lb[1]; c.quals += le[3] - lb[3];
@@ -399,3 +399,17 @@ void tg_fastq_fill(const char* text, size_t begin, size_t end, uint64_t n, uint8
 }
 
 size_t tg_fastq_record_start(const char* text, size_t len, size_t p) { return fastq_record_start(text, len, p); }
+
+size_t tg_fastq_skip(const char* text, size_t begin, size_t end, uint64_t k) {
+  LineWalker w{text, begin, end, true};
+  size_t lb, le, done = begin;
+  for (uint64_t i = 0; i < k;) {
+    if (!w.next(lb, le)) return done;
+    if (lb == le) { done = w.p < end ? w.p : end; continue; }
+    for (int q = 1; q < 4; q++)
+      if (!w.next(lb, le)) return done;
+    i++;
+    done = w.p < end ? w.p : end;
+  }
+  return done;
+}

@@ -1,0 +1,537 @@
+// host_stream.cpp -- streaming FASTQ ingest (plain, gzip, BGZF) and the file-to-file pipeline of libthermite_gpu.
+//
+// Replaces the read loop of align_reads_from_file (reference src/aligner.rs:22-120): needletail::parse_fastx_file is
+// gz-transparent and yields one record at a time (src/aligner.rs:51-55); the reference's own data sets are .fastq.gz
+// (data/Makefile:26,35).  Here a reader hands out BATCHES of reads in page-locked buffers -- text is inflated (BGZF blocks
+// on all host cores, plain gzip members on one), cut at record starts and parsed by all host cores straight into the
+// batch -- and tg_align_files runs reader, aligner and writers as three overlapped stages, so that no stage ever holds a
+// whole file and the GPU works on batch k while batch k + 1 is parsed and batch k - 1 is written.
+// Product code: must never include anything from oracle/.
+#include <zlib.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime_api.h>
+
+#include "host_text.h"
+#include "tg_internal.h"
+
+namespace {
+
+unsigned host_threads() { return (unsigned)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64); }
+
+template <class F>
+void run_threads(unsigned T, F&& f) {
+  if (T <= 1) { f(0u); return; }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < T; t++) th.emplace_back([&f, t]() { f(t); });
+  for (auto& x : th) x.join();
+}
+
+// Grow-only buffer, page-locked when a CUDA device is there (the batch goes to the GPU by DMA), pageable otherwise (the
+// reader is host logic and is tested without a GPU).
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+  ~HostBuf() { release(); }
+  void release() {
+    if (!p) return;
+    if (pinned) cudaFreeHost(p); else free(p);
+    p = nullptr; cap = 0;
+  }
+  bool ensure(size_t bytes, bool want_pinned) {
+    if (bytes <= cap) return true;
+    release();
+    size_t want = bytes + bytes / 8 + 4096;
+    if (want_pinned && cudaHostAlloc(&p, want, cudaHostAllocPortable) == cudaSuccess) { pinned = true; cap = want; return true; }
+    if (want_pinned) cudaGetLastError();  // no device / no driver: clear the sticky error and fall back to pageable memory
+    p = malloc(want);
+    pinned = false;
+    cap = p ? want : 0;
+    return p != nullptr;
+  }
+};
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// ---- reader ---------------------------------------------------------------------------------------------------------
+struct tg_fastq_reader {
+  FILE* f = nullptr;
+  int format = 0;  // 0 plain, 1 gzip (serial inflate), 2 BGZF (blocks inflated in parallel)
+  std::vector<unsigned char> zin;  // compressed bytes not yet inflated
+  size_t zin_len = 0;
+  bool file_eof = false;
+  z_stream zs;
+  bool zs_open = false;
+  std::vector<char> text;  // inflated / plain text not yet handed out; starts at a record start
+  size_t text_len = 0;
+  bool text_final = false;  // nothing will be appended to `text` any more
+  double bytes_per_read = 220.0;
+  struct Set {
+    HostBuf bases, offs, names, name_offs, quals, qual_offs;
+  } set[3];
+  int cur = 0;
+  uint64_t total_reads = 0, total_text = 0;
+  std::string err;
+
+  ~tg_fastq_reader() {
+    if (zs_open) inflateEnd(&zs);
+    if (f) fclose(f);
+  }
+  void grow_text(size_t need) {
+    if (text.size() < need) text.resize(need + need / 4 + (1u << 20));
+  }
+  bool read_file(size_t want) {  // appends up to `want` bytes of the file to zin; false on a read error
+    if (file_eof) return true;
+    if (zin.size() < zin_len + want) zin.resize(zin_len + want);
+    const size_t got = fread(zin.data() + zin_len, 1, want, f);
+    if (got < want) {
+      if (ferror(f)) { err = "read error"; return false; }
+      file_eof = true;
+    }
+    zin_len += got;
+    return true;
+  }
+  bool fill_plain(size_t target) {
+    while (text_len < target && !text_final) {
+      const size_t want = std::max<size_t>(target - text_len, 1u << 20);
+      grow_text(text_len + want);
+      const size_t got = fread(text.data() + text_len, 1, want, f);
+      if (got < want) {
+        if (ferror(f)) { err = "read error"; return false; }
+        text_final = true;
+      }
+      text_len += got;
+    }
+    return true;
+  }
+  // gzip, any number of members (RFC 1952: a file is a series of members; needletail / flate2's MultiGzDecoder read them all)
+  bool fill_gzip(size_t target) {
+    size_t zpos = 0;
+    while (text_len < target && !text_final) {
+      if (zpos == zin_len) {
+        zin_len = 0; zpos = 0;
+        if (!read_file(4u << 20)) return false;
+        if (zin_len == 0) {  // end of the file
+          if (zs_open) { err = "gzip stream ends inside a member"; return false; }
+          text_final = true;
+          break;
+        }
+      }
+      if (!zs_open) {
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, 15 + 32) != Z_OK) { err = "inflateInit2 failed"; return false; }
+        zs_open = true;
+      }
+      grow_text(text_len + (8u << 20));
+      zs.next_in = zin.data() + zpos;
+      zs.avail_in = (uInt)std::min<size_t>(zin_len - zpos, 1u << 30);
+      zs.next_out = (Bytef*)text.data() + text_len;
+      zs.avail_out = (uInt)std::min<size_t>(text.size() - text_len, 1u << 30);
+      const uInt in0 = zs.avail_in, out0 = zs.avail_out;
+      const int rc = inflate(&zs, Z_NO_FLUSH);
+      zpos += in0 - zs.avail_in;
+      text_len += out0 - zs.avail_out;
+      if (rc == Z_STREAM_END) { inflateEnd(&zs); zs_open = false; }
+      else if (rc != Z_OK && rc != Z_BUF_ERROR) { err = std::string("gzip data error: ") + (zs.msg ? zs.msg : "?"); return false; }
+    }
+    // keep what was not consumed
+    if (zpos < zin_len) memmove(zin.data(), zin.data() + zpos, zin_len - zpos);
+    zin_len -= zpos;
+    return true;
+  }
+  // BGZF (SAM spec 4.1): gzip members of at most 64 KiB, each with a 'BC' extra subfield holding its size, so the
+  // members of a chunk are independent jobs
+  struct Block { size_t src, clen, dst; uint32_t isize; };
+  bool fill_bgzf(size_t target) {
+    while (text_len < target && !text_final) {
+      if (!read_file(std::max<size_t>((target - text_len) / 3, 4u << 20))) return false;
+      if (zin_len == 0) { text_final = true; break; }
+      std::vector<Block> blocks;
+      size_t p = 0, out_bytes = 0;
+      bool not_bgzf = false;
+      while (p + 18 <= zin_len) {
+        const unsigned char* h = zin.data() + p;
+        if (!(h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4))) { not_bgzf = true; break; }
+        const size_t xlen = h[10] | (h[11] << 8);
+        if (p + 12 + xlen > zin_len) break;
+        size_t bsize = 0;
+        for (size_t q = 12; q + 4 <= 12 + xlen;) {
+          const size_t slen = h[q + 2] | (h[q + 3] << 8);
+          if (h[q] == 'B' && h[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) bsize = (size_t)(h[q + 4] | (h[q + 5] << 8)) + 1;
+          q += 4 + slen;
+        }
+        if (bsize == 0) { not_bgzf = true; break; }
+        if (bsize < 12 + xlen + 8) { err = "corrupt BGZF block"; return false; }
+        if (p + bsize > zin_len) break;  // incomplete block: wait for more input
+        const unsigned char* tail = h + bsize - 4;
+        const uint32_t isize = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
+        blocks.push_back(Block{p + 12 + xlen, bsize - (12 + xlen) - 8, out_bytes, isize});
+        out_bytes += isize;
+        p += bsize;
+      }
+      if (blocks.empty() && !not_bgzf) {
+        if (file_eof) { if (zin_len) { err = "BGZF stream ends inside a block"; return false; } text_final = true; }
+        continue;
+      }
+      if (!blocks.empty()) {
+        grow_text(text_len + out_bytes);
+        char* dst0 = text.data() + text_len;
+        const unsigned T = (unsigned)std::min<size_t>(host_threads(), blocks.size());
+        std::vector<int> bad(T, 0);
+        run_threads(T, [&](unsigned t) {
+          z_stream z;
+          memset(&z, 0, sizeof(z));
+          if (inflateInit2(&z, -15) != Z_OK) { bad[t] = 1; return; }
+          const size_t b0 = blocks.size() * t / T, b1 = blocks.size() * (t + 1) / T;
+          for (size_t b = b0; b < b1; b++) {
+            const Block& k = blocks[b];
+            z.next_in = zin.data() + k.src; z.avail_in = (uInt)k.clen;
+            z.next_out = (Bytef*)dst0 + k.dst; z.avail_out = k.isize;
+            const int rc = inflate(&z, Z_FINISH);
+            if (rc != Z_STREAM_END || z.avail_out != 0) { bad[t] = 1; break; }
+            inflateReset(&z);
+          }
+          inflateEnd(&z);
+        });
+        for (int b : bad) if (b) { err = "corrupt BGZF block"; return false; }
+        text_len += out_bytes;
+      }
+      if (p < zin_len) memmove(zin.data(), zin.data() + p, zin_len - p);
+      zin_len -= p;
+      if (not_bgzf) { format = 1; return fill_gzip(target); }  // a plain gzip member in between: go on serially
+    }
+    return true;
+  }
+  bool fill_text(size_t target) {
+    if (format == 0) return fill_plain(target);
+    if (format == 1) return fill_gzip(target);
+    return fill_bgzf(target);
+  }
+};
+
+extern "C" {
+
+tg_status tg_fastq_open(const char* path, tg_fastq_reader** out) {
+  TG_GUARD_BEGIN
+  if (!path || !out) return tg_fail(TG_ERR_INVALID, "null argument");
+  FILE* f = strcmp(path, "-") == 0 ? stdin : fopen(path, "rb");
+  if (!f) return tg_fail(TG_ERR_IO, std::string("cannot open ") + path);
+  auto* r = new tg_fastq_reader();
+  r->f = f;
+  // format from the first bytes (needletail sniffs the magic as well): 1f 8b = gzip; FEXTRA + a 'BC' subfield = BGZF
+  if (!r->read_file(64u << 10)) { delete r; return tg_fail(TG_ERR_IO, "read error"); }
+  if (r->zin_len >= 2 && r->zin[0] == 0x1f && r->zin[1] == 0x8b) {
+    r->format = 1;
+    if (r->zin_len >= 18 && r->zin[2] == 8 && (r->zin[3] & 4)) {
+      const size_t xlen = r->zin[10] | (r->zin[11] << 8);
+      for (size_t q = 12; q + 6 <= 12 + xlen && q + 6 <= r->zin_len;) {
+        const size_t slen = r->zin[q + 2] | (r->zin[q + 3] << 8);
+        if (r->zin[q] == 'B' && r->zin[q + 1] == 'C' && slen == 2) { r->format = 2; break; }
+        q += 4 + slen;
+      }
+    }
+  } else {  // plain text: what was read is text already
+    r->grow_text(r->zin_len);
+    memcpy(r->text.data(), r->zin.data(), r->zin_len);
+    r->text_len = r->zin_len;
+    r->zin_len = 0;
+    if (r->file_eof) r->text_final = true;
+  }
+  *out = r;
+  return TG_OK;
+  TG_GUARD_END
+}
+
+int tg_fastq_format(const tg_fastq_reader* r) { return r ? r->format : -1; }
+
+void tg_fastq_close(tg_fastq_reader* r) {
+  if (!r) return;
+  if (r->f == stdin) r->f = nullptr;
+  delete r;
+}
+
+tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* out) {
+  TG_GUARD_BEGIN
+  if (!r || !out || max_reads == 0) return tg_fail(TG_ERR_INVALID, "null argument");
+  memset(out, 0, sizeof(*out));
+  const unsigned T0 = host_threads();
+  size_t target = (size_t)((double)max_reads * r->bytes_per_read * 1.03) + (64u << 10);
+  struct Seg { size_t begin, end; TgFastqCount c; };
+  std::vector<Seg> seg;
+  uint64_t n = 0;
+  size_t consumed = 0;
+  for (;;) {
+    if (!r->fill_text(target)) return tg_fail(TG_ERR_IO, "FASTQ input: " + r->err);
+    const char* text = r->text.data();
+    const size_t len = r->text_len;
+    // segments cut at record starts, counted on all cores
+    unsigned T = len < (4u << 20) ? 1u : T0;
+    std::vector<size_t> cut(T + 1, len);
+    cut[0] = 0;
+    for (unsigned t = 1; t < T; t++) cut[t] = std::max(cut[t - 1], tg_fastq_record_start(text, len, (size_t)((double)len * t / T)));
+    seg.assign(T, Seg());
+    run_threads(T, [&](unsigned t) {
+      seg[t].begin = cut[t]; seg[t].end = cut[t + 1];
+      // an inner segment ends at a record start, so its last line is terminated; only the last segment can be cut short
+      tg_fastq_count(text, cut[t], cut[t + 1], t + 1 < T || r->text_final, seg[t].c);
+    });
+    n = 0; consumed = 0;
+    size_t used = 0;
+    for (unsigned t = 0; t < T; t++) {
+      if (seg[t].c.bad) return tg_fail(TG_ERR_IO, "FASTQ record does not start with '@'");
+      if (seg[t].begin == seg[t].end) { used = t + 1; continue; }
+      if (n + seg[t].c.n > max_reads) {  // the batch ends inside this segment: find the cut and count again up to it
+        const uint64_t take = max_reads - n;
+        const size_t stop = tg_fastq_skip(text, seg[t].begin, seg[t].end, take);
+        seg[t].end = stop;
+        tg_fastq_count(text, seg[t].begin, stop, true, seg[t].c);
+        n += seg[t].c.n;
+        consumed = stop;
+        used = t + 1;
+        break;
+      }
+      n += seg[t].c.n;
+      consumed = seg[t].c.consumed;
+      used = t + 1;
+      if (seg[t].c.consumed < seg[t].end && t + 1 < T) {
+        // cannot happen for an inner segment (it ends at a record start); guard against a cut heuristic gone wrong
+        return tg_fail(TG_ERR_IO, "FASTQ text: records are not four lines each");
+      }
+    }
+    seg.resize(used);
+    if (n > 0 || r->text_final) break;
+    target = std::max(target * 2, len + (1u << 20));  // not a single complete record yet: read on
+  }
+  if (n == 0) {  // end of input (a truncated last record is dropped, as needletail's reader does on EOF)
+    r->text_len = 0;
+    return TG_OK;
+  }
+  uint64_t nb = 0, nn = 0, nq = 0;
+  for (auto& s : seg) { nb += s.c.bases; nn += s.c.names; nq += s.c.quals; }
+  tg_fastq_reader::Set& S = r->set[r->cur];
+  r->cur = (r->cur + 1) % 3;
+  if (!S.bases.ensure(nb + 64, true) || !S.offs.ensure((n + 1) * 8, true) || !S.names.ensure(nn + 1, false) ||
+      !S.name_offs.ensure((n + 1) * 8, false) || !S.quals.ensure(nq + 1, false) || !S.qual_offs.ensure((n + 1) * 8, false))
+    return tg_fail(TG_ERR_INTERNAL, "out of memory");
+  uint8_t* bases = (uint8_t*)S.bases.p; uint64_t* offs = (uint64_t*)S.offs.p;
+  uint8_t* names = (uint8_t*)S.names.p; uint64_t* name_offs = (uint64_t*)S.name_offs.p;
+  uint8_t* quals = (uint8_t*)S.quals.p; uint64_t* qual_offs = (uint64_t*)S.qual_offs.p;
+  offs[0] = 0; name_offs[0] = 0; qual_offs[0] = 0;
+  std::vector<uint64_t> r0(seg.size()), b0(seg.size()), n0(seg.size()), q0(seg.size());
+  {
+    uint64_t cr = 0, cb = 0, cn = 0, cq = 0;
+    for (size_t t = 0; t < seg.size(); t++) {
+      r0[t] = cr; b0[t] = cb; n0[t] = cn; q0[t] = cq;
+      cr += seg[t].c.n; cb += seg[t].c.bases; cn += seg[t].c.names; cq += seg[t].c.quals;
+    }
+  }
+  const char* text = r->text.data();
+  run_threads((unsigned)seg.size(), [&](unsigned t) {
+    if (seg[t].c.n == 0) return;
+    tg_fastq_fill(text, seg[t].begin, seg[t].end, seg[t].c.n, bases, offs + r0[t], b0[t], names, name_offs + r0[t], n0[t], quals,
+                  qual_offs + r0[t], q0[t]);
+  });
+  // what is left starts at a record start
+  if (consumed < r->text_len) memmove(r->text.data(), r->text.data() + consumed, r->text_len - consumed);
+  r->text_len -= consumed;
+  r->bytes_per_read = 0.5 * r->bytes_per_read + 0.5 * ((double)consumed / (double)n);
+  r->total_reads += n; r->total_text += consumed;
+  out->n_reads = (uint32_t)n;
+  out->bases = bases; out->offs = offs; out->names = names; out->name_offs = name_offs; out->quals = quals; out->qual_offs = qual_offs;
+  return TG_OK;
+  TG_GUARD_END
+}
+
+}  // extern "C"
+
+// ---- file-to-file pipeline ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Job {
+  tg_read_batch batch;
+  tg_result_c res;
+  uint64_t index = 0;
+  bool end = false;
+};
+// bounded hand-over between two stages
+struct Channel {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<Job> q;
+  void push(const Job& j) {
+    { std::lock_guard<std::mutex> l(mu); q.push_back(j); }
+    cv.notify_all();
+  }
+  Job pop() {
+    std::unique_lock<std::mutex> l(mu);
+    cv.wait(l, [&] { return !q.empty(); });
+    Job j = q.front();
+    q.pop_front();
+    return j;
+  }
+};
+struct Progress {  // batches completely written; the earlier stages wait on it before they reuse a buffer set
+  std::mutex mu;
+  std::condition_variable cv;
+  uint64_t written = 0;
+  bool failed = false;
+  void done_one() {
+    { std::lock_guard<std::mutex> l(mu); written++; }
+    cv.notify_all();
+  }
+  void fail() {
+    { std::lock_guard<std::mutex> l(mu); failed = true; }
+    cv.notify_all();
+  }
+  bool wait_written(uint64_t at_least) {  // false when another stage failed
+    std::unique_lock<std::mutex> l(mu);
+    cv.wait(l, [&] { return failed || written >= at_least; });
+    return !failed;
+  }
+};
+
+}  // namespace
+
+extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_multi* multi, const char* const* query_paths,
+                                    int n_paths, const char* out_path, int output_fmt, uint32_t batch_reads, tg_file_stats* stats) {
+  TG_GUARD_BEGIN
+  if (!ix || (!ctx) == (!multi) || !query_paths || n_paths < 1 || !out_path || output_fmt < 0 || output_fmt > 2)
+    return tg_fail(TG_ERR_INVALID, "tg_align_files: bad argument (exactly one of ctx / multi; format 0 PAF, 1 SAM, 2 BAM)");
+  if (batch_reads == 0) batch_reads = 1u << 20;
+  tg_status st;
+  if (ctx) st = tg_ctx_set_result_buffers(ctx, 2);
+  else st = tg_multi_set_result_buffers(multi, 2);
+  if (st != TG_OK) return st;
+  FILE* out = strcmp(out_path, "-") == 0 ? stdout : fopen(out_path, "wb");
+  if (!out) return tg_fail(TG_ERR_IO, std::string("cannot create ") + out_path);
+  auto close_out = [&]() { if (out != stdout) fclose(out); else fflush(out); };
+  const double t_start = now_ms();
+  tg_file_stats S;
+  memset(&S, 0, sizeof(S));
+  // file header (src/aligner.rs:41-47)
+  if (output_fmt == 1) {
+    char* h = nullptr; size_t hl = 0;
+    if ((st = tg_format_sam_header(ix, &h, &hl)) != TG_OK) { close_out(); return st; }
+    fwrite(h, 1, hl, out); S.bytes_out += hl; free(h);
+  } else if (output_fmt == 2) {
+    void* h = nullptr; size_t hl = 0;
+    if ((st = tg_format_bam_header(ix, &h, &hl)) != TG_OK) { close_out(); return st; }
+    fwrite(h, 1, hl, out); S.bytes_out += hl; free(h);
+  }
+  Channel to_align, to_write;
+  Progress prog;
+  std::string err_read, err_write;
+  tg_status st_read = TG_OK, st_write = TG_OK;
+  double read_ms = 0, write_ms = 0;
+
+  // stage 1: files -> batches.  A reader owns three buffer sets; batch b may be overwritten by batch b + 3, which is
+  // produced only after batch b has been written.
+  std::thread producer([&]() {
+    uint64_t b = 0;
+    for (int f = 0; f < n_paths && st_read == TG_OK; f++) {
+      tg_fastq_reader* r = nullptr;
+      if ((st_read = tg_fastq_open(query_paths[f], &r)) != TG_OK) { err_read = tg_last_error(); break; }
+      for (;;) {
+        if (b >= 2 && !prog.wait_written(b - 2)) break;
+        Job j;
+        const double t0 = now_ms();
+        if ((st_read = tg_fastq_next(r, batch_reads, &j.batch)) != TG_OK) { err_read = tg_last_error(); break; }
+        read_ms += now_ms() - t0;
+        if (j.batch.n_reads == 0) break;
+        j.index = b++;
+        to_align.push(j);
+      }
+      // the reader's buffers must outlive its batches
+      if (st_read == TG_OK) prog.wait_written(b);
+      tg_fastq_close(r);
+    }
+    if (st_read != TG_OK) prog.fail();
+    Job e; e.end = true;
+    to_align.push(e);
+  });
+
+  // stage 3: records -> text -> file.  Per-thread text buffers are kept across batches (fresh buffers cost a page fault
+  // per 4 KiB of output) and written one after the other: no merged copy of the batch's text is ever made.
+  std::thread writer([&]() {
+    const unsigned T = host_threads();
+    std::vector<TgOut> parts(T);
+    std::string z;
+    for (;;) {
+      Job j = to_write.pop();
+      if (j.end) break;
+      if (st_write != TG_OK) { prog.done_one(); continue; }  // keep draining so that nobody waits forever
+      const double t0 = now_ms();
+      const uint32_t n = j.batch.n_reads;
+      const unsigned Tn = n < 32768 ? 1u : T;
+      TgRecView v;
+      v.first32 = j.res.read_aln_first; v.count = j.res.read_aln_count; v.comp = j.res.alns; v.ops = j.res.ops;
+      run_threads(Tn, [&](unsigned t) {
+        parts[t].s.n = 0;
+        const uint32_t r0 = (uint32_t)((uint64_t)n * t / Tn), r1 = (uint32_t)((uint64_t)n * (t + 1) / Tn);
+        tg_format_reads(ix, v, j.batch.bases, j.batch.offs, j.batch.names, j.batch.name_offs, j.batch.quals, j.batch.qual_offs,
+                        output_fmt == 0 ? 0 : 1, r0, r1, parts[t]);
+      });
+      for (unsigned t = 0; t < Tn && st_write == TG_OK; t++) {
+        const char* p = parts[t].s.data();
+        size_t len = parts[t].s.size();
+        if (output_fmt == 2) {
+          z.clear();
+          if ((st_write = tg_sam_text_to_bam(ix, p, len, false, z)) != TG_OK) { err_write = tg_last_error(); break; }
+          p = z.data(); len = z.size();
+        }
+        if (len && fwrite(p, 1, len, out) != len) { st_write = TG_ERR_IO; err_write = "write error"; }
+        S.bytes_out += len;
+      }
+      S.n_reads += n; S.n_alns += j.res.n_alns; S.n_batches++;
+      write_ms += now_ms() - t0;
+      if (st_write != TG_OK) prog.fail();
+      prog.done_one();
+    }
+  });
+
+  // stage 2 (this thread): batches -> records.  Two result sets alternate: batch b overwrites the result of batch b - 2.
+  tg_status st_align = TG_OK;
+  double align_ms = 0;
+  for (;;) {
+    Job j = to_align.pop();
+    if (j.end) break;
+    if (st_align != TG_OK) continue;
+    if (j.index >= 1 && !prog.wait_written(j.index - 1)) { st_align = TG_ERR_INTERNAL; continue; }
+    const double t0 = now_ms();
+    if (ctx) st_align = tg_align_batch_compact(ctx, j.batch.bases, j.batch.offs, j.batch.n_reads, &j.res);
+    else st_align = tg_multi_align_batch(multi, j.batch.bases, j.batch.offs, j.batch.n_reads, &j.res);
+    align_ms += now_ms() - t0;
+    if (st_align != TG_OK) { prog.fail(); continue; }
+    to_write.push(j);
+  }
+  { Job e; e.end = true; to_write.push(e); }
+  producer.join();
+  writer.join();
+  if (output_fmt == 2 && st_align == TG_OK && st_read == TG_OK && st_write == TG_OK) {
+    static const unsigned char eof_block[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    fwrite(eof_block, 1, sizeof(eof_block), out);
+    S.bytes_out += sizeof(eof_block);
+  }
+  close_out();
+  S.read_ms = read_ms; S.align_ms = align_ms; S.write_ms = write_ms; S.wall_ms = now_ms() - t_start;
+  if (stats) *stats = S;
+  if (st_read != TG_OK) return tg_fail(st_read, err_read);
+  if (st_align != TG_OK) return st_align == TG_ERR_INTERNAL && prog.failed ? tg_fail(st_write != TG_OK ? st_write : TG_ERR_INTERNAL, err_write.empty() ? "pipeline stage failed" : err_write) : st_align;
+  if (st_write != TG_OK) return tg_fail(st_write, err_write);
+  return TG_OK;
+  TG_GUARD_END
+}

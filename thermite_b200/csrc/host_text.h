@@ -70,5 +70,7 @@ void tg_fastq_count(const char* text, size_t begin, size_t end, bool final, TgFa
 void tg_fastq_fill(const char* text, size_t begin, size_t end, uint64_t n, uint8_t* bases, uint64_t* offs, uint64_t base0,
                    uint8_t* names, uint64_t* name_offs, uint64_t name0, uint8_t* quals, uint64_t* qual_offs, uint64_t qual0);
 size_t tg_fastq_record_start(const char* text, size_t len, size_t p);
+// offset just behind the k-th complete record of [begin, end) (end when there are fewer)
+size_t tg_fastq_skip(const char* text, size_t begin, size_t end, uint64_t k);
 // SAM lines -> BGZF-compressed BAM records (host_bam.cpp)
 tg_status tg_sam_text_to_bam(const tg_index_host* ix, const char* sam, size_t sl, bool append_eof, std::string& z);
