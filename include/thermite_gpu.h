@@ -399,6 +399,7 @@ void tg_fastq_close(tg_fastq_reader* r);
 typedef struct tg_file_stats {
   uint64_t n_reads, n_alns, n_batches, bytes_out;
   double read_ms, align_ms, write_ms;  /* busy time of each stage */
+  double format_ms;                    /* the part of write_ms spent turning records into text */
   double wall_ms;
 } tg_file_stats;
 tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_multi* multi, const char* const* query_paths, int n_paths,

@@ -788,7 +788,8 @@ class _ReadBatch(C.Structure):
 
 class FileStats(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_alns", C.c_uint64), ("n_batches", C.c_uint64), ("bytes_out", C.c_uint64),
-                ("read_ms", C.c_double), ("align_ms", C.c_double), ("write_ms", C.c_double), ("wall_ms", C.c_double)]
+                ("read_ms", C.c_double), ("align_ms", C.c_double), ("write_ms", C.c_double), ("format_ms", C.c_double),
+                ("wall_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

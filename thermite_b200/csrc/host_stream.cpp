@@ -7,6 +7,10 @@
 // batch -- and tg_align_files runs reader, aligner and writers as three overlapped stages, so that no stage ever holds a
 // whole file and the GPU works on batch k while batch k + 1 is parsed and batch k - 1 is written.
 // Product code: must never include anything from oracle/.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <chrono>
@@ -78,6 +82,9 @@ struct tg_fastq_reader {
   bool zs_open = false;
   std::vector<char> text;  // inflated / plain text not yet handed out; starts at a record start
   size_t text_len = 0;
+  const char* map = nullptr;  // a plain regular file is parsed in place from its mapping: no copy of the text is made
+  size_t map_len = 0, map_pos = 0;
+  const char* tptr() const { return map ? map + map_pos : text.data(); }
   bool text_final = false;  // nothing will be appended to `text` any more
   double bytes_per_read = 220.0;
   struct Set {
@@ -89,6 +96,7 @@ struct tg_fastq_reader {
 
   ~tg_fastq_reader() {
     if (zs_open) inflateEnd(&zs);
+    if (map) munmap((void*)map, map_len);
     if (f) fclose(f);
   }
   void grow_text(size_t need) {
@@ -217,6 +225,7 @@ struct tg_fastq_reader {
     return true;
   }
   bool fill_text(size_t target) {
+    if (map) return true;
     if (format == 0) return fill_plain(target);
     if (format == 1) return fill_gzip(target);
     return fill_bgzf(target);
@@ -244,7 +253,17 @@ tg_status tg_fastq_open(const char* path, tg_fastq_reader** out) {
         q += 4 + slen;
       }
     }
-  } else {  // plain text: what was read is text already
+  } else if ([&]() {  // plain text in a regular file: map it
+               struct stat sb;
+               if (f == stdin || fstat(fileno(f), &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size == 0) return false;
+               void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+               if (m == MAP_FAILED) return false;
+               madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+               r->map = (const char*)m; r->map_len = (size_t)sb.st_size; r->map_pos = 0;
+               r->text_len = r->map_len; r->text_final = true; r->zin_len = 0;
+               return true;
+             }()) {
+  } else {  // plain text from a pipe: what was read is text already
     r->grow_text(r->zin_len);
     memcpy(r->text.data(), r->zin.data(), r->zin_len);
     r->text_len = r->zin_len;
@@ -276,8 +295,9 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
   size_t consumed = 0;
   for (;;) {
     if (!r->fill_text(target)) return tg_fail(TG_ERR_IO, "FASTQ input: " + r->err);
-    const char* text = r->text.data();
-    const size_t len = r->text_len;
+    const char* text = r->tptr();
+    const size_t len = std::min(r->text_len, target);  // (a mapped file is all there: look at one batch's worth of it)
+    const bool at_end = r->text_final && len == r->text_len;
     // segments cut at record starts, counted on all cores
     unsigned T = len < (4u << 20) ? 1u : T0;
     std::vector<size_t> cut(T + 1, len);
@@ -287,7 +307,7 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
     run_threads(T, [&](unsigned t) {
       seg[t].begin = cut[t]; seg[t].end = cut[t + 1];
       // an inner segment ends at a record start, so its last line is terminated; only the last segment can be cut short
-      tg_fastq_count(text, cut[t], cut[t + 1], t + 1 < T || r->text_final, seg[t].c);
+      tg_fastq_count(text, cut[t], cut[t + 1], t + 1 < T || at_end, seg[t].c);
     });
     n = 0; consumed = 0;
     size_t used = 0;
@@ -313,7 +333,7 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
       }
     }
     seg.resize(used);
-    if (n > 0 || r->text_final) break;
+    if (n > 0 || at_end) break;
     target = std::max(target * 2, len + (1u << 20));  // not a single complete record yet: read on
   }
   if (n == 0) {  // end of input (a truncated last record is dropped, as needletail's reader does on EOF)
@@ -339,14 +359,15 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
       cr += seg[t].c.n; cb += seg[t].c.bases; cn += seg[t].c.names; cq += seg[t].c.quals;
     }
   }
-  const char* text = r->text.data();
+  const char* text = r->tptr();
   run_threads((unsigned)seg.size(), [&](unsigned t) {
     if (seg[t].c.n == 0) return;
     tg_fastq_fill(text, seg[t].begin, seg[t].end, seg[t].c.n, bases, offs + r0[t], b0[t], names, name_offs + r0[t], n0[t], quals,
                   qual_offs + r0[t], q0[t]);
   });
   // what is left starts at a record start
-  if (consumed < r->text_len) memmove(r->text.data(), r->text.data() + consumed, r->text_len - consumed);
+  if (r->map) r->map_pos += consumed;
+  else if (consumed < r->text_len) memmove(r->text.data(), r->text.data() + consumed, r->text_len - consumed);
   r->text_len -= consumed;
   r->bytes_per_read = 0.5 * r->bytes_per_read + 0.5 * ((double)consumed / (double)n);
   r->total_reads += n; r->total_text += consumed;
@@ -432,11 +453,20 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
     if ((st = tg_format_bam_header(ix, &h, &hl)) != TG_OK) { close_out(); return st; }
     fwrite(h, 1, hl, out); S.bytes_out += hl; free(h);
   }
+  // a regular file is written with pwrite from many threads; a pipe / terminal through the stdio stream
+  fflush(out);
+  const int out_fd = fileno(out);
+  off_t file_pos = lseek(out_fd, 0, SEEK_CUR);
+  bool seekable = false;
+  {
+    struct stat sb;
+    seekable = out != stdout && file_pos >= 0 && fstat(out_fd, &sb) == 0 && S_ISREG(sb.st_mode);  // (stdout may be in append mode)
+  }
   Channel to_align, to_write;
   Progress prog;
   std::string err_read, err_write;
   tg_status st_read = TG_OK, st_write = TG_OK;
-  double read_ms = 0, write_ms = 0;
+  double read_ms = 0, write_ms = 0, format_ms = 0;
 
   // stage 1: files -> batches.  A reader owns three buffer sets; batch b may be overwritten by batch b + 3, which is
   // produced only after batch b has been written.
@@ -485,16 +515,37 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
         tg_format_reads(ix, v, j.batch.bases, j.batch.offs, j.batch.names, j.batch.name_offs, j.batch.quals, j.batch.qual_offs,
                         output_fmt == 0 ? 0 : 1, r0, r1, parts[t]);
       });
-      for (unsigned t = 0; t < Tn && st_write == TG_OK; t++) {
-        const char* p = parts[t].s.data();
-        size_t len = parts[t].s.size();
-        if (output_fmt == 2) {
-          z.clear();
-          if ((st_write = tg_sam_text_to_bam(ix, p, len, false, z)) != TG_OK) { err_write = tg_last_error(); break; }
-          p = z.data(); len = z.size();
+      format_ms += now_ms() - t0;
+      if (output_fmt != 2 && seekable) {
+        // every thread copies its own piece into the file (page cache) at its final offset
+        std::vector<off_t> at(Tn + 1, file_pos);
+        for (unsigned t = 0; t < Tn; t++) at[t + 1] = at[t] + (off_t)parts[t].s.size();
+        std::vector<int> bad(Tn, 0);
+        run_threads(Tn, [&](unsigned t) {
+          const char* p = parts[t].s.data();
+          size_t len = parts[t].s.size();
+          off_t o = at[t];
+          while (len) {
+            const ssize_t w = pwrite(out_fd, p, len, o);
+            if (w <= 0) { bad[t] = 1; return; }
+            p += w; len -= (size_t)w; o += w;
+          }
+        });
+        for (int b : bad) if (b) { st_write = TG_ERR_IO; err_write = "write error"; }
+        S.bytes_out += (uint64_t)(at[Tn] - file_pos);
+        file_pos = at[Tn];
+      } else {
+        for (unsigned t = 0; t < Tn && st_write == TG_OK; t++) {
+          const char* p = parts[t].s.data();
+          size_t len = parts[t].s.size();
+          if (output_fmt == 2) {
+            z.clear();
+            if ((st_write = tg_sam_text_to_bam(ix, p, len, false, z)) != TG_OK) { err_write = tg_last_error(); break; }
+            p = z.data(); len = z.size();
+          }
+          if (len && fwrite(p, 1, len, out) != len) { st_write = TG_ERR_IO; err_write = "write error"; }
+          S.bytes_out += len;
         }
-        if (len && fwrite(p, 1, len, out) != len) { st_write = TG_ERR_IO; err_write = "write error"; }
-        S.bytes_out += len;
       }
       S.n_reads += n; S.n_alns += j.res.n_alns; S.n_batches++;
       write_ms += now_ms() - t0;
@@ -527,7 +578,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
     S.bytes_out += sizeof(eof_block);
   }
   close_out();
-  S.read_ms = read_ms; S.align_ms = align_ms; S.write_ms = write_ms; S.wall_ms = now_ms() - t_start;
+  S.read_ms = read_ms; S.align_ms = align_ms; S.write_ms = write_ms; S.format_ms = format_ms; S.wall_ms = now_ms() - t_start;
   if (stats) *stats = S;
   if (st_read != TG_OK) return tg_fail(st_read, err_read);
   if (st_align != TG_OK) return st_align == TG_ERR_INTERNAL && prog.failed ? tg_fail(st_write != TG_OK ? st_write : TG_ERR_INTERNAL, err_write.empty() ? "pipeline stage failed" : err_write) : st_align;

@@ -24,13 +24,14 @@ rows = bases.reshape(n, L)
 q = b"F" * L
 fq = b"".join(b"@r%d\n" % r + rows[r].tobytes() + b"\n+\n" + q + b"\n" for r in range(n))
 tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-files = {"plain": fq, "bgzf": bgzf(fq), "gzip": gzip.compress(fq, 4)}
+kinds = os.environ.get("TG_INPUTS", "plain,bgzf,gzip").split(",")
+files = {k: (fq if k == "plain" else bgzf(fq) if k == "bgzf" else gzip.compress(fq, 4)) for k in kinds}
 for k, v in files.items():
     open(os.path.join(tmp, "q." + k), "wb").write(v)
-print(f"{n} reads, FASTQ text {len(fq) / 1e6:.0f} MB (bgzf {len(files['bgzf']) / 1e6:.0f} MB, gzip {len(files['gzip']) / 1e6:.0f} MB), "
+print(f"{n} reads, FASTQ text {len(fq) / 1e6:.0f} MB (" + ", ".join(f"{k} {len(v) / 1e6:.0f} MB" for k, v in files.items()) + "), "
       f"batches of {batch}, {gpus} GPU(s), host threads {os.cpu_count()}, files in {tmp}", flush=True)
 devices = list(range(gpus)) if gpus > 1 else None
-for inp in ("plain", "bgzf", "gzip"):
+for inp in kinds:
     for fmt in (OutputFormat.Paf, OutputFormat.Sam, OutputFormat.Bam):
         if fmt == OutputFormat.Bam and inp != "plain":
             continue
@@ -43,7 +44,7 @@ for inp in ("plain", "bgzf", "gzip"):
             if best is None or st["wall_ms"] < best["wall_ms"]:
                 best = dict(st, total_s=dt)
         print(f"{inp:5s} -> {fmt:3s}: {n / best['wall_ms'] / 1e3:6.2f} M reads/s (pipeline {best['wall_ms']:.0f} ms; stage busy ms: read {best['read_ms']:.0f}, "
-              f"align {best['align_ms']:.0f}, write {best['write_ms']:.0f}; {best['bytes_out'] / 1e6:.0f} MB out; call incl. context {best['total_s']:.2f} s)", flush=True)
+              f"align {best['align_ms']:.0f}, write {best['write_ms']:.0f} (format {best['format_ms']:.0f}); {best['bytes_out'] / 1e6:.0f} MB out; call incl. context {best['total_s']:.2f} s)", flush=True)
 for f in os.listdir(tmp):
     os.remove(os.path.join(tmp, f))
 os.rmdir(tmp)
