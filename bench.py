@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--swg-pairs", type=int, default=1 << 20, help="config 5 microbench: pairs per band width per GPU")
     ap.add_argument("--no-swg-microbench", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true", help="skip the default-flags / pageable / file-pipeline blocks")
+    ap.add_argument("--file-reads", type=int, default=4_000_000, help="reads of the FASTQ -> PAF / SAM file-pipeline block")
     return ap.parse_args()
 
 
@@ -400,6 +402,89 @@ def run_multi(args):
     m.close()
 
 
+def extra_workloads(args, index, aligner, bases, offs, n, dev, stream):
+    """Single-GPU side measurements next to the headline (not the `value`): config 4's DEFAULT-flags variant
+    (src/main.rs:115-132: -k20 -s0.66, intron mode off), the host-buffer call with PAGEABLE inputs, and the file-to-file
+    pipeline (FASTQ file -> tg_align_files -> PAF / SAM file)."""
+    import tempfile as _tf
+    import torch
+    from thermite_b200 import AlignOpts, Aligner, OutputFormat, align_reads_from_file
+    out = {}
+    steps = max(2, args.steps // 2)
+
+    # (1) pageable inputs through the same call as `e2e` (a caller that did not page-lock its buffers)
+    for _ in range(2):
+        aligner.align_reads_compact_raw(bases.ctypes.data, offs.ctypes.data, n)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        aligner.align_reads_compact_raw(bases.ctypes.data, offs.ctypes.data, n)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    out["e2e_pageable_inputs"] = dict(value=n / (ms / 1e3), unit="reads/s", ms_per_step=ms,
+                                      call="tg_align_batch_compact with ordinary (pageable) host arrays")
+
+    # (2) default flags: fewer hits survive the 0.66 x L score floor, exonic records only
+    d_bases = torch.from_numpy(bases).to(dev)
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    h_bases = torch.from_numpy(bases).pin_memory()
+    h_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    al2 = Aligner(index, AlignOpts(), device=dev.index)
+    st2 = torch.cuda.ExternalStream(al2.stream_ptr(), device=dev)
+    for _ in range(2):
+        r2 = al2.align_reads_device_raw(d_bases.data_ptr(), d_offs.data_ptr(), n, int(offs[n]), READ_LEN)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st2)
+    for _ in range(steps):
+        r2 = al2.align_reads_device_raw(d_bases.data_ptr(), d_offs.data_ptr(), n, int(offs[n]), READ_LEN)
+    e1.record(st2)
+    torch.cuda.synchronize()
+    dms = e0.elapsed_time(e1) / steps
+    al2.align_reads_compact_raw(h_bases.data_ptr(), h_offs.data_ptr(), n)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        h2 = al2.align_reads_compact_raw(h_bases.data_ptr(), h_offs.data_ptr(), n)
+    torch.cuda.synchronize()
+    hms = (time.perf_counter() - t0) * 1e3 / steps
+    out["default_flags"] = dict(flags="-k20 -s0.66 (intron mode off): src/main.rs:115-132", reads_per_step=n,
+                                value=n / (dms / 1e3), unit="reads/s", ms_per_step=dms,
+                                e2e=dict(value=n / (hms / 1e3), ms_per_step=hms),
+                                alns_per_read=r2.n_alns / n, swg_ext_per_read=r2.swg_extensions / n)
+    del al2, d_bases, d_offs
+
+    # (3) FASTQ file -> PAF / SAM file (tg_align_files: reader, aligner, writers overlapped; files on tmpfs)
+    nf = min(args.file_reads, n)
+    rows = bases[: nf * READ_LEN].reshape(nf, READ_LEN)
+    q = b"F" * READ_LEN
+    tmp = _tf.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        qp = os.path.join(tmp, "q.fastq")
+        with open(qp, "wb") as f:
+            for lo in range(0, nf, 65536):
+                f.write(b"".join(b"@r%d\n" % r + rows[r].tobytes() + b"\n+\n" + q + b"\n" for r in range(lo, min(nf, lo + 65536))))
+        opts = AlignOpts(FLAGS["k"], FLAGS["pct"], FLAGS["min_score"], FLAGS["score_range"], FLAGS["intron_mode"])
+        fp = {}
+        for fmt in (OutputFormat.Paf, OutputFormat.Sam):
+            best = None
+            for _ in range(2):
+                st = align_reads_from_file(index, [qp], os.path.join(tmp, "out." + fmt), fmt, opts, device=dev.index, batch_reads=1 << 19)
+                if best is None or st["wall_ms"] < best["wall_ms"]:
+                    best = st
+            fp[fmt] = dict(value=nf / (best["wall_ms"] / 1e3), unit="reads/s", wall_ms=best["wall_ms"], read_ms=best["read_ms"],
+                           align_ms=best["align_ms"], write_ms=best["write_ms"], format_ms=best["format_ms"],
+                           bytes_out=int(best["bytes_out"]), batches=int(best["n_batches"]))
+        out["file_pipeline"] = dict(reads=nf, input="plain FASTQ on tmpfs, %d MB" % (os.path.getsize(qp) >> 20), host_threads=os.cpu_count(),
+                                    batch_reads=1 << 19,
+                                    note="best of 2; a fresh context per run, so the first batches grow the device and page-locked buffers", **fp)
+    finally:
+        for f in os.listdir(tmp):
+            os.remove(os.path.join(tmp, f))
+        os.rmdir(tmp)
+    return out
+
+
 def main():
     args = parse_args()
     # exactly ONE line on stdout (the JSON): libraries that print there (NCCL's version banner) go to stderr instead
@@ -668,6 +753,8 @@ def _main(args):
                              for bw, a in zip(SWG_BWS, agg)],
             identical_to_oracle=(all(r["identical"] for r in swg_rows) if swg_rows[0].get("oracle_digest") else None),
             min_frac_executed=min(r["frac_executed"] for r in swg_rows))
+    if world == 1 and not args.no_extra_workloads:
+        line["other_workloads"] = extra_workloads(args, index, aligner, bases, offs, n, dev, stream)
     if world == 1 and not args.no_cpu_baseline:
         cb, (n_cpu, orc_res) = cpu_baseline(fa, gtf, bases, offs, args.cpu_seconds, os.cpu_count() or 1)
         line["cpu_baseline"] = cb

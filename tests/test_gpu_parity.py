@@ -383,3 +383,29 @@ def test_align_files_gz_inputs_many_batches(tmp_path):
         assert st["n_reads"] == 3000 and st["n_batches"] >= 12
         want = oix.align_fastq_text(fq1 + fq2, k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True, sam=sam)
         assert op.read_bytes() == want, fmt   # (the oracle's SAM text starts with the header, like the file)
+
+
+def test_contexts_share_one_kmer_table():
+    """Two contexts of one index with the same min_seed_len share the k-mer table (reference counted); a third with another
+    k builds its own.  Results do not depend on which context built the table or on the order they are closed in."""
+    import torch
+    contigs, gtf, txs, fa = small_world(4)
+    bases, offs = synth.make_reads(9, contigs, txs, 400, L=91, sub=0.02, ins=0.003, dele=0.003)
+    ix = Index.create_from_memory(fa, gtf)
+    oix = orc.Index.create(fa, gtf)
+    ores = oix.align_batch(bases, offs, k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True)
+    a1 = Aligner(ix, AlignOpts(20, 0.0, 30, 1, True))
+    free1 = torch.cuda.mem_get_info()[0]
+    a2 = Aligner(ix, AlignOpts(20, 0.66, 30, 1, False))   # same k, other options: same table
+    free2 = torch.cuda.mem_get_info()[0]
+    assert a1.kmer_table_bytes() == a2.kmer_table_bytes() > 0
+    assert free1 - free2 < a1.kmer_table_bytes() + (64 << 20)  # a context's own allocations, but no second table
+    a3 = Aligner(ix, AlignOpts(12, 0.0, 30, 1, True))
+    _cmp(a1.align_reads(bases, offs), ores, 400)
+    a1.close()                                              # the table lives on for a2
+    r2 = a2.align_reads(bases, offs)
+    _cmp(r2, oix.align_batch(bases, offs, k=20, pct=0.66, min_score=30, score_range=1, intron_mode=False), 400)
+    a4 = Aligner(ix, AlignOpts(20, 0.0, 30, 1, True))
+    a2.close()
+    _cmp(a4.align_reads(bases, offs), ores, 400)
+    _cmp(a3.align_reads(bases, offs), oix.align_batch(bases, offs, k=12, pct=0.0, min_score=30, score_range=1, intron_mode=True), 400)

@@ -400,10 +400,15 @@ class Aligner:
         self._h = h
         self._ref_names = [r.name for r in index.refs()]
 
+    def close(self):
+        """Destroy the context (its k-mer table stays while another context of the index uses it)."""
+        if getattr(self, "_owned", True) and getattr(self, "_h", None):
+            lib().tg_ctx_destroy(self._h)
+        self._h = None
+
     def __del__(self):
         try:
-            if getattr(self, "_owned", True):
-                lib().tg_ctx_destroy(self._h)
+            self.close()
         except Exception:
             pass
 

@@ -26,6 +26,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <mutex>
 #include <vector>
 
 #include "tg_rounds.h"
@@ -1151,12 +1152,22 @@ struct PinBuf {
 
 }  // namespace
 
+// A k-mer table depends only on (index, min_seed_len): contexts of one index with the same k share one table (two
+// contexts on a GPU used to hold 4.3 GB each for chr21).  Reference counted; freed with its last context.
+struct TgKmerTable {
+  uint32_t k = 0;
+  TgSlot* slots = nullptr;
+  uint64_t n_slots = 0;
+  int refs = 0;
+};
 struct tg_index {
   int device = 0;
   void* d_blob = nullptr;
   bool owns = false;
   TgBlobHeader hdr;
   TgIndexDev dev;
+  mutable std::recursive_mutex table_mu;  // (recursive: a failing tg_ctx_create destroys its context while it holds the lock)
+  mutable std::vector<TgKmerTable> tables;
 };
 
 struct tg_ctx {
@@ -1336,7 +1347,15 @@ void tg_ctx_destroy(tg_ctx* c) {
     b->release();
   for (PinBuf* b : {&c->h_first, &c->h_count, &c->h_alns, &c->h_ops, &c->h_seeds, &c->h_seed_first, &c->h_seed_count, &c->h_late,
                     &c->h2_first, &c->h2_count, &c->h2_alns, &c->h2_ops}) b->release();
-  if (c->slots) cudaFree(c->slots);
+  if (c->slots && c->ix) {
+    std::lock_guard<std::recursive_mutex> l(c->ix->table_mu);
+    for (size_t i = 0; i < c->ix->tables.size(); i++) {
+      TgKmerTable& t = c->ix->tables[i];
+      if (t.slots != c->slots) continue;
+      if (--t.refs == 0) { cudaFree(t.slots); c->ix->tables.erase(c->ix->tables.begin() + (long)i); }
+      break;
+    }
+  }
   if (c->d_ctr) cudaFree(c->d_ctr);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1404,23 +1423,33 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
   CTX_CHECK(cudaMalloc(&c->d_ctr, sizeof(DevCounters)));
   CTX_CHECK(cudaMallocHost(&c->h_ctr, sizeof(DevCounters)));
   CTX_CHECK(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
-  // k-mer table for this min_seed_len, built on the device from the suffix array
-  const uint64_t T = ix->dev.text_len;
-  const int threads = 256;
-  const int blocks = (int)std::min<uint64_t>((T + threads - 1) / threads, (uint64_t)c->n_sms * 32);
-  k_kmer_count<<<blocks, threads, 0, c->stream>>>(ix->dev.text4, T, ix->dev.sa, opts->min_seed_len, c->d_ctr);
-  CTX_CHECK(cudaGetLastError());
-  CTX_CHECK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
-  CTX_CHECK(cudaStreamSynchronize(c->stream));
-  uint64_t groups = c->h_ctr->kmer_groups;
-  uint64_t n_slots = 1024;
-  while (n_slots < 2 * groups + 2) n_slots <<= 1;
-  c->n_slots = n_slots;
-  CTX_CHECK(cudaMalloc(&c->slots, n_slots * sizeof(TgSlot)));
-  CTX_CHECK(cudaMemsetAsync(c->slots, 0, n_slots * sizeof(TgSlot), c->stream));
-  k_kmer_insert<<<blocks, threads, 0, c->stream>>>(ix->dev.text4, T, ix->dev.sa, opts->min_seed_len, c->slots, n_slots - 1);
-  CTX_CHECK(cudaGetLastError());
-  CTX_CHECK(cudaStreamSynchronize(c->stream));
+  // k-mer table for this min_seed_len: shared with the other contexts of this index, else built on the device from the
+  // suffix array (sized from the number of distinct k-mers: <= 50 % load)
+  {
+    std::lock_guard<std::recursive_mutex> l(ix->table_mu);
+    for (TgKmerTable& t : ix->tables)
+      if (t.k == opts->min_seed_len) { c->slots = t.slots; c->n_slots = t.n_slots; t.refs++; break; }
+    if (!c->slots) {
+      const uint64_t T = ix->dev.text_len;
+      const int threads = 256;
+      const int blocks = (int)std::min<uint64_t>((T + threads - 1) / threads, (uint64_t)c->n_sms * 32);
+      k_kmer_count<<<blocks, threads, 0, c->stream>>>(ix->dev.text4, T, ix->dev.sa, opts->min_seed_len, c->d_ctr);
+      CTX_CHECK(cudaGetLastError());
+      CTX_CHECK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+      CTX_CHECK(cudaStreamSynchronize(c->stream));
+      uint64_t groups = c->h_ctr->kmer_groups;
+      uint64_t n_slots = 1024;
+      while (n_slots < 2 * groups + 2) n_slots <<= 1;
+      TgSlot* slots = nullptr;
+      CTX_CHECK(cudaMalloc(&slots, n_slots * sizeof(TgSlot)));
+      c->slots = slots; c->n_slots = n_slots;
+      ix->tables.push_back(TgKmerTable{opts->min_seed_len, slots, n_slots, 1});  // (from here on tg_ctx_destroy releases it)
+      CTX_CHECK(cudaMemsetAsync(c->slots, 0, n_slots * sizeof(TgSlot), c->stream));
+      k_kmer_insert<<<blocks, threads, 0, c->stream>>>(ix->dev.text4, T, ix->dev.sa, opts->min_seed_len, c->slots, n_slots - 1);
+      CTX_CHECK(cudaGetLastError());
+      CTX_CHECK(cudaStreamSynchronize(c->stream));
+    }
+  }
 #undef CTX_CHECK
   *out = c;
   return TG_OK;
