@@ -23,6 +23,15 @@
  * Threading: a tg_index is immutable and may be shared by any number of contexts/threads.  A tg_ctx owns a
  * CUDA stream plus scratch and is NOT thread-safe: use one per host thread / per GPU (the reference's
  * ThermiteAligner is Clone + Send with an Arc<Index>, src/wrapper.rs:20-27).
+ *
+ * Scale limits of this build (the reference uses usize throughout, src/index.rs:383-388); every one is reported as
+ * TG_ERR_CAPACITY / TG_ERR_INVALID, never as a wrong result:
+ *   - both-strand concatenated text < 2^31 symbols (32-bit suffix array and text positions): about 1.07 Gbp of reference,
+ *     i.e. any single human chromosome or a mouse-sized transcriptome, not a whole human genome in one index;
+ *   - reads <= TG_MAX_READ_LEN (512) symbols; min_seed_len <= 32;
+ *   - one batch: < 2^32 reads, seed hits, records and operation words (split larger batches);
+ *   - the k-mer table takes 16 B x the next power of two above twice the number of distinct k-mers (4.3 GB for chr21,
+ *     shared by all contexts of an index that use the same min_seed_len).
  */
 #ifndef THERMITE_GPU_H
 #define THERMITE_GPU_H

@@ -64,6 +64,16 @@ def test_bad_inputs_are_errors_not_crashes():
         tb.Index.create_from_memory(b">a\nACGTACGT\n", b'b\t.\texon\t1\t4\t.\t+\t.\tgene_id "g"; transcript_id "t";\n')
 
 
+def test_text_beyond_the_32_bit_limit_is_a_capacity_error():
+    """The reference indexes with usize (src/index.rs:383-388); this build keeps 32-bit text positions and must say so:
+    a reference whose both-strand text reaches 2^31 symbols is refused with TG_ERR_CAPACITY before anything is built."""
+    n = (1 << 30) + 4096                       # 2 * (n + 1) symbols >= 2^31
+    fa = b">big\n" + b"A" * n + b"\n"
+    with pytest.raises(tb.ThermiteError) as e:
+        tb.Index.create_from_memory(fa, b"")
+    assert "2^31" in str(e.value)
+
+
 def test_corrupt_index_blobs_are_refused(tmp_path):
     """A truncated, stale or foreign .tai must fail cleanly in tg_index_host_load / from_blob (the reference's bincode load
     does), never reach the string decoder or a kernel with out-of-range offsets."""
