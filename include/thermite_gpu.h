@@ -410,6 +410,8 @@ typedef struct tg_file_stats {
   double read_ms, align_ms, write_ms;  /* busy time of each stage */
   double format_ms;                    /* the part of write_ms spent turning records into text */
   double wall_ms;
+  uint64_t warm_reads;                 /* reads of the first two batches and the time until they were written: the context's */
+  double warm_ms;                      /* buffers grow there; (n_reads - warm_reads) / (wall_ms - warm_ms) is the steady rate */
 } tg_file_stats;
 tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_multi* multi, const char* const* query_paths, int n_paths,
                          const char* out_path, int output_fmt, uint32_t batch_reads, tg_file_stats* stats);

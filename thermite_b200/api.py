@@ -794,10 +794,13 @@ class _ReadBatch(C.Structure):
 class FileStats(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_alns", C.c_uint64), ("n_batches", C.c_uint64), ("bytes_out", C.c_uint64),
                 ("read_ms", C.c_double), ("align_ms", C.c_double), ("write_ms", C.c_double), ("format_ms", C.c_double),
-                ("wall_ms", C.c_double)]
+                ("wall_ms", C.c_double), ("warm_reads", C.c_uint64), ("warm_ms", C.c_double)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        if self.n_batches > 2 and self.wall_ms > self.warm_ms:
+            d["steady_reads_per_s"] = (self.n_reads - self.warm_reads) / ((self.wall_ms - self.warm_ms) / 1e3)
+        return d
 
 
 class FastqReader:

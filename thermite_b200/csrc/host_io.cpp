@@ -19,11 +19,33 @@ namespace {
 unsigned mapq_of(uint64_t n) {
   if (n <= 1) return 255;
   if (n >= 5) return 0;
-  return (unsigned)std::lround(-10.0f * std::log10(1.0f - 1.0f / (float)n));
+  static const unsigned tab[5] = {255, 255, (unsigned)std::lround(-10.0f * std::log10(1.0f - 1.0f / 2.0f)),
+                                  (unsigned)std::lround(-10.0f * std::log10(1.0f - 1.0f / 3.0f)),
+                                  (unsigned)std::lround(-10.0f * std::log10(1.0f - 1.0f / 4.0f))};
+  return tab[n];
 }
 
-// to_noodles_cigar (src/aln_writer.rs:279-323): Match and Subst both print as M and merge
-void cigar(TgOut& o, const uint32_t* w, uint32_t n) {
+// decimal digits of v at d, two at a time; returns the end
+inline char* put_num(char* d, uint64_t v) {
+  static const char lut[201] =
+      "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263"
+      "646566676869707172737475767778798081828384858687888990919293949596979899";
+  char buf[24];
+  int k = 24;
+  while (v >= 100) {
+    const unsigned q = (unsigned)(v % 100);
+    v /= 100;
+    buf[--k] = lut[2 * q + 1]; buf[--k] = lut[2 * q];
+  }
+  if (v >= 10) { buf[--k] = lut[2 * v + 1]; buf[--k] = lut[2 * v]; }
+  else buf[--k] = (char)('0' + v);
+  memcpy(d, buf + k, (size_t)(24 - k));
+  return d + (24 - k);
+}
+
+// to_noodles_cigar (src/aln_writer.rs:279-323): Match and Subst both print as M and merge.  Writes at d (at most 21 bytes
+// per operation word), returns the end.
+char* put_cigar(char* d, const uint32_t* w, uint32_t n) {
   static const char sym[6] = {'M', 'M', 'D', 'I', 'S', 'N'};
   uint32_t i = 0;
   while (i < n) {
@@ -31,20 +53,23 @@ void cigar(TgOut& o, const uint32_t* w, uint32_t n) {
     if (kind <= TG_OP_SUBST) {
       uint64_t tot = run;
       while (i + 1 < n && (w[i + 1] & 7u) <= TG_OP_SUBST) { tot += w[i + 1] >> 3; i++; }
-      o.num(tot);
-      o.s.push_back('M');
+      d = put_num(d, tot);
+      *d++ = 'M';
     } else if (kind >= TG_OP_XCLIP) {
       // equal adjacent clips collapse into one entry carrying a single clip's length (:309-316, :292-294)
       while (i + 1 < n && w[i + 1] == w[i]) i++;
-      o.num(run);
-      o.s.push_back(sym[kind]);
+      d = put_num(d, run);
+      *d++ = sym[kind];
     } else {
-      o.num(run);
-      o.s.push_back(sym[kind]);
+      d = put_num(d, run);
+      *d++ = sym[kind];
     }
     i++;
   }
+  return d;
 }
+inline char* put_str(char* d, const char* lit, size_t n) { memcpy(d, lit, n); return d + n; }
+#define PUT_LIT(d, lit) put_str(d, lit, sizeof(lit) - 1)
 
 char comp(char c) {  // bio::alphabets::dna::revcomp keeps case and maps IUPAC codes; ACGTN is what reads carry
   switch (c) {
@@ -91,6 +116,16 @@ void tg_format_reads(const tg_index_host* ix, const TgRecView& v, const uint8_t*
   const TgRef* refs = (const TgRef*)(ix->blob.data() + bh->off_refs);
   const uint64_t* tso = (const uint64_t*)(ix->blob.data() + bh->off_tx_seq_off);
   for (uint32_t r = r0; r < r1; r++) {
+    // the record pool is in the device's allocation order, not in read order: fetch ahead (records 8 reads ahead, their
+    // operation words 4 reads ahead)
+    if (r + 8 < r1 && v.count[r + 8]) {
+      const uint64_t f8 = v.first64 ? v.first64[r + 8] : (uint64_t)v.first32[r + 8];
+      if (v.wide) __builtin_prefetch(v.wide + f8); else __builtin_prefetch(v.comp + f8);
+    }
+    if (r + 4 < r1 && v.count[r + 4]) {
+      const uint64_t f4 = v.first64 ? v.first64[r + 4] : (uint64_t)v.first32[r + 4];
+      __builtin_prefetch(v.ops + (v.wide ? v.wide[f4].ops_off : v.comp[f4].ops_off));
+    }
     const char* nm = (const char*)names + name_offs[r];
     size_t nm_len = name_offs[r + 1] - name_offs[r];
     size_t qn_len = nm_len;  // format_read_name: cut at the first space (src/aln_writer.rs:344-349)
@@ -124,60 +159,74 @@ void tg_format_reads(const tg_index_host* ix, const TgRecView& v, const uint8_t*
           if (kind <= TG_OP_INS) n_match_gap += run;
           else if (kind == TG_OP_XCLIP) n_match_gap += 1;
         }
-        o.s.append(nm, nm_len); o.s.push_back('\t');
-        o.num(L); o.s.push_back('\t');
-        o.num(a.xstart); o.s.push_back('\t');
-        o.num(a.xend); o.s.push_back('\t');
-        o.s.push_back(a.strand ? '+' : '-'); o.s.push_back('\t');
-        o.s += rname; o.s.push_back('\t');
-        o.num(a.ylen); o.s.push_back('\t');
-        o.num(a.ystart); o.s.push_back('\t');
-        o.num(a.yend); o.s.push_back('\t');
-        o.num(n_match); o.s.push_back('\t');
-        o.num(n_match_gap); o.s.push_back('\t');
-        o.num(mapq_of(cnt)); o.s += "\t\n";
+        // one reservation per line, then plain stores (a line holds the two names and 11 numbers of at most 20 digits)
+        char* d = o.s.room(nm_len + rname.size() + 11 * 21 + 16);
+        memcpy(d, nm, nm_len); d += nm_len; *d++ = '\t';
+        d = put_num(d, L); *d++ = '\t';
+        d = put_num(d, a.xstart); *d++ = '\t';
+        d = put_num(d, a.xend); *d++ = '\t';
+        *d++ = a.strand ? '+' : '-'; *d++ = '\t';
+        memcpy(d, rname.data(), rname.size()); d += rname.size(); *d++ = '\t';
+        d = put_num(d, a.ylen); *d++ = '\t';
+        d = put_num(d, a.ystart); *d++ = '\t';
+        d = put_num(d, a.yend); *d++ = '\t';
+        d = put_num(d, n_match); *d++ = '\t';
+        d = put_num(d, n_match_gap); *d++ = '\t';
+        d = put_num(d, mapq_of(cnt)); *d++ = '\t'; *d++ = '\n';
+        o.s.n = (size_t)(d - o.s.p);
       } else {  // aln_to_sam_record (src/aln_writer.rs:118-238)
         unsigned flags = 0;
         if (!a.strand) flags |= 0x10;
         if (!a.primary) flags |= 0x100;
         uint64_t n_mis = 0;
         for (uint32_t k = 0; k < a.ops_len; k++) if ((w[k] & 7u) == TG_OP_SUBST) n_mis += w[k] >> 3;
-        o.s.append(nm, qn_len); o.s.push_back('\t');
-        o.num(flags); o.s.push_back('\t');
-        o.s += rname; o.s.push_back('\t');
-        o.num(a.ystart + 1); o.s.push_back('\t');
-        o.num(mapq_of(cnt)); o.s.push_back('\t');
-        cigar(o, w, a.ops_len);
-        o.s += "\t*\t0\t0\t";
-        const char* sq = (const char*)bases + offs[r];
-        if (L == 0) o.s.push_back('*');
-        else if (a.strand) o.s.append(sq, L);
-        else for (uint64_t k = L; k-- > 0;) o.s.push_back(comp(sq[k]));
-        o.s.push_back('\t');
-        const char* ql = (const char*)quals + qual_offs[r];
-        size_t qn = qual_offs[r + 1] - qual_offs[r];
-        if (qn == 0) o.s.push_back('*');
-        else if (a.strand) o.s.append(ql, qn);
-        else for (size_t k = qn; k-- > 0;) o.s.push_back(ql[k]);
-        o.s += "\tAS:i:"; o.snum(a.score);
-        o.s += "\tNH:i:"; o.num(cnt);
-        o.s += "\tHI:i:"; o.num(i + 1);
-        o.s += "\tnM:i:"; o.num(n_mis);
+        // one reservation per line, then plain stores
+        const std::string* tx_id = nullptr; const std::string* gid = nullptr; const std::string* gname = nullptr;
         if (a.aln_type == TG_ALN_EXONIC) {
-          uint32_t g = ix->tx_gene[a.tx_or_gene_idx];
-          o.s += "\tTX:Z:"; o.s += ix->tx_ids[a.tx_or_gene_idx]; o.s += ",+"; o.num(a.tx_ystart); o.s.push_back(',');
-          cigar(o, v.ops + a.tx_ops_off, a.tx_ops_len);
-          o.s += "\tGX:Z:"; o.s += ix->gene_ids[g];
-          o.s += "\tGN:Z:"; o.s += ix->gene_names[g];
-          o.s += "\tRE:A:E";
+          const uint32_t g = ix->tx_gene[a.tx_or_gene_idx];
+          tx_id = &ix->tx_ids[a.tx_or_gene_idx]; gid = &ix->gene_ids[g]; gname = &ix->gene_names[g];
         } else if (a.aln_type == TG_ALN_INTRONIC) {
-          o.s += "\tGX:Z:"; o.s += ix->gene_ids[a.tx_or_gene_idx];
-          o.s += "\tGN:Z:"; o.s += ix->gene_names[a.tx_or_gene_idx];
-          o.s += "\tRE:A:N";
-        } else {
-          o.s += "\tRE:A:I";
+          gid = &ix->gene_ids[a.tx_or_gene_idx]; gname = &ix->gene_names[a.tx_or_gene_idx];
         }
-        o.s.push_back('\n');
+        const size_t qn = qual_offs[r + 1] - qual_offs[r];
+        char* d = o.s.room(qn_len + rname.size() + (size_t)L + qn + 21 * ((size_t)a.ops_len + a.tx_ops_len) + (tx_id ? tx_id->size() : 0) +
+                           (gid ? gid->size() + gname->size() : 0) + 256);
+        memcpy(d, nm, qn_len); d += qn_len; *d++ = '\t';
+        d = put_num(d, flags); *d++ = '\t';
+        memcpy(d, rname.data(), rname.size()); d += rname.size(); *d++ = '\t';
+        d = put_num(d, a.ystart + 1); *d++ = '\t';
+        d = put_num(d, mapq_of(cnt)); *d++ = '\t';
+        d = put_cigar(d, w, a.ops_len);
+        d = PUT_LIT(d, "\t*\t0\t0\t");
+        const char* sq = (const char*)bases + offs[r];
+        if (L == 0) *d++ = '*';
+        else if (a.strand) { memcpy(d, sq, L); d += L; }
+        else for (uint64_t k = L; k-- > 0;) *d++ = comp(sq[k]);
+        *d++ = '\t';
+        const char* ql = (const char*)quals + qual_offs[r];
+        if (qn == 0) *d++ = '*';
+        else if (a.strand) { memcpy(d, ql, qn); d += qn; }
+        else for (size_t k = qn; k-- > 0;) *d++ = ql[k];
+        d = PUT_LIT(d, "\tAS:i:");
+        if (a.score < 0) { *d++ = '-'; d = put_num(d, (uint64_t)(-(int64_t)a.score)); } else d = put_num(d, (uint64_t)a.score);
+        d = PUT_LIT(d, "\tNH:i:"); d = put_num(d, cnt);
+        d = PUT_LIT(d, "\tHI:i:"); d = put_num(d, i + 1);
+        d = PUT_LIT(d, "\tnM:i:"); d = put_num(d, n_mis);
+        if (a.aln_type == TG_ALN_EXONIC) {
+          d = PUT_LIT(d, "\tTX:Z:"); d = put_str(d, tx_id->data(), tx_id->size()); d = PUT_LIT(d, ",+"); d = put_num(d, a.tx_ystart); *d++ = ',';
+          d = put_cigar(d, v.ops + a.tx_ops_off, a.tx_ops_len);
+          d = PUT_LIT(d, "\tGX:Z:"); d = put_str(d, gid->data(), gid->size());
+          d = PUT_LIT(d, "\tGN:Z:"); d = put_str(d, gname->data(), gname->size());
+          d = PUT_LIT(d, "\tRE:A:E");
+        } else if (a.aln_type == TG_ALN_INTRONIC) {
+          d = PUT_LIT(d, "\tGX:Z:"); d = put_str(d, gid->data(), gid->size());
+          d = PUT_LIT(d, "\tGN:Z:"); d = put_str(d, gname->data(), gname->size());
+          d = PUT_LIT(d, "\tRE:A:N");
+        } else {
+          d = PUT_LIT(d, "\tRE:A:I");
+        }
+        *d++ = '\n';
+        o.s.n = (size_t)(d - o.s.p);
       }
     }
   }

@@ -9,6 +9,8 @@
 // Product code: must never include anything from oracle/.
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -16,6 +18,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -30,13 +33,26 @@
 
 namespace {
 
-unsigned host_threads() { return (unsigned)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64); }
+// threads a stage may use: all cores by default; TG_IO_THREADS overrides (reader and writers run at the same time inside
+// tg_align_files, so half the cores each avoids oversubscription there)
+unsigned host_threads() {
+  static const unsigned n = []() {
+    const char* e = getenv("TG_IO_THREADS");
+    const long v = e ? atol(e) : 0;
+    return v > 0 ? (unsigned)std::min<long>(v, 64) : (unsigned)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64);
+  }();
+  return n;
+}
+
+// Parser / formatter workers run at a lower priority than the thread that drives the GPU: with reader and writers busy
+// on every core, the launching thread was descheduled between kernel launches and a 25 ms batch took 50 ms.
+void lower_priority() { setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 10); }
 
 template <class F>
 void run_threads(unsigned T, F&& f) {
   if (T <= 1) { f(0u); return; }
   std::vector<std::thread> th;
-  for (unsigned t = 0; t < T; t++) th.emplace_back([&f, t]() { f(t); });
+  for (unsigned t = 0; t < T; t++) th.emplace_back([&f, t]() { lower_priority(); f(t); });
   for (auto& x : th) x.join();
 }
 
@@ -471,6 +487,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
   // stage 1: files -> batches.  A reader owns three buffer sets; batch b may be overwritten by batch b + 3, which is
   // produced only after batch b has been written.
   std::thread producer([&]() {
+    lower_priority();
     uint64_t b = 0;
     for (int f = 0; f < n_paths && st_read == TG_OK; f++) {
       tg_fastq_reader* r = nullptr;
@@ -497,6 +514,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
   // stage 3: records -> text -> file.  Per-thread text buffers are kept across batches (fresh buffers cost a page fault
   // per 4 KiB of output) and written one after the other: no merged copy of the batch's text is ever made.
   std::thread writer([&]() {
+    lower_priority();
     const unsigned T = host_threads();
     std::vector<TgOut> parts(T);
     std::string z;
@@ -548,6 +566,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
         }
       }
       S.n_reads += n; S.n_alns += j.res.n_alns; S.n_batches++;
+      if (S.n_batches == 2) { S.warm_reads = S.n_reads; S.warm_ms = now_ms() - t_start; }  // first batches: buffers grow, a batch may be re-run
       write_ms += now_ms() - t0;
       if (st_write != TG_OK) prog.fail();
       prog.done_one();

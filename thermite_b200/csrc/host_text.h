@@ -33,13 +33,21 @@ struct TgText {
 };
 struct TgOut {
   TgText s;
-  void num(uint64_t v) {
+  void num(uint64_t v) {  // decimal digits, two at a time
+    static const char lut[201] =
+        "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263"
+        "646566676869707172737475767778798081828384858687888990919293949596979899";
     char buf[24];
-    int k = 0;
-    do { buf[k++] = (char)('0' + v % 10); v /= 10; } while (v);
-    char* d = s.room((size_t)k);
-    for (int i = 0; i < k; i++) d[i] = buf[k - 1 - i];
-    s.n += (size_t)k;
+    int k = 24;
+    while (v >= 100) {
+      const unsigned q = (unsigned)(v % 100);
+      v /= 100;
+      buf[--k] = lut[2 * q + 1]; buf[--k] = lut[2 * q];
+    }
+    if (v >= 10) { buf[--k] = lut[2 * v + 1]; buf[--k] = lut[2 * v]; }
+    else buf[--k] = (char)('0' + v);
+    memcpy(s.room((size_t)(24 - k)), buf + k, (size_t)(24 - k));
+    s.n += (size_t)(24 - k);
   }
   void snum(int64_t v) {
     if (v < 0) { s.push_back('-'); num((uint64_t)(-v)); } else num((uint64_t)v);

@@ -43,7 +43,7 @@ for inp in kinds:
             dt = time.perf_counter() - t0
             if best is None or st["wall_ms"] < best["wall_ms"]:
                 best = dict(st, total_s=dt)
-        print(f"{inp:5s} -> {fmt:3s}: {n / best['wall_ms'] / 1e3:6.2f} M reads/s (pipeline {best['wall_ms']:.0f} ms; stage busy ms: read {best['read_ms']:.0f}, "
+        print(f"{inp:5s} -> {fmt:3s}: {n / best['wall_ms'] / 1e3:6.2f} M reads/s whole run, {best.get('steady_reads_per_s', 0) / 1e6:6.2f} M reads/s after the first two batches (pipeline {best['wall_ms']:.0f} ms; stage busy ms: read {best['read_ms']:.0f}, "
               f"align {best['align_ms']:.0f}, write {best['write_ms']:.0f} (format {best['format_ms']:.0f}); {best['bytes_out'] / 1e6:.0f} MB out; call incl. context {best['total_s']:.2f} s)", flush=True)
 for f in os.listdir(tmp):
     os.remove(os.path.join(tmp, f))
