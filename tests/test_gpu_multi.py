@@ -123,3 +123,24 @@ def test_multi_over_all_gpus_equals_oracle_in_read_order(monkeypatch):
     assert m.replication()[0] == "peer-copy"
     _cmp(m.align_reads(bases, offs), ores, n)
     m.close()
+
+
+def test_file_pipeline_over_tg_multi_equals_oracle_text(tmp_path):
+    """tg_align_files with a tg_multi (two contexts here; every visible GPU when there are several): the reads of every
+    batch are sharded, the text is written in input order and equals the oracle's PAF text."""
+    import gzip
+    from thermite_b200 import OutputFormat, align_reads_from_file
+    fa, gtf, bases, offs = _world(6, 2500)
+    lines = []
+    for i in range(len(offs) - 1):
+        seq = bases[int(offs[i]):int(offs[i + 1])].tobytes()
+        lines.append(b"@q%d\n%s\n+\n%s\n" % (i, seq, b"I" * len(seq)))
+    fq = b"".join(lines)
+    (tmp_path / "q.fastq.gz").write_bytes(gzip.compress(fq))
+    ix = Index.create_from_memory(fa, gtf)
+    want = orc.Index.create(fa, gtf).align_fastq_text(fq, k=20, pct=0.0, min_score=30, score_range=1, intron_mode=True, sam=False)
+    devs = list(range(_n_gpus())) if _n_gpus() > 1 else [0, 0]
+    st = align_reads_from_file(ix, [str(tmp_path / "q.fastq.gz")], str(tmp_path / "o.paf"), OutputFormat.Paf,
+                               AlignOpts(20, 0.0, 30, 1, True), batch_reads=333, devices=devs)
+    assert st["n_reads"] == 2500 and st["n_batches"] == 8
+    assert (tmp_path / "o.paf").read_bytes() == want
