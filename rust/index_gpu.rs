@@ -68,7 +68,7 @@ impl Index {
         let mut h = std::ptr::null_mut();
         unsafe {
             match gpu {
-                Some(d) => check(tg_index_host_create_from_files_gpu(r.as_ptr(), a.as_ptr(), d, &mut h, std::ptr::null_mut()))?,
+                Some(d) => check(tg_index_host_create_from_files_gpu(r.as_ptr(), a.as_ptr(), d, &mut h))?,
                 None => check(tg_index_host_create_from_files(r.as_ptr(), a.as_ptr(), &mut h))?,
             }
         }
