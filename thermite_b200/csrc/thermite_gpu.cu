@@ -8,7 +8,7 @@
 //   k_round_{init,plan,prep,hist,binscan,scatter,post,scan,final}
 //                                     align_read / align_seed_hit (src/aligner.rs:123-449, src/txome.rs:82-160) as the
 //                                     speculative round pipeline of tg_rounds.h: thread per read / per hit
-//   k_round_dpt<0..3>                 SwgExtend::extend / trace (src/swg.rs:31-207): thread per extension, band in
+//   k_round_dpt<1..11>                SwgExtend::extend / trace (src/swg.rs:31-207): thread per extension, band in
 //                                     registers (tg_dpt.h), one kernel per group of band classes.  INT-pipe bound
 //   k_round_dp<R>, k_swg_batch<R>     the same on the warp-cooperative wavefront (tg_core.h): long reads, very wide
 //                                     bands, raw-byte pairs of tg_swg_extend_batch
@@ -185,7 +185,7 @@ struct DevCounters {
   unsigned long long n_late;  // reads finalised by the LAST pass (their first/count reach the host as a fix-up list)
   unsigned long long round_end[TG_MAX_ROUNDS];  // items_used after round r
   unsigned long long round_active[TG_MAX_ROUNDS];  // reads still unfinished after round r
-  unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS][4];
+  unsigned long long round_tasks[TG_MAX_ROUNDS], round_ops[TG_MAX_ROUNDS], round_work[TG_MAX_ROUNDS], round_work2[TG_MAX_ROUNDS][TG_DPT_NCLS];
   // task sorting for the thread-per-extension kernel: bins = class * TG_DPT_CBINS + column bucket
   uint32_t bin_count[TG_DPT_NBINS], bin_cursor[TG_DPT_NBINS];
   uint32_t cls_start[TG_DPT_NCLS + 1], cls_end[TG_DPT_NCLS + 1], cls_chunk0[TG_DPT_NCLS + 1];
@@ -476,7 +476,7 @@ struct RoundParams {
   uint32_t* ibins;         // [2][TG_IB_N] bucket counts, cursors
   uint32_t ib_shift;
   uint32_t* dpt_trace;     // thread kernels: per class group, [warp][col][word][lane]
-  size_t dpt_trace_off[4], dpt_trace_words[4];  // region of each group, words per warp
+  size_t dpt_trace_off[TG_DPT_NCLS], dpt_trace_words[TG_DPT_NCLS];  // region of each band class, words per warp
   int dpt_one, dpt_k128;   // 1 and 128 (see TgDptMem)
   uint32_t max_xlen, max_cols, trace_bytes, ops_words;
   int bound_stop;
@@ -786,16 +786,15 @@ __device__ __forceinline__ void dpt_task(const RoundParams& p, TgTask& t, bool a
   }
 }
 
-// Four kernels, one per group of band classes, so that the narrow classes are not held to the register budget (and
-// occupancy) of the widest one.  Group g handles classes [GFIRST, GLAST].
-template <int G> struct DptGroup;
-template <> struct DptGroup<0> { static constexpr int first = 1, last = 3, min_blocks = 6; };    // WB 4, 8, 16
-template <> struct DptGroup<1> { static constexpr int first = 4, last = 5, min_blocks = 4; };    // WB 24, 32
-template <> struct DptGroup<2> { static constexpr int first = 6, last = 8, min_blocks = 3; };    // WB 40, 48, 56
-template <> struct DptGroup<3> { static constexpr int first = 9, last = 11, min_blocks = 2; };   // WB 64, 72, 80
+// One kernel per band class (round 1 had four class groups): a class is not held to the register budget of a wider one
+// that shares its kernel, and an SM's instruction cache sees one unrolled band per kernel.  Resident CTAs per SM were
+// tuned per class on the bench workload (DP section per 4 M reads: four groups 19.5 ms; per class with the groups'
+// budgets 18.4 ms; natural register counts without spills -- 72 ... 255 -- 20.4 ms; the budgets below, with small spills
+// in the 40- to 64-slot classes, 18.0 ms): occupancy is worth more than spill-free code here.
+template <int CLS> struct DptCls { static constexpr int min_blocks = CLS == 1 ? 8 : CLS == 2 ? 7 : CLS == 3 ? 6 : CLS == 4 ? 5 : CLS <= 6 ? 4 : CLS <= 9 ? 3 : 2; };
 
-template <int G>
-__global__ void __launch_bounds__(128, DptGroup<G>::min_blocks) k_round_dpt(RoundParams p) {
+template <int CLS>
+__global__ void __launch_bounds__(128, DptCls<CLS>::min_blocks) k_round_dpt(RoundParams p) {
   __shared__ uint32_t msk[32 * 128];
   __shared__ uint32_t obuf_s[DPT_OBUF * 128];
   uint32_t* obuf = obuf_s + threadIdx.x;
@@ -803,34 +802,17 @@ __global__ void __launch_bounds__(128, DptGroup<G>::min_blocks) k_round_dpt(Roun
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   TgDptMem m;
   m.msk = msk + threadIdx.x; m.mstride = 128;
-  m.tr = p.dpt_trace + p.dpt_trace_off[G] + (size_t)gw * p.dpt_trace_words[G] + lane; m.tstride = 32;
+  m.tr = p.dpt_trace + p.dpt_trace_off[CLS] + (size_t)gw * p.dpt_trace_words[CLS] + lane; m.tstride = 32;
   m.one = p.dpt_one; m.k128 = p.dpt_k128;
-  const uint32_t chunk0 = p.ctr->cls_chunk0[DptGroup<G>::first], chunk1 = p.ctr->cls_chunk0[DptGroup<G>::last + 1];
+  const uint32_t n_chunks = p.ctr->cls_chunk0[CLS + 1] - p.ctr->cls_chunk0[CLS];
+  const uint32_t start = p.ctr->cls_start[CLS], end = p.ctr->cls_end[CLS];
   for (;;) {
-    const uint32_t g = chunk0 + next_work(&p.ctr->round_work2[p.round][G]);
-    if (g >= chunk1) break;
-    int cls = DptGroup<G>::first;
-    while (cls < DptGroup<G>::last && g >= p.ctr->cls_chunk0[cls + 1]) cls++;
-    const uint32_t first = p.ctr->cls_start[cls] + (g - p.ctr->cls_chunk0[cls]) * 32u;
-    const uint32_t end = p.ctr->cls_end[cls];
+    const uint32_t g = next_work(&p.ctr->round_work2[p.round][CLS]);
+    if (g >= n_chunks) break;
+    const uint32_t first = start + g * 32u;
     const bool active = first + lane < end;
     TgTask& t = p.tasks[active ? p.sorted[first + lane] : p.sorted[first]];
-    if constexpr (G == 0) {
-      if (cls == 1) dpt_task<4>(p, t, active, m, obuf, lane);
-      else if (cls == 2) dpt_task<8>(p, t, active, m, obuf, lane);
-      else dpt_task<16>(p, t, active, m, obuf, lane);
-    } else if constexpr (G == 1) {
-      if (cls == 4) dpt_task<24>(p, t, active, m, obuf, lane);
-      else dpt_task<32>(p, t, active, m, obuf, lane);
-    } else if constexpr (G == 2) {
-      if (cls == 6) dpt_task<40>(p, t, active, m, obuf, lane);
-      else if (cls == 7) dpt_task<48>(p, t, active, m, obuf, lane);
-      else dpt_task<56>(p, t, active, m, obuf, lane);
-    } else {
-      if (cls == 9) dpt_task<64>(p, t, active, m, obuf, lane);
-      else if (cls == 10) dpt_task<72>(p, t, active, m, obuf, lane);
-      else dpt_task<80>(p, t, active, m, obuf, lane);
-    }
+    dpt_task<tg_dpt_wb(CLS)>(p, t, active, m, obuf, lane);
     __syncwarp();
   }
 }
@@ -1198,6 +1180,7 @@ struct tg_ctx {
   DevBuf d_cands, d_arena, d_order, d_aln_first, d_aln_count, d_alns, d_ops;
   uint64_t alns_cap = 0, ops_cap = 0;
   uint32_t scratch_warps = 0;
+  int dpt_occ[TG_DPT_NCLS] = {};  // resident CTAs per SM of k_round_dpt<cls> (queried once)
   // round pipeline scratch
   DevBuf r_state, r_hits, r_ires, r_cands, r_hops, r_fin, r_rp, r_tasks, r_ops, r_complex, r_sorted, r_dpt_trace, r_late, r_perm, r_ikey, r_ibins;
   PinBuf h_late;
@@ -1655,18 +1638,36 @@ tg_status launch_extend(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
 
 // Geometry and scratch of the thread-per-extension kernels: one grid per class group, trace regions for `max_cols`
 // columns, the sorted task index.
-tg_status dpt_geometry(tg_ctx* c, RoundParams& p, uint32_t max_cols, uint64_t task_cap, int grid[4]) {
+typedef void (*DptKernel)(RoundParams);
+static DptKernel dpt_kernel(int cls) {
+  switch (cls) {
+    case 1: return k_round_dpt<1>;
+    case 2: return k_round_dpt<2>;
+    case 3: return k_round_dpt<3>;
+    case 4: return k_round_dpt<4>;
+    case 5: return k_round_dpt<5>;
+    case 6: return k_round_dpt<6>;
+    case 7: return k_round_dpt<7>;
+    case 8: return k_round_dpt<8>;
+    case 9: return k_round_dpt<9>;
+    case 10: return k_round_dpt<10>;
+    default: return k_round_dpt<11>;
+  }
+}
+tg_status dpt_geometry(tg_ctx* c, RoundParams& p, uint32_t max_cols, uint64_t task_cap, int grid[TG_DPT_NCLS]) {
   tg_status st;
-  void (*ks[4])(RoundParams) = {k_round_dpt<0>, k_round_dpt<1>, k_round_dpt<2>, k_round_dpt<3>};
-  const int group_wb[4] = {16, 32, 56, 80};  // widest class of each group
   size_t off = 0;
-  for (int g = 0; g < 4; g++) {
-    int o = 0;
-    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ks[g], 128, 0));
-    if (o < 1) return tg_fail(TG_ERR_INTERNAL, "thread DP kernel does not fit");
-    grid[g] = c->n_sms * o;
+  grid[0] = 0; p.dpt_trace_off[0] = 0; p.dpt_trace_words[0] = 0;
+  for (int g = 1; g < TG_DPT_NCLS; g++) {
+    if (c->dpt_occ[g] == 0) {
+      int o = 0;
+      CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dpt_kernel(g), 128, 0));
+      if (o < 1) return tg_fail(TG_ERR_INTERNAL, "thread DP kernel does not fit");
+      c->dpt_occ[g] = o;
+    }
+    grid[g] = c->n_sms * c->dpt_occ[g];
     p.dpt_trace_off[g] = off;
-    p.dpt_trace_words[g] = (size_t)max_cols * ((2 * group_wb[g] + 31) / 32) * 32;
+    p.dpt_trace_words[g] = (size_t)max_cols * ((2 * tg_dpt_wb(g) + 31) / 32) * 32;  // per warp: [column][word][lane]
     off += (size_t)grid[g] * 4 * p.dpt_trace_words[g];
   }
   if ((st = c->r_dpt_trace.ensure(off * 4)) != TG_OK) return st;
@@ -1677,25 +1678,23 @@ tg_status dpt_geometry(tg_ctx* c, RoundParams& p, uint32_t max_cols, uint64_t ta
   return TG_OK;
 }
 
-// sort the tasks of round p.round by band class and run the thread-per-extension kernels and the warp-cooperative kernel
-// (`warp_launch`, for what the thread kernels do not take) concurrently on the context's side streams
+// sort the tasks of round p.round by band class and run the thread-per-extension kernels (one per class, widest first) and
+// the warp-cooperative kernel (`warp_launch`, for what the thread kernels do not take) concurrently on the side streams
 template <class WarpLaunch>
-tg_status launch_dpt(tg_ctx* c, RoundParams& p, const int grid[4], WarpLaunch&& warp_launch) {
+tg_status launch_dpt(tg_ctx* c, RoundParams& p, const int grid[TG_DPT_NCLS], WarpLaunch&& warp_launch) {
   k_round_hist<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
   k_round_binscan<<<1, TG_BINSCAN_THREADS, 0, c->stream>>>(p);
   k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
   CU_CHECK(cudaEventRecord(c->ev_fork, c->stream));
   for (int i = 0; i < 4; i++) CU_CHECK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
-  k_round_dpt<3><<<grid[3], 128, 0, c->side[0]>>>(p);
-  k_round_dpt<2><<<grid[2], 128, 0, c->side[1]>>>(p);
-  k_round_dpt<1><<<grid[1], 128, 0, c->side[2]>>>(p);
   warp_launch(c->side[3]);
-  k_round_dpt<0><<<grid[0], 128, 0, c->stream>>>(p);
+  cudaStream_t lanes[4] = {c->side[0], c->side[1], c->side[2], c->stream};
+  for (int cls = TG_DPT_NCLS - 1, k = 0; cls >= 1; cls--, k++) dpt_kernel(cls)<<<grid[cls], 128, 0, lanes[k & 3]>>>(p);
   for (int i = 0; i < 4; i++) {
     CU_CHECK(cudaEventRecord(c->ev_join[i], c->side[i]));
     CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
   }
-  c->n_launches += 8;
+  c->n_launches += 4 + (TG_DPT_NCLS - 1);
   return TG_OK;
 }
 
@@ -1770,7 +1769,7 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   const int tblocks = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->n_sms * 16);
   const int iblocks = c->n_sms * 16;
   // thread-per-extension kernel: geometry, trace scratch, sorted task list
-  int dpt_grid[4];
+  int dpt_grid[TG_DPT_NCLS];
   if ((st = dpt_geometry(c, p, std::min<uint32_t>(max_xlen, TG_DPT_MAX_X) + max_bw + 1, c->round_task_cap, dpt_grid)) != TG_OK) return st;
   k_round_init<<<tblocks, 128, 0, c->stream>>>(p);
   c->n_launches++;
@@ -2306,7 +2305,7 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
     rp.n_reads = n; rp.rp_words = rp_words; rp.rp = p.xpk;
     rp.tasks = p.tasks; rp.task_cap = n; rp.ops_pool = (uint32_t*)c->r_ops.p; rp.ops_cap = worst_ops; rp.round = 0;
     rp.bound_stop = p.bound_stop; rp.ctr = c->d_ctr;
-    int grid[4];
+    int grid[TG_DPT_NCLS];
     if ((st = dpt_geometry(c, rp, dpt_cols + 1, n, grid)) != TG_OK) return st;
     const unsigned long long n_tasks = n;
     CU_CHECK(cudaMemcpyAsync(&c->d_ctr->round_tasks[0], &n_tasks, sizeof(n_tasks), cudaMemcpyHostToDevice, c->stream));
