@@ -380,7 +380,7 @@ def run_multi(args):
                       "(40-byte records, segmented pools; every GPU's copies land at their final place)",
                  per_device_last_call=timing, segments=int(hres.n_segments)),
         gpu_launches=int(launches),
-        roofline=dict(bound="int-pipe", kernel="k_round_dpt<0..3> on every GPU", achieved=ref_cells / (dp_ms / 1e3) / 1e9, peak=int_roof,
+        roofline=dict(bound="int-pipe", kernel="k_round_dpt<1..11> on every GPU", achieved=ref_cells / (dp_ms / 1e3) / 1e9, peak=int_roof,
                       unit="GCUPS", frac=ref_cells / (dp_ms / 1e3) / 1e9 / int_roof, traffic=None,
                       achieved_computed_cells=cells / (dp_ms / 1e3) / 1e9, ms_per_step=dp_ms, sm_mhz=sm_mhz,
                       peak_source=f"{G} x 148 SM x 4 SMSP x 16 lanes/clk x sm_mhz / 9 ALU-pipe instructions per cell",
@@ -672,7 +672,7 @@ def _main(args):
     cells, hits, n_alns, n_ops, n_smems, n_ext, ref_cells, launches = [float(x) / world for x in cnt.tolist()]  # per GPU
     seed_launch_ms = seed_ms / args.steps   # pack + probe waves + select
     ext_launch_ms = ext_ms / args.steps     # all rounds: control kernels + DP
-    dp_launch_ms = dp_ms / args.steps       # the banded-SWG kernels of all rounds (class groups run concurrently)
+    dp_launch_ms = dp_ms / args.steps       # the banded-SWG kernels of all rounds (the per-class kernels run concurrently)
     seed_bytes = seed_algorithmic_bytes(n, READ_LEN, FLAGS["k"], hits)
     seed_gbs = seed_bytes / (seed_launch_ms / 1e3) / 1e9
     gcups_ref = ref_cells / (dp_launch_ms / 1e3) / 1e9
@@ -704,7 +704,7 @@ def _main(args):
                  wide_records=dict(value=n * world / (wide_ms / 1e3), ms_per_step=wide_ms, d2h_bytes_per_step=d2h_wide,
                                    call="tg_align_batch: 104-byte records (tg_aln)")),
         gpu_launches=int(launches),
-        roofline=dict(bound="int-pipe", kernel="k_round_dpt<0..3> (banded SWG, thread per extension)", achieved=gcups_ref,
+        roofline=dict(bound="int-pipe", kernel="k_round_dpt<1..11> (banded SWG, thread per extension, one kernel per band class)", achieved=gcups_ref,
                       peak=int_roof, unit="GCUPS", frac=gcups_ref / int_roof, traffic=(traffic.get("k_round_dpt") or {}).get("bytes"),
                       traffic_note=(traffic.get("k_round_dpt") or {}).get("what"),
                       achieved_computed_cells=gcups_computed, ms_per_step=dp_launch_ms,
@@ -715,8 +715,8 @@ def _main(args):
                                                  "best of 5, CUDA events, measured in this run"),
                       peak_theory=int_roof_theory,
                       hbm_view=dict(peak=hbm_peak, unit="GB/s",
-                                    note="not HBM bound: the four DP launches of the heaviest round move 0.78 GB of DRAM traffic "
-                                         "in 3.2 ms (ncu, profiles/r1_ncu_dpt.csv) = 0.04 of the streaming peak; the contract's "
+                                    note="not HBM bound: the DP launches of the heaviest round move 0.87 GB of DRAM traffic "
+                                         "in 3.3 ms (ncu, profiles/r2_ncu_dpt.csv) = 0.04 of the streaming peak; the contract's "
                                          "bound enum (hbm | tensor) has no entry for an integer max-plus recurrence"),
                       peak_source="measured ALU-pipe rate (min of the VIADDMNMX and VIMNMX3 streams, int_peak_measured) / 9 ALU-pipe "
                                   "instructions per cell; peak_theory = 148 SM x 4 SMSP x 16 lanes/clk x sm_mhz / 9 (no tensor "
@@ -742,8 +742,8 @@ def _main(args):
     if swg_rows:
         agg = swg_gcups.tolist()
         line["swg_microbench"] = dict(
-            what="config 5: SwgExtend::extend alone (tg_swg_extend_batch -> k_round_dpt<0..3>), synthetic pairs, x_drop = bw; "
-                 "GCUPS = cells / CUDA-event time of the DP section (task sort + the four DP kernels, as in the align path; "
+            what="config 5: SwgExtend::extend alone (tg_swg_extend_batch -> k_round_dpt<1..11>), synthetic pairs, x_drop = bw; "
+                 "GCUPS = cells / CUDA-event time of the DP section (task sort + the per-class DP kernels, as in the align path; "
                  "all_kernels adds the byte -> 4-bit packing and the result collection of this entry point); credited = cells "
                  "the reference's loops visit, executed = cells the bound-stopped kernels visit; exact_mode = every reference "
                  "column computed",

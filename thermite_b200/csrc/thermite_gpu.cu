@@ -1157,7 +1157,7 @@ struct tg_ctx {
   tg_opts opts;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // the band-class groups of a round's DP run concurrently
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // the band-class kernels of a round's DP are spread over these
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_dp0[TG_MAX_ROUNDS] = {}, ev_dp1[TG_MAX_ROUNDS] = {};  // DP section of every round (timing)
   int rounds_run = 0;
@@ -2298,7 +2298,7 @@ tg_status tg_swg_extend_batch(tg_ctx* c, const uint8_t* xs, const uint64_t* xoff
     kern<<<blocks, wpc * 32, smem, c->stream>>>(p);
     c->n_launches++;
   } else {
-    // pairs of A/C/G/N/T symbols that fit the register-band kernels: round-pipeline tasks on k_round_dpt<0..3>; the rest
+    // pairs of A/C/G/N/T symbols that fit the register-band kernels: round-pipeline tasks on k_round_dpt<1..11>; the rest
     // (other bytes, very long x, very wide bands, empty inputs) on the warp kernel with raw bytes
     RoundParams rp{};
     rp.P.ix = c->ix->dev; rp.P.ix.text4 = p.ypk; rp.P.opts = c->opts;
