@@ -314,6 +314,7 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
       uint64_t yl = e.hi_abs - t.y0;
       t.ylen = (uint32_t)(yl > (uint64_t)xr_len + bw ? (uint64_t)xr_len + bw + 1 : yl);
       t.bw = bw; t.x_drop = (int32_t)s_xd;
+      t.pad0 = 0; t.pad1 = 0;  // (pad0 = 1 marks a task the thread kernels must not take: the task buffer is shared with tg_swg_extend_batch)
     }
     if (e.task_l == 0) {
       TgTask& t = tasks[base];
@@ -324,6 +325,7 @@ TG_HDN bool tg_item_prep(W& w, const TgAlignParams& P, const uint64_t* rp, const
       uint64_t yl = e.r_abs - ys0;
       t.ylen = (uint32_t)(yl > (uint64_t)e.q + bw ? (uint64_t)e.q + bw + 1 : yl);
       t.bw = bw; t.x_drop = (int32_t)s_xd;
+      t.pad0 = 0; t.pad1 = 0;
     }
   }
   hit.n_prob = n_prob; hit.n_cand = n_cand;
