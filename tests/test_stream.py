@@ -127,3 +127,16 @@ def test_reader_errors(tmp_path):
     p = os.path.join(tmp_path, "empty.fastq")
     open(p, "wb").write(b"")
     assert list(FastqReader(p)) == []
+
+
+def test_align_files_rejects_bad_arguments_without_touching_the_gpu(tmp_path):
+    """tg_align_files needs exactly one of ctx / multi and a known format; nothing is created or run otherwise."""
+    import ctypes as C
+    from thermite_b200 import Index, lib
+    ix = Index.create_from_memory(b">a\nACGTACGTACGTACGTACGTACGT\n", b"")
+    paths = (C.c_char_p * 1)(b"/nonexistent.fastq")
+    out = os.path.join(tmp_path, "never.paf").encode()
+    assert lib().tg_align_files(ix._h, None, None, paths, 1, out, 0, 0, None) == -1          # TG_ERR_INVALID: no context
+    assert lib().tg_align_files(ix._h, C.c_void_p(1), C.c_void_p(1), paths, 1, out, 0, 0, None) == -1   # both given
+    assert lib().tg_align_files(ix._h, C.c_void_p(1), None, paths, 1, out, 7, 0, None) == -1  # unknown format
+    assert not os.path.exists(out.decode())

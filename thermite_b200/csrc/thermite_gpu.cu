@@ -475,6 +475,7 @@ struct RoundParams {
   uint32_t* ikey;          // [item] locus bucket
   uint32_t* ibins;         // [2][TG_IB_N] bucket counts, cursors
   uint32_t ib_shift;
+  int all_warp;            // 1: every task of the round goes to the warp-cooperative kernel (tiny batches: no per-class launches)
   uint32_t* dpt_trace;     // thread kernels: per class group, [warp][col][word][lane]
   size_t dpt_trace_off[TG_DPT_NCLS], dpt_trace_words[TG_DPT_NCLS];  // region of each band class, words per warp
   int dpt_one, dpt_k128;   // 1 and 128 (see TgDptMem)
@@ -688,7 +689,7 @@ __global__ void __launch_bounds__(TG_BINSCAN_THREADS) k_round_binscan(RoundParam
     bool small[TG_DPT_NCLS];
     for (int c = 0; c < TG_DPT_NCLS; c++) {
       const uint32_t thr = tg_dpt_wb(c) <= 32 ? 4096u : 8192u;
-      small[c] = c == 0 || cls_n[c] < thr;
+      small[c] = c == 0 || p.all_warp || cls_n[c] < thr;
       p.ctr->round_cls[p.round][c] = cls_n[c];
     }
     for (int c = 0; c < TG_DPT_NCLS; c++)
@@ -1188,6 +1189,7 @@ struct tg_ctx {
   uint64_t round_task_cap = 0, round_ops_cap = 0, item_cap = 0, hops_cap = 0;
   int use_rounds = 1;
   int item_sort = 2;  // rounds whose items are handed out in locus order (TG_ITEM_SORT; 0 = off)
+  uint32_t tiny_batch = 256;     // below this many reads every extension runs on the warp kernel (TG_TINY_BATCH)
   uint32_t small_batch = 32768;  // below this many reads a batch is latency-bound: no early output, no item sort (TG_SMALL_BATCH)
   // chunked host-buffer path: results of chunk k start at these pool positions / read row
   unsigned long long base_alns = 0, base_ops = 0;
@@ -1378,7 +1380,8 @@ tg_status tg_ctx_create(const tg_index* ix, const tg_opts* opts, tg_ctx** out) {
     return tg_fail(TG_ERR_INVALID, "Min alignment score percent must be between 0.0 and 1.0!");  // src/main.rs:46-49
   CU_CHECK(cudaSetDevice(ix->device));
   auto* c = new tg_ctx();
-  if (const char* e = getenv("TG_SMALL_BATCH")) c->small_batch = (uint32_t)atol(e);  // tests: 0 = every batch takes the large-batch path
+  if (const char* e = getenv("TG_SMALL_BATCH")) c->small_batch = (uint32_t)atol(e);
+  if (const char* e = getenv("TG_TINY_BATCH")) c->tiny_batch = (uint32_t)atol(e);  // tests: 0 = every batch takes the large-batch path
   if (const char* e = getenv("TG_ITEM_SORT")) c->item_sort = atoi(e);  // experiments: rounds with locus-ordered items (0 = off)
   c->ix = ix;
   c->opts = *opts;
@@ -1685,6 +1688,11 @@ tg_status launch_dpt(tg_ctx* c, RoundParams& p, const int grid[TG_DPT_NCLS], War
   k_round_hist<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
   k_round_binscan<<<1, TG_BINSCAN_THREADS, 0, c->stream>>>(p);
   k_round_scatter<<<c->n_sms * 4, 256, 0, c->stream>>>(p);
+  if (p.all_warp) {  // a tiny batch: one launch on the main stream, no fork / join
+    warp_launch(c->stream);
+    c->n_launches += 4;
+    return TG_OK;
+  }
   CU_CHECK(cudaEventRecord(c->ev_fork, c->stream));
   for (int i = 0; i < 4; i++) CU_CHECK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
   warp_launch(c->side[3]);
@@ -1771,6 +1779,9 @@ tg_status launch_rounds(tg_ctx* c, const uint8_t* d_bases, const uint64_t* d_off
   // thread-per-extension kernel: geometry, trace scratch, sorted task list
   int dpt_grid[TG_DPT_NCLS];
   if ((st = dpt_geometry(c, p, std::min<uint32_t>(max_xlen, TG_DPT_MAX_X) + max_bw + 1, c->round_task_cap, dpt_grid)) != TG_OK) return st;
+  // a tiny batch cannot fill even one class of the thread kernels: all of its extensions run on the warp-cooperative
+  // kernel and the eleven per-class launches (with their fork / join across streams) are not made at all
+  p.all_warp = n < c->tiny_batch ? 1 : 0;
   k_round_init<<<tblocks, 128, 0, c->stream>>>(p);
   c->n_launches++;
   // a small batch (per-read callers behind tg_batcher) is all launch latency: no item sort, and the host looks for "nothing
