@@ -1,5 +1,7 @@
+"""Cost of the FIRST tg_align_batch call on a fresh context (device buffers grow there) against the following ones, 1 M reads.
+usage: TG_DEBUG_TIMING=1 python tools/first_call.py"""
 import os, sys, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
 from thermite_b200 import AlignOpts, Aligner, Index

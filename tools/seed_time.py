@@ -1,5 +1,8 @@
+"""Device-resident 4 M-read passes: CUDA-event times of the seeding stage, the extension stage and the DP section alone
+(what the A/B runs of profiles/r2_dp_pair_experiment.txt compare).  usage: python tools/seed_time.py"""
+import os
 import sys
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from thermite_b200 import AlignOpts, Aligner, Index
 contigs, gtf, txs, fa = bench.make_world(1.0)
