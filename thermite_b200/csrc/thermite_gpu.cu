@@ -1158,7 +1158,19 @@ struct tg_index {
 // check the read offsets of the later input chunks while the calling thread checks the first chunk and issues its copy:
 // one core streams 32 MB of offsets (4 M reads) in 3.4 ms, during which the GPU had nothing to do.
 struct OffsCheck {
-  struct Job { const uint64_t* o = nullptr; uint32_t m = 0; uint64_t wide = 0; uint32_t longest = 0; bool pending = false; };
+  struct Job {
+    const uint64_t* o = nullptr; uint32_t m = 0; uint64_t wide = 0; uint32_t longest = 0; bool pending = false;
+    // second kind of job: entries [0, n_fix) of a fix-up list (first index, read | count << 32) applied to the host result
+    const unsigned long long* fix = nullptr; uint64_t n_fix = 0; void* first = nullptr; uint32_t* count = nullptr; bool compact = false;
+  };
+  static void apply_fix(const Job& j) {
+    for (uint64_t i = 0; i < j.n_fix; i++) {
+      const uint32_t r = (uint32_t)(j.fix[2 * i + 1] & 0xFFFFFFFFull);
+      if (j.compact) ((uint32_t*)j.first)[r] = (uint32_t)j.fix[2 * i];
+      else ((uint64_t*)j.first)[r] = j.fix[2 * i];
+      j.count[r] = (uint32_t)(j.fix[2 * i + 1] >> 32);
+    }
+  }
   std::thread th[2];
   std::mutex mu;
   std::condition_variable cv, cv_done;
@@ -1181,7 +1193,7 @@ struct OffsCheck {
       cv.wait(l, [&] { return stop || job[k].pending; });
       if (stop) return;
       l.unlock();
-      scan(job[k]);
+      if (job[k].fix) apply_fix(job[k]); else scan(job[k]);
       l.lock();
       job[k].pending = false;
       cv_done.notify_all();
@@ -1192,10 +1204,29 @@ struct OffsCheck {
       std::lock_guard<std::mutex> l(mu);
       if (!started) { started = true; th[0] = std::thread([this] { run(0); }); th[1] = std::thread([this] { run(1); }); }
       const uint32_t h = m / 2;
+      job[0].fix = nullptr; job[1].fix = nullptr;
       job[0].o = o; job[0].m = h; job[0].pending = true;
       job[1].o = o + h; job[1].m = m - h; job[1].pending = true;
     }
     cv.notify_all();
+  }
+  // the late reads' first / count (a few per cent of a batch, scattered): thirds of the list on the helpers and the caller
+  void fix_up(const unsigned long long* list, uint64_t n, void* first, uint32_t* count, bool compact) {
+    Job mine;
+    mine.fix = list; mine.n_fix = n; mine.first = first; mine.count = count; mine.compact = compact;
+    if (!started || n < 4096) { apply_fix(mine); return; }
+    const uint64_t a = n / 3, b = 2 * n / 3;
+    {
+      std::lock_guard<std::mutex> l(mu);
+      for (int k = 0; k < 2; k++) { job[k].first = first; job[k].count = count; job[k].compact = compact; job[k].pending = true; }
+      job[0].fix = list + 2 * a; job[0].n_fix = b - a;
+      job[1].fix = list + 2 * b; job[1].n_fix = n - b;
+    }
+    cv.notify_all();
+    mine.n_fix = a;
+    apply_fix(mine);
+    uint64_t w; uint32_t l;
+    wait(w, l);
   }
   void wait(uint64_t& wide, uint32_t& longest) {
     std::unique_lock<std::mutex> l(mu);
@@ -2180,18 +2211,14 @@ static tg_status align_host(tg_ctx* c, const uint8_t* bases, const uint64_t* off
   if (n_ops > eo)
     CU_CHECK(cudaMemcpyAsync(c->ho.ops + eo, (uint32_t*)c->d_ops.p + eo, (size_t)(n_ops - eo) * 4, cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(cudaStreamSynchronize(c->stream));
+  const double t_sync1 = now();
   CU_CHECK(cudaStreamSynchronize(c->copy_out));
-  if (fixup) {
-    const unsigned long long* l = (const unsigned long long*)c->h_late.p;
-    uint32_t* hc = c->ho.count;
-    for (uint64_t i = 0; i < n_late; i++) {
-      const uint32_t r = (uint32_t)(l[2 * i + 1] & 0xFFFFFFFFull);
-      if (compact) ((uint32_t*)c->ho.first)[r] = (uint32_t)l[2 * i];
-      else ((uint64_t*)c->ho.first)[r] = l[2 * i];
-      hc[r] = (uint32_t)(l[2 * i + 1] >> 32);
-    }
-  }
+  const double t_sync2 = now();
+  if (fixup) c->offs_check.fix_up((const unsigned long long*)c->h_late.p, n_late, c->ho.first, c->ho.count, compact);
   c->last_wall_ms = now() - t_in;
+  if (dbg)
+    fprintf(stderr, "tg_align_batch tail: late copies %.2f ms, early copies still in flight %.2f ms, fix-up of %llu reads %.2f ms\n",
+            t_sync1 - t_pipe, t_sync2 - t_sync1, (unsigned long long)n_late, now() - t_sync2);
   if (dbg)
     fprintf(stderr, "tg_align_batch[dev %d]: %u reads, issue inputs %.2f ms, pipeline %.2f ms (seed %.2f + extend %.2f on the device), tail %.2f ms; "
             "H2D %.1f MB, D2H %.1f MB (%.1f MB early)\n", c->ix->device, n_reads,
