@@ -400,11 +400,24 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
 int tg_fastq_format(const tg_fastq_reader* r);
 void tg_fastq_close(tg_fastq_reader* r);
 
+/* PAF lines written on the GPU (PafEntry, src/aln_writer.rs:47-116; csrc/tg_paf.cu): the batch is aligned with its records left in
+ * HBM and two kernels turn them into text, so only names go up and only text comes back; byte-identical to tg_format_batch.
+ * `ctx` must live on `device` and is used by the formatter (one call at a time).  *text points into a page-locked buffer
+ * owned by the formatter, valid until the second next call (two buffers alternate); counters (may be NULL) receives the
+ * tg_result counters of the batch (its pointers are device pointers). */
+typedef struct tg_paf tg_paf;
+tg_status tg_paf_create(const tg_index_host* ix, tg_ctx* ctx, int device, tg_paf** out);
+tg_status tg_paf_align_batch(tg_paf* f, const tg_read_batch* batch, const char** text, size_t* text_len, tg_result* counters);
+void tg_paf_destroy(tg_paf* f);
+/* The device a context lives on. */
+int tg_ctx_device(const tg_ctx* ctx);
+
 /* align_reads_from_file (src/aligner.rs:22-120): query files -> PAF (output_fmt 0), SAM (1) or BAM (2) at out_path
  * ("-" = stdout), records in input order.  Exactly one of ctx / multi is given (one GPU, or the reads of every batch
  * sharded over the GPUs of a tg_multi).  Three overlapped stages: reader (inflate + parse batch k + 1), aligner (batch k
  * on the GPU), writers (format batch k - 1 on all host cores and write it); no stage holds more than three batches of
- * batch_reads reads (0 = 1 Mi).  The call switches ctx / multi to two alternating result sets. */
+ * batch_reads reads (0 = 1 Mi).  The call switches ctx / multi to two alternating result sets.  PAF on one GPU is written on
+ * the device (tg_paf_*; TG_PAF_HOST=1 in the environment keeps the host writers). */
 typedef struct tg_file_stats {
   uint64_t n_reads, n_alns, n_batches, bytes_out;
   double read_ms, align_ms, write_ms;  /* busy time of each stage */

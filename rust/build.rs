@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from(env::var("THERMITE_GPU_CSRC").unwrap_or_else(|_| "thermite_b200/csrc".into()));
     let lib = out.join("libthermite_gpu.a");
-    let objs = ["thermite_gpu.cu", "tg_sa.cu", "tg_multi.cpp", "host_index.cpp", "host_io.cpp", "host_stream.cpp", "host_bam.cpp", "host_batcher.cpp"];
+    let objs = ["thermite_gpu.cu", "tg_sa.cu", "tg_paf.cu", "tg_multi.cpp", "host_index.cpp", "host_io.cpp", "host_stream.cpp", "host_bam.cpp", "host_batcher.cpp"];
     let mut obj_paths = Vec::new();
     for src in objs.iter() {
         let obj = out.join(format!("{}.o", src));

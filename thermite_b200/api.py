@@ -96,6 +96,7 @@ ABI_SYMBOLS = [
     "tg_multi_create", "tg_multi_destroy", "tg_multi_set_result_buffers", "tg_multi_n_devices", "tg_multi_replication", "tg_multi_ctx",
     "tg_multi_align_batch", "tg_multi_last_timing",
     "tg_fastq_open", "tg_fastq_next", "tg_fastq_format", "tg_fastq_close", "tg_align_files",
+    "tg_paf_create", "tg_paf_align_batch", "tg_paf_destroy", "tg_ctx_device",
 ]
 
 
@@ -127,6 +128,7 @@ def lib():
         L.tg_free.restype = None
         L.tg_multi_destroy.restype = None
         L.tg_fastq_close.restype = None
+        L.tg_paf_destroy.restype = None
         L.tg_multi_replication.restype = C.c_char_p
         L.tg_multi_ctx.restype = C.c_void_p
         _LIB = L

@@ -171,9 +171,9 @@ struct tg_fastq_reader {
   bool zs_open = false;
   std::vector<char> text;  // inflated / plain text not yet handed out; starts at a record start
   size_t text_len = 0;
-  const char* map = nullptr;  // a plain regular file is parsed in place from its mapping: no copy of the text is made
-  size_t map_len = 0, map_pos = 0;
-  const char* tptr() const { return map ? map + map_pos : text.data(); }
+  int pread_fd = -1;          // a plain regular file: read with pread from all cores
+  size_t file_size = 0, file_off = 0;
+  const char* tptr() const { return text.data(); }
   bool text_final = false;  // nothing will be appended to `text` any more
   double bytes_per_read = 220.0;
   struct Set {
@@ -186,7 +186,6 @@ struct tg_fastq_reader {
 
   ~tg_fastq_reader() {
     if (zs_open) inflateEnd(&zs);
-    if (map) munmap((void*)map, map_len);
     if (f) fclose(f);
   }
   void grow_text(size_t need) {
@@ -204,6 +203,29 @@ struct tg_fastq_reader {
     return true;
   }
   bool fill_plain(size_t target) {
+    // Regular file: every core reads its slice of the next stretch straight into the text buffer.  (Mapping the file and
+    // parsing in place was tried first: no copy, but 48 k first-touch page faults per 1 M reads, taken by sixteen parser
+    // threads under one lock, cost more than the copy; one thread's fread cost 40 ms per 1 M reads.)
+    while (pread_fd >= 0 && text_len < target && !text_final) {
+      size_t want = std::min(std::max<size_t>(target - text_len, 1u << 20), file_size - file_off);
+      if (want == 0) { text_final = true; break; }
+      grow_text(text_len + want);
+      char* dst = text.data() + text_len;
+      const unsigned T = want < (4u << 20) ? 1u : host_threads();
+      std::vector<int> bad(T, 0);
+      run_threads(T, [&](unsigned t) {
+        size_t a = want * t / T;
+        const size_t b = want * (t + 1) / T;
+        while (a < b) {
+          const ssize_t g = pread(pread_fd, dst + a, b - a, (off_t)(file_off + a));
+          if (g <= 0) { bad[t] = 1; return; }  // (the file shrank under us, or an I/O error)
+          a += (size_t)g;
+        }
+      });
+      for (int x : bad) if (x) { err = "read error"; return false; }
+      text_len += want; file_off += want;
+      if (file_off >= file_size) text_final = true;
+    }
     while (text_len < target && !text_final) {
       const size_t want = std::max<size_t>(target - text_len, 1u << 20);
       grow_text(text_len + want);
@@ -315,7 +337,6 @@ struct tg_fastq_reader {
     return true;
   }
   bool fill_text(size_t target) {
-    if (map) return true;
     if (format == 0) return fill_plain(target);
     if (format == 1) return fill_gzip(target);
     return fill_bgzf(target);
@@ -343,22 +364,17 @@ tg_status tg_fastq_open(const char* path, tg_fastq_reader** out) {
         q += 4 + slen;
       }
     }
-  } else if ([&]() {  // plain text in a regular file: map it
-               struct stat sb;
-               if (f == stdin || fstat(fileno(f), &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size == 0) return false;
-               void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fileno(f), 0);
-               if (m == MAP_FAILED) return false;
-               madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
-               r->map = (const char*)m; r->map_len = (size_t)sb.st_size; r->map_pos = 0;
-               r->text_len = r->map_len; r->text_final = true; r->zin_len = 0;
-               return true;
-             }()) {
   } else {  // plain text from a pipe: what was read is text already
     r->grow_text(r->zin_len);
     memcpy(r->text.data(), r->zin.data(), r->zin_len);
     r->text_len = r->zin_len;
     r->zin_len = 0;
     if (r->file_eof) r->text_final = true;
+    // a regular file is read on from here with positional reads from all cores (fill_plain); a pipe through the stream
+    struct stat sb;
+    if (f != stdin && fstat(fileno(f), &sb) == 0 && S_ISREG(sb.st_mode)) {
+      r->pread_fd = fileno(f); r->file_size = (size_t)sb.st_size; r->file_off = r->text_len;
+    }
   }
   *out = r;
   return TG_OK;
@@ -386,7 +402,7 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
   for (;;) {
     if (!r->fill_text(target)) return tg_fail(TG_ERR_IO, "FASTQ input: " + r->err);
     const char* text = r->tptr();
-    const size_t len = std::min(r->text_len, target);  // (a mapped file is all there: look at one batch's worth of it)
+    const size_t len = std::min(r->text_len, target);  // (one batch's worth of the text that is there)
     const bool at_end = r->text_final && len == r->text_len;
     // segments cut at record starts; every core indexes the lines of one and counts its records
     unsigned T = len < (4u << 20) ? 1u : T0;
@@ -430,8 +446,8 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
   for (size_t t = 0; t < used; t++) { nb += seg[t].bases; nn += seg[t].names; nq += seg[t].quals; }
   tg_fastq_reader::Set& S = r->set[r->cur];
   r->cur = (r->cur + 1) % 3;
-  if (!S.bases.ensure(nb + 64, true) || !S.offs.ensure((n + 1) * 8, true) || !S.names.ensure(nn + 1, false) ||
-      !S.name_offs.ensure((n + 1) * 8, false) || !S.quals.ensure(nq + 1, false) || !S.qual_offs.ensure((n + 1) * 8, false))
+  if (!S.bases.ensure(nb + 64, true) || !S.offs.ensure((n + 1) * 8, true) || !S.names.ensure(nn + 1, true) ||
+      !S.name_offs.ensure((n + 1) * 8, true) || !S.quals.ensure(nq + 1, false) || !S.qual_offs.ensure((n + 1) * 8, false))
     return tg_fail(TG_ERR_INTERNAL, "out of memory");
   uint8_t* bases = (uint8_t*)S.bases.p; uint64_t* offs = (uint64_t*)S.offs.p;
   uint8_t* names = (uint8_t*)S.names.p; uint64_t* name_offs = (uint64_t*)S.name_offs.p;
@@ -451,8 +467,7 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
     seg[t].fill(text, bases, offs + r0[t], b0[t], names, name_offs + r0[t], n0[t], quals, qual_offs + r0[t], q0[t]);
   });
   // what is left starts at a record start
-  if (r->map) r->map_pos += consumed;
-  else if (consumed < r->text_len) memmove(r->text.data(), r->text.data() + consumed, r->text_len - consumed);
+  if (consumed < r->text_len) memmove(r->text.data(), r->text.data() + consumed, r->text_len - consumed);
   r->text_len -= consumed;
   r->bytes_per_read = 0.5 * r->bytes_per_read + 0.5 * ((double)consumed / (double)n);
   r->total_reads += n; r->total_text += consumed;
@@ -470,6 +485,8 @@ namespace {
 struct Job {
   tg_read_batch batch;
   tg_result_c res;
+  const char* text = nullptr;  // PAF written on the GPU (tg_paf_*): the batch's text instead of its records
+  size_t text_len = 0;
   uint64_t index = 0;
   bool end = false;
 };
@@ -547,6 +564,11 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
     struct stat sb;
     seekable = out != stdout && file_pos >= 0 && fstat(out_fd, &sb) == 0 && S_ISREG(sb.st_mode);  // (stdout may be in append mode)
   }
+  // PAF on one GPU: lines are written on the device (tg_paf.cu), the writers only copy text into the file
+  tg_paf* paf = nullptr;
+  if (output_fmt == 0 && ctx && !getenv("TG_PAF_HOST")) {
+    if ((st = tg_paf_create(ix, ctx, tg_ctx_device(ctx), &paf)) != TG_OK) { close_out(); return st; }
+  }
   Channel to_align, to_write;
   Progress prog;
   std::string err_read, err_write;
@@ -593,6 +615,31 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
       if (st_write != TG_OK) { prog.done_one(); continue; }  // keep draining so that nobody waits forever
       const double t0 = now_ms();
       const uint32_t n = j.batch.n_reads;
+      if (paf) {  // the text is there already: slices of it go into the file from all threads
+        const unsigned Tw = (!seekable || j.text_len < (8u << 20)) ? 1u : T;
+        if (!seekable) {
+          if (j.text_len && fwrite(j.text, 1, j.text_len, out) != j.text_len) { st_write = TG_ERR_IO; err_write = "write error"; }
+        } else {
+          std::vector<int> bad(Tw, 0);
+          run_threads(Tw, [&](unsigned t) {
+            size_t a = j.text_len * t / Tw, b = j.text_len * (t + 1) / Tw;
+            while (a < b) {
+              const ssize_t w = pwrite(out_fd, j.text + a, b - a, file_pos + (off_t)a);
+              if (w <= 0) { bad[t] = 1; return; }
+              a += (size_t)w;
+            }
+          });
+          for (int x : bad) if (x) { st_write = TG_ERR_IO; err_write = "write error"; }
+          file_pos += (off_t)j.text_len;
+        }
+        S.bytes_out += j.text_len;
+        S.n_reads += n; S.n_alns += j.res.n_alns; S.n_batches++;
+        if (S.n_batches == 2) { S.warm_reads = S.n_reads; S.warm_ms = now_ms() - t_start; }
+        write_ms += now_ms() - t0;
+        if (st_write != TG_OK) prog.fail();
+        prog.done_one();
+        continue;
+      }
       const unsigned Tn = n < 32768 ? 1u : T;
       TgRecView v;
       v.first32 = j.res.read_aln_first; v.count = j.res.read_aln_count; v.comp = j.res.alns; v.ops = j.res.ops;
@@ -651,7 +698,12 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
     if (st_align != TG_OK) continue;
     if (j.index >= 1 && !prog.wait_written(j.index - 1)) { st_align = TG_ERR_INTERNAL; continue; }
     const double t0 = now_ms();
-    if (ctx) st_align = tg_align_batch_compact(ctx, j.batch.bases, j.batch.offs, j.batch.n_reads, &j.res);
+    if (paf) {
+      tg_result counters;
+      memset(&j.res, 0, sizeof(j.res));
+      st_align = tg_paf_align_batch(paf, &j.batch, &j.text, &j.text_len, &counters);
+      if (st_align == TG_OK) { j.res.n_reads = j.batch.n_reads; j.res.n_alns = counters.n_alns; j.res.n_ops = counters.n_ops; }
+    } else if (ctx) st_align = tg_align_batch_compact(ctx, j.batch.bases, j.batch.offs, j.batch.n_reads, &j.res);
     else st_align = tg_multi_align_batch(multi, j.batch.bases, j.batch.offs, j.batch.n_reads, &j.res);
     align_ms += now_ms() - t0;
     if (st_align != TG_OK) { prog.fail(); continue; }
@@ -665,6 +717,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
     fwrite(eof_block, 1, sizeof(eof_block), out);
     S.bytes_out += sizeof(eof_block);
   }
+  if (paf) tg_paf_destroy(paf);
   close_out();
   S.read_ms = read_ms; S.align_ms = align_ms; S.write_ms = write_ms; S.format_ms = format_ms; S.wall_ms = now_ms() - t_start;
   if (stats) *stats = S;

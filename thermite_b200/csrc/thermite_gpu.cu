@@ -1540,6 +1540,7 @@ tg_status tg_ctx_set_result_buffers(tg_ctx* ctx, int n) {
 void tg_ctx_set_chunk_reads(tg_ctx* ctx, uint32_t reads) {
   if (ctx) ctx->chunk_reads = reads == 0 ? 0 : (reads < 1024 ? 1024 : reads);
 }
+int tg_ctx_device(const tg_ctx* ctx) { return ctx ? ctx->ix->device : -1; }
 void* tg_ctx_stream(tg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 void tg_ctx_last_kernel_ms(const tg_ctx* ctx, float* seed_ms, float* extend_ms) {
@@ -2270,8 +2271,6 @@ tg_status tg_align_batch_compact(tg_ctx* ctx, const uint8_t* bases, const uint64
 }
 
 }  // extern "C"
-
-int tg_ctx_device(const tg_ctx* ctx) { return ctx->ix->device; }
 
 tg_status tg_ctx_align_segment(tg_ctx* ctx, const uint8_t* bases, const uint64_t* offs, uint32_t n_reads, const TgHostSegment& seg,
                                TgShardStat* stat) {
