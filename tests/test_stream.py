@@ -140,3 +140,18 @@ def test_align_files_rejects_bad_arguments_without_touching_the_gpu(tmp_path):
     assert lib().tg_align_files(ix._h, C.c_void_p(1), C.c_void_p(1), paths, 1, out, 0, 0, None) == -1   # both given
     assert lib().tg_align_files(ix._h, C.c_void_p(1), None, paths, 1, out, 7, 0, None) == -1  # unknown format
     assert not os.path.exists(out.decode())
+
+
+def test_reader_reads_a_pipe_through_stdin(tmp_path):
+    """"-" reads stdin (the reference's CLI takes query paths only, but needletail can read any reader): plain and gzip text
+    through a pipe take the streaming path (no positional reads)."""
+    import subprocess
+    import sys
+    text = make_fastq(11, 3000, blank_every=13)
+    want = python_parse(text)
+    prog = ("import sys; sys.path.insert(0, %r); from thermite_b200 import FastqReader; r = FastqReader('-', 700); "
+            "n = sum(len(o) - 1 for _, o, *rest in r); print(r.format if False else '', n)") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for data in (text, gzip.compress(text)):
+        out = subprocess.run([sys.executable, "-c", prog], input=data, capture_output=True, timeout=120)
+        assert out.returncode == 0, out.stderr.decode()[-500:]
+        assert int(out.stdout.split()[-1]) == len(want)
