@@ -477,7 +477,7 @@ def extra_workloads(args, index, aligner, bases, offs, n, dev, stream):
                            bytes_out=int(best["bytes_out"]), batches=int(best["n_batches"]))
         out["file_pipeline"] = dict(reads=nf, input="plain FASTQ on tmpfs, %d MB" % (os.path.getsize(qp) >> 20), host_threads=os.cpu_count(),
                                     batch_reads=1 << 19,
-                                    note="best of 2; a fresh context per run, so the first batches grow the device and page-locked buffers", **fp)
+                                    note="best of 2; PAF lines and SAM records are written on the GPU; a fresh context per run, so the first batches grow the device and page-locked buffers", **fp)
     finally:
         for f in os.listdir(tmp):
             os.remove(os.path.join(tmp, f))

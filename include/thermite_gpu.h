@@ -407,7 +407,16 @@ void tg_fastq_close(tg_fastq_reader* r);
  * tg_result counters of the batch (its pointers are device pointers). */
 typedef struct tg_paf tg_paf;
 tg_status tg_paf_create(const tg_index_host* ix, tg_ctx* ctx, int device, tg_paf** out);
+/* The same formatter writing SAM records instead (aln_to_sam_record / unmapped_sam_record, src/aln_writer.rs:118-253; one
+ * thread per read runs csrc/tg_textfmt.h): the batch's qualities go up as well, every read prints (unmapped ones as flag 4);
+ * byte-identical to tg_format_batch(sam = 1).  No header lines (tg_format_sam_header). */
+tg_status tg_sam_create(const tg_index_host* ix, tg_ctx* ctx, int device, tg_paf** out);
 tg_status tg_paf_align_batch(tg_paf* f, const tg_read_batch* batch, const char** text, size_t* text_len, tg_result* counters);
+/* The same call returning while the text is still on its way home (its copy runs on a stream of the formatter's own, so the
+ * next batch can be aligned meanwhile): *text must not be read before tg_paf_wait(f, *text) has returned (text = NULL waits
+ * for every copy in flight).  tg_align_files hands the wait to its writer stage. */
+tg_status tg_paf_align_batch_async(tg_paf* f, const tg_read_batch* batch, const char** text, size_t* text_len, tg_result* counters);
+tg_status tg_paf_wait(tg_paf* f, const char* text);
 void tg_paf_destroy(tg_paf* f);
 /* The device a context lives on. */
 int tg_ctx_device(const tg_ctx* ctx);
@@ -417,7 +426,7 @@ int tg_ctx_device(const tg_ctx* ctx);
  * sharded over the GPUs of a tg_multi).  Three overlapped stages: reader (inflate + parse batch k + 1), aligner (batch k
  * on the GPU), writers (format batch k - 1 on all host cores and write it); no stage holds more than three batches of
  * batch_reads reads (0 = 1 Mi).  The call switches ctx / multi to two alternating result sets.  PAF on one GPU is written on
- * the device (tg_paf_*; TG_PAF_HOST=1 in the environment keeps the host writers). */
+ * the device (tg_paf_* / tg_sam_create; TG_PAF_HOST=1 in the environment keeps the host writers). */
 typedef struct tg_file_stats {
   uint64_t n_reads, n_alns, n_batches, bytes_out;
   double read_ms, align_ms, write_ms;  /* busy time of each stage */

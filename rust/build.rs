@@ -36,7 +36,7 @@ fn main() {
         println!("cargo:rerun-if-changed={}", csrc.join(src).display());
     }
     // headers every object depends on (the C ABI header lives in include/)
-    for h in ["tg_core.h", "tg_rounds.h", "tg_dpt.h", "tg_internal.h", "host_text.h"].iter() {
+    for h in ["tg_core.h", "tg_rounds.h", "tg_dpt.h", "tg_internal.h", "host_text.h", "tg_textfmt.h"].iter() {
         println!("cargo:rerun-if-changed={}", csrc.join(h).display());
     }
     println!("cargo:rerun-if-changed={}", csrc.join("../../include").join("thermite_gpu.h").display());

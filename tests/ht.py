@@ -24,7 +24,7 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_CSRC, "libtg_hosttest.so")
-        srcs = [os.path.join(_CSRC, f) for f in ("hosttest.cpp", "host_index.cpp", "host_batcher.cpp", "tg_core.h", "tg_rounds.h", "tg_dpt.h", "tg_internal.h")]
+        srcs = [os.path.join(_CSRC, f) for f in ("hosttest.cpp", "host_index.cpp", "host_batcher.cpp", "tg_core.h", "tg_rounds.h", "tg_dpt.h", "tg_internal.h", "tg_textfmt.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["make", "-C", _CSRC, "libtg_hosttest.so"], stdout=subprocess.DEVNULL)
         L = C.CDLL(so)
@@ -50,6 +50,17 @@ def batcher_selftest(n_threads, per_thread, max_batch, max_wait_us, fail_every=0
     bad = lib().ht_batcher_selftest(C.c_int(n_threads), C.c_int(per_thread), C.c_uint32(max_batch), C.c_uint32(max_wait_us),
                                     C.c_int(fail_every), C.byref(nb), C.byref(lg), C.byref(nf))
     return bad, nb.value, lg.value, nf.value
+
+
+def format_sam(index, res, bases, offs, names, name_offs, quals, qual_offs):
+    """tg_textfmt.h (the routine tg_paf.cu's SAM kernels run, one thread per read) on the host: count, scan, write."""
+    out, ln = C.c_void_p(), C.c_size_t()
+    st = lib().ht_format_sam(index.h, C.byref(res), _p(bases), _p(offs), _p(names), _p(name_offs), _p(quals), _p(qual_offs),
+                             C.byref(out), C.byref(ln))
+    assert st == 0
+    text = C.string_at(out, ln.value)
+    C.CDLL(None).free(out)
+    return text
 
 
 class HostIndex:

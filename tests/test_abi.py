@@ -144,6 +144,9 @@ def test_fastq_parser_and_writers_match_oracle_text():
         if sam:
             text = tb.sam_header(ix) + text
         assert text == want
+    # the SAM routine the device formatter runs (csrc/tg_textfmt.h), built for the host
+    import ht
+    assert tb.sam_header(ix) + ht.format_sam(ht.HostIndex(fa, gtf), res, bases, offs, names, name_offs, quals, qual_offs) == want
 
 
 def test_parallel_fastq_parser_and_writers_large_input():
@@ -194,6 +197,8 @@ def test_parallel_fastq_parser_and_writers_large_input():
         if sam:
             text = tb.sam_header(ix) + text
         assert text == want
+    import ht
+    assert tb.sam_header(ix) + ht.format_sam(ht.HostIndex(fa, gtf), res, bases, offs, names, name_offs, quals, qual_offs) == want
 
 
 def test_device_entry_points_fail_loudly_without_gpu():

@@ -411,12 +411,13 @@ def test_contexts_share_one_kmer_table():
     _cmp(a3.align_reads(bases, offs), oix.align_batch(bases, offs, k=12, pct=0.0, min_score=30, score_range=1, intron_mode=True), 400)
 
 
-def test_paf_written_on_the_gpu_equals_the_host_writer(tmp_path, monkeypatch):
-    """tg_paf_* (csrc/tg_paf.cu): PAF lines formatted on the device are byte-identical to the host writer's and to the
-    oracle's text -- test data (config 1), a world with both strands / multi-mappers / unmapped reads, long read names --
-    and tg_align_files gives the same file with either writer (TG_PAF_HOST=1 selects the host one)."""
+def test_paf_and_sam_written_on_the_gpu_equal_the_host_writer(tmp_path, monkeypatch):
+    """tg_paf_* / tg_sam_create (csrc/tg_paf.cu, csrc/tg_textfmt.h): PAF lines and SAM records formatted on the device are
+    byte-identical to the host writer's and to the oracle's text -- test data (config 1), a world with both strands /
+    multi-mappers / unmapped reads, long read names with spaces -- and tg_align_files gives the same file with either
+    writer (TG_PAF_HOST=1 selects the host one)."""
     import ctypes as C
-    from thermite_b200 import OutputFormat, align_reads_from_file, lib
+    from thermite_b200 import OutputFormat, align_reads_from_file, lib, sam_header
     from thermite_b200.api import _ReadBatch, _Result, _check
     cases = []
     fa, gtf, fq = golden("test_ref.fasta"), golden("test_ref.gtf"), golden("test_query.fastq")
@@ -424,30 +425,35 @@ def test_paf_written_on_the_gpu_equals_the_host_writer(tmp_path, monkeypatch):
     contigs, gtf2, txs, fa2 = small_world(7)
     b2, o2 = synth.make_reads(3, contigs, txs, 4000, L=91, sub=0.03, ins=0.004, dele=0.004, polya_frac=0.2, polya_len=(10, 40))
     fq2 = b"".join(b"@read_%d/1 a rather long header with spaces %d\n%s\n+\n%s\n" %
-                   (i, i * 7919, b2[int(o2[i]):int(o2[i + 1])].tobytes(), b"I" * int(o2[i + 1] - o2[i])) for i in range(len(o2) - 1))
+                   (i, i * 7919, b2[int(o2[i]):int(o2[i + 1])].tobytes(),
+                    bytes(33 + (i + 3 * k) % 40 for k in range(int(o2[i + 1] - o2[i])))) for i in range(len(o2) - 1))
     cases.append((fa2, gtf2, fq2, AlignOpts(20, 0.0, 30, 3, True), dict(k=20, pct=0.0, min_score=30, score_range=3, intron_mode=True)))
     for fa_, gtf_, fq_, opts, okw in cases:
         ix = Index.create_from_memory(fa_, gtf_)
         al = Aligner(ix, opts)
-        want = orc.Index.create(fa_, gtf_).align_fastq_text(fq_, sam=False, **okw)
+        oix = orc.Index.create(fa_, gtf_)
         bases, offs, names, name_offs, quals, qual_offs = parse_fastq(fq_)
-        f = C.c_void_p()
-        _check(lib().tg_paf_create(ix._h, al._h, 0, C.byref(f)))
         batch = _ReadBatch(len(offs) - 1, 0, bases.ctypes.data, offs.ctypes.data, names.ctypes.data, name_offs.ctypes.data,
                            quals.ctypes.data, qual_offs.ctypes.data)
-        for _ in range(3):  # the two text buffers alternate
-            text, n = C.c_void_p(), C.c_size_t()
-            res = _Result()
-            _check(lib().tg_paf_align_batch(f, C.byref(batch), C.byref(text), C.byref(n), C.byref(res)))
-            assert C.string_at(text, n.value) == want
-        lib().tg_paf_destroy(f)
         qp = tmp_path / "q.fastq"
         qp.write_bytes(fq_)
-        for host in ("0", "1"):
-            if host == "1":
-                monkeypatch.setenv("TG_PAF_HOST", "1")
-            else:
-                monkeypatch.delenv("TG_PAF_HOST", raising=False)
-            op = tmp_path / ("o%s.paf" % host)
-            st = align_reads_from_file(ix, [str(qp)], str(op), OutputFormat.Paf, opts, batch_reads=777)
-            assert op.read_bytes() == want and st["n_reads"] == len(offs) - 1
+        for sam in (False, True):
+            want = oix.align_fastq_text(fq_, sam=sam, **okw)
+            head = sam_header(ix) if sam else b""
+            f = C.c_void_p()
+            _check((lib().tg_sam_create if sam else lib().tg_paf_create)(ix._h, al._h, 0, C.byref(f)))
+            for _ in range(3):  # the two text buffers alternate
+                text, n = C.c_void_p(), C.c_size_t()
+                res = _Result()
+                _check(lib().tg_paf_align_batch(f, C.byref(batch), C.byref(text), C.byref(n), C.byref(res)))
+                assert head + C.string_at(text, n.value) == want
+            lib().tg_paf_destroy(f)
+            for host in ("0", "1"):
+                if host == "1":
+                    monkeypatch.setenv("TG_PAF_HOST", "1")
+                else:
+                    monkeypatch.delenv("TG_PAF_HOST", raising=False)
+                op = tmp_path / ("o%s.%s" % (host, "sam" if sam else "paf"))
+                st = align_reads_from_file(ix, [str(qp)], str(op), OutputFormat.Sam if sam else OutputFormat.Paf, opts, batch_reads=777)
+                assert op.read_bytes() == want and st["n_reads"] == len(offs) - 1
+        monkeypatch.delenv("TG_PAF_HOST", raising=False)

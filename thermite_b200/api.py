@@ -96,7 +96,7 @@ ABI_SYMBOLS = [
     "tg_multi_create", "tg_multi_destroy", "tg_multi_set_result_buffers", "tg_multi_n_devices", "tg_multi_replication", "tg_multi_ctx",
     "tg_multi_align_batch", "tg_multi_last_timing",
     "tg_fastq_open", "tg_fastq_next", "tg_fastq_format", "tg_fastq_close", "tg_align_files",
-    "tg_paf_create", "tg_paf_align_batch", "tg_paf_destroy", "tg_ctx_device",
+    "tg_paf_create", "tg_sam_create", "tg_paf_align_batch", "tg_paf_align_batch_async", "tg_paf_wait", "tg_paf_destroy", "tg_ctx_device",
 ]
 
 

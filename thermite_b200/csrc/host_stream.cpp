@@ -176,6 +176,7 @@ struct tg_fastq_reader {
   const char* tptr() const { return text.data(); }
   bool text_final = false;  // nothing will be appended to `text` any more
   double bytes_per_read = 220.0;
+  bool pin_quals = false;     // qualities in page-locked memory too (they go to the GPU when it writes SAM: tg_align_files)
   struct Set {
     HostBuf bases, offs, names, name_offs, quals, qual_offs;
   } set[3];
@@ -399,8 +400,11 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
   uint64_t n = 0;
   size_t consumed = 0;
   size_t used = 0;
+  static const bool timing = getenv("TG_READER_TIMING") != nullptr;
+  double tq0 = now_ms(), tq1 = 0, tq2 = 0;
   for (;;) {
     if (!r->fill_text(target)) return tg_fail(TG_ERR_IO, "FASTQ input: " + r->err);
+    tq1 = now_ms();
     const char* text = r->tptr();
     const size_t len = std::min(r->text_len, target);  // (one batch's worth of the text that is there)
     const bool at_end = r->text_final && len == r->text_len;
@@ -442,12 +446,13 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
     r->text_len = 0;
     return TG_OK;
   }
+  tq2 = now_ms();
   uint64_t nb = 0, nn = 0, nq = 0;
   for (size_t t = 0; t < used; t++) { nb += seg[t].bases; nn += seg[t].names; nq += seg[t].quals; }
   tg_fastq_reader::Set& S = r->set[r->cur];
   r->cur = (r->cur + 1) % 3;
   if (!S.bases.ensure(nb + 64, true) || !S.offs.ensure((n + 1) * 8, true) || !S.names.ensure(nn + 1, true) ||
-      !S.name_offs.ensure((n + 1) * 8, true) || !S.quals.ensure(nq + 1, false) || !S.qual_offs.ensure((n + 1) * 8, false))
+      !S.name_offs.ensure((n + 1) * 8, true) || !S.quals.ensure(nq + 1, r->pin_quals) || !S.qual_offs.ensure((n + 1) * 8, r->pin_quals))
     return tg_fail(TG_ERR_INTERNAL, "out of memory");
   uint8_t* bases = (uint8_t*)S.bases.p; uint64_t* offs = (uint64_t*)S.offs.p;
   uint8_t* names = (uint8_t*)S.names.p; uint64_t* name_offs = (uint64_t*)S.name_offs.p;
@@ -466,11 +471,13 @@ tg_status tg_fastq_next(tg_fastq_reader* r, uint32_t max_reads, tg_read_batch* o
     if (seg[t].n == 0) return;
     seg[t].fill(text, bases, offs + r0[t], b0[t], names, name_offs + r0[t], n0[t], quals, qual_offs + r0[t], q0[t]);
   });
+  const double tq3 = now_ms();
   // what is left starts at a record start
   if (consumed < r->text_len) memmove(r->text.data(), r->text.data() + consumed, r->text_len - consumed);
   r->text_len -= consumed;
   r->bytes_per_read = 0.5 * r->bytes_per_read + 0.5 * ((double)consumed / (double)n);
   r->total_reads += n; r->total_text += consumed;
+  if (timing) fprintf(stderr, "[reader] %llu reads: fill %.1f ms, index %.1f ms, copy out %.1f ms, keep rest (%zu B) %.1f ms\n", (unsigned long long)n, tq1 - tq0, tq2 - tq1, tq3 - tq2, r->text_len, now_ms() - tq3);
   out->n_reads = (uint32_t)n;
   out->bases = bases; out->offs = offs; out->names = names; out->name_offs = name_offs; out->quals = quals; out->qual_offs = qual_offs;
   return TG_OK;
@@ -564,10 +571,11 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
     struct stat sb;
     seekable = out != stdout && file_pos >= 0 && fstat(out_fd, &sb) == 0 && S_ISREG(sb.st_mode);  // (stdout may be in append mode)
   }
-  // PAF on one GPU: lines are written on the device (tg_paf.cu), the writers only copy text into the file
+  // PAF / SAM on one GPU: lines are written on the device (tg_paf.cu), the writers only copy text into the file
   tg_paf* paf = nullptr;
-  if (output_fmt == 0 && ctx && !getenv("TG_PAF_HOST")) {
-    if ((st = tg_paf_create(ix, ctx, tg_ctx_device(ctx), &paf)) != TG_OK) { close_out(); return st; }
+  if (output_fmt <= 1 && ctx && !getenv("TG_PAF_HOST")) {
+    st = output_fmt == 0 ? tg_paf_create(ix, ctx, tg_ctx_device(ctx), &paf) : tg_sam_create(ix, ctx, tg_ctx_device(ctx), &paf);
+    if (st != TG_OK) { close_out(); return st; }
   }
   Channel to_align, to_write;
   Progress prog;
@@ -583,6 +591,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
     for (int f = 0; f < n_paths && st_read == TG_OK; f++) {
       tg_fastq_reader* r = nullptr;
       if ((st_read = tg_fastq_open(query_paths[f], &r)) != TG_OK) { err_read = tg_last_error(); break; }
+      r->pin_quals = paf && output_fmt == 1;
       for (;;) {
         if (b >= 2 && !prog.wait_written(b - 2)) break;
         Job j;
@@ -615,8 +624,12 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
       if (st_write != TG_OK) { prog.done_one(); continue; }  // keep draining so that nobody waits forever
       const double t0 = now_ms();
       const uint32_t n = j.batch.n_reads;
-      if (paf) {  // the text is there already: slices of it go into the file from all threads
-        const unsigned Tw = (!seekable || j.text_len < (8u << 20)) ? 1u : T;
+      if (paf) {  // the text arrives by itself: wait for the copy, then put it into the file
+        if (tg_paf_wait(paf, j.text) != TG_OK) { st_write = TG_ERR_CUDA; err_write = tg_last_error(); }
+        // (writes into one file take turns on its lock: one thread is as fast as sixteen and leaves the cores to the parser;
+        // TG_WRITE_THREADS sets another number)
+        static const unsigned write_threads = []() { const char* e = getenv("TG_WRITE_THREADS"); const long v = e ? atol(e) : 0; return v > 0 ? (unsigned)std::min<long>(v, 64) : 0u; }();
+        const unsigned Tw = (!seekable || j.text_len < (8u << 20)) ? 1u : write_threads ? std::min(write_threads, T) : 1u;
         if (!seekable) {
           if (j.text_len && fwrite(j.text, 1, j.text_len, out) != j.text_len) { st_write = TG_ERR_IO; err_write = "write error"; }
         } else {
@@ -701,7 +714,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
     if (paf) {
       tg_result counters;
       memset(&j.res, 0, sizeof(j.res));
-      st_align = tg_paf_align_batch(paf, &j.batch, &j.text, &j.text_len, &counters);
+      st_align = tg_paf_align_batch_async(paf, &j.batch, &j.text, &j.text_len, &counters);  // the writer waits for the text
       if (st_align == TG_OK) { j.res.n_reads = j.batch.n_reads; j.res.n_alns = counters.n_alns; j.res.n_ops = counters.n_ops; }
     } else if (ctx) st_align = tg_align_batch_compact(ctx, j.batch.bases, j.batch.offs, j.batch.n_reads, &j.res);
     else st_align = tg_multi_align_batch(multi, j.batch.bases, j.batch.offs, j.batch.n_reads, &j.res);

@@ -589,6 +589,41 @@ long long ht_swg_extend_batch(const uint8_t* xs, const uint64_t* xoff, const uin
 
 }  // extern "C"
 
+// ---- the device's SAM formatter (tg_textfmt.h) on the host: count -> exclusive scan -> write, like tg_paf.cu --------------
+#include "tg_textfmt.h"
+extern "C" int ht_format_sam(const tg_index_host* ix, const tg_result* res, const uint8_t* bases, const uint64_t* offs,
+                             const uint8_t* names, const uint64_t* name_offs, const uint8_t* quals, const uint64_t* qual_offs,
+                             char** out, size_t* out_len) {
+  TgTextTables tb;
+  tb.build(ix);
+  const uint32_t n = res->n_reads;
+  std::vector<unsigned long long> line_off(n + 1, 0);
+  TgTextParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_reads = n; p.bases = bases; p.offs = offs;
+  p.aln_first = res->read_aln_first; p.aln_count = res->read_aln_count; p.alns = res->alns; p.ops = res->ops;
+  p.names = names; p.name_offs = name_offs; p.quals = quals; p.qual_offs = qual_offs;
+  p.ref_names = tb.ref_names.data(); p.ref_name_offs = tb.ref_name_offs.data();
+  p.tx_ids = tb.tx_ids.data(); p.tx_id_offs = tb.tx_id_offs.data();
+  p.gene_ids = tb.gene_ids.data(); p.gene_id_offs = tb.gene_id_offs.data();
+  p.gene_names = tb.gene_names.data(); p.gene_name_offs = tb.gene_name_offs.data();
+  p.tx_gene = tb.tx_gene.data();
+  p.line_off = line_off.data();
+  p.mapq[0] = 255; p.mapq[1] = 255; p.mapq[5] = 0;
+  for (int k = 2; k <= 4; k++) p.mapq[k] = (uint32_t)std::lround(-10.0f * std::log10(1.0f - 1.0f / (float)k));
+  unsigned long long total = 0;
+  for (uint32_t r = 0; r < n; r++) { const unsigned long long b = tg_sam_read<false>(p, r); line_off[r] = total; total += b; }
+  line_off[n] = total;
+  char* text = (char*)malloc(total + 1);
+  if (!text) return -1;
+  memset(text, '#', total);
+  text[total] = 0;
+  p.text = text;
+  for (uint32_t r = 0; r < n; r++) tg_sam_read<true>(p, r);
+  *out = text; *out_len = (size_t)total;
+  return 0;
+}
+
 // ---- micro-batcher (host_batcher.cpp) over a stand-in batch aligner -----------------------------------------------------
 // The stand-in derives a read's records from its bytes alone (count = len % 4, scores / coordinates / operation words
 // from a hash), scatters them through the result pools in a scrambled order and serves `n_threads` callers that each

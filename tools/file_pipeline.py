@@ -32,7 +32,7 @@ print(f"{n} reads, FASTQ text {len(fq) / 1e6:.0f} MB (" + ", ".join(f"{k} {len(v
       f"batches of {batch}, {gpus} GPU(s), host threads {os.cpu_count()}, files in {tmp}", flush=True)
 devices = list(range(gpus)) if gpus > 1 else None
 for inp in kinds:
-    for fmt in (OutputFormat.Paf, OutputFormat.Sam, OutputFormat.Bam):
+    for fmt in os.environ.get("TG_FORMATS", "paf,sam,bam").split(","):
         if fmt == OutputFormat.Bam and inp != "plain":
             continue
         best = None
