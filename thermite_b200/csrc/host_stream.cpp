@@ -614,7 +614,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
   // stage 3: records -> text -> file.  Per-thread text buffers are kept across batches (fresh buffers cost a page fault
   // per 4 KiB of output) and written one after the other: no merged copy of the batch's text is ever made.
   std::thread writer([&]() {
-    lower_priority();
+    if (!paf) lower_priority();  // (with the text written on the GPU this thread only copies it into the file: the bound of SAM output)
     const unsigned T = host_threads();
     std::vector<TgOut> parts(T);
     std::string z;
