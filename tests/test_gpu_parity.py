@@ -457,3 +457,17 @@ def test_paf_and_sam_written_on_the_gpu_equal_the_host_writer(tmp_path, monkeypa
                 st = align_reads_from_file(ix, [str(qp)], str(op), OutputFormat.Sam if sam else OutputFormat.Paf, opts, batch_reads=777)
                 assert op.read_bytes() == want and st["n_reads"] == len(offs) - 1
         monkeypatch.delenv("TG_PAF_HOST", raising=False)
+
+
+def test_file_pipeline_names_a_read_that_is_too_long(tmp_path):
+    """Limits (include/thermite_gpu.h): reads of more than TG_MAX_READ_LEN bases are not aligned by the device path.  The file
+    pipeline says which read it was, the batches before it are in the output and every stage comes to rest."""
+    from thermite_b200 import OutputFormat, ThermiteError, align_reads_from_file
+    fa, gtf, fq = golden("test_ref.fasta"), golden("test_ref.gtf"), golden("test_query.fastq")
+    ix = Index.create_from_memory(fa, gtf)
+    opts = AlignOpts(min_seed_len=3, min_aln_score=0)
+    qp = tmp_path / "q.fastq"
+    qp.write_bytes(fq + b"@the_long_one extra\n" + b"ACGT" * 150 + b"\n+\n" + b"F" * 600 + b"\n" + fq)
+    for fmt in (OutputFormat.Paf, OutputFormat.Sam, OutputFormat.Bam):
+        with pytest.raises(ThermiteError, match="the_long_one extra.* has 600 bases"):
+            align_reads_from_file(ix, [str(qp)], str(tmp_path / "o.out"), fmt, opts, batch_reads=4)

@@ -101,28 +101,33 @@ struct SegIndex {
   std::vector<uint32_t> rec;  // index of the header line of every complete record
   uint64_t n = 0, bases = 0, names = 0, quals = 0;
   size_t consumed = 0;        // offset in the whole text just behind the last complete record (and blank lines before it)
-  bool bad = false;
+  bool bad = false, has_cr = false;
   void scan(const char* text, bool final) {
     nl.clear();
     const size_t len = end - begin;
     nl.reserve(len / 40 + 16);
     const char* p = text + begin;
     size_t i = 0;
+    has_cr = false;
 #if defined(__AVX2__)
-    const __m256i nlv = _mm256_set1_epi8('\n');
+    const __m256i nlv = _mm256_set1_epi8('\n'), crv = _mm256_set1_epi8('\r');
+    __m256i any_cr = _mm256_setzero_si256();
     for (; i + 32 <= len; i += 32) {
-      uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(p + i)), nlv));
+      const __m256i v = _mm256_loadu_si256((const __m256i*)(p + i));
+      uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, nlv));
+      any_cr = _mm256_or_si256(any_cr, _mm256_cmpeq_epi8(v, crv));
       while (m) { nl.push_back((uint32_t)(i + (size_t)__builtin_ctz(m))); m &= m - 1; }
     }
+    has_cr = _mm256_movemask_epi8(any_cr) != 0;
 #endif
-    for (; i < len; i++) if (p[i] == '\n') nl.push_back((uint32_t)i);
+    for (; i < len; i++) { if (p[i] == '\n') nl.push_back((uint32_t)i); else if (p[i] == '\r') has_cr = true; }
     if (final && len > 0 && p[len - 1] != '\n') nl.push_back((uint32_t)len);
   }
   // line k: [lb, le) relative to begin, '\r' stripped
   inline void line(const char* text, size_t k, uint32_t& lb, uint32_t& le) const {
     lb = k == 0 ? 0u : nl[k - 1] + 1u;
     le = nl[k];
-    if (le > lb && text[begin + le - 1] == '\r') le--;
+    if (has_cr && le > lb && text[begin + le - 1] == '\r') le--;  // (no '\r' anywhere in the segment: the text is not touched)
   }
   size_t after_line(size_t k) const { const size_t o = begin + (size_t)nl[k] + 1; return o < end ? o : end; }
   // records among the first max_records; sums and `consumed` for exactly those
@@ -585,13 +590,15 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
 
   // stage 1: files -> batches.  A reader owns three buffer sets; batch b may be overwritten by batch b + 3, which is
   // produced only after batch b has been written.
+  std::vector<tg_fastq_reader*> open_readers;
   std::thread producer([&]() {
     lower_priority();
     uint64_t b = 0;
     for (int f = 0; f < n_paths && st_read == TG_OK; f++) {
       tg_fastq_reader* r = nullptr;
       if ((st_read = tg_fastq_open(query_paths[f], &r)) != TG_OK) { err_read = tg_last_error(); break; }
-      r->pin_quals = paf && output_fmt == 1;
+      // (page-locked qualities for SAM on the GPU were tried: 7 ms less copy per 1 M reads in the aligner stage, which is not the
+      // bound, against three more page-locked allocations in the reader: 8 M reads went from 5.4 to 4.4 M reads/s overall)
       for (;;) {
         if (b >= 2 && !prog.wait_written(b - 2)) break;
         Job j;
@@ -599,12 +606,24 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
         if ((st_read = tg_fastq_next(r, batch_reads, &j.batch)) != TG_OK) { err_read = tg_last_error(); break; }
         read_ms += now_ms() - t0;
         if (j.batch.n_reads == 0) break;
+        // the device path takes reads of at most TG_MAX_READ_LEN bases (include/thermite_gpu.h, limits): name the read here
+        // instead of letting the aligner refuse the whole batch
+        for (uint32_t i = 0; i < j.batch.n_reads && st_read == TG_OK; i++) {
+          const uint64_t len = j.batch.offs[i + 1] - j.batch.offs[i];
+          if (len <= TG_MAX_READ_LEN) continue;
+          st_read = TG_ERR_INVALID;
+          err_read = "read '" + std::string((const char*)j.batch.names + j.batch.name_offs[i], (size_t)std::min<uint64_t>(j.batch.name_offs[i + 1] - j.batch.name_offs[i], 200)) +
+                     "' of " + query_paths[f] + " has " + std::to_string(len) + " bases; reads of at most " + std::to_string(TG_MAX_READ_LEN) +
+                     " are aligned (batches before it are already in the output)";
+        }
+        if (st_read != TG_OK) break;
         j.index = b++;
         to_align.push(j);
       }
-      // the reader's buffers must outlive its batches
-      if (st_read == TG_OK) prog.wait_written(b);
-      tg_fastq_close(r);
+      // the reader's buffers must outlive its batches: close it once they are written; after a failure in any stage the
+      // batches on their way may still be read, so the reader is closed when the pipeline has come to rest
+      if (st_read == TG_OK && prog.wait_written(b)) tg_fastq_close(r);
+      else { open_readers.push_back(r); break; }
     }
     if (st_read != TG_OK) prog.fail();
     Job e; e.end = true;
@@ -725,6 +744,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
   { Job e; e.end = true; to_write.push(e); }
   producer.join();
   writer.join();
+  for (tg_fastq_reader* r : open_readers) tg_fastq_close(r);
   if (output_fmt == 2 && st_align == TG_OK && st_read == TG_OK && st_write == TG_OK) {
     static const unsigned char eof_block[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     fwrite(eof_block, 1, sizeof(eof_block), out);

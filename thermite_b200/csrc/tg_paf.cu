@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "tg_internal.h"
@@ -160,6 +161,9 @@ struct tg_paf {
   cudaEvent_t written = nullptr, text_ready[2] = {nullptr, nullptr};
   bool in_flight[2] = {false, false};
   bool timing = false;
+  // first batch: the page-locked text buffers (155 ms per 400 MB) are allocated by a helper while the batch is aligned
+  std::thread prealloc;
+  bool prealloc_started = false;
   bool sam = false;  // SAM records instead of PAF lines: qualities and the annotation's names are needed as well
   DBuf d_quals, d_qual_offs, d_tx_ids, d_tx_id_offs, d_gene_ids, d_gene_id_offs, d_gene_names, d_gene_name_offs, d_tx_gene;
   HBuf h_text[2];
@@ -234,6 +238,7 @@ void tg_paf_destroy(tg_paf* f) {
   if (!f) return;
   cudaSetDevice(f->device);
   cudaStreamSynchronize(f->stream);
+  if (f->prealloc.joinable()) f->prealloc.join();
   if (f->copy_stream) { cudaStreamSynchronize(f->copy_stream); cudaStreamDestroy(f->copy_stream); }
   if (f->written) cudaEventDestroy(f->written);
   for (int i = 0; i < 2; i++) if (f->text_ready[i]) cudaEventDestroy(f->text_ready[i]);
@@ -293,6 +298,16 @@ tg_status tg_paf_align_batch_async(tg_paf* f, const tg_read_batch* b, const char
     PAF_CHECK(cudaMemcpyAsync(f->d_qual_offs.p, b->qual_offs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, f->stream));
     if (nq) PAF_CHECK(cudaMemcpyAsync(f->d_quals.p, b->quals, nq, cudaMemcpyHostToDevice, f->stream));
   }
+  if (!f->prealloc_started) {
+    f->prealloc_started = true;
+    const size_t est = f->sam ? (size_t)(nb + nq + nn) + (size_t)n * 170 : (size_t)nn + (size_t)n * 64;
+    f->prealloc = std::thread([f, est]() {
+      if (cudaSetDevice(f->device) != cudaSuccess) return;
+      f->h_text[0].ensure(est);
+      f->h_text[1].ensure(est);
+    });
+  }
+  struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } join_guard{f->prealloc};
   tg_result res;
   if ((st = tg_align_batch_device(f->ctx, (const uint8_t*)f->d_bases.p, (const uint64_t*)f->d_offs.p, n, nb, maxL, &res)) != TG_OK) return st;
   if (counters) *counters = res;
@@ -329,6 +344,7 @@ tg_status tg_paf_align_batch_async(tg_paf* f, const tg_read_batch* b, const char
   PAF_CHECK(cudaStreamSynchronize(f->stream));
   const double t1 = f->timing ? tg_now_ms() : 0;
   const size_t total = (size_t)*f->h_total;
+  if (f->prealloc.joinable()) f->prealloc.join();
   const int cur = f->cur;
   f->cur ^= 1;
   HBuf& H = f->h_text[cur];
