@@ -310,3 +310,68 @@ def test_bam_output_decodes_to_the_sam_text():
         assert [b"@SQ\tSN:%s\tLN:%d" % r for r in refs] == [l for l in text.split(b"\n") if l.startswith(b"@SQ")]
         assert lines == sam and lines.count(b"\n") >= n
         assert n_blocks >= 3
+
+
+def test_device_sam_routine_equals_host_writer_on_synthetic_records():
+    """csrc/tg_textfmt.h (what tg_paf.cu's SAM kernels run) against the host writer (tg_format_batch) on records no aligner
+    would produce together: empty reads and empty quality strings, lower-case and N bases on the reverse strand, negative and
+    zero scores, secondary records, every alignment type, operation lists with adjacent clips of equal and unequal length,
+    runs of Match / Subst to be merged, zero-length lists, up to 7 records per read, names with and without a space."""
+    import ht
+    from common import small_world
+    from oracle.orc import ALN_DTYPE
+    contigs, gtf, txs, fa = small_world(5)
+    ix = tb.Index.create_from_memory(fa, gtf)
+    L = tb.lib()
+    n_refs, n_txs, n_genes = L.tg_index_host_n_refs(ix._h), L.tg_index_host_n_txs(ix._h), L.tg_index_host_n_genes(ix._h)
+    assert n_refs >= 2 and n_txs >= 1 and n_genes >= 1
+    rng = np.random.default_rng(77)
+    n = 3000
+    lens = rng.integers(0, 120, n)
+    lens[rng.random(n) < 0.05] = 0
+    qlens = np.where(rng.random(n) < 0.1, 0, lens)
+    bases = rng.choice(np.frombuffer(b"ACGTNacgtn", np.uint8), int(lens.sum()))
+    quals = rng.integers(33, 74, int(qlens.sum())).astype(np.uint8)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    qual_offs = np.concatenate([[0], np.cumsum(qlens)]).astype(np.uint64)
+    name_list = [(b"r%d" % i) + (b" tail %d x" % i if i % 3 else b"") for i in range(n)]
+    names = np.frombuffer(b"".join(name_list), np.uint8).copy()
+    name_offs = np.concatenate([[0], np.cumsum([len(x) for x in name_list])]).astype(np.uint64)
+    count = rng.integers(0, 8, n).astype(np.uint32)
+    count[rng.random(n) < 0.2] = 0
+    first = np.concatenate([[0], np.cumsum(count)]).astype(np.uint64)
+    na = int(count.sum())
+    alns = np.zeros(na, ALN_DTYPE)
+    ops = []
+
+    def op_list():
+        k = int(rng.integers(0, 9))
+        w = []
+        for _ in range(k):
+            kind = int(rng.integers(0, 6))
+            run = int(rng.integers(1, 400))
+            w.append(run << 3 | kind)
+            if kind >= 4 and rng.random() < 0.5:      # the same clip again (collapses) or another length (does not)
+                w.append((run if rng.random() < 0.6 else run + 1) << 3 | kind)
+        return w
+
+    for a in range(na):
+        rec = alns[a]
+        rec["ystart"] = rng.integers(0, 1 << 31); rec["tx_ystart"] = rng.integers(0, 100000)
+        rec["score"] = rng.integers(-50, 200); rec["ref_id"] = rng.integers(0, n_refs)
+        rec["aln_type"] = rng.integers(0, 3)
+        rec["tx_or_gene_idx"] = rng.integers(0, n_txs) if rec["aln_type"] == 0 else rng.integers(0, n_genes) if rec["aln_type"] == 1 else 0xFFFFFFFF
+        rec["primary"] = rng.integers(0, 2); rec["strand"] = rng.integers(0, 2)
+        w = op_list(); rec["ops_off"] = len(ops); rec["ops_len"] = len(w); ops += w
+        w = op_list(); rec["tx_ops_off"] = len(ops); rec["tx_ops_len"] = len(w); ops += w
+    ops = np.array(ops + [0], np.uint32)
+    firsts = np.ascontiguousarray(first[:-1])
+    res = api._Result(n, na, len(ops), firsts.ctypes.data, count.ctypes.data, alns.ctypes.data, ops.ctypes.data, 0, 0, 0, 0)
+    out, ln = C.c_void_p(), C.c_size_t()
+    assert L.tg_format_batch(ix._h, C.byref(res), api._p(bases), api._p(offs), api._p(names), api._p(name_offs),
+                             api._p(quals), api._p(qual_offs), 1, C.byref(out), C.byref(ln)) == 0
+    host = C.string_at(out, ln.value)
+    L.tg_free(out)
+    dev = ht.format_sam(ht.HostIndex(fa, gtf), res, bases, offs, names, name_offs, quals, qual_offs)
+    assert host.count(b"\n") == na + int((count == 0).sum())
+    assert dev == host
