@@ -425,8 +425,9 @@ int tg_ctx_device(const tg_ctx* ctx);
  * ("-" = stdout), records in input order.  Exactly one of ctx / multi is given (one GPU, or the reads of every batch
  * sharded over the GPUs of a tg_multi).  Three overlapped stages: reader (inflate + parse batch k + 1), aligner (batch k
  * on the GPU), writers (format batch k - 1 on all host cores and write it); no stage holds more than three batches of
- * batch_reads reads (0 = 1 Mi).  The call switches ctx / multi to two alternating result sets.  PAF on one GPU is written on
- * the device (tg_paf_* / tg_sam_create; TG_PAF_HOST=1 in the environment keeps the host writers). */
+ * batch_reads reads (0 = 1 Mi).  The call switches ctx / multi to two alternating result sets.  PAF and SAM on one GPU are written
+ * on the device (tg_paf_* / tg_sam_create; TG_PAF_HOST=1 in the environment keeps the host writers); a read of more than
+ * TG_MAX_READ_LEN bases ends the run with TG_ERR_INVALID naming it (the batches before it are in the output). */
 typedef struct tg_file_stats {
   uint64_t n_reads, n_alns, n_batches, bytes_out;
   double read_ms, align_ms, write_ms;  /* busy time of each stage */
