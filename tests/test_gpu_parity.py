@@ -471,3 +471,26 @@ def test_file_pipeline_names_a_read_that_is_too_long(tmp_path):
     for fmt in (OutputFormat.Paf, OutputFormat.Sam, OutputFormat.Bam):
         with pytest.raises(ThermiteError, match="the_long_one extra.* has 600 bases"):
             align_reads_from_file(ix, [str(qp)], str(tmp_path / "o.out"), fmt, opts, batch_reads=4)
+
+
+def test_file_pipeline_bam_from_all_cores(tmp_path):
+    """BAM through tg_align_files with a batch large enough for the threaded writers (>= 32768 reads): every thread formats its
+    reads, encodes them as BAM records and compresses its own BGZF blocks; the file decodes to exactly the SAM file."""
+    from thermite_b200 import OutputFormat, align_reads_from_file
+    contigs, gtf, txs, fa = small_world(12)
+    n = 40000
+    bases, offs = synth.make_reads(6, contigs, txs, n, L=91, sub=0.02, ins=0.003, dele=0.003)
+    rows = bases.reshape(n, 91)
+    fq = b"".join(b"@q%d some words\n%s\n+\n%s\n" % (i, rows[i].tobytes(), bytes(33 + (i + k) % 41 for k in range(91))) for i in range(n))
+    qp = tmp_path / "q.fastq"
+    qp.write_bytes(fq)
+    ix = Index.create_from_memory(fa, gtf)
+    opts = AlignOpts(20, 0.0, 30, 2, True)
+    outs = {}
+    for fmt in (OutputFormat.Sam, OutputFormat.Bam):
+        op = tmp_path / ("out." + fmt)
+        st = align_reads_from_file(ix, [str(qp)], str(op), fmt, opts, batch_reads=n)
+        assert st["n_reads"] == n and st["n_batches"] == 1
+        outs[fmt] = op.read_bytes()
+    text, refs, lines, n_blocks = bam_to_sam(outs[OutputFormat.Bam])
+    assert text + lines == outs[OutputFormat.Sam] and n_blocks > 16

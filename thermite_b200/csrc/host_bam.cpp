@@ -116,24 +116,43 @@ std::vector<std::string> header_refs(const tg_index_host* ix, std::vector<uint32
   return seen;
 }
 
-// one SAM line (without the newline) -> one BAM record appended to `out`
-bool sam_line_to_bam(const char* line, size_t len, const std::vector<std::string>& refs, std::string& out, std::string& err) {
-  std::vector<Field> f;
-  size_t b = 0;
-  for (size_t i = 0; i <= len; i++)
-    if (i == len || line[i] == '\t') { f.push_back(Field{line + b, i - b}); b = i + 1; }
-  if (f.size() < 11) { err = "SAM line with fewer than 11 fields"; return false; }
+// one SAM line (without the newline) -> one BAM record appended to `out`.  No allocation per line: the fields sit in a fixed
+// array, the CIGAR words in a vector the caller keeps, the record is built in place and its length patched in at the end.
+struct LineScratch {
+  std::vector<uint32_t> cig;
+  size_t last_ref = 0;
+};
+inline void set32(std::string& s, size_t at, uint32_t v) {
+  s[at] = (char)(v & 255); s[at + 1] = (char)((v >> 8) & 255); s[at + 2] = (char)((v >> 16) & 255); s[at + 3] = (char)((v >> 24) & 255);
+}
+bool sam_line_to_bam(const char* line, size_t len, const std::vector<std::string>& refs, LineScratch& sc, std::string& out, std::string& err) {
+  enum { MAXF = 64 };
+  Field f[MAXF];
+  size_t nf = 0, b = 0;
+  while (nf < MAXF) {
+    const char* tab = b < len ? (const char*)memchr(line + b, '\t', len - b) : nullptr;
+    const size_t e = tab ? (size_t)(tab - line) : len;
+    f[nf++] = Field{line + b, e - b};
+    if (!tab) break;
+    b = e + 1;
+  }
+  if (nf == MAXF && memchr(f[MAXF - 1].p, '\t', (size_t)(line + len - f[MAXF - 1].p))) { err = "SAM line with too many fields"; return false; }
+  if (nf < 11) { err = "SAM line with fewer than 11 fields"; return false; }
   auto num = [](const Field& x) { long long v = 0; bool neg = false; size_t i = 0; if (x.n && x.p[0] == '-') { neg = true; i = 1; }
                                   for (; i < x.n; i++) v = v * 10 + (x.p[i] - '0'); return neg ? -v : v; };
   int32_t ref_id = -1;
   if (!(f[2].n == 1 && f[2].p[0] == '*')) {
-    for (size_t i = 0; i < refs.size(); i++)
-      if (refs[i].size() == f[2].n && memcmp(refs[i].data(), f[2].p, f[2].n) == 0) { ref_id = (int32_t)i; break; }
+    auto same = [&](size_t i) { return refs[i].size() == f[2].n && memcmp(refs[i].data(), f[2].p, f[2].n) == 0; };
+    if (sc.last_ref < refs.size() && same(sc.last_ref)) ref_id = (int32_t)sc.last_ref;  // (neighbouring lines mostly share it)
+    else
+      for (size_t i = 0; i < refs.size(); i++)
+        if (same(i)) { ref_id = (int32_t)i; sc.last_ref = i; break; }
     if (ref_id < 0) { err = "reference name not in the header"; return false; }
   }
   const int64_t pos = num(f[3]) - 1;
   // CIGAR
-  std::vector<uint32_t> cig;
+  std::vector<uint32_t>& cig = sc.cig;
+  cig.clear();
   int64_t ref_len = 0;
   if (!(f[5].n == 1 && f[5].p[0] == '*')) {
     uint64_t v = 0;
@@ -141,7 +160,7 @@ bool sam_line_to_bam(const char* line, size_t len, const std::vector<std::string
       const char c = f[5].p[i];
       if (c >= '0' && c <= '9') { v = v * 10 + (uint64_t)(c - '0'); continue; }
       const char* ops = "MIDNSHP=X";
-      const char* at = strchr(ops, c);
+      const char* at = c ? strchr(ops, c) : nullptr;
       if (!at || v >= (1ull << 28)) { err = "bad CIGAR"; return false; }
       const uint32_t op = (uint32_t)(at - ops);
       cig.push_back((uint32_t)(v << 4) | op);
@@ -153,59 +172,72 @@ bool sam_line_to_bam(const char* line, size_t len, const std::vector<std::string
   const uint32_t l_seq = has_seq ? (uint32_t)f[9].n : 0u;
   const int64_t end = pos + (ref_len > 0 ? ref_len : 1);
   const uint32_t bin = reg2bin(pos, end);  // unmapped (pos -1): reg2bin(-1, 0) = 4680, as the spec asks
-  std::string r;
-  put32(r, (uint32_t)ref_id);
-  put32(r, (uint32_t)(int32_t)pos);
-  r.push_back((char)(f[0].n + 1));
-  r.push_back((char)num(f[4]));
-  put16(r, bin);
-  put16(r, (uint32_t)cig.size());
-  put16(r, (uint32_t)num(f[1]));
-  put32(r, l_seq);
-  put32(r, 0xFFFFFFFFu);  // RNEXT '*'
-  put32(r, 0xFFFFFFFFu);  // PNEXT 0
-  put32(r, 0);            // TLEN
   if (f[0].n > 254) { err = "read name longer than 254 bytes"; return false; }
-  r.append(f[0].p, f[0].n);
-  r.push_back('\0');
-  for (uint32_t c : cig) put32(r, c);
-  static const char* codes = "=ACMGRSVTWYHKDBN";
-  for (uint32_t i = 0; i < l_seq; i += 2) {
-    auto code = [&](char ch) { if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32); const char* at = strchr(codes, ch); return (unsigned)(at && ch ? at - codes : 15); };
-    const unsigned hi = code(f[9].p[i]), lo = i + 1 < l_seq ? code(f[9].p[i + 1]) : 0u;
-    r.push_back((char)(hi << 4 | lo));
+  const bool has_qual = !(f[10].n == 1 && f[10].p[0] == '*');
+  if (has_qual && f[10].n != l_seq) { err = "SEQ and QUAL differ in length"; return false; }
+  const size_t at0 = out.size();
+  // fixed part, name, CIGAR, packed bases, qualities: sizes are known, written through a pointer
+  const size_t fixed = 4 + 32 + f[0].n + 1 + 4 * cig.size() + (l_seq + 1) / 2 + l_seq;
+  out.resize(at0 + fixed);
+  {
+    unsigned char* d = (unsigned char*)&out[at0 + 4];
+    auto w16 = [&](uint32_t v) { d[0] = (unsigned char)(v & 255); d[1] = (unsigned char)((v >> 8) & 255); d += 2; };
+    auto w32 = [&](uint32_t v) { d[0] = (unsigned char)(v & 255); d[1] = (unsigned char)((v >> 8) & 255); d[2] = (unsigned char)((v >> 16) & 255); d[3] = (unsigned char)((v >> 24) & 255); d += 4; };
+    w32((uint32_t)ref_id);
+    w32((uint32_t)(int32_t)pos);
+    *d++ = (unsigned char)(f[0].n + 1);
+    *d++ = (unsigned char)num(f[4]);
+    w16(bin);
+    w16((uint32_t)cig.size());
+    w16((uint32_t)num(f[1]));
+    w32(l_seq);
+    w32(0xFFFFFFFFu);  // RNEXT '*'
+    w32(0xFFFFFFFFu);  // PNEXT 0
+    w32(0);            // TLEN
+    memcpy(d, f[0].p, f[0].n); d += f[0].n;
+    *d++ = 0;
+    for (uint32_t c : cig) w32(c);
+    // "=ACMGRSVTWYHKDBN", case-insensitive; anything else is N (15)
+    static const struct Codes {
+      unsigned char t[256];
+      Codes() {
+        memset(t, 15, sizeof(t));
+        const char* codes = "=ACMGRSVTWYHKDBN";
+        for (int i = 0; i < 16; i++) { t[(unsigned char)codes[i]] = (unsigned char)i; if (codes[i] >= 'A' && codes[i] <= 'Z') t[(unsigned char)(codes[i] + 32)] = (unsigned char)i; }
+      }
+    } C;
+    const unsigned char* sq = (const unsigned char*)f[9].p;
+    uint32_t i = 0;
+    for (; i + 1 < l_seq; i += 2) *d++ = (unsigned char)(C.t[sq[i]] << 4 | C.t[sq[i + 1]]);
+    if (i < l_seq) *d++ = (unsigned char)(C.t[sq[i]] << 4);
+    if (!has_qual) memset(d, 0xFF, l_seq);
+    else for (uint32_t k = 0; k < l_seq; k++) d[k] = (unsigned char)(f[10].p[k] - 33);
   }
-  if (f[10].n == 1 && f[10].p[0] == '*') r.append(l_seq, (char)0xFF);
-  else {
-    if (f[10].n != l_seq) { err = "SEQ and QUAL differ in length"; return false; }
-    for (uint32_t i = 0; i < l_seq; i++) r.push_back((char)(f[10].p[i] - 33));
-  }
-  for (size_t k = 11; k < f.size(); k++) {  // TAG:TYPE:VALUE
+  for (size_t k = 11; k < nf; k++) {  // TAG:TYPE:VALUE
     const Field& t = f[k];
     if (t.n < 5 || t.p[2] != ':' || t.p[4] != ':') { err = "bad optional field"; return false; }
-    r.append(t.p, 2);
+    out.append(t.p, 2);
     const Field val{t.p + 5, t.n - 5};
     switch (t.p[3]) {
-      case 'A': r.push_back('A'); r.push_back(val.n ? val.p[0] : ' '); break;
-      case 'Z': r.push_back('Z'); r.append(val.p, val.n); r.push_back('\0'); break;
+      case 'A': out.push_back('A'); out.push_back(val.n ? val.p[0] : ' '); break;
+      case 'Z': out.push_back('Z'); out.append(val.p, val.n); out.push_back('\0'); break;
       case 'i': {
         const long long v = num(val);
         if (v >= 0) {
-          if (v <= 255) { r.push_back('C'); r.push_back((char)v); }
-          else if (v <= 65535) { r.push_back('S'); put16(r, (uint32_t)v); }
-          else { r.push_back('I'); put32(r, (uint32_t)v); }
+          if (v <= 255) { out.push_back('C'); out.push_back((char)v); }
+          else if (v <= 65535) { out.push_back('S'); put16(out, (uint32_t)v); }
+          else { out.push_back('I'); put32(out, (uint32_t)v); }
         } else {
-          if (v >= -128) { r.push_back('c'); r.push_back((char)v); }
-          else if (v >= -32768) { r.push_back('s'); put16(r, (uint32_t)(int32_t)v); }
-          else { r.push_back('i'); put32(r, (uint32_t)(int32_t)v); }
+          if (v >= -128) { out.push_back('c'); out.push_back((char)v); }
+          else if (v >= -32768) { out.push_back('s'); put16(out, (uint32_t)(int32_t)v); }
+          else { out.push_back('i'); put32(out, (uint32_t)(int32_t)v); }
         }
         break;
       }
       default: err = "optional field type not produced by thermite"; return false;
     }
   }
-  put32(out, (uint32_t)r.size());
-  out += r;
+  set32(out, at0, (uint32_t)(out.size() - at0 - 4));
   return true;
 }
 
@@ -251,30 +283,40 @@ tg_status tg_format_bam_header(const tg_index_host* ix, void** out, size_t* out_
 
 }  // extern "C" (closed for an internal C++ function)
 
-// SAM lines (without header) -> BAM records in BGZF blocks (optionally followed by the end-of-file block)
-tg_status tg_sam_text_to_bam(const tg_index_host* ix, const char* sam, size_t sl, bool append_eof, std::string& z) {
+// SAM lines (without header) -> BAM records in BGZF blocks (optionally followed by the end-of-file block).  The text is cut at
+// line ends into one piece per thread; a thread encodes its piece and compresses it into blocks of its own (BGZF blocks are
+// independent, a short last block per piece is legal), so the only serial step is joining the compressed pieces.
+// max_threads = 1: the caller already runs one call per core (tg_align_files).
+tg_status tg_sam_text_to_bam(const tg_index_host* ix, const char* sam, size_t sl, bool append_eof, std::string& z, unsigned max_threads) {
     const std::vector<std::string> refs = header_refs(ix, nullptr);
-    // line ranges on the host's cores; pieces concatenated in order
     uint32_t T = (uint32_t)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 64);
+    if (max_threads) T = std::min<uint32_t>(T, max_threads);
     if (sl < (1u << 22)) T = 1;
     std::vector<size_t> cut(T + 1, sl);
     cut[0] = 0;
     for (uint32_t t = 1; t < T; t++) {
-      size_t p = sl * t / T;
+      size_t p = std::max(cut[t - 1], sl * t / T);
       while (p < sl && sam[p] != '\n') p++;
       cut[t] = p < sl ? p + 1 : sl;
     }
-    std::vector<std::string> parts(T), errs(T);
+    std::vector<std::string> zparts(T), errs(T);
     auto work = [&](uint32_t t) {
       size_t p = cut[t];
       const size_t e = cut[t + 1];
-      parts[t].reserve((e - p) * 3 / 4 + 64);
+      std::string raw;
+      raw.reserve((e - p) * 3 / 4 + 64);
+      LineScratch sc;
       while (p < e) {
         const char* nl = (const char*)memchr(sam + p, '\n', e - p);
         const size_t n = nl ? (size_t)(nl - (sam + p)) : e - p;
-        if (n && !sam_line_to_bam(sam + p, n, refs, parts[t], errs[t])) return;
+        if (n && !sam_line_to_bam(sam + p, n, refs, sc, raw, errs[t])) return;
         p += n + 1;
       }
+      std::string& out = T == 1 ? z : zparts[t];
+      const size_t BLK = 0xff00;
+      out.reserve(out.size() + raw.size() / 2 + 64);
+      for (size_t at = 0; at < raw.size(); at += BLK)
+        if (!bgzf_block(raw.data() + at, std::min(BLK, raw.size() - at), out)) { errs[t] = "deflate failed"; return; }
     };
     if (T == 1) work(0);
     else {
@@ -282,12 +324,14 @@ tg_status tg_sam_text_to_bam(const tg_index_host* ix, const char* sam, size_t sl
       for (uint32_t t = 0; t < T; t++) th.emplace_back(work, t);
       for (auto& x : th) x.join();
     }
-    std::string raw;
-    for (uint32_t t = 0; t < T; t++) {
+    for (uint32_t t = 0; t < T; t++)
       if (!errs[t].empty()) return tg_fail(TG_ERR_INTERNAL, "BAM encoding: " + errs[t]);
-      raw += parts[t];
+    if (T > 1) {
+      size_t tot = z.size();
+      for (uint32_t t = 0; t < T; t++) tot += zparts[t].size();
+      z.reserve(tot + 28);
+      for (uint32_t t = 0; t < T; t++) z += zparts[t];
     }
-    if (!bgzf_compress(raw, z)) return tg_fail(TG_ERR_INTERNAL, "deflate failed");
     if (append_eof) z.append((const char*)BGZF_EOF, 28);
     return TG_OK;
 }
@@ -304,7 +348,7 @@ tg_status tg_format_batch_bam(const tg_index_host* ix, const tg_result* res, con
     tg_status st = tg_format_batch(ix, res, bases, offs, names, name_offs, quals, qual_offs, 1, &sam, &sl);
     if (st != TG_OK) return st;
     std::string z;
-    st = tg_sam_text_to_bam(ix, sam, sl, append_eof != 0, z);
+    st = tg_sam_text_to_bam(ix, sam, sl, append_eof != 0, z, 0);
     free(sam);
     if (st != TG_OK) return st;
     return hand_over(z, out, out_len);

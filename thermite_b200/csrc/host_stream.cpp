@@ -636,7 +636,7 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
     if (!paf) lower_priority();  // (with the text written on the GPU this thread only copies it into the file: the bound of SAM output)
     const unsigned T = host_threads();
     std::vector<TgOut> parts(T);
-    std::string z;
+    std::vector<std::string> zparts;
     for (;;) {
       Job j = to_write.pop();
       if (j.end) break;
@@ -649,7 +649,9 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
         // TG_WRITE_THREADS sets another number)
         static const unsigned write_threads = []() { const char* e = getenv("TG_WRITE_THREADS"); const long v = e ? atol(e) : 0; return v > 0 ? (unsigned)std::min<long>(v, 64) : 0u; }();
         const unsigned Tw = (!seekable || j.text_len < (8u << 20)) ? 1u : write_threads ? std::min(write_threads, T) : 1u;
-        if (!seekable) {
+        if (st_write != TG_OK) {
+          // (the copy failed: nothing of this batch is written)
+        } else if (!seekable) {
           if (j.text_len && fwrite(j.text, 1, j.text_len, out) != j.text_len) { st_write = TG_ERR_IO; err_write = "write error"; }
         } else {
           std::vector<int> bad(Tw, 0);
@@ -701,14 +703,20 @@ extern "C" tg_status tg_align_files(const tg_index_host* ix, tg_ctx* ctx, tg_mul
         S.bytes_out += (uint64_t)(at[Tn] - file_pos);
         file_pos = at[Tn];
       } else {
+        if (output_fmt == 2) {  // every thread turns its own text into BAM records and BGZF blocks; the pieces go out in order
+          if (zparts.size() < Tn) zparts.resize(Tn);
+          std::vector<tg_status> zst(Tn, TG_OK);
+          std::vector<std::string> zerr(Tn);
+          run_threads(Tn, [&](unsigned t) {
+            zparts[t].clear();
+            zst[t] = tg_sam_text_to_bam(ix, parts[t].s.data(), parts[t].s.size(), false, zparts[t], 1);
+            if (zst[t] != TG_OK) zerr[t] = tg_last_error();
+          });
+          for (unsigned t = 0; t < Tn && st_write == TG_OK; t++) if (zst[t] != TG_OK) { st_write = zst[t]; err_write = zerr[t]; }
+        }
         for (unsigned t = 0; t < Tn && st_write == TG_OK; t++) {
-          const char* p = parts[t].s.data();
-          size_t len = parts[t].s.size();
-          if (output_fmt == 2) {
-            z.clear();
-            if ((st_write = tg_sam_text_to_bam(ix, p, len, false, z)) != TG_OK) { err_write = tg_last_error(); break; }
-            p = z.data(); len = z.size();
-          }
+          const char* p = output_fmt == 2 ? zparts[t].data() : parts[t].s.data();
+          const size_t len = output_fmt == 2 ? zparts[t].size() : parts[t].s.size();
           if (len && fwrite(p, 1, len, out) != len) { st_write = TG_ERR_IO; err_write = "write error"; }
           S.bytes_out += len;
         }

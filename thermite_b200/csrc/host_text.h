@@ -81,4 +81,4 @@ size_t tg_fastq_record_start(const char* text, size_t len, size_t p);
 // offset just behind the k-th complete record of [begin, end) (end when there are fewer)
 size_t tg_fastq_skip(const char* text, size_t begin, size_t end, uint64_t k);
 // SAM lines -> BGZF-compressed BAM records (host_bam.cpp)
-tg_status tg_sam_text_to_bam(const tg_index_host* ix, const char* sam, size_t sl, bool append_eof, std::string& z);
+tg_status tg_sam_text_to_bam(const tg_index_host* ix, const char* sam, size_t sl, bool append_eof, std::string& z, unsigned max_threads = 0);
